@@ -1,0 +1,184 @@
+"""Second, independent restatement of the reference hot path (numpy + math).
+
+TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (the reference has no golden vectors and cannot
+be built here): two independent restatements agreeing bit for bit -- this
+file and oracle/scorus_oracle.c -- is the substitute.  Written from the Rust source, not
+from the C file.  Vectorised over walkers, strictly sequential over coordinates so that
+every per-walker sum has the reference's left-to-right order; exp / log / cos go through
+`math` (glibc libm, what Rust's f64::exp/ln/cos call on Linux), never numpy's SIMD routines.
+
+Reference: src/mcmc/ensemble_sample.rs:57-75,107-190; src/mcmc/utils.rs:47-70,72-112;
+log-densities from examples/*.rs.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+INF = float("inf")
+
+
+def _vmath(fn, arr):
+    return np.array([fn(float(v)) for v in np.asarray(arr).ravel()], dtype=np.float64).reshape(np.shape(arr))
+
+
+def logprob(kind: int, params, x: np.ndarray) -> np.ndarray:
+    """x is [n, d]; returns [n]."""
+    x = np.asarray(x, dtype=np.float64)
+    n, d = x.shape
+    p = np.asarray(params if params is not None else [], dtype=np.float64).ravel()
+    if kind == 0:  # examples/test_emcee.rs:18-24 (c=.5), examples/sample_high_dim.rs:22-28 (c=1)
+        c = p[0] if p.size else 0.5
+        res = np.zeros(n)
+        for k in range(d):
+            res = res - (x[:, k] * x[:, k]) * c
+        return res
+    if kind == 1:  # examples/sample_bimodal.rs:35-44
+        limit = p[0] if p.size else 1.5
+        res = np.zeros(n)
+        dead = np.zeros(n, dtype=bool)
+        for k in range(d):
+            res = res - x[:, k] * x[:, k]
+            dead |= np.abs(x[:, k]) > limit
+        res[dead] = -INF
+        return res
+    if kind == 2:  # examples/test_emcee.rs:26-32
+        res = np.zeros(n)
+        for k in range(d - 1):
+            t = x[:, k + 1] - x[:, k] * x[:, k]
+            s = 1.0 - x[:, k]
+            res = res + (100.0 * (t * t) + s * s)
+        return -res
+    if kind == 3:  # examples/sample_rastrigin.rs:17-25
+        a = p[0] if p.size else 10.0
+        two_pi = 2.0 * math.pi
+        res = np.full(n, -(float(d) * a))
+        for k in range(d):
+            c = _vmath(math.cos, two_pi * x[:, k])
+            res = res + (a * c - x[:, k] * x[:, k])
+        return res
+    if kind == 4:  # examples/sample_bimodal.rs:46-54
+        lo0, hi0, lo1, hi1, split, mu_a, sg_a, mu_b, sg_b = (p if p.size >= 9 else
+                                                             [-15.0, 15.0, 0.0, 1.0, 0.5, -5.0, 0.1, 5.0, 1.0])
+        out = np.empty(n)
+        for i in range(n):
+            x0, x1 = float(x[i, 0]), float(x[i, 1])
+            if x0 < lo0 or x0 > hi0 or x1 < lo1 or x1 > hi1:
+                out[i] = -INF
+                continue
+            mu, sg = (mu_a, sg_a) if x1 < split else (mu_b, sg_b)
+            out[i] = -(x0 - mu) * (x0 - mu) / (2.0 * sg * sg) - math.log(sg)
+        return out
+    if kind == 5:  # examples/sample_bimodal.rs:56-65
+        out = np.empty(n)
+        for i in range(n):
+            x0, x1 = float(x[i, 0]), float(x[i, 1])
+            if x0 < 0.0 or x0 > 1.0 or x1 < 0.0 or x1 > 1.0:
+                out[i] = -INF
+            else:
+                out[i] = math.log(0.1) if x0 > 0.5 else math.log(0.9)
+        return out
+    if kind == 6:  # builder-defined correlated Gaussian: -0.5 |L (x - mu)|^2
+        mu, L = p[:d], p[d:d + d * d].reshape(d, d)
+        s = np.zeros(n)
+        for i in range(d):
+            w = np.zeros(n)
+            for j in range(d):
+                w = w + L[i, j] * (x[:, j] - mu[j])
+            s = s + w * w
+        return -0.5 * s
+    if kind == 7:  # builder-defined two-component mixture
+        s1, s2, m = p[0], p[1], p[2:2 + d]
+        q1 = np.zeros(n)
+        q2 = np.zeros(n)
+        for k in range(d):
+            a_ = x[:, k] - m[k]
+            b_ = x[:, k] + m[k]
+            q1 = q1 + a_ * a_
+            q2 = q2 + b_ * b_
+        t1 = (-q1) / ((2.0 * s1) * s1) - float(d) * math.log(s1)
+        t2 = (-q2) / ((2.0 * s2) * s2) - float(d) * math.log(s2)
+        out = np.empty(n)
+        for i in range(n):
+            hi, lo = (t1[i], t2[i]) if t1[i] > t2[i] else (t2[i], t1[i])
+            out[i] = -INF if hi == -INF else hi + math.log1p(math.exp(lo - hi))
+        return out
+    raise ValueError(kind)
+
+
+def propose(ens, partner, z, flags):
+    """src/mcmc/utils.rs:55 then src/mcmc/ensemble_sample.rs:67-73, for all walkers at once."""
+    x1 = ens
+    x2 = ens[partner]
+    zc = z[:, None]
+    y = x1 * zc + x2 * (1.0 - zc)          # two rounded products, one rounded sum
+    fl = flags.shape[1]
+    keep = np.zeros(ens.shape, dtype=bool)
+    keep[:, :fl] = flags == 0               # only the first flags.len() entries can be held back
+    return np.where(keep, x1, y)
+
+
+def sample_pt_fixed(kind, params, ens, lp, beta, partner, z, flags, u):
+    """Returns (new_ens, new_lp, accepted); inputs untouched.  Raises on the reference's asserts."""
+    ens = np.asarray(ens, dtype=np.float64)
+    lp = np.asarray(lp, dtype=np.float64)
+    n = ens.shape[0]
+    nb = len(beta)
+    npb = n // nb
+    assert npb * nb == n and n > 0 and npb % 2 == 0 and lp.shape[0] == n  # ensemble_sample.rs:130-133
+    partner = np.asarray(partner, dtype=np.int64)
+    y = propose(ens, partner, np.asarray(z), np.asarray(flags))
+    ylp = logprob(kind, params, y)
+    nphi = np.asarray(flags).astype(bool).sum(axis=1)
+    out_e, out_lp, acc = ens.copy(), lp.copy(), np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        b = float(beta[i // npb])
+        delta = float(ylp[i]) - float(lp[i])
+        e = float(nphi[i] - 1) * math.log(float(z[i])) + delta * b
+        try:
+            q = math.exp(e)
+        except OverflowError:
+            q = INF
+        if float(u[i]) < q:  # NaN compares false
+            out_e[i] = y[i]
+            out_lp[i] = ylp[i]
+            acc[i] = 1
+    return out_e, out_lp, acc
+
+
+def exchange_prob(lp1, lp2, beta1, beta2):
+    e = (beta2 - beta1) * (-lp2 + lp1)
+    if e != e:
+        return e
+    try:
+        x = math.exp(e)
+    except OverflowError:
+        x = INF
+    return 1.0 if x > 1.0 else x
+
+
+def swap_walkers_fixed(ens, lp, beta, jvec, r):
+    """src/mcmc/utils.rs:72-112; jvec/r are [(nbeta-1), npb] in sweep order (hottest first)."""
+    ens = np.array(ens, dtype=np.float64)
+    lp = np.array(lp, dtype=np.float64)
+    n = ens.shape[0]
+    nb = len(beta)
+    npb = n // nb
+    assert nb * npb == n
+    swapped = np.zeros(np.shape(jvec), dtype=np.uint8)
+    if n != lp.shape[0]:
+        return ens, lp, swapped
+    for s, i in enumerate(range(nb - 1, 0, -1)):
+        b1, b2 = float(beta[i]), float(beta[i - 1])
+        if b1 > b2:
+            raise ValueError("beta list must be in decreasing order")
+        for j2 in range(npb):
+            j1 = int(jvec[s][j2])
+            hot, cold = i * npb + j1, (i - 1) * npb + j2
+            ep = exchange_prob(float(lp[hot]), float(lp[cold]), b1, b2)
+            if float(r[s][j2]) < ep:
+                ens[[hot, cold]] = ens[[cold, hot]]
+                lp[[hot, cold]] = lp[[cold, hot]]
+                swapped[s][j2] = 1
+    return ens, lp, swapped

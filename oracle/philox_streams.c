@@ -1,0 +1,237 @@
+/*
+ * philox_streams.c -- CPU restatement of scorus_b200's DEVICE random-stream
+ * generator ("stream spec v1").
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is NOT reference behaviour: the reference
+ * consumes a caller-supplied rand::Rng sequentially, which a
+ * GPU cannot reproduce in parallel.  The product draws its partner / z / flag
+ * / accept streams from counter-based Philox4x32-10 keyed by (seed, step,
+ * walker).  This file regenerates exactly those streams on the CPU so that a
+ * Philox-mode GPU step can be replayed through orc_sample_pt_fixed /
+ * orc_swap_walkers_fixed and compared bit for bit.  It is written
+ * independently of scorus_b200/csrc/rng.cuh; the two must agree.
+ */
+#include "scorus_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum {
+    ST_ZU = 1,        /* idx = walker, sub = 0: (r0,r1) -> z uniform, (r2,r3) -> accept uniform */
+    ST_FLAGS = 2,     /* idx = walker, sub = attempt*nblk + blk */
+    ST_PERM = 3,      /* idx = rung, sub = 0,1: keys of the pairing bijection (npb > 1024) */
+    ST_SWAP_PERM = 4, /* idx = hot rung, sub = 0,1: keys of the jvec bijection (npb > 1024) */
+    ST_SWAP_U = 5,    /* idx = cold slot j2, sub = hot rung */
+    ST_PERM_KEY = 6,  /* idx = walker: 64-bit sort key of the exact shuffle (npb <= 1024) */
+    ST_SWAP_KEY = 7   /* idx = hot walker slot: 64-bit sort key of the exact jvec (npb <= 1024) */
+};
+
+#define EXACT_SHUFFLE_MAX 1024u
+
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    philox4x32_10(ctr, key, out);
+}
+
+static void draw(uint64_t seed, uint64_t step, uint32_t stream, uint32_t idx, uint32_t sub,
+                 uint32_t out[4])
+{
+    uint32_t ctr[4] = {idx, sub, (uint32_t)step,
+                       ((uint32_t)(step >> 32) & 0x00FFFFFFu) | (stream << 24)};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    philox4x32_10(ctr, key, out);
+}
+
+static double u53(uint32_t lo, uint32_t hi)
+{
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (double)(v >> 11) * 0x1.0p-53;
+}
+
+/* keyed bijection on [0, n): 4 add / multiply / xorshift rounds on b bits, cycle-walked */
+static uint32_t bij(uint32_t x, uint32_t n, const uint32_t k[8])
+{
+    static const uint32_t C[4] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu};
+    uint32_t b = 1;
+    while (b < 32 && (1ull << b) < n) ++b;
+    uint32_t mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    uint32_t s1 = (b + 1) / 2, s2 = b / 3;
+    if (s1 < 1) s1 = 1;
+    if (s2 < 1) s2 = 1;
+    do {
+        for (int r = 0; r < 4; ++r) {
+            x = (x + k[2 * r]) & mask;
+            x = (x * (k[2 * r + 1] | 1u)) & mask;
+            x ^= x >> s1;
+            x = (x * C[r]) & mask;
+            x ^= x >> s2;
+        }
+    } while (x >= n);
+    return x;
+}
+
+typedef struct { uint64_t key; uint32_t id; } keyed;
+static int cmp_keyed(const void *a, const void *b)
+{
+    const keyed *x = (const keyed *)a, *y = (const keyed *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->id < y->id ? -1 : (x->id > y->id);
+}
+
+/* order[j] = walker at matching position j; positions 2k and 2k+1 are partners */
+static void pairing_order(uint64_t seed, uint64_t step, size_t n, size_t nbeta, uint32_t *order)
+{
+    size_t npb = n / nbeta;
+    if (npb <= EXACT_SHUFFLE_MAX) {
+        keyed *kv = (keyed *)malloc(npb * sizeof(keyed));
+        for (size_t r = 0; r < nbeta; ++r) {
+            for (size_t k = 0; k < npb; ++k) {
+                uint32_t o[4];
+                uint32_t w = (uint32_t)(r * npb + k);
+                draw(seed, step, ST_PERM_KEY, w, 0, o);
+                kv[k].key = ((uint64_t)o[1] << 32) | o[0];
+                kv[k].id = w;
+            }
+            qsort(kv, npb, sizeof(keyed), cmp_keyed);
+            for (size_t k = 0; k < npb; ++k) order[r * npb + k] = kv[k].id;
+        }
+        free(kv);
+    } else {
+        for (size_t r = 0; r < nbeta; ++r) {
+            uint32_t k[8];
+            draw(seed, step, ST_PERM, (uint32_t)r, 0, k);
+            draw(seed, step, ST_PERM, (uint32_t)r, 1, k + 4);
+            for (size_t j = 0; j < npb; ++j)
+                order[r * npb + j] = (uint32_t)(r * npb) + bij((uint32_t)j, (uint32_t)npb, k);
+        }
+    }
+}
+
+/* bits per Bernoulli flag: the smallest of 1,2,4,8,16 for which prob*2^bits is an integer, else 32 */
+static uint32_t flag_bits(double prob)
+{
+    static const uint32_t cand[5] = {1, 2, 4, 8, 16};
+    for (int i = 0; i < 5; ++i) {
+        double t = prob * (double)(1u << cand[i]);
+        if (t == floor(t)) return cand[i];
+    }
+    return 32;
+}
+
+int orc_philox_sample_streams(uint64_t seed, uint64_t step, size_t n, size_t dim, size_t nbeta,
+                              double a, int ufs_kind, double prob, uint64_t onehot_counter,
+                              uint32_t *partner, double *z, uint8_t *flags, double *u)
+{
+    if (nbeta == 0 || n == 0 || n % nbeta || (n / nbeta) % 2) return ORC_ERR_INVALID_ARG;
+    uint32_t *order = (uint32_t *)malloc(n * sizeof(uint32_t));
+    pairing_order(seed, step, n, nbeta, order);
+    for (size_t j = 0; j < n; j += 2) {
+        partner[order[j]] = order[j + 1];
+        partner[order[j + 1]] = order[j];
+    }
+    free(order);
+
+    double sqrt_a = sqrt(a);
+    double inv_sqrt_a = 1.0 / sqrt_a;
+    double range = 2.0 * (sqrt_a - inv_sqrt_a);
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t o[4];
+        draw(seed, step, ST_ZU, (uint32_t)i, 0, o);
+        double p = u53(o[0], o[1]) * range;
+        double y = inv_sqrt_a + p / 2.0;
+        z[i] = y * y;
+        u[i] = u53(o[2], o[3]);
+    }
+
+    if (ufs_kind == ORC_UFS_ALL) {
+        memset(flags, 1, n * dim);
+    } else if (ufs_kind == ORC_UFS_ONE_HOT_CYCLE) {
+        for (size_t i = 0; i < n; ++i) {
+            size_t hot = (size_t)((onehot_counter + 1 + i) % dim);
+            for (size_t k = 0; k < dim; ++k) flags[i * dim + k] = (k == hot);
+        }
+    } else if (ufs_kind == ORC_UFS_PROB) {
+        if (!(prob > 0.0)) return ORC_ERR_INVALID_ARG;
+        uint32_t bpf = flag_bits(prob);
+        uint32_t fpc = 128 / bpf;
+        uint32_t nblk = (uint32_t)((dim + fpc - 1) / fpc);
+        /* threshold: flag = value < thr; thr = prob * 2^bpf (rounded to nearest for 32 bits) */
+        uint64_t thr = bpf == 32 ? (uint64_t)llrint(fmin(prob, 1.0) * 4294967296.0)
+                                 : (uint64_t)(fmin(prob, 1.0) * (double)(1u << bpf));
+        uint64_t vmask = bpf == 32 ? 0xFFFFFFFFull : ((1ull << bpf) - 1);
+        for (size_t i = 0; i < n; ++i) {
+            for (uint32_t attempt = 0;; ++attempt) {
+                int any = 0;
+                for (uint32_t blk = 0; blk < nblk; ++blk) {
+                    uint32_t o[4];
+                    draw(seed, step, ST_FLAGS, (uint32_t)i, attempt * nblk + blk, o);
+                    for (uint32_t w = 0; w < fpc; ++w) {
+                        size_t d = (size_t)blk * fpc + w;
+                        if (d >= dim) break;
+                        uint32_t bit = w * bpf;
+                        uint64_t v = (o[bit / 32] >> (bit % 32)) & vmask;
+                        uint8_t f = v < thr;
+                        flags[i * dim + d] = f;
+                        any |= f;
+                    }
+                }
+                if (any) break;
+            }
+        }
+    } else {
+        return ORC_ERR_INVALID_ARG;
+    }
+    return ORC_OK;
+}
+
+int orc_philox_swap_streams(uint64_t seed, uint64_t swap_call, size_t n, size_t nbeta,
+                            uint32_t *jvec, double *r)
+{
+    if (nbeta == 0 || n % nbeta) return ORC_ERR_INVALID_ARG;
+    size_t npb = n / nbeta;
+    keyed *kv = (keyed *)malloc((npb ? npb : 1) * sizeof(keyed));
+    for (size_t s = 0; s + 1 < nbeta; ++s) {
+        size_t i = nbeta - 1 - s;
+        if (npb <= EXACT_SHUFFLE_MAX) {
+            for (size_t k = 0; k < npb; ++k) {
+                uint32_t o[4];
+                draw(seed, swap_call, ST_SWAP_KEY, (uint32_t)(i * npb + k), 0, o);
+                kv[k].key = ((uint64_t)o[1] << 32) | o[0];
+                kv[k].id = (uint32_t)k;
+            }
+            qsort(kv, npb, sizeof(keyed), cmp_keyed);
+            for (size_t k = 0; k < npb; ++k) jvec[s * npb + k] = kv[k].id;
+        } else {
+            uint32_t k[8];
+            draw(seed, swap_call, ST_SWAP_PERM, (uint32_t)i, 0, k);
+            draw(seed, swap_call, ST_SWAP_PERM, (uint32_t)i, 1, k + 4);
+            for (size_t j = 0; j < npb; ++j) jvec[s * npb + j] = bij((uint32_t)j, (uint32_t)npb, k);
+        }
+        for (size_t j2 = 0; j2 < npb; ++j2) {
+            uint32_t o[4];
+            draw(seed, swap_call, ST_SWAP_U, (uint32_t)j2, (uint32_t)i, o);
+            r[s * npb + j2] = u53(o[0], o[1]);
+        }
+    }
+    free(kv);
+    return ORC_OK;
+}

@@ -1,0 +1,299 @@
+"""ctypes binding of the C oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/scorus_oracle.h.  Importable from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never from
+scorus_b200/ (the product).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+# plugin ids / ufs kinds / status codes (same values as include/scorus_b200.h)
+LP_GAUSSIAN, LP_BOUNDED_GAUSSIAN, LP_ROSENBROCK, LP_RASTRIGIN = 0, 1, 2, 3
+LP_BIMODAL2D, LP_STEP2D, LP_CORR_GAUSSIAN, LP_MIXTURE = 4, 5, 6, 7
+UFS_PROB, UFS_ALL, UFS_ONE_HOT_CYCLE = 0, 1, 2
+OK = 0
+ERR_NWALKERS_IS_ZERO, ERR_NWALKERS_IS_NOT_EVEN = 1, 2
+ERR_NWALKERS_MISMATCHES_NBETA, ERR_BETA_NOT_IN_DECR_ORD = 3, 4
+ERR_LENGTH_MISMATCH, ERR_INVALID_ARG, ERR_NPHI_ZERO = 5, 6, 7
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so with the committed Makefile (gcc, no FMA contraction)."""
+    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "scorus_oracle.h", "Makefile"]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if stale:
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        dp, u32p, u8p, u64p = (C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
+                               C.POINTER(C.c_uint64))
+        sz, u64, dbl, ci = C.c_size_t, C.c_uint64, C.c_double, C.c_int
+        L.orc_logprob.restype = dbl
+        L.orc_logprob.argtypes = [ci, dp, sz, dp, sz]
+        L.orc_z_from_p.restype = dbl
+        L.orc_z_from_p.argtypes = [dbl, dbl]
+        L.orc_z_range.restype = dbl
+        L.orc_z_range.argtypes = [dbl]
+        L.orc_exchange_prob.restype = dbl
+        L.orc_exchange_prob.argtypes = [dbl] * 4
+        L.orc_init_logprob.restype = None
+        L.orc_init_logprob.argtypes = [ci, dp, sz, dp, sz, sz, dp]
+        L.orc_sample_pt_fixed.restype = ci
+        L.orc_sample_pt_fixed.argtypes = [ci, dp, sz, dp, dp, sz, sz, sz, dp, sz, u32p, dp, u8p, sz,
+                                          dp, u8p, dp, dp]
+        L.orc_swap_walkers_fixed.restype = ci
+        L.orc_swap_walkers_fixed.argtypes = [dp, dp, sz, sz, sz, dp, sz, u32p, dp, u8p]
+        L.orc_rng_seed.restype = None
+        L.orc_rng_seed.argtypes = [C.c_void_p, u64]
+        L.orc_rng_uniform.restype = dbl
+        L.orc_rng_uniform.argtypes = [C.c_void_p]
+        L.orc_draw_sample_streams.restype = ci
+        L.orc_draw_sample_streams.argtypes = [C.c_void_p, sz, sz, sz, dbl, ci, dbl, u64p, u32p, dp,
+                                              u8p, dp]
+        L.orc_draw_swap_streams.restype = ci
+        L.orc_draw_swap_streams.argtypes = [C.c_void_p, sz, sz, u32p, dp]
+        L.orc_sample_pt.restype = ci
+        L.orc_sample_pt.argtypes = [ci, dp, sz, dp, dp, sz, sz, C.c_void_p, dbl, ci, dbl, u64p, dp, sz]
+        L.orc_swap_walkers.restype = ci
+        L.orc_swap_walkers.argtypes = [dp, dp, sz, sz, C.c_void_p, dp, sz]
+        L.orc_mean.restype = None
+        L.orc_mean.argtypes = [dp, sz, sz, dp]
+        L.orc_cov.restype = None
+        L.orc_cov.argtypes = [dp, sz, sz, dp]
+        L.orc_init_realization.restype = None
+        L.orc_init_realization.argtypes = [C.c_void_p, dp, dp, sz, dp]
+        L.orc_philox4x32_10.restype = None
+        L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
+        L.orc_philox_sample_streams.restype = ci
+        L.orc_philox_sample_streams.argtypes = [u64, u64, sz, sz, sz, dbl, ci, dbl, u64, u32p, dp, u8p, dp]
+        L.orc_philox_swap_streams.restype = ci
+        L.orc_philox_swap_streams.argtypes = [u64, u64, sz, sz, u32p, dp]
+        L.orc_ref_structure_run.restype = dbl
+        L.orc_ref_structure_run.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, sz, dbl, ci, dbl, u64, sz,
+                                            ci, dp]
+        L.orc_flat_threaded_run.restype = dbl
+        L.orc_flat_threaded_run.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, sz, dbl, ci, dbl, u64, u64,
+                                            sz, ci]
+        L.orc_max_threads.restype = ci
+        L.orc_max_threads.argtypes = []
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _u32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32)) if a is not None else None
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def _params(params):
+    p = np.ascontiguousarray(np.asarray(params if params is not None else [], dtype=np.float64).ravel())
+    return p, _dp(p) if p.size else None, p.size
+
+
+class Rng:
+    """The oracle's own seeded generator (xoshiro256**)."""
+
+    def __init__(self, seed: int):
+        self._state = (C.c_uint64 * 4)()
+        lib().orc_rng_seed(self._state, seed)
+
+    @property
+    def ptr(self):
+        return C.cast(self._state, C.c_void_p)
+
+    def uniform(self) -> float:
+        return lib().orc_rng_uniform(self.ptr)
+
+
+def logprob(kind, params, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    p, pp, npar = _params(params)
+    if x.ndim == 1:
+        return lib().orc_logprob(kind, pp, npar, _dp(x), x.shape[0])
+    out = np.empty(x.shape[0])
+    lib().orc_init_logprob(kind, pp, npar, _dp(x), x.shape[0], x.shape[1], _dp(out))
+    return out
+
+
+def init_logprob(kind, params, ens):
+    return logprob(kind, params, ens)
+
+
+def z_from_p(p, a):
+    return lib().orc_z_from_p(p, a)
+
+
+def z_range(a):
+    return lib().orc_z_range(a)
+
+
+def exchange_prob(lp1, lp2, beta1, beta2):
+    return lib().orc_exchange_prob(lp1, lp2, beta1, beta2)
+
+
+def sample_pt_fixed(kind, params, ens, lp, beta, partner, z, flags, u, want_proposals=False):
+    """In place on ens/lp (float64 C-contiguous).  Returns (rc, accepted[, proposed, new_lp])."""
+    n, dim = ens.shape
+    assert ens.flags.c_contiguous and ens.dtype == np.float64 and lp.dtype == np.float64
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    partner = np.ascontiguousarray(partner, dtype=np.uint32)
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    flag_len = flags.shape[1] if flags.ndim == 2 else dim
+    p, pp, npar = _params(params)
+    acc = np.zeros(n, dtype=np.uint8)
+    prop = np.empty((n, dim)) if want_proposals else None
+    nlp = np.empty(n) if want_proposals else None
+    rc = lib().orc_sample_pt_fixed(kind, pp, npar, _dp(ens), _dp(lp), n, lp.shape[0], dim, _dp(beta),
+                                   beta.shape[0], _u32p(partner), _dp(z), _u8p(flags), flag_len,
+                                   _dp(u), _u8p(acc), _dp(prop), _dp(nlp))
+    if want_proposals:
+        return rc, acc, prop, nlp
+    return rc, acc
+
+
+def swap_walkers_fixed(ens, lp, beta, jvec, r):
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    jvec = np.ascontiguousarray(jvec, dtype=np.uint32)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    sw = np.zeros(max(jvec.size, 1), dtype=np.uint8)
+    rc = lib().orc_swap_walkers_fixed(_dp(ens), _dp(lp), n, lp.shape[0], dim, _dp(beta), beta.shape[0],
+                                      _u32p(jvec), _dp(r), _u8p(sw))
+    return rc, sw[:jvec.size].reshape(jvec.shape)
+
+
+def draw_sample_streams(rng: Rng, n, dim, nbeta, a, ufs_kind, prob=0.5, onehot_counter=0):
+    partner = np.zeros(n, dtype=np.uint32)
+    z = np.zeros(n)
+    u = np.zeros(n)
+    flags = np.zeros((n, dim), dtype=np.uint8)
+    oc = C.c_uint64(onehot_counter)
+    rc = lib().orc_draw_sample_streams(rng.ptr, n, dim, nbeta, a, ufs_kind, prob, C.byref(oc),
+                                       _u32p(partner), _dp(z), _u8p(flags), _dp(u))
+    if rc:
+        raise ValueError(f"orc_draw_sample_streams rc={rc}")
+    return partner, z, flags, u, oc.value
+
+
+def draw_swap_streams(rng: Rng, n, nbeta):
+    npb = n // nbeta
+    jvec = np.zeros((max(nbeta - 1, 0), npb), dtype=np.uint32)
+    r = np.zeros((max(nbeta - 1, 0), npb))
+    rc = lib().orc_draw_swap_streams(rng.ptr, n, nbeta, _u32p(jvec), _dp(r))
+    if rc:
+        raise ValueError(f"orc_draw_swap_streams rc={rc}")
+    return jvec, r
+
+
+def sample_pt(kind, params, ens, lp, rng: Rng, a, ufs_kind, prob, beta, onehot_counter=0):
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    oc = C.c_uint64(onehot_counter)
+    rc = lib().orc_sample_pt(kind, pp, npar, _dp(ens), _dp(lp), n, dim, rng.ptr, a, ufs_kind, prob,
+                             C.byref(oc), _dp(beta), beta.shape[0])
+    return rc, oc.value
+
+
+def swap_walkers(ens, lp, rng: Rng, beta):
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    return lib().orc_swap_walkers(_dp(ens), _dp(lp), n, dim, rng.ptr, _dp(beta), beta.shape[0])
+
+
+def mean(ens):
+    n, dim = ens.shape
+    out = np.empty(dim)
+    lib().orc_mean(_dp(np.ascontiguousarray(ens)), n, dim, _dp(out))
+    return out
+
+
+def cov(ens):
+    n, dim = ens.shape
+    out = np.empty((dim, dim))
+    lib().orc_cov(_dp(np.ascontiguousarray(ens)), n, dim, _dp(out))
+    return out
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def philox_sample_streams(seed, step, n, dim, nbeta, a, ufs_kind, prob=0.5, onehot_counter=0):
+    partner = np.zeros(n, dtype=np.uint32)
+    z = np.zeros(n)
+    u = np.zeros(n)
+    flags = np.zeros((n, dim), dtype=np.uint8)
+    rc = lib().orc_philox_sample_streams(seed, step, n, dim, nbeta, a, ufs_kind, prob, onehot_counter,
+                                         _u32p(partner), _dp(z), _u8p(flags), _dp(u))
+    if rc:
+        raise ValueError(f"orc_philox_sample_streams rc={rc}")
+    return partner, z, flags, u
+
+
+def philox_swap_streams(seed, swap_call, n, nbeta):
+    npb = n // nbeta
+    jvec = np.zeros((max(nbeta - 1, 0), npb), dtype=np.uint32)
+    r = np.zeros((max(nbeta - 1, 0), npb))
+    rc = lib().orc_philox_swap_streams(seed, swap_call, n, nbeta, _u32p(jvec), _dp(r))
+    if rc:
+        raise ValueError(f"orc_philox_swap_streams rc={rc}")
+    return jvec, r
+
+
+def ref_structure_run(kind, params, ens, lp, beta, a, ufs_kind, prob, seed, nsteps, nthreads=0):
+    """CPU baseline with the reference's execution structure. Returns (seconds, stage_seconds[6])."""
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    stage = np.zeros(6)
+    t = lib().orc_ref_structure_run(kind, pp, npar, _dp(ens), _dp(lp), n, dim, _dp(beta), beta.shape[0],
+                                    a, ufs_kind, prob, seed, nsteps, nthreads, _dp(stage))
+    return t, stage
+
+
+def flat_threaded_run(kind, params, ens, lp, beta, a, ufs_kind, prob, seed, first_step, nsteps, nthreads=0):
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    return lib().orc_flat_threaded_run(kind, pp, npar, _dp(ens), _dp(lp), n, dim, _dp(beta),
+                                       beta.shape[0], a, ufs_kind, prob, seed, first_step, nsteps, nthreads)
+
+
+def max_threads() -> int:
+    return lib().orc_max_threads()
