@@ -1,0 +1,177 @@
+/*
+ * scorus_b200.h -- C ABI of the B200-native ensemble sampler (libscorus_b200.so).
+ *
+ * This is the drop-in boundary for scorus's data-parallel MCMC hot path.  The reference
+ * (astrojhgu/scorus, pure Rust) has no FFI of its own; each entry point below names the
+ * reference function (path:line, relative to the reference root) it replaces, and is what a
+ * thin Rust `-sys` crate binds (INTEGRATION.md shows the shim; rust/ holds its source).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ / torch types.
+ *  - every call returns 0 (SCORUS_OK) or a positive status code; nothing unwinds.
+ *    Codes 1..4 are the reference's McmcErr variants (src/mcmc/mcmc_errors.rs:1-7) in
+ *    declaration order; the reference itself assert!s / panics on them
+ *    (src/mcmc/ensemble_sample.rs:130-133, src/mcmc/utils.rs:86,93-95).
+ *  - a context is NOT thread-safe (mirrors the reference's `&mut` exclusivity).
+ *  - ensembles cross the ABI flat and walker-major, double[n][dim]: row i is walker i,
+ *    rung r owns walkers [r*n/nbeta, (r+1)*n/nbeta) (src/mcmc/ensemble_sample.rs:137,181).
+ *  - there is no CPU fallback: without a CUDA device scorus_ctx_create fails.
+ */
+#ifndef SCORUS_B200_H
+#define SCORUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCORUS_B200_ABI_VERSION 1
+
+typedef struct scorus_ctx scorus_ctx;
+
+/* status codes */
+enum {
+    SCORUS_OK = 0,
+    SCORUS_ERR_NWALKERS_IS_ZERO = 1,          /* McmcErr::NWalkersIsZero          */
+    SCORUS_ERR_NWALKERS_IS_NOT_EVEN = 2,      /* McmcErr::NWalkersIsNotEven       */
+    SCORUS_ERR_NWALKERS_MISMATCHES_NBETA = 3, /* McmcErr::NWalkersMismatchesNBeta */
+    SCORUS_ERR_BETA_NOT_IN_DECR_ORD = 4,      /* McmcErr::BetaNotInDecrOrd        */
+    SCORUS_ERR_LENGTH_MISMATCH = 5,           /* assert at ensemble_sample.rs:133 */
+    SCORUS_ERR_INVALID_ARG = 6,
+    SCORUS_ERR_NPHI_ZERO = 7,                 /* `nphi - 1` on usize, ensemble_sample.rs:184 */
+    SCORUS_ERR_NO_LOGPROB = 8,                /* no log-density plugin registered */
+    SCORUS_ERR_NOT_UPLOADED = 9,
+    SCORUS_ERR_DIM_TOO_LARGE = 10,            /* one 32-walker tile must fit in shared memory */
+    SCORUS_ERR_CUDA = 100,                    /* see scorus_last_error */
+    SCORUS_ERR_NO_DEVICE = 101
+};
+
+/* log-density plugins: the device-side replacements of the `flogprob: &F` closure
+ * (src/mcmc/ensemble_sample.rs:88,102).  params layouts in the comments. */
+enum {
+    SCORUS_LP_GAUSSIAN = 0,         /* {c}: -sum c*x^2; c=0.5 examples/test_emcee.rs:18-24, c=1 examples/sample_high_dim.rs:22-28 */
+    SCORUS_LP_BOUNDED_GAUSSIAN = 1, /* {limit}: examples/sample_bimodal.rs:35-44 */
+    SCORUS_LP_ROSENBROCK = 2,       /* {}: examples/test_emcee.rs:26-32 */
+    SCORUS_LP_RASTRIGIN = 3,        /* {a}: examples/sample_rastrigin.rs:17-25 */
+    SCORUS_LP_BIMODAL2D = 4,        /* {} or {lo0,hi0,lo1,hi1,split,mu_a,sigma_a,mu_b,sigma_b}: examples/sample_bimodal.rs:46-54 */
+    SCORUS_LP_STEP2D = 5,           /* {}: examples/sample_bimodal.rs:56-65 */
+    SCORUS_LP_CORR_GAUSSIAN = 6,    /* {mu[D], L[D][D] row-major}: -0.5*|L(x-mu)|^2 (not in the reference; BASELINE config 2) */
+    SCORUS_LP_MIXTURE = 7,          /* {sigma1, sigma2, m[D]}: two-component mixture (not in the reference; BASELINE config 3) */
+    SCORUS_LP_COUNT = 8
+};
+
+/* UpdateFlagSpec (src/mcmc/ensemble_sample.rs:25-55) */
+enum {
+    SCORUS_UFS_PROB = 0,          /* Prob(p): D Bernoulli(p), redrawn until one is set (:43-50) */
+    SCORUS_UFS_ALL = 1,           /* All (:51) */
+    SCORUS_UFS_ONE_HOT_CYCLE = 2, /* the cycling Func closure of examples/sample_high_dim.rs:59-65 */
+    SCORUS_UFS_MASK = 3           /* Func(f) in general: the caller evaluates f() once per walker
+                                     on the host and passes the [n][mask_len] byte matrix (:52) */
+};
+typedef struct scorus_ufs {
+    int32_t kind;
+    int32_t reserved;
+    double prob;          /* SCORUS_UFS_PROB */
+    const uint8_t *mask;  /* SCORUS_UFS_MASK: [n][mask_len], nonzero = move */
+    size_t mask_len;      /* <= dim; coordinates >= mask_len always move (:68) */
+} scorus_ufs;
+
+#define SCORUS_CFG_DEFAULT 0u
+typedef struct scorus_cfg {
+    uint64_t n_walkers; /* ensemble.len() */
+    uint32_t dim;       /* ensemble[i].dimension() */
+    int32_t device;     /* CUDA device ordinal, -1 = the current device */
+    uint64_t seed;      /* key of the counter-based device RNG (replaces `rng: &mut U`) */
+    uint32_t flags;     /* SCORUS_CFG_* */
+    uint32_t reserved;
+} scorus_cfg;
+
+/* ---- library ---- */
+int scorus_abi_version(void);
+const char *scorus_status_string(int status);
+int scorus_device_count(void);
+
+/* Precondition checks, callable without a GPU.
+ * scorus_check_sample_args: asserts of src/mcmc/ensemble_sample.rs:127-133, in order.
+ * scorus_check_beta_order:  the panic of src/mcmc/utils.rs:91-95 (equal betas tolerated). */
+int scorus_check_sample_args(size_t n_walkers, size_t logprob_len, size_t nbeta);
+int scorus_check_beta_order(const double *beta_list, size_t nbeta);
+
+/* ---- context: owns the device copy of (ensemble, logprob) ---- */
+int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg);
+void scorus_ctx_destroy(scorus_ctx *ctx);
+const char *scorus_last_error(const scorus_ctx *ctx);
+
+/* registers the log-density; replaces the `flogprob` argument of every reference call */
+int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *params, size_t nparams);
+
+/* host <-> device. logprob == NULL on upload runs init_logprob on the device. */
+int scorus_upload(scorus_ctx *ctx, const double *ensemble, const double *logprob);
+int scorus_download(scorus_ctx *ctx, double *ensemble, double *logprob);
+
+/* init_logprob, src/mcmc/ensemble_sample.rs:77-85 */
+int scorus_init_logprob(scorus_ctx *ctx);
+
+/* sample, src/mcmc/ensemble_sample.rs:87-105 (= sample_pt with beta_list = [1]) */
+int scorus_sample(scorus_ctx *ctx, double a, const scorus_ufs *ufs, uint64_t nsteps);
+
+/* sample_pt, src/mcmc/ensemble_sample.rs:107-190: nsteps fused steps on the device copy.
+ * Asynchronous on the context's stream; scorus_sync / scorus_download wait. */
+int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list,
+                     size_t nbeta, uint64_t nsteps);
+
+/* sample_pt with every random draw supplied by the caller (the parity entry point):
+ * partner[n] (ensemble_sample.rs:135-148), z[n] (:149), flags[n][flag_len] bytes (:150-153),
+ * u[n] (:185).  accepted_out[n] (may be NULL) receives the accept decisions.  Synchronous. */
+int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta_list, size_t nbeta,
+                           const uint32_t *partner, const double *z, const uint8_t *flags,
+                           size_t flag_len, const double *u, uint8_t *accepted_out);
+
+/* draw_z, src/mcmc/utils.rs:33-45: `count` stretch factors g(z) ~ 1/sqrt(z) on [1/a, a) from the
+ * device stream (the draws walkers 0..count-1 would get at the current step; the step counter
+ * advances by one).  out is a host array.  count <= n_walkers. */
+int scorus_draw_z(scorus_ctx *ctx, double a, size_t count, double *out);
+
+/* swap_walkers, src/mcmc/utils.rs:72-112 */
+int scorus_swap_walkers(scorus_ctx *ctx, const double *beta_list, size_t nbeta);
+/* ... with the draws supplied: jvec[(nbeta-1)][n/nbeta] (utils.rs:97) and r (same shape,
+ * :104) in sweep order, stage s = rung nbeta-1-s.  swapped_out same shape or NULL. */
+int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta_list, size_t nbeta,
+                              const uint32_t *jvec, const double *r, uint8_t *swapped_out);
+
+/* The literal drop-in for the reference's `&mut [V]`, `&mut [T]` call shape: host buffers in,
+ * one sample_pt step, host buffers out (upload + step + download on the context's stream).
+ * logprob_len is cached_logprob.len() (checked like ensemble_sample.rs:133). */
+int scorus_sample_pt_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
+                          double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
+/* swap_walkers on host buffers; a logprob_len mismatch is the reference's silent no-op
+ * (src/mcmc/utils.rs:88). */
+int scorus_swap_walkers_host(scorus_ctx *ctx, double *ensemble, double *logprob,
+                             size_t logprob_len, const double *beta_list, size_t nbeta);
+
+/* ---- plumbing ---- */
+int scorus_sync(scorus_ctx *ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+int scorus_set_stream(scorus_ctx *ctx, void *cuda_stream);
+void *scorus_get_stream(scorus_ctx *ctx);
+/* device pointers of the resident state: ensemble rows are pitch_elems doubles apart */
+int scorus_device_buffers(scorus_ctx *ctx, double **ensemble, size_t *pitch_elems, double **logprob);
+/* RNG position = (step counter, swap-call counter, one-hot cycle counter); with the seed and a
+ * download this is a complete checkpoint */
+int scorus_get_counters(const scorus_ctx *ctx, uint64_t *step, uint64_t *swap_call, uint64_t *onehot);
+int scorus_set_counters(scorus_ctx *ctx, uint64_t step, uint64_t swap_call, uint64_t onehot);
+/* running totals since creation (synchronises): accepted / proposed moves, accepted / proposed swaps */
+int scorus_get_stats(scorus_ctx *ctx, uint64_t *accepted, uint64_t *proposed, uint64_t *swapped,
+                     uint64_t *swap_proposed);
+/* number of kernels this library has launched on this context since creation */
+uint64_t scorus_launch_count(const scorus_ctx *ctx);
+/* pinned host memory for callers that want full-speed scorus_*_host / upload / download */
+void *scorus_host_alloc(size_t bytes);
+void scorus_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCORUS_B200_H */

@@ -224,7 +224,8 @@ int orc_philox_swap_streams(uint64_t seed, uint64_t swap_call, size_t n, size_t 
             uint32_t k[8];
             draw(seed, swap_call, ST_SWAP_PERM, (uint32_t)i, 0, k);
             draw(seed, swap_call, ST_SWAP_PERM, (uint32_t)i, 1, k + 4);
-            for (size_t j = 0; j < npb; ++j) jvec[s * npb + j] = bij((uint32_t)j, (uint32_t)npb, k);
+            /* the bijection maps the hot slot j1 to the cold slot j2, i.e. jvec[j2] = j1 */
+            for (size_t j1 = 0; j1 < npb; ++j1) jvec[s * npb + bij((uint32_t)j1, (uint32_t)npb, k)] = (uint32_t)j1;
         }
         for (size_t j2 = 0; j2 < npb; ++j2) {
             uint32_t o[4];

@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
         L.orc_z_range.argtypes = [dbl]
         L.orc_exchange_prob.restype = dbl
         L.orc_exchange_prob.argtypes = [dbl] * 4
+        L.orc_propose_move.restype = None
+        L.orc_propose_move.argtypes = [dp, dp, dbl, u8p, sz, sz, dp]
         L.orc_init_logprob.restype = None
         L.orc_init_logprob.argtypes = [ci, dp, sz, dp, sz, sz, dp]
         L.orc_sample_pt_fixed.restype = ci
@@ -154,6 +156,15 @@ def z_from_p(p, a):
 
 def z_range(a):
     return lib().orc_z_range(a)
+
+
+def propose_move(p1, p2, z, flags=None):
+    p1 = np.ascontiguousarray(p1, dtype=np.float64)
+    p2 = np.ascontiguousarray(p2, dtype=np.float64)
+    out = np.empty_like(p1)
+    f = np.ascontiguousarray(flags, dtype=np.uint8) if flags is not None else None
+    lib().orc_propose_move(_dp(p1), _dp(p2), z, _u8p(f), f.size if f is not None else 0, p1.size, _dp(out))
+    return out
 
 
 def exchange_prob(lp1, lp2, beta1, beta2):

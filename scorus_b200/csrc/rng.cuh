@@ -1,0 +1,119 @@
+// rng.cuh -- counter-based random streams of the device sampler ("stream spec v1").
+//
+// The reference consumes one sequential rand::Rng on the calling thread
+// (src/mcmc/ensemble_sample.rs:139,149,152,185; src/mcmc/utils.rs:97,104).  Here every draw
+// is a pure function of (seed, step, walker, stream id), so any walker can be processed by
+// any thread / GPU and a run is reproducible from (seed, counters).  DESIGN.md section 5
+// states the spec; oracle/philox_streams.c restates it independently on the CPU for replay.
+#pragma once
+#include <cstdint>
+
+namespace scorus {
+
+enum : uint32_t {
+    ST_ZU = 1,         // idx = walker, sub = 0: (r0,r1) -> z uniform, (r2,r3) -> accept uniform
+    ST_FLAGS = 2,      // idx = walker, sub = attempt*nblk + blk: Bernoulli flag bits
+    ST_PERM = 3,       // idx = rung, sub = 0,1: keys of the pairing bijection (npb > 1024)
+    ST_SWAP_PERM = 4,  // idx = hot rung, sub = 0,1: keys of the jvec bijection (npb > 1024)
+    ST_SWAP_U = 5,     // idx = cold slot j2, sub = hot rung: swap uniform
+    ST_PERM_KEY = 6,   // idx = walker: 64-bit sort key of the exact shuffle (npb <= 1024)
+    ST_SWAP_KEY = 7    // idx = hot walker slot: 64-bit sort key of the exact jvec (npb <= 1024)
+};
+
+constexpr uint32_t kExactShuffleMax = 1024;  // rungs up to this size get an exact uniform shuffle
+
+struct U4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al. 2011)
+__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        U4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__host__ __device__ __forceinline__ U4 draw(uint64_t seed, uint64_t step, uint32_t stream,
+                                            uint32_t idx, uint32_t sub)
+{
+    U4 c;
+    c.x = idx;
+    c.y = sub;
+    c.z = (uint32_t)step;
+    c.w = ((uint32_t)(step >> 32) & 0x00FFFFFFu) | (stream << 24);
+    return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 53-bit uniform in [0,1)
+__host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi)
+{
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (double)(v >> 11) * 0x1.0p-53;
+}
+
+struct BijKeys { uint32_t k[8]; };
+
+__host__ __device__ __forceinline__ BijKeys bij_keys(uint64_t seed, uint64_t step, uint32_t stream,
+                                                     uint32_t idx)
+{
+    U4 a = draw(seed, step, stream, idx, 0), b = draw(seed, step, stream, idx, 1);
+    BijKeys r;
+    r.k[0] = a.x; r.k[1] = a.y; r.k[2] = a.z; r.k[3] = a.w;
+    r.k[4] = b.x; r.k[5] = b.y; r.k[6] = b.z; r.k[7] = b.w;
+    return r;
+}
+
+__host__ __device__ __forceinline__ uint32_t bij_bits(uint32_t n)
+{
+    uint32_t b = 1;
+    while (b < 32 && (1ull << b) < n) ++b;
+    return b;
+}
+
+// keyed bijection of [0, n): four add / odd-multiply / xorshift rounds on b = ceil(log2 n)
+// bits (each a bijection of the b-bit integers), cycle-walked back into range.
+__host__ __device__ __forceinline__ uint32_t bij(uint32_t x, uint32_t n, uint32_t b, const BijKeys &K)
+{
+    const uint32_t C0 = 0x9E3779B1u, C1 = 0x85EBCA6Bu, C2 = 0xC2B2AE35u, C3 = 0x27D4EB2Fu;
+    const uint32_t mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    uint32_t s1 = (b + 1) / 2, s2 = b / 3;
+    if (s1 < 1) s1 = 1;
+    if (s2 < 1) s2 = 1;
+    do {
+        x = (x + K.k[0]) & mask; x = (x * (K.k[1] | 1u)) & mask; x ^= x >> s1; x = (x * C0) & mask; x ^= x >> s2;
+        x = (x + K.k[2]) & mask; x = (x * (K.k[3] | 1u)) & mask; x ^= x >> s1; x = (x * C1) & mask; x ^= x >> s2;
+        x = (x + K.k[4]) & mask; x = (x * (K.k[5] | 1u)) & mask; x ^= x >> s1; x = (x * C2) & mask; x ^= x >> s2;
+        x = (x + K.k[6]) & mask; x = (x * (K.k[7] | 1u)) & mask; x ^= x >> s1; x = (x * C3) & mask; x ^= x >> s2;
+    } while (x >= n);
+    return x;
+}
+
+// Goodman-Weare stretch factor from a unit uniform: src/mcmc/utils.rs:39-44 with
+// p = u * 2(sqrt a - 1/sqrt a);  inv_sqrt_a and range are computed once on the host.
+__host__ __device__ __forceinline__ double z_from_uniform(double u01, double inv_sqrt_a, double range)
+{
+    double p = u01 * range;
+    double y = inv_sqrt_a + p / 2.0;
+    return y * y;
+}
+
+}  // namespace scorus

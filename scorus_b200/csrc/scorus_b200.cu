@@ -1,0 +1,776 @@
+// scorus_b200.cu -- context + C ABI of libscorus_b200.so (see include/scorus_b200.h).
+//
+// Host side of the B200-native ensemble sampler: owns the device-resident (ensemble, logprob),
+// validates the reference's preconditions, and launches the kernels of step_kernel.cuh and
+// swap_kernel.cuh.  There is deliberately no CPU path in this file.
+#include "../../include/scorus_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "step_kernel.cuh"
+#include "swap_kernel.cuh"
+
+using namespace scorus;
+
+struct scorus_ctx {
+    int device = 0;
+    uint64_t n = 0;
+    uint32_t dim = 0, pitch = 0;
+    uint64_t seed = 0;
+    uint64_t step = 0, swap_call = 0, onehot = 0;
+    uint64_t launches = 0, proposed = 0, swap_proposed = 0;
+    int num_sms = 0, smem_optin = 0;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double *d_ens = nullptr, *d_lp = nullptr, *d_scratch = nullptr;
+    double *d_beta = nullptr;   size_t beta_cap = 0;
+    double *d_params = nullptr; size_t params_cap = 0;
+    uint32_t *d_order = nullptr, *d_src = nullptr;
+    unsigned long long *d_stats = nullptr;
+    // scratch for caller-supplied streams
+    double *d_z = nullptr, *d_u = nullptr;
+    uint8_t *d_flags = nullptr; size_t flags_cap = 0;
+    uint8_t *d_acc = nullptr;
+    uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
+    double *d_r = nullptr;      size_t r_cap = 0;
+    uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
+
+    int lp_kind = -1;
+    uint32_t nparams = 0;
+    bool uploaded = false;
+    std::string err;
+    std::vector<double> h_beta;
+};
+
+static int fail(scorus_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, SCORUS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// library-level helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_abi_version(void) { return SCORUS_B200_ABI_VERSION; }
+
+extern "C" const char *scorus_status_string(int s)
+{
+    switch (s) {
+    case SCORUS_OK: return "ok";
+    case SCORUS_ERR_NWALKERS_IS_ZERO: return "NWalkersIsZero";
+    case SCORUS_ERR_NWALKERS_IS_NOT_EVEN: return "NWalkersIsNotEven";
+    case SCORUS_ERR_NWALKERS_MISMATCHES_NBETA: return "NWalkersMismatchesNBeta";
+    case SCORUS_ERR_BETA_NOT_IN_DECR_ORD: return "BetaNotInDecrOrd";
+    case SCORUS_ERR_LENGTH_MISMATCH: return "ensemble and logprob lengths differ";
+    case SCORUS_ERR_INVALID_ARG: return "invalid argument";
+    case SCORUS_ERR_NPHI_ZERO: return "update flags of a walker are all false";
+    case SCORUS_ERR_NO_LOGPROB: return "no log-density registered";
+    case SCORUS_ERR_NOT_UPLOADED: return "no ensemble uploaded";
+    case SCORUS_ERR_DIM_TOO_LARGE: return "dimension too large for one shared-memory tile";
+    case SCORUS_ERR_CUDA: return "CUDA error";
+    case SCORUS_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+    }
+}
+
+extern "C" int scorus_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int scorus_check_sample_args(size_t n, size_t lp_len, size_t nbeta)
+{
+    // src/mcmc/ensemble_sample.rs:127-133, in assert order
+    if (nbeta == 0) return SCORUS_ERR_INVALID_ARG;  // division by zero in the reference
+    size_t npb = n / nbeta;
+    if (npb * nbeta != n) return SCORUS_ERR_NWALKERS_MISMATCHES_NBETA;
+    if (n == 0) return SCORUS_ERR_NWALKERS_IS_ZERO;
+    if (npb % 2 != 0) return SCORUS_ERR_NWALKERS_IS_NOT_EVEN;
+    if (n != lp_len) return SCORUS_ERR_LENGTH_MISMATCH;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_check_beta_order(const double *beta, size_t nbeta)
+{
+    // src/mcmc/utils.rs:91-95: panic if beta[i] > beta[i-1]; equal values pass
+    if (!beta && nbeta) return SCORUS_ERR_INVALID_ARG;
+    for (size_t i = 1; i < nbeta; ++i)
+        if (beta[i] > beta[i - 1]) return SCORUS_ERR_BETA_NOT_IN_DECR_ORD;
+    return SCORUS_OK;
+}
+
+extern "C" void *scorus_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void scorus_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
+{
+    if (!out || !cfg) return SCORUS_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->n_walkers == 0) return SCORUS_ERR_NWALKERS_IS_ZERO;
+    if (cfg->n_walkers % 2) return SCORUS_ERR_NWALKERS_IS_NOT_EVEN;
+    if (cfg->dim == 0 || cfg->n_walkers > 0xFFFFFFFFull) return SCORUS_ERR_INVALID_ARG;
+    int ndev = scorus_device_count();
+    if (ndev <= 0) return SCORUS_ERR_NO_DEVICE;  // no CPU fallback, by design
+    scorus_ctx *ctx = new scorus_ctx();
+    int dev = cfg->device;
+    cudaError_t e;
+    if (dev < 0) {
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) { delete ctx; return SCORUS_ERR_CUDA; }
+    }
+    if (dev >= ndev) { delete ctx; return SCORUS_ERR_INVALID_ARG; }
+    ctx->device = dev;
+    ctx->n = cfg->n_walkers;
+    ctx->dim = cfg->dim;
+    ctx->pitch = cfg->dim + (cfg->dim & 1u);  // rows are 16-byte multiples for cp.async.bulk
+    ctx->seed = cfg->seed;
+    auto bail = [&](cudaError_t err, const char *what) {
+        fprintf(stderr, "scorus_ctx_create: %s: %s\n", what, cudaGetErrorString(err));
+        scorus_ctx_destroy(ctx);
+        return SCORUS_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    ctx->stream = ctx->own_stream;
+    size_t ens_bytes = (size_t)ctx->n * ctx->pitch * sizeof(double);
+    if ((e = cudaMalloc(&ctx->d_ens, ens_bytes)) != cudaSuccess) return bail(e, "cudaMalloc ensemble");
+    if ((e = cudaMalloc(&ctx->d_lp, ctx->n * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logprob");
+    if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc stats");
+    cudaMemsetAsync(ctx->d_ens, 0, ens_bytes, ctx->stream);
+    cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    *out = ctx;
+    return SCORUS_OK;
+}
+
+extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_beta, ctx->d_params, ctx->d_order,
+                    ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
+                    ctx->d_jinv, ctx->d_r, ctx->d_swapped};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *scorus_last_error(const scorus_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int scorus_set_stream(scorus_ctx *ctx, void *s)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return SCORUS_OK;
+}
+extern "C" void *scorus_get_stream(scorus_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int scorus_sync(scorus_ctx *ctx)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_device_buffers(scorus_ctx *ctx, double **ens, size_t *pitch, double **lp)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (ens) *ens = ctx->d_ens;
+    if (pitch) *pitch = ctx->pitch;
+    if (lp) *lp = ctx->d_lp;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_get_counters(const scorus_ctx *ctx, uint64_t *step, uint64_t *swap_call, uint64_t *onehot)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (step) *step = ctx->step;
+    if (swap_call) *swap_call = ctx->swap_call;
+    if (onehot) *onehot = ctx->onehot;
+    return SCORUS_OK;
+}
+extern "C" int scorus_set_counters(scorus_ctx *ctx, uint64_t step, uint64_t swap_call, uint64_t onehot)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    ctx->step = step;
+    ctx->swap_call = swap_call;
+    ctx->onehot = onehot % ctx->dim;
+    return SCORUS_OK;
+}
+
+extern "C" uint64_t scorus_launch_count(const scorus_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int scorus_get_stats(scorus_ctx *ctx, uint64_t *accepted, uint64_t *proposed, uint64_t *swapped,
+                                uint64_t *swap_proposed)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    unsigned long long h[4];
+    CU(cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (accepted) *accepted = h[0];
+    if (proposed) *proposed = ctx->proposed;
+    if (swapped) *swapped = h[2];
+    if (swap_proposed) *swap_proposed = ctx->swap_proposed;
+    return SCORUS_OK;
+}
+
+static int ensure(scorus_ctx *ctx, void **buf, size_t *cap, size_t bytes)
+{
+    if (*buf && *cap >= bytes) return SCORUS_OK;
+    if (*buf) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(*buf); *buf = nullptr; }
+    CU(cudaMalloc(buf, bytes ? bytes : 16));
+    *cap = bytes;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *params, size_t nparams)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (kind < 0 || kind >= SCORUS_LP_COUNT) return fail(ctx, SCORUS_ERR_INVALID_ARG, "unknown log-density kind %d", kind);
+    if (nparams && !params) return fail(ctx, SCORUS_ERR_INVALID_ARG, "params is NULL");
+    const size_t d = ctx->dim;
+    if ((kind == SCORUS_LP_BIMODAL2D || kind == SCORUS_LP_STEP2D) && d < 2)
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "2-D log-density needs dim >= 2");
+    if (kind == SCORUS_LP_BIMODAL2D && nparams != 0 && nparams != 9)
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "BIMODAL2D takes 0 or 9 params");
+    if (kind == SCORUS_LP_CORR_GAUSSIAN && nparams != d + d * d)
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "CORR_GAUSSIAN takes dim + dim*dim params");
+    if (kind == SCORUS_LP_MIXTURE && nparams != 2 + d)
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "MIXTURE takes 2 + dim params");
+    cudaSetDevice(ctx->device);
+    int rc = ensure(ctx, (void **)&ctx->d_params, &ctx->params_cap, (nparams ? nparams : 1) * sizeof(double));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nparams) CU(cudaMemcpy(ctx->d_params, params, nparams * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->lp_kind = kind;
+    ctx->nparams = (uint32_t)nparams;
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch geometry
+// ------------------------------------------------------------------------------------------
+struct Geometry {
+    uint32_t row_bytes, row_stride, flag_words, stages, warps, grid;
+    size_t smem;
+};
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+static int step_geometry(scorus_ctx *ctx, Geometry *g)
+{
+    g->row_bytes = ctx->pitch * 8u;
+    g->row_stride = g->row_bytes;
+    if (((g->row_stride / 16u) & 1u) == 0) g->row_stride += 16u;  // odd number of 16-byte units
+    g->flag_words = (ctx->dim + 31u) / 32u;
+    const size_t flag_bytes = ((size_t)g->flag_words * 128u + 127u) & ~(size_t)127u;
+    const size_t tile = 32u * (size_t)g->row_stride;
+    const size_t budget = (size_t)ctx->smem_optin;
+    const int want_stages = env_int("SCORUS_STAGES", 0), want_warps = env_int("SCORUS_WARPS", 0);
+    auto fit = [&](uint32_t s) {
+        const size_t per_warp = s * tile + flag_bytes;
+        uint32_t w = 16;
+        while (w >= 1 && ((8u * w * s + 127u) & ~127u) + w * per_warp > budget) --w;
+        return w;
+    };
+    uint32_t best_s, best_w;
+    if (want_stages >= 2 && want_stages <= 4) {
+        best_s = (uint32_t)want_stages;
+        best_w = fit(best_s);
+    } else {
+        // three stages (two tiles in flight while one is computed) when at least four warps fit
+        best_s = 3;
+        best_w = fit(3);
+        if (best_w < 4) {
+            uint32_t w2 = fit(2);
+            if (w2 > best_w) { best_s = 2; best_w = w2; }
+        }
+    }
+    if (best_w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
+    if (want_warps > 0 && (uint32_t)want_warps < best_w) best_w = (uint32_t)want_warps;
+    g->stages = best_s;
+    g->warps = best_w;
+    const uint32_t ntiles = (uint32_t)((ctx->n + 31u) / 32u);
+    uint32_t grid = (ntiles + g->warps - 1) / g->warps;
+    if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+    g->grid = grid;
+    g->smem = ((8u * g->warps * g->stages + 127u) & ~127u) + (size_t)g->warps * (g->stages * tile + flag_bytes);
+    return SCORUS_OK;
+}
+
+template <class Plugin>
+static cudaError_t launch_step_t(const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st)
+{
+    cudaError_t e;
+    if (all_flags) {
+        e = cudaFuncSetAttribute(step_kernel<Plugin, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+        if (e != cudaSuccess) return e;
+        step_kernel<Plugin, true><<<g.grid, g.warps * 32, g.smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(step_kernel<Plugin, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+        if (e != cudaSuccess) return e;
+        step_kernel<Plugin, false><<<g.grid, g.warps * 32, g.smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st)
+{
+    switch (kind) {
+    case SCORUS_LP_GAUSSIAN: return launch_step_t<LpGaussian>(p, g, all_flags, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_step_t<LpBoundedGaussian>(p, g, all_flags, st);
+    case SCORUS_LP_ROSENBROCK: return launch_step_t<LpRosenbrock>(p, g, all_flags, st);
+    case SCORUS_LP_RASTRIGIN: return launch_step_t<LpRastrigin>(p, g, all_flags, st);
+    case SCORUS_LP_BIMODAL2D: return launch_step_t<LpBimodal2d>(p, g, all_flags, st);
+    case SCORUS_LP_STEP2D: return launch_step_t<LpStep2d>(p, g, all_flags, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_step_t<LpCorrGaussian>(p, g, all_flags, st);
+    case SCORUS_LP_MIXTURE: return launch_step_t<LpMixture>(p, g, all_flags, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <class Plugin>
+static cudaError_t launch_init_t(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(init_logprob_kernel<Plugin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    init_logprob_kernel<Plugin><<<grid, p.warps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+extern "C" int scorus_init_logprob(scorus_ctx *ctx)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
+    cudaSetDevice(ctx->device);
+    Geometry g;
+    int rc = step_geometry(ctx, &g);
+    if (rc) return rc;
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.ens = ctx->d_ens; p.lp = ctx->d_lp; p.pparams = ctx->d_params; p.nparams = ctx->nparams;
+    p.n = (uint32_t)ctx->n; p.dim = ctx->dim; p.pitch = ctx->pitch;
+    p.row_bytes = g.row_bytes; p.row_stride = g.row_stride;
+    p.ntiles = (uint32_t)((ctx->n + 31u) / 32u);
+    const size_t tile = 32u * (size_t)g.row_stride;
+    uint32_t w = 16;
+    while (w > 1 && ((8u * w + 127u) & ~127u) + w * tile > (size_t)ctx->smem_optin) --w;
+    p.warps = w;
+    size_t smem = ((8u * w + 127u) & ~127u) + w * tile;
+    uint32_t grid = (p.ntiles + w - 1) / w;
+    // several CTAs per SM are fine here: one stage per warp, latency hidden across CTAs
+    uint32_t max_grid = (uint32_t)ctx->num_sms * 4u;
+    if (grid > max_grid) grid = max_grid;
+    cudaError_t e;
+    switch (ctx->lp_kind) {
+    case SCORUS_LP_GAUSSIAN: e = launch_init_t<LpGaussian>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_BOUNDED_GAUSSIAN: e = launch_init_t<LpBoundedGaussian>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_ROSENBROCK: e = launch_init_t<LpRosenbrock>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_RASTRIGIN: e = launch_init_t<LpRastrigin>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_BIMODAL2D: e = launch_init_t<LpBimodal2d>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_STEP2D: e = launch_init_t<LpStep2d>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_CORR_GAUSSIAN: e = launch_init_t<LpCorrGaussian>(p, grid, smem, ctx->stream); break;
+    case SCORUS_LP_MIXTURE: e = launch_init_t<LpMixture>(p, grid, smem, ctx->stream); break;
+    default: e = cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "init_logprob launch: %s", cudaGetErrorString(e));
+    ++ctx->launches;
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host <-> device
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_upload(scorus_ctx *ctx, const double *ens, const double *lp)
+{
+    if (!ctx || !ens) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    const size_t rb = (size_t)ctx->dim * sizeof(double);
+    CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(double), ens, rb, rb, ctx->n,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    ctx->uploaded = true;
+    if (lp) {
+        CU(cudaMemcpyAsync(ctx->d_lp, lp, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        int rc = scorus_init_logprob(ctx);
+        if (rc) return rc;
+    }
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_download(scorus_ctx *ctx, double *ens, double *lp)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "nothing uploaded");
+    cudaSetDevice(ctx->device);
+    const size_t rb = (size_t)ctx->dim * sizeof(double);
+    if (ens)
+        CU(cudaMemcpy2DAsync(ens, rb, ctx->d_ens, (size_t)ctx->pitch * sizeof(double), rb, ctx->n,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    if (lp) CU(cudaMemcpyAsync(lp, ctx->d_lp, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sample_pt
+// ------------------------------------------------------------------------------------------
+static int upload_beta(scorus_ctx *ctx, const double *beta, size_t nbeta)
+{
+    if (ctx->h_beta.size() == nbeta && memcmp(ctx->h_beta.data(), beta, nbeta * sizeof(double)) == 0 && ctx->d_beta)
+        return SCORUS_OK;
+    int rc = ensure(ctx, (void **)&ctx->d_beta, &ctx->beta_cap, nbeta * sizeof(double));
+    if (rc) return rc;
+    // stream-ordered copy from a context-owned staging vector: earlier launches keep their values
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->h_beta.assign(beta, beta + nbeta);
+    CU(cudaMemcpyAsync(ctx->d_beta, ctx->h_beta.data(), nbeta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return SCORUS_OK;
+}
+
+static uint32_t flag_bits_for(double prob)
+{
+    const uint32_t cand[5] = {1, 2, 4, 8, 16};
+    for (uint32_t b : cand) {
+        double t = prob * (double)(1u << b);
+        if (t == floor(t)) return b;
+    }
+    return 32;
+}
+
+static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta)
+{
+    int rc = step_geometry(ctx, g);
+    if (rc) return rc;
+    memset(p, 0, sizeof(*p));
+    p->ens = ctx->d_ens; p->lp = ctx->d_lp; p->beta = ctx->d_beta; p->pparams = ctx->d_params;
+    p->nparams = ctx->nparams; p->stats = ctx->d_stats; p->seed = ctx->seed;
+    p->n = (uint32_t)ctx->n; p->npb = (uint32_t)(ctx->n / nbeta); p->dim = ctx->dim; p->pitch = ctx->pitch;
+    p->nbeta = (uint32_t)nbeta;
+    p->row_bytes = g->row_bytes; p->row_stride = g->row_stride; p->stages = g->stages; p->warps = g->warps;
+    p->flag_words = g->flag_words;
+    p->ntiles = (uint32_t)((ctx->n + 31u) / 32u);
+    p->bij_bits = bij_bits(p->npb);
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
+                                size_t nbeta, uint64_t nsteps)
+{
+    if (!ctx || !ufs || !beta) return SCORUS_ERR_INVALID_ARG;
+    int rc = scorus_check_sample_args(ctx->n, ctx->n, nbeta);
+    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
+    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1 (empty Uniform range panics in the reference)");
+    cudaSetDevice(ctx->device);
+
+    StepParams p;
+    Geometry g;
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    if ((rc = fill_common(ctx, &p, &g, nbeta))) return rc;
+    const double sqrt_a = sqrt(a);
+    p.inv_sqrt_a = 1.0 / sqrt_a;
+    p.z_range = 2.0 * (sqrt_a - p.inv_sqrt_a);  // src/mcmc/utils.rs:42
+    p.flag_kind = (uint32_t)ufs->kind;
+    bool all_flags = false;
+    switch (ufs->kind) {
+    case SCORUS_UFS_ALL: all_flags = true; break;
+    case SCORUS_UFS_PROB:
+        if (!(ufs->prob > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "Prob(p) needs p > 0 (the reference would loop forever)");
+        p.flag_bits = flag_bits_for(ufs->prob);
+        p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(ufs->prob, 1.0) * 4294967296.0)
+                                       : (uint64_t)(fmin(ufs->prob, 1.0) * (double)(1u << p.flag_bits));
+        break;
+    case SCORUS_UFS_ONE_HOT_CYCLE: break;
+    case SCORUS_UFS_MASK: {
+        if (!ufs->mask || ufs->mask_len > ctx->dim) return fail(ctx, SCORUS_ERR_INVALID_ARG, "bad mask");
+        if (nsteps != 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "a host-evaluated mask covers exactly one step");
+        for (size_t i = 0; i < ctx->n; ++i) {
+            size_t c = 0;
+            for (size_t k = 0; k < ufs->mask_len; ++k) c += ufs->mask[i * ufs->mask_len + k] ? 1 : 0;
+            if (c == 0) return fail(ctx, SCORUS_ERR_NPHI_ZERO, "walker %zu has no update flag set", i);
+        }
+        size_t bytes = (size_t)ctx->n * ufs->mask_len;
+        if ((rc = ensure(ctx, (void **)&ctx->d_flags, &ctx->flags_cap, bytes))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_flags, ufs->mask, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        p.flags_in = ctx->d_flags;
+        p.flag_len = (uint32_t)ufs->mask_len;
+        break;
+    }
+    default: return fail(ctx, SCORUS_ERR_INVALID_ARG, "unknown UpdateFlagSpec kind %d", ufs->kind);
+    }
+
+    const bool exact = p.npb <= kExactShuffleMax;
+    if (exact && !ctx->d_order) CU(cudaMalloc(&ctx->d_order, ctx->n * sizeof(uint32_t)));
+    for (uint64_t s = 0; s < nsteps; ++s) {
+        p.step = ctx->step;
+        p.onehot = ctx->onehot;
+        if (exact) {
+            exact_order_kernel<<<(unsigned)nbeta, (p.npb + 31u) & ~31u, 0, ctx->stream>>>(ctx->seed, ctx->step, p.npb, ctx->d_order);
+            ++ctx->launches;
+            p.order = ctx->d_order;
+        }
+        cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
+        ++ctx->launches;
+        ++ctx->step;
+        ctx->proposed += ctx->n;
+        if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n) % ctx->dim;
+    }
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_sample(scorus_ctx *ctx, double a, const scorus_ufs *ufs, uint64_t nsteps)
+{
+    const double one = 1.0;  // src/mcmc/ensemble_sample.rs:104
+    return scorus_sample_pt(ctx, a, ufs, &one, 1, nsteps);
+}
+
+extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_t nbeta, const uint32_t *partner,
+                                      const double *z, const uint8_t *flags, size_t flag_len, const double *u,
+                                      uint8_t *accepted_out)
+{
+    if (!ctx || !beta || !partner || !z || !flags || !u) return SCORUS_ERR_INVALID_ARG;
+    int rc = scorus_check_sample_args(ctx->n, ctx->n, nbeta);
+    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
+    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    if (flag_len > ctx->dim) return fail(ctx, SCORUS_ERR_INVALID_ARG, "flag_len > dim (index panic in the reference)");
+    cudaSetDevice(ctx->device);
+    const size_t n = ctx->n, npb = n / nbeta;
+
+    // the pairing must be a fixed-point-free involution inside each rung (ensemble_sample.rs:135-148)
+    std::vector<uint32_t> order(n);
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        size_t q = partner[i];
+        if (q >= n || q == i || q / npb != i / npb || partner[q] != i)
+            return fail(ctx, SCORUS_ERR_INVALID_ARG, "partner[] is not a within-rung involution at walker %zu", i);
+        if (i < q) { order[k++] = (uint32_t)i; order[k++] = (uint32_t)q; }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        size_t c = 0;
+        for (size_t d = 0; d < flag_len; ++d) c += flags[i * flag_len + d] ? 1 : 0;
+        if (c == 0) return fail(ctx, SCORUS_ERR_NPHI_ZERO, "walker %zu has no update flag set", i);
+    }
+
+    StepParams p;
+    Geometry g;
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    if ((rc = fill_common(ctx, &p, &g, nbeta))) return rc;
+    if (!ctx->d_order) CU(cudaMalloc(&ctx->d_order, n * sizeof(uint32_t)));
+    if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, n * sizeof(double)));
+    if (!ctx->d_u) CU(cudaMalloc(&ctx->d_u, n * sizeof(double)));
+    if (!ctx->d_acc) CU(cudaMalloc(&ctx->d_acc, n));
+    if ((rc = ensure(ctx, (void **)&ctx->d_flags, &ctx->flags_cap, n * (flag_len ? flag_len : 1)))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_order, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_z, z, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_u, u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_flags, flags, n * flag_len, cudaMemcpyHostToDevice, ctx->stream));
+    p.order = ctx->d_order; p.z_in = ctx->d_z; p.u_in = ctx->d_u; p.flags_in = ctx->d_flags;
+    p.flag_len = (uint32_t)flag_len; p.flag_kind = SCORUS_UFS_MASK; p.accepted_out = ctx->d_acc;
+    p.step = ctx->step;
+    cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
+    ++ctx->launches;
+    ctx->proposed += n;
+    if (accepted_out) CU(cudaMemcpyAsync(accepted_out, ctx->d_acc, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // `order` and the caller's arrays are released here
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// draw_z
+// ------------------------------------------------------------------------------------------
+__global__ void draw_z_kernel(uint64_t seed, uint64_t step, double inv_sqrt_a, double range, uint32_t count,
+                              double *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        U4 r = draw(seed, step, ST_ZU, i, 0);
+        out[i] = z_from_uniform(u53(r.x, r.y), inv_sqrt_a, range);
+    }
+}
+
+extern "C" int scorus_draw_z(scorus_ctx *ctx, double a, size_t count, double *out)
+{
+    if (!ctx || !out || count > ctx->n) return SCORUS_ERR_INVALID_ARG;
+    if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1");
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, ctx->n * sizeof(double)));
+    const double sqrt_a = sqrt(a), inv = 1.0 / sqrt_a;
+    draw_z_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(ctx->seed, ctx->step, inv,
+                                                                            2.0 * (sqrt_a - inv), (uint32_t)count, ctx->d_z);
+    ++ctx->launches;
+    ++ctx->step;
+    CU(cudaMemcpyAsync(out, ctx->d_z, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// swap_walkers
+// ------------------------------------------------------------------------------------------
+static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const uint32_t *jvec, const double *r,
+                     uint8_t *swapped_out)
+{
+    const size_t n = ctx->n;
+    if (nbeta == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "nbeta == 0");
+    const size_t npb = n / nbeta;
+    if (npb * nbeta != n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");  // utils.rs:86
+    int rc = scorus_check_beta_order(beta, nbeta);  // utils.rs:91-95, checked before anything moves
+    if (rc) return fail(ctx, rc, "beta list must be in decreasing order");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    cudaSetDevice(ctx->device);
+    if (nbeta == 1) { ++ctx->swap_call; return SCORUS_OK; }  // for i in (1..1).rev() is empty
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    const size_t m = (nbeta - 1) * npb;
+
+    SwapParams sp;
+    memset(&sp, 0, sizeof(sp));
+    if (!ctx->d_src) CU(cudaMalloc(&ctx->d_src, n * sizeof(uint32_t)));
+    if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, n * (size_t)ctx->pitch * sizeof(double)));
+    sp.lp = ctx->d_lp; sp.beta = ctx->d_beta; sp.src = ctx->d_src; sp.stats = ctx->d_stats;
+    sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
+    sp.npb = (uint32_t)npb; sp.nbeta = (uint32_t)nbeta; sp.bij_bits = bij_bits((uint32_t)npb);
+
+    std::vector<uint32_t> jinv;
+    if (jvec) {
+        // caller-supplied draws: invert each stage's permutation on the host (j1 = jvec[s][j2])
+        jinv.assign(m, 0xFFFFFFFFu);
+        for (size_t s = 0; s + 1 < nbeta; ++s)
+            for (size_t j2 = 0; j2 < npb; ++j2) {
+                uint32_t j1 = jvec[s * npb + j2];
+                if (j1 >= npb || jinv[s * npb + j1] != 0xFFFFFFFFu)
+                    return fail(ctx, SCORUS_ERR_INVALID_ARG, "jvec stage %zu is not a permutation", s);
+                jinv[s * npb + j1] = (uint32_t)j2;
+            }
+        if ((rc = ensure(ctx, (void **)&ctx->d_jinv, &ctx->jinv_cap, m * sizeof(uint32_t)))) return rc;
+        if ((rc = ensure(ctx, (void **)&ctx->d_r, &ctx->r_cap, m * sizeof(double)))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_jinv, jinv.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_r, r, m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        sp.jinv = ctx->d_jinv;
+        sp.r_in = ctx->d_r;
+    } else if (npb <= kExactShuffleMax) {
+        if ((rc = ensure(ctx, (void **)&ctx->d_jinv, &ctx->jinv_cap, m * sizeof(uint32_t)))) return rc;
+        exact_jvec_kernel<<<(unsigned)(nbeta - 1), ((unsigned)npb + 31u) & ~31u, 0, ctx->stream>>>(
+            ctx->seed, ctx->swap_call, (uint32_t)npb, (uint32_t)nbeta, ctx->d_jinv);
+        ++ctx->launches;
+        sp.jinv = ctx->d_jinv;
+    }
+    if (swapped_out) {
+        if ((rc = ensure(ctx, (void **)&ctx->d_swapped, &ctx->swapped_cap, m))) return rc;
+        sp.swapped_out = ctx->d_swapped;
+    }
+    swap_chain_kernel<<<(unsigned)((npb + 127) / 128), 128, 0, ctx->stream>>>(sp);
+    ++ctx->launches;
+    const uint32_t vpr = ctx->pitch / 2;
+    const size_t total = n * (size_t)vpr;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    unsigned cap = (unsigned)ctx->num_sms * 16u;
+    if (blocks > cap) blocks = cap;
+    permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
+                                                         (uint32_t)n, vpr, 0);
+    permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
+                                                         (uint32_t)n, vpr, 1);
+    ctx->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap launch: %s", cudaGetErrorString(e));
+    ++ctx->swap_call;
+    ctx->swap_proposed += m;
+    if (swapped_out) CU(cudaMemcpyAsync(swapped_out, ctx->d_swapped, m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (jvec || swapped_out) CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_swap_walkers(scorus_ctx *ctx, const double *beta, size_t nbeta)
+{
+    if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
+    return swap_impl(ctx, beta, nbeta, nullptr, nullptr, nullptr);
+}
+
+extern "C" int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta, size_t nbeta, const uint32_t *jvec,
+                                         const double *r, uint8_t *swapped_out)
+{
+    if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
+    if (nbeta > 1 && (!jvec || !r)) return SCORUS_ERR_INVALID_ARG;
+    return swap_impl(ctx, beta, nbeta, nbeta > 1 ? jvec : nullptr, r, swapped_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// literal drop-ins on host buffers
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                     const scorus_ufs *ufs, const double *beta, size_t nbeta)
+{
+    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    int rc = scorus_check_sample_args(ctx->n, lp_len, nbeta);
+    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
+    if ((rc = scorus_upload(ctx, ens, lp))) return rc;
+    if ((rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, 1))) return rc;
+    return scorus_download(ctx, ens, lp);
+}
+
+extern "C" int scorus_swap_walkers_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len,
+                                        const double *beta, size_t nbeta)
+{
+    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    if (nbeta == 0) return SCORUS_ERR_INVALID_ARG;
+    if ((ctx->n / nbeta) * nbeta != ctx->n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
+    if (lp_len != ctx->n) return SCORUS_OK;  // src/mcmc/utils.rs:88: silently does nothing
+    int rc = scorus_check_beta_order(beta, nbeta);
+    if (rc) return fail(ctx, rc, "beta list must be in decreasing order");
+    if ((rc = scorus_upload(ctx, ens, lp))) return rc;
+    if ((rc = scorus_swap_walkers(ctx, beta, nbeta))) return rc;
+    return scorus_download(ctx, ens, lp);
+}

@@ -1,0 +1,424 @@
+"""Host-side mirror of scorus::mcmc::ensemble_sample (src/mcmc/ensemble_sample.rs) over the C ABI.
+
+Same names and argument order as the reference:
+
+    init_logprob(flogprob, ensemble, logprob)                                   # :77
+    sample(flogprob, ensemble, cached_logprob, rng, a, ufs)                      # :87
+    sample_pt(flogprob, ensemble, cached_logprob, rng, a, ufs, beta_list)        # :107
+    propose_move(p1, p2, z, update_flags)                                        # :57
+    UpdateFlagSpec.Prob(p) / .All() / .Func(f)                                   # :25
+
+with two substitutions the device forces:
+  * `flogprob` is a registered device plugin (`LogProb` instances below) instead of a closure;
+  * `rng` is a `DeviceRng(seed)`: the key of the counter-based device streams.  It also caches
+    the device context, so repeated calls on same-shaped ensembles reuse their device buffers.
+
+`ensemble` / `cached_logprob` are numpy float64 arrays [n, dim] / [n], updated in place like the
+reference's `&mut` slices.  Where the reference panics, these raise `McmcErr`
+(src/mcmc/mcmc_errors.rs) or ValueError.  Long runs should keep the state on the device with
+`Sampler` and download when needed; the free functions move the ensemble both ways per call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class McmcErr(RuntimeError):
+    """src/mcmc/mcmc_errors.rs:1-7; `.code` is the C ABI status."""
+
+    NAMES = {1: "NWalkersIsZero", 2: "NWalkersIsNotEven", 3: "NWalkersMismatchesNBeta", 4: "BetaNotInDecrOrd"}
+
+    def __init__(self, code: int, msg: str = ""):
+        self.code = code
+        self.variant = self.NAMES.get(code)
+        super().__init__(f"{self.variant or 'status ' + str(code)}: {msg}")
+
+
+def _raise(code: int, ctx=None):
+    if code == L.OK:
+        return
+    lib = L.load()
+    msg = lib.scorus_status_string(code).decode()
+    if ctx is not None:
+        detail = lib.scorus_last_error(ctx).decode()
+        if detail:
+            msg = f"{msg} ({detail})"
+    if 1 <= code <= 4:
+        raise McmcErr(code, msg)
+    if code == L.ERR_LENGTH_MISMATCH:
+        raise AssertionError(msg)  # assert!(ensemble.len() == cached_logprob.len()), :133
+    if code in (L.ERR_CUDA, L.ERR_NO_DEVICE):
+        raise RuntimeError(msg)
+    raise ValueError(msg)
+
+
+# ------------------------------------------------------------------------------------------------
+# log-density plugins (replace the `flogprob: &F` closure)
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class LogProb:
+    kind: int
+    params: tuple = ()
+
+    def param_array(self) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(self.params, dtype=np.float64).ravel())
+
+
+def Gaussian(c: float = 0.5) -> LogProb:
+    """-sum c x^2: examples/test_emcee.rs:18-24 (c=1/2), examples/sample_high_dim.rs:22-28 (c=1)."""
+    return LogProb(L.LP_GAUSSIAN, (float(c),))
+
+
+def BoundedGaussian(limit: float = 1.5) -> LogProb:
+    """examples/sample_bimodal.rs:35-44"""
+    return LogProb(L.LP_BOUNDED_GAUSSIAN, (float(limit),))
+
+
+def Rosenbrock() -> LogProb:
+    """examples/test_emcee.rs:26-32"""
+    return LogProb(L.LP_ROSENBROCK)
+
+
+def Rastrigin(a: float = 10.0) -> LogProb:
+    """examples/sample_rastrigin.rs:17-25"""
+    return LogProb(L.LP_RASTRIGIN, (float(a),))
+
+
+def Bimodal2d(*params: float) -> LogProb:
+    """examples/sample_bimodal.rs:46-54 (optionally the 9 constants)."""
+    return LogProb(L.LP_BIMODAL2D, tuple(float(p) for p in params))
+
+
+def Step2d() -> LogProb:
+    """examples/sample_bimodal.rs:56-65"""
+    return LogProb(L.LP_STEP2D)
+
+
+def CorrGaussian(mu, Lfac) -> LogProb:
+    """-0.5 |L (x - mu)|^2 with L^T L the precision matrix (BASELINE config 2; not in the reference)."""
+    mu = np.asarray(mu, dtype=np.float64).ravel()
+    Lfac = np.asarray(Lfac, dtype=np.float64)
+    assert Lfac.shape == (mu.size, mu.size)
+    return LogProb(L.LP_CORR_GAUSSIAN, tuple(np.concatenate([mu, Lfac.ravel()]).tolist()))
+
+
+def Mixture(sigma1: float, sigma2: float, m) -> LogProb:
+    """logsumexp of N(+m, sigma1^2 I) and N(-m, sigma2^2 I) up to constants (BASELINE config 3)."""
+    m = np.asarray(m, dtype=np.float64).ravel()
+    return LogProb(L.LP_MIXTURE, (float(sigma1), float(sigma2)) + tuple(m.tolist()))
+
+
+# ------------------------------------------------------------------------------------------------
+# UpdateFlagSpec (:25-55)
+# ------------------------------------------------------------------------------------------------
+class UpdateFlagSpec:
+    """enum UpdateFlagSpec { Prob(T), All, Func(&mut dyn FnMut() -> Vec<bool>) }"""
+
+    def __init__(self, kind: int, prob: float = 0.0, func: Optional[Callable[[], Sequence[bool]]] = None):
+        self.kind, self.prob, self.func = kind, prob, func
+
+    @classmethod
+    def Prob(cls, p: float) -> "UpdateFlagSpec":
+        return cls(L.UFS_PROB, prob=float(p))
+
+    @classmethod
+    def All(cls) -> "UpdateFlagSpec":
+        return cls(L.UFS_ALL)
+
+    @classmethod
+    def Func(cls, f: Callable[[], Sequence[bool]]) -> "UpdateFlagSpec":
+        """General closure: called once per walker per step on the host (:150-153), the flags are
+        uploaded as a byte matrix.  For the cycling one-hot closure of
+        examples/sample_high_dim.rs:59-65 use OneHotCycle(), which stays on the device."""
+        return cls(L.UFS_MASK, func=f)
+
+    @classmethod
+    def OneHotCycle(cls) -> "UpdateFlagSpec":
+        return cls(L.UFS_ONE_HOT_CYCLE)
+
+    def _c(self, n: int, dim: int):
+        """-> (Ufs struct, keepalive)"""
+        u = L.Ufs()
+        u.kind = self.kind
+        u.prob = self.prob
+        keep = None
+        if self.kind == L.UFS_MASK:
+            rows = [np.asarray(self.func(), dtype=bool) for _ in range(n)]
+            lens = {r.size for r in rows}
+            if len(lens) != 1:
+                raise ValueError("Func must return flag vectors of one length per step")
+            flen = lens.pop()
+            if flen > dim:
+                raise IndexError("update_flags longer than the walker (index panic, :70)")
+            keep = np.ascontiguousarray(np.stack(rows).astype(np.uint8))
+            u.mask = keep.ctypes.data_as(C.POINTER(C.c_uint8))
+            u.mask_len = flen
+        return u, keep
+
+
+# ------------------------------------------------------------------------------------------------
+# device context
+# ------------------------------------------------------------------------------------------------
+def _dp(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _check_arrays(ensemble: np.ndarray, logprob: Optional[np.ndarray]):
+    if not (isinstance(ensemble, np.ndarray) and ensemble.dtype == np.float64 and ensemble.ndim == 2
+            and ensemble.flags.c_contiguous):
+        raise TypeError("ensemble must be a C-contiguous float64 array [n_walkers, dim]")
+    if logprob is not None and not (isinstance(logprob, np.ndarray) and logprob.dtype == np.float64
+                                    and logprob.ndim == 1 and logprob.flags.c_contiguous):
+        raise TypeError("logprob must be a C-contiguous float64 array [n_walkers]")
+
+
+class Sampler:
+    """RAII handle over scorus_ctx: the device-resident (ensemble, logprob) plus RNG counters."""
+
+    def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, seed: int = 0, device: int = -1):
+        self._lib = L.load()
+        self._ctx = C.c_void_p()
+        cfg = L.Cfg(n_walkers=n_walkers, dim=dim, device=device, seed=seed, flags=0, reserved=0)
+        _raise(self._lib.scorus_ctx_create(C.byref(self._ctx), C.byref(cfg)))
+        self.n, self.dim, self.seed = n_walkers, dim, seed
+        self.flogprob = None
+        self.set_logprob(flogprob)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.scorus_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ok(self, code: int):
+        _raise(code, self._ctx)
+
+    # -- configuration
+    def set_logprob(self, flogprob: LogProb):
+        if flogprob is self.flogprob:
+            return
+        p = flogprob.param_array()
+        self._ok(self._lib.scorus_set_logprob(self._ctx, flogprob.kind, _dp(p) if p.size else None, p.size))
+        self.flogprob = flogprob
+
+    def set_stream(self, cuda_stream: int):
+        self._ok(self._lib.scorus_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    # -- data movement
+    def upload(self, ensemble: np.ndarray, logprob: Optional[np.ndarray] = None):
+        _check_arrays(ensemble, logprob)
+        if ensemble.shape != (self.n, self.dim):
+            raise ValueError("ensemble shape does not match the sampler")
+        if logprob is not None and logprob.shape[0] != self.n:
+            raise AssertionError("ensemble and logprob lengths differ")
+        self._ok(self._lib.scorus_upload(self._ctx, _dp(ensemble), _dp(logprob)))
+        self._ok(self._lib.scorus_sync(self._ctx))
+
+    def download(self, ensemble: Optional[np.ndarray] = None, logprob: Optional[np.ndarray] = None):
+        if ensemble is None:
+            ensemble = np.empty((self.n, self.dim))
+        if logprob is None:
+            logprob = np.empty(self.n)
+        _check_arrays(ensemble, logprob)
+        self._ok(self._lib.scorus_download(self._ctx, _dp(ensemble), _dp(logprob)))
+        return ensemble, logprob
+
+    # -- the hot path
+    def init_logprob(self):
+        self._ok(self._lib.scorus_init_logprob(self._ctx))
+
+    def sample_pt(self, a: float, ufs: UpdateFlagSpec, beta_list, nsteps: int = 1):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if ufs.kind == L.UFS_MASK:
+            for _ in range(nsteps):
+                u, keep = ufs._c(self.n, self.dim)
+                self._ok(self._lib.scorus_sample_pt(self._ctx, a, C.byref(u), _dp(beta), beta.size, 1))
+            return
+        u, keep = ufs._c(self.n, self.dim)
+        self._ok(self._lib.scorus_sample_pt(self._ctx, a, C.byref(u), _dp(beta), beta.size, nsteps))
+
+    def sample(self, a: float, ufs: UpdateFlagSpec, nsteps: int = 1):
+        self.sample_pt(a, ufs, [1.0], nsteps)
+
+    def sample_pt_fixed(self, beta_list, partner, z, flags, u):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        partner = np.ascontiguousarray(partner, dtype=np.uint32)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        if partner.shape != (self.n,) or z.shape != (self.n,) or u.shape != (self.n,) or flags.shape[0] != self.n:
+            raise ValueError("stream arrays must have one entry per walker")
+        flag_len = flags.shape[1] if flags.ndim == 2 else self.dim
+        acc = np.zeros(self.n, dtype=np.uint8)
+        self._ok(self._lib.scorus_sample_pt_fixed(
+            self._ctx, _dp(beta), beta.size, partner.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(z),
+            flags.ctypes.data_as(C.POINTER(C.c_uint8)), flag_len, _dp(u),
+            acc.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return acc
+
+    def draw_z(self, a: float, count: int = 1) -> np.ndarray:
+        out = np.empty(count)
+        self._ok(self._lib.scorus_draw_z(self._ctx, a, count, _dp(out)))
+        return out
+
+    def swap_walkers(self, beta_list):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        self._ok(self._lib.scorus_swap_walkers(self._ctx, _dp(beta), beta.size))
+
+    def swap_walkers_fixed(self, beta_list, jvec, r):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        jvec = np.ascontiguousarray(jvec, dtype=np.uint32)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        sw = np.zeros(max(jvec.size, 1), dtype=np.uint8)
+        self._ok(self._lib.scorus_swap_walkers_fixed(
+            self._ctx, _dp(beta), beta.size, jvec.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(r),
+            sw.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return sw[:jvec.size].reshape(jvec.shape)
+
+    def sample_pt_host(self, ensemble, logprob, a, ufs: UpdateFlagSpec, beta_list):
+        """One reference-shaped call: host buffers in, one step, host buffers out."""
+        _check_arrays(ensemble, logprob)
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        u, keep = ufs._c(self.n, self.dim)
+        self._ok(self._lib.scorus_sample_pt_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0], a,
+                                                 C.byref(u), _dp(beta), beta.size))
+
+    def swap_walkers_host(self, ensemble, logprob, beta_list):
+        _check_arrays(ensemble, logprob)
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        self._ok(self._lib.scorus_swap_walkers_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0],
+                                                    _dp(beta), beta.size))
+
+    # -- plumbing
+    def sync(self):
+        self._ok(self._lib.scorus_sync(self._ctx))
+
+    @property
+    def counters(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ok(self._lib.scorus_get_counters(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    @counters.setter
+    def counters(self, v):
+        self._ok(self._lib.scorus_set_counters(self._ctx, int(v[0]), int(v[1]), int(v[2])))
+
+    def stats(self):
+        v = [C.c_uint64() for _ in range(4)]
+        self._ok(self._lib.scorus_get_stats(self._ctx, *[C.byref(x) for x in v]))
+        return dict(accepted=v[0].value, proposed=v[1].value, swapped=v[2].value, swap_proposed=v[3].value)
+
+    @property
+    def launch_count(self) -> int:
+        return self._lib.scorus_launch_count(self._ctx)
+
+    def device_buffers(self):
+        e, lp, pitch = C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.c_size_t()
+        self._ok(self._lib.scorus_device_buffers(self._ctx, C.byref(e), C.byref(pitch), C.byref(lp)))
+        return C.cast(e, C.c_void_p).value, pitch.value, C.cast(lp, C.c_void_p).value
+
+
+@dataclass
+class DeviceRng:
+    """Stands in for the reference's `rng: &mut U`: the seed of the device streams.  Caches one
+    Sampler per (n, dim, plugin) so the free functions below do not re-create device state."""
+    seed: int = 0
+    device: int = -1
+    _samplers: dict = field(default_factory=dict, repr=False)
+
+    def sampler(self, flogprob: LogProb, n: int, dim: int) -> Sampler:
+        key = (n, dim)
+        s = self._samplers.get(key)
+        if s is None:
+            s = Sampler(flogprob, n, dim, seed=self.seed, device=self.device)
+            self._samplers[key] = s
+        else:
+            s.set_logprob(flogprob)
+        return s
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array over pinned host memory (scorus_host_alloc) for full-speed host calls."""
+    lib = L.load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.scorus_host_alloc(n)
+    if not p:
+        raise MemoryError("scorus_host_alloc failed")
+    buf = (C.c_char * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED: dict = {}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's free functions
+# ------------------------------------------------------------------------------------------------
+def init_logprob(flogprob: LogProb, ensemble: np.ndarray, logprob: np.ndarray, rng: Optional[DeviceRng] = None):
+    """src/mcmc/ensemble_sample.rs:77-85"""
+    _check_arrays(ensemble, logprob)
+    if logprob.shape[0] != ensemble.shape[0]:
+        raise ValueError("copy_from_slice: source and destination lengths differ")  # :84
+    rng = rng or DeviceRng()
+    s = rng.sampler(flogprob, *ensemble.shape)
+    s.upload(ensemble, None)
+    s.download(None, logprob)
+
+
+def sample_pt(flogprob: LogProb, ensemble: np.ndarray, cached_logprob: np.ndarray, rng: DeviceRng, a: float,
+              ufs: UpdateFlagSpec, beta_list):
+    """src/mcmc/ensemble_sample.rs:107-190, in place on the host arrays."""
+    _check_arrays(ensemble, cached_logprob)
+    n = ensemble.shape[0]
+    nb = len(beta_list)
+    _raise(L.load().scorus_check_sample_args(n, cached_logprob.shape[0], nb))
+    s = rng.sampler(flogprob, *ensemble.shape)
+    s.sample_pt_host(ensemble, cached_logprob, a, ufs, beta_list)
+
+
+def sample(flogprob: LogProb, ensemble: np.ndarray, cached_logprob: np.ndarray, rng: DeviceRng, a: float,
+           ufs: UpdateFlagSpec):
+    """src/mcmc/ensemble_sample.rs:87-105"""
+    sample_pt(flogprob, ensemble, cached_logprob, rng, a, ufs, [1.0])
+
+
+def propose_move(p1, p2, z: float, update_flags=None) -> np.ndarray:
+    """src/mcmc/ensemble_sample.rs:57-75, evaluated by the fused step kernel on a two-walker
+    ensemble with the accept forced (u = 0 < q for any finite log-density)."""
+    p1 = np.ascontiguousarray(p1, dtype=np.float64)
+    p2 = np.ascontiguousarray(p2, dtype=np.float64)
+    d = p1.size
+    ens = np.ascontiguousarray(np.stack([p1, p2]))
+    if update_flags is None:
+        fl = np.ones((2, d), dtype=np.uint8)
+    else:
+        f = np.asarray(update_flags, dtype=np.uint8)
+        fl = np.ascontiguousarray(np.stack([f, f]))
+    with Sampler(LogProb(L.LP_GAUSSIAN, (0.0,)), 2, d) as s:
+        s.upload(ens, np.zeros(2))
+        s.sample_pt_fixed([1.0], [1, 0], [z, z], fl if fl.any() else np.ones((2, d), dtype=np.uint8),
+                          [0.0, 0.0])
+        out, _ = s.download()
+    if update_flags is not None and not fl.any():
+        return p1.copy()
+    return out[0]

@@ -1,0 +1,83 @@
+"""Generates tests/golden/*.npz: fixed-stream known-answer vectors for the hot path.
+
+The reference ships no golden vectors for this path and cannot be built here (SURVEY.md 0.6,
+8c), so these are produced by the C oracle (oracle/scorus_oracle.c) and cross-checked, before
+being written, against the independent numpy restatement (oracle/numpy_oracle.py): a case is
+only saved if both agree bit for bit.  Re-run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import numpy_oracle as no  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# name, plugin kind, params, n, dim, nbeta, ufs, prob, steps, init box, seed
+CASES = [
+    ("c1_test_emcee_gaussian", po.LP_GAUSSIAN, [0.5], 16, 2, 1, po.UFS_PROB, 0.5, 40, (0.9, 1.1), 1),
+    ("rosenbrock_d8_pt2", po.LP_ROSENBROCK, [], 24, 8, 2, po.UFS_PROB, 0.5, 12, (0.9, 1.1), 2),
+    ("rastrigin_d10_pt4", po.LP_RASTRIGIN, [10.0], 32, 10, 4, po.UFS_PROB, 0.2, 12, (-0.01, 0.01), 4),
+    ("high_dim_onehot_pt4", po.LP_GAUSSIAN, [1.0], 80, 10, 4, po.UFS_ONE_HOT_CYCLE, 0.0, 10, (-1.0, 1.0), 5),
+    ("bimodal2d_pt8", po.LP_BIMODAL2D, [], 32, 2, 8, po.UFS_PROB, 0.5, 20, None, 6),
+    ("bounded_gaussian_all", po.LP_BOUNDED_GAUSSIAN, [1.5], 20, 3, 1, po.UFS_ALL, 0.0, 12, (-1.4, 1.4), 7),
+    ("mixture_d5", po.LP_MIXTURE, [1.0, 2.0, 5.0, 0.0, 0.0, 0.0, 0.0], 16, 5, 1, po.UFS_PROB, 0.5, 10, (-6.0, 6.0), 8),
+    ("corr_gaussian_d7_odd", po.LP_CORR_GAUSSIAN, None, 12, 7, 1, po.UFS_ALL, 0.0, 8, (-1.0, 1.0), 9),
+]
+
+BIMODAL_TABLE = [[0.10, 0.20], [0.20, 0.10], [0.23, 0.21], [0.03, 0.22], [0.10, 0.20], [0.20, 0.24],
+                 [0.20, 0.12], [0.23, 0.12]]  # examples/sample_bimodal.rs:68-101 (tiled 4x)
+
+
+def ar1_factor(d, rho):
+    """Upper-triangular L with L^T L = Sigma^-1 for Sigma_ij = rho^|i-j|."""
+    cov = rho ** np.abs(np.subtract.outer(np.arange(d), np.arange(d)))
+    prec = np.linalg.inv(cov)
+    return np.linalg.cholesky(prec).T
+
+
+def make(case):
+    name, kind, params, n, dim, nb, ufs, prob, steps, box, seed = case
+    g = po.Rng(seed)
+    if kind == po.LP_CORR_GAUSSIAN:
+        params = np.concatenate([np.linspace(-0.5, 0.5, dim), ar1_factor(dim, 0.9).ravel()])
+    params = np.asarray(params, dtype=np.float64)
+    if box is None:
+        ens = np.ascontiguousarray(np.tile(np.array(BIMODAL_TABLE), (n // 8, 1)))
+    else:
+        ens = np.array([[box[0] + g.uniform() * (box[1] - box[0]) for _ in range(dim)] for _ in range(n)])
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    lp = po.init_logprob(kind, params, ens)
+    assert np.array_equal(lp, no.logprob(kind, params, ens), equal_nan=True), name
+    out = dict(kind=kind, params=params, beta=beta, a=2.0, ens0=ens.copy(), lp0=lp.copy())
+    partners, zs, flagss, us, accs, enss, lps, jvecs, rs, sws = [], [], [], [], [], [], [], [], [], []
+    onehot = 0
+    for k in range(steps):
+        if nb > 1 and k % 10 == 0:  # examples/sample_rastrigin.rs:51-53: swap before every 10th step
+            jvec, r = po.draw_swap_streams(g, n, nb)
+            e2, l2, s2 = no.swap_walkers_fixed(ens, lp, beta, jvec, r)
+            rc, s1 = po.swap_walkers_fixed(ens, lp, beta, jvec, r)
+            assert rc == 0 and np.array_equal(s1, s2) and np.array_equal(ens, e2) and np.array_equal(lp, l2, equal_nan=True), name
+            jvecs.append(jvec); rs.append(r); sws.append(s1)
+        partner, z, flags, u, onehot = po.draw_sample_streams(g, n, dim, nb, 2.0, ufs, prob, onehot)
+        e2, l2, a2 = no.sample_pt_fixed(kind, params, ens, lp, beta, partner, z, flags, u)
+        rc, a1 = po.sample_pt_fixed(kind, params, ens, lp, beta, partner, z, flags, u)
+        assert rc == 0 and np.array_equal(a1, a2) and np.array_equal(ens, e2) and np.array_equal(lp, l2, equal_nan=True), (name, k)
+        partners.append(partner); zs.append(z); flagss.append(flags); us.append(u); accs.append(a1)
+        enss.append(ens.copy()); lps.append(lp.copy())
+    out.update(partner=np.stack(partners), z=np.stack(zs), flags=np.stack(flagss), u=np.stack(us),
+               accepted=np.stack(accs), ens=np.stack(enss), lp=np.stack(lps))
+    if jvecs:
+        out.update(jvec=np.stack(jvecs), r=np.stack(rs), swapped=np.stack(sws))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: n={n} dim={dim} nbeta={nb} steps={steps} accept={np.mean(accs):.3f}")
+
+
+if __name__ == "__main__":
+    po.build()
+    for c in CASES:
+        make(c)

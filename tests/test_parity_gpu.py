@@ -1,0 +1,206 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle and the golden vectors.
+
+Bar (BASELINE.json north_star): fed identical partner / z / flags / u, accept decisions and
+partner handling match bit for bit, positions and log-probs agree within 1e-12 relative in fp64
+(positions are in fact bit-identical: the kernel rounds x1*z, x2*(1-z) and their sum separately,
+as src/mcmc/utils.rs:55 does; log-probs of the transcendental-free targets are bit-identical too).
+"""
+import numpy as np
+import pytest
+
+from tests.util import assert_lp_close, golden_files
+
+pytestmark = pytest.mark.gpu
+
+
+def _box(rng, n, d, lo, hi):
+    return np.ascontiguousarray(rng.uniform(lo, hi, (n, d)))
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_fixed_stream(sb, path):
+    g = np.load(path)
+    kind, params, beta = int(g["kind"]), g["params"], g["beta"]
+    n, dim = g["ens0"].shape
+    nb = beta.size
+    with sb.Sampler(sb.LogProb(kind, tuple(params.tolist())), n, dim, seed=0) as s:
+        s.upload(np.ascontiguousarray(g["ens0"]), np.ascontiguousarray(g["lp0"]))
+        nswap = 0
+        for k in range(g["z"].shape[0]):
+            if nb > 1 and k % 10 == 0:
+                sw = s.swap_walkers_fixed(beta, g["jvec"][nswap], g["r"][nswap])
+                assert np.array_equal(sw, g["swapped"][nswap]), f"swap decisions differ at step {k}"
+                nswap += 1
+            acc = s.sample_pt_fixed(beta, g["partner"][k], g["z"][k], g["flags"][k], g["u"][k])
+            ens, lp = s.download()
+            assert np.array_equal(acc, g["accepted"][k]), f"accept mask differs at step {k}"
+            assert np.array_equal(ens, g["ens"][k]), f"positions differ at step {k}"
+            assert_lp_close(kind, params, ens, lp, g["lp"][k])
+
+
+SHAPES = [
+    # kind, params, n, dim, nbeta, init box
+    (0, [0.5], 64, 2, 1, (-1, 1)),
+    (0, [1.0], 4096, 64, 1, (-1, 1)),
+    (2, [], 2048, 64, 1, (0.9, 1.1)),
+    (2, [], 96, 200, 4, (0.9, 1.1)),      # examples/test_emcee.rs: 200-D rosenbrock
+    (2, [], 70, 33, 1, (0.9, 1.1)),       # odd dim, ragged tail tile
+    (3, [10.0], 4096, 10, 64, (-0.5, 0.5)),
+    (1, [1.5], 512, 5, 2, (-1.6, 1.6)),   # -inf proposals and -inf starts
+    (4, [], 256, 2, 8, None),
+    (5, [], 128, 3, 2, (-0.1, 1.1)),
+    (7, None, 1024, 32, 1, (-6, 6)),
+    (6, None, 256, 12, 1, (-1, 1)),
+]
+
+
+def _params_for(kind, params, dim, rng):
+    if kind == 7:
+        m = np.zeros(dim); m[0] = 5.0
+        return np.concatenate([[1.0, 2.0], m])
+    if kind == 6:
+        L = np.triu(rng.normal(size=(dim, dim))) * 0.3 + np.eye(dim)
+        return np.concatenate([rng.normal(size=dim) * 0.1, L.ravel()])
+    return np.asarray(params, dtype=np.float64)
+
+
+@pytest.mark.parametrize("case", SHAPES, ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}")
+@pytest.mark.parametrize("ufs", ["prob", "all", "short"])
+def test_fixed_stream_vs_oracle(sb, oracle, case, ufs):
+    kind, params, n, dim, nb, box = case
+    rng = np.random.default_rng(1000 * kind + dim)
+    params = _params_for(kind, params, dim, rng)
+    if box is None:
+        ens = np.ascontiguousarray(np.c_[rng.uniform(-16, 16, n), rng.uniform(-0.1, 1.1, n)])
+    else:
+        ens = _box(rng, n, dim, *box)
+    beta = 2.0 ** -(np.arange(nb) / max(1, nb // 8))
+    g = oracle.Rng(kind * 7 + dim)
+    lp = oracle.init_logprob(kind, params, ens)
+    with sb.Sampler(sb.LogProb(kind, tuple(params.tolist())), n, dim, seed=0) as s:
+        s.upload(ens, None)                       # device init_logprob (K2)
+        _, lp_dev = s.download()
+        assert_lp_close(kind, params, ens, lp_dev, lp)
+        s.upload(ens, lp)
+        for step in range(6):
+            ukind = oracle.UFS_ALL if ufs == "all" else oracle.UFS_PROB
+            partner, z, flags, u, _ = oracle.draw_sample_streams(g, n, dim, nb, 2.0, ukind, 0.3)
+            if ufs == "short" and dim > 1:
+                flags = np.ascontiguousarray(flags[:, : max(1, dim // 2)])  # Func returning fewer flags (:68)
+                flags[:, 0] |= (flags.sum(axis=1) == 0).astype(np.uint8)
+            want_e, want_lp = ens.copy(), lp.copy()
+            rc, want_acc = oracle.sample_pt_fixed(kind, params, want_e, want_lp, beta, partner, z, flags, u)
+            assert rc == 0
+            acc = s.sample_pt_fixed(beta, partner, z, flags, u)
+            got_e, got_lp = s.download()
+            assert np.array_equal(acc, want_acc), f"accept mask differs at step {step}: {np.flatnonzero(acc != want_acc)[:8]}"
+            assert np.array_equal(got_e, want_e), f"positions differ at step {step}"
+            assert_lp_close(kind, params, got_e, got_lp, want_lp)
+            ens, lp = want_e, want_lp
+            if nb > 1:
+                jvec, r = oracle.draw_swap_streams(g, n, nb)
+                rc, want_sw = oracle.swap_walkers_fixed(ens, lp, beta, jvec, r)
+                assert rc == 0
+                sw = s.swap_walkers_fixed(beta, jvec, r)
+                got_e, got_lp = s.download()
+                assert np.array_equal(sw, want_sw), f"swap decisions differ at step {step}"
+                assert np.array_equal(got_e, ens), f"positions after swap differ at step {step}"
+                assert_lp_close(kind, params, got_e, got_lp, lp)
+
+
+@pytest.mark.parametrize("case", [(0, [0.5], 16, 2, 1), (2, [], 4096, 64, 1), (3, [10.0], 2048, 10, 8),
+                                  (2, [], 8192, 16, 2), (0, [1.0], 320, 10, 4)],
+                         ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}")
+@pytest.mark.parametrize("ufs", ["prob0.5", "prob0.2", "all", "onehot"])
+def test_philox_mode_replays_through_oracle(sb, oracle, case, ufs):
+    """The device draws its own streams (Philox); the oracle regenerates the same streams on the
+    CPU (oracle/philox_streams.c) and replays the step: results must agree as in fixed mode."""
+    kind, params, n, dim, nb = case
+    rng = np.random.default_rng(5)
+    params = np.asarray(params, dtype=np.float64)
+    ens = _box(rng, n, dim, 0.5, 1.5) if kind == 2 else _box(rng, n, dim, -1, 1)
+    lp = oracle.init_logprob(kind, params, ens)
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    seed = 12345 + n
+    spec = {"prob0.5": sb.UpdateFlagSpec.Prob(0.5), "prob0.2": sb.UpdateFlagSpec.Prob(0.2),
+            "all": sb.UpdateFlagSpec.All(), "onehot": sb.UpdateFlagSpec.OneHotCycle()}[ufs]
+    okind = {"prob0.5": oracle.UFS_PROB, "prob0.2": oracle.UFS_PROB, "all": oracle.UFS_ALL,
+             "onehot": oracle.UFS_ONE_HOT_CYCLE}[ufs]
+    prob = 0.2 if ufs == "prob0.2" else 0.5
+    with sb.Sampler(sb.LogProb(kind, tuple(params.tolist())), n, dim, seed=seed) as s:
+        s.upload(ens, lp)
+        for k in range(8):
+            if nb > 1 and k % 4 == 0:
+                _, swap_call, _ = s.counters
+                jvec, r = oracle.philox_swap_streams(seed, swap_call, n, nb)
+                rc, _ = oracle.swap_walkers_fixed(ens, lp, beta, jvec, r)
+                assert rc == 0
+                s.swap_walkers(beta)
+            step, _, onehot = s.counters
+            partner, z, flags, u = oracle.philox_sample_streams(seed, step, n, dim, nb, 2.0, okind, prob, onehot)
+            rc, _ = oracle.sample_pt_fixed(kind, params, ens, lp, beta, partner, z, flags, u)
+            assert rc == 0
+            s.sample_pt(2.0, spec, beta, 1)
+            got_e, got_lp = s.download()
+            assert np.array_equal(got_e, ens), f"positions differ at step {k}"
+            assert_lp_close(kind, params, got_e, got_lp, lp)
+        st = s.stats()
+        assert st["proposed"] == 8 * n and 0 < st["accepted"] <= st["proposed"]
+
+
+def test_errors_mirror_mcmc_err(sb):
+    with sb.Sampler(sb.Gaussian(), 12, 2) as s:
+        s.upload(np.zeros((12, 2)) + 0.1, None)
+        with pytest.raises(sb.McmcErr) as e:
+            s.sample_pt(2.0, sb.UpdateFlagSpec.All(), [1.0, 0.5, 0.25, 0.125, 0.0625], 1)  # 12 % 5 != 0
+        assert e.value.variant == "NWalkersMismatchesNBeta"
+        with pytest.raises(sb.McmcErr) as e:
+            s.sample_pt(2.0, sb.UpdateFlagSpec.All(), [1.0, 0.5, 0.25, 0.125], 1)          # 3 per rung
+        assert e.value.variant == "NWalkersIsNotEven"
+        with pytest.raises(sb.McmcErr) as e:
+            s.swap_walkers([0.5, 1.0])
+        assert e.value.variant == "BetaNotInDecrOrd"
+        s.swap_walkers([1.0, 1.0])  # equal betas are tolerated (utils.rs:93)
+        with pytest.raises(ValueError):
+            s.sample_pt_fixed([1.0], np.arange(12), np.ones(12), np.ones((12, 2)), np.zeros(12))  # not an involution
+        with pytest.raises(ValueError):
+            s.sample_pt_fixed([1.0], np.arange(12) ^ 1, np.ones(12), np.zeros((12, 2)), np.zeros(12))  # nphi == 0
+
+
+def test_free_functions_reference_call_shape(sb, oracle):
+    """sample / sample_pt / swap_walkers / init_logprob with the reference's argument order."""
+    n, dim, nb = 64, 4, 4
+    rng = np.random.default_rng(0)
+    ens = _box(rng, n, dim, -1, 1)
+    lp = np.empty(n)
+    dev = sb.DeviceRng(seed=99)
+    f = sb.Gaussian(1.0)
+    sb.init_logprob(f, ens, lp, dev)
+    assert np.array_equal(lp, oracle.init_logprob(0, [1.0], ens))
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    ref_e, ref_lp = ens.copy(), lp.copy()
+    for k in range(5):
+        smp = dev.sampler(f, n, dim)
+        step, swap_call, onehot = smp.counters
+        if k % 2 == 0:
+            jvec, r = oracle.philox_swap_streams(99, swap_call, n, nb)
+            oracle.swap_walkers_fixed(ref_e, ref_lp, beta, jvec, r)
+            sb.swap_walkers(ens, lp, dev, beta)
+        partner, z, flags, u = oracle.philox_sample_streams(99, step, n, dim, nb, 2.0, oracle.UFS_PROB, 0.5, onehot)
+        oracle.sample_pt_fixed(0, [1.0], ref_e, ref_lp, beta, partner, z, flags, u)
+        sb.sample_pt(f, ens, lp, dev, 2.0, sb.UpdateFlagSpec.Prob(0.5), beta)
+        assert np.array_equal(ens, ref_e) and np.array_equal(lp, ref_lp)
+    # length mismatch: sample_pt asserts (ensemble_sample.rs:133), swap_walkers silently returns (utils.rs:88)
+    with pytest.raises(AssertionError):
+        sb.sample_pt(f, ens, lp[:-1].copy(), dev, 2.0, sb.UpdateFlagSpec.All(), beta)
+    before = ens.copy()
+    sb.swap_walkers(ens, lp[:-2].copy(), dev, beta)
+    assert np.array_equal(ens, before)
+    # propose_move / scale_vec / draw_z
+    p1, p2 = rng.normal(size=6), rng.normal(size=6)
+    fl = np.array([1, 0, 1, 1, 0, 1], dtype=np.uint8)
+    want = oracle.propose_move(p1, p2, 1.37, fl)
+    assert np.array_equal(sb.propose_move(p1, p2, 1.37, fl), want)
+    assert np.array_equal(sb.scale_vec(p1, p2, 0.81), p1 * 0.81 + p2 * (1.0 - 0.81))
+    zs = np.array([sb.draw_z(dev, 2.0) for _ in range(200)])
+    assert np.all(zs >= 0.5) and np.all(zs < 2.0)
