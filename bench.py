@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- walker-steps/s of the ensemble-sampler hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--impl ours|reference]
+
+A "step" is one fused sample_pt pass over the whole ensemble (plus swap_walkers before every 10th
+step for the tempered workload).  Default workload = BASELINE config 5, the one the metric and
+the 70 %-of-HBM target are quoted on: 64-D Rosenbrock, 2^22 walkers, a = 2, Prob(0.5) flags as in
+examples/test_emcee.rs:55-62, fp64.  One JSON line on stdout (rank 0); see DESIGN.md section 7.
+
+  value        device-timed (CUDA events on the launch stream), ensemble resident in HBM
+  e2e          same metric through the reference-shaped host call (scorus_sample_pt_host):
+               pinned host buffers in, one step, host buffers out, copies inside the timed region
+  roofline     algorithmic bytes (16*D+16 per walker-step) / measured launch time
+               against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline the oracle's reference-structured CPU port on this box's cores, bounded sample
+  --impl reference   times only that CPU port (the reference is Rust; no toolchain in the image)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, kind, n, dim, nbeta, ufs, prob, init box, swap_every)
+    "c1": ("c1_test_emcee: 2-D Gaussian, 16 walkers", 0, 16, 2, 1, "prob", 0.5, (0.9, 1.1), 0),
+    "c2": ("c2_sample_high_dim: 100-D AR(1) rho=0.9 correlated Gaussian, 65536 walkers", 6, 65536, 100, 1, "all", 0.0, (-1.0, 1.0), 0),
+    "c3": ("c3_sample_bimodal: 32-D two-component mixture, 2^20 walkers", 7, 1 << 20, 32, 1, "prob", 0.5, (-6.0, 6.0), 0),
+    "c4": ("c4_sample_rastrigin: 10-D Rastrigin, 64 rungs x 16384 walkers, swap before every 10th step", 3, 1 << 20, 10, 64, "prob", 0.2, (-0.01, 0.01), 10),
+    "c5": ("c5_scale_sweep: 64-D Rosenbrock, 2^22 walkers", 2, 1 << 22, 64, 1, "prob", 0.5, (0.9, 1.1), 0),
+}
+
+
+def workload_params(kind, dim):
+    if kind == 0:
+        return [0.5]
+    if kind == 3:
+        return [10.0]
+    if kind == 6:  # AR(1), Sigma_ij = rho^|i-j|: L upper bidiagonal with L^T L = Sigma^-1
+        rho = 0.9
+        L = np.zeros((dim, dim))
+        s = 1.0 / np.sqrt(1.0 - rho * rho)
+        for i in range(dim - 1):
+            L[i, i] = s
+            L[i, i + 1] = -rho * s
+        L[dim - 1, dim - 1] = 1.0
+        return np.concatenate([np.zeros(dim), L.ravel()]).tolist()
+    if kind == 7:
+        m = np.zeros(dim)
+        m[0] = 5.0
+        return [1.0, 2.0] + m.tolist()
+    return []
+
+
+def betas(nbeta):
+    # 8 rungs: the reference's 2^-i ladder (examples/sample_rastrigin.rs:29); 64 rungs: 2^(-i/8)
+    k = max(1, nbeta // 8)
+    return (2.0 ** -(np.arange(nbeta) / k)).astype(np.float64)
+
+
+def b_alg(dim):
+    return 16 * dim + 16
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def run(self):
+        if self._nvml is None:
+            return
+        nv = self._nvml
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "display_clocks": 0x100}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:  # fallback: one nvidia-smi query
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = out.strip().split(",")
+                self.samples, self.max_mhz = [int(a)], int(b)
+            except Exception:
+                pass
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_ensemble(n, dim, box, seed, kind):
+    rng = np.random.default_rng(seed)
+    ens = rng.random((n, dim))
+    ens *= (box[1] - box[0])
+    ens += box[0]
+    if kind == 7:  # start near the +m mode
+        ens[:, 0] = np.abs(ens[:, 0])
+    return ens
+
+
+def cpu_reference_leg(wl, steps, warmup, sample_walkers=None, target_seconds=12.0):
+    """The reference's CPU path, restated (oracle/ref_structure_bench.c), on all host threads, on a
+    bounded sample of the workload: the first `sample_walkers` walkers (whole rungs)."""
+    from oracle import pyoracle as po
+    po.build()
+    desc, kind, n, dim, nbeta, ufs, prob, box, swap_every = WORKLOADS[wl]
+    params = workload_params(kind, dim)
+    if sample_walkers is None:
+        sample_walkers = min(n, 1 << 17)
+    npb = n // nbeta
+    if nbeta > 1:
+        rungs = max(1, min(nbeta, sample_walkers // npb))
+        n_s, nb_s = rungs * npb, rungs
+    else:
+        n_s, nb_s = sample_walkers, 1
+    beta = betas(nbeta)[:nb_s]
+    ens = make_ensemble(n_s, dim, box, 5, kind)
+    lp = po.init_logprob(kind, params, ens)
+    ukind = {"prob": po.UFS_PROB, "all": po.UFS_ALL, "onehot": po.UFS_ONE_HOT_CYCLE}[ufs]
+    cores = po.max_threads()
+    # warm-up + calibration: one step, then as many as fit the time budget (bounded by `steps`)
+    t1, _ = po.ref_structure_run(kind, params, ens, lp, beta, 2.0, ukind, prob, 11, max(1, min(warmup, 1)), cores)
+    k = int(max(1, min(steps, target_seconds / max(t1, 1e-6))))
+    t, stage = po.ref_structure_run(kind, params, ens, lp, beta, 2.0, ukind, prob, 12, k, cores)
+    value = n_s * k / t
+    names = ["pairing", "z", "flags", "proposal", "logprob", "accept"]
+    return {
+        "value": value, "unit": "walker-steps/s", "cores": cores, "kind": "port",
+        "sample": f"{k} steps of the first {n_s} walkers ({nb_s} rung(s)) of {desc}; reference-structured C port "
+                  f"(per-walker heap vectors, serial stages, log-density on {cores} threads)",
+        "seconds": t, "steps": k, "n_walkers": n_s,
+        "stage_share": {nm: float(s / stage.sum()) for nm, s in zip(names, stage)},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ufs", default=None, choices=["prob", "all", "onehot"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    desc, kind, n, dim, nbeta, ufs, prob, box, swap_every = WORKLOADS[args.workload]
+    if args.ufs:
+        ufs = args.ufs
+    W = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_leg(args.workload, args.steps, W, target_seconds=60.0)
+        line = {
+            "impl": "reference", "metric": "walker_steps_per_sec", "value": r["value"], "unit": "walker-steps/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "n_walkers": n, "dim": dim, "nbeta": nbeta, "ufs": ufs, "prob": prob, "a": 2.0,
+                       "sample_walkers": r["n_walkers"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")},
+            "e2e": {"value": r["value"], "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import scorus_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- shard the walkers: whole rungs per rank when tempered, contiguous walkers otherwise ----
+    if nbeta > 1:
+        assert nbeta % world == 0, "rungs must divide over the ranks"
+        nb_local = nbeta // world
+        n_local = n // world
+        beta = betas(nbeta)[rank * nb_local:(rank + 1) * nb_local]
+        parallelism = f"rungs->gpus x{world}" if world > 1 else "single gpu"
+    else:
+        n_local, nb_local = n // world, 1
+        beta = betas(1)
+        parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)" if world > 1 else "single gpu"
+    params = workload_params(kind, dim)
+    spec = {"prob": sb.UpdateFlagSpec.Prob(prob), "all": sb.UpdateFlagSpec.All(),
+            "onehot": sb.UpdateFlagSpec.OneHotCycle()}[ufs]
+    ens = make_ensemble(n_local, dim, box, 5 + rank, kind)
+
+    s = sb.Sampler(sb.LogProb(kind, tuple(params)), n_local, dim, seed=2024 + rank, device=local_rank)
+    stream = torch.cuda.Stream()  # the launch stream; the CUDA events below are recorded on it
+    torch.cuda.set_stream(stream)
+    s.set_stream(stream.cuda_stream)
+    s.upload(ens, None)
+    s.sync()
+
+    def run_steps(k0, count):
+        for k in range(k0, k0 + count):
+            if swap_every and nb_local > 1 and k % swap_every == 0:
+                s.swap_walkers(beta)
+            s.sample_pt(2.0, spec, beta, 1)
+
+    run_steps(0, W)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = s.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    run_steps(W, args.steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    launches = s.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    if dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stats = s.stats()
+    value = n * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the reference-shaped call on pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h_ens = sb.pinned_empty((n_local, dim))
+        h_lp = sb.pinned_empty((n_local,))
+        s.download(h_ens, h_lp)
+        s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)  # warm-up
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        bytes_dir = n_local * dim * 8 + n_local * 8
+        e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
+               "d2h_bytes_per_step": bytes_dir, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "api": "Sampler.sample_pt_host -> scorus_sample_pt_host (pinned host buffers in/out, one step per call)"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (step_kernel): algorithmic bytes / measured launch time ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_launch = b_alg(dim) * n_local
+    achieved = bytes_per_launch * args.steps / (ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "step_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_walker_step": b_alg(dim), "walkers_per_launch": n_local,
+                "note": "launch time = device time of the timed region / steps (one step_kernel launch per step)"}
+
+    cpu = None
+    if not args.no_cpu and world == 1 or (not args.no_cpu and rank == 0 and world == 1):
+        cpu = cpu_reference_leg(args.workload, 20, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")}
+
+    line = {
+        "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "n_walkers": n, "dim": dim, "nbeta": nbeta, "ufs": ufs, "prob": prob, "a": 2.0,
+                   "parallelism": parallelism, "swap_every": swap_every,
+                   "l2": f"resident ensemble {n_local * dim * 8 / 2**20:.0f} MiB per GPU vs 126 MB L2 (no flush needed)"
+                         if n_local * dim * 8 > 2 * 126e6 else "ensemble fits in L2: numbers are L2-resident, not HBM"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "accept_rate": stats["accepted"] / max(1, stats["proposed"]),
+    }
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -79,6 +79,11 @@ typedef struct scorus_ufs {
 } scorus_ufs;
 
 #define SCORUS_CFG_DEFAULT 0u
+/* Evaluate every log-density with one lane per walker, summing left to right exactly like the
+ * reference closures (bit-identical log-probs for the transcendental-free targets).  The default
+ * cooperative kernel sums per-lane partials in a fixed tree instead: same positions and accept
+ * decisions, log-probs equal to a few ulp, about 2x faster. */
+#define SCORUS_CFG_SEQUENTIAL_SUM 1u
 typedef struct scorus_cfg {
     uint64_t n_walkers; /* ensemble.len() */
     uint32_t dim;       /* ensemble[i].dimension() */
@@ -153,8 +158,10 @@ int scorus_swap_walkers_host(scorus_ctx *ctx, double *ensemble, double *logprob,
 
 /* ---- plumbing ---- */
 int scorus_sync(scorus_ctx *ctx);
-/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream; NULL is CUDA's legacy default
+ * stream, as everywhere in CUDA); scorus_reset_stream returns to the context's own stream */
 int scorus_set_stream(scorus_ctx *ctx, void *cuda_stream);
+int scorus_reset_stream(scorus_ctx *ctx);
 void *scorus_get_stream(scorus_ctx *ctx);
 /* device pointers of the resident state: ensemble rows are pitch_elems doubles apart */
 int scorus_device_buffers(scorus_ctx *ctx, double **ensemble, size_t *pitch_elems, double **logprob);

@@ -32,6 +32,7 @@ ERR_CUDA, ERR_NO_DEVICE = 100, 101
 LP_GAUSSIAN, LP_BOUNDED_GAUSSIAN, LP_ROSENBROCK, LP_RASTRIGIN = 0, 1, 2, 3
 LP_BIMODAL2D, LP_STEP2D, LP_CORR_GAUSSIAN, LP_MIXTURE = 4, 5, 6, 7
 UFS_PROB, UFS_ALL, UFS_ONE_HOT_CYCLE, UFS_MASK = 0, 1, 2, 3
+CFG_SEQUENTIAL_SUM = 1
 
 _lib = None
 
@@ -71,6 +72,7 @@ def load() -> C.CDLL:
         "scorus_swap_walkers_host": (ci, [vp, dp, dp, sz, dp, sz]),
         "scorus_sync": (ci, [vp]),
         "scorus_set_stream": (ci, [vp, vp]),
+        "scorus_reset_stream": (ci, [vp]),
         "scorus_get_stream": (vp, [vp]),
         "scorus_device_buffers": (ci, [vp, C.POINTER(dp), C.POINTER(sz), C.POINTER(dp)]),
         "scorus_get_counters": (ci, [vp, u64p, u64p, u64p]),
@@ -93,7 +95,7 @@ EXPORTS = [
     "scorus_check_beta_order", "scorus_ctx_create", "scorus_ctx_destroy", "scorus_last_error",
     "scorus_set_logprob", "scorus_upload", "scorus_download", "scorus_init_logprob", "scorus_sample",
     "scorus_sample_pt", "scorus_sample_pt_fixed", "scorus_draw_z", "scorus_swap_walkers", "scorus_swap_walkers_fixed",
-    "scorus_sample_pt_host", "scorus_swap_walkers_host", "scorus_sync", "scorus_set_stream",
+    "scorus_sample_pt_host", "scorus_swap_walkers_host", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",
     "scorus_get_stats", "scorus_launch_count", "scorus_host_alloc", "scorus_host_free",
 ]

@@ -1,0 +1,36 @@
+// launch.cuh -- kernel launchers, one translation unit per log-density plugin (launch_plugin.cu
+// compiled with -DSCORUS_PLUGIN=...), so the 60-odd kernel instantiations build in parallel.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace scorus {
+
+struct StepParams;
+
+struct Geometry {
+    uint32_t row_bytes, row_stride, flag_words, stages, warps, grid;
+    size_t smem;
+};
+
+#define SCORUS_DECLARE_LAUNCHERS(NAME)                                                                   \
+    cudaError_t launch_step_##NAME(const StepParams &p, const Geometry &g, bool all_flags, bool sequential, \
+                                   cudaStream_t st);                                                     \
+    cudaError_t launch_init_##NAME(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
+
+SCORUS_DECLARE_LAUNCHERS(LpGaussian)
+SCORUS_DECLARE_LAUNCHERS(LpBoundedGaussian)
+SCORUS_DECLARE_LAUNCHERS(LpRosenbrock)
+SCORUS_DECLARE_LAUNCHERS(LpRastrigin)
+SCORUS_DECLARE_LAUNCHERS(LpBimodal2d)
+SCORUS_DECLARE_LAUNCHERS(LpStep2d)
+SCORUS_DECLARE_LAUNCHERS(LpCorrGaussian)
+SCORUS_DECLARE_LAUNCHERS(LpMixture)
+
+// dispatch on the plugin id of include/scorus_b200.h (SCORUS_LP_*)
+cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, bool sequential,
+                        cudaStream_t st);
+cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
+
+}  // namespace scorus

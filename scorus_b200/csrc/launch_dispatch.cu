@@ -1,0 +1,38 @@
+// launch_dispatch.cu -- plugin id (SCORUS_LP_*) -> per-plugin launcher.
+#include "../../include/scorus_b200.h"
+#include "launch.cuh"
+
+namespace scorus {
+
+cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, bool sequential,
+                        cudaStream_t st)
+{
+    switch (kind) {
+    case SCORUS_LP_GAUSSIAN: return launch_step_LpGaussian(p, g, all_flags, sequential, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_step_LpBoundedGaussian(p, g, all_flags, sequential, st);
+    case SCORUS_LP_ROSENBROCK: return launch_step_LpRosenbrock(p, g, all_flags, sequential, st);
+    case SCORUS_LP_RASTRIGIN: return launch_step_LpRastrigin(p, g, all_flags, sequential, st);
+    case SCORUS_LP_BIMODAL2D: return launch_step_LpBimodal2d(p, g, all_flags, sequential, st);
+    case SCORUS_LP_STEP2D: return launch_step_LpStep2d(p, g, all_flags, sequential, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_step_LpCorrGaussian(p, g, all_flags, sequential, st);
+    case SCORUS_LP_MIXTURE: return launch_step_LpMixture(p, g, all_flags, sequential, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st)
+{
+    switch (kind) {
+    case SCORUS_LP_GAUSSIAN: return launch_init_LpGaussian(p, grid, smem, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_init_LpBoundedGaussian(p, grid, smem, st);
+    case SCORUS_LP_ROSENBROCK: return launch_init_LpRosenbrock(p, grid, smem, st);
+    case SCORUS_LP_RASTRIGIN: return launch_init_LpRastrigin(p, grid, smem, st);
+    case SCORUS_LP_BIMODAL2D: return launch_init_LpBimodal2d(p, grid, smem, st);
+    case SCORUS_LP_STEP2D: return launch_init_LpStep2d(p, grid, smem, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_init_LpCorrGaussian(p, grid, smem, st);
+    case SCORUS_LP_MIXTURE: return launch_init_LpMixture(p, grid, smem, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace scorus

@@ -1,0 +1,58 @@
+// launch_plugin.cu -- instantiates the step / init kernels for ONE log-density plugin and exports
+// their launchers.  Compiled once per plugin with -DSCORUS_PLUGIN=<struct name> (see Makefile).
+#include "launch.cuh"
+#include "step_coop_kernel.cuh"
+#include "step_kernel.cuh"
+
+#ifndef SCORUS_PLUGIN
+#error "compile with -DSCORUS_PLUGIN=LpGaussian (or another plugin of logprob.cuh)"
+#endif
+#define SCORUS_CAT2(a, b) a##b
+#define SCORUS_CAT(a, b) SCORUS_CAT2(a, b)
+
+namespace scorus {
+
+template <class K>
+static cudaError_t launch_kernel(K kernel, const StepParams &p, const Geometry &g, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<g.grid, g.warps * 32, g.smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// lanes sharing a pair in the cooperative kernel: the power of two covering a row's double2 count
+static int coop_group(uint32_t pitch)
+{
+    uint32_t nvec = pitch / 2, g = 2;
+    while (g < 32 && g < nvec) g <<= 1;
+    return (int)g;
+}
+
+cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const Geometry &g, bool all_flags,
+                                                    bool sequential, cudaStream_t st)
+{
+    using Plugin = SCORUS_PLUGIN;
+    if (sequential) {
+        if (all_flags) return launch_kernel(step_seq_kernel<Plugin, true>, p, g, st);
+        return launch_kernel(step_seq_kernel<Plugin, false>, p, g, st);
+    }
+    switch (coop_group(p.pitch)) {
+    case 2: return launch_kernel(step_coop_kernel<Plugin, 2>, p, g, st);
+    case 4: return launch_kernel(step_coop_kernel<Plugin, 4>, p, g, st);
+    case 8: return launch_kernel(step_coop_kernel<Plugin, 8>, p, g, st);
+    case 16: return launch_kernel(step_coop_kernel<Plugin, 16>, p, g, st);
+    default: return launch_kernel(step_coop_kernel<Plugin, 32>, p, g, st);
+    }
+}
+
+cudaError_t SCORUS_CAT(launch_init_, SCORUS_PLUGIN)(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st)
+{
+    using Plugin = SCORUS_PLUGIN;
+    cudaError_t e = cudaFuncSetAttribute(init_logprob_kernel<Plugin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    init_logprob_kernel<Plugin><<<grid, p.warps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace scorus

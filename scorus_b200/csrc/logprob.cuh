@@ -1,16 +1,26 @@
 // logprob.cuh -- device-side log-density plugins.
 //
 // These replace the `flogprob: &F` closure of the reference
-// (src/mcmc/ensemble_sample.rs:88,102,161).  A plugin consumes the proposed point one
-// coordinate at a time, in index order, so every per-walker sum is accumulated left to right
-// exactly as the reference closures do -- with -fmad=false the results are
-// bit-identical to the CPU oracle for the transcendental-free targets.
+// (src/mcmc/ensemble_sample.rs:88,102,161).  Two evaluation interfaces per plugin:
 //
-// Interface (all __device__):
+// Sequential (step_seq_kernel, init_logprob_kernel: one lane walks one row):
 //   void   init(const double* params, uint32_t nparams, uint32_t dim)
-//   void   accum(uint32_t d, double y)        // coordinate d of the proposal, d ascending
+//   void   accum(uint32_t d, double y)        // coordinate d of the point, d ascending
 //   double finish()
-//   static constexpr bool kNeedsRow           // true: finish_row(row) re-reads the whole row
+//   Every per-walker sum is accumulated left to right exactly as the reference closures do
+//   (SURVEY App. B); with -fmad=false the transcendental-free targets are bit-identical to the
+//   CPU oracle.
+//
+// Cooperative (step_coop_kernel: the lanes of a warp share a row, two coordinates per lane and
+// trip; per-lane partial sums are combined by a fixed shuffle tree, so the summation ORDER
+// differs from the reference's -- the values agree to a few ulp of the sum of |terms|, the bar
+// is 1e-12 relative):
+//   static constexpr int kAcc                 // partial accumulators per walker (1 or 2)
+//   void   terms(d, y0, y1, nb, has1, hasnb, acc)   // coordinates d (and d+1 if has1);
+//                                                   // nb = coordinate d+2 (valid if hasnb)
+//   double finish_acc(const double* acc)      // acc = lane-reduced accumulators
+//
+//   static constexpr bool kNeedsRow           // true: finish_row(row) evaluates from the whole row
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -20,6 +30,7 @@ namespace scorus {
 // -sum c*x^2.  examples/test_emcee.rs:18-24 (c = 1/2), examples/sample_high_dim.rs:22-28 (c = 1)
 struct LpGaussian {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kAcc = 1;
     double c, acc;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t)
     {
@@ -32,11 +43,18 @@ struct LpGaussian {
         acc -= sq * c;
     }
     __device__ __forceinline__ double finish() const { return acc; }
+    __device__ __forceinline__ void terms(uint32_t, double y0, double y1, double, bool has1, bool, double *a) const
+    {
+        a[0] -= (y0 * y0) * c;
+        if (has1) a[0] -= (y1 * y1) * c;
+    }
+    __device__ __forceinline__ double finish_acc(const double *a) const { return a[0]; }
 };
 
 // examples/sample_bimodal.rs:35-44: subtract, then -inf as soon as one |x| exceeds the limit
 struct LpBoundedGaussian {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kAcc = 2;  // [0] the sum, [1] number of coordinates beyond the limit
     double limit, acc;
     bool dead;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t)
@@ -51,56 +69,85 @@ struct LpBoundedGaussian {
         dead |= fabs(y) > limit;
     }
     __device__ __forceinline__ double finish() const { return dead ? -INFINITY : acc; }
+    __device__ __forceinline__ void terms(uint32_t, double y0, double y1, double, bool has1, bool, double *a) const
+    {
+        a[0] -= y0 * y0;
+        a[1] += fabs(y0) > limit ? 1.0 : 0.0;
+        if (has1) {
+            a[0] -= y1 * y1;
+            a[1] += fabs(y1) > limit ? 1.0 : 0.0;
+        }
+    }
+    __device__ __forceinline__ double finish_acc(const double *a) const { return a[1] > 0.0 ? -INFINITY : a[0]; }
 };
 
 // examples/test_emcee.rs:26-32: -sum_i [100 (x[i+1] - x[i]^2)^2 + (1 - x[i])^2]
 struct LpRosenbrock {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kAcc = 1;
     double prev, acc;
     __device__ __forceinline__ void init(const double *, uint32_t, uint32_t)
     {
         prev = 0.0;
         acc = 0.0;
     }
+    static __device__ __forceinline__ double term(double xi, double xn)
+    {
+        double xi2 = xi * xi;
+        double t = xn - xi2;
+        double t2 = t * t;
+        double s = 1.0 - xi;
+        double s2 = s * s;
+        return 100.0 * t2 + s2;
+    }
     __device__ __forceinline__ void accum(uint32_t d, double y)
     {
-        if (d > 0) {
-            double xi2 = prev * prev;
-            double t = y - xi2;
-            double t2 = t * t;
-            double s = 1.0 - prev;
-            double s2 = s * s;
-            double term = 100.0 * t2 + s2;
-            acc += term;
-        }
+        if (d > 0) acc += term(prev, y);
         prev = y;
     }
     __device__ __forceinline__ double finish() const { return -acc; }
+    __device__ __forceinline__ void terms(uint32_t, double y0, double y1, double nb, bool has1, bool hasnb,
+                                          double *a) const
+    {
+        if (has1) a[0] += term(y0, y1);
+        if (hasnb) a[0] += term(y1, nb);
+    }
+    __device__ __forceinline__ double finish_acc(const double *a) const { return -a[0]; }
 };
 
 // examples/sample_rastrigin.rs:17-25: -(n a) + sum [a cos(2 pi x) - x^2]
 struct LpRastrigin {
     static constexpr bool kNeedsRow = false;
-    double a, acc;
-    __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t dim)
-    {
-        a = np >= 1 ? __ldg(p) : 10.0;
-        acc = -((double)dim * a);
-    }
-    __device__ __forceinline__ void accum(uint32_t, double y)
+    static constexpr int kAcc = 1;
+    double a, acc, base;
+    static __device__ __forceinline__ double term(double a, double y)
     {
         const double two_pi = 2.0 * 3.14159265358979323846;
         double arg = two_pi * y;
         double c = a * cos(arg);
         double sq = y * y;
-        acc += c - sq;
+        return c - sq;
     }
+    __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t dim)
+    {
+        a = np >= 1 ? __ldg(p) : 10.0;
+        base = -((double)dim * a);
+        acc = base;
+    }
+    __device__ __forceinline__ void accum(uint32_t, double y) { acc += term(a, y); }
     __device__ __forceinline__ double finish() const { return acc; }
+    __device__ __forceinline__ void terms(uint32_t, double y0, double y1, double, bool has1, bool, double *s) const
+    {
+        s[0] += term(a, y0);
+        if (has1) s[0] += term(a, y1);
+    }
+    __device__ __forceinline__ double finish_acc(const double *s) const { return base + s[0]; }
 };
 
 // examples/sample_bimodal.rs:46-54
 struct LpBimodal2d {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kAcc = 2;  // [0] carries x0, [1] carries x1
     double lo0, hi0, lo1, hi1, split, mu_a, sg_a, mu_b, sg_b, x0, x1;
     uint32_t dim;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t d)
@@ -119,22 +166,32 @@ struct LpBimodal2d {
         if (d == 0) x0 = y;
         if (d == 1) x1 = y;
     }
-    __device__ __forceinline__ double finish() const
+    __device__ __forceinline__ double eval(double a0, double a1) const
     {
         if (dim < 2) return NAN;
-        if (x0 < lo0 || x0 > hi0 || x1 < lo1 || x1 > hi1) return -INFINITY;
-        double mu = x1 < split ? mu_a : mu_b;
-        double sigma = x1 < split ? sg_a : sg_b;
-        double dx = x0 - mu;
+        if (a0 < lo0 || a0 > hi0 || a1 < lo1 || a1 > hi1) return -INFINITY;
+        double mu = a1 < split ? mu_a : mu_b;
+        double sigma = a1 < split ? sg_a : sg_b;
+        double dx = a0 - mu;
         double num = (-dx) * dx;
         double den = (2.0 * sigma) * sigma;
         return num / den - log(sigma);
     }
+    __device__ __forceinline__ double finish() const { return eval(x0, x1); }
+    __device__ __forceinline__ void terms(uint32_t d, double y0, double y1, double, bool has1, bool, double *a) const
+    {
+        if (d == 0) {  // only the lane holding coordinates 0,1 contributes; x + 0 is exact
+            a[0] += y0;
+            if (has1) a[1] += y1;
+        }
+    }
+    __device__ __forceinline__ double finish_acc(const double *a) const { return eval(a[0], a[1]); }
 };
 
 // examples/sample_bimodal.rs:56-65
 struct LpStep2d {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kAcc = 2;
     double x0, x1;
     uint32_t dim;
     __device__ __forceinline__ void init(const double *, uint32_t, uint32_t d)
@@ -146,17 +203,27 @@ struct LpStep2d {
         if (d == 0) x0 = y;
         if (d == 1) x1 = y;
     }
-    __device__ __forceinline__ double finish() const
+    __device__ __forceinline__ double eval(double a0, double a1) const
     {
         if (dim < 2) return NAN;
-        if (x0 < 0.0 || x0 > 1.0 || x1 < 0.0 || x1 > 1.0) return -INFINITY;
-        return x0 > 0.5 ? log(0.1) : log(0.9);
+        if (a0 < 0.0 || a0 > 1.0 || a1 < 0.0 || a1 > 1.0) return -INFINITY;
+        return a0 > 0.5 ? log(0.1) : log(0.9);
     }
+    __device__ __forceinline__ double finish() const { return eval(x0, x1); }
+    __device__ __forceinline__ void terms(uint32_t d, double y0, double y1, double, bool has1, bool, double *a) const
+    {
+        if (d == 0) {
+            a[0] += y0;
+            if (has1) a[1] += y1;
+        }
+    }
+    __device__ __forceinline__ double finish_acc(const double *a) const { return eval(a[0], a[1]); }
 };
 
 // builder-defined (BASELINE config 3): logsumexp of two isotropic Gaussians at +m and -m
 struct LpMixture {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kAcc = 2;
     const double *m;
     double s1, s2, q1, q2;
     uint32_t dim;
@@ -177,23 +244,38 @@ struct LpMixture {
         q1 += a * a;
         q2 += b * b;
     }
-    __device__ __forceinline__ double finish() const
+    __device__ __forceinline__ double eval(double a1, double a2) const
     {
         if (!ok) return NAN;
-        double t1 = (-q1) / ((2.0 * s1) * s1) - (double)dim * log(s1);
-        double t2 = (-q2) / ((2.0 * s2) * s2) - (double)dim * log(s2);
+        double t1 = (-a1) / ((2.0 * s1) * s1) - (double)dim * log(s1);
+        double t2 = (-a2) / ((2.0 * s2) * s2) - (double)dim * log(s2);
         double hi = t1 > t2 ? t1 : t2;
         double lo = t1 > t2 ? t2 : t1;
         if (hi == -INFINITY) return -INFINITY;
         return hi + log1p(exp(lo - hi));
     }
+    __device__ __forceinline__ double finish() const { return eval(q1, q2); }
+    __device__ __forceinline__ void terms(uint32_t d, double y0, double y1, double, bool has1, bool, double *a) const
+    {
+        double m0 = ok ? __ldg(m + d) : 0.0;
+        double u0 = y0 - m0, v0 = y0 + m0;
+        a[0] += u0 * u0;
+        a[1] += v0 * v0;
+        if (has1) {
+            double m1 = ok ? __ldg(m + d + 1) : 0.0;
+            double u1 = y1 - m1, v1 = y1 + m1;
+            a[0] += u1 * u1;
+            a[1] += v1 * v1;
+        }
+    }
+    __device__ __forceinline__ double finish_acc(const double *a) const { return eval(a[0], a[1]); }
 };
 
 // builder-defined (BASELINE config 2): -0.5 |L (x - mu)|^2, general dense L.
-// Scalar fallback evaluated from the finished row in shared memory; the tensor-core (DMMA)
-// tile version lives in dense_kernel.cuh.
+// Scalar evaluation from the finished row in shared memory (one lane per walker).
 struct LpCorrGaussian {
     static constexpr bool kNeedsRow = true;
+    static constexpr int kAcc = 1;
     const double *mu, *L;
     uint32_t dim;
     bool ok;
@@ -206,6 +288,8 @@ struct LpCorrGaussian {
     }
     __device__ __forceinline__ void accum(uint32_t, double) {}
     __device__ __forceinline__ double finish() const { return NAN; }
+    __device__ __forceinline__ void terms(uint32_t, double, double, double, bool, bool, double *) const {}
+    __device__ __forceinline__ double finish_acc(const double *) const { return NAN; }
     __device__ __forceinline__ double finish_row(const double *row) const
     {
         if (!ok) return NAN;

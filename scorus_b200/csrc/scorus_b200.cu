@@ -15,8 +15,9 @@
 
 #include <cuda_runtime.h>
 
-#include "step_kernel.cuh"
+#include "launch.cuh"
 #include "swap_kernel.cuh"
+#include "tile_common.cuh"
 
 using namespace scorus;
 
@@ -46,6 +47,7 @@ struct scorus_ctx {
     int lp_kind = -1;
     uint32_t nparams = 0;
     bool uploaded = false;
+    bool sequential = false;  // SCORUS_CFG_SEQUENTIAL_SUM
     std::string err;
     std::vector<double> h_beta;
 };
@@ -160,6 +162,7 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     ctx->dim = cfg->dim;
     ctx->pitch = cfg->dim + (cfg->dim & 1u);  // rows are 16-byte multiples for cp.async.bulk
     ctx->seed = cfg->seed;
+    ctx->sequential = (cfg->flags & SCORUS_CFG_SEQUENTIAL_SUM) != 0;
     auto bail = [&](cudaError_t err, const char *what) {
         fprintf(stderr, "scorus_ctx_create: %s: %s\n", what, cudaGetErrorString(err));
         scorus_ctx_destroy(ctx);
@@ -202,7 +205,15 @@ extern "C" int scorus_set_stream(scorus_ctx *ctx, void *s)
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;
+    return SCORUS_OK;
+}
+extern "C" int scorus_reset_stream(scorus_ctx *ctx)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return SCORUS_OK;
 }
 extern "C" void *scorus_get_stream(scorus_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -294,10 +305,6 @@ extern "C" int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *param
 // ------------------------------------------------------------------------------------------
 // launch geometry
 // ------------------------------------------------------------------------------------------
-struct Geometry {
-    uint32_t row_bytes, row_stride, flag_words, stages, warps, grid;
-    size_t smem;
-};
 
 static int env_int(const char *name, int dflt)
 {
@@ -346,46 +353,6 @@ static int step_geometry(scorus_ctx *ctx, Geometry *g)
     return SCORUS_OK;
 }
 
-template <class Plugin>
-static cudaError_t launch_step_t(const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st)
-{
-    cudaError_t e;
-    if (all_flags) {
-        e = cudaFuncSetAttribute(step_kernel<Plugin, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-        if (e != cudaSuccess) return e;
-        step_kernel<Plugin, true><<<g.grid, g.warps * 32, g.smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(step_kernel<Plugin, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-        if (e != cudaSuccess) return e;
-        step_kernel<Plugin, false><<<g.grid, g.warps * 32, g.smem, st>>>(p);
-    }
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st)
-{
-    switch (kind) {
-    case SCORUS_LP_GAUSSIAN: return launch_step_t<LpGaussian>(p, g, all_flags, st);
-    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_step_t<LpBoundedGaussian>(p, g, all_flags, st);
-    case SCORUS_LP_ROSENBROCK: return launch_step_t<LpRosenbrock>(p, g, all_flags, st);
-    case SCORUS_LP_RASTRIGIN: return launch_step_t<LpRastrigin>(p, g, all_flags, st);
-    case SCORUS_LP_BIMODAL2D: return launch_step_t<LpBimodal2d>(p, g, all_flags, st);
-    case SCORUS_LP_STEP2D: return launch_step_t<LpStep2d>(p, g, all_flags, st);
-    case SCORUS_LP_CORR_GAUSSIAN: return launch_step_t<LpCorrGaussian>(p, g, all_flags, st);
-    case SCORUS_LP_MIXTURE: return launch_step_t<LpMixture>(p, g, all_flags, st);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-template <class Plugin>
-static cudaError_t launch_init_t(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st)
-{
-    cudaError_t e = cudaFuncSetAttribute(init_logprob_kernel<Plugin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    init_logprob_kernel<Plugin><<<grid, p.warps * 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
 extern "C" int scorus_init_logprob(scorus_ctx *ctx)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
@@ -409,18 +376,7 @@ extern "C" int scorus_init_logprob(scorus_ctx *ctx)
     // several CTAs per SM are fine here: one stage per warp, latency hidden across CTAs
     uint32_t max_grid = (uint32_t)ctx->num_sms * 4u;
     if (grid > max_grid) grid = max_grid;
-    cudaError_t e;
-    switch (ctx->lp_kind) {
-    case SCORUS_LP_GAUSSIAN: e = launch_init_t<LpGaussian>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_BOUNDED_GAUSSIAN: e = launch_init_t<LpBoundedGaussian>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_ROSENBROCK: e = launch_init_t<LpRosenbrock>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_RASTRIGIN: e = launch_init_t<LpRastrigin>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_BIMODAL2D: e = launch_init_t<LpBimodal2d>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_STEP2D: e = launch_init_t<LpStep2d>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_CORR_GAUSSIAN: e = launch_init_t<LpCorrGaussian>(p, grid, smem, ctx->stream); break;
-    case SCORUS_LP_MIXTURE: e = launch_init_t<LpMixture>(p, grid, smem, ctx->stream); break;
-    default: e = cudaErrorInvalidValue;
-    }
+    cudaError_t e = launch_init(ctx->lp_kind, p, grid, smem, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "init_logprob launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     return SCORUS_OK;
@@ -560,7 +516,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
             ++ctx->launches;
             p.order = ctx->d_order;
         }
-        cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
+        cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->sequential, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
         ++ctx->launches;
         ++ctx->step;
@@ -620,7 +576,7 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
     p.order = ctx->d_order; p.z_in = ctx->d_z; p.u_in = ctx->d_u; p.flags_in = ctx->d_flags;
     p.flag_len = (uint32_t)flag_len; p.flag_kind = SCORUS_UFS_MASK; p.accepted_out = ctx->d_acc;
     p.step = ctx->step;
-    cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
+    cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->sequential, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     ctx->proposed += n;

@@ -21,106 +21,9 @@
 //  * Warps are independent: no __syncthreads in the loop, only __syncwarp between the read
 //    and the in-place write of a chunk (lane l^1 reads lane l's row).
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
-
-#include "logprob.cuh"
-#include "rng.cuh"
+#include "tile_common.cuh"
 
 namespace scorus {
-
-enum : int { FK_ALL = 0, FK_BITS = 1, FK_ONEHOT = 2 };
-
-struct StepParams {
-    double *ens;            // [n][pitch]
-    double *lp;             // [n]
-    const double *beta;     // [nbeta] (device)
-    const double *pparams;  // plugin params (device)
-    const uint32_t *order;  // [n] matching order (device) or nullptr -> keyed bijection
-    const double *z_in;     // fixed streams (device) or nullptr -> Philox
-    const double *u_in;
-    const uint8_t *flags_in;  // [n][flag_len] bytes or nullptr
-    uint8_t *accepted_out;    // [n] or nullptr
-    unsigned long long *stats;  // [0] accepted, [1] proposed
-    uint64_t seed, step, onehot;
-    uint64_t flag_thr;      // Bernoulli threshold on flag_bits random bits
-    double inv_sqrt_a, z_range;
-    uint32_t n, npb, dim, pitch, nbeta, nparams;
-    uint32_t flag_len, flag_bits, flag_kind;  // flag_kind: SCORUS_UFS_*
-    uint32_t row_bytes, row_stride;           // bytes copied per row / shared-memory row stride
-    uint32_t stages, warps, ntiles, flag_words;
-    uint32_t bij_bits;
-};
-
-// ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-        "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all()
-{
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void fence_mbar_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-// walker at matching position j (positions 2k, 2k+1 are partners; both in the same rung)
-__device__ __forceinline__ uint32_t walker_at(const StepParams &p, uint32_t j)
-{
-    if (p.order) return __ldg(p.order + j);
-    uint32_t r = j / p.npb;
-    uint32_t k = j - r * p.npb;
-    BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r);
-    return r * p.npb + bij(k, p.npb, p.bij_bits, K);
-}
 
 constexpr int kChunk = 8;  // doubles per lane between two __syncwarp (4 x LDS.128 per row)
 
@@ -128,7 +31,7 @@ constexpr int kChunk = 8;  // doubles per lane between two __syncwarp (4 x LDS.1
 //   [0, 8*warps*stages)                  mbarriers, one per (warp, stage)
 //   then per warp: stages * 32 * row_stride bytes of rows, then 32*flag_words*4 bytes of flag bits
 template <class Plugin, bool kAllFlags>
-__global__ void __launch_bounds__(512, 1) step_kernel(const StepParams p)
+__global__ void __launch_bounds__(512, 1) step_seq_kernel(const StepParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31u;
@@ -222,46 +125,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams p)
 
         // ---- update flags (:38-54) ----
         uint32_t nphi = p.dim;
-        uint32_t hot = 0;
-        if (!kAllFlags) {
-            if (p.flag_kind == 2u) {  // ONE_HOT_CYCLE: the closure is called once per walker, in order
-                hot = (uint32_t)((p.onehot + 1ull + (uint64_t)w) % (uint64_t)p.dim);
-                nphi = 1;
-            } else if (p.flag_kind == 3u) {  // MASK: caller-evaluated Func / fixed streams
-                nphi = 0;
-                for (uint32_t wd = 0; wd < p.flag_words; ++wd) {
-                    uint32_t bits = 0;
-                    for (uint32_t b = 0; b < 32u; ++b) {
-                        uint32_t d = wd * 32u + b;
-                        if (d >= p.dim) break;
-                        bool f = d >= p.flag_len ? true
-                                                 : (act ? __ldg(p.flags_in + (size_t)w * p.flag_len + d) != 0 : true);
-                        bits |= (uint32_t)f << b;
-                        nphi += (f && d < p.flag_len) ? 1u : 0u;
-                    }
-                    flagw[wd * 32u + lane] = bits;
-                }
-            } else {  // PROB: Bernoulli(p) per coordinate, redrawn until at least one is set
-                const uint32_t bpf = p.flag_bits, fpc = 128u / bpf;
-                const uint32_t nblk = (p.dim + fpc - 1u) / fpc;
-                const uint64_t vmask = bpf == 32u ? 0xFFFFFFFFull : ((1ull << bpf) - 1ull);
-                for (uint32_t attempt = 0;; ++attempt) {
-                    nphi = 0;
-                    uint32_t bits = 0;
-                    U4 r = {0u, 0u, 0u, 0u};
-                    for (uint32_t d = 0, q = 0, blk = 0; d < p.dim; ++d) {
-                        if (q == 0) r = draw(p.seed, p.step, ST_FLAGS, w, attempt * nblk + blk);
-                        const uint32_t bit = q * bpf, wi = bit >> 5;
-                        const uint32_t word = wi == 0 ? r.x : wi == 1 ? r.y : wi == 2 ? r.z : r.w;
-                        const uint64_t v = ((uint64_t)(word >> (bit & 31u))) & vmask;
-                        if (v < p.flag_thr) { bits |= 1u << (d & 31u); ++nphi; }
-                        if ((d & 31u) == 31u || d + 1u == p.dim) { flagw[(d >> 5) * 32u + lane] = bits; bits = 0; }
-                        if (++q == fpc) { q = 0; ++blk; }
-                    }
-                    if (nphi > 0 || !act) break;
-                }
-            }
-        }
+        if (!kAllFlags) nphi = gen_flags(p, w, flagw, lane, act);
 
         // ---- wait for the rows, then propose + evaluate in one pass over the row ----
         mbar_wait(bar0 + 8u * stage, parity);
@@ -285,16 +149,13 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams p)
             }
             __syncwarp();  // lane^1 has read my row before I overwrite it
             uint32_t fbits = 0xFFFFFFFFu;
-            if (!kAllFlags && p.flag_kind != 2u) fbits = flagw[((c * 2u) >> 5) * 32u + lane] >> ((c * 2u) & 31u);
+            if (!kAllFlags) fbits = flagw[((c * 2u) >> 5) * 32u + lane] >> ((c * 2u) & 31u);
 #pragma unroll
             for (int q = 0; q < kChunk / 2; ++q) {
                 const uint32_t d0 = (c + q) * 2u;
                 if (d0 < p.dim) {
                     bool f0 = true, f1 = true;
-                    if (!kAllFlags) {
-                        if (p.flag_kind == 2u) { f0 = d0 == hot; f1 = d0 + 1u == hot; }
-                        else { f0 = (fbits >> (2 * q)) & 1u; f1 = (fbits >> (2 * q + 1)) & 1u; }
-                    }
+                    if (!kAllFlags) { f0 = (fbits >> (2 * q)) & 1u; f1 = (fbits >> (2 * q + 1)) & 1u; }
                     // scale_vec, src/mcmc/utils.rs:55: (x1*z) + (x2*(1-z)), three roundings
                     double t1 = a[q].x * z, t2 = b[q].x * omz;
                     double y0 = t1 + t2;

@@ -1,0 +1,191 @@
+// tile_common.cuh -- pieces shared by the step kernels: launch parameters, the PTX wrappers for
+// mbarrier + bulk async copies (TMA, non-tensor form), the matching order and the update-flag
+// generator.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "logprob.cuh"
+#include "rng.cuh"
+
+namespace scorus {
+
+struct StepParams {
+    double *ens;            // [n][pitch]
+    double *lp;             // [n]
+    const double *beta;     // [nbeta] (device)
+    const double *pparams;  // plugin params (device)
+    const uint32_t *order;  // [n] matching order (device) or nullptr -> keyed bijection
+    const double *z_in;     // fixed streams (device) or nullptr -> Philox
+    const double *u_in;
+    const uint8_t *flags_in;  // [n][flag_len] bytes or nullptr
+    uint8_t *accepted_out;    // [n] or nullptr
+    unsigned long long *stats;  // [0] accepted, [1] proposed
+    uint64_t seed, step, onehot;
+    uint64_t flag_thr;      // Bernoulli threshold on flag_bits random bits
+    double inv_sqrt_a, z_range;
+    uint32_t n, npb, dim, pitch, nbeta, nparams;
+    uint32_t flag_len, flag_bits, flag_kind;  // flag_kind: SCORUS_UFS_*
+    uint32_t row_bytes, row_stride;           // bytes copied per row / shared-memory row stride
+    uint32_t stages, warps, ntiles, flag_words;
+    uint32_t bij_bits;
+};
+
+// ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// walker at matching position j (positions 2k, 2k+1 are partners; both in the same rung)
+__device__ __forceinline__ uint32_t walker_at(const StepParams &p, uint32_t j)
+{
+    if (p.order) return __ldg(p.order + j);
+    uint32_t r = j / p.npb;
+    uint32_t k = j - r * p.npb;
+    BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r);
+    return r * p.npb + bij(k, p.npb, p.bij_bits, K);
+}
+
+// ---- update flags (src/mcmc/ensemble_sample.rs:38-54), one lane per walker ----
+// Flag words live in shared memory as flagw[word * 32 + lane]: bit (d & 31) of word (d >> 5) set
+// means coordinate d moves.  Returns nphi = number of set flags that count (:164-167).
+
+// Prob(p): BPF random bits per coordinate, flag = value < thr; redrawn (attempt + 1) until one is set.
+template <int BPF>
+__device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint32_t w, uint32_t *flagw,
+                                                   uint32_t lane, bool act)
+{
+    constexpr uint32_t FPC = 128u / BPF;   // flags per Philox call
+    constexpr uint32_t VPW = 32u / BPF;    // values per 32-bit random word
+    constexpr uint32_t VMASK = BPF == 32 ? 0xFFFFFFFFu : ((1u << (BPF & 31)) - 1u);
+    const uint32_t nblk = (p.dim + FPC - 1u) / FPC;
+    const uint32_t thr = (uint32_t)(p.flag_thr > 0xFFFFFFFFull ? 0xFFFFFFFFull : p.flag_thr);
+    const bool always = p.flag_thr > (uint64_t)VMASK;  // p == 1: every value is below the threshold
+    uint32_t nphi = 0;
+    for (uint32_t attempt = 0;; ++attempt) {
+        nphi = 0;
+        uint32_t cur = 0;
+        for (uint32_t blk = 0; blk < nblk; ++blk) {
+            const U4 r = draw(p.seed, p.step, ST_FLAGS, w, attempt * nblk + blk);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (uint32_t wi = 0; wi < 4; ++wi) {
+                uint32_t bits = 0;  // VPW flag bits from this random word
+                if (BPF == 1) {
+                    bits = always ? 0xFFFFFFFFu : (thr ? ~rr[wi] : 0u);  // value < 1  <=>  bit clear
+                } else {
+#pragma unroll
+                    for (uint32_t q = 0; q < VPW; ++q) {
+                        const uint32_t v = (rr[wi] >> ((q * BPF) & 31u)) & VMASK;
+                        bits |= (uint32_t)(always || v < thr) << q;
+                    }
+                }
+                const uint32_t d0 = blk * FPC + wi * VPW;  // first coordinate these bits belong to
+                if (d0 < p.dim) {
+                    if (d0 + VPW > p.dim) bits &= (1u << (p.dim - d0)) - 1u;
+                    nphi += __popc(bits);
+                    cur |= bits << (d0 & 31u);
+                    if (((d0 + VPW) & 31u) == 0u || d0 + VPW >= p.dim) {
+                        flagw[(d0 >> 5) * 32u + lane] = cur;
+                        cur = 0;
+                    }
+                }
+            }
+        }
+        if (nphi > 0 || !act) break;
+    }
+    return nphi;
+}
+
+__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, uint32_t *flagw, uint32_t lane,
+                                              bool act)
+{
+    if (p.flag_kind == 2u) {  // ONE_HOT_CYCLE: the cycling closure, called once per walker in order
+        const uint32_t hot = (uint32_t)((p.onehot + 1ull + (uint64_t)w) % (uint64_t)p.dim);
+        for (uint32_t wd = 0; wd < p.flag_words; ++wd)
+            flagw[wd * 32u + lane] = (hot >> 5) == wd ? (1u << (hot & 31u)) : 0u;
+        return 1u;
+    }
+    if (p.flag_kind == 3u) {  // MASK: caller-evaluated Func / fixed streams, [n][flag_len] bytes
+        uint32_t nphi = 0;
+        for (uint32_t wd = 0; wd < p.flag_words; ++wd) {
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < 32u; ++b) {
+                const uint32_t d = wd * 32u + b;
+                if (d >= p.dim) break;
+                // coordinates beyond flag_len always move and are not counted (:68, :164-167)
+                const bool f = d >= p.flag_len ? true
+                                               : (act ? __ldg(p.flags_in + (size_t)w * p.flag_len + d) != 0 : true);
+                bits |= (uint32_t)f << b;
+                nphi += (f && d < p.flag_len) ? 1u : 0u;
+            }
+            flagw[wd * 32u + lane] = bits;
+        }
+        return nphi;
+    }
+    switch (p.flag_bits) {  // PROB
+    case 1: return gen_flags_prob<1>(p, w, flagw, lane, act);
+    case 2: return gen_flags_prob<2>(p, w, flagw, lane, act);
+    case 4: return gen_flags_prob<4>(p, w, flagw, lane, act);
+    case 8: return gen_flags_prob<8>(p, w, flagw, lane, act);
+    case 16: return gen_flags_prob<16>(p, w, flagw, lane, act);
+    default: return gen_flags_prob<32>(p, w, flagw, lane, act);
+    }
+}
+
+}  // namespace scorus

@@ -181,10 +181,14 @@ def _check_arrays(ensemble: np.ndarray, logprob: Optional[np.ndarray]):
 class Sampler:
     """RAII handle over scorus_ctx: the device-resident (ensemble, logprob) plus RNG counters."""
 
-    def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, seed: int = 0, device: int = -1):
+    def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, seed: int = 0, device: int = -1,
+                 sequential_sum: bool = False):
+        """sequential_sum=True selects SCORUS_CFG_SEQUENTIAL_SUM: one lane per walker, log-density
+        summed left to right like the reference closures (bit-identical log-probs, ~2x slower)."""
         self._lib = L.load()
         self._ctx = C.c_void_p()
-        cfg = L.Cfg(n_walkers=n_walkers, dim=dim, device=device, seed=seed, flags=0, reserved=0)
+        cfg = L.Cfg(n_walkers=n_walkers, dim=dim, device=device, seed=seed,
+                    flags=L.CFG_SEQUENTIAL_SUM if sequential_sum else 0, reserved=0)
         _raise(self._lib.scorus_ctx_create(C.byref(self._ctx), C.byref(cfg)))
         self.n, self.dim, self.seed = n_walkers, dim, seed
         self.flogprob = None
@@ -220,7 +224,11 @@ class Sampler:
         self.flogprob = flogprob
 
     def set_stream(self, cuda_stream: int):
+        """Launch on a caller-owned cudaStream_t handle (0 = CUDA's legacy default stream)."""
         self._ok(self._lib.scorus_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def reset_stream(self):
+        self._ok(self._lib.scorus_reset_stream(self._ctx))
 
     # -- data movement
     def upload(self, ensemble: np.ndarray, logprob: Optional[np.ndarray] = None):
@@ -342,13 +350,14 @@ class DeviceRng:
     Sampler per (n, dim, plugin) so the free functions below do not re-create device state."""
     seed: int = 0
     device: int = -1
+    sequential_sum: bool = False
     _samplers: dict = field(default_factory=dict, repr=False)
 
     def sampler(self, flogprob: LogProb, n: int, dim: int) -> Sampler:
         key = (n, dim)
         s = self._samplers.get(key)
         if s is None:
-            s = Sampler(flogprob, n, dim, seed=self.seed, device=self.device)
+            s = Sampler(flogprob, n, dim, seed=self.seed, device=self.device, sequential_sum=self.sequential_sum)
             self._samplers[key] = s
         else:
             s.set_logprob(flogprob)
