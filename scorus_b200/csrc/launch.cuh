@@ -9,13 +9,16 @@ namespace scorus {
 
 struct StepParams;
 
+enum : int { KERNEL_SEQ = 0, KERNEL_COOP = 1, KERNEL_REG = 2 };
+
 struct Geometry {
     uint32_t row_bytes, row_stride, flag_words, stages, warps, grid;
     size_t smem;
+    int kernel;  // KERNEL_*
 };
 
 #define SCORUS_DECLARE_LAUNCHERS(NAME)                                                                   \
-    cudaError_t launch_step_##NAME(const StepParams &p, const Geometry &g, bool all_flags, bool sequential, \
+    cudaError_t launch_step_##NAME(const StepParams &p, const Geometry &g, bool all_flags, \
                                    cudaStream_t st);                                                     \
     cudaError_t launch_init_##NAME(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
 
@@ -29,8 +32,7 @@ SCORUS_DECLARE_LAUNCHERS(LpCorrGaussian)
 SCORUS_DECLARE_LAUNCHERS(LpMixture)
 
 // dispatch on the plugin id of include/scorus_b200.h (SCORUS_LP_*)
-cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, bool sequential,
-                        cudaStream_t st);
+cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st);
 cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
 
 }  // namespace scorus

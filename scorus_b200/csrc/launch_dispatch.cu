@@ -4,18 +4,17 @@
 
 namespace scorus {
 
-cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, bool sequential,
-                        cudaStream_t st)
+cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st)
 {
     switch (kind) {
-    case SCORUS_LP_GAUSSIAN: return launch_step_LpGaussian(p, g, all_flags, sequential, st);
-    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_step_LpBoundedGaussian(p, g, all_flags, sequential, st);
-    case SCORUS_LP_ROSENBROCK: return launch_step_LpRosenbrock(p, g, all_flags, sequential, st);
-    case SCORUS_LP_RASTRIGIN: return launch_step_LpRastrigin(p, g, all_flags, sequential, st);
-    case SCORUS_LP_BIMODAL2D: return launch_step_LpBimodal2d(p, g, all_flags, sequential, st);
-    case SCORUS_LP_STEP2D: return launch_step_LpStep2d(p, g, all_flags, sequential, st);
-    case SCORUS_LP_CORR_GAUSSIAN: return launch_step_LpCorrGaussian(p, g, all_flags, sequential, st);
-    case SCORUS_LP_MIXTURE: return launch_step_LpMixture(p, g, all_flags, sequential, st);
+    case SCORUS_LP_GAUSSIAN: return launch_step_LpGaussian(p, g, all_flags, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_step_LpBoundedGaussian(p, g, all_flags, st);
+    case SCORUS_LP_ROSENBROCK: return launch_step_LpRosenbrock(p, g, all_flags, st);
+    case SCORUS_LP_RASTRIGIN: return launch_step_LpRastrigin(p, g, all_flags, st);
+    case SCORUS_LP_BIMODAL2D: return launch_step_LpBimodal2d(p, g, all_flags, st);
+    case SCORUS_LP_STEP2D: return launch_step_LpStep2d(p, g, all_flags, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_step_LpCorrGaussian(p, g, all_flags, st);
+    case SCORUS_LP_MIXTURE: return launch_step_LpMixture(p, g, all_flags, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -3,6 +3,7 @@
 #include "launch.cuh"
 #include "step_coop_kernel.cuh"
 #include "step_kernel.cuh"
+#include "step_reg_kernel.cuh"
 
 #ifndef SCORUS_PLUGIN
 #error "compile with -DSCORUS_PLUGIN=LpGaussian (or another plugin of logprob.cuh)"
@@ -30,20 +31,28 @@ static int coop_group(uint32_t pitch)
 }
 
 cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const Geometry &g, bool all_flags,
-                                                    bool sequential, cudaStream_t st)
+                                                    cudaStream_t st)
 {
     using Plugin = SCORUS_PLUGIN;
-    if (sequential) {
+    if (g.kernel == KERNEL_SEQ) {
         if (all_flags) return launch_kernel(step_seq_kernel<Plugin, true>, p, g, st);
         return launch_kernel(step_seq_kernel<Plugin, false>, p, g, st);
     }
-    switch (coop_group(p.pitch)) {
-    case 2: return launch_kernel(step_coop_kernel<Plugin, 2>, p, g, st);
-    case 4: return launch_kernel(step_coop_kernel<Plugin, 4>, p, g, st);
-    case 8: return launch_kernel(step_coop_kernel<Plugin, 8>, p, g, st);
-    case 16: return launch_kernel(step_coop_kernel<Plugin, 16>, p, g, st);
-    default: return launch_kernel(step_coop_kernel<Plugin, 32>, p, g, st);
+    const uint32_t nvec = p.pitch / 2;
+    if (g.kernel == KERNEL_REG) {
+        if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4>, p, g, st);
+        if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2>, p, g, st);
+        switch (coop_group(p.pitch)) {
+        case 2: return launch_kernel(step_reg_kernel<Plugin, 2, 1>, p, g, st);
+        case 4: return launch_kernel(step_reg_kernel<Plugin, 4, 1>, p, g, st);
+        case 8: return launch_kernel(step_reg_kernel<Plugin, 8, 1>, p, g, st);
+        case 16: return launch_kernel(step_reg_kernel<Plugin, 16, 1>, p, g, st);
+        default: return launch_kernel(step_reg_kernel<Plugin, 32, 1>, p, g, st);
+        }
     }
+    // cooperative kernel with the old rows staged by TMA: any dimension that fits a tile
+    if (nvec >= 32) return launch_kernel(step_coop_kernel<Plugin, 32>, p, g, st);
+    return launch_kernel(step_coop_kernel<Plugin, 8>, p, g, st);
 }
 
 cudaError_t SCORUS_CAT(launch_init_, SCORUS_PLUGIN)(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st)

@@ -322,34 +322,54 @@ static int step_geometry(scorus_ctx *ctx, Geometry *g)
     const size_t tile = 32u * (size_t)g->row_stride;
     const size_t budget = (size_t)ctx->smem_optin;
     const int want_stages = env_int("SCORUS_STAGES", 0), want_warps = env_int("SCORUS_WARPS", 0);
-    auto fit = [&](uint32_t s) {
-        const size_t per_warp = s * tile + flag_bytes;
-        uint32_t w = 16;
-        while (w >= 1 && ((8u * w * s + 127u) & ~127u) + w * per_warp > budget) --w;
-        return w;
-    };
-    uint32_t best_s, best_w;
-    if (want_stages >= 2 && want_stages <= 4) {
-        best_s = (uint32_t)want_stages;
-        best_w = fit(best_s);
-    } else {
-        // three stages (two tiles in flight while one is computed) when at least four warps fit
-        best_s = 3;
-        best_w = fit(3);
-        if (best_w < 4) {
-            uint32_t w2 = fit(2);
-            if (w2 > best_w) { best_s = 2; best_w = w2; }
-        }
-    }
-    if (best_w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
-    if (want_warps > 0 && (uint32_t)want_warps < best_w) best_w = (uint32_t)want_warps;
-    g->stages = best_s;
-    g->warps = best_w;
     const uint32_t ntiles = (uint32_t)((ctx->n + 31u) / 32u);
+    const char *force = getenv("SCORUS_KERNEL");
+
+    // kernel choice: sequential sums on request; else register streaming (dim <= 256); else the
+    // cooperative kernel that stages old rows by TMA
+    g->kernel = ctx->sequential ? KERNEL_SEQ : (ctx->pitch <= 256 ? KERNEL_REG : KERNEL_COOP);
+    if (force && !ctx->sequential) {
+        if (!strcmp(force, "coop")) g->kernel = KERNEL_COOP;
+        else if (!strcmp(force, "reg") && ctx->pitch <= 256) g->kernel = KERNEL_REG;
+        else if (!strcmp(force, "seq")) g->kernel = KERNEL_SEQ;
+    }
+
+    if (g->kernel == KERNEL_REG) {
+        // one tile of proposed rows + the flag words per warp; at most 14 warps (448 threads)
+        const size_t per_warp = tile + flag_bytes;
+        uint32_t w = 14;
+        while (w >= 1 && w * per_warp > budget) --w;
+        if (w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
+        if (want_warps > 0 && (uint32_t)want_warps < w) w = (uint32_t)want_warps;
+        g->stages = 1;
+        g->warps = w;
+        g->smem = w * per_warp;
+    } else {
+        auto fit = [&](uint32_t s) {
+            const size_t per_warp = s * tile + flag_bytes;
+            uint32_t w = 16;
+            while (w >= 1 && ((8u * w * s + 127u) & ~127u) + w * per_warp > budget) --w;
+            return w;
+        };
+        uint32_t best_s, best_w;
+        if (want_stages >= 2 && want_stages <= 4) {
+            best_s = (uint32_t)want_stages;
+            best_w = fit(best_s);
+        } else {
+            // measured on B200 (profiles/r1_notes.md): these kernels are bound by warps per SM, not
+            // by prefetch depth, so two stages (more warps) beat three
+            best_s = 2;
+            best_w = fit(2);
+        }
+        if (best_w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
+        if (want_warps > 0 && (uint32_t)want_warps < best_w) best_w = (uint32_t)want_warps;
+        g->stages = best_s;
+        g->warps = best_w;
+        g->smem = ((8u * g->warps * g->stages + 127u) & ~127u) + (size_t)g->warps * (g->stages * tile + flag_bytes);
+    }
     uint32_t grid = (ntiles + g->warps - 1) / g->warps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     g->grid = grid;
-    g->smem = ((8u * g->warps * g->stages + 127u) & ~127u) + (size_t)g->warps * (g->stages * tile + flag_bytes);
     return SCORUS_OK;
 }
 
@@ -516,7 +536,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
             ++ctx->launches;
             p.order = ctx->d_order;
         }
-        cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->sequential, ctx->stream);
+        cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
         ++ctx->launches;
         ++ctx->step;
@@ -576,7 +596,7 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
     p.order = ctx->d_order; p.z_in = ctx->d_z; p.u_in = ctx->d_u; p.flags_in = ctx->d_flags;
     p.flag_len = (uint32_t)flag_len; p.flag_kind = SCORUS_UFS_MASK; p.accepted_out = ctx->d_acc;
     p.step = ctx->step;
-    cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->sequential, ctx->stream);
+    cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     ctx->proposed += n;

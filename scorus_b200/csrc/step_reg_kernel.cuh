@@ -1,0 +1,248 @@
+// step_reg_kernel.cuh -- K1: the fused stretch-move step, register-streaming version (default
+// for dim <= 256).
+//
+// One launch does everything src/mcmc/ensemble_sample.rs:135-189 does per step: partner pick
+// (:135-148), z draw (:149 -> utils.rs:33-45), update flags (:150-153 -> :38-54), proposal
+// (:155-159 -> :57-75 -> utils.rs:47-56), log-density (:161) and Metropolis accept (:164-189).
+//
+// Why a third shape (profiles/r1_notes.md has the measurements): staging the OLD rows in shared
+// memory (step_kernel.cuh, step_coop_kernel.cuh) costs two tiles of shared memory per warp, which
+// caps an SM at 6 warps for D = 64 -- 1.5 warps per scheduler cannot hide fp64 / LDS latency and
+// the kernel ran at 43 % of the HBM roofline, issue-bound.  Here the old rows never touch shared
+// memory:
+//   * a group of G lanes owns a pair; lane j loads double2 chunk j (+ k*G) of BOTH rows straight
+//     into registers with 128-bit coalesced loads (a row is one contiguous 16*G-byte burst), one
+//     block of 8 rows ahead of the arithmetic (software pipeline, 4 KB in flight per warp);
+//   * the proposals y = x1*z + x2*(1-z) (both walkers of the pair, from the old values) and their
+//     log-density terms are computed from registers; Rosenbrock's neighbour coordinate comes from
+//     the next lane by shuffle;
+//   * only the PROPOSED rows go to shared memory (one tile per warp -> 13 warps per SM at D = 64),
+//     and only accepted ones leave it, through TMA bulk stores (cp.async.bulk shared->global);
+//   * per-lane partial sums are combined by a transposed shuffle tree so that lane = walker for the
+//     scalar tail (exp, accept), as in the cooperative kernel.
+// HBM traffic stays at the algorithmic 16*D+16 bytes per walker-step (less: rejected rows are not
+// written).  Positions are bit-identical to the reference's rounding sequence; log-probs differ
+// from a left-to-right sum by a few ulp of the sum of |terms| (fixed tree, deterministic).
+#pragma once
+#include "step_coop_kernel.cuh"  // transpose_reduce
+#include "tile_common.cuh"
+
+namespace scorus {
+
+template <int G, int ITERS>
+struct RegGeom {
+    static constexpr int kRowsPerBlock = (G < 8 / ITERS) ? G : (8 / ITERS < 2 ? 2 : 8 / ITERS);  // GB
+    static constexpr int kPairs = kRowsPerBlock / 2;
+    static constexpr int kBlocks = G / kRowsPerBlock;
+};
+
+template <class Plugin, int G, int ITERS>
+__global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
+{
+    using Geo = RegGeom<G, ITERS>;
+    constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t tile_bytes = 32u * p.row_stride;
+    const uint32_t warp_bytes = tile_bytes + ((p.flag_words * 128u + 127u) & ~127u);
+    unsigned char *ytile = smem + (size_t)warp * warp_bytes;
+    uint32_t *flagw = reinterpret_cast<uint32_t *>(ytile + tile_bytes);
+
+    const uint32_t gwarp = blockIdx.x * p.warps + warp;
+    const uint32_t nwarps = gridDim.x * p.warps;
+    const uint32_t grp = lane / G, j = lane % G;
+    const uint32_t nvec = p.pitch >> 1;
+    const bool all_flags = p.flag_kind == 1u;
+    unsigned long long n_acc = 0;
+
+    Plugin plug;
+    plug.init(p.pparams, p.nparams, p.dim);
+
+    // walker at matching position `pos` (keys of the pairing bijection cached per rung)
+    uint32_t key_rung = 0xFFFFFFFFu;
+    BijKeys K;
+    auto walker_of = [&](uint32_t pos) -> uint32_t {
+        if (p.order) return __ldg(p.order + pos);
+        const uint32_t r = pos / p.npb;
+        if (r != key_rung) { K = bij_keys(p.seed, p.step, ST_PERM, r); key_rung = r; }
+        return r * p.npb + bij(pos - r * p.npb, p.npb, p.bij_bits, K);
+    };
+
+    // loads block `blk` of a tile whose lane = walker ids are `wt`: rows wl = grp*G + blk*GB + i
+    auto load_block = [&](double2 (&x)[GB][ITERS], uint32_t wt, int blk) {
+#pragma unroll
+        for (int i = 0; i < GB; ++i) {
+            const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
+            const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
+            const double2 *src = reinterpret_cast<const double2 *>(p.ens + (size_t)row * p.pitch);
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t c = (uint32_t)it * G + j;
+                x[i][it] = c < nvec ? __ldcs(src + c) : make_double2(0.0, 0.0);  // streamed: read exactly once
+            }
+        }
+    };
+
+    uint32_t tile = gwarp;
+    if (tile >= p.ntiles) return;
+    uint32_t w;
+    bool act;
+    {
+        const uint32_t pos = tile * 32u + lane;
+        act = pos < p.n;
+        w = act ? walker_of(pos) : 0u;
+    }
+    double lp_old = act ? __ldg(p.lp + w) : 0.0;
+    double2 xn[GB][ITERS];
+    load_block(xn, w, 0);
+
+    for (;;) {
+        // ---- P1: lane = walker: z, u, flags, (nphi-1) ln z ----
+        double z, u;
+        if (p.z_in) {
+            z = act ? __ldg(p.z_in + w) : 1.0;
+            u = act ? __ldg(p.u_in + w) : 1.0;
+        } else {
+            const U4 r = draw(p.seed, p.step, ST_ZU, w, 0);
+            z = z_from_uniform(u53(r.x, r.y), p.inv_sqrt_a, p.z_range);
+            u = u53(r.z, r.w);
+        }
+        // the previous tile's accepted rows must have left the y tile / flag words before reuse
+        bulk_wait_read_all();
+        __syncwarp();
+        uint32_t nphi = p.dim;
+        if (!all_flags) nphi = gen_flags(p, w, flagw, lane, act);
+        const double lz = (double)(nphi - 1u) * log(z);  // ensemble_sample.rs:184, first summand
+        const double beta = __ldg(p.beta + (act ? w / p.npb : 0u));
+        __syncwarp();  // flag words visible to the whole warp
+
+        // ids of the next tile (its first block is prefetched during this tile's last block)
+        const uint32_t tile_n = tile + nwarps;
+        uint32_t w_n = 0;
+        bool act_n = false;
+        double lp_n = 0.0;
+        if (tile_n < p.ntiles) {
+            const uint32_t pos = tile_n * 32u + lane;
+            act_n = pos < p.n;
+            w_n = act_n ? walker_of(pos) : 0u;
+            if (act_n) lp_n = __ldg(p.lp + w_n);
+        }
+
+        double tot[Plugin::kAcc];
+#pragma unroll
+        for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
+
+#pragma unroll 1
+        for (int blk = 0; blk < NB; ++blk) {
+            double2 xc[GB][ITERS];
+#pragma unroll
+            for (int i = 0; i < GB; ++i)
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
+            if (blk + 1 < NB) load_block(xn, w, blk + 1);
+            else if (tile_n < p.ntiles) load_block(xn, w_n, 0);
+
+            double acc[Plugin::kAcc][GB];
+#pragma unroll
+            for (int pr = 0; pr < PB; ++pr) {
+                const uint32_t wa = grp * G + (uint32_t)(blk * GB + 2 * pr), wb = wa + 1u;
+                const double za = __shfl_sync(0xffffffffu, z, wa), zb = __shfl_sync(0xffffffffu, z, wb);
+                const double omza = 1.0 - za, omzb = 1.0 - zb;
+                double2 *rowa = reinterpret_cast<double2 *>(ytile + wa * p.row_stride);
+                double2 *rowb = reinterpret_cast<double2 *>(ytile + wb * p.row_stride);
+                double2 ya[ITERS], yb[ITERS];
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const uint32_t c = (uint32_t)it * G + j;
+                    const uint32_t d = 2u * c;
+                    const double2 xa = xc[2 * pr][it], xb = xc[2 * pr + 1][it];
+                    uint32_t fa = 3u, fb = 3u;
+                    if (!all_flags) {
+                        const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
+                        fa = flagw[wd * 32u + wa] >> (d & 31u);
+                        fb = flagw[wd * 32u + wb] >> (d & 31u);
+                    }
+                    // scale_vec, src/mcmc/utils.rs:55: (x1*z) + (x2*(1-z)), three roundings; then
+                    // propose_move, ensemble_sample.rs:69-71: coordinates whose flag is clear stay
+                    { double t1 = xa.x * za, t2 = xb.x * omza; ya[it].x = (fa & 1u) ? t1 + t2 : xa.x; }
+                    { double t1 = xa.y * za, t2 = xb.y * omza; ya[it].y = (fa & 2u) ? t1 + t2 : xa.y; }
+                    { double t1 = xb.x * zb, t2 = xa.x * omzb; yb[it].x = (fb & 1u) ? t1 + t2 : xb.x; }
+                    { double t1 = xb.y * zb, t2 = xa.y * omzb; yb[it].y = (fb & 2u) ? t1 + t2 : xb.y; }
+                    if (c < nvec) {
+                        rowa[c] = ya[it];
+                        rowb[c] = yb[it];
+                    }
+                }
+                // log-density terms from registers; coordinate d+2 lives in the next lane
+                double pa[Plugin::kAcc], pb[Plugin::kAcc];
+#pragma unroll
+                for (int a = 0; a < Plugin::kAcc; ++a) { pa[a] = 0.0; pb[a] = 0.0; }
+                if constexpr (!Plugin::kNeedsRow) {
+#pragma unroll
+                    for (int it = 0; it < ITERS; ++it) {
+                        const uint32_t c = (uint32_t)it * G + j;
+                        const uint32_t d = 2u * c;
+                        double nba = __shfl_down_sync(0xffffffffu, ya[it].x, 1, G);
+                        double nbb = __shfl_down_sync(0xffffffffu, yb[it].x, 1, G);
+                        if (ITERS > 1 && it + 1 < ITERS) {  // last lane of the group: next trip, lane 0
+                            const double wa0 = __shfl_sync(0xffffffffu, ya[it + 1 < ITERS ? it + 1 : it].x, 0, G);
+                            const double wb0 = __shfl_sync(0xffffffffu, yb[it + 1 < ITERS ? it + 1 : it].x, 0, G);
+                            if (j == G - 1) { nba = wa0; nbb = wb0; }
+                        }
+                        if (c < nvec) {
+                            const bool has1 = d + 1u < p.dim, hasnb = d + 2u < p.dim;
+                            plug.terms(d, ya[it].x, ya[it].y, nba, has1, hasnb, pa);
+                            plug.terms(d, yb[it].x, yb[it].y, nbb, has1, hasnb, pb);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < Plugin::kAcc; ++a) { acc[a][2 * pr] = pa[a]; acc[a][2 * pr + 1] = pb[a]; }
+            }
+            if constexpr (!Plugin::kNeedsRow) {
+#pragma unroll
+                for (int a = 0; a < Plugin::kAcc; ++a) {
+                    double r = transpose_reduce<GB>(acc[a], lane);
+#pragma unroll
+                    for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
+                    if ((int)(j / GB) == blk) tot[a] = r;
+                }
+            }
+        }
+        fence_proxy_async();  // my writes of the proposed rows -> visible to the TMA stores below
+        __syncwarp();
+
+        // ---- P5: lane = walker: Metropolis accept, ensemble_sample.rs:181-188 ----
+        unsigned char *own_b = ytile + lane * p.row_stride;
+        double lp_new;
+        if constexpr (Plugin::kNeedsRow) {
+            lp_new = plug.finish_row(reinterpret_cast<const double *>(own_b));
+        } else {
+            lp_new = plug.finish_acc(tot);
+        }
+        const double delta_lp = lp_new - lp_old;
+        const double q = exp(lz + delta_lp * beta);
+        const bool accept = act && (u < q);
+        if (accept) {
+            bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
+            p.lp[w] = lp_new;
+            ++n_acc;
+        }
+        bulk_commit();
+        if (p.accepted_out && act) p.accepted_out[w] = accept ? 1 : 0;
+
+        if (tile_n >= p.ntiles) break;
+        tile = tile_n;
+        w = w_n;
+        act = act_n;
+        lp_old = lp_n;
+    }
+
+    bulk_wait_all();
+    for (int off = 16; off; off >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, off);
+    if (lane == 0 && n_acc) atomicAdd(p.stats, n_acc);
+}
+
+}  // namespace scorus
