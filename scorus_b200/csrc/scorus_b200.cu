@@ -336,9 +336,13 @@ static int step_geometry(scorus_ctx *ctx, Geometry *g)
 
     if (g->kernel == KERNEL_REG) {
         // one tile of proposed rows + the flag words per warp; at most 14 warps (448 threads)
+        // leave SCORUS_L1_KB (default 32) of the SM's unified array to L1: the row loads stream through
+        // it, and with the carve-out at its maximum the kernel ran 12 % slower (profiles/r1_notes.md)
         const size_t per_warp = tile + flag_bytes;
+        const size_t l1_keep = (size_t)env_int("SCORUS_L1_KB", 32) * 1024u;
         uint32_t w = 14;
         while (w >= 1 && w * per_warp > budget) --w;
+        while (w > 8 && w * per_warp + l1_keep > budget) --w;
         if (w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
         if (want_warps > 0 && (uint32_t)want_warps < w) w = (uint32_t)want_warps;
         g->stages = 1;
@@ -475,6 +479,7 @@ static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta
     p->flag_words = g->flag_words;
     p->ntiles = (uint32_t)((ctx->n + 31u) / 32u);
     p->bij_bits = bij_bits(p->npb);
+    p->debug_identity = env_int("SCORUS_DEBUG_IDENTITY", 0) ? 1u : 0u;
     return SCORUS_OK;
 }
 

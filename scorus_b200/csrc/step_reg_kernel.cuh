@@ -29,6 +29,14 @@
 
 namespace scorus {
 
+// 128-bit streaming load: read once, do not keep in L1 (the shared-memory carve-out leaves little)
+__device__ __forceinline__ double2 ld_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 template <int G, int ITERS>
 struct RegGeom {
     static constexpr int kRowsPerBlock = (G < 8 / ITERS) ? G : (8 / ITERS < 2 ? 2 : 8 / ITERS);  // GB
@@ -65,6 +73,7 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
     BijKeys K;
     auto walker_of = [&](uint32_t pos) -> uint32_t {
         if (p.order) return __ldg(p.order + pos);
+        if (p.debug_identity) return pos;
         const uint32_t r = pos / p.npb;
         if (r != key_rung) { K = bij_keys(p.seed, p.step, ST_PERM, r); key_rung = r; }
         return r * p.npb + bij(pos - r * p.npb, p.npb, p.bij_bits, K);
@@ -79,8 +88,10 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
             const double2 *src = reinterpret_cast<const double2 *>(p.ens + (size_t)row * p.pitch);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
+                // lanes beyond the row re-read its last chunk (never used): an unconditional load keeps
+                // the result out of any select, so nothing waits on it before the arithmetic does
                 const uint32_t c = (uint32_t)it * G + j;
-                x[i][it] = c < nvec ? __ldcs(src + c) : make_double2(0.0, 0.0);  // streamed: read exactly once
+                x[i][it] = ld_stream(src + (c < nvec ? c : nvec - 1u));  // streamed: read exactly once
             }
         }
     };

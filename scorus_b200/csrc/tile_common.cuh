@@ -29,6 +29,7 @@ struct StepParams {
     uint32_t row_bytes, row_stride;           // bytes copied per row / shared-memory row stride
     uint32_t stages, warps, ntiles, flag_words;
     uint32_t bij_bits;
+    uint32_t debug_identity;  // measurement only (SCORUS_DEBUG_IDENTITY=1): position j holds walker j
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
@@ -95,6 +96,7 @@ __device__ __forceinline__ void fence_mbar_init()
 __device__ __forceinline__ uint32_t walker_at(const StepParams &p, uint32_t j)
 {
     if (p.order) return __ldg(p.order + j);
+    if (p.debug_identity) return j;
     uint32_t r = j / p.npb;
     uint32_t k = j - r * p.npb;
     BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r);
