@@ -1,0 +1,87 @@
+//! Raw bindings of `include/scorus_b200.h` (ABI version 1).  One declaration per C entry point;
+//! the comment on each names the reference function it replaces.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct scorus_ctx {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct scorus_cfg {
+    pub n_walkers: u64,
+    pub dim: u32,
+    pub device: i32,
+    pub seed: u64,
+    pub flags: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct scorus_ufs {
+    pub kind: i32,
+    pub reserved: i32,
+    pub prob: f64,
+    pub mask: *const u8,
+    pub mask_len: usize,
+}
+
+pub const SCORUS_OK: c_int = 0;
+pub const SCORUS_UFS_PROB: i32 = 0;
+pub const SCORUS_UFS_ALL: i32 = 1;
+pub const SCORUS_UFS_ONE_HOT_CYCLE: i32 = 2;
+pub const SCORUS_UFS_MASK: i32 = 3;
+pub const SCORUS_CFG_SEQUENTIAL_SUM: u32 = 1;
+
+extern "C" {
+    pub fn scorus_abi_version() -> c_int;
+    pub fn scorus_status_string(status: c_int) -> *const c_char;
+    pub fn scorus_device_count() -> c_int;
+    /// asserts of src/mcmc/ensemble_sample.rs:127-133
+    pub fn scorus_check_sample_args(n_walkers: usize, logprob_len: usize, nbeta: usize) -> c_int;
+    /// panic of src/mcmc/utils.rs:91-95
+    pub fn scorus_check_beta_order(beta_list: *const f64, nbeta: usize) -> c_int;
+    pub fn scorus_ctx_create(out: *mut *mut scorus_ctx, cfg: *const scorus_cfg) -> c_int;
+    pub fn scorus_ctx_destroy(ctx: *mut scorus_ctx);
+    pub fn scorus_last_error(ctx: *const scorus_ctx) -> *const c_char;
+    /// replaces the `flogprob: &F` argument (src/mcmc/ensemble_sample.rs:88,102)
+    pub fn scorus_set_logprob(ctx: *mut scorus_ctx, kind: c_int, params: *const f64, nparams: usize) -> c_int;
+    pub fn scorus_upload(ctx: *mut scorus_ctx, ensemble: *const f64, logprob: *const f64) -> c_int;
+    pub fn scorus_download(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64) -> c_int;
+    /// init_logprob, src/mcmc/ensemble_sample.rs:77-85
+    pub fn scorus_init_logprob(ctx: *mut scorus_ctx) -> c_int;
+    /// sample, src/mcmc/ensemble_sample.rs:87-105
+    pub fn scorus_sample(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, nsteps: u64) -> c_int;
+    /// sample_pt, src/mcmc/ensemble_sample.rs:107-190
+    pub fn scorus_sample_pt(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, beta_list: *const f64,
+                            nbeta: usize, nsteps: u64) -> c_int;
+    pub fn scorus_sample_pt_fixed(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize, partner: *const u32,
+                                  z: *const f64, flags: *const u8, flag_len: usize, u: *const f64,
+                                  accepted_out: *mut u8) -> c_int;
+    /// draw_z, src/mcmc/utils.rs:33-45
+    pub fn scorus_draw_z(ctx: *mut scorus_ctx, a: f64, count: usize, out: *mut f64) -> c_int;
+    /// swap_walkers, src/mcmc/utils.rs:72-112
+    pub fn scorus_swap_walkers(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize) -> c_int;
+    pub fn scorus_swap_walkers_fixed(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize, jvec: *const u32,
+                                     r: *const f64, swapped_out: *mut u8) -> c_int;
+    pub fn scorus_sample_pt_host(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64, logprob_len: usize,
+                                 a: f64, ufs: *const scorus_ufs, beta_list: *const f64, nbeta: usize) -> c_int;
+    pub fn scorus_swap_walkers_host(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64,
+                                    logprob_len: usize, beta_list: *const f64, nbeta: usize) -> c_int;
+    pub fn scorus_sync(ctx: *mut scorus_ctx) -> c_int;
+    pub fn scorus_set_stream(ctx: *mut scorus_ctx, cuda_stream: *mut c_void) -> c_int;
+    pub fn scorus_reset_stream(ctx: *mut scorus_ctx) -> c_int;
+    pub fn scorus_get_stream(ctx: *mut scorus_ctx) -> *mut c_void;
+    pub fn scorus_device_buffers(ctx: *mut scorus_ctx, ensemble: *mut *mut f64, pitch_elems: *mut usize,
+                                 logprob: *mut *mut f64) -> c_int;
+    pub fn scorus_get_counters(ctx: *const scorus_ctx, step: *mut u64, swap_call: *mut u64, onehot: *mut u64) -> c_int;
+    pub fn scorus_set_counters(ctx: *mut scorus_ctx, step: u64, swap_call: u64, onehot: u64) -> c_int;
+    pub fn scorus_get_stats(ctx: *mut scorus_ctx, accepted: *mut u64, proposed: *mut u64, swapped: *mut u64,
+                            swap_proposed: *mut u64) -> c_int;
+    pub fn scorus_launch_count(ctx: *const scorus_ctx) -> u64;
+    pub fn scorus_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn scorus_host_free(p: *mut c_void);
+}

@@ -1,0 +1,153 @@
+//! Safe wrapper with the reference's names and argument order (NOT compiled in this repo's image:
+//! no Rust toolchain; see rust/README.md).
+//!
+//! ```text
+//! reference (src/mcmc/ensemble_sample.rs:107)              this crate
+//! sample_pt(&flogprob, &mut ensemble, &mut lp,             sample_pt(&flogprob, &mut ensemble, &mut lp,
+//!           &mut rng, a, &mut ufs, &beta_list)                       &mut rng, a, &mut ufs, &beta_list)
+//!   flogprob: &F where F: Fn(&V) -> T                        flogprob: &LogProb   (device plugin id + params)
+//!   rng: &mut U where U: Rng                                 rng: &mut DeviceRng  (seed; owns the device context)
+//! ```
+use scorus::linear_space::IndexableLinearSpace;
+use scorus_b200_sys as sys;
+use std::collections::HashMap;
+use std::ffi::CStr;
+
+/// src/mcmc/mcmc_errors.rs:1-7 (the reference declares it and then panics instead)
+#[derive(Debug, Clone, Copy, PartialEq, Eq)]
+pub enum McmcErr {
+    NWalkersIsZero = 1,
+    NWalkersIsNotEven = 2,
+    NWalkersMismatchesNBeta = 3,
+    BetaNotInDecrOrd = 4,
+}
+
+fn check(code: i32, ctx: *const sys::scorus_ctx) {
+    if code == sys::SCORUS_OK {
+        return;
+    }
+    // the reference panics (assert! at ensemble_sample.rs:130-133, panic! at utils.rs:93-95): so do we
+    let what = unsafe { CStr::from_ptr(sys::scorus_status_string(code)) }.to_string_lossy().into_owned();
+    let detail = if ctx.is_null() { String::new() } else {
+        unsafe { CStr::from_ptr(sys::scorus_last_error(ctx)) }.to_string_lossy().into_owned()
+    };
+    panic!("scorus-b200: {what} {detail}");
+}
+
+/// Device-side log-density (replaces `F: Fn(&V) -> T + Send + Sync`).
+#[derive(Clone, Debug)]
+pub struct LogProb { pub kind: i32, pub params: Vec<f64> }
+impl LogProb {
+    pub fn gaussian(c: f64) -> Self { Self { kind: 0, params: vec![c] } }          // examples/test_emcee.rs:18-24
+    pub fn bounded_gaussian(limit: f64) -> Self { Self { kind: 1, params: vec![limit] } }
+    pub fn rosenbrock() -> Self { Self { kind: 2, params: vec![] } }               // examples/test_emcee.rs:26-32
+    pub fn rastrigin(a: f64) -> Self { Self { kind: 3, params: vec![a] } }         // examples/sample_rastrigin.rs:17-25
+    pub fn bimodal2d() -> Self { Self { kind: 4, params: vec![] } }                // examples/sample_bimodal.rs:46-54
+}
+
+/// src/mcmc/ensemble_sample.rs:25-32
+pub enum UpdateFlagSpec<'a> {
+    Prob(f64),
+    All,
+    Func(&'a mut dyn FnMut() -> Vec<bool>),
+    /// the cycling closure of examples/sample_high_dim.rs:59-65, evaluated on the device
+    OneHotCycle,
+}
+
+/// RAII owner of the device buffers (`scorus_ctx`).
+pub struct Sampler { ctx: *mut sys::scorus_ctx, n: usize, dim: usize }
+impl Sampler {
+    pub fn new(flogprob: &LogProb, n: usize, dim: usize, seed: u64) -> Self {
+        let cfg = sys::scorus_cfg { n_walkers: n as u64, dim: dim as u32, device: -1, seed, flags: 0, reserved: 0 };
+        let mut ctx = std::ptr::null_mut();
+        check(unsafe { sys::scorus_ctx_create(&mut ctx, &cfg) }, std::ptr::null());
+        let s = Self { ctx, n, dim };
+        s.set_logprob(flogprob);
+        s
+    }
+    pub fn set_logprob(&self, f: &LogProb) {
+        check(unsafe { sys::scorus_set_logprob(self.ctx, f.kind, f.params.as_ptr(), f.params.len()) }, self.ctx);
+    }
+    fn with_ufs<R>(&self, ufs: &mut UpdateFlagSpec, body: impl FnOnce(&sys::scorus_ufs) -> R) -> R {
+        let mut mask: Vec<u8> = Vec::new();
+        let mut c = sys::scorus_ufs { kind: sys::SCORUS_UFS_ALL, reserved: 0, prob: 0.0, mask: std::ptr::null(), mask_len: 0 };
+        match ufs {
+            UpdateFlagSpec::Prob(p) => { c.kind = sys::SCORUS_UFS_PROB; c.prob = *p; }
+            UpdateFlagSpec::All => {}
+            UpdateFlagSpec::OneHotCycle => { c.kind = sys::SCORUS_UFS_ONE_HOT_CYCLE; }
+            UpdateFlagSpec::Func(f) => {
+                // called once per walker, in walker order, as ensemble_sample.rs:150-153 does
+                let mut len = 0;
+                for i in 0..self.n {
+                    let v = f();
+                    if i == 0 { len = v.len(); }
+                    assert!(v.len() == len && len <= self.dim);
+                    mask.extend(v.into_iter().map(|b| b as u8));
+                }
+                c.kind = sys::SCORUS_UFS_MASK; c.mask = mask.as_ptr(); c.mask_len = len;
+            }
+        }
+        body(&c)
+    }
+    pub fn sample_pt_host(&self, ens: &mut [f64], lp: &mut [f64], a: f64, ufs: &mut UpdateFlagSpec, beta: &[f64]) {
+        let (ctx, n_lp) = (self.ctx, lp.len());
+        let (pe, pl) = (ens.as_mut_ptr(), lp.as_mut_ptr());
+        self.with_ufs(ufs, |c| check(unsafe {
+            sys::scorus_sample_pt_host(ctx, pe, pl, n_lp, a, c, beta.as_ptr(), beta.len()) }, ctx));
+    }
+    pub fn swap_walkers_host(&self, ens: &mut [f64], lp: &mut [f64], beta: &[f64]) {
+        check(unsafe { sys::scorus_swap_walkers_host(self.ctx, ens.as_mut_ptr(), lp.as_mut_ptr(), lp.len(),
+                                                     beta.as_ptr(), beta.len()) }, self.ctx);
+    }
+}
+impl Drop for Sampler { fn drop(&mut self) { unsafe { sys::scorus_ctx_destroy(self.ctx) } } }
+
+/// Replaces `rng: &mut U`: the seed of the counter-based device streams; caches one context per shape.
+pub struct DeviceRng { pub seed: u64, cache: HashMap<(usize, usize), Sampler> }
+impl DeviceRng {
+    pub fn new(seed: u64) -> Self { Self { seed, cache: HashMap::new() } }
+    fn sampler(&mut self, f: &LogProb, n: usize, dim: usize) -> &Sampler {
+        let seed = self.seed;
+        let s = self.cache.entry((n, dim)).or_insert_with(|| Sampler::new(f, n, dim, seed));
+        s.set_logprob(f);
+        s
+    }
+}
+
+fn flatten<V: IndexableLinearSpace<f64>>(ensemble: &[V]) -> (Vec<f64>, usize) {
+    let dim = ensemble[0].dimension();
+    let mut flat = Vec::with_capacity(ensemble.len() * dim);
+    for w in ensemble { for k in 0..dim { flat.push(w[k]); } }
+    (flat, dim)
+}
+fn unflatten<V: IndexableLinearSpace<f64>>(flat: &[f64], ensemble: &mut [V], dim: usize) {
+    for (i, w) in ensemble.iter_mut().enumerate() { for k in 0..dim { w[k] = flat[i * dim + k]; } }
+}
+
+/// src/mcmc/ensemble_sample.rs:107-190
+pub fn sample_pt<'a, V>(flogprob: &LogProb, ensemble: &mut [V], cached_logprob: &mut [f64], rng: &mut DeviceRng,
+                        a: f64, ufs: &mut UpdateFlagSpec<'a>, beta_list: &[f64])
+where V: Clone + IndexableLinearSpace<f64> + Sync + Send {
+    check(unsafe { sys::scorus_check_sample_args(ensemble.len(), cached_logprob.len(), beta_list.len()) }, std::ptr::null());
+    let (mut flat, dim) = flatten(ensemble);
+    rng.sampler(flogprob, ensemble.len(), dim).sample_pt_host(&mut flat, cached_logprob, a, ufs, beta_list);
+    unflatten(&flat, ensemble, dim);
+}
+
+/// src/mcmc/ensemble_sample.rs:87-105
+pub fn sample<'a, V>(flogprob: &LogProb, ensemble: &mut [V], cached_logprob: &mut [f64], rng: &mut DeviceRng, a: f64,
+                     ufs: &mut UpdateFlagSpec<'a>)
+where V: Clone + IndexableLinearSpace<f64> + Sync + Send {
+    sample_pt(flogprob, ensemble, cached_logprob, rng, a, ufs, &[1.0])
+}
+
+/// src/mcmc/utils.rs:72-112 (silently does nothing when the lengths differ, :88)
+pub fn swap_walkers<V>(ensemble: &mut [V], logprob: &mut [f64], rng: &mut DeviceRng, beta_list: &[f64])
+where V: Clone + IndexableLinearSpace<f64> {
+    let nbeta = beta_list.len();
+    assert!(nbeta * (ensemble.len() / nbeta) == ensemble.len());
+    if ensemble.len() != logprob.len() { return; }
+    let (mut flat, dim) = flatten(ensemble);
+    rng.sampler(&LogProb::gaussian(0.5), ensemble.len(), dim).swap_walkers_host(&mut flat, logprob, beta_list);
+    unflatten(&flat, ensemble, dim);
+}

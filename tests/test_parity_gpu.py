@@ -207,3 +207,55 @@ def test_free_functions_reference_call_shape(sb, oracle):
     assert np.array_equal(sb.scale_vec(p1, p2, 0.81), p1 * 0.81 + p2 * (1.0 - 0.81))
     zs = np.array([sb.draw_z(dev, 2.0) for _ in range(200)])
     assert np.all(zs >= 0.5) and np.all(zs < 2.0)
+
+
+def test_cpp_host_layer_matches_python_mirror(sb, tmp_path):
+    """include/scorus_b200.hpp (reference names / argument order in C++) drives the same C ABI:
+    the example-shaped loops of tests/cpp/driver_like_reference.cpp must print what the Python
+    mirror computes for the same seeds."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "driver")
+    libdir = os.path.join(root, "scorus_b200", "lib")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "driver_like_reference.cpp"), "-o", exe,
+                    "-L", libdir, "-lscorus_b200", f"-Wl,-rpath,{libdir}"], check=True, env=env)
+    niter = 30
+    out = subprocess.run([exe, str(niter)], check=True, capture_output=True, text=True, env=env).stdout.splitlines()
+
+    st = [12345]
+
+    def lcg():
+        st[0] = (st[0] * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        return float(st[0] >> 11) * (1.0 / 9007199254740992.0)
+
+    # A: test_emcee.rs shape
+    ens = np.array([[0.9 + 0.2 * lcg() for _ in range(8)] for _ in range(16)])
+    lp = np.empty(16)
+    dev = sb.DeviceRng(seed=7)
+    f = sb.Rosenbrock()
+    sb.init_logprob(f, ens, lp, dev)
+    for _ in range(niter):
+        sb.sample(f, ens, lp, dev, 2.0, sb.UpdateFlagSpec.Prob(0.5))
+    got = [ln.split() for ln in out if ln.startswith("A ")]
+    assert len(got) == 16
+    for i, t in enumerate(got):
+        assert (float(t[2]), float(t[3]), float(t[4])) == (ens[i, 0], ens[i, 7], lp[i])
+    # B: sample_rastrigin.rs shape
+    blist = [2.0 ** -i for i in range(8)]
+    ens = np.array([[-0.01 + 0.02 * lcg() for _ in range(20)] for _ in range(32)])
+    lp = np.empty(32)
+    dev = sb.DeviceRng(seed=11)
+    f = sb.Rastrigin()
+    sb.init_logprob(f, ens, lp, dev)
+    for k in range(niter):
+        if k % 10 == 0:
+            sb.swap_walkers(ens, lp, dev, blist, f)
+        sb.sample_pt(f, ens, lp, dev, 2.0, sb.UpdateFlagSpec.Prob(0.2), blist)
+    got = [ln.split() for ln in out if ln.startswith("B ")]
+    assert len(got) == 32
+    for i, t in enumerate(got):
+        assert (float(t[2]), float(t[3]), float(t[4])) == (ens[i, 0], ens[i, 19], lp[i])
+    assert "C 2" in out and "D 4" in out  # NWalkersIsNotEven, BetaNotInDecrOrd
