@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--matching", default="local", choices=["local", "global"],
+                    help="N>1, single temperature: shard-local matchings (no per-step exchange) or the "
+                         "reference's whole-ensemble matching over an NCCL all-gather per step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,32 +220,44 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- shard the walkers: whole rungs per rank when tempered, contiguous walkers otherwise ----
-    if nbeta > 1:
-        assert nbeta % world == 0, "rungs must divide over the ranks"
-        nb_local = nbeta // world
-        n_local = n // world
-        beta = betas(nbeta)[rank * nb_local:(rank + 1) * nb_local]
-        parallelism = f"rungs->gpus x{world}" if world > 1 else "single gpu"
-    else:
-        n_local, nb_local = n // world, 1
-        beta = betas(1)
-        parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)" if world > 1 else "single gpu"
     params = workload_params(kind, dim)
     spec = {"prob": sb.UpdateFlagSpec.Prob(prob), "all": sb.UpdateFlagSpec.All(),
             "onehot": sb.UpdateFlagSpec.OneHotCycle()}[ufs]
-    ens = make_ensemble(n_local, dim, box, 5 + rank, kind)
-
-    s = sb.Sampler(sb.LogProb(kind, tuple(params)), n_local, dim, seed=2024 + rank, device=local_rank)
     stream = torch.cuda.Stream()  # the launch stream; the CUDA events below are recorded on it
     torch.cuda.set_stream(stream)
-    s.set_stream(stream.cuda_stream)
-    s.upload(ens, None)
-    s.sync()
+    beta = betas(nbeta)
+    if world > 1:
+        from scorus_b200.distributed import ShardedSampler
+        s = ShardedSampler(sb.LogProb(kind, tuple(params)), n, dim, nbeta=nbeta, seed=2024, matching=args.matching)
+        n_local, nb_local = s.n_local, s.nb_local
+        if s.mode == "rungs":
+            parallelism = f"rungs->gpus x{world}: no per-step exchange; swap = all-gather(lp) + all-to-all of crossing rows"
+        elif args.matching == "global":
+            parallelism = f"walker shards x{world}, whole-ensemble matching, NCCL all-gather of the ensemble per step"
+        else:
+            parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)"
+        ens = make_ensemble(n_local, dim, box, 5 + rank, kind)
+        s.upload(ens, None)
+        s.sync()
+        launch_count = lambda: s.sampler.launch_count
+        swap = s.swap_walkers
+        can_swap = s.mode == "rungs"
+    else:
+        n_local, nb_local = n, nbeta
+        parallelism = "single gpu"
+        ens = make_ensemble(n_local, dim, box, 5, kind)
+        s = sb.Sampler(sb.LogProb(kind, tuple(params)), n_local, dim, seed=2024, device=local_rank)
+        s.set_stream(stream.cuda_stream)
+        s.upload(ens, None)
+        s.sync()
+        launch_count = lambda: s.launch_count
+        swap = s.swap_walkers
+        can_swap = True
 
     def run_steps(k0, count):
         for k in range(k0, k0 + count):
-            if swap_every and nb_local > 1 and k % swap_every == 0:
-                s.swap_walkers(beta)
+            if swap_every and nbeta > 1 and can_swap and k % swap_every == 0:
+                swap(beta)
             s.sample_pt(2.0, spec, beta, 1)
 
     run_steps(0, W)
@@ -252,7 +267,7 @@ def main():
     torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0 = s.launch_count
+    l0 = launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     run_steps(W, args.steps)
@@ -262,7 +277,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     clk = clocks.stop()
-    launches = s.launch_count - l0
+    launches = launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     if dist:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -276,14 +291,25 @@ def main():
     if not args.no_e2e:
         h_ens = sb.pinned_empty((n_local, dim))
         h_lp = sb.pinned_empty((n_local,))
-        s.download(h_ens, h_lp)
-        s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)  # warm-up
+        if world > 1:
+            def host_step():  # upload shard, one (possibly exchanging) step, download shard
+                s.upload(h_ens, h_lp)
+                s.sample_pt(2.0, spec, beta, 1)
+                s.sampler.download(h_ens, h_lp)
+            s.sampler.download(h_ens, h_lp)
+            api = "ShardedSampler.upload + sample_pt + download (pinned host buffers, one step per call)"
+        else:
+            def host_step():
+                s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
+            s.download(h_ens, h_lp)
+            api = "Sampler.sample_pt_host -> scorus_sample_pt_host (pinned host buffers in/out, one step per call)"
+        host_step()  # warm-up
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
+            host_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist:
@@ -293,7 +319,7 @@ def main():
         bytes_dir = n_local * dim * 8 + n_local * 8
         e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
                "d2h_bytes_per_step": bytes_dir, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "api": "Sampler.sample_pt_host -> scorus_sample_pt_host (pinned host buffers in/out, one step per call)"}
+               "api": api}
 
     if rank != 0:
         if dist:
@@ -318,7 +344,7 @@ def main():
                 "note": "launch time = device time of the timed region / steps (one step_kernel launch per step)"}
 
     cpu = None
-    if not args.no_cpu and world == 1 or (not args.no_cpu and rank == 0 and world == 1):
+    if not args.no_cpu and world == 1:
         cpu = cpu_reference_leg(args.workload, 20, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")}
 

@@ -156,6 +156,25 @@ int scorus_sample_pt_host(scorus_ctx *ctx, double *ensemble, double *logprob, si
 int scorus_swap_walkers_host(scorus_ctx *ctx, double *ensemble, double *logprob,
                              size_t logprob_len, const double *beta_list, size_t nbeta);
 
+/* ---- sharding: one process per GPU ----
+ * scorus_set_shard tells a context which slice of the whole ensemble it holds: its walker i is
+ * global walker walker_offset + i, its rung r is global rung rung_offset + r.  The device streams are
+ * keyed by global ids, so a sharded run draws exactly what a single-GPU run of the whole ensemble
+ * draws.  With whole rungs per rank (tempered runs) scorus_sample_pt then needs no communication. */
+int scorus_set_shard(scorus_ctx *ctx, uint64_t walker_offset, uint32_t rung_offset, uint64_t n_walkers_global);
+/* One sample_pt step (src/mcmc/ensemble_sample.rs:107-190) of a walker-sharded ensemble with the
+ * reference's whole-rung matching: ens_all / lp_all are DEVICE copies of the whole ensemble
+ * ([n_global][pitch], [n_global]; e.g. an NCCL all-gather of every rank's scorus_device_buffers),
+ * beta_list is the global list.  Updates this context's shard only; identical to the single-GPU step. */
+int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list,
+                            size_t nbeta, const double *ens_all, const double *lp_all);
+/* swap_walkers (src/mcmc/utils.rs:72-112) decided for the whole ladder from the gathered log-probs
+ * (DEVICE, [n_global], updated in place to the post-swap values): src_all[slot] (DEVICE, [n_global])
+ * receives the global slot whose walker ends in `slot`.  Every rank computes the same plan; rows are
+ * then exchanged by the caller (scorus_b200/distributed.py). */
+int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta_list, size_t nbeta, double *lp_all,
+                            uint32_t *src_all);
+
 /* ---- plumbing ---- */
 int scorus_sync(scorus_ctx *ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream; NULL is CUDA's legacy default

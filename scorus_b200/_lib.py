@@ -70,6 +70,9 @@ def load() -> C.CDLL:
         "scorus_swap_walkers_fixed": (ci, [vp, dp, sz, u32p, dp, u8p]),
         "scorus_sample_pt_host": (ci, [vp, dp, dp, sz, dbl, C.POINTER(Ufs), dp, sz]),
         "scorus_swap_walkers_host": (ci, [vp, dp, dp, sz, dp, sz]),
+        "scorus_set_shard": (ci, [vp, u64, C.c_uint32, u64]),
+        "scorus_sample_pt_global": (ci, [vp, dbl, C.POINTER(Ufs), dp, sz, vp, vp]),
+        "scorus_swap_plan_device": (ci, [vp, dp, sz, vp, vp]),
         "scorus_sync": (ci, [vp]),
         "scorus_set_stream": (ci, [vp, vp]),
         "scorus_reset_stream": (ci, [vp]),
@@ -95,7 +98,8 @@ EXPORTS = [
     "scorus_check_beta_order", "scorus_ctx_create", "scorus_ctx_destroy", "scorus_last_error",
     "scorus_set_logprob", "scorus_upload", "scorus_download", "scorus_init_logprob", "scorus_sample",
     "scorus_sample_pt", "scorus_sample_pt_fixed", "scorus_draw_z", "scorus_swap_walkers", "scorus_swap_walkers_fixed",
-    "scorus_sample_pt_host", "scorus_swap_walkers_host", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
+    "scorus_sample_pt_host", "scorus_swap_walkers_host", "scorus_set_shard", "scorus_sample_pt_global",
+    "scorus_swap_plan_device", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",
     "scorus_get_stats", "scorus_launch_count", "scorus_host_alloc", "scorus_host_free",
 ]

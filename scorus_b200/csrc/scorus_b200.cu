@@ -27,6 +27,8 @@ struct scorus_ctx {
     uint32_t dim = 0, pitch = 0;
     uint64_t seed = 0;
     uint64_t step = 0, swap_call = 0, onehot = 0;
+    uint64_t w_off = 0, n_global = 0;  // shard position in the whole ensemble (scorus_set_shard)
+    uint32_t rung_off = 0;
     uint64_t launches = 0, proposed = 0, swap_proposed = 0;
     int num_sms = 0, smem_optin = 0;
 
@@ -35,6 +37,9 @@ struct scorus_ctx {
     double *d_beta = nullptr;   size_t beta_cap = 0;
     double *d_params = nullptr; size_t params_cap = 0;
     uint32_t *d_order = nullptr, *d_src = nullptr;
+    uint32_t *d_gorder = nullptr; size_t gorder_cap = 0;   // global-matching mode: exact order of the whole ensemble
+    uint32_t *d_pairs = nullptr;  size_t pairs_cap = 0;    // ... local pair list
+    uint32_t *d_count = nullptr;
     unsigned long long *d_stats = nullptr;
     // scratch for caller-supplied streams
     double *d_z = nullptr, *d_u = nullptr;
@@ -162,6 +167,7 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     ctx->dim = cfg->dim;
     ctx->pitch = cfg->dim + (cfg->dim & 1u);  // rows are 16-byte multiples for cp.async.bulk
     ctx->seed = cfg->seed;
+    ctx->n_global = cfg->n_walkers;
     ctx->sequential = (cfg->flags & SCORUS_CFG_SEQUENTIAL_SUM) != 0;
     auto bail = [&](cudaError_t err, const char *what) {
         fprintf(stderr, "scorus_ctx_create: %s: %s\n", what, cudaGetErrorString(err));
@@ -191,7 +197,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_beta, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_jinv, ctx->d_r, ctx->d_swapped};
+                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -480,6 +486,8 @@ static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta
     p->ntiles = (uint32_t)((ctx->n + 31u) / 32u);
     p->bij_bits = bij_bits(p->npb);
     p->debug_identity = env_int("SCORUS_DEBUG_IDENTITY", 0) ? 1u : 0u;
+    p->w_off = (uint32_t)ctx->w_off; p->rung_off = ctx->rung_off; p->n_global = ctx->n_global;
+    p->src_ens = ctx->d_ens; p->src_lp = ctx->d_lp; p->n_dev = nullptr; p->w_lo = 0; p->w_hi = (uint32_t)ctx->n;
     return SCORUS_OK;
 }
 
@@ -537,7 +545,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
         p.step = ctx->step;
         p.onehot = ctx->onehot;
         if (exact) {
-            exact_order_kernel<<<(unsigned)nbeta, (p.npb + 31u) & ~31u, 0, ctx->stream>>>(ctx->seed, ctx->step, p.npb, ctx->d_order);
+            exact_order_kernel<<<(unsigned)nbeta, (p.npb + 31u) & ~31u, 0, ctx->stream>>>(ctx->seed, ctx->step, p.npb, ctx->d_order, (uint32_t)ctx->w_off);
             ++ctx->launches;
             p.order = ctx->d_order;
         }
@@ -546,7 +554,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
         ++ctx->launches;
         ++ctx->step;
         ctx->proposed += ctx->n;
-        if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n) % ctx->dim;
+        if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
     }
     return SCORUS_OK;
 }
@@ -726,6 +734,134 @@ extern "C" int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta, si
     if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
     if (nbeta > 1 && (!jvec || !r)) return SCORUS_ERR_INVALID_ARG;
     return swap_impl(ctx, beta, nbeta, nbeta > 1 ? jvec : nullptr, r, swapped_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// sharding: one process per GPU
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_set_shard(scorus_ctx *ctx, uint64_t walker_offset, uint32_t rung_offset, uint64_t n_walkers_global)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (walker_offset + ctx->n > n_walkers_global || n_walkers_global > 0xFFFFFFFFull)
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "shard [%llu, %llu) does not fit in %llu walkers",
+                    (unsigned long long)walker_offset, (unsigned long long)(walker_offset + ctx->n),
+                    (unsigned long long)n_walkers_global);
+    ctx->w_off = walker_offset;
+    ctx->rung_off = rung_offset;
+    ctx->n_global = n_walkers_global;
+    return SCORUS_OK;
+}
+
+// walker at every matching position of the WHOLE ensemble -> pairs with a member in [w_lo, w_hi)
+__global__ void local_pairs_kernel(const StepParams p, uint32_t n_global, uint32_t *pairs, uint32_t *count)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (2u * k + 1u >= n_global) return;
+    const uint32_t a = walker_at(p, 2u * k), b = walker_at(p, 2u * k + 1u);
+    const bool ina = a >= p.w_lo && a < p.w_hi, inb = b >= p.w_lo && b < p.w_hi;
+    if (ina || inb) {
+        const uint32_t slot = atomicAdd(count, 2u);
+        pairs[slot] = a;
+        pairs[slot + 1] = b;
+    }
+}
+
+extern "C" int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
+                                       size_t nbeta, const double *ens_all, const double *lp_all)
+{
+    if (!ctx || !ufs || !beta || !ens_all || !lp_all) return SCORUS_ERR_INVALID_ARG;
+    const size_t ng = ctx->n_global;
+    int rc = scorus_check_sample_args(ng, ng, nbeta);
+    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
+    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1");
+    if (ufs->kind == SCORUS_UFS_MASK) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-evaluated masks are not supported across shards");
+    if (ctx->sequential || ctx->pitch > 256) return fail(ctx, SCORUS_ERR_INVALID_ARG, "global matching needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
+    cudaSetDevice(ctx->device);
+
+    StepParams p;
+    Geometry g;
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    if ((rc = fill_common(ctx, &p, &g, nbeta))) return rc;
+    if (g.kernel != KERNEL_REG) return fail(ctx, SCORUS_ERR_INVALID_ARG, "global matching needs the register kernel");
+    const double sqrt_a = sqrt(a);
+    p.inv_sqrt_a = 1.0 / sqrt_a;
+    p.z_range = 2.0 * (sqrt_a - p.inv_sqrt_a);
+    p.flag_kind = (uint32_t)ufs->kind;
+    bool all_flags = ufs->kind == SCORUS_UFS_ALL;
+    if (ufs->kind == SCORUS_UFS_PROB) {
+        if (!(ufs->prob > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "Prob(p) needs p > 0");
+        p.flag_bits = flag_bits_for(ufs->prob);
+        p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(ufs->prob, 1.0) * 4294967296.0)
+                                       : (uint64_t)(fmin(ufs->prob, 1.0) * (double)(1u << p.flag_bits));
+    }
+    // ids are global in this mode: no offsets on the stream keys
+    p.npb = (uint32_t)(ng / nbeta);
+    p.bij_bits = bij_bits(p.npb);
+    p.w_off = 0; p.rung_off = 0;
+    p.w_lo = (uint32_t)ctx->w_off; p.w_hi = (uint32_t)(ctx->w_off + ctx->n);
+    p.step = ctx->step; p.onehot = ctx->onehot;
+    p.order = nullptr;
+    if (p.npb <= kExactShuffleMax) {  // exact shuffle of every rung of the whole ensemble
+        if ((rc = ensure(ctx, (void **)&ctx->d_gorder, &ctx->gorder_cap, ng * sizeof(uint32_t)))) return rc;
+        exact_order_kernel<<<(unsigned)nbeta, (p.npb + 31u) & ~31u, 0, ctx->stream>>>(ctx->seed, ctx->step, p.npb, ctx->d_gorder, 0u);
+        ++ctx->launches;
+        p.order = ctx->d_gorder;
+    }
+    if ((rc = ensure(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * ctx->n * sizeof(uint32_t)))) return rc;
+    if (!ctx->d_count) CU(cudaMalloc(&ctx->d_count, sizeof(uint32_t)));
+    CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(uint32_t), ctx->stream));
+    local_pairs_kernel<<<(unsigned)((ng / 2 + 255) / 256), 256, 0, ctx->stream>>>(p, (uint32_t)ng, ctx->d_pairs, ctx->d_count);
+    ++ctx->launches;
+    // the step itself: pair list as the matching order, rows from the gathered copies
+    p.order = ctx->d_pairs;
+    p.n_dev = ctx->d_count;
+    p.n = (uint32_t)(2 * ctx->n);
+    p.ntiles = (p.n + 31u) / 32u;
+    p.src_ens = ens_all;
+    p.src_lp = lp_all;
+    cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
+    ++ctx->launches;
+    ++ctx->step;
+    ctx->proposed += ctx->n;
+    if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ng) % ctx->dim;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size_t nbeta, double *lp_all,
+                                       uint32_t *src_all)
+{
+    if (!ctx || !beta || !lp_all || !src_all) return SCORUS_ERR_INVALID_ARG;
+    const size_t n = ctx->n_global;
+    if (nbeta == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "nbeta == 0");
+    const size_t npb = n / nbeta;
+    if (npb * nbeta != n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
+    int rc = scorus_check_beta_order(beta, nbeta);
+    if (rc) return fail(ctx, rc, "beta list must be in decreasing order");
+    cudaSetDevice(ctx->device);
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    SwapParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.lp = lp_all; sp.beta = ctx->d_beta; sp.src = src_all; sp.stats = ctx->d_stats;
+    sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
+    sp.npb = (uint32_t)npb; sp.nbeta = (uint32_t)nbeta; sp.bij_bits = bij_bits((uint32_t)npb);
+    if (nbeta > 1 && npb <= kExactShuffleMax) {
+        const size_t m = (nbeta - 1) * npb;
+        if ((rc = ensure(ctx, (void **)&ctx->d_jinv, &ctx->jinv_cap, m * sizeof(uint32_t)))) return rc;
+        exact_jvec_kernel<<<(unsigned)(nbeta - 1), ((unsigned)npb + 31u) & ~31u, 0, ctx->stream>>>(
+            ctx->seed, ctx->swap_call, (uint32_t)npb, (uint32_t)nbeta, ctx->d_jinv);
+        ++ctx->launches;
+        sp.jinv = ctx->d_jinv;
+    }
+    swap_chain_kernel<<<(unsigned)((npb + 127) / 128), 128, 0, ctx->stream>>>(sp);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap plan launch: %s", cudaGetErrorString(e));
+    ++ctx->swap_call;
+    ctx->swap_proposed += (nbeta - 1) * npb;  // whole ladder, as counted by the chain kernel
+    return SCORUS_OK;
 }
 
 // ------------------------------------------------------------------------------------------

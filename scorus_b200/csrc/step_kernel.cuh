@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(512, 1) step_seq_kernel(const StepParams p)
             z = act ? __ldg(p.z_in + w) : 1.0;
             u = act ? __ldg(p.u_in + w) : 1.0;
         } else {
-            U4 r = draw(p.seed, p.step, ST_ZU, w, 0);
+            U4 r = draw(p.seed, p.step, ST_ZU, w + p.w_off, 0);
             z = z_from_uniform(u53(r.x, r.y), p.inv_sqrt_a, p.z_range);
             u = u53(r.z, r.w);
         }

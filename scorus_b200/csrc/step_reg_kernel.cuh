@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         if (p.order) return __ldg(p.order + pos);
         if (p.debug_identity) return pos;
         const uint32_t r = pos / p.npb;
-        if (r != key_rung) { K = bij_keys(p.seed, p.step, ST_PERM, r); key_rung = r; }
+        if (r != key_rung) { K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off); key_rung = r; }
         return r * p.npb + bij(pos - r * p.npb, p.npb, p.bij_bits, K);
     };
 
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         for (int i = 0; i < GB; ++i) {
             const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
             const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
-            const double2 *src = reinterpret_cast<const double2 *>(p.ens + (size_t)row * p.pitch);
+            const double2 *src = reinterpret_cast<const double2 *>(p.src_ens + (size_t)row * p.pitch);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 // lanes beyond the row re-read its last chunk (never used): an unconditional load keeps
@@ -96,16 +96,19 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         }
     };
 
+    // matching positions to process: N, or (global-matching mode) the length of the local pair list
+    const uint32_t npos = p.n_dev ? __ldg(p.n_dev) : p.n;
+    const uint32_t ntiles = (npos + 31u) >> 5;
     uint32_t tile = gwarp;
-    if (tile >= p.ntiles) return;
+    if (tile >= ntiles) return;
     uint32_t w;
     bool act;
     {
         const uint32_t pos = tile * 32u + lane;
-        act = pos < p.n;
+        act = pos < npos;
         w = act ? walker_of(pos) : 0u;
     }
-    double lp_old = act ? __ldg(p.lp + w) : 0.0;
+    double lp_old = act ? __ldg(p.src_lp + w) : 0.0;
     double2 xn[GB][ITERS];
     load_block(xn, w, 0);
 
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
             z = act ? __ldg(p.z_in + w) : 1.0;
             u = act ? __ldg(p.u_in + w) : 1.0;
         } else {
-            const U4 r = draw(p.seed, p.step, ST_ZU, w, 0);
+            const U4 r = draw(p.seed, p.step, ST_ZU, w + p.w_off, 0);
             z = z_from_uniform(u53(r.x, r.y), p.inv_sqrt_a, p.z_range);
             u = u53(r.z, r.w);
         }
@@ -134,11 +137,11 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         uint32_t w_n = 0;
         bool act_n = false;
         double lp_n = 0.0;
-        if (tile_n < p.ntiles) {
+        if (tile_n < ntiles) {
             const uint32_t pos = tile_n * 32u + lane;
-            act_n = pos < p.n;
+            act_n = pos < npos;
             w_n = act_n ? walker_of(pos) : 0u;
-            if (act_n) lp_n = __ldg(p.lp + w_n);
+            if (act_n) lp_n = __ldg(p.src_lp + w_n);
         }
 
         double tot[Plugin::kAcc];
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
             if (blk + 1 < NB) load_block(xn, w, blk + 1);
-            else if (tile_n < p.ntiles) load_block(xn, w_n, 0);
+            else if (tile_n < ntiles) load_block(xn, w_n, 0);
 
             double acc[Plugin::kAcc][GB];
 #pragma unroll
@@ -235,16 +238,18 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         }
         const double delta_lp = lp_new - lp_old;
         const double q = exp(lz + delta_lp * beta);
-        const bool accept = act && (u < q);
+        // global-matching mode: walkers outside [w_lo, w_hi) belong to another rank, which updates them
+        const bool mine = act && w >= p.w_lo && w < p.w_hi;
+        const bool accept = mine && (u < q);
         if (accept) {
-            bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
-            p.lp[w] = lp_new;
+            bulk_store(p.ens + (size_t)(w - p.w_lo) * p.pitch, smem_u32(own_b), p.row_bytes);
+            p.lp[w - p.w_lo] = lp_new;
             ++n_acc;
         }
         bulk_commit();
-        if (p.accepted_out && act) p.accepted_out[w] = accept ? 1 : 0;
+        if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0;
 
-        if (tile_n >= p.ntiles) break;
+        if (tile_n >= ntiles) break;
         tile = tile_n;
         w = w_n;
         act = act_n;

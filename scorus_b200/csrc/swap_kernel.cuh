@@ -21,13 +21,13 @@ namespace scorus {
 // Exact uniform shuffle of every rung by ranking 64-bit Philox keys (npb <= kExactShuffleMax).
 // order[r*npb + rank] = r*npb + i.  One block per rung.
 __global__ void __launch_bounds__(1024) exact_order_kernel(uint64_t seed, uint64_t step, uint32_t npb,
-                                                           uint32_t *order)
+                                                           uint32_t *order, uint32_t w_off)
 {
     __shared__ uint64_t keys[kExactShuffleMax];
     const uint32_t r = blockIdx.x, i = threadIdx.x;
     uint64_t ki = 0;
     if (i < npb) {
-        U4 o = draw(seed, step, ST_PERM_KEY, r * npb + i, 0);
+        U4 o = draw(seed, step, ST_PERM_KEY, w_off + r * npb + i, 0);
         ki = ((uint64_t)o.y << 32) | o.x;
         keys[i] = ki;
     }

@@ -30,6 +30,18 @@ struct StepParams {
     uint32_t stages, warps, ntiles, flag_words;
     uint32_t bij_bits;
     uint32_t debug_identity;  // measurement only (SCORUS_DEBUG_IDENTITY=1): position j holds walker j
+    // ---- sharding (one process per GPU) ----
+    // Random streams are keyed by GLOBAL walker / rung ids so that a sharded run draws exactly what
+    // the single-GPU run draws: global walker = w_off + w, global rung = rung_off + r.
+    uint32_t w_off, rung_off;
+    uint64_t n_global;        // walkers of the whole ensemble (one-hot cycle advances by this per step)
+    // Global-matching mode (register kernel only): ids in `order` are global, rows and log-probs are
+    // read from the gathered copies src_ens / src_lp, results are written for walkers in
+    // [w_lo, w_hi) only, at local row w - w_lo.  Single-GPU: src_* = ens / lp, [0, n).
+    const double *src_ens;
+    const double *src_lp;
+    const uint32_t *n_dev;    // if set, the number of matching positions is read from device memory
+    uint32_t w_lo, w_hi;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
@@ -99,7 +111,7 @@ __device__ __forceinline__ uint32_t walker_at(const StepParams &p, uint32_t j)
     if (p.debug_identity) return j;
     uint32_t r = j / p.npb;
     uint32_t k = j - r * p.npb;
-    BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r);
+    BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off);
     return r * p.npb + bij(k, p.npb, p.bij_bits, K);
 }
 
@@ -123,7 +135,7 @@ __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint32_t
         nphi = 0;
         uint32_t cur = 0;
         for (uint32_t blk = 0; blk < nblk; ++blk) {
-            const U4 r = draw(p.seed, p.step, ST_FLAGS, w, attempt * nblk + blk);
+            const U4 r = draw(p.seed, p.step, ST_FLAGS, w + p.w_off, attempt * nblk + blk);
             const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (uint32_t wi = 0; wi < 4; ++wi) {
@@ -158,7 +170,7 @@ __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, u
                                               bool act)
 {
     if (p.flag_kind == 2u) {  // ONE_HOT_CYCLE: the cycling closure, called once per walker in order
-        const uint32_t hot = (uint32_t)((p.onehot + 1ull + (uint64_t)w) % (uint64_t)p.dim);
+        const uint32_t hot = (uint32_t)((p.onehot + 1ull + (uint64_t)w + (uint64_t)p.w_off) % (uint64_t)p.dim);
         for (uint32_t wd = 0; wd < p.flag_words; ++wd)
             flagw[wd * 32u + lane] = (hot >> 5) == wd ? (1u << (hot & 31u)) : 0u;
         return 1u;

@@ -1,0 +1,210 @@
+"""Walker / rung sharding over the GPUs of one box: one process per GPU, torch.distributed (NCCL) for
+the plumbing, the library's own kernels for the work.
+
+Two layouts, chosen from (nbeta, world size):
+
+* ``rungs``   -- tempered runs with nbeta % world == 0: every rank holds whole rungs.  The pairing never
+  leaves a rung (src/mcmc/ensemble_sample.rs:136-146), so ``sample_pt`` needs NO communication.
+  ``swap_walkers`` couples adjacent rungs (src/mcmc/utils.rs:89-108): the log-probs are all-gathered
+  (8*N bytes), every rank computes the same swap plan on its GPU (scorus_swap_plan_device), and only the
+  rows that cross a rank boundary are exchanged (all_to_all_single).
+* ``walkers`` -- single-temperature runs: contiguous walker shards.
+    - matching="global": the reference's whole-rung matching.  Each step all-gathers the ensemble over
+      NVLink and runs scorus_sample_pt_global; results are bit-identical to the single-GPU run.  It is
+      NVLink-bound -- the faithful, not the fast, configuration.
+    - matching="local": every shard pairs within itself, no per-step exchange (each shard is itself a
+      valid ensemble; the matching stays state-independent, so the move is still a valid MCMC kernel).
+
+Random streams are keyed by global walker / rung ids (Sampler.set_shard), so ``rungs`` and
+``walkers/global`` reproduce the single-GPU chain exactly.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .ensemble_sample import LogProb, Sampler, UpdateFlagSpec
+
+
+# ------------------------------------------------------------------------------------------------
+# pure host logic (unit-tested on CPU with gloo, tests/test_distributed_cpu.py)
+# ------------------------------------------------------------------------------------------------
+def shard_layout(n_walkers: int, nbeta: int, world: int, rank: int):
+    """-> (mode, walker_offset, n_local, rung_offset, nbeta_local)."""
+    if n_walkers % world:
+        raise ValueError("the number of walkers must divide over the ranks")
+    n_local = n_walkers // world
+    if n_local % 2:
+        raise ValueError("every shard needs an even number of walkers")
+    if nbeta > 1 and nbeta % world == 0:
+        nb_local = nbeta // world
+        return "rungs", rank * n_local, n_local, rank * nb_local, nb_local
+    return "walkers", rank * n_local, n_local, 0, nbeta
+
+
+def exchange_plan(src_all: np.ndarray, n_local: int, world: int, rank: int):
+    """Who sends which rows to whom after a ladder swap.
+
+    src_all[slot] = global slot whose (old) row must end in `slot`.  Returns
+      local_dst, local_src : moves inside this rank (local indices; read old rows before writing)
+      send_idx[q]          : local indices of my old rows that rank q needs, in q's slot order
+      recv_dst[q]          : local indices of my slots filled from rank q, in my slot order
+    Every rank derives the same plan from the same src_all, so no metadata is exchanged."""
+    lo, hi = rank * n_local, (rank + 1) * n_local
+    src_all = np.asarray(src_all, dtype=np.int64)
+    mine = src_all[lo:hi]
+    slots = np.arange(lo, hi)
+    moved = mine != slots
+    owner = mine // n_local
+    loc = moved & (owner == rank)
+    local_dst = (slots[loc] - lo).astype(np.int64)
+    local_src = (mine[loc] - lo).astype(np.int64)
+    send_idx, recv_dst = [], []
+    for q in range(world):
+        if q == rank:
+            send_idx.append(np.zeros(0, dtype=np.int64))
+            recv_dst.append(np.zeros(0, dtype=np.int64))
+            continue
+        theirs = src_all[q * n_local:(q + 1) * n_local]
+        send_idx.append((theirs[(theirs >= lo) & (theirs < hi)] - lo).astype(np.int64))
+        recv_dst.append((slots[moved & (owner == q)] - lo).astype(np.int64))
+    return local_dst, local_src, send_idx, recv_dst
+
+
+def exchange_plan_torch(src_all, n_local: int, world: int, rank: int):
+    """exchange_plan with torch ops on whatever device src_all lives on (the GPU in production: the
+    plan never visits the host except for the world x world matrix of row counts that
+    all_to_all_single needs).  Returns (local_dst, local_src, send_idx, recv_dst, send_counts,
+    recv_counts): send_idx / recv_dst are concatenated in peer order."""
+    import torch
+    n = src_all.numel()
+    dev = src_all.device
+    src = src_all.to(torch.int64) & 0xFFFFFFFF
+    slot = torch.arange(n, device=dev, dtype=torch.int64)
+    moved = src != slot
+    owner = torch.div(src, n_local, rounding_mode="floor")       # rank holding the row that moves in
+    holder = torch.div(slot, n_local, rounding_mode="floor")     # rank holding the destination slot
+    cross = moved & (owner != holder)
+    counts = torch.bincount(holder[cross] * world + owner[cross], minlength=world * world).view(world, world).cpu()
+    recv_counts = [int(c) for c in counts[rank]]                 # rows I receive from each peer
+    send_counts = [int(c) for c in counts[:, rank]]              # rows each peer receives from me
+    lo = rank * n_local
+    # rows I send: slots of other ranks fed from my range, in (peer, slot) = ascending slot order
+    send_idx = src[cross & (owner == rank)] - lo
+    # slots I fill from peers, grouped by peer (stable sort keeps slot order inside a peer)
+    my = slice(lo, lo + n_local)
+    rmask = cross[my]
+    rslots = slot[my][rmask] - lo
+    order = torch.argsort(owner[my][rmask], stable=True)
+    recv_dst = rslots[order]
+    lmask = moved[my] & (owner[my] == rank)
+    local_dst = slot[my][lmask] - lo
+    local_src = src[my][lmask] - lo
+    return local_dst, local_src, send_idx, recv_dst, send_counts, recv_counts
+
+
+# ------------------------------------------------------------------------------------------------
+# device views (zero-copy torch tensors over the context's buffers)
+# ------------------------------------------------------------------------------------------------
+class _CudaArray:
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def device_views(s: Sampler, device):
+    import torch
+    ens_ptr, pitch, lp_ptr = s.device_buffers()
+    ens = torch.as_tensor(_CudaArray(ens_ptr, (s.n, pitch), "<f8"), device=device)
+    lp = torch.as_tensor(_CudaArray(lp_ptr, (s.n,), "<f8"), device=device)
+    return ens, lp, pitch
+
+
+class ShardedSampler:
+    """The sharded counterpart of Sampler: same calls, global beta list, local data."""
+
+    def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, nbeta: int = 1, seed: int = 0,
+                 matching: str = "global", device: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.torch, self.group = dist, torch, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_global, self.dim, self.nbeta = n_walkers, dim, nbeta
+        self.mode, self.w_off, self.n_local, self.rung_off, self.nb_local = shard_layout(n_walkers, nbeta, self.world,
+                                                                                        self.rank)
+        if matching not in ("global", "local"):
+            raise ValueError("matching must be 'global' or 'local'")
+        self.matching = matching
+        dev = torch.cuda.current_device() if device is None else device
+        self.device = torch.device("cuda", dev)
+        # shard-local matchings are independent ensembles: give each shard its own stream key
+        local = self.mode == "walkers" and matching == "local"
+        self.sampler = Sampler(flogprob, self.n_local, dim, seed=seed + (self.rank if local else 0), device=dev)
+        if not local:
+            self.sampler.set_shard(self.w_off, self.rung_off, n_walkers)
+        self.sampler.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.ens, self.lp, self.pitch = device_views(self.sampler, self.device)
+        self._ens_all = self._lp_all = self._src_all = None
+
+    # -- data
+    def upload(self, ens_local: np.ndarray, lp_local: Optional[np.ndarray] = None):
+        self.sampler.upload(ens_local, lp_local)
+
+    def download(self):
+        return self.sampler.download()
+
+    def _gather_buffers(self):
+        t = self.torch
+        if self._ens_all is None:
+            self._ens_all = t.empty((self.n_global, self.pitch), dtype=t.float64, device=self.device)
+            self._lp_all = t.empty((self.n_global,), dtype=t.float64, device=self.device)
+            self._src_all = t.empty((self.n_global,), dtype=t.int32, device=self.device)
+        return self._ens_all, self._lp_all, self._src_all
+
+    # -- the hot path
+    def sample_pt(self, a: float, ufs: UpdateFlagSpec, beta_list: Sequence[float], nsteps: int = 1):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if self.mode == "rungs":
+            local_beta = beta[self.rung_off:self.rung_off + self.nb_local]
+            self.sampler.sample_pt(a, ufs, local_beta, nsteps)      # no communication
+            return
+        if self.matching == "local" or self.world == 1:
+            self.sampler.sample_pt(a, ufs, beta, nsteps)
+            return
+        ens_all, lp_all, _ = self._gather_buffers()
+        for _ in range(nsteps):                                      # all-gather + global-matching step
+            self.dist.all_gather_into_tensor(ens_all, self.ens, group=self.group)
+            self.dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
+            self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
+
+    def swap_walkers(self, beta_list: Sequence[float]):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if self.world == 1 or self.mode != "rungs":
+            if self.mode == "rungs" or self.world == 1:
+                self.sampler.swap_walkers(beta)
+                return
+            # walker shards of a tempered ensemble whose rungs do not divide over the ranks
+            raise NotImplementedError("swap_walkers across walker shards needs nbeta % world == 0")
+        t, dist = self.torch, self.dist
+        _, lp_all, src_all = self._gather_buffers()
+        dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
+        self.sampler.swap_plan_device(beta, lp_all.data_ptr(), src_all.data_ptr())
+        local_dst, local_src, send_idx, recv_dst, send_counts, recv_counts = exchange_plan_torch(
+            src_all, self.n_local, self.world, self.rank)
+        send = self.ens.index_select(0, send_idx)                    # old rows, gathered before any write
+        local_rows = self.ens.index_select(0, local_src)
+        recv = t.empty((sum(recv_counts), self.pitch), dtype=t.float64, device=self.device)
+        dist.all_to_all_single(recv, send, recv_counts, send_counts, group=self.group)
+        if local_dst.numel():
+            self.ens.index_copy_(0, local_dst, local_rows)
+        if recv_dst.numel():
+            self.ens.index_copy_(0, recv_dst, recv)
+        self.lp.copy_(lp_all[self.w_off:self.w_off + self.n_local])
+
+    def sync(self):
+        self.sampler.sync()
+
+    def stats(self):
+        return self.sampler.stats()

@@ -315,6 +315,21 @@ class Sampler:
         self._ok(self._lib.scorus_swap_walkers_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0],
                                                     _dp(beta), beta.size))
 
+    # -- sharding (one process per GPU; scorus_b200/distributed.py drives these)
+    def set_shard(self, walker_offset: int, rung_offset: int, n_walkers_global: int):
+        self._ok(self._lib.scorus_set_shard(self._ctx, walker_offset, rung_offset, n_walkers_global))
+
+    def sample_pt_global(self, a: float, ufs: UpdateFlagSpec, beta_list, ens_all_ptr: int, lp_all_ptr: int):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        u, keep = ufs._c(self.n, self.dim)
+        self._ok(self._lib.scorus_sample_pt_global(self._ctx, a, C.byref(u), _dp(beta), beta.size,
+                                                   C.c_void_p(ens_all_ptr), C.c_void_p(lp_all_ptr)))
+
+    def swap_plan_device(self, beta_list, lp_all_ptr: int, src_all_ptr: int):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        self._ok(self._lib.scorus_swap_plan_device(self._ctx, _dp(beta), beta.size, C.c_void_p(lp_all_ptr),
+                                                   C.c_void_p(src_all_ptr)))
+
     # -- plumbing
     def sync(self):
         self._ok(self._lib.scorus_sync(self._ctx))
