@@ -271,10 +271,23 @@ struct LpMixture {
     __device__ __forceinline__ double finish_acc(const double *a) const { return eval(a[0], a[1]); }
 };
 
+// fp64 tensor-core MMA, D[8x8] += A[8x4] * B[4x8] (SASS: DMMA.8x8x4).  Lane l holds A[l/4][l%4],
+// B[l%4][l/4] and C/D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
 // builder-defined (BASELINE config 2): -0.5 |L (x - mu)|^2, general dense L.
-// Scalar evaluation from the finished row in shared memory (one lane per walker).
+// finish_row: scalar evaluation, one lane per walker, reference-style left-to-right sums (used by the
+// sequential kernels and init_logprob).  tile_logprob: the K3 path of the register kernel -- the
+// 32 proposed rows of a warp's tile times L^T as a batched fp64 tensor-core GEMM (this really is a
+// dense contraction: 2 D^2 flops per 16 D bytes), row norms from the accumulators.
 struct LpCorrGaussian {
     static constexpr bool kNeedsRow = true;
+    static constexpr bool kTile = true;
     static constexpr int kAcc = 1;
     const double *mu, *L;
     uint32_t dim;
@@ -290,6 +303,54 @@ struct LpCorrGaussian {
     __device__ __forceinline__ double finish() const { return NAN; }
     __device__ __forceinline__ void terms(uint32_t, double, double, double, bool, bool, double *) const {}
     __device__ __forceinline__ double finish_acc(const double *) const { return NAN; }
+    // log-density of row `lane` of a 32-row tile in shared memory (rows row_stride bytes apart)
+    __device__ __forceinline__ double tile_logprob(const unsigned char *tile, uint32_t row_stride, uint32_t lane) const
+    {
+        if (!ok) return NAN;
+        const uint32_t g = lane >> 2, t = lane & 3u;
+        const double *rows[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+            rows[mt] = reinterpret_cast<const double *>(tile + (size_t)(mt * 8 + g) * row_stride);
+        double ss[4] = {0.0, 0.0, 0.0, 0.0};  // sum over my columns of W[row mt*8+g][.]^2
+        constexpr int NG = 2;                 // n-tiles per pass: bounds the accumulators to 16 doubles
+        for (uint32_t n0 = 0; n0 < dim; n0 += 8 * NG) {
+            double c[NG][4][2];
+#pragma unroll
+            for (int ng = 0; ng < NG; ++ng)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) c[ng][mt][0] = c[ng][mt][1] = 0.0;
+            for (uint32_t k0 = 0; k0 < dim; k0 += 4) {
+                const uint32_t k = k0 + t;
+                const bool kin = k < dim;
+                const double mu_k = kin ? __ldg(mu + k) : 0.0;
+                double a[4];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) a[mt] = kin ? rows[mt][k] - mu_k : 0.0;
+#pragma unroll
+                for (int ng = 0; ng < NG; ++ng) {
+                    const uint32_t n = n0 + 8u * ng + g;  // W column = row of L:  B[k][n] = L[n][k]
+                    const double b = (kin && n < dim) ? __ldg(L + (size_t)n * dim + k) : 0.0;
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) dmma_m8n8k4(c[ng][mt], a[mt], b);
+                }
+            }
+#pragma unroll
+            for (int ng = 0; ng < NG; ++ng)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) ss[mt] += c[ng][mt][0] * c[ng][mt][0] + c[ng][mt][1] * c[ng][mt][1];
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            double x = ss[mt];
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);          // all columns of row mt*8+g
+            x = __shfl_sync(0xffffffffu, x, (lane & 7u) * 4u);  // row (lane % 8) of m-tile mt
+            if ((int)(lane >> 3) == mt) v = x;
+        }
+        return -0.5 * v;
+    }
     __device__ __forceinline__ double finish_row(const double *row) const
     {
         if (!ok) return NAN;

@@ -34,7 +34,10 @@ struct scorus_ctx {
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     double *d_ens = nullptr, *d_lp = nullptr, *d_scratch = nullptr;
-    double *d_beta = nullptr;   size_t beta_cap = 0;
+    double *d_beta = nullptr;   // the beta list of the current call (one of beta_cache)
+    struct BetaEntry { std::vector<double> host; double *dev = nullptr; uint64_t used = 0; };
+    std::vector<BetaEntry> beta_cache;  // callers alternate between a few lists (local / global ladder)
+    uint64_t beta_clock = 0;
     double *d_params = nullptr; size_t params_cap = 0;
     uint32_t *d_order = nullptr, *d_src = nullptr;
     uint32_t *d_gorder = nullptr; size_t gorder_cap = 0;   // global-matching mode: exact order of the whole ensemble
@@ -54,7 +57,6 @@ struct scorus_ctx {
     bool uploaded = false;
     bool sequential = false;  // SCORUS_CFG_SEQUENTIAL_SUM
     std::string err;
-    std::vector<double> h_beta;
 };
 
 static int fail(scorus_ctx *c, int code, const char *fmt, ...)
@@ -195,11 +197,13 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_beta, ctx->d_params, ctx->d_order,
+    void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
                     ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    for (auto &e : ctx->beta_cache)
+        if (e.dev) cudaFree(e.dev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -451,14 +455,32 @@ extern "C" int scorus_download(scorus_ctx *ctx, double *ens, double *lp)
 // ------------------------------------------------------------------------------------------
 static int upload_beta(scorus_ctx *ctx, const double *beta, size_t nbeta)
 {
-    if (ctx->h_beta.size() == nbeta && memcmp(ctx->h_beta.data(), beta, nbeta * sizeof(double)) == 0 && ctx->d_beta)
-        return SCORUS_OK;
-    int rc = ensure(ctx, (void **)&ctx->d_beta, &ctx->beta_cap, nbeta * sizeof(double));
-    if (rc) return rc;
-    // stream-ordered copy from a context-owned staging vector: earlier launches keep their values
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->h_beta.assign(beta, beta + nbeta);
-    CU(cudaMemcpyAsync(ctx->d_beta, ctx->h_beta.data(), nbeta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // Device copies of the last few beta lists are kept so that alternating lists (a rank's own rungs
+    // for sample_pt, the whole ladder for the swap plan) never force a stream synchronisation.
+    for (auto &e : ctx->beta_cache)
+        if (e.host.size() == nbeta && memcmp(e.host.data(), beta, nbeta * sizeof(double)) == 0) {
+            e.used = ++ctx->beta_clock;
+            ctx->d_beta = e.dev;
+            return SCORUS_OK;
+        }
+    scorus_ctx::BetaEntry *slot = nullptr;
+    if (ctx->beta_cache.size() < 8) {
+        ctx->beta_cache.reserve(8);  // entries must not move: async copies read e.host
+        ctx->beta_cache.emplace_back();
+        slot = &ctx->beta_cache.back();
+    } else {
+        slot = &ctx->beta_cache[0];
+        for (auto &e : ctx->beta_cache)
+            if (e.used < slot->used) slot = &e;
+        CU(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the evicted list
+        cudaFree(slot->dev);
+        slot->dev = nullptr;
+    }
+    slot->host.assign(beta, beta + nbeta);
+    CU(cudaMalloc(&slot->dev, nbeta * sizeof(double)));
+    CU(cudaMemcpyAsync(slot->dev, slot->host.data(), nbeta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    slot->used = ++ctx->beta_clock;
+    ctx->d_beta = slot->dev;
     return SCORUS_OK;
 }
 

@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         unsigned char *own_b = ytile + lane * p.row_stride;
         double lp_new;
         if constexpr (Plugin::kNeedsRow) {
-            lp_new = plug.finish_row(reinterpret_cast<const double *>(own_b));
+            // K3: dense targets evaluate the whole tile of proposed rows on the fp64 tensor cores
+            lp_new = plug.tile_logprob(ytile, p.row_stride, lane);
         } else {
             lp_new = plug.finish_acc(tot);
         }
