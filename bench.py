@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--matching", default="local", choices=["local", "global"],
+    ap.add_argument("--matching", default="local", choices=["local", "global", "p2p"],
                     help="N>1, single temperature: shard-local matchings (no per-step exchange) or the "
                          "reference's whole-ensemble matching over an NCCL all-gather per step")
     args = ap.parse_args()
@@ -234,6 +234,8 @@ def main():
             parallelism = f"rungs->gpus x{world}: no per-step exchange; swap = all-gather(lp) + all-to-all of crossing rows"
         elif args.matching == "global":
             parallelism = f"walker shards x{world}, whole-ensemble matching, NCCL all-gather of the ensemble per step"
+        elif args.matching == "p2p":
+            parallelism = f"walker shards x{world}, whole-ensemble matching, one-sided NVLink reads of remote partners"
         else:
             parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)"
         ens = make_ensemble(n_local, dim, box, 5 + rank, kind)
@@ -326,22 +328,43 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (step_kernel): algorithmic bytes / measured launch time ----
+    # ---- roofline of the dominant kernel: algorithmic bytes (or flops) per launch / measured launch time ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bytes_per_launch = b_alg(dim) * n_local
-    achieved = bytes_per_launch * args.steps / (ms * 1e-3) / 1e9
+    kernel_name = {6: "step_reg_kernel<LpCorrGaussian> (K1 + K3 DMMA tile)"}.get(kind, "step_reg_kernel (K1)")
     traffic = None
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(prof):
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "step_kernel", "peak_source": peak_src,
-                "algorithmic_bytes_per_walker_step": b_alg(dim), "walkers_per_launch": n_local,
-                "note": "launch time = device time of the timed region / steps (one step_kernel launch per step)"}
+    if kind == 6:
+        # dense quadratic form: 2 D^2 + 2 D flops per walker-step against an fp64 DGEMM
+        # peak measured here (MEASURED_PEAKS.json has no fp64 entry): torch.matmul fp64, best of 5
+        m = 4096
+        a_ = torch.randn(m, m, device="cuda", dtype=torch.float64)
+        b_ = torch.randn(m, m, device="cuda", dtype=torch.float64)
+        best = 0.0
+        for _ in range(6):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(); c_ = a_ @ b_; t1.record(); torch.cuda.synchronize()
+            best = max(best, 2.0 * m ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12)
+        flops_per_launch = (2 * dim * dim + 2 * dim) * n_local
+        achieved = flops_per_launch * args.steps / (ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best,
+                    "traffic": traffic, "kernel": kernel_name,
+                    "peak_source": "cuBLAS fp64 DGEMM 4096^3 via torch.matmul, best of 6, measured in this run",
+                    "algorithmic_flops_per_walker_step": 2 * dim * dim + 2 * dim, "walkers_per_launch": n_local,
+                    "hbm_frac": b_alg(dim) * n_local * args.steps / (ms * 1e-3) / 1e9 / peak}
+    else:
+        bytes_per_launch = b_alg(dim) * n_local
+        achieved = bytes_per_launch * args.steps / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
+                    "algorithmic_bytes_per_walker_step": b_alg(dim), "walkers_per_launch": n_local,
+                    "note": "launch time = device time of the timed region / steps (one step kernel launch per step"
+                            + (", swap kernels amortised in)" if swap_every else ")")}
 
     cpu = None
     if not args.no_cpu and world == 1:

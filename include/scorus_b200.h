@@ -175,6 +175,25 @@ int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_ufs *ufs, co
 int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta_list, size_t nbeta, double *lp_all,
                             uint32_t *src_all);
 
+/* One-sided partner exchange: scorus_ipc_export fills two 64-byte CUDA IPC handles (ensemble,
+ * log-probs); after the ranks have exchanged them (any transport), scorus_ipc_attach maps every
+ * peer's buffers so that kernels of this context can read partner rows straight over NVLink. */
+int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens_64b, void *handle_lp_64b);
+int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_ens, const void *handles_lp);
+
+/* sample_pt of a walker shard with the reference's whole-ensemble matching, WITHOUT an all-gather:
+ * _begin builds the local pair list and pulls only the remote partners' rows over NVLink (one-sided
+ * reads of the peers mapped by scorus_ipc_attach); _end runs the fused step.  The caller inserts a
+ * stream-ordered barrier across ranks before _begin and between _begin and _end (peers must not
+ * overwrite rows that are still being read).  Identical to the single-GPU step. */
+int scorus_sample_pt_p2p_begin(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
+int scorus_sample_pt_p2p_end(scorus_ctx *ctx);
+
+/* Applies a swap plan to this rank's slots with one-sided reads of the peers (scorus_ipc_attach):
+ * phase 0 pulls every incoming row into scratch, the caller barriers across ranks, phase 1 commits
+ * rows and log-probs.  Equal shards (n_global = world * n_local). */
+int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, const double *lp_all, int phase);
+
 /* ---- plumbing ---- */
 int scorus_sync(scorus_ctx *ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream; NULL is CUDA's legacy default

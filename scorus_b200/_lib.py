@@ -73,6 +73,11 @@ def load() -> C.CDLL:
         "scorus_set_shard": (ci, [vp, u64, C.c_uint32, u64]),
         "scorus_sample_pt_global": (ci, [vp, dbl, C.POINTER(Ufs), dp, sz, vp, vp]),
         "scorus_swap_plan_device": (ci, [vp, dp, sz, vp, vp]),
+        "scorus_ipc_export": (ci, [vp, vp, vp]),
+        "scorus_ipc_attach": (ci, [vp, ci, ci, vp, vp]),
+        "scorus_sample_pt_p2p_begin": (ci, [vp, dbl, C.POINTER(Ufs), dp, sz]),
+        "scorus_sample_pt_p2p_end": (ci, [vp]),
+        "scorus_swap_apply_p2p": (ci, [vp, vp, vp, ci]),
         "scorus_sync": (ci, [vp]),
         "scorus_set_stream": (ci, [vp, vp]),
         "scorus_reset_stream": (ci, [vp]),
@@ -99,7 +104,8 @@ EXPORTS = [
     "scorus_set_logprob", "scorus_upload", "scorus_download", "scorus_init_logprob", "scorus_sample",
     "scorus_sample_pt", "scorus_sample_pt_fixed", "scorus_draw_z", "scorus_swap_walkers", "scorus_swap_walkers_fixed",
     "scorus_sample_pt_host", "scorus_swap_walkers_host", "scorus_set_shard", "scorus_sample_pt_global",
-    "scorus_swap_plan_device", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
+    "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
+    "scorus_sample_pt_p2p_begin", "scorus_sample_pt_p2p_end", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",
     "scorus_get_stats", "scorus_launch_count", "scorus_host_alloc", "scorus_host_free",
 ]

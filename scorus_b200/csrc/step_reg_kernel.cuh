@@ -85,7 +85,13 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
         for (int i = 0; i < GB; ++i) {
             const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
             const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
-            const double2 *src = reinterpret_cast<const double2 *>(p.src_ens + (size_t)row * p.pitch);
+            const double *base = p.src_ens + (size_t)row * p.pitch;
+            if (p.stage_ens) {  // one-sided mode: my rows are local, a remote partner's row sits in the stage
+                const uint32_t mate = __shfl_sync(0xffffffffu, wt, wl ^ 1u);
+                const bool mine_r = row >= p.w_lo && row < p.w_hi;
+                base = mine_r ? p.ens + (size_t)(row - p.w_lo) * p.pitch : p.stage_ens + (size_t)(mate - p.w_lo) * p.pitch;
+            }
+            const double2 *src = reinterpret_cast<const double2 *>(base);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 // lanes beyond the row re-read its last chunk (never used): an unconditional load keeps
@@ -106,9 +112,19 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
     {
         const uint32_t pos = tile * 32u + lane;
         act = pos < npos;
-        w = act ? walker_of(pos) : 0u;
+        w = act ? walker_of(pos) : p.w_lo;
     }
-    double lp_old = act ? __ldg(p.src_lp + w) : 0.0;
+    // old log-prob: from the (gathered) array, or in one-sided mode local / staged like the rows
+    auto load_lp = [&](uint32_t wid, bool a) -> double {
+        const uint32_t mate = __shfl_xor_sync(0xffffffffu, wid, 1);
+        if (!a) return 0.0;
+        if (p.stage_lp) {
+            const bool mine_w = wid >= p.w_lo && wid < p.w_hi;
+            return mine_w ? __ldg(p.lp + (wid - p.w_lo)) : __ldg(p.stage_lp + (mate - p.w_lo));
+        }
+        return __ldg(p.src_lp + wid);
+    };
+    double lp_old = load_lp(w, act);
     double2 xn[GB][ITERS];
     load_block(xn, w, 0);
 
@@ -134,15 +150,17 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
 
         // ids of the next tile (its first block is prefetched during this tile's last block)
         const uint32_t tile_n = tile + nwarps;
-        uint32_t w_n = 0;
+        uint32_t w_n = p.w_lo;
         bool act_n = false;
         double lp_n = 0.0;
         if (tile_n < ntiles) {
             const uint32_t pos = tile_n * 32u + lane;
             act_n = pos < npos;
-            w_n = act_n ? walker_of(pos) : 0u;
-            if (act_n) lp_n = __ldg(p.src_lp + w_n);
+            w_n = act_n ? walker_of(pos) : p.w_lo;
+        } else {
+            w_n = p.w_lo;
         }
+        lp_n = load_lp(w_n, act_n);
 
         double tot[Plugin::kAcc];
 #pragma unroll

@@ -41,6 +41,10 @@ struct StepParams {
     const double *src_ens;
     const double *src_lp;
     const uint32_t *n_dev;    // if set, the number of matching positions is read from device memory
+    // One-sided mode: instead of gathered copies, remote partners' rows were pulled over NVLink into
+    // stage_ens / stage_lp, indexed by the LOCAL member of the pair (local row = id - w_lo).
+    const double *stage_ens;
+    const double *stage_lp;
     uint32_t w_lo, w_hi;
 };
 

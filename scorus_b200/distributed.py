@@ -12,6 +12,9 @@ Two layouts, chosen from (nbeta, world size):
     - matching="global": the reference's whole-rung matching.  Each step all-gathers the ensemble over
       NVLink and runs scorus_sample_pt_global; results are bit-identical to the single-GPU run.  It is
       NVLink-bound -- the faithful, not the fast, configuration.
+    - matching="p2p": the same matching without the all-gather: each rank maps its peers' buffers
+      (CUDA IPC) and pulls only the rows of its walkers' remote partners with one-sided NVLink reads
+      (1/world of the all-gather's traffic), then runs the fused step; also bit-identical.
     - matching="local": every shard pairs within itself, no per-step exchange (each shard is itself a
       valid ensemble; the matching stays state-independent, so the move is still a valid MCMC kernel).
 
@@ -125,7 +128,7 @@ class ShardedSampler:
     """The sharded counterpart of Sampler: same calls, global beta list, local data."""
 
     def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, nbeta: int = 1, seed: int = 0,
-                 matching: str = "global", device: Optional[int] = None, group=None):
+                 matching: str = "global", device: Optional[int] = None, group=None, p2p_swap: bool = True):
         import torch
         import torch.distributed as dist
         self.dist, self.torch, self.group = dist, torch, group
@@ -134,8 +137,8 @@ class ShardedSampler:
         self.n_global, self.dim, self.nbeta = n_walkers, dim, nbeta
         self.mode, self.w_off, self.n_local, self.rung_off, self.nb_local = shard_layout(n_walkers, nbeta, self.world,
                                                                                         self.rank)
-        if matching not in ("global", "local"):
-            raise ValueError("matching must be 'global' or 'local'")
+        if matching not in ("global", "p2p", "local"):
+            raise ValueError("matching must be 'global', 'p2p' or 'local'")
         self.matching = matching
         dev = torch.cuda.current_device() if device is None else device
         self.device = torch.device("cuda", dev)
@@ -147,6 +150,16 @@ class ShardedSampler:
         self.sampler.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.ens, self.lp, self.pitch = device_views(self.sampler, self.device)
         self._ens_all = self._lp_all = self._src_all = None
+        self._token = None
+        self.p2p = False
+        if self.world > 1 and ((self.mode == "walkers" and matching == "p2p") or (self.mode == "rungs" and p2p_swap)):
+            self.p2p = True
+            # map every peer's ensemble / log-probs (CUDA IPC) for one-sided partner reads over NVLink
+            mine = self.sampler.ipc_export()
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            self.sampler.ipc_attach(self.world, self.rank, [h[0] for h in handles], [h[1] for h in handles])
+            self._token = torch.zeros(1, device=self.device)
 
     # -- data
     def upload(self, ens_local: np.ndarray, lp_local: Optional[np.ndarray] = None):
@@ -173,11 +186,22 @@ class ShardedSampler:
         if self.matching == "local" or self.world == 1:
             self.sampler.sample_pt(a, ufs, beta, nsteps)
             return
+        if self.matching == "p2p":
+            for _ in range(nsteps):
+                self._barrier()                                      # peers have finished their previous step
+                self.sampler.sample_pt_p2p_begin(a, ufs, beta)       # pull remote partners' rows over NVLink
+                self._barrier()                                      # nobody writes before everybody has read
+                self.sampler.sample_pt_p2p_end()                     # fused step, in place
+            return
         ens_all, lp_all, _ = self._gather_buffers()
         for _ in range(nsteps):                                      # all-gather + global-matching step
             self.dist.all_gather_into_tensor(ens_all, self.ens, group=self.group)
             self.dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
             self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
+
+    def _barrier(self):
+        """Stream-ordered barrier across ranks (a one-element all-reduce: no host synchronisation)."""
+        self.dist.all_reduce(self._token, group=self.group)
 
     def swap_walkers(self, beta_list: Sequence[float]):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
@@ -191,6 +215,12 @@ class ShardedSampler:
         _, lp_all, src_all = self._gather_buffers()
         dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
         self.sampler.swap_plan_device(beta, lp_all.data_ptr(), src_all.data_ptr())
+        if self.p2p:
+            # one-sided: pull incoming rows from the peers' (still old) buffers, barrier, commit
+            self.sampler.swap_apply_p2p(src_all.data_ptr(), lp_all.data_ptr(), 0)
+            self._barrier()
+            self.sampler.swap_apply_p2p(src_all.data_ptr(), lp_all.data_ptr(), 1)
+            return   # a step only writes the rank's own rows: no barrier needed after the commit
         local_dst, local_src, send_idx, recv_dst, send_counts, recv_counts = exchange_plan_torch(
             src_all, self.n_local, self.world, self.rank)
         send = self.ens.index_select(0, send_idx)                    # old rows, gathered before any write

@@ -330,6 +330,26 @@ class Sampler:
         self._ok(self._lib.scorus_swap_plan_device(self._ctx, _dp(beta), beta.size, C.c_void_p(lp_all_ptr),
                                                    C.c_void_p(src_all_ptr)))
 
+    def ipc_export(self):
+        he, hl = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._ok(self._lib.scorus_ipc_export(self._ctx, he, hl))
+        return he.raw, hl.raw
+
+    def ipc_attach(self, world: int, rank: int, handles_ens, handles_lp):
+        be, bl = b"".join(handles_ens), b"".join(handles_lp)
+        self._ok(self._lib.scorus_ipc_attach(self._ctx, world, rank, be, bl))
+
+    def sample_pt_p2p_begin(self, a: float, ufs: UpdateFlagSpec, beta_list):
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        u, keep = ufs._c(self.n, self.dim)
+        self._ok(self._lib.scorus_sample_pt_p2p_begin(self._ctx, a, C.byref(u), _dp(beta), beta.size))
+
+    def sample_pt_p2p_end(self):
+        self._ok(self._lib.scorus_sample_pt_p2p_end(self._ctx))
+
+    def swap_apply_p2p(self, src_all_ptr: int, lp_all_ptr: int, phase: int):
+        self._ok(self._lib.scorus_swap_apply_p2p(self._ctx, C.c_void_p(src_all_ptr), C.c_void_p(lp_all_ptr), phase))
+
     # -- plumbing
     def sync(self):
         self._ok(self._lib.scorus_sync(self._ctx))

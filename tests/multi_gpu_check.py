@@ -18,7 +18,7 @@ import scorus_b200 as sb  # noqa: E402
 from scorus_b200.distributed import ShardedSampler  # noqa: E402
 
 
-def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matching="global"):
+def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matching="global", p2p_swap=True):
     rank, world = dist.get_rank(), dist.get_world_size()
     rng = np.random.default_rng(1234)
     ens = np.ascontiguousarray(rng.uniform(box[0], box[1], (n, dim)))
@@ -27,7 +27,7 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
     # single-GPU reference of the WHOLE ensemble
     ref = sb.Sampler(flogprob, n, dim, seed=seed, device=torch.cuda.current_device())
     ref.upload(ens, None)
-    sh = ShardedSampler(flogprob, n, dim, nbeta=nbeta, seed=seed, matching=matching)
+    sh = ShardedSampler(flogprob, n, dim, nbeta=nbeta, seed=seed, matching=matching, p2p_swap=p2p_swap)
     lo, hi = sh.w_off, sh.w_off + sh.n_local
     sh.upload(np.ascontiguousarray(ens[lo:hi]), None)
     for k in range(steps):
@@ -44,7 +44,7 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
     flag = torch.tensor([int(ok_pos and ok_lp and moved)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"{name}: mode={sh.mode}/{matching} world={world} n={n} dim={dim} nbeta={nbeta} "
+        print(f"{name}: mode={sh.mode}/{matching}{'/p2p' if sh.p2p else ''} world={world} n={n} dim={dim} nbeta={nbeta} "
               f"{'OK' if flag.item() else 'MISMATCH'} (pos={ok_pos} lp={ok_lp} moved={moved})", flush=True)
     ref.close()
     return bool(flag.item())
@@ -63,11 +63,19 @@ def main():
                    sb.UpdateFlagSpec.Prob(0.2), 12, 4, (-0.5, 0.5))
     ok &= run_case("gauss_onehot_pt", sb.Gaussian(1.0), 40 * 2 * world, 10, 2 * world,
                    sb.UpdateFlagSpec.OneHotCycle(), 12, 3, (-1.0, 1.0))
+    # the same swaps with the NCCL all-to-all row exchange instead of one-sided reads
+    ok &= run_case("rastrigin_pt_nccl_exchange", sb.Rastrigin(), 2048 * 4 * world, 10, 4 * world,
+                   sb.UpdateFlagSpec.Prob(0.2), 12, 4, (-0.5, 0.5), p2p_swap=False)
     # single temperature, walker shards, the reference's whole-rung matching over an all-gather
     ok &= run_case("rosenbrock_global_matching", sb.Rosenbrock(), 8192 * world, 64, 1,
                    sb.UpdateFlagSpec.Prob(0.5), 10, 0, (0.9, 1.1))
     ok &= run_case("mixture_global_matching_small", sb.Mixture(1.0, 2.0, [5.0] + [0.0] * 5), 64 * world, 6, 1,
                    sb.UpdateFlagSpec.All(), 10, 0, (-6.0, 6.0))
+    # the same matching with one-sided NVLink reads of the partners instead of the all-gather
+    ok &= run_case("rosenbrock_p2p_matching", sb.Rosenbrock(), 8192 * world, 64, 1,
+                   sb.UpdateFlagSpec.Prob(0.5), 10, 0, (0.9, 1.1), matching="p2p")
+    ok &= run_case("rastrigin_p2p_matching_small_odd", sb.Rastrigin(), 70 * world, 7, 1,
+                   sb.UpdateFlagSpec.Prob(0.2), 10, 0, (-0.5, 0.5), matching="p2p")
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
