@@ -257,10 +257,17 @@ def main():
         can_swap = True
 
     def run_steps(k0, count):
-        for k in range(k0, k0 + count):
+        # consecutive steps between two swaps go down in ONE library call (nsteps): the launches are
+        # queued back to back from C, without a Python round trip per step
+        k, end = k0, k0 + count
+        while k < end:
             if swap_every and nbeta > 1 and can_swap and k % swap_every == 0:
                 swap(beta)
-            s.sample_pt(2.0, spec, beta, 1)
+            nxt = min(end, (k // swap_every + 1) * swap_every) if (swap_every and nbeta > 1 and can_swap) else end
+            if os.environ.get("BENCH_STEP_PER_CALL"):
+                nxt = k + 1
+            s.sample_pt(2.0, spec, beta, nxt - k)
+            k = nxt
 
     run_steps(0, W)
     torch.cuda.synchronize()

@@ -40,6 +40,17 @@ cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const G
     }
     const uint32_t nvec = p.pitch / 2;
     if (g.kernel == KERNEL_REG) {
+        if (p.stage_ens) {  // one-sided multi-GPU mode
+            if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4, true>, p, g, st);
+            if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2, true>, p, g, st);
+            switch (coop_group(p.pitch)) {
+            case 2: return launch_kernel(step_reg_kernel<Plugin, 2, 1, true>, p, g, st);
+            case 4: return launch_kernel(step_reg_kernel<Plugin, 4, 1, true>, p, g, st);
+            case 8: return launch_kernel(step_reg_kernel<Plugin, 8, 1, true>, p, g, st);
+            case 16: return launch_kernel(step_reg_kernel<Plugin, 16, 1, true>, p, g, st);
+            default: return launch_kernel(step_reg_kernel<Plugin, 32, 1, true>, p, g, st);
+            }
+        }
         if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4>, p, g, st);
         if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2>, p, g, st);
         switch (coop_group(p.pitch)) {

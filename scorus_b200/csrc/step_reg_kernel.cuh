@@ -44,7 +44,9 @@ struct RegGeom {
     static constexpr int kBlocks = G / kRowsPerBlock;
 };
 
-template <class Plugin, int G, int ITERS>
+// kStaged: one-sided multi-GPU mode (remote partners' rows pulled into p.stage_ens / p.stage_lp).  A
+// template parameter because even uniform branches on it cost 12 % in the single-GPU kernel.
+template <class Plugin, int G, int ITERS, bool kStaged = false>
 __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
 {
     using Geo = RegGeom<G, ITERS>;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
             const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
             const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
             const double *base = p.src_ens + (size_t)row * p.pitch;
-            if (p.stage_ens) {  // one-sided mode: my rows are local, a remote partner's row sits in the stage
+            if constexpr (kStaged) {  // one-sided mode: my rows are local, a remote partner's row sits in the stage
                 const uint32_t mate = __shfl_sync(0xffffffffu, wt, wl ^ 1u);
                 const bool mine_r = row >= p.w_lo && row < p.w_hi;
                 base = mine_r ? p.ens + (size_t)(row - p.w_lo) * p.pitch : p.stage_ens + (size_t)(mate - p.w_lo) * p.pitch;
@@ -116,13 +118,14 @@ __global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
     }
     // old log-prob: from the (gathered) array, or in one-sided mode local / staged like the rows
     auto load_lp = [&](uint32_t wid, bool a) -> double {
-        const uint32_t mate = __shfl_xor_sync(0xffffffffu, wid, 1);
-        if (!a) return 0.0;
-        if (p.stage_lp) {
+        if constexpr (kStaged) {
+            const uint32_t mate = __shfl_xor_sync(0xffffffffu, wid, 1);
+            if (!a) return 0.0;
             const bool mine_w = wid >= p.w_lo && wid < p.w_hi;
             return mine_w ? __ldg(p.lp + (wid - p.w_lo)) : __ldg(p.stage_lp + (mate - p.w_lo));
+        } else {
+            return a ? __ldg(p.src_lp + wid) : 0.0;
         }
-        return __ldg(p.src_lp + wid);
     };
     double lp_old = load_lp(w, act);
     double2 xn[GB][ITERS];

@@ -17,7 +17,7 @@ def _box(rng, n, d, lo, hi):
     return np.ascontiguousarray(rng.uniform(lo, hi, (n, d)))
 
 
-@pytest.mark.parametrize("seq", [False, True], ids=["coop", "seq"])
+@pytest.mark.parametrize("seq", [False, True], ids=["reg", "seq"])
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
 def test_golden_fixed_stream(sb, path, seq):
     g = np.load(path)
@@ -52,6 +52,10 @@ SHAPES = [
     (5, [], 128, 3, 2, (-0.1, 1.1)),
     (7, None, 1024, 32, 1, (-6, 6)),
     (6, None, 256, 12, 1, (-1, 1)),
+    (6, None, 2048, 100, 1, (-1, 1)),     # BASELINE config 2 shape: DMMA tile path, two chunks per lane
+    (2, [], 64, 300, 2, (0.9, 1.1)),      # dim > 256: the TMA-staged cooperative kernel is the default
+    (0, [0.5], 4096, 128, 1, (-1, 1)),    # two chunks per lane in the register kernel
+    (3, [10.0], 1024, 200, 1, (-0.5, 0.5)),  # four chunks per lane
 ]
 
 
@@ -66,9 +70,14 @@ def _params_for(kind, params, dim, rng):
 
 
 @pytest.mark.parametrize("case", SHAPES, ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}")
-@pytest.mark.parametrize("seq", [False, True], ids=["coop", "seq"])
+@pytest.mark.parametrize("variant", ["reg", "seq", "coop"])
 @pytest.mark.parametrize("ufs", ["prob", "all", "short"])
-def test_fixed_stream_vs_oracle(sb, oracle, case, ufs, seq):
+def test_fixed_stream_vs_oracle(sb, oracle, case, ufs, variant, monkeypatch):
+    """variant: the default register-streaming kernel, the sequential-sum kernel
+    (SCORUS_CFG_SEQUENTIAL_SUM), or the TMA-staged cooperative kernel (forced here; used for dim > 256)."""
+    seq = variant == "seq"
+    if variant == "coop":
+        monkeypatch.setenv("SCORUS_KERNEL", "coop")
     kind, params, n, dim, nb, box = case
     rng = np.random.default_rng(1000 * kind + dim)
     params = _params_for(kind, params, dim, rng)
@@ -113,7 +122,7 @@ def test_fixed_stream_vs_oracle(sb, oracle, case, ufs, seq):
 @pytest.mark.parametrize("case", [(0, [0.5], 16, 2, 1), (2, [], 4096, 64, 1), (3, [10.0], 2048, 10, 8),
                                   (2, [], 8192, 16, 2), (0, [1.0], 320, 10, 4)],
                          ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}")
-@pytest.mark.parametrize("seq", [False, True], ids=["coop", "seq"])
+@pytest.mark.parametrize("seq", [False, True], ids=["reg", "seq"])
 @pytest.mark.parametrize("ufs", ["prob0.5", "prob0.2", "prob0.25", "all", "onehot"])
 def test_philox_mode_replays_through_oracle(sb, oracle, case, ufs, seq):
     """The device draws its own streams (Philox); the oracle regenerates the same streams on the
