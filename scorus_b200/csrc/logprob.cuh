@@ -30,6 +30,7 @@ namespace scorus {
 // -sum c*x^2.  examples/test_emcee.rs:18-24 (c = 1/2), examples/sample_high_dim.rs:22-28 (c = 1)
 struct LpGaussian {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 1;
     double c, acc;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t)
@@ -54,6 +55,7 @@ struct LpGaussian {
 // examples/sample_bimodal.rs:35-44: subtract, then -inf as soon as one |x| exceeds the limit
 struct LpBoundedGaussian {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 2;  // [0] the sum, [1] number of coordinates beyond the limit
     double limit, acc;
     bool dead;
@@ -84,6 +86,7 @@ struct LpBoundedGaussian {
 // examples/test_emcee.rs:26-32: -sum_i [100 (x[i+1] - x[i]^2)^2 + (1 - x[i])^2]
 struct LpRosenbrock {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 1;
     double prev, acc;
     __device__ __forceinline__ void init(const double *, uint32_t, uint32_t)
@@ -118,6 +121,7 @@ struct LpRosenbrock {
 // examples/sample_rastrigin.rs:17-25: -(n a) + sum [a cos(2 pi x) - x^2]
 struct LpRastrigin {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 1;
     double a, acc, base;
     static __device__ __forceinline__ double term(double a, double y)
@@ -147,6 +151,7 @@ struct LpRastrigin {
 // examples/sample_bimodal.rs:46-54
 struct LpBimodal2d {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 2;  // [0] carries x0, [1] carries x1
     double lo0, hi0, lo1, hi1, split, mu_a, sg_a, mu_b, sg_b, x0, x1;
     uint32_t dim;
@@ -191,6 +196,7 @@ struct LpBimodal2d {
 // examples/sample_bimodal.rs:56-65
 struct LpStep2d {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 2;
     double x0, x1;
     uint32_t dim;
@@ -223,9 +229,11 @@ struct LpStep2d {
 // builder-defined (BASELINE config 3): logsumexp of two isotropic Gaussians at +m and -m
 struct LpMixture {
     static constexpr bool kNeedsRow = false;
+    static constexpr int kMaxWarps = 14;
     static constexpr int kAcc = 2;
     const double *m;
     double s1, s2, q1, q2;
+    double den1, den2, c1, c2;  // (2 s) s and D ln s, hoisted out of the per-walker tail (same roundings)
     uint32_t dim;
     bool ok;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t d)
@@ -235,6 +243,10 @@ struct LpMixture {
         s2 = ok ? __ldg(p + 1) : 1.0;
         m = p + 2;
         q1 = 0.0; q2 = 0.0; dim = d;
+        den1 = (2.0 * s1) * s1;
+        den2 = (2.0 * s2) * s2;
+        c1 = (double)d * log(s1);
+        c2 = (double)d * log(s2);
     }
     __device__ __forceinline__ void accum(uint32_t d, double y)
     {
@@ -247,8 +259,8 @@ struct LpMixture {
     __device__ __forceinline__ double eval(double a1, double a2) const
     {
         if (!ok) return NAN;
-        double t1 = (-a1) / ((2.0 * s1) * s1) - (double)dim * log(s1);
-        double t2 = (-a2) / ((2.0 * s2) * s2) - (double)dim * log(s2);
+        double t1 = (-a1) / den1 - c1;
+        double t2 = (-a2) / den2 - c2;
         double hi = t1 > t2 ? t1 : t2;
         double lo = t1 > t2 ? t2 : t1;
         if (hi == -INFINITY) return -INFINITY;
@@ -271,6 +283,10 @@ struct LpMixture {
     __device__ __forceinline__ double finish_acc(const double *a) const { return eval(a[0], a[1]); }
 };
 
+#ifndef SCORUS_K3_NG
+#define SCORUS_K3_NG 4
+#endif
+
 // fp64 tensor-core MMA, D[8x8] += A[8x4] * B[4x8] (SASS: DMMA.8x8x4).  Lane l holds A[l/4][l%4],
 // B[l%4][l/4] and C/D[l/4][2*(l%4) + {0,1}].
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
@@ -288,6 +304,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
 struct LpCorrGaussian {
     static constexpr bool kNeedsRow = true;
     static constexpr bool kTile = true;
+    static constexpr int kMaxWarps = 8;  // register kernel: 256 threads -> up to 255 registers for the DMMA accumulators
     static constexpr int kAcc = 1;
     const double *mu, *L;
     uint32_t dim;
@@ -313,7 +330,7 @@ struct LpCorrGaussian {
         for (int mt = 0; mt < 4; ++mt)
             rows[mt] = reinterpret_cast<const double *>(tile + (size_t)(mt * 8 + g) * row_stride);
         double ss[4] = {0.0, 0.0, 0.0, 0.0};  // sum over my columns of W[row mt*8+g][.]^2
-        constexpr int NG = 2;                 // n-tiles per pass: bounds the accumulators to 16 doubles
+        constexpr int NG = SCORUS_K3_NG;      // n-tiles per pass: NG*8 accumulator doubles, NG*4 independent DMMAs per k-step
         for (uint32_t n0 = 0; n0 < dim; n0 += 8 * NG) {
             double c[NG][4][2];
 #pragma unroll

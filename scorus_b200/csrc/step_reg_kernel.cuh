@@ -47,7 +47,7 @@ struct RegGeom {
 // kStaged: one-sided multi-GPU mode (remote partners' rows pulled into p.stage_ens / p.stage_lp).  A
 // template parameter because even uniform branches on it cost 12 % in the single-GPU kernel.
 template <class Plugin, int G, int ITERS, bool kStaged = false>
-__global__ void __launch_bounds__(448, 1) step_reg_kernel(const StepParams p)
+__global__ void __launch_bounds__(Plugin::kMaxWarps * 32, 1) step_reg_kernel(const StepParams p)
 {
     using Geo = RegGeom<G, ITERS>;
     constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;
