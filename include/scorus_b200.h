@@ -156,6 +156,22 @@ int scorus_sample_pt_host(scorus_ctx *ctx, double *ensemble, double *logprob, si
 int scorus_swap_walkers_host(scorus_ctx *ctx, double *ensemble, double *logprob,
                              size_t logprob_len, const double *beta_list, size_t nbeta);
 
+/* ---- periphery of the path ----
+ * get_one_init_realization, src/mcmc/init_ensemble.rs:19-32, for every walker on the device:
+ * x[d] ~ U[lo[d], hi[d]) from the device stream; runs init_logprob if a log-density is registered. */
+int scorus_init_ensemble(scorus_ctx *ctx, const double *lo, const double *hi);
+/* mean / cov, src/linear_space/utils.rs:4-15, 17-41, of walkers [first, first+count) (a rung or the
+ * whole ensemble) computed on the device: mean_out[dim]; cov_out[dim][dim], biased (/N), about the mean. */
+int scorus_mean(scorus_ctx *ctx, size_t first, size_t count, double *mean_out);
+int scorus_cov(scorus_ctx *ctx, size_t first, size_t count, double *cov_out);
+/* The examples' recording loops (`results[i].push(ensemble[i*n+0][0])`, examples/sample_high_dim.rs:84-86)
+ * without a download per step: after every sample_pt step the values ens[walkers[c]][coords[c]] are
+ * captured on the device (up to capacity_steps rows).  scorus_trace_download copies min(recorded,
+ * max_steps) rows of ncapture doubles, reports how many steps were recorded and rewinds the buffer. */
+int scorus_trace_enable(scorus_ctx *ctx, const uint32_t *walkers, const uint32_t *coords, size_t ncapture,
+                        size_t capacity_steps);
+int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_steps, size_t *nrecorded);
+
 /* ---- sharding: one process per GPU ----
  * scorus_set_shard tells a context which slice of the whole ensemble it holds: its walker i is
  * global walker walker_offset + i, its rung r is global rung rung_offset + r.  The device streams are

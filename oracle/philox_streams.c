@@ -24,7 +24,8 @@ enum {
     ST_SWAP_PERM = 4, /* idx = hot rung, sub = 0,1: keys of the jvec bijection (npb > 1024) */
     ST_SWAP_U = 5,    /* idx = cold slot j2, sub = hot rung */
     ST_PERM_KEY = 6,  /* idx = walker: 64-bit sort key of the exact shuffle (npb <= 1024) */
-    ST_SWAP_KEY = 7   /* idx = hot walker slot: 64-bit sort key of the exact jvec (npb <= 1024) */
+    ST_SWAP_KEY = 7,  /* idx = hot walker slot: 64-bit sort key of the exact jvec (npb <= 1024) */
+    ST_INIT = 8       /* idx = walker, sub = d/2, step = 0: box-uniform start of coordinates d, d+1 */
 };
 
 #define EXACT_SHUFFLE_MAX 1024u
@@ -235,4 +236,18 @@ int orc_philox_swap_streams(uint64_t seed, uint64_t swap_call, size_t n, size_t 
     }
     free(kv);
     return ORC_OK;
+}
+
+/* the device's box-uniform init (scorus_init_ensemble): x[w][d] = lo[d] + u * (hi[d] - lo[d]) */
+void orc_philox_init_ensemble(uint64_t seed, size_t n, size_t dim, uint64_t walker_offset, const double *lo,
+                              const double *hi, double *ens)
+{
+    for (size_t w = 0; w < n; ++w)
+        for (size_t c = 0; 2 * c < dim; ++c) {
+            uint32_t o[4];
+            draw(seed, 0, ST_INIT, (uint32_t)(w + walker_offset), (uint32_t)c, o);
+            size_t d0 = 2 * c;
+            ens[w * dim + d0] = lo[d0] + u53(o[0], o[1]) * (hi[d0] - lo[d0]);
+            if (d0 + 1 < dim) ens[w * dim + d0 + 1] = lo[d0 + 1] + u53(o[2], o[3]) * (hi[d0 + 1] - lo[d0 + 1]);
+        }
 }

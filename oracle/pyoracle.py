@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         L.orc_philox_sample_streams.argtypes = [u64, u64, sz, sz, sz, dbl, ci, dbl, u64, u32p, dp, u8p, dp]
         L.orc_philox_swap_streams.restype = ci
         L.orc_philox_swap_streams.argtypes = [u64, u64, sz, sz, u32p, dp]
+        L.orc_philox_init_ensemble.restype = None
+        L.orc_philox_init_ensemble.argtypes = [u64, sz, sz, u64, dp, dp, dp]
         L.orc_ref_structure_run.restype = dbl
         L.orc_ref_structure_run.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, sz, dbl, ci, dbl, u64, sz,
                                             ci, dp]
@@ -285,6 +287,14 @@ def philox_swap_streams(seed, swap_call, n, nbeta):
     if rc:
         raise ValueError(f"orc_philox_swap_streams rc={rc}")
     return jvec, r
+
+
+def philox_init_ensemble(seed, n, dim, lo, hi, walker_offset=0):
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    out = np.empty((n, dim))
+    lib().orc_philox_init_ensemble(seed, n, dim, walker_offset, _dp(lo), _dp(hi), _dp(out))
+    return out
 
 
 def ref_structure_run(kind, params, ens, lp, beta, a, ufs_kind, prob, seed, nsteps, nthreads=0):

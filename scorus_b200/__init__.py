@@ -3,14 +3,14 @@
 Only what the path needs: csrc/ (CUDA kernels + the C ABI of include/scorus_b200.h) and the
 host-side mirror of the reference modules `mcmc::ensemble_sample` and `mcmc::utils`.
 """
-from . import ensemble_sample, utils  # noqa: F401
+from . import ensemble_sample, init_ensemble, linear_space, utils  # noqa: F401
 from .ensemble_sample import (  # noqa: F401
     BoundedGaussian, Bimodal2d, CorrGaussian, DeviceRng, Gaussian, LogProb, McmcErr, Mixture, Rastrigin,
     Rosenbrock, Sampler, Step2d, UpdateFlagSpec, init_logprob, pinned_empty, propose_move, sample, sample_pt)
 from .utils import draw_z, scale_vec, swap_walkers  # noqa: F401
 
 __all__ = [
-    "ensemble_sample", "utils", "Sampler", "DeviceRng", "LogProb", "McmcErr", "UpdateFlagSpec",
+    "ensemble_sample", "utils", "init_ensemble", "linear_space", "Sampler", "DeviceRng", "LogProb", "McmcErr", "UpdateFlagSpec",
     "Gaussian", "BoundedGaussian", "Rosenbrock", "Rastrigin", "Bimodal2d", "Step2d", "CorrGaussian", "Mixture",
     "init_logprob", "sample", "sample_pt", "propose_move", "swap_walkers", "draw_z", "scale_vec", "pinned_empty",
 ]

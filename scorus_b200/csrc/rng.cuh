@@ -17,7 +17,8 @@ enum : uint32_t {
     ST_SWAP_PERM = 4,  // idx = hot rung, sub = 0,1: keys of the jvec bijection (npb > 1024)
     ST_SWAP_U = 5,     // idx = cold slot j2, sub = hot rung: swap uniform
     ST_PERM_KEY = 6,   // idx = walker: 64-bit sort key of the exact shuffle (npb <= 1024)
-    ST_SWAP_KEY = 7    // idx = hot walker slot: 64-bit sort key of the exact jvec (npb <= 1024)
+    ST_SWAP_KEY = 7,   // idx = hot walker slot: 64-bit sort key of the exact jvec (npb <= 1024)
+    ST_INIT = 8        // idx = walker, sub = d/2: box-uniform start of coordinates d, d+1 (step = 0)
 };
 
 constexpr uint32_t kExactShuffleMax = 1024;  // rungs up to this size get an exact uniform shuffle

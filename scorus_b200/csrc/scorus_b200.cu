@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "launch.cuh"
+#include "stats_kernel.cuh"
 #include "swap_kernel.cuh"
 #include "tile_common.cuh"
 
@@ -48,6 +49,12 @@ struct scorus_ctx {
     double *peer_ens[16] = {nullptr}, *peer_lp[16] = {nullptr};
     double **d_peer_ens = nullptr, **d_peer_lp = nullptr;   // device copies of the tables
     double *d_stage = nullptr, *d_stage_lp = nullptr;       // pulled partner rows, one per local walker
+    // K6: statistics scratch and the chain trace
+    double *d_part = nullptr; size_t part_cap = 0;
+    double *d_stat = nullptr; size_t stat_cap = 0;
+    uint32_t *d_tr_walker = nullptr, *d_tr_coord = nullptr;
+    double *d_trace = nullptr;
+    size_t tr_ncap = 0, tr_capacity = 0, tr_count = 0;
     bool p2p_pending = false;                                // scorus_sample_pt_p2p_begin without _end
     StepParams p2p_params;
     Geometry p2p_geom;
@@ -218,7 +225,8 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
             if (ctx->peer_ens[q]) cudaIpcCloseMemHandle(ctx->peer_ens[q]);
             if (ctx->peer_lp[q]) cudaIpcCloseMemHandle(ctx->peer_lp[q]);
         }
-    void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_stage, ctx->d_stage_lp};
+    void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_stage, ctx->d_stage_lp, ctx->d_part, ctx->d_stat,
+                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace};
     for (void *b : p2p)
         if (b) cudaFree(b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -530,6 +538,17 @@ static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta
     return SCORUS_OK;
 }
 
+// chain capture after a step (scorus_trace_enable); silently stops when the buffer is full
+static void record_trace(scorus_ctx *ctx)
+{
+    if (!ctx->tr_ncap || ctx->tr_count >= ctx->tr_capacity) return;
+    trace_kernel<<<(unsigned)((ctx->tr_ncap + 127) / 128), 128, 0, ctx->stream>>>(
+        ctx->d_ens, ctx->pitch, ctx->d_tr_walker, ctx->d_tr_coord, (uint32_t)ctx->tr_ncap,
+        ctx->d_trace + ctx->tr_count * ctx->tr_ncap);
+    ++ctx->launches;
+    ++ctx->tr_count;
+}
+
 extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
                                 size_t nbeta, uint64_t nsteps)
 {
@@ -594,6 +613,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
         ++ctx->step;
         ctx->proposed += ctx->n;
         if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
+        record_trace(ctx);
     }
     return SCORUS_OK;
 }
@@ -1109,6 +1129,113 @@ extern "C" int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, c
     ++ctx->launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap apply launch: %s", cudaGetErrorString(e));
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// periphery: box init, ensemble statistics, chain trace (stats_kernel.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_init_ensemble(scorus_ctx *ctx, const double *lo, const double *hi)
+{
+    if (!ctx || !lo || !hi) return SCORUS_ERR_INVALID_ARG;
+    for (uint32_t d = 0; d < ctx->dim; ++d)
+        if (!(lo[d] < hi[d])) return fail(ctx, SCORUS_ERR_INVALID_ARG, "empty range in coordinate %u (Uniform::new panics)", d);
+    cudaSetDevice(ctx->device);
+    int rc = ensure(ctx, (void **)&ctx->d_stat, &ctx->stat_cap, 2 * (size_t)ctx->dim * sizeof(double));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(ctx->d_stat, lo, ctx->dim * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_stat + ctx->dim, hi, ctx->dim * sizeof(double), cudaMemcpyHostToDevice));
+    init_ensemble_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, ctx->stream>>>(
+        ctx->d_ens, (uint32_t)ctx->n, ctx->dim, ctx->pitch, ctx->d_stat, ctx->d_stat + ctx->dim, ctx->seed, (uint32_t)ctx->w_off);
+    ++ctx->launches;
+    ctx->uploaded = true;
+    if (ctx->lp_kind >= 0) return scorus_init_logprob(ctx);
+    return SCORUS_OK;
+}
+
+static int stats_impl(scorus_ctx *ctx, size_t first, size_t count, double *mean_out, double *cov_out)
+{
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    if (count == 0 || first + count > ctx->n) return fail(ctx, SCORUS_ERR_INVALID_ARG, "walker range outside the ensemble");
+    const uint32_t dim = ctx->dim, len = dim * dim;
+    if (cov_out && dim > (uint32_t)kCovMaxDim) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "cov supports dim <= %d", kCovMaxDim);
+    cudaSetDevice(ctx->device);
+    uint32_t blocks = (uint32_t)ctx->num_sms * 2u;
+    if (blocks > count) blocks = (uint32_t)count;
+    int rc = ensure(ctx, (void **)&ctx->d_part, &ctx->part_cap, (size_t)blocks * (cov_out ? len : dim) * sizeof(double));
+    if (rc) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_stat, &ctx->stat_cap, ((size_t)dim + len) * sizeof(double)))) return rc;
+    double *d_mean = ctx->d_stat, *d_cov = ctx->d_stat + dim;
+    colsum_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ens, (uint32_t)first, (uint32_t)count, dim, ctx->pitch, ctx->d_part);
+    reduce_partials_kernel<<<(dim + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_part, blocks, dim, 1.0 / (double)count, 0, d_mean);
+    ctx->launches += 2;
+    if (mean_out) CU(cudaMemcpyAsync(mean_out, d_mean, dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cov_out) {
+        uint32_t cblocks = (uint32_t)ctx->num_sms;
+        if (cblocks > (count + 31) / 32) cblocks = (uint32_t)((count + 31) / 32);
+        const size_t smem = 32u * (size_t)dim * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(cov_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "cov smem: %s", cudaGetErrorString(e));
+        cov_partial_kernel<<<cblocks, 256, smem, ctx->stream>>>(ctx->d_ens, (uint32_t)first, (uint32_t)count, dim, ctx->pitch,
+                                                               d_mean, ctx->d_part);
+        reduce_partials_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_part, cblocks, len, (double)count, 1, d_cov);
+        ctx->launches += 2;
+        CU(cudaMemcpyAsync(cov_out, d_cov, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "stats launch: %s", cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_mean(scorus_ctx *ctx, size_t first, size_t count, double *mean_out)
+{
+    if (!ctx || !mean_out) return SCORUS_ERR_INVALID_ARG;
+    return stats_impl(ctx, first, count, mean_out, nullptr);
+}
+
+extern "C" int scorus_cov(scorus_ctx *ctx, size_t first, size_t count, double *cov_out)
+{
+    if (!ctx || !cov_out) return SCORUS_ERR_INVALID_ARG;
+    return stats_impl(ctx, first, count, nullptr, cov_out);
+}
+
+extern "C" int scorus_trace_enable(scorus_ctx *ctx, const uint32_t *walkers, const uint32_t *coords, size_t ncapture,
+                                   size_t capacity_steps)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    void *old[] = {ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace};
+    for (void *b : old)
+        if (b) cudaFree(b);
+    ctx->d_tr_walker = ctx->d_tr_coord = nullptr;
+    ctx->d_trace = nullptr;
+    ctx->tr_ncap = ctx->tr_capacity = ctx->tr_count = 0;
+    if (ncapture == 0 || capacity_steps == 0) return SCORUS_OK;  // disabled
+    if (!walkers || !coords) return SCORUS_ERR_INVALID_ARG;
+    for (size_t c = 0; c < ncapture; ++c)
+        if (walkers[c] >= ctx->n || coords[c] >= ctx->dim) return fail(ctx, SCORUS_ERR_INVALID_ARG, "trace entry %zu out of range", c);
+    CU(cudaMalloc(&ctx->d_tr_walker, ncapture * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_tr_coord, ncapture * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_trace, ncapture * capacity_steps * sizeof(double)));
+    CU(cudaMemcpy(ctx->d_tr_walker, walkers, ncapture * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_tr_coord, coords, ncapture * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->tr_ncap = ncapture;
+    ctx->tr_capacity = capacity_steps;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_steps, size_t *nrecorded)
+{
+    if (!ctx || !nrecorded) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    size_t k = ctx->tr_count < max_steps ? ctx->tr_count : max_steps;
+    if (k && out) CU(cudaMemcpyAsync(out, ctx->d_trace, k * ctx->tr_ncap * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *nrecorded = ctx->tr_count;
+    ctx->tr_count = 0;
     return SCORUS_OK;
 }
 

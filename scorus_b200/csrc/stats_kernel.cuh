@@ -1,0 +1,103 @@
+// stats_kernel.cuh -- the periphery of the path: K6 ensemble statistics, chain capture, box init.
+//
+//   mean / cov        src/linear_space/utils.rs:4-15, 17-41 (ensemble mean, biased /N covariance):
+//                     the reference's own summary statistics, here as deterministic two-stage
+//                     reductions over a walker range (a rung or the whole ensemble)
+//   trace             the recording loops of the examples (`results[i].push(ensemble[i*n+0][0])`,
+//                     examples/sample_high_dim.rs:84-86, examples/sample_bimodal.rs:137-139): selected
+//                     (walker, coordinate) values captured on the device after every step
+//   init              get_one_init_realization, src/mcmc/init_ensemble.rs:19-32: x[d] ~ U[lo[d], hi[d])
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rng.cuh"
+
+namespace scorus {
+
+// x[w][d] = lo[d] + u * (hi[d] - lo[d]), u from stream ST_INIT keyed by the GLOBAL walker id
+__global__ void __launch_bounds__(256) init_ensemble_kernel(double *ens, uint32_t n, uint32_t dim, uint32_t pitch,
+                                                            const double *lo, const double *hi, uint64_t seed,
+                                                            uint32_t w_off)
+{
+    const uint32_t half = (dim + 1u) / 2u;
+    const size_t total = (size_t)n * half;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(g / half), c = (uint32_t)(g - (size_t)w * half);
+        const U4 r = draw(seed, 0, ST_INIT, w + w_off, c);
+        const uint32_t d0 = 2u * c;
+        double *row = ens + (size_t)w * pitch;
+        row[d0] = __ldg(lo + d0) + u53(r.x, r.y) * (__ldg(hi + d0) - __ldg(lo + d0));
+        if (d0 + 1u < dim) row[d0 + 1u] = __ldg(lo + d0 + 1u) + u53(r.z, r.w) * (__ldg(hi + d0 + 1u) - __ldg(lo + d0 + 1u));
+    }
+}
+
+// stage 1 of the column sums: block b sums rows b, b+grid, ... of [first, first+count) -> part[b][dim]
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const double *ens, uint32_t first, uint32_t count,
+                                                             uint32_t dim, uint32_t pitch, double *part)
+{
+    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
+        double s = 0.0;
+        for (uint32_t r = blockIdx.x; r < count; r += gridDim.x) s += ens[(size_t)(first + r) * pitch + d];
+        part[(size_t)blockIdx.x * dim + d] = s;
+    }
+}
+
+// stage 2: fixed-order sum over the partials, then scale (mean: * (1/N) as utils.rs:14; cov: / N as :38)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *part, uint32_t nparts, uint32_t len,
+                                                              double scale, int divide, double *out)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double s = 0.0;
+    for (uint32_t b = 0; b < nparts; ++b) s += part[(size_t)b * len + e];
+    out[e] = divide ? s / scale : s * scale;
+}
+
+// stage 1 of the covariance: block b accumulates sum_r c_r c_r^T over its rows (c = x - mean), rows staged
+// through shared memory 32 at a time; thread t owns entries t, t+256, ... of the D x D matrix (D <= 128)
+constexpr int kCovMaxDim = 128;
+__global__ void __launch_bounds__(256) cov_partial_kernel(const double *ens, uint32_t first, uint32_t count, uint32_t dim,
+                                                          uint32_t pitch, const double *mean, double *part)
+{
+    extern __shared__ double rows[];  // [32][dim]
+    constexpr int kPer = (kCovMaxDim * kCovMaxDim + 255) / 256;
+    double acc[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) acc[k] = 0.0;
+    const uint32_t len = dim * dim;
+    for (uint32_t r0 = blockIdx.x * 32u; r0 < count; r0 += gridDim.x * 32u) {
+        const uint32_t nr = count - r0 < 32u ? count - r0 : 32u;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < nr * dim; e += blockDim.x) {
+            const uint32_t r = e / dim, d = e - r * dim;
+            rows[e] = ens[(size_t)(first + r0 + r) * pitch + d] - __ldg(mean + d);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const uint32_t e = threadIdx.x + 256u * (uint32_t)k;
+            if (e < len) {
+                const uint32_t i = e / dim, j = e - i * dim;
+                double s = acc[k];
+                for (uint32_t r = 0; r < nr; ++r) s += rows[r * dim + i] * rows[r * dim + j];
+                acc[k] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const uint32_t e = threadIdx.x + 256u * (uint32_t)k;
+        if (e < len) part[(size_t)blockIdx.x * len + e] = acc[k];
+    }
+}
+
+// out[slot][c] = ens[walker[c]][coord[c]]
+__global__ void trace_kernel(const double *ens, uint32_t pitch, const uint32_t *walker, const uint32_t *coord,
+                             uint32_t ncap, double *out_row)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncap) out_row[c] = ens[(size_t)walker[c] * pitch + coord[c]];
+}
+
+}  // namespace scorus

@@ -315,6 +315,39 @@ class Sampler:
         self._ok(self._lib.scorus_swap_walkers_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0],
                                                     _dp(beta), beta.size))
 
+    # -- periphery: box init, ensemble statistics, chain trace
+    def init_ensemble(self, lo, hi):
+        """get_one_init_realization (src/mcmc/init_ensemble.rs:19-32) for every walker, on the device."""
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.float64), (self.dim,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (self.dim,)))
+        self._ok(self._lib.scorus_init_ensemble(self._ctx, _dp(lo), _dp(hi)))
+
+    def mean(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """linear_space::utils::mean (src/linear_space/utils.rs:4-15) of walkers [first, first+count)."""
+        out = np.empty(self.dim)
+        self._ok(self._lib.scorus_mean(self._ctx, first, self.n - first if count is None else count, _dp(out)))
+        return out
+
+    def cov(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """linear_space::utils::cov (src/linear_space/utils.rs:17-41): biased (/N) covariance."""
+        out = np.empty((self.dim, self.dim))
+        self._ok(self._lib.scorus_cov(self._ctx, first, self.n - first if count is None else count, _dp(out)))
+        return out
+
+    def trace_enable(self, walkers, coords, capacity_steps: int):
+        """Capture ens[walkers[c]][coords[c]] after every step (the examples' recording loops)."""
+        w = np.ascontiguousarray(walkers, dtype=np.uint32)
+        c = np.ascontiguousarray(coords, dtype=np.uint32)
+        self._trace_ncap = w.size
+        self._ok(self._lib.scorus_trace_enable(self._ctx, w.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                               c.ctypes.data_as(C.POINTER(C.c_uint32)), w.size, capacity_steps))
+
+    def trace_download(self, max_steps: int) -> np.ndarray:
+        out = np.empty((max_steps, self._trace_ncap))
+        k = C.c_size_t()
+        self._ok(self._lib.scorus_trace_download(self._ctx, _dp(out), max_steps, C.byref(k)))
+        return out[:min(k.value, max_steps)]
+
     # -- sharding (one process per GPU; scorus_b200/distributed.py drives these)
     def set_shard(self, walker_offset: int, rung_offset: int, n_walkers_global: int):
         self._ok(self._lib.scorus_set_shard(self._ctx, walker_offset, rung_offset, n_walkers_global))

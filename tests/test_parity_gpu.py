@@ -268,3 +268,75 @@ def test_cpp_host_layer_matches_python_mirror(sb, tmp_path):
     for i, t in enumerate(got):
         assert (float(t[2]), float(t[3]), float(t[4])) == (ens[i, 0], ens[i, 19], lp[i])
     assert "C 2" in out and "D 4" in out  # NWalkersIsNotEven, BetaNotInDecrOrd
+
+
+def test_device_init_matches_stream_restatement(sb, oracle):
+    """get_one_init_realization on the device (src/mcmc/init_ensemble.rs:19-32) against the CPU
+    restatement of the device stream; then init_logprob of the result."""
+    n, dim = 1000, 7
+    lo, hi = np.linspace(-1.0, 0.5, dim), np.linspace(1.0, 2.5, dim)
+    with sb.Sampler(sb.Rosenbrock(), n, dim, seed=321) as s:
+        s.init_ensemble(lo, hi)
+        ens, lp = s.download()
+    want = oracle.philox_init_ensemble(321, n, dim, lo, hi)
+    assert np.array_equal(ens, want)
+    assert np.all(ens >= lo) and np.all(ens < hi)
+    assert np.array_equal(lp, oracle.init_logprob(2, [], want))
+    with sb.Sampler(sb.Gaussian(), 4, 2) as s:
+        with pytest.raises(ValueError):
+            s.init_ensemble([0.0, 1.0], [1.0, 1.0])  # empty range: Uniform::new panics in the reference
+
+
+@pytest.mark.parametrize("n,dim,nb", [(256, 4, 4), (4096, 64, 1), (1000, 7, 2), (64, 128, 1)])
+def test_device_mean_and_cov_match_reference_estimators(sb, oracle, n, dim, nb):
+    """linear_space::utils::{mean, cov} (src/linear_space/utils.rs:4-41) per rung, on the device."""
+    g = np.random.default_rng(n + dim)
+    ens = np.ascontiguousarray(g.normal(size=(n, dim)) * g.uniform(0.5, 3.0, dim) + g.normal(size=dim))
+    npb = n // nb
+    with sb.Sampler(sb.Gaussian(), n, dim) as s:
+        s.upload(ens, None)
+        for r in range(nb):
+            sub = np.ascontiguousarray(ens[r * npb:(r + 1) * npb])
+            m, c = s.mean(r * npb, npb), s.cov(r * npb, npb)
+            wm, wc = oracle.mean(sub), oracle.cov(sub)
+            # different summation order than the reference's fold: 1e-12 of the sum of |terms|
+            assert np.all(np.abs(m - wm) <= 1e-12 * np.abs(sub).mean(axis=0) + 1e-300)
+            scale = np.sqrt(np.outer((sub ** 2).mean(axis=0), (sub ** 2).mean(axis=0)))
+            assert np.all(np.abs(c - wc) <= 1e-11 * scale)
+        with pytest.raises(ValueError):
+            s.mean(n - 1, 2)
+
+
+def test_device_trace_equals_per_step_download(sb):
+    """The examples' `results[i].push(ensemble[i*n+0][0])` loop (examples/sample_high_dim.rs:84-86)."""
+    nb, per, dim, steps = 4, 20, 10, 25
+    g = np.random.default_rng(0)
+    ens = np.ascontiguousarray(g.uniform(-1, 1, (nb * per, dim)))
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    walkers, coords = [r * per for r in range(nb)], [0] * nb
+    with sb.Sampler(sb.Gaussian(1.0), nb * per, dim, seed=5) as a, sb.Sampler(sb.Gaussian(1.0), nb * per, dim, seed=5) as b:
+        a.upload(ens, None)
+        b.upload(ens, None)
+        a.trace_enable(walkers, coords, steps)
+        want = []
+        for k in range(steps):
+            if k % 10 == 0:
+                a.swap_walkers(beta)
+                b.swap_walkers(beta)
+            a.sample_pt(2.0, sb.UpdateFlagSpec.OneHotCycle(), beta, 1)
+            b.sample_pt(2.0, sb.UpdateFlagSpec.OneHotCycle(), beta, 1)
+            e, _ = b.download()
+            want.append([e[w, 0] for w in walkers])
+        got = a.trace_download(steps)
+    assert got.shape == (steps, nb) and np.array_equal(got, np.array(want))
+
+
+def test_periphery_mirrors_reference_call_shapes(sb, oracle):
+    """init_ensemble::get_one_init_realization(y1, y2, rng) and linear_space::utils::{mean, cov}(x)."""
+    dev = sb.DeviceRng(seed=77)
+    lo, hi = np.array([0.9, -1.0, 0.0]), np.array([1.1, 1.0, 5.0])
+    rows = np.array([sb.init_ensemble.get_one_init_realization(lo, hi, dev) for _ in range(5)])
+    assert np.array_equal(rows, oracle.philox_init_ensemble(77, 5, 3, lo, hi))   # successive walkers of the stream
+    x = np.ascontiguousarray(np.random.default_rng(3).normal(size=(51, 3)))
+    assert np.allclose(sb.linear_space.mean(x), oracle.mean(x), rtol=1e-13, atol=1e-15)
+    assert np.allclose(sb.linear_space.cov(x), oracle.cov(x), rtol=1e-12, atol=1e-15)
