@@ -56,6 +56,10 @@ SHAPES = [
     (2, [], 64, 300, 2, (0.9, 1.1)),      # dim > 256: the TMA-staged cooperative kernel is the default
     (0, [0.5], 4096, 128, 1, (-1, 1)),    # two chunks per lane in the register kernel
     (3, [10.0], 1024, 200, 1, (-0.5, 0.5)),  # four chunks per lane
+    (0, [0.5], 2, 1, 1, (-1, 1)),         # the smallest legal ensemble: one pair, one coordinate
+    (2, [], 34, 3, 17, (0.9, 1.1)),       # two walkers per rung, a two-walker tail tile
+    (3, [10.0], 66, 1, 1, (-0.5, 0.5)),   # one coordinate (odd dim, padded row), ragged tail
+    (1, [1.5], 4, 2, 2, (-1.6, 1.6)),
 ]
 
 
@@ -340,3 +344,33 @@ def test_periphery_mirrors_reference_call_shapes(sb, oracle):
     x = np.ascontiguousarray(np.random.default_rng(3).normal(size=(51, 3)))
     assert np.allclose(sb.linear_space.mean(x), oracle.mean(x), rtol=1e-13, atol=1e-15)
     assert np.allclose(sb.linear_space.cov(x), oracle.cov(x), rtol=1e-12, atol=1e-15)
+
+
+def test_nan_and_infinite_log_probs_follow_reference_accept_rules(sb, oracle):
+    """SURVEY A.4 on the device: NaN / -inf log-probs in the accept test and in the swap."""
+    kind, params = 1, [1.5]
+    ens = np.array([[0.1], [1.45], [1.6], [1.7], [0.2], [1.4], [1.6], [0.0]])
+    beta = [1.0, 0.5]
+    lp = oracle.init_logprob(kind, params, ens)
+    partner = np.array([1, 0, 3, 2, 5, 4, 7, 6], dtype=np.uint32)
+    z = np.array([1.0, 2.0, 1.0, 1.0, 0.9, 1.0, 0.5, 1.0])
+    u = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1 - 2 ** -53, 0.5])
+    flags = np.ones((8, 1), dtype=np.uint8)
+    want_e, want_lp = ens.copy(), lp.copy()
+    rc, want_acc = oracle.sample_pt_fixed(kind, params, want_e, want_lp, beta, partner, z, flags, u)
+    assert rc == 0 and want_acc.tolist() == [1, 0, 0, 0, 1, 1, 1, 1]
+    for seq in (False, True):
+        with sb.Sampler(sb.BoundedGaussian(1.5), 8, 1, sequential_sum=seq) as s:
+            s.upload(ens, None)
+            acc = s.sample_pt_fixed(beta, partner, z, flags, u)
+            e, l = s.download()
+            assert acc.tolist() == want_acc.tolist() and np.array_equal(e, want_e)
+            assert np.array_equal(l, want_lp, equal_nan=True)
+            # swap: both -inf -> NaN probability -> no swap; finite vs -inf decided by the sign
+            jvec, r = np.array([[0, 1, 2, 3]], dtype=np.uint32), np.array([[0.0, 0.0, 0.999, 0.5]])
+            we, wl = want_e.copy(), want_lp.copy()
+            rc, want_sw = oracle.swap_walkers_fixed(we, wl, beta, jvec, r)
+            sw = s.swap_walkers_fixed(beta, jvec, r)
+            e, l = s.download()
+            assert rc == 0 and np.array_equal(sw, want_sw) and np.array_equal(e, we)
+            assert np.array_equal(l, wl, equal_nan=True)
