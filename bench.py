@@ -329,6 +329,17 @@ def main():
         e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
                "d2h_bytes_per_step": bytes_dir, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": api}
+        if world == 1:
+            # extra, not the headline: a driver that records every 10th iteration (examples/test_emcee.rs:82-84)
+            # makes one host round trip per 10 steps (scorus_sample_pt_host_n)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta, nsteps=10)
+            torch.cuda.synchronize()
+            dt10 = time.perf_counter() - t0
+            e2e["thin10"] = {"value": n * 30 / dt10, "unit": "walker-steps/s", "ms_per_step": 1e3 * dt10 / 30,
+                             "note": "10 steps per host round trip; bytes per step are a tenth of the above"}
 
     if rank != 0:
         if dist:

@@ -151,6 +151,11 @@ int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta_list, size_t n
  * logprob_len is cached_logprob.len() (checked like ensemble_sample.rs:133). */
 int scorus_sample_pt_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
                           double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
+/* The same with nsteps steps between the upload and the download: what a driver that records every
+ * k-th iteration needs (examples/test_emcee.rs:82-84 writes every 10th), one PCIe round trip per k. */
+int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
+                            double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta,
+                            uint64_t nsteps);
 /* swap_walkers on host buffers; a logprob_len mismatch is the reference's silent no-op
  * (src/mcmc/utils.rs:88). */
 int scorus_swap_walkers_host(scorus_ctx *ctx, double *ensemble, double *logprob,

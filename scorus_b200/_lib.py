@@ -69,6 +69,7 @@ def load() -> C.CDLL:
         "scorus_swap_walkers": (ci, [vp, dp, sz]),
         "scorus_swap_walkers_fixed": (ci, [vp, dp, sz, u32p, dp, u8p]),
         "scorus_sample_pt_host": (ci, [vp, dp, dp, sz, dbl, C.POINTER(Ufs), dp, sz]),
+        "scorus_sample_pt_host_n": (ci, [vp, dp, dp, sz, dbl, C.POINTER(Ufs), dp, sz, u64]),
         "scorus_swap_walkers_host": (ci, [vp, dp, dp, sz, dp, sz]),
         "scorus_init_ensemble": (ci, [vp, dp, dp]),
         "scorus_mean": (ci, [vp, sz, sz, dp]),
@@ -108,7 +109,7 @@ EXPORTS = [
     "scorus_check_beta_order", "scorus_ctx_create", "scorus_ctx_destroy", "scorus_last_error",
     "scorus_set_logprob", "scorus_upload", "scorus_download", "scorus_init_logprob", "scorus_sample",
     "scorus_sample_pt", "scorus_sample_pt_fixed", "scorus_draw_z", "scorus_swap_walkers", "scorus_swap_walkers_fixed",
-    "scorus_sample_pt_host", "scorus_swap_walkers_host", "scorus_init_ensemble", "scorus_mean", "scorus_cov",
+    "scorus_sample_pt_host", "scorus_sample_pt_host_n", "scorus_swap_walkers_host", "scorus_init_ensemble", "scorus_mean", "scorus_cov",
     "scorus_trace_enable", "scorus_trace_download", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
     "scorus_sample_pt_p2p_begin", "scorus_sample_pt_p2p_end", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",

@@ -1242,15 +1242,21 @@ extern "C" int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_st
 // ------------------------------------------------------------------------------------------
 // literal drop-ins on host buffers
 // ------------------------------------------------------------------------------------------
-extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
-                                     const scorus_ufs *ufs, const double *beta, size_t nbeta)
+extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                       const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
 {
     if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
     int rc = scorus_check_sample_args(ctx->n, lp_len, nbeta);
     if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
     if ((rc = scorus_upload(ctx, ens, lp))) return rc;
-    if ((rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, 1))) return rc;
+    if ((rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps))) return rc;
     return scorus_download(ctx, ens, lp);
+}
+
+extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                     const scorus_ufs *ufs, const double *beta, size_t nbeta)
+{
+    return scorus_sample_pt_host_n(ctx, ens, lp, lp_len, a, ufs, beta, nbeta, 1);
 }
 
 extern "C" int scorus_swap_walkers_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len,

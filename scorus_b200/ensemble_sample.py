@@ -301,13 +301,14 @@ class Sampler:
             sw.ctypes.data_as(C.POINTER(C.c_uint8))))
         return sw[:jvec.size].reshape(jvec.shape)
 
-    def sample_pt_host(self, ensemble, logprob, a, ufs: UpdateFlagSpec, beta_list):
-        """One reference-shaped call: host buffers in, one step, host buffers out."""
+    def sample_pt_host(self, ensemble, logprob, a, ufs: UpdateFlagSpec, beta_list, nsteps: int = 1):
+        """One reference-shaped call: host buffers in, one step (or nsteps, for drivers that record
+        every k-th iteration), host buffers out."""
         _check_arrays(ensemble, logprob)
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         u, keep = ufs._c(self.n, self.dim)
-        self._ok(self._lib.scorus_sample_pt_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0], a,
-                                                 C.byref(u), _dp(beta), beta.size))
+        self._ok(self._lib.scorus_sample_pt_host_n(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0], a,
+                                                   C.byref(u), _dp(beta), beta.size, nsteps))
 
     def swap_walkers_host(self, ensemble, logprob, beta_list):
         _check_arrays(ensemble, logprob)
