@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--global-every", type=int, default=1,
+                    help="with --matching global/p2p: whole-ensemble matching every k-th step, shard-local in between")
     ap.add_argument("--matching", default="local", choices=["local", "global", "p2p"],
                     help="N>1, single temperature: shard-local matchings (no per-step exchange) or the "
                          "reference's whole-ensemble matching over an NCCL all-gather per step")
@@ -228,7 +230,8 @@ def main():
     beta = betas(nbeta)
     if world > 1:
         from scorus_b200.distributed import ShardedSampler
-        s = ShardedSampler(sb.LogProb(kind, tuple(params)), n, dim, nbeta=nbeta, seed=2024, matching=args.matching)
+        s = ShardedSampler(sb.LogProb(kind, tuple(params)), n, dim, nbeta=nbeta, seed=2024, matching=args.matching,
+                           global_every=args.global_every)
         n_local, nb_local = s.n_local, s.nb_local
         if s.mode == "rungs":
             parallelism = f"rungs->gpus x{world}: no per-step exchange; swap = all-gather(lp) + all-to-all of crossing rows"
@@ -236,6 +239,8 @@ def main():
             parallelism = f"walker shards x{world}, whole-ensemble matching, NCCL all-gather of the ensemble per step"
         elif args.matching == "p2p":
             parallelism = f"walker shards x{world}, whole-ensemble matching, one-sided NVLink reads of remote partners"
+        if s.mode == "walkers" and args.matching != "local" and args.global_every > 1:
+            parallelism += f" every {args.global_every}th step, shard-local matching in between"
         else:
             parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)"
         ens = make_ensemble(n_local, dim, box, 5 + rank, kind)

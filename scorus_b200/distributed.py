@@ -128,7 +128,8 @@ class ShardedSampler:
     """The sharded counterpart of Sampler: same calls, global beta list, local data."""
 
     def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, nbeta: int = 1, seed: int = 0,
-                 matching: str = "global", device: Optional[int] = None, group=None, p2p_swap: bool = True):
+                 matching: str = "global", device: Optional[int] = None, group=None, p2p_swap: bool = True,
+                 global_every: int = 1):
         import torch
         import torch.distributed as dist
         self.dist, self.torch, self.group = dist, torch, group
@@ -140,6 +141,12 @@ class ShardedSampler:
         if matching not in ("global", "p2p", "local"):
             raise ValueError("matching must be 'global', 'p2p' or 'local'")
         self.matching = matching
+        # global_every = k > 1 (matching "global" / "p2p"): only every k-th step uses the whole-ensemble
+        # matching, the steps in between pair inside each shard.  The schedule depends on the
+        # step index only, so every step's matching is still state-independent -- a valid kernel whose
+        # cross-shard mixing costs 1/k of the NVLink traffic.
+        self.global_every = max(1, int(global_every))
+        self._step_index = 0
         dev = torch.cuda.current_device() if device is None else device
         self.device = torch.device("cuda", dev)
         # shard-local matchings are independent ensembles: give each shard its own stream key
@@ -186,18 +193,27 @@ class ShardedSampler:
         if self.matching == "local" or self.world == 1:
             self.sampler.sample_pt(a, ufs, beta, nsteps)
             return
-        if self.matching == "p2p":
-            for _ in range(nsteps):
+        done = 0
+        while done < nsteps:
+            k = self.global_every
+            if k > 1 and self._step_index % k != 0:                  # shard-local steps up to the next global one
+                run = min(nsteps - done, k - self._step_index % k)
+                self.sampler.sample_pt(a, ufs, beta, run)
+                self._step_index += run
+                done += run
+                continue
+            if self.matching == "p2p":
                 self._barrier()                                      # peers have finished their previous step
                 self.sampler.sample_pt_p2p_begin(a, ufs, beta)       # pull remote partners' rows over NVLink
                 self._barrier()                                      # nobody writes before everybody has read
                 self.sampler.sample_pt_p2p_end()                     # fused step, in place
-            return
-        ens_all, lp_all, _ = self._gather_buffers()
-        for _ in range(nsteps):                                      # all-gather + global-matching step
-            self.dist.all_gather_into_tensor(ens_all, self.ens, group=self.group)
-            self.dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
-            self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
+            else:                                                    # all-gather + global-matching step
+                ens_all, lp_all, _ = self._gather_buffers()
+                self.dist.all_gather_into_tensor(ens_all, self.ens, group=self.group)
+                self.dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
+                self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
+            self._step_index += 1
+            done += 1
 
     def _barrier(self):
         """Stream-ordered barrier across ranks (a one-element all-reduce: no host synchronisation)."""

@@ -50,6 +50,25 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
     return bool(flag.item())
 
 
+def run_mixed(world):
+    """Whole-ensemble matching every 5th step, shard-local in between: a different (still valid) kernel,
+    so it is checked statistically: unit Gaussian in, unit Gaussian out, across all shards."""
+    n, dim = 8192 * world, 8
+    rng = np.random.default_rng(7)
+    ens = np.ascontiguousarray(rng.normal(size=(n, dim)) * 3.0)       # over-dispersed start
+    sh = ShardedSampler(sb.Gaussian(0.5), n, dim, nbeta=1, seed=99, matching="p2p", global_every=5)
+    sh.upload(np.ascontiguousarray(ens[sh.w_off:sh.w_off + sh.n_local]), None)
+    sh.sample_pt(2.0, sb.UpdateFlagSpec.Prob(0.5), [1.0], 300)
+    e, lp = sh.download()
+    stat = torch.tensor([e.sum(), (e ** 2).sum(), float(e.size)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(stat)
+    mean, var = (stat[0] / stat[2]).item(), (stat[1] / stat[2]).item()
+    good = abs(mean) < 0.02 and abs(var - 1.0) < 0.03 and np.allclose(lp, -0.5 * (e ** 2).sum(axis=1), rtol=1e-12)
+    if dist.get_rank() == 0:
+        print(f"mixed_p2p_every5: world={world} mean={mean:.4f} var={var:.4f} {'OK' if good else 'MISMATCH'}", flush=True)
+    return good
+
+
 def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -76,6 +95,7 @@ def main():
                    sb.UpdateFlagSpec.Prob(0.5), 10, 0, (0.9, 1.1), matching="p2p")
     ok &= run_case("rastrigin_p2p_matching_small_odd", sb.Rastrigin(), 70 * world, 7, 1,
                    sb.UpdateFlagSpec.Prob(0.2), 10, 0, (-0.5, 0.5), matching="p2p")
+    ok &= run_mixed(world)
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
