@@ -321,18 +321,22 @@ def main():
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
+        acc0 = s.stats()["accepted"]
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             host_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        acc_per_step = (s.stats()["accepted"] - acc0) / args.e2e_steps
         if dist:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         bytes_dir = n_local * dim * 8 + n_local * 8
+        # single-GPU host call on pinned buffers: only accepted walkers are written back (scatter download)
+        d2h = int(acc_per_step * (dim * 8 + 8)) if world == 1 and os.environ.get("SCORUS_SCATTER_DOWNLOAD", "1") != "0" else bytes_dir
         e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
-               "d2h_bytes_per_step": bytes_dir, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": api}
         if world == 1:
             # extra, not the headline: a driver that records every 10th iteration (examples/test_emcee.rs:82-84)

@@ -64,6 +64,8 @@ struct scorus_ctx {
     double *d_z = nullptr, *d_u = nullptr;
     uint8_t *d_flags = nullptr; size_t flags_cap = 0;
     uint8_t *d_acc = nullptr;
+    uint8_t *d_dirty = nullptr;     // host-buffer call: walkers accepted since the upload
+    bool track_dirty = false;
     uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
     double *d_r = nullptr;      size_t r_cap = 0;
     uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
@@ -215,7 +217,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count};
+                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_dirty};
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (auto &e : ctx->beta_cache)
@@ -535,6 +537,7 @@ static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta
     p->debug_identity = env_int("SCORUS_DEBUG_IDENTITY", 0) ? 1u : 0u;
     p->w_off = (uint32_t)ctx->w_off; p->rung_off = ctx->rung_off; p->n_global = ctx->n_global;
     p->src_ens = ctx->d_ens; p->src_lp = ctx->d_lp; p->n_dev = nullptr; p->w_lo = 0; p->w_hi = (uint32_t)ctx->n;
+    p->dirty = ctx->track_dirty ? ctx->d_dirty : nullptr;
     return SCORUS_OK;
 }
 
@@ -1249,8 +1252,32 @@ extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp,
     int rc = scorus_check_sample_args(ctx->n, lp_len, nbeta);
     if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
     if ((rc = scorus_upload(ctx, ens, lp))) return rc;
-    if ((rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps))) return rc;
-    return scorus_download(ctx, ens, lp);
+    // Pinned (device-mapped) host buffers: after the steps only the accepted walkers differ from what
+    // was just uploaded, so only those rows travel back, written in place by scatter_download_kernel.
+    // Pageable buffers take the full copy.
+    cudaPointerAttributes ae{}, al{};
+    const bool pinned = env_int("SCORUS_SCATTER_DOWNLOAD", 1) &&
+                        cudaPointerGetAttributes(&ae, ens) == cudaSuccess && ae.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&al, lp) == cudaSuccess && al.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {
+        if ((rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps))) return rc;
+        return scorus_download(ctx, ens, lp);
+    }
+    if (!ctx->d_dirty) CU(cudaMalloc(&ctx->d_dirty, ctx->n));
+    CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, ctx->stream));
+    ctx->track_dirty = true;
+    rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps);
+    ctx->track_dirty = false;
+    if (rc) return rc;
+    scatter_download_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, ctx->stream>>>(
+        ctx->d_ens, ctx->d_lp, ctx->d_dirty, (uint32_t)ctx->n, ctx->dim, ctx->pitch, (double *)ae.devicePointer,
+        (double *)al.devicePointer);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "scatter download launch: %s", cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
 }
 
 extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,

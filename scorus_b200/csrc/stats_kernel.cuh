@@ -92,6 +92,30 @@ __global__ void __launch_bounds__(256) cov_partial_kernel(const double *ens, uin
     }
 }
 
+// Host-buffer call, download side: only walkers accepted since the upload changed, so only their rows
+// and log-probs are written -- straight into the caller's pinned (device-mapped) host buffers at their
+// final place.  One warp per walker; host rows are dim doubles apart (no padding).
+__global__ void __launch_bounds__(256) scatter_download_kernel(const double *ens, const double *lp, const uint8_t *dirty,
+                                                               uint32_t n, uint32_t dim, uint32_t pitch, double *host_ens,
+                                                               double *host_lp)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = warp; w < n; w += nwarps) {
+        if (!dirty[w]) continue;
+        const double *src = ens + (size_t)w * pitch;
+        double *dst = host_ens + (size_t)w * dim;
+        if ((dim & 1u) == 0) {
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 *d2 = reinterpret_cast<double2 *>(dst);
+            for (uint32_t c = lane; c < dim / 2; c += 32) d2[c] = s2[c];
+        } else {
+            for (uint32_t c = lane; c < dim; c += 32) dst[c] = src[c];
+        }
+        if (lane == 0) host_lp[w] = lp[w];
+    }
+}
+
 // out[slot][c] = ens[walker[c]][coord[c]]
 __global__ void trace_kernel(const double *ens, uint32_t pitch, const uint32_t *walker, const uint32_t *coord,
                              uint32_t ncap, double *out_row)

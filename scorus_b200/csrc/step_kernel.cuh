@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(512, 1) step_seq_kernel(const StepParams p)
             fence_proxy_async();  // my generic-proxy writes of the row -> visible to the TMA store
             bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
             p.lp[w] = lp_new;
+            if (p.dirty) p.dirty[w] = 1;
             ++n_acc;
         }
         bulk_commit();

@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(Plugin::kMaxWarps * 32, 1) step_reg_kernel(con
         if (accept) {
             bulk_store(p.ens + (size_t)(w - p.w_lo) * p.pitch, smem_u32(own_b), p.row_bytes);
             p.lp[w - p.w_lo] = lp_new;
+            if (p.dirty) p.dirty[w - p.w_lo] = 1;
             ++n_acc;
         }
         bulk_commit();

@@ -20,6 +20,7 @@ struct StepParams {
     const double *u_in;
     const uint8_t *flags_in;  // [n][flag_len] bytes or nullptr
     uint8_t *accepted_out;    // [n] or nullptr
+    uint8_t *dirty;           // [n] or nullptr: set to 1 when a walker is accepted (never cleared by the kernel)
     unsigned long long *stats;  // [0] accepted, [1] proposed
     uint64_t seed, step, onehot;
     uint64_t flag_thr;      // Bernoulli threshold on flag_bits random bits

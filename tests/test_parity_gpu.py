@@ -374,3 +374,28 @@ def test_nan_and_infinite_log_probs_follow_reference_accept_rules(sb, oracle):
             e, l = s.download()
             assert rc == 0 and np.array_equal(sw, want_sw) and np.array_equal(e, we)
             assert np.array_equal(l, wl, equal_nan=True)
+
+
+@pytest.mark.parametrize("dim", [6, 7])
+def test_host_call_pinned_and_pageable_buffers_agree(sb, dim):
+    """scorus_sample_pt_host writes only accepted walkers back into pinned host buffers
+    (scatter download); pageable buffers take the full copy.  Same result either way."""
+    n, nb = 512, 2
+    g = np.random.default_rng(dim)
+    ens0 = np.ascontiguousarray(g.uniform(-1, 1, (n, dim)))
+    beta = [1.0, 0.5]
+    out = []
+    for pinned in (False, True):
+        with sb.Sampler(sb.Gaussian(0.5), n, dim, seed=3) as s:
+            ens = sb.pinned_empty((n, dim)) if pinned else np.empty((n, dim))
+            lp = sb.pinned_empty((n,)) if pinned else np.empty(n)
+            ens[:] = ens0
+            s.upload(ens, None)
+            s.download(ens, lp)
+            for k in range(4):
+                s.sample_pt_host(ens, lp, 2.0, sb.UpdateFlagSpec.Prob(0.5), beta, nsteps=1 + k % 2)
+            dev_e, dev_lp = s.download()
+            assert np.array_equal(ens, dev_e) and np.array_equal(lp, dev_lp)   # host copy == device copy
+            out.append((ens.copy(), lp.copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert not np.array_equal(out[0][0], ens0)
