@@ -40,6 +40,11 @@ cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const G
     }
     const uint32_t nvec = p.pitch / 2;
     if (g.kernel == KERNEL_REG) {
+        // rows of 5 or 6 double2 (D = 9..12): two lanes x three chunks wastes 1/6 of the lanes, eight lanes
+        // x one chunk would waste 3/8 -- and these targets (10-D Rastrigin) are bound by fp64 arithmetic
+        if (nvec == 5 || nvec == 6)
+            return p.stage_ens ? launch_kernel(step_reg_kernel<Plugin, 2, 3, true>, p, g, st)
+                               : launch_kernel(step_reg_kernel<Plugin, 2, 3>, p, g, st);
         if (p.stage_ens) {  // one-sided multi-GPU mode
             if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4, true>, p, g, st);
             if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2, true>, p, g, st);
