@@ -140,7 +140,7 @@ def cpu_reference_leg(wl, steps, warmup, sample_walkers=None, target_seconds=12.
     desc, kind, n, dim, nbeta, ufs, prob, box, swap_every = WORKLOADS[wl]
     params = workload_params(kind, dim)
     if sample_walkers is None:
-        sample_walkers = min(n, 1 << 17)
+        sample_walkers = min(n, int(os.environ.get("SCORUS_BENCH_CPU_WALKERS", 1 << 17)))
     npb = n // nbeta
     if nbeta > 1:
         rungs = max(1, min(nbeta, sample_walkers // npb))
