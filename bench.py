@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--n-walkers", type=int, default=0, help="experiments only: override the workload's ensemble size")
     ap.add_argument("--global-every", type=int, default=1,
                     help="with --matching global/p2p: whole-ensemble matching every k-th step, shard-local in between")
     ap.add_argument("--matching", default="local", choices=["local", "global", "p2p"],
@@ -191,6 +192,9 @@ def main():
     desc, kind, n, dim, nbeta, ufs, prob, box, swap_every = WORKLOADS[args.workload]
     if args.ufs:
         ufs = args.ufs
+    if args.n_walkers:
+        n = args.n_walkers
+        desc += f" [n_walkers overridden to {n}]"
     W = max(args.warmup, 3)
 
     if args.impl == "reference":

@@ -15,6 +15,7 @@ struct Geometry {
     uint32_t row_bytes, row_stride, flag_words, stages, warps, grid;
     size_t smem;
     int kernel;  // KERNEL_*
+    int pdl;     // launch with programmatic stream serialization (register kernel only)
 };
 
 #define SCORUS_DECLARE_LAUNCHERS(NAME)                                                                   \

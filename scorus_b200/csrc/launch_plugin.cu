@@ -18,6 +18,21 @@ static cudaError_t launch_kernel(K kernel, const StepParams &p, const Geometry &
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
+    if (g.pdl) {
+        // programmatic dependent launch: this step's blocks are scheduled while the previous launch
+        // drains and block in griddepcontrol.wait before touching its results (step_reg_kernel.cuh)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(g.grid);
+        cfg.blockDim = dim3(g.warps * 32);
+        cfg.dynamicSmemBytes = g.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    }
     kernel<<<g.grid, g.warps * 32, g.smem, st>>>(p);
     return cudaGetLastError();
 }

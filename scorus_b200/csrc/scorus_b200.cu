@@ -65,6 +65,8 @@ struct scorus_ctx {
     uint8_t *d_flags = nullptr; size_t flags_cap = 0;
     uint8_t *d_acc = nullptr;
     uint8_t *d_dirty = nullptr;     // host-buffer call: walkers accepted since the upload
+    unsigned long long *d_tile_counter = nullptr;  // dynamic tile scheduling of the register kernel
+    unsigned long long tile_ticket = 0;
     bool track_dirty = false;
     uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
     double *d_r = nullptr;      size_t r_cap = 0;
@@ -204,6 +206,8 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     if ((e = cudaMalloc(&ctx->d_ens, ens_bytes)) != cudaSuccess) return bail(e, "cudaMalloc ensemble");
     if ((e = cudaMalloc(&ctx->d_lp, ctx->n * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logprob");
     if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc stats");
+    if ((e = cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tile counter");
+    cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(ctx->d_ens, 0, ens_bytes, ctx->stream);
     cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
@@ -217,7 +221,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_dirty};
+                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_dirty, ctx->d_tile_counter};
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (auto &e : ctx->beta_cache)
@@ -411,6 +415,7 @@ static int step_geometry(scorus_ctx *ctx, Geometry *g)
     uint32_t grid = (ntiles + g->warps - 1) / g->warps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     g->grid = grid;
+    g->pdl = g->kernel == KERNEL_REG && env_int("SCORUS_PDL", 1);
     return SCORUS_OK;
 }
 
@@ -509,6 +514,18 @@ static int upload_beta(scorus_ctx *ctx, const double *beta, size_t nbeta)
     slot->used = ++ctx->beta_clock;
     ctx->d_beta = slot->dev;
     return SCORUS_OK;
+}
+
+// standard (single-GPU layout) launches of the register kernel claim tiles dynamically; the counter
+// advances by exactly ntiles per launch (see tile_common.cuh), so the base is known on the host
+static void stamp_tiles(scorus_ctx *ctx, StepParams *p, const Geometry &g)
+{
+    p->tile_counter = nullptr;
+    if (g.kernel == KERNEL_REG && !p->n_dev && env_int("SCORUS_DYNAMIC_TILES", 1)) {
+        p->tile_counter = ctx->d_tile_counter;
+        p->tile_base = ctx->tile_ticket;
+        ctx->tile_ticket += p->ntiles;
+    }
 }
 
 static uint32_t flag_bits_for(double prob)
@@ -610,6 +627,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
             ++ctx->launches;
             p.order = ctx->d_order;
         }
+        stamp_tiles(ctx, &p, g);
         cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
         ++ctx->launches;
@@ -671,6 +689,7 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
     p.order = ctx->d_order; p.z_in = ctx->d_z; p.u_in = ctx->d_u; p.flags_in = ctx->d_flags;
     p.flag_len = (uint32_t)flag_len; p.flag_kind = SCORUS_UFS_MASK; p.accepted_out = ctx->d_acc;
     p.step = ctx->step;
+    stamp_tiles(ctx, &p, g);
     cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;

@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(Plugin::kMaxWarps * 32, 1) step_reg_kernel(con
     const bool all_flags = p.flag_kind == 1u;
     unsigned long long n_acc = 0;
 
+    grid_dep_launch();  // the next step's blocks may be scheduled as soon as an SM frees up
+
     Plugin plug;
     plug.init(p.pparams, p.nparams, p.dim);
 
@@ -103,6 +105,10 @@ __global__ void __launch_bounds__(Plugin::kMaxWarps * 32, 1) step_reg_kernel(con
             }
         }
     };
+
+    // Everything above touches launch parameters and constants only.  From here on the kernel reads what
+    // earlier launches wrote (order / pair lists, the ensemble, the log-probs): wait for them.
+    grid_dep_wait();
 
     // matching positions to process: N, or (global-matching mode) the length of the local pair list
     const uint32_t npos = p.n_dev ? __ldg(p.n_dev) : p.n;
@@ -151,8 +157,15 @@ __global__ void __launch_bounds__(Plugin::kMaxWarps * 32, 1) step_reg_kernel(con
         const double beta = __ldg(p.beta + (act ? w / p.npb : 0u));
         __syncwarp();  // flag words visible to the whole warp
 
-        // ids of the next tile (its first block is prefetched during this tile's last block)
-        const uint32_t tile_n = tile + nwarps;
+        // ids of the next tile (its first block is prefetched during this tile's last block): static
+        // stride, or -- single-GPU mode -- the next unclaimed tile, which trims the last, ragged round
+        uint32_t tile_n = tile + nwarps;
+        if (p.tile_counter) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(p.tile_counter, 1ull) - p.tile_base;
+            t = __shfl_sync(0xffffffffu, t, 0);
+            tile_n = t + nwarps > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)(t + nwarps);
+        }
         uint32_t w_n = p.w_lo;
         bool act_n = false;
         double lp_n = 0.0;

@@ -47,6 +47,11 @@ struct StepParams {
     const double *stage_ens;
     const double *stage_lp;
     uint32_t w_lo, w_hi;
+    // Dynamic tile scheduling (register kernel, single-GPU mode): after its first tile a warp takes
+    // the next unclaimed one, tile = nwarps + (atomicAdd(tile_counter, 1) - tile_base).  Every launch
+    // advances the counter by exactly ntiles, so the host knows the next base without a reset.
+    unsigned long long *tile_counter;
+    unsigned long long tile_base;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
@@ -104,6 +109,11 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with programmatic stream serialization
+// may start while its predecessor drains; grid_dep_wait blocks until the predecessor has completed and
+// its writes are visible, grid_dep_launch lets the successor's blocks be scheduled early.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
