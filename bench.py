@@ -238,15 +238,16 @@ def main():
                            global_every=args.global_every)
         n_local, nb_local = s.n_local, s.nb_local
         if s.mode == "rungs":
-            parallelism = f"rungs->gpus x{world}: no per-step exchange; swap = all-gather(lp) + all-to-all of crossing rows"
+            parallelism = (f"rungs->gpus x{world}: no per-step exchange; swap = all-gather(lp) + "
+                           + ("one-sided NVLink pull" if s.p2p else "all-to-all") + " of crossing rows")
         elif args.matching == "global":
             parallelism = f"walker shards x{world}, whole-ensemble matching, NCCL all-gather of the ensemble per step"
         elif args.matching == "p2p":
             parallelism = f"walker shards x{world}, whole-ensemble matching, one-sided NVLink reads of remote partners"
-        if s.mode == "walkers" and args.matching != "local" and args.global_every > 1:
-            parallelism += f" every {args.global_every}th step, shard-local matching in between"
         else:
             parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)"
+        if s.mode == "walkers" and args.matching != "local" and args.global_every > 1:
+            parallelism += f" every {args.global_every}th step, shard-local matching in between"
         ens = make_ensemble(n_local, dim, box, 5 + rank, kind)
         s.upload(ens, None)
         s.sync()
