@@ -381,7 +381,8 @@ static int step_geometry(scorus_ctx *ctx, Geometry *g)
         // it, and with the carve-out at its maximum the kernel ran 12 % slower (profiles/r1_notes.md)
         const size_t per_warp = tile + flag_bytes;
         const size_t l1_keep = (size_t)env_int("SCORUS_L1_KB", 32) * 1024u;
-        uint32_t w = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN ? 8 : 14;  // Plugin::kMaxWarps (logprob.cuh)
+        // mirrors reg_kernel_max_warps (step_reg_kernel.cuh): dense plugin 8, rows of <= 8 double2 16, else 14
+        uint32_t w = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN ? 8 : (ctx->pitch / 2 <= 8 ? 16 : 14);
         while (w >= 1 && w * per_warp > budget) --w;
         while (w > 8 && w * per_warp + l1_keep > budget) --w;
         if (w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
