@@ -31,6 +31,7 @@ namespace scorus {
 struct LpGaussian {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 1;
     double c, acc;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t)
@@ -56,6 +57,7 @@ struct LpGaussian {
 struct LpBoundedGaussian {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;  // [0] the sum, [1] number of coordinates beyond the limit
     double limit, acc;
     bool dead;
@@ -87,6 +89,7 @@ struct LpBoundedGaussian {
 struct LpRosenbrock {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = true;   // term(x[d+1], x[d+2]) couples neighbouring chunks
     static constexpr int kAcc = 1;
     double prev, acc;
     __device__ __forceinline__ void init(const double *, uint32_t, uint32_t)
@@ -122,6 +125,7 @@ struct LpRosenbrock {
 struct LpRastrigin {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 1;
     double a, acc, base;
     static __device__ __forceinline__ double term(double a, double y)
@@ -152,6 +156,7 @@ struct LpRastrigin {
 struct LpBimodal2d {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;  // [0] carries x0, [1] carries x1
     double lo0, hi0, lo1, hi1, split, mu_a, sg_a, mu_b, sg_b, x0, x1;
     uint32_t dim;
@@ -197,6 +202,7 @@ struct LpBimodal2d {
 struct LpStep2d {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;
     double x0, x1;
     uint32_t dim;
@@ -230,6 +236,7 @@ struct LpStep2d {
 struct LpMixture {
     static constexpr bool kNeedsRow = false;
     static constexpr int kMaxWarps = 14;
+    static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;
     const double *m;
     double s1, s2, q1, q2;
@@ -305,6 +312,7 @@ struct LpCorrGaussian {
     static constexpr bool kNeedsRow = true;
     static constexpr bool kTile = true;
     static constexpr int kMaxWarps = 8;  // register kernel: 256 threads -> up to 255 registers for the DMMA accumulators
+    static constexpr bool kNeedsNext = false;
     static constexpr int kAcc = 1;
     const double *mu, *L;
     uint32_t dim;

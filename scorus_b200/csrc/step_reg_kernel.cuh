@@ -241,12 +241,15 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
                     for (int it = 0; it < ITERS; ++it) {
                         const uint32_t c = (uint32_t)it * G + j;
                         const uint32_t d = 2u * c;
-                        double nba = __shfl_down_sync(0xffffffffu, ya[it].x, 1, G);
-                        double nbb = __shfl_down_sync(0xffffffffu, yb[it].x, 1, G);
-                        if (ITERS > 1 && it + 1 < ITERS) {  // last lane of the group: next trip, lane 0
-                            const double wa0 = __shfl_sync(0xffffffffu, ya[it + 1 < ITERS ? it + 1 : it].x, 0, G);
-                            const double wb0 = __shfl_sync(0xffffffffu, yb[it + 1 < ITERS ? it + 1 : it].x, 0, G);
-                            if (j == G - 1) { nba = wa0; nbb = wb0; }
+                        double nba = 0.0, nbb = 0.0;
+                        if constexpr (Plugin::kNeedsNext) {
+                            nba = __shfl_down_sync(0xffffffffu, ya[it].x, 1, G);
+                            nbb = __shfl_down_sync(0xffffffffu, yb[it].x, 1, G);
+                            if (ITERS > 1 && it + 1 < ITERS) {  // last lane of the group: next trip, lane 0
+                                const double wa0 = __shfl_sync(0xffffffffu, ya[it + 1 < ITERS ? it + 1 : it].x, 0, G);
+                                const double wb0 = __shfl_sync(0xffffffffu, yb[it + 1 < ITERS ? it + 1 : it].x, 0, G);
+                                if (j == G - 1) { nba = wa0; nbb = wb0; }
+                            }
                         }
                         if (c < nvec) {
                             const bool has1 = d + 1u < p.dim, hasnb = d + 2u < p.dim;
