@@ -618,7 +618,15 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
     default: return fail(ctx, SCORUS_ERR_INVALID_ARG, "unknown UpdateFlagSpec kind %d", ufs->kind);
     }
 
-    const bool exact = p.npb <= kExactShuffleMax;
+    bool exact = p.npb <= kExactShuffleMax;
+    // one-block ensembles: the register kernel shuffles the rungs itself (step_reg_kernel.cuh)
+    const size_t fused_bytes = ctx->n * (sizeof(uint64_t) + sizeof(uint32_t));
+    if (exact && g.kernel == KERNEL_REG && g.grid == 1 && g.smem + fused_bytes <= (size_t)ctx->smem_optin &&
+        env_int("SCORUS_FUSED_ORDER", 1)) {
+        p.fused_order = 1;
+        g.smem += fused_bytes;
+        exact = false;
+    }
     if (exact && !ctx->d_order) CU(cudaMalloc(&ctx->d_order, ctx->n * sizeof(uint32_t)));
     for (uint64_t s = 0; s < nsteps; ++s) {
         p.step = ctx->step;

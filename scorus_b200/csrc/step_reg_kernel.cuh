@@ -78,6 +78,32 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
 
     grid_dep_launch();  // the next step's blocks may be scheduled as soon as an SM frees up
 
+    // One-block ensembles: exact uniform shuffle of every rung right here (rank of 64-bit Philox keys,
+    // the same keys and tie-break as exact_order_kernel), saving a launch per step.
+    const uint32_t *sm_order = nullptr;
+    if (p.fused_order) {
+        unsigned char *extra = smem + (size_t)p.warps * warp_bytes;
+        uint64_t *keys = reinterpret_cast<uint64_t *>(extra);
+        uint32_t *ord = reinterpret_cast<uint32_t *>(extra + (size_t)p.n * sizeof(uint64_t));
+        for (uint32_t i = threadIdx.x; i < p.n; i += blockDim.x) {
+            const U4 o = draw(p.seed, p.step, ST_PERM_KEY, p.w_off + i, 0);
+            keys[i] = ((uint64_t)o.y << 32) | o.x;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < p.n; i += blockDim.x) {
+            const uint32_t r = i / p.npb, base = r * p.npb;
+            const uint64_t ki = keys[i];
+            uint32_t rank = 0;
+            for (uint32_t jj = 0; jj < p.npb; ++jj) {
+                const uint64_t kj = keys[base + jj];
+                rank += (kj < ki) || (kj == ki && base + jj < i);
+            }
+            ord[base + rank] = i;
+        }
+        __syncthreads();
+        sm_order = ord;
+    }
+
     Plugin plug;
     plug.init(p.pparams, p.nparams, p.dim);
 
@@ -85,6 +111,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
     uint32_t key_rung = 0xFFFFFFFFu;
     BijKeys K;
     auto walker_of = [&](uint32_t pos) -> uint32_t {
+        if (sm_order) return sm_order[pos];
         if (p.order) return __ldg(p.order + pos);
         if (p.debug_identity) return pos;
         const uint32_t r = pos / p.npb;

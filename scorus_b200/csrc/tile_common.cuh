@@ -52,6 +52,9 @@ struct StepParams {
     // advances the counter by exactly ntiles, so the host knows the next base without a reset.
     unsigned long long *tile_counter;
     unsigned long long tile_base;
+    // One-block ensembles (register kernel, grid == 1): the exact shuffle of every rung is computed by the
+    // step kernel itself in shared memory instead of a separate exact_order_kernel launch.
+    uint32_t fused_order;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
