@@ -176,6 +176,30 @@ int scorus_cov(scorus_ctx *ctx, size_t first, size_t count, double *cov_out);
 int scorus_trace_enable(scorus_ctx *ctx, const uint32_t *walkers, const uint32_t *coords, size_t ncapture,
                         size_t capacity_steps);
 int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_steps, size_t *nrecorded);
+/* capture after every `every`-th step only (thinned output, examples/test_emcee.rs:82-84); default 1 */
+int scorus_trace_stride(scorus_ctx *ctx, uint64_t every);
+
+/* ---- chain statistics on the device: what the example drivers compute from
+ * per-step downloads (examples/sample_bimodal.rs:137-161, examples/sample_high_dim.rs:84-108), without
+ * the downloads ----
+ * Acceptance per rung and exchange acceptance per ladder stage since creation: accepted / proposed have
+ * nrungs entries (indexed like beta_list), swapped / swap_proposed nrungs-1 (entry k = exchanges between
+ * rung k and rung k+1).  Any output may be NULL.  Synchronises. */
+int scorus_get_rung_stats(scorus_ctx *ctx, size_t nrungs, uint64_t *accepted, uint64_t *proposed,
+                          uint64_t *swapped, uint64_t *swap_proposed);
+/* Running moments of each of nrungs equal rungs, accumulated over the walkers of the rung after every
+ * `every`-th step from now on: mean and (with_cov, dim <= 128) the biased covariance as
+ * src/linear_space/utils.rs:4-41 define them, over steps x walkers.  nrungs == 0 disables.
+ * scorus_moments_download reports nsamples = accumulations x walkers per rung; cov_out may be NULL. */
+int scorus_moments_enable(scorus_ctx *ctx, size_t nrungs, uint64_t every, int with_cov);
+int scorus_moments_download(scorus_ctx *ctx, size_t rung, double *mean_out, double *cov_out, uint64_t *nsamples);
+/* Integrated autocorrelation time of every captured series (scorus_trace_enable), from the rows recorded so
+ * far (the buffer is not rewound): C(k) = sum_{t<T-k} (x_t - m)(x_{t+k} - m) / T for k <= max_lag (0 = T-1),
+ * tau(M) = 1 + 2 sum_{k=1..M} C(k)/C(0) with Sokal's window, M = the first lag with M >= c_window * tau(M)
+ * (max_lag if none: check window_out).  tau_out / window_out / mean_out / var_out (= C(0)) have ncapture
+ * entries; all but tau_out may be NULL. */
+int scorus_trace_iat(scorus_ctx *ctx, double c_window, size_t max_lag, double *tau_out, uint32_t *window_out,
+                     double *mean_out, double *var_out);
 
 /* ---- sharding: one process per GPU ----
  * scorus_set_shard tells a context which slice of the whole ensemble it holds: its walker i is

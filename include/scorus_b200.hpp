@@ -174,6 +174,42 @@ public:
         check(scorus_draw_z(ctx_, a, 1, &z), ctx_);
         return z;
     }
+    // chain statistics on the device (what the example drivers compute from per-step downloads)
+    struct RungStats { std::vector<uint64_t> accepted, proposed, swapped, swap_proposed; };
+    RungStats rung_stats(size_t nrungs)
+    {
+        RungStats r{std::vector<uint64_t>(nrungs), std::vector<uint64_t>(nrungs), std::vector<uint64_t>(nrungs),
+                    std::vector<uint64_t>(nrungs)};
+        check(scorus_get_rung_stats(ctx_, nrungs, r.accepted.data(), r.proposed.data(), r.swapped.data(), r.swap_proposed.data()), ctx_);
+        r.swapped.resize(nrungs - 1);
+        r.swap_proposed.resize(nrungs - 1);
+        return r;
+    }
+    void moments_enable(size_t nrungs, uint64_t every = 1, bool with_cov = true)
+    {
+        check(scorus_moments_enable(ctx_, nrungs, every, with_cov ? 1 : 0), ctx_);
+    }
+    uint64_t moments(size_t rung, std::vector<double> &mean, std::vector<double> *cov = nullptr)
+    {
+        uint64_t m = 0;
+        mean.resize(dim_);
+        if (cov) cov->resize(dim_ * dim_);
+        check(scorus_moments_download(ctx_, rung, mean.data(), cov ? cov->data() : nullptr, &m), ctx_);
+        return m;
+    }
+    void trace_enable(const std::vector<uint32_t> &walkers, const std::vector<uint32_t> &coords, size_t capacity_steps, uint64_t every = 1)
+    {
+        check(scorus_trace_enable(ctx_, walkers.data(), coords.data(), walkers.size(), capacity_steps), ctx_);
+        check(scorus_trace_stride(ctx_, every), ctx_);
+        ncapture_ = walkers.size();
+    }
+    std::vector<double> trace_iat(double c_window = 5.0, size_t max_lag = 0, std::vector<uint32_t> *window = nullptr)
+    {
+        std::vector<double> tau(ncapture_);
+        if (window) window->resize(ncapture_);
+        check(scorus_trace_iat(ctx_, c_window, max_lag, tau.data(), window ? window->data() : nullptr, nullptr, nullptr), ctx_);
+        return tau;
+    }
     void sync() { check(scorus_sync(ctx_), ctx_); }
     scorus_ctx *raw() { return ctx_; }
     size_t n_walkers() const { return n_; }
@@ -181,7 +217,7 @@ public:
 
 private:
     scorus_ctx *ctx_ = nullptr;
-    size_t n_, dim_;
+    size_t n_, dim_, ncapture_ = 0;
 };
 
 // Stands in for `rng: &mut U`: the seed of the device streams.  Caches one Sampler per ensemble shape.

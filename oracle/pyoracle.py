@@ -27,7 +27,7 @@ ERR_LENGTH_MISMATCH, ERR_INVALID_ARG, ERR_NPHI_ZERO = 5, 6, 7
 
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so with the committed Makefile (gcc, no FMA contraction)."""
-    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "scorus_oracle.h", "Makefile"]
+    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "chain_stats.c", "scorus_oracle.h", "Makefile"]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
@@ -102,6 +102,10 @@ def lib() -> C.CDLL:
                                             sz, ci]
         L.orc_max_threads.restype = ci
         L.orc_max_threads.argtypes = []
+        L.orc_trace_iat.restype = None
+        L.orc_trace_iat.argtypes = [dp, sz, sz, dbl, sz, dp, u32p, dp, dp, dp]
+        L.orc_running_moments.restype = None
+        L.orc_running_moments.argtypes = [dp, sz, sz, sz, dp, dp]
         _lib = L
     return _lib
 
@@ -257,6 +261,28 @@ def cov(ens):
     out = np.empty((dim, dim))
     lib().orc_cov(_dp(np.ascontiguousarray(ens)), n, dim, _dp(out))
     return out
+
+
+def trace_iat(trace, c_window=5.0, max_lag=0):
+    """(tau, window, mean, var) of every column of trace[T][ncap]; bit-identical to scorus_trace_iat."""
+    trace = np.ascontiguousarray(trace, dtype=np.float64)
+    T, ncap = trace.shape
+    tau, mean_, var = np.empty(ncap), np.empty(ncap), np.empty(ncap)
+    window = np.empty(ncap, dtype=np.uint32)
+    scratch = np.empty(T)
+    lib().orc_trace_iat(_dp(trace), T, ncap, float(c_window), int(max_lag), _dp(tau), _u32p(window), _dp(mean_),
+                        _dp(var), _dp(scratch))
+    return tau, window, mean_, var
+
+
+def running_moments(samples, want_cov=True):
+    """mean / biased cov of samples[nsnap][npb][dim] over all nsnap * npb rows (one rung)."""
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    nsnap, npb, dim = samples.shape
+    mean_ = np.empty(dim)
+    cov_ = np.empty((dim, dim)) if want_cov else None
+    lib().orc_running_moments(_dp(samples), nsnap, npb, dim, _dp(mean_), _dp(cov_) if want_cov else None)
+    return mean_, cov_
 
 
 def philox4x32_10(ctr, key):

@@ -76,6 +76,11 @@ def load() -> C.CDLL:
         "scorus_cov": (ci, [vp, sz, sz, dp]),
         "scorus_trace_enable": (ci, [vp, u32p, u32p, sz, sz]),
         "scorus_trace_download": (ci, [vp, dp, sz, C.POINTER(sz)]),
+        "scorus_trace_stride": (ci, [vp, u64]),
+        "scorus_get_rung_stats": (ci, [vp, sz, u64p, u64p, u64p, u64p]),
+        "scorus_moments_enable": (ci, [vp, sz, u64, ci]),
+        "scorus_moments_download": (ci, [vp, sz, dp, dp, u64p]),
+        "scorus_trace_iat": (ci, [vp, dbl, sz, dp, u32p, dp, dp]),
         "scorus_set_shard": (ci, [vp, u64, C.c_uint32, u64]),
         "scorus_sample_pt_global": (ci, [vp, dbl, C.POINTER(Ufs), dp, sz, vp, vp]),
         "scorus_swap_plan_device": (ci, [vp, dp, sz, vp, vp]),
@@ -110,7 +115,8 @@ EXPORTS = [
     "scorus_set_logprob", "scorus_upload", "scorus_download", "scorus_init_logprob", "scorus_sample",
     "scorus_sample_pt", "scorus_sample_pt_fixed", "scorus_draw_z", "scorus_swap_walkers", "scorus_swap_walkers_fixed",
     "scorus_sample_pt_host", "scorus_sample_pt_host_n", "scorus_swap_walkers_host", "scorus_init_ensemble", "scorus_mean", "scorus_cov",
-    "scorus_trace_enable", "scorus_trace_download", "scorus_set_shard", "scorus_sample_pt_global",
+    "scorus_trace_enable", "scorus_trace_download", "scorus_trace_stride", "scorus_get_rung_stats",
+    "scorus_moments_enable", "scorus_moments_download", "scorus_trace_iat", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
     "scorus_sample_pt_p2p_begin", "scorus_sample_pt_p2p_end", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",

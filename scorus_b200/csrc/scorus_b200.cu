@@ -5,6 +5,7 @@
 // swap_kernel.cuh.  There is deliberately no CPU path in this file.
 #include "../../include/scorus_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -55,6 +56,15 @@ struct scorus_ctx {
     uint32_t *d_tr_walker = nullptr, *d_tr_coord = nullptr;
     double *d_trace = nullptr;
     size_t tr_ncap = 0, tr_capacity = 0, tr_count = 0;
+    uint64_t tr_every = 1, tr_tick = 0;                     // capture after every tr_every-th step
+    // chain statistics: per-rung accepted moves [0, rung_cap) and per-stage accepted exchanges [rung_cap, 2 rung_cap)
+    unsigned long long *d_rung_stats = nullptr; size_t rung_cap = 0;
+    std::vector<uint64_t> rung_proposed, stage_proposed;
+    // running per-rung moments: sums of (x - shift) and of its outer products, taken every mom_every-th step
+    double *d_mom = nullptr;   // [shift: rungs*dim][s1: rungs*dim][s2: rungs*dim*dim]
+    double *d_iat = nullptr; size_t iat_cap = 0;
+    uint32_t mom_rungs = 0; bool mom_cov = false;
+    uint64_t mom_every = 1, mom_tick = 0, mom_count = 0;
     bool p2p_pending = false;                                // scorus_sample_pt_p2p_begin without _end
     StepParams p2p_params;
     Geometry p2p_geom;
@@ -232,7 +242,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
             if (ctx->peer_lp[q]) cudaIpcCloseMemHandle(ctx->peer_lp[q]);
         }
     void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_stage, ctx->d_stage_lp, ctx->d_part, ctx->d_stat,
-                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace};
+                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace, ctx->d_rung_stats, ctx->d_mom, ctx->d_iat};
     for (void *b : p2p)
         if (b) cudaFree(b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -539,6 +549,46 @@ static uint32_t flag_bits_for(double prob)
     return 32;
 }
 
+// chain statistics: device counters per rung (accepted moves) and per exchange stage (accepted swaps),
+// grown on demand; the proposal counts are known on the host
+static int ensure_rung_stats(scorus_ctx *ctx, size_t nbeta)
+{
+    if (ctx->rung_cap >= nbeta) return SCORUS_OK;
+    size_t cap = ctx->rung_cap ? ctx->rung_cap : 64;
+    while (cap < nbeta) cap *= 2;
+    unsigned long long *nb = nullptr;
+    CU(cudaMalloc(&nb, 2 * cap * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(nb, 0, 2 * cap * sizeof(unsigned long long), ctx->stream));
+    if (ctx->d_rung_stats) {
+        CU(cudaMemcpyAsync(nb, ctx->d_rung_stats, ctx->rung_cap * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(nb + cap, ctx->d_rung_stats + ctx->rung_cap, ctx->rung_cap * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_rung_stats);
+    }
+    ctx->d_rung_stats = nb;
+    ctx->rung_cap = cap;
+    return SCORUS_OK;
+}
+
+// walkers [w_lo, w_hi) of an ensemble with npb walkers per rung were proposed `steps` times
+static void count_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb, uint64_t w_lo, uint64_t w_hi, uint64_t steps)
+{
+    ctx->proposed += (w_hi - w_lo) * steps;
+    if (ctx->rung_proposed.size() < nbeta) ctx->rung_proposed.resize(nbeta, 0);
+    for (uint64_t r = w_lo / npb; r < nbeta && r * npb < w_hi; ++r) {
+        const uint64_t lo = std::max(w_lo, r * npb), hi = std::min(w_hi, (r + 1) * npb);
+        ctx->rung_proposed[r] += (hi - lo) * steps;
+    }
+}
+
+static void count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb)
+{
+    ctx->swap_proposed += (nbeta - 1) * npb;
+    if (ctx->stage_proposed.size() < nbeta - 1) ctx->stage_proposed.resize(nbeta - 1, 0);
+    for (size_t k = 0; k + 1 < nbeta; ++k) ctx->stage_proposed[k] += npb;
+}
+
 static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta)
 {
     int rc = step_geometry(ctx, g);
@@ -556,18 +606,32 @@ static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta
     p->w_off = (uint32_t)ctx->w_off; p->rung_off = ctx->rung_off; p->n_global = ctx->n_global;
     p->src_ens = ctx->d_ens; p->src_lp = ctx->d_lp; p->n_dev = nullptr; p->w_lo = 0; p->w_hi = (uint32_t)ctx->n;
     p->dirty = ctx->track_dirty ? ctx->d_dirty : nullptr;
+    if (nbeta > 1) {
+        if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
+        p->rung_acc = ctx->d_rung_stats;
+    }
     return SCORUS_OK;
 }
 
-// chain capture after a step (scorus_trace_enable); silently stops when the buffer is full
-static void record_trace(scorus_ctx *ctx)
+static int accumulate_moments(scorus_ctx *ctx);
+
+// after every step: chain capture (scorus_trace_enable; silently stops when the buffer is full) and the
+// running moments (scorus_moments_enable)
+static int after_step(scorus_ctx *ctx)
 {
-    if (!ctx->tr_ncap || ctx->tr_count >= ctx->tr_capacity) return;
-    trace_kernel<<<(unsigned)((ctx->tr_ncap + 127) / 128), 128, 0, ctx->stream>>>(
-        ctx->d_ens, ctx->pitch, ctx->d_tr_walker, ctx->d_tr_coord, (uint32_t)ctx->tr_ncap,
-        ctx->d_trace + ctx->tr_count * ctx->tr_ncap);
-    ++ctx->launches;
-    ++ctx->tr_count;
+    if (ctx->tr_ncap && ctx->tr_count < ctx->tr_capacity && ++ctx->tr_tick >= ctx->tr_every) {
+        ctx->tr_tick = 0;
+        trace_kernel<<<(unsigned)((ctx->tr_ncap + 127) / 128), 128, 0, ctx->stream>>>(
+            ctx->d_ens, ctx->pitch, ctx->d_tr_walker, ctx->d_tr_coord, (uint32_t)ctx->tr_ncap,
+            ctx->d_trace + ctx->tr_count * ctx->tr_ncap);
+        ++ctx->launches;
+        ++ctx->tr_count;
+    }
+    if (ctx->mom_rungs && ++ctx->mom_tick >= ctx->mom_every) {
+        ctx->mom_tick = 0;
+        return accumulate_moments(ctx);
+    }
+    return SCORUS_OK;
 }
 
 extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
@@ -641,10 +705,10 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
         ++ctx->launches;
         ++ctx->step;
-        ctx->proposed += ctx->n;
         if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
-        record_trace(ctx);
+        if ((rc = after_step(ctx))) return rc;
     }
+    count_proposed(ctx, nbeta, p.npb, 0, ctx->n, nsteps);
     return SCORUS_OK;
 }
 
@@ -702,7 +766,7 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
     cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
-    ctx->proposed += n;
+    count_proposed(ctx, nbeta, p.npb, 0, n, 1);
     if (accepted_out) CU(cudaMemcpyAsync(accepted_out, ctx->d_acc, n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));  // `order` and the caller's arrays are released here
     return SCORUS_OK;
@@ -760,6 +824,8 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
     if (!ctx->d_src) CU(cudaMalloc(&ctx->d_src, n * sizeof(uint32_t)));
     if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, n * (size_t)ctx->pitch * sizeof(double)));
     sp.lp = ctx->d_lp; sp.beta = ctx->d_beta; sp.src = ctx->d_src; sp.stats = ctx->d_stats;
+    if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
+    sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
     sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
     sp.npb = (uint32_t)npb; sp.nbeta = (uint32_t)nbeta; sp.bij_bits = bij_bits((uint32_t)npb);
 
@@ -806,7 +872,7 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap launch: %s", cudaGetErrorString(e));
     ++ctx->swap_call;
-    ctx->swap_proposed += m;
+    count_swap_proposed(ctx, nbeta, npb);
     if (swapped_out) CU(cudaMemcpyAsync(swapped_out, ctx->d_swapped, m, cudaMemcpyDeviceToHost, ctx->stream));
     if (jvec || swapped_out) CU(cudaStreamSynchronize(ctx->stream));
     return SCORUS_OK;
@@ -915,9 +981,9 @@ extern "C" int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_u
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     ++ctx->step;
-    ctx->proposed += ctx->n;
+    count_proposed(ctx, nbeta, p.npb, p.w_lo, p.w_hi, 1);
     if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ng) % ctx->dim;
-    return SCORUS_OK;
+    return after_step(ctx);
 }
 
 extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size_t nbeta, double *lp_all,
@@ -935,6 +1001,8 @@ extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size
     SwapParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.lp = lp_all; sp.beta = ctx->d_beta; sp.src = src_all; sp.stats = ctx->d_stats;
+    if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
+    sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
     sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
     sp.npb = (uint32_t)npb; sp.nbeta = (uint32_t)nbeta; sp.bij_bits = bij_bits((uint32_t)npb);
     if (nbeta > 1 && npb <= kExactShuffleMax) {
@@ -950,7 +1018,7 @@ extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap plan launch: %s", cudaGetErrorString(e));
     ++ctx->swap_call;
-    ctx->swap_proposed += (nbeta - 1) * npb;  // whole ladder, as counted by the chain kernel
+    count_swap_proposed(ctx, nbeta, npb);  // whole ladder, as counted by the chain kernel
     return SCORUS_OK;
 }
 
@@ -1102,9 +1170,9 @@ extern "C" int scorus_sample_pt_p2p_end(scorus_ctx *ctx)
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     ++ctx->step;
-    ctx->proposed += ctx->n;
+    count_proposed(ctx, ctx->p2p_params.nbeta, ctx->p2p_params.npb, ctx->p2p_params.w_lo, ctx->p2p_params.w_hi, 1);
     if (ctx->p2p_params.flag_kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
-    return SCORUS_OK;
+    return after_step(ctx);
 }
 
 // rows of a cross-rank ladder swap, pulled one-sidedly: scratch[slot] <- (peer holding src)[src] for
@@ -1198,8 +1266,8 @@ static int stats_impl(scorus_ctx *ctx, size_t first, size_t count, double *mean_
     if (rc) return rc;
     if ((rc = ensure(ctx, (void **)&ctx->d_stat, &ctx->stat_cap, ((size_t)dim + len) * sizeof(double)))) return rc;
     double *d_mean = ctx->d_stat, *d_cov = ctx->d_stat + dim;
-    colsum_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ens, (uint32_t)first, (uint32_t)count, dim, ctx->pitch, ctx->d_part);
-    reduce_partials_kernel<<<(dim + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_part, blocks, dim, 1.0 / (double)count, 0, d_mean);
+    colsum_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ens, (uint32_t)first, (uint32_t)count, dim, ctx->pitch, nullptr, ctx->d_part);
+    reduce_partials_kernel<<<(dim + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_part, blocks, dim, 1.0 / (double)count, 0, 0, d_mean);
     ctx->launches += 2;
     if (mean_out) CU(cudaMemcpyAsync(mean_out, d_mean, dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (cov_out) {
@@ -1210,7 +1278,7 @@ static int stats_impl(scorus_ctx *ctx, size_t first, size_t count, double *mean_
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "cov smem: %s", cudaGetErrorString(e));
         cov_partial_kernel<<<cblocks, 256, smem, ctx->stream>>>(ctx->d_ens, (uint32_t)first, (uint32_t)count, dim, ctx->pitch,
                                                                d_mean, ctx->d_part);
-        reduce_partials_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_part, cblocks, len, (double)count, 1, d_cov);
+        reduce_partials_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_part, cblocks, len, (double)count, 1, 0, d_cov);
         ctx->launches += 2;
         CU(cudaMemcpyAsync(cov_out, d_cov, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -1244,6 +1312,7 @@ extern "C" int scorus_trace_enable(scorus_ctx *ctx, const uint32_t *walkers, con
     ctx->d_tr_walker = ctx->d_tr_coord = nullptr;
     ctx->d_trace = nullptr;
     ctx->tr_ncap = ctx->tr_capacity = ctx->tr_count = 0;
+    ctx->tr_tick = 0;
     if (ncapture == 0 || capacity_steps == 0) return SCORUS_OK;  // disabled
     if (!walkers || !coords) return SCORUS_ERR_INVALID_ARG;
     for (size_t c = 0; c < ncapture; ++c)
@@ -1267,6 +1336,165 @@ extern "C" int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_st
     CU(cudaStreamSynchronize(ctx->stream));
     *nrecorded = ctx->tr_count;
     ctx->tr_count = 0;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_trace_stride(scorus_ctx *ctx, uint64_t every)
+{
+    if (!ctx || every == 0) return SCORUS_ERR_INVALID_ARG;
+    ctx->tr_every = every;
+    ctx->tr_tick = 0;
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// chain statistics on the device
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_get_rung_stats(scorus_ctx *ctx, size_t nrungs, uint64_t *accepted, uint64_t *proposed,
+                                     uint64_t *swapped, uint64_t *swap_proposed)
+{
+    if (!ctx || nrungs == 0) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    std::vector<unsigned long long> h(2 * ctx->rung_cap + 4, 0);
+    CU(cudaMemcpyAsync(h.data(), ctx->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->rung_cap)
+        CU(cudaMemcpyAsync(h.data() + 4, ctx->d_rung_stats, 2 * ctx->rung_cap * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t r = 0; r < nrungs; ++r) {
+        if (accepted) accepted[r] = r < ctx->rung_cap ? h[4 + r] : 0;
+        if (proposed) proposed[r] = r < ctx->rung_proposed.size() ? ctx->rung_proposed[r] : 0;
+        if (r + 1 < nrungs) {
+            if (swapped) swapped[r] = r < ctx->rung_cap ? h[4 + ctx->rung_cap + r] : 0;
+            if (swap_proposed) swap_proposed[r] = r < ctx->stage_proposed.size() ? ctx->stage_proposed[r] : 0;
+        }
+    }
+    // single-rung calls are counted in the totals only (rung 0 of a one-rung ensemble)
+    if (accepted) {
+        unsigned long long in_rungs = 0;
+        for (size_t r = 0; r < ctx->rung_cap; ++r) in_rungs += h[4 + r];
+        accepted[0] += h[0] - in_rungs;
+    }
+    return SCORUS_OK;
+}
+
+static uint32_t moment_blocks(const scorus_ctx *ctx, uint64_t npb, uint32_t rungs, uint32_t rows_per_block)
+{
+    uint64_t b = ((uint64_t)ctx->num_sms * 4u + rungs - 1) / rungs;
+    const uint64_t need = (npb + rows_per_block - 1) / rows_per_block;
+    if (b > need) b = need;
+    return (uint32_t)(b ? b : 1);
+}
+
+extern "C" int scorus_moments_enable(scorus_ctx *ctx, size_t nrungs, uint64_t every, int with_cov)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_mom) { cudaFree(ctx->d_mom); ctx->d_mom = nullptr; }
+    ctx->mom_rungs = 0; ctx->mom_count = 0; ctx->mom_tick = 0;
+    if (nrungs == 0) return SCORUS_OK;  // disabled
+    if (every == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "every must be >= 1");
+    if (ctx->n % nrungs) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
+    const size_t dim = ctx->dim;
+    if (with_cov && dim > (size_t)kCovMaxDim) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "cov supports dim <= %d", kCovMaxDim);
+    const size_t words = nrungs * (2 * dim + (with_cov ? dim * dim : 0));
+    CU(cudaMalloc(&ctx->d_mom, words * sizeof(double)));
+    CU(cudaMemsetAsync(ctx->d_mom, 0, words * sizeof(double), ctx->stream));
+    ctx->mom_rungs = (uint32_t)nrungs;
+    ctx->mom_every = every;
+    ctx->mom_cov = with_cov != 0;
+    return SCORUS_OK;
+}
+
+// S1 += sum (x - shift), S2 += sum (x - shift)(x - shift)^T per rung; the shift is the rung mean at the
+// first accumulation, so that the final cov = S2/M - (S1/M)(S1/M)^T does not cancel
+static int accumulate_moments(scorus_ctx *ctx)
+{
+    const uint32_t R = ctx->mom_rungs, dim = ctx->dim, len = dim * dim;
+    const uint64_t npb = ctx->n / R;
+    double *shift = ctx->d_mom, *s1 = shift + (size_t)R * dim, *s2 = s1 + (size_t)R * dim;
+    const uint32_t bx = moment_blocks(ctx, npb, R, 1), cbx = moment_blocks(ctx, npb, R, 32);
+    int rc = ensure(ctx, (void **)&ctx->d_part, &ctx->part_cap,
+                    (size_t)R * std::max((size_t)bx * dim, ctx->mom_cov ? (size_t)cbx * len : 0) * sizeof(double));
+    if (rc) return rc;
+    if (ctx->mom_count == 0) {
+        colsum_partial_kernel<<<dim3(bx, R), 256, 0, ctx->stream>>>(ctx->d_ens, 0u, (uint32_t)npb, dim, ctx->pitch, nullptr, ctx->d_part);
+        reduce_partials_kernel<<<dim3((dim + 255) / 256, R), 256, 0, ctx->stream>>>(ctx->d_part, bx, dim, 1.0 / (double)npb, 0, 0, shift);
+        ctx->launches += 2;
+    }
+    colsum_partial_kernel<<<dim3(bx, R), 256, 0, ctx->stream>>>(ctx->d_ens, 0u, (uint32_t)npb, dim, ctx->pitch, shift, ctx->d_part);
+    reduce_partials_kernel<<<dim3((dim + 255) / 256, R), 256, 0, ctx->stream>>>(ctx->d_part, bx, dim, 1.0, 0, 1, s1);
+    ctx->launches += 2;
+    if (ctx->mom_cov) {
+        const size_t smem = 32u * (size_t)dim * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(cov_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "cov smem: %s", cudaGetErrorString(e));
+        cov_partial_kernel<<<dim3(cbx, R), 256, smem, ctx->stream>>>(ctx->d_ens, 0u, (uint32_t)npb, dim, ctx->pitch, shift, ctx->d_part);
+        reduce_partials_kernel<<<dim3((len + 255) / 256, R), 256, 0, ctx->stream>>>(ctx->d_part, cbx, len, 1.0, 0, 1, s2);
+        ctx->launches += 2;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "moments launch: %s", cudaGetErrorString(e));
+    ++ctx->mom_count;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_moments_download(scorus_ctx *ctx, size_t rung, double *mean_out, double *cov_out, uint64_t *nsamples)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx->mom_rungs) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_moments_enable first");
+    if (rung >= ctx->mom_rungs) return fail(ctx, SCORUS_ERR_INVALID_ARG, "rung %zu of %u", rung, ctx->mom_rungs);
+    if (cov_out && !ctx->mom_cov) return fail(ctx, SCORUS_ERR_INVALID_ARG, "moments were enabled without the covariance");
+    cudaSetDevice(ctx->device);
+    const size_t R = ctx->mom_rungs, dim = ctx->dim, len = dim * dim;
+    const uint64_t m = ctx->mom_count * (ctx->n / R);
+    if (nsamples) *nsamples = m;
+    if (m == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "no step has been accumulated yet");
+    std::vector<double> shift(dim), s1(dim), s2(cov_out ? len : 0);
+    const double *d_shift = ctx->d_mom, *d_s1 = d_shift + R * dim, *d_s2 = d_s1 + R * dim;
+    CU(cudaMemcpyAsync(shift.data(), d_shift + rung * dim, dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(s1.data(), d_s1 + rung * dim, dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cov_out) CU(cudaMemcpyAsync(s2.data(), d_s2 + rung * len, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t d = 0; d < dim; ++d) s1[d] /= (double)m;
+    if (mean_out)
+        for (size_t d = 0; d < dim; ++d) mean_out[d] = shift[d] + s1[d];
+    if (cov_out)
+        for (size_t i = 0; i < dim; ++i)
+            for (size_t j = 0; j < dim; ++j) cov_out[i * dim + j] = s2[i * dim + j] / (double)m - s1[i] * s1[j];
+    return SCORUS_OK;
+}
+
+// integrated autocorrelation time of every captured series, from the rows recorded so far (not rewound)
+extern "C" int scorus_trace_iat(scorus_ctx *ctx, double c_window, size_t max_lag, double *tau_out, uint32_t *window_out,
+                                double *mean_out, double *var_out)
+{
+    if (!ctx || !tau_out) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx->tr_ncap) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_trace_enable first");
+    const size_t T = ctx->tr_count, C = ctx->tr_ncap;
+    if (T < 2) return fail(ctx, SCORUS_ERR_INVALID_ARG, "need at least two recorded steps");
+    if (!(c_window > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "window factor must be > 0");
+    const size_t L = max_lag == 0 || max_lag > T - 1 ? T - 1 : max_lag;
+    cudaSetDevice(ctx->device);
+    // [xc: C*T][acov: C*(L+1)][mean: C][tau: C][window: C (u32)]
+    const size_t words = C * T + C * (L + 1) + 3 * C;
+    int rc = ensure(ctx, (void **)&ctx->d_iat, &ctx->iat_cap, words * sizeof(double));
+    if (rc) return rc;
+    double *xc = ctx->d_iat, *acov = xc + C * T, *mean = acov + C * (L + 1), *tau = mean + C;
+    uint32_t *window = reinterpret_cast<uint32_t *>(tau + C);
+    iat_center_kernel<<<(unsigned)C, 256, 0, ctx->stream>>>(ctx->d_trace, (uint32_t)C, (uint32_t)T, xc, mean);
+    iat_autocov_kernel<<<dim3((unsigned)((L + 128) / 128), (unsigned)C), 128, 0, ctx->stream>>>(xc, (uint32_t)T, (uint32_t)L, acov);
+    iat_window_kernel<<<(unsigned)((C + 63) / 64), 64, 0, ctx->stream>>>(acov, (uint32_t)C, (uint32_t)L, c_window, tau, window);
+    ctx->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "iat launch: %s", cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(tau_out, tau, C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (window_out) CU(cudaMemcpyAsync(window_out, window, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mean_out) CU(cudaMemcpyAsync(mean_out, mean, C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_out) CU(cudaMemcpy2DAsync(var_out, sizeof(double), acov, (L + 1) * sizeof(double), sizeof(double), C,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return SCORUS_OK;
 }
 

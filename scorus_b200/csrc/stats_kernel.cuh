@@ -32,30 +32,46 @@ __global__ void __launch_bounds__(256) init_ensemble_kernel(double *ens, uint32_
     }
 }
 
-// stage 1 of the column sums: block b sums rows b, b+grid, ... of [first, first+count) -> part[b][dim]
+// stage 1 of the column sums: block (b, g) sums rows b, b+grid, ... of group g = [first + g*count, +count)
+// -> part[g][b][dim].  A group is a rung (running moments) or the caller's range (gridDim.y == 1).  With
+// `shift` (one row of dim per group) the terms are x - shift.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const double *ens, uint32_t first, uint32_t count,
-                                                             uint32_t dim, uint32_t pitch, double *part)
+                                                             uint32_t dim, uint32_t pitch, const double *shift,
+                                                             double *part)
 {
+    const uint32_t g = blockIdx.y;
+    const size_t base = (size_t)first + (size_t)g * count;
     for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
+        const double c = shift ? __ldg(shift + (size_t)g * dim + d) : 0.0;
         double s = 0.0;
-        for (uint32_t r = blockIdx.x; r < count; r += gridDim.x) s += ens[(size_t)(first + r) * pitch + d];
-        part[(size_t)blockIdx.x * dim + d] = s;
+        if (shift) {
+            for (uint32_t r = blockIdx.x; r < count; r += gridDim.x) s += ens[(base + r) * pitch + d] - c;
+        } else {
+            for (uint32_t r = blockIdx.x; r < count; r += gridDim.x) s += ens[(base + r) * pitch + d];
+        }
+        part[((size_t)g * gridDim.x + blockIdx.x) * dim + d] = s;
     }
 }
 
-// stage 2: fixed-order sum over the partials, then scale (mean: * (1/N) as utils.rs:14; cov: / N as :38)
+// stage 2: fixed-order sum over the partials of group blockIdx.y, then scale (mean: * (1/N) as utils.rs:14;
+// cov: / N as :38); accumulate != 0 adds the unscaled sum to out (running moments)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *part, uint32_t nparts, uint32_t len,
-                                                              double scale, int divide, double *out)
+                                                              double scale, int divide, int accumulate, double *out)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= len) return;
+    const uint32_t g = blockIdx.y;
+    part += (size_t)g * nparts * len;
+    out += (size_t)g * len;
     double s = 0.0;
     for (uint32_t b = 0; b < nparts; ++b) s += part[(size_t)b * len + e];
-    out[e] = divide ? s / scale : s * scale;
+    if (accumulate) out[e] += s;
+    else out[e] = divide ? s / scale : s * scale;
 }
 
 // stage 1 of the covariance: block b accumulates sum_r c_r c_r^T over its rows (c = x - mean), rows staged
-// through shared memory 32 at a time; thread t owns entries t, t+256, ... of the D x D matrix (D <= 128)
+// through shared memory 32 at a time; thread t owns entries t, t+256, ... of the D x D matrix (D <= 128);
+// blockIdx.y = group as above (its rows, its `mean` row, its partials)
 constexpr int kCovMaxDim = 128;
 __global__ void __launch_bounds__(256) cov_partial_kernel(const double *ens, uint32_t first, uint32_t count, uint32_t dim,
                                                           uint32_t pitch, const double *mean, double *part)
@@ -66,6 +82,9 @@ __global__ void __launch_bounds__(256) cov_partial_kernel(const double *ens, uin
 #pragma unroll
     for (int k = 0; k < kPer; ++k) acc[k] = 0.0;
     const uint32_t len = dim * dim;
+    first += blockIdx.y * count;
+    mean += (size_t)blockIdx.y * dim;
+    part += (size_t)blockIdx.y * gridDim.x * len;
     for (uint32_t r0 = blockIdx.x * 32u; r0 < count; r0 += gridDim.x * 32u) {
         const uint32_t nr = count - r0 < 32u ? count - r0 : 32u;
         __syncthreads();
@@ -122,6 +141,57 @@ __global__ void trace_kernel(const double *ens, uint32_t pitch, const uint32_t *
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ncap) out_row[c] = ens[(size_t)walker[c] * pitch + coord[c]];
+}
+
+// ---- integrated autocorrelation time of the captured chains ----
+// trace[t][c], t < T.  Per series c: mean (256 strided partial sums, combined in index order), centred copy
+// xc[c][t], autocovariance C(k) = sum_{t < T-k} xc[t] xc[t+k] / T for k <= L (sequential sums), then Sokal's
+// window: tau(M) = 1 + 2 sum_{k=1..M} C(k)/C(0), M = the first lag with M >= c_win * tau(M) (L if none).
+__global__ void __launch_bounds__(256) iat_center_kernel(const double *trace, uint32_t ncap, uint32_t T, double *xc,
+                                                         double *mean_out)
+{
+    __shared__ double part[256];
+    const uint32_t c = blockIdx.x;
+    double s = 0.0;
+    for (uint32_t t = threadIdx.x; t < T; t += 256u) s += trace[(size_t)t * ncap + c];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < 256; ++k) tot += part[k];
+        part[0] = tot / (double)T;
+        mean_out[c] = part[0];
+    }
+    __syncthreads();
+    const double mu = part[0];
+    for (uint32_t t = threadIdx.x; t < T; t += 256u) xc[(size_t)c * T + t] = trace[(size_t)t * ncap + c] - mu;
+}
+
+__global__ void __launch_bounds__(128) iat_autocov_kernel(const double *xc, uint32_t T, uint32_t L, double *acov)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (k > L) return;
+    const double *x = xc + (size_t)c * T;
+    double s = 0.0;
+    for (uint32_t t = 0; t + k < T; ++t) s += x[t] * x[t + k];
+    acov[(size_t)c * (L + 1u) + k] = s / (double)T;
+}
+
+__global__ void iat_window_kernel(const double *acov, uint32_t ncap, uint32_t L, double c_win, double *tau_out,
+                                  uint32_t *window_out)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncap) return;
+    const double *a = acov + (size_t)c * (L + 1u);
+    const double c0 = a[0];
+    double tau = 1.0;
+    uint32_t m = L;
+    for (uint32_t k = 1; k <= L; ++k) {
+        tau += 2.0 * (a[k] / c0);
+        if ((double)k >= c_win * tau) { m = k; break; }
+    }
+    tau_out[c] = tau;
+    window_out[c] = m;
 }
 
 }  // namespace scorus

@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(512, 1) step_coop_kernel(const StepParams p)
         }
         bulk_commit();
         if (p.accepted_out && act) p.accepted_out[w] = accept ? 1 : 0;
+        if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
     }
 
     bulk_wait_all();

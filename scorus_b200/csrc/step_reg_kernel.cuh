@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
         }
         bulk_commit();
         if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0;
+        if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
 
         if (tile_n >= ntiles) break;
         tile = tile_n;

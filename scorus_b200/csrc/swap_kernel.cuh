@@ -74,6 +74,7 @@ struct SwapParams {
     uint32_t *src;         // [n] out: original slot of the walker that ends in each slot
     uint8_t *swapped_out;  // [(nbeta-1)][npb] indexed by cold slot, or nullptr
     unsigned long long *stats;  // [2] swapped, [3] swap_proposed
+    unsigned long long *stage_swapped;  // [nbeta-1] accepted exchanges between rung k and k+1, or nullptr
     uint64_t seed, swap_call;
     uint32_t npb, nbeta, bij_bits;
 };
@@ -122,6 +123,13 @@ __global__ void __launch_bounds__(128) swap_chain_kernel(const SwapParams p)
                 carry_lp = lp_cold;
             }
             if (p.swapped_out) p.swapped_out[(size_t)s * npb + j2] = sw ? 1 : 0;
+            if (p.stage_swapped) {
+                // every active lane of the warp runs the same B-1 stages: one atomic per warp per stage
+                const unsigned live = __activemask();
+                const unsigned m = __ballot_sync(live, sw);
+                if ((threadIdx.x & 31u) == (uint32_t)(__ffs(live) - 1) && m)
+                    atomicAdd(p.stage_swapped + (i - 1), (unsigned long long)__popc(m));
+            }
             a = j2;
         }
         p.src[a] = carry_src;

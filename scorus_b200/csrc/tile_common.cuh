@@ -55,6 +55,9 @@ struct StepParams {
     // One-block ensembles (register kernel, grid == 1): the exact shuffle of every rung is computed by the
     // step kernel itself in shared memory instead of a separate exact_order_kernel launch.
     uint32_t fused_order;
+    // Chain statistics: per-rung acceptance counts, indexed like beta; nullptr for
+    // single-rung calls, whose count is stats[0].
+    unsigned long long *rung_acc;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
@@ -217,6 +220,20 @@ __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, u
     case 8: return gen_flags_prob<8>(p, w, flagw, lane, act);
     case 16: return gen_flags_prob<16>(p, w, flagw, lane, act);
     default: return gen_flags_prob<32>(p, w, flagw, lane, act);
+    }
+}
+
+// per-rung acceptance counts: one atomic per tile when the tile lies inside one rung (the usual case),
+// one per accepted walker for a tile that straddles a rung boundary.  All 32 lanes call this.
+__device__ __forceinline__ void count_rung_accepts(unsigned long long *rung_acc, uint32_t rung, bool act, bool accept,
+                                                   uint32_t lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, accept);
+    const uint32_t r0 = __shfl_sync(0xffffffffu, rung, 0);
+    if (__all_sync(0xffffffffu, !act || rung == r0)) {
+        if (lane == 0 && m) atomicAdd(rung_acc + r0, (unsigned long long)__popc(m));
+    } else if (accept) {
+        atomicAdd(rung_acc + rung, 1ull);
     }
 }
 

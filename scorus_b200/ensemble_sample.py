@@ -349,6 +349,46 @@ class Sampler:
         self._ok(self._lib.scorus_trace_download(self._ctx, _dp(out), max_steps, C.byref(k)))
         return out[:min(k.value, max_steps)]
 
+    def trace_stride(self, every: int):
+        """Capture after every `every`-th step only (examples/test_emcee.rs:82-84 keeps every 10th)."""
+        self._ok(self._lib.scorus_trace_stride(self._ctx, every))
+
+    # -- chain statistics on the device (SURVEY.md 8(f) rank 1)
+    def rung_stats(self, nrungs: int):
+        """Accepted / proposed moves per rung and accepted / proposed exchanges per ladder stage (entry k =
+        rung k <-> rung k+1) since the sampler was created."""
+        acc, prop = np.zeros(nrungs, dtype=np.uint64), np.zeros(nrungs, dtype=np.uint64)
+        sw, swp = np.zeros(max(nrungs - 1, 1), dtype=np.uint64), np.zeros(max(nrungs - 1, 1), dtype=np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        self._ok(self._lib.scorus_get_rung_stats(self._ctx, nrungs, acc.ctypes.data_as(u64p), prop.ctypes.data_as(u64p),
+                                                 sw.ctypes.data_as(u64p), swp.ctypes.data_as(u64p)))
+        return dict(accepted=acc, proposed=prop, swapped=sw[:nrungs - 1], swap_proposed=swp[:nrungs - 1])
+
+    def moments_enable(self, nrungs: int, every: int = 1, with_cov: bool = True):
+        """Accumulate per-rung mean / covariance (src/linear_space/utils.rs:4-41, over steps x walkers) on the
+        device after every `every`-th step from now on; nrungs = 0 stops."""
+        self._ok(self._lib.scorus_moments_enable(self._ctx, nrungs, every, 1 if with_cov else 0))
+        self._moments_cov = bool(with_cov)
+
+    def moments(self, rung: int = 0):
+        """(mean, cov or None, nsamples) of one rung from the running sums."""
+        mean = np.empty(self.dim)
+        cov = np.empty((self.dim, self.dim)) if getattr(self, "_moments_cov", False) else None
+        m = C.c_uint64()
+        self._ok(self._lib.scorus_moments_download(self._ctx, rung, _dp(mean), _dp(cov) if cov is not None else None,
+                                                   C.byref(m)))
+        return mean, cov, m.value
+
+    def trace_iat(self, c_window: float = 5.0, max_lag: int = 0):
+        """Integrated autocorrelation time of every captured series (Sokal window M >= c_window * tau):
+        dict(tau, window, mean, var), one entry per captured (walker, coordinate)."""
+        k = self._trace_ncap
+        tau, mean, var = np.empty(k), np.empty(k), np.empty(k)
+        window = np.empty(k, dtype=np.uint32)
+        self._ok(self._lib.scorus_trace_iat(self._ctx, c_window, max_lag, _dp(tau),
+                                            window.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(mean), _dp(var)))
+        return dict(tau=tau, window=window, mean=mean, var=var)
+
     # -- sharding (one process per GPU; scorus_b200/distributed.py drives these)
     def set_shard(self, walker_offset: int, rung_offset: int, n_walkers_global: int):
         self._ok(self._lib.scorus_set_shard(self._ctx, walker_offset, rung_offset, n_walkers_global))
