@@ -71,6 +71,39 @@ extern "C" {
                                  a: f64, ufs: *const scorus_ufs, beta_list: *const f64, nbeta: usize) -> c_int;
     pub fn scorus_swap_walkers_host(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64,
                                     logprob_len: usize, beta_list: *const f64, nbeta: usize) -> c_int;
+    pub fn scorus_sample_pt_host_n(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64, logprob_len: usize,
+                                   a: f64, ufs: *const scorus_ufs, beta_list: *const f64, nbeta: usize, nsteps: u64) -> c_int;
+    /// get_one_init_realization, src/mcmc/init_ensemble.rs:19-32, for every walker
+    pub fn scorus_init_ensemble(ctx: *mut scorus_ctx, lo: *const f64, hi: *const f64) -> c_int;
+    /// mean / cov, src/linear_space/utils.rs:4-15, 17-41
+    pub fn scorus_mean(ctx: *mut scorus_ctx, first: usize, count: usize, mean_out: *mut f64) -> c_int;
+    pub fn scorus_cov(ctx: *mut scorus_ctx, first: usize, count: usize, cov_out: *mut f64) -> c_int;
+    /// the recording loops of examples/sample_high_dim.rs:84-86, on the device
+    pub fn scorus_trace_enable(ctx: *mut scorus_ctx, walkers: *const u32, coords: *const u32, ncapture: usize,
+                               capacity_steps: usize) -> c_int;
+    pub fn scorus_trace_download(ctx: *mut scorus_ctx, out: *mut f64, max_steps: usize, nrecorded: *mut usize) -> c_int;
+    pub fn scorus_trace_stride(ctx: *mut scorus_ctx, every: u64) -> c_int;
+    /// chain statistics on the device
+    pub fn scorus_get_rung_stats(ctx: *mut scorus_ctx, nrungs: usize, accepted: *mut u64, proposed: *mut u64,
+                                 swapped: *mut u64, swap_proposed: *mut u64) -> c_int;
+    pub fn scorus_moments_enable(ctx: *mut scorus_ctx, nrungs: usize, every: u64, with_cov: c_int) -> c_int;
+    pub fn scorus_moments_download(ctx: *mut scorus_ctx, rung: usize, mean_out: *mut f64, cov_out: *mut f64,
+                                   nsamples: *mut u64) -> c_int;
+    pub fn scorus_trace_iat(ctx: *mut scorus_ctx, c_window: f64, max_lag: usize, tau_out: *mut f64,
+                            window_out: *mut u32, mean_out: *mut f64, var_out: *mut f64) -> c_int;
+    /// one process per GPU: shards of one ensemble
+    pub fn scorus_set_shard(ctx: *mut scorus_ctx, walker_offset: u64, rung_offset: u32, n_walkers_global: u64) -> c_int;
+    pub fn scorus_sample_pt_global(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, beta_list: *const f64,
+                                   nbeta: usize, ens_all: *const f64, lp_all: *const f64) -> c_int;
+    pub fn scorus_swap_plan_device(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize, lp_all: *mut f64,
+                                   src_all: *mut u32) -> c_int;
+    pub fn scorus_ipc_export(ctx: *mut scorus_ctx, handle_ens_64b: *mut c_void, handle_lp_64b: *mut c_void) -> c_int;
+    pub fn scorus_ipc_attach(ctx: *mut scorus_ctx, world: c_int, rank: c_int, handles_ens: *const c_void,
+                             handles_lp: *const c_void) -> c_int;
+    pub fn scorus_sample_pt_p2p_begin(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, beta_list: *const f64,
+                                      nbeta: usize) -> c_int;
+    pub fn scorus_sample_pt_p2p_end(ctx: *mut scorus_ctx) -> c_int;
+    pub fn scorus_swap_apply_p2p(ctx: *mut scorus_ctx, src_all: *const u32, lp_all: *const f64, phase: c_int) -> c_int;
     pub fn scorus_sync(ctx: *mut scorus_ctx) -> c_int;
     pub fn scorus_set_stream(ctx: *mut scorus_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn scorus_reset_stream(ctx: *mut scorus_ctx) -> c_int;
