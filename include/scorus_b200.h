@@ -161,6 +161,37 @@ int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ensemble, double *logprob, 
 int scorus_swap_walkers_host(scorus_ctx *ctx, double *ensemble, double *logprob,
                              size_t logprob_len, const double *beta_list, size_t nbeta);
 
+/* ---- the ensemble / parallel-tempering t-walk, src/mcmc/twalk.rs ----
+ * TWalkParams (:75-83): aw, at, pphi and the CUMULATIVE kernel weights fw (Walk below fw[0], Traverse
+ * up to fw[1], :57-62); scorus_twalk_params_default is TWalkParams::new(dim) (:89-110). */
+typedef struct scorus_twalk_params {
+    double aw, at, pphi;
+    double fw[2];
+} scorus_twalk_params;
+int scorus_twalk_params_default(size_t dim, scorus_twalk_params *out);
+/* twalk::sample (:586-648) on the resident ensemble, nsteps times: a random perfect matching per rung, then
+ * two half-passes (sample1, :650-762) in which one member of every pair is proposed a Walk (:274-304) or
+ * Traverse (:324-353) move against the other and accepted with calc_a (:463-503).  The pairs of rung r are
+ * walkers of rung r (the reference's sample1 reads them unshifted, :686-690, and writes them shifted, :757-758;
+ * with one rung the two agree -- DESIGN.md 4.7).  Each half-pass advances the step counter by one.  The
+ * nthreads argument of the reference has no counterpart.  dim <= 256. */
+int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *tw, const double *beta_list, size_t nbeta,
+                        uint64_t nsteps);
+/* One half-pass with every random draw supplied, per pair k < n/2 in matching order: pair k moves walker
+ * order[2k + half] against order[2k + 1 - half] (order: a permutation of the walkers, rung by rung);
+ * kernel[k] 0 = Walk, 1 = Traverse; b[k] (sim_b, :306-322); flags[k][dim] (:259-272); walk_u[k][dim]
+ * (sim_walk's uniforms, flagged coordinates only); u[k] the accept uniform (:756).  accepted_out[k] may be
+ * NULL.  Synchronous. */
+int scorus_twalk_half_fixed(scorus_ctx *ctx, const scorus_twalk_params *tw, const double *beta_list, size_t nbeta,
+                            const uint32_t *order, int half, const uint8_t *kernel, const double *b,
+                            const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted_out);
+/* twalk::sample on caller-owned host buffers (`ensemble_logprob: &mut (W, X)`, :588): upload, nsteps, download */
+int scorus_twalk_sample_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
+                             const scorus_twalk_params *tw, const double *beta_list, size_t nbeta, uint64_t nsteps);
+/* the device stream's sim_b value of walkers [0, count) at step counter `step` (the one draw that goes through
+ * pow(); exposed so that a device-stream run can be replayed exactly through scorus_twalk_half_fixed) */
+int scorus_twalk_draw_b(scorus_ctx *ctx, double at, uint64_t step, size_t count, double *out);
+
 /* ---- periphery of the path ----
  * get_one_init_realization, src/mcmc/init_ensemble.rs:19-32, for every walker on the device:
  * x[d] ~ U[lo[d], hi[d]) from the device stream; runs init_logprob if a log-density is registered. */

@@ -182,3 +182,56 @@ def swap_walkers_fixed(ens, lp, beta, jvec, r):
                 lp[[hot, cold]] = lp[[cold, hot]]
                 swapped[s][j2] = 1
     return ens, lp, swapped
+
+
+# ------------------------------------------------------------------------------------------------
+# t-walk, src/mcmc/twalk.rs (second restatement of oracle/twalk.c, written from the Rust source)
+# ------------------------------------------------------------------------------------------------
+def twalk_b(x: float, v: float, at: float) -> float:
+    """sim_b, twalk.rs:306-322, from its two uniforms."""
+    if x == 0.0:
+        return x
+    if v < (at - 1.0) / (2.0 * at):
+        return math.pow(x, 1.0 / (at + 1.0))
+    return math.pow(x, 1.0 / (1.0 - at))
+
+
+def twalk_half_fixed(kind, params, ens, lp, beta, aw, order, half, kernel, b, flags, walk_u, u):
+    """sample1 (twalk.rs:650-762) with supplied draws; pair k moves order[2k+half] against order[2k+1-half],
+    both read inside their own rung.  Returns (new_ens, new_lp, accepted[n/2])."""
+    ens = np.array(ens, dtype=np.float64)
+    lp = np.array(lp, dtype=np.float64)
+    n, d = ens.shape
+    npb = n // len(beta)
+    order = np.asarray(order).reshape(-1, 2)
+    mover, partner = order[:, half], order[:, 1 - half]
+    x, xp = ens[mover], ens[partner]
+    f = np.asarray(flags, dtype=bool)
+    kern = np.asarray(kernel)
+    uu = np.asarray(walk_u, dtype=np.float64)
+    # sim_walk :287-301 / sim_traverse :342-350, all proposals from the ensemble as it stands
+    z = np.where(f, (aw / (1.0 + aw)) * (aw * (uu * uu) + 2.0 * uu - 1.0), 0.0)
+    y_walk = x + (x - xp) * z
+    bb = np.asarray(b, dtype=np.float64)[:, None]
+    y_trav = np.where(f, xp + bb * (xp - x), x)
+    y = np.where((kern == 0)[:, None], y_walk, y_trav)
+    ylp = logprob(kind, params, y)
+    acc = np.zeros(len(mover), dtype=np.uint8)
+    for k in range(len(mover)):   # accept loop :736-760; a pair only touches its own mover, so order is immaterial
+        nphi = int(f[k].sum())
+        if nphi == 0 or np.any(y[k] == xp[k]):   # calc_a :482-483 with all_different :226-240
+            a = 0.0
+        else:
+            t = (ylp[k] - lp[mover[k]]) * beta[mover[k] // npb]
+            if kern[k] == 1:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t = t + float(nphi - 2) * (math.log(b[k]) if b[k] > 0.0 else (-INF if b[k] == 0.0 else float("nan")))
+            try:
+                a = math.exp(t)
+            except OverflowError:
+                a = INF
+        if u[k] < a:
+            ens[mover[k]] = y[k]
+            lp[mover[k]] = ylp[k]
+            acc[k] = 1
+    return ens, lp, acc

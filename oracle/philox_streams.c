@@ -251,3 +251,61 @@ void orc_philox_init_ensemble(uint64_t seed, size_t n, size_t dim, uint64_t walk
             if (d0 + 1 < dim) ens[w * dim + d0 + 1] = lo[d0 + 1] + u53(o[2], o[3]) * (hi[d0 + 1] - lo[d0 + 1]);
         }
 }
+
+/* ---- t-walk half-pass streams (scorus_b200/csrc/twalk_kernel.cuh) ----
+ * The matching is drawn at order_step (shared by both half-passes); everything else at `step`, keyed by the
+ * MOVING walker: ST_ZU (r0,r1) -> kernel uniform scaled by fw[1], (r2,r3) -> accept uniform; ST_TW_B = 9
+ * (r0,r1) -> x, (r2,r3) -> v of sim_b; ST_FLAGS as Prob(pphi); ST_TW_WALK = 10, sub = d/2 -> the sim_walk
+ * uniforms of coordinates d, d+1.  Outputs are per pair k in matching order, as orc_twalk_half_fixed takes
+ * them.  b goes through this host's pow(): a device run is replayed with the device's own b values
+ * (scorus_twalk_draw_b), which agree with these to a few ulp. */
+enum { ST_TW_B = 9, ST_TW_WALK = 10 };
+
+int orc_philox_twalk_streams(uint64_t seed, uint64_t step, uint64_t order_step, size_t n, size_t dim, size_t nbeta,
+                             const orc_twalk_params *tw, int half, uint32_t *order, uint8_t *kernel, double *b,
+                             uint8_t *flags, double *walk_u, double *u)
+{
+    if (nbeta == 0 || n == 0 || n % nbeta || (n / nbeta) % 2) return ORC_ERR_INVALID_ARG;
+    if (!(tw->pphi > 0.0)) return ORC_ERR_INVALID_ARG;
+    pairing_order(seed, order_step, n, nbeta, order);
+    const uint32_t bpf = flag_bits(tw->pphi);
+    const uint32_t fpc = 128 / bpf;
+    const uint32_t nblk = (uint32_t)((dim + fpc - 1) / fpc);
+    const uint64_t thr = bpf == 32 ? (uint64_t)llrint(fmin(tw->pphi, 1.0) * 4294967296.0)
+                                   : (uint64_t)(fmin(tw->pphi, 1.0) * (double)(1u << bpf));
+    const uint64_t vmask = bpf == 32 ? 0xFFFFFFFFull : ((1ull << bpf) - 1);
+    for (size_t k = 0; k < n / 2; ++k) {
+        const uint32_t w = order[2 * k + half];
+        uint32_t o[4];
+        draw(seed, step, ST_ZU, w, 0, o);
+        kernel[k] = u53(o[0], o[1]) * tw->fw[1] < tw->fw[0] ? 0 : 1;
+        u[k] = u53(o[2], o[3]);
+        b[k] = 1.0;
+        if (kernel[k] == 1) {
+            draw(seed, step, ST_TW_B, w, 0, o);
+            b[k] = orc_twalk_b_from_uniforms(u53(o[0], o[1]), u53(o[2], o[3]), tw->at);
+        }
+        uint8_t *f = flags + k * dim;
+        for (uint32_t attempt = 0;; ++attempt) {
+            int any = 0;
+            for (uint32_t blk = 0; blk < nblk; ++blk) {
+                draw(seed, step, ST_FLAGS, w, attempt * nblk + blk, o);
+                for (uint32_t q = 0; q < fpc; ++q) {
+                    const size_t d = (size_t)blk * fpc + q;
+                    if (d >= dim) break;
+                    const uint32_t bit = q * bpf;
+                    const uint64_t v = (o[bit / 32] >> (bit % 32)) & vmask;
+                    f[d] = v < thr;
+                    any |= f[d];
+                }
+            }
+            if (any) break;
+        }
+        for (size_t d = 0; d < dim; d += 2) {
+            draw(seed, step, ST_TW_WALK, w, (uint32_t)(d / 2), o);
+            walk_u[k * dim + d] = u53(o[0], o[1]);
+            if (d + 1 < dim) walk_u[k * dim + d + 1] = u53(o[2], o[3]);
+        }
+    }
+    return ORC_OK;
+}

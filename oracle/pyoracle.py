@@ -27,7 +27,7 @@ ERR_LENGTH_MISMATCH, ERR_INVALID_ARG, ERR_NPHI_ZERO = 5, 6, 7
 
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so with the committed Makefile (gcc, no FMA contraction)."""
-    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "chain_stats.c", "scorus_oracle.h", "Makefile"]
+    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "chain_stats.c", "twalk.c", "scorus_oracle.h", "Makefile"]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
@@ -36,6 +36,11 @@ def build(force: bool = False) -> str:
         subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return _LIB_PATH
+
+
+class TwalkParams(C.Structure):
+    """TWalkParams, src/mcmc/twalk.rs:75-83 (fw cumulative)."""
+    _fields_ = [("aw", C.c_double), ("at", C.c_double), ("pphi", C.c_double), ("fw", C.c_double * 2)]
 
 
 _lib = None
@@ -102,6 +107,15 @@ def lib() -> C.CDLL:
                                             sz, ci]
         L.orc_max_threads.restype = ci
         L.orc_max_threads.argtypes = []
+        L.orc_twalk_params_default.restype = None
+        L.orc_twalk_params_default.argtypes = [sz, C.POINTER(TwalkParams)]
+        L.orc_twalk_b_from_uniforms.restype = dbl
+        L.orc_twalk_b_from_uniforms.argtypes = [dbl, dbl, dbl]
+        L.orc_twalk_half_fixed.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, sz, C.POINTER(TwalkParams), u32p, ci, u8p, dp,
+                                           u8p, dp, dp, u8p, dp, dp]
+        L.orc_twalk_sample.argtypes = [ci, dp, sz, dp, dp, sz, sz, C.c_void_p, C.POINTER(TwalkParams), dp, sz]
+        L.orc_philox_twalk_streams.argtypes = [u64, u64, u64, sz, sz, sz, C.POINTER(TwalkParams), ci, u32p, u8p, dp,
+                                               u8p, dp, dp]
         L.orc_trace_iat.restype = None
         L.orc_trace_iat.argtypes = [dp, sz, sz, dbl, sz, dp, u32p, dp, dp, dp]
         L.orc_running_moments.restype = None
@@ -261,6 +275,65 @@ def cov(ens):
     out = np.empty((dim, dim))
     lib().orc_cov(_dp(np.ascontiguousarray(ens)), n, dim, _dp(out))
     return out
+
+
+def twalk_params(dim, pphi=None, fw=None, aw=None, at=None) -> TwalkParams:
+    """TWalkParams::new(dim) (twalk.rs:89-110), with_pphi (:126-128), with_fw (:112-124: plain weights in)."""
+    t = TwalkParams()
+    lib().orc_twalk_params_default(dim, C.byref(t))
+    if pphi is not None:
+        t.pphi = pphi
+    if fw is not None:
+        t.fw[0], t.fw[1] = fw[0], fw[0] + fw[1]
+    if aw is not None:
+        t.aw = aw
+    if at is not None:
+        t.at = at
+    return t
+
+
+def twalk_half_fixed(kind, params, ens, lp, beta, tw, order, half, kernel, b, flags, walk_u, u, want_proposals=False):
+    """One half-pass of twalk::sample1 with supplied draws, in place; returns accepted[n/2] (+ proposals, new_lp)."""
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    order = np.ascontiguousarray(order, dtype=np.uint32)
+    kernel = np.ascontiguousarray(kernel, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    walk_u = np.ascontiguousarray(walk_u, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    acc = np.zeros(n // 2, dtype=np.uint8)
+    prop = np.zeros((n // 2, dim)) if want_proposals else None
+    nlp = np.zeros(n // 2) if want_proposals else None
+    rc = lib().orc_twalk_half_fixed(kind, pp, npar, _dp(ens), _dp(lp), n, dim, _dp(beta), beta.shape[0], C.byref(tw),
+                                    _u32p(order), half, _u8p(kernel), _dp(b), _u8p(flags), _dp(walk_u), _dp(u),
+                                    _u8p(acc), _dp(prop), _dp(nlp))
+    if rc:
+        raise ValueError(f"orc_twalk_half_fixed rc={rc}")
+    return (acc, prop, nlp) if want_proposals else acc
+
+
+def twalk_sample(kind, params, ens, lp, rng: Rng, tw, beta):
+    """twalk::sample (twalk.rs:586-648) driven by the oracle's generator in the reference's draw order."""
+    n, dim = ens.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    return lib().orc_twalk_sample(kind, pp, npar, _dp(ens), _dp(lp), n, dim, rng.ptr, C.byref(tw), _dp(beta), beta.shape[0])
+
+
+def philox_twalk_streams(seed, step, order_step, n, dim, nbeta, tw, half):
+    """The device streams of one t-walk half-pass: (order, kernel, b, flags, walk_u, u), per pair."""
+    order = np.zeros(n, dtype=np.uint32)
+    kernel = np.zeros(n // 2, dtype=np.uint8)
+    b, u = np.zeros(n // 2), np.zeros(n // 2)
+    flags = np.zeros((n // 2, dim), dtype=np.uint8)
+    walk_u = np.zeros((n // 2, dim))
+    rc = lib().orc_philox_twalk_streams(seed, step, order_step, n, dim, nbeta, C.byref(tw), half, _u32p(order),
+                                        _u8p(kernel), _dp(b), _u8p(flags), _dp(walk_u), _dp(u))
+    if rc:
+        raise ValueError(f"orc_philox_twalk_streams rc={rc}")
+    return order, kernel, b, flags, walk_u, u
 
 
 def trace_iat(trace, c_window=5.0, max_lag=0):

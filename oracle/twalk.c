@@ -1,0 +1,167 @@
+/* twalk.c -- TEST INFRASTRUCTURE ONLY (see scorus_oracle.h).  CPU restatement of the reference's ensemble /
+ * parallel-tempering t-walk, src/mcmc/twalk.rs: TWalkParams::new :89-110,
+ * TWalkKernal::random :40-63, gen_update_flags :259-272, sim_walk :274-304, sim_b :306-322,
+ * sim_traverse :324-353, calc_a :463-503, propose_move :505-532, sample :586-648, sample1 :650-762.
+ * PARITY UNPINNED: the reference has no test or golden vector for this path and cannot be compiled here.
+ *
+ * One deliberate reading.  sample() builds each rung's pairs from indices 0..n/B (:605-612) and sample1()
+ * uses them unshifted when it READS walkers and log-probs (:686-690, :741-749) but shifted by
+ * ibeta * nwalkers_per_beta when it WRITES (:757-758): with B > 1 every rung would propose from rung 0's
+ * walkers.  With B = 1 there is no shift and nothing to decide.  This restatement (and the device path)
+ * applies the shift on both sides -- the pairs of rung r are walkers of rung r -- which is the only reading
+ * under which rung r samples its own tempered density.  DESIGN.md section 4.7 records it. */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "scorus_oracle.h"
+
+/* TWalkParams::new(n), twalk.rs:89-110: aw = 1.5, at = 6, pphi = min(n, 4) / n, fw = cumsum [0.5, 0.5] */
+void orc_twalk_params_default(size_t dim, orc_twalk_params *out)
+{
+    const double n = (double)dim, n1phi = 4.0;
+    out->aw = 1.5;
+    out->at = 6.0;
+    out->pphi = (n < n1phi ? n : n1phi) / n;
+    out->fw[0] = 0.0 + 0.5;
+    out->fw[1] = out->fw[0] + 0.5;
+}
+
+/* sim_b with its two uniforms supplied, twalk.rs:314-321 */
+double orc_twalk_b_from_uniforms(double x, double v, double at)
+{
+    if (x == 0.0) return x;
+    if (v < (at - 1.0) / (2.0 * at)) return pow(x, 1.0 / (at + 1.0));
+    return pow(x, 1.0 / (1.0 - at));
+}
+
+/* One half-pass (sample1, twalk.rs:650-762) with the draws supplied per pair k = 0..n/2-1 in rung-major pair
+ * order: pair k moves walker order[2k + half] against order[2k + 1 - half].
+ *   kernel[k] 0 = Walk, 1 = Traverse;  b[k] (Traverse);  flags[k][dim];  walk_u[k][dim] (Walk, flagged
+ *   coordinates only);  u[k] accept uniform.  accepted[k] (out, may be NULL), proposed [k][dim] / new_lp[k]
+ *   (out, may be NULL). */
+int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n,
+                         size_t dim, const double *beta, size_t nbeta, const orc_twalk_params *tw,
+                         const uint32_t *order, int half, const uint8_t *kernel, const double *b,
+                         const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted,
+                         double *proposed, double *new_lp)
+{
+    if (nbeta == 0 || n == 0) return ORC_ERR_INVALID_ARG;
+    const size_t npb = n / nbeta;
+    if (npb * nbeta != n) return ORC_ERR_NWALKERS_MISMATCHES_NBETA; /* assert :675 */
+    if (npb % 2) return ORC_ERR_NWALKERS_IS_NOT_EVEN;               /* a.chunks(2) ... a[1] panics, :610 */
+    const size_t npair = n / 2;
+    double *y = (double *)malloc(npair * dim * sizeof(double));
+    double *ylp = (double *)malloc(npair * sizeof(double));
+    /* proposals of every pair from the ensemble as it stands (:676-688), then their log-densities (:693-732) */
+    for (size_t k = 0; k < npair; ++k) {
+        const double *x = ens + (size_t)order[2 * k + half] * dim;        /* the walker that moves */
+        const double *xp = ens + (size_t)order[2 * k + 1 - half] * dim;   /* its partner */
+        const uint8_t *f = flags + k * dim;
+        double *yk = y + k * dim;
+        if (kernel[k] == 0) {
+            /* sim_walk :287-301: z = aw/(1+aw) * (aw u^2 + 2u - 1) on flagged coordinates, else 0 */
+            for (size_t i = 0; i < dim; ++i) {
+                double z = 0.0;
+                if (f[i]) {
+                    const double uu = walk_u[k * dim + i];
+                    z = (tw->aw / (1.0 + tw->aw)) * (tw->aw * (uu * uu) + 2.0 * uu - 1.0);
+                }
+                yk[i] = x[i] + (x[i] - xp[i]) * z;
+            }
+        } else {
+            /* sim_traverse :342-350 */
+            for (size_t i = 0; i < dim; ++i) yk[i] = f[i] ? xp[i] + b[k] * (xp[i] - x[i]) : x[i];
+        }
+        ylp[k] = orc_logprob(kind, params, nparams, yk, dim);
+    }
+    /* accept loop :736-760, pairs in order */
+    for (size_t k = 0; k < npair; ++k) {
+        const size_t i1 = order[2 * k + half], i2 = order[2 * k + 1 - half];
+        const double *yk = y + k * dim, *xpart = ens + i2 * dim;
+        const uint8_t *f = flags + k * dim;
+        size_t nphi = 0;
+        for (size_t i = 0; i < dim; ++i) nphi += f[i] ? 1 : 0;
+        int all_diff = 1; /* all_different(yp, x) :226-240, x = the partner */
+        for (size_t i = 0; i < dim; ++i)
+            if (yk[i] == xpart[i]) { all_diff = 0; break; }
+        double a;
+        const double bt = beta[i1 / npb];
+        if (nphi == 0 || !all_diff) {
+            a = 0.0; /* :482-483 */
+        } else if (kernel[k] == 0) {
+            a = exp((ylp[k] - lp[i1]) * bt); /* :486 */
+        } else {
+            a = exp((ylp[k] - lp[i1]) * bt + (double)((long)nphi - 2) * log(b[k])); /* :487-489 */
+        }
+        const int acc = u[k] < a; /* :756 */
+        if (acc) {
+            memcpy(ens + i1 * dim, yk, dim * sizeof(double));
+            lp[i1] = ylp[k];
+        }
+        if (accepted) accepted[k] = (uint8_t)acc;
+    }
+    if (proposed) memcpy(proposed, y, npair * dim * sizeof(double));
+    if (new_lp) memcpy(new_lp, ylp, npair * sizeof(double));
+    free(y);
+    free(ylp);
+    return ORC_OK;
+}
+
+/* the draws of propose_move (:519-531) for one pair, in the reference's consumption order */
+static void draw_proposal(orc_rng *g, size_t dim, const orc_twalk_params *tw, uint8_t *kernel, double *b, uint8_t *f,
+                          double *wu)
+{
+    const double uk = orc_rng_uniform(g) * tw->fw[1]; /* Uniform::new(0, fw[1]) :57 */
+    *kernel = uk < tw->fw[0] ? 0 : 1;
+    *b = 0.0;
+    if (*kernel == 1) { /* sim_b :314-321: the second uniform is drawn only when the first is not 0 */
+        const double x = orc_rng_uniform(g);
+        *b = x == 0.0 ? x : orc_twalk_b_from_uniforms(x, orc_rng_uniform(g), tw->at);
+    }
+    for (;;) { /* gen_update_flags :264-271 */
+        int any = 0;
+        for (size_t i = 0; i < dim; ++i) {
+            f[i] = orc_rng_uniform(g) < tw->pphi;
+            any |= f[i];
+        }
+        if (any) break;
+    }
+    for (size_t i = 0; i < dim; ++i) wu[i] = 0.0;
+    if (*kernel == 0)
+        for (size_t i = 0; i < dim; ++i)
+            if (f[i]) wu[i] = orc_rng_uniform(g); /* :291, flagged coordinates only */
+}
+
+/* twalk::sample (:586-648) driven by the oracle's own generator in the reference's order: the rung shuffles,
+ * then per half-pass every pair's proposal draws followed by every pair's accept uniform. */
+int orc_twalk_sample(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n, size_t dim,
+                     orc_rng *g, const orc_twalk_params *tw, const double *beta, size_t nbeta)
+{
+    if (nbeta == 0 || n == 0) return ORC_ERR_INVALID_ARG;
+    const size_t npb = n / nbeta, npair = n / 2;
+    if (npb * nbeta != n) return ORC_ERR_NWALKERS_MISMATCHES_NBETA;
+    if (npb % 2) return ORC_ERR_NWALKERS_IS_NOT_EVEN;
+    uint32_t *order = (uint32_t *)malloc(n * sizeof(uint32_t));
+    for (size_t r = 0; r < nbeta; ++r) { /* :605-612 */
+        for (size_t k = 0; k < npb; ++k) order[r * npb + k] = (uint32_t)(r * npb + k);
+        for (size_t i = npb; i-- > 1;) {
+            const uint32_t j = orc_rng_below(g, (uint32_t)(i + 1));
+            const uint32_t t = order[r * npb + i];
+            order[r * npb + i] = order[r * npb + j];
+            order[r * npb + j] = t;
+        }
+    }
+    uint8_t *kernel = (uint8_t *)malloc(npair), *flags = (uint8_t *)malloc(npair * dim);
+    double *b = (double *)malloc(npair * sizeof(double)), *wu = (double *)malloc(npair * dim * sizeof(double));
+    double *u = (double *)malloc(npair * sizeof(double));
+    int rc = ORC_OK;
+    for (int half = 0; half < 2 && rc == ORC_OK; ++half) { /* sample1 twice, :618-647 */
+        for (size_t k = 0; k < npair; ++k) draw_proposal(g, dim, tw, kernel + k, b + k, flags + k * dim, wu + k * dim);
+        for (size_t k = 0; k < npair; ++k) u[k] = orc_rng_uniform(g);
+        rc = orc_twalk_half_fixed(kind, params, nparams, ens, lp, n, dim, beta, nbeta, tw, order, half, kernel, b, flags,
+                                  wu, u, NULL, NULL, NULL);
+    }
+    free(order); free(kernel); free(flags); free(b); free(wu); free(u);
+    return rc;
+}

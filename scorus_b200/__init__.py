@@ -1,16 +1,18 @@
 """scorus_b200 -- B200-native drop-in for scorus's ensemble-sampler hot path.
 
 Only what the path needs: csrc/ (CUDA kernels + the C ABI of include/scorus_b200.h) and the
-host-side mirror of the reference modules `mcmc::ensemble_sample` and `mcmc::utils`.
+host-side mirror of the reference modules `mcmc::ensemble_sample`, `mcmc::utils` and (ensemble entry point
+only) `mcmc::twalk`.
 """
-from . import ensemble_sample, init_ensemble, linear_space, utils  # noqa: F401
+from . import ensemble_sample, init_ensemble, linear_space, twalk, utils  # noqa: F401
 from .ensemble_sample import (  # noqa: F401
     BoundedGaussian, Bimodal2d, CorrGaussian, DeviceRng, Gaussian, LogProb, McmcErr, Mixture, Rastrigin,
     Rosenbrock, Sampler, Step2d, UpdateFlagSpec, init_logprob, pinned_empty, propose_move, sample, sample_pt)
+from .twalk import TWalkKernal, TWalkParams  # noqa: F401
 from .utils import draw_z, scale_vec, swap_walkers  # noqa: F401
 
 __all__ = [
-    "ensemble_sample", "utils", "init_ensemble", "linear_space", "Sampler", "DeviceRng", "LogProb", "McmcErr", "UpdateFlagSpec",
+    "ensemble_sample", "utils", "init_ensemble", "linear_space", "twalk", "TWalkParams", "TWalkKernal", "Sampler", "DeviceRng", "LogProb", "McmcErr", "UpdateFlagSpec",
     "Gaussian", "BoundedGaussian", "Rosenbrock", "Rastrigin", "Bimodal2d", "Step2d", "CorrGaussian", "Mixture",
     "init_logprob", "sample", "sample_pt", "propose_move", "swap_walkers", "draw_z", "scale_vec", "pinned_empty",
 ]

@@ -34,6 +34,11 @@ LP_BIMODAL2D, LP_STEP2D, LP_CORR_GAUSSIAN, LP_MIXTURE = 4, 5, 6, 7
 UFS_PROB, UFS_ALL, UFS_ONE_HOT_CYCLE, UFS_MASK = 0, 1, 2, 3
 CFG_SEQUENTIAL_SUM = 1
 
+class TwalkParams(C.Structure):
+    """scorus_twalk_params (include/scorus_b200.h): TWalkParams of src/mcmc/twalk.rs:75-83, fw cumulative."""
+    _fields_ = [("aw", C.c_double), ("at", C.c_double), ("pphi", C.c_double), ("fw", C.c_double * 2)]
+
+
 _lib = None
 
 
@@ -77,6 +82,11 @@ def load() -> C.CDLL:
         "scorus_trace_enable": (ci, [vp, u32p, u32p, sz, sz]),
         "scorus_trace_download": (ci, [vp, dp, sz, C.POINTER(sz)]),
         "scorus_trace_stride": (ci, [vp, u64]),
+        "scorus_twalk_params_default": (ci, [sz, C.POINTER(TwalkParams)]),
+        "scorus_twalk_sample": (ci, [vp, C.POINTER(TwalkParams), dp, sz, u64]),
+        "scorus_twalk_half_fixed": (ci, [vp, C.POINTER(TwalkParams), dp, sz, u32p, ci, u8p, dp, u8p, dp, dp, u8p]),
+        "scorus_twalk_sample_host": (ci, [vp, dp, dp, sz, C.POINTER(TwalkParams), dp, sz, u64]),
+        "scorus_twalk_draw_b": (ci, [vp, dbl, u64, sz, dp]),
         "scorus_get_rung_stats": (ci, [vp, sz, u64p, u64p, u64p, u64p]),
         "scorus_moments_enable": (ci, [vp, sz, u64, ci]),
         "scorus_moments_download": (ci, [vp, sz, dp, dp, u64p]),
@@ -116,7 +126,8 @@ EXPORTS = [
     "scorus_sample_pt", "scorus_sample_pt_fixed", "scorus_draw_z", "scorus_swap_walkers", "scorus_swap_walkers_fixed",
     "scorus_sample_pt_host", "scorus_sample_pt_host_n", "scorus_swap_walkers_host", "scorus_init_ensemble", "scorus_mean", "scorus_cov",
     "scorus_trace_enable", "scorus_trace_download", "scorus_trace_stride", "scorus_get_rung_stats",
-    "scorus_moments_enable", "scorus_moments_download", "scorus_trace_iat", "scorus_set_shard", "scorus_sample_pt_global",
+    "scorus_moments_enable", "scorus_moments_download", "scorus_trace_iat", "scorus_twalk_params_default",
+    "scorus_twalk_sample", "scorus_twalk_half_fixed", "scorus_twalk_sample_host", "scorus_twalk_draw_b", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
     "scorus_sample_pt_p2p_begin", "scorus_sample_pt_p2p_end", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",

@@ -8,6 +8,7 @@
 namespace scorus {
 
 struct StepParams;
+struct TwalkParams;
 
 enum : int { KERNEL_SEQ = 0, KERNEL_COOP = 1, KERNEL_REG = 2 };
 
@@ -21,7 +22,8 @@ struct Geometry {
 #define SCORUS_DECLARE_LAUNCHERS(NAME)                                                                   \
     cudaError_t launch_step_##NAME(const StepParams &p, const Geometry &g, bool all_flags, \
                                    cudaStream_t st);                                                     \
-    cudaError_t launch_init_##NAME(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
+    cudaError_t launch_init_##NAME(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);         \
+    cudaError_t launch_twalk_##NAME(const TwalkParams &tp, const Geometry &g, cudaStream_t st);
 
 SCORUS_DECLARE_LAUNCHERS(LpGaussian)
 SCORUS_DECLARE_LAUNCHERS(LpBoundedGaussian)
@@ -35,5 +37,6 @@ SCORUS_DECLARE_LAUNCHERS(LpMixture)
 // dispatch on the plugin id of include/scorus_b200.h (SCORUS_LP_*)
 cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st);
 cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
+cudaError_t launch_twalk(int kind, const TwalkParams &tp, const Geometry &g, cudaStream_t st);
 
 }  // namespace scorus

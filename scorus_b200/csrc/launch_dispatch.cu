@@ -34,4 +34,19 @@ cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t sme
     }
 }
 
+cudaError_t launch_twalk(int kind, const TwalkParams &tp, const Geometry &g, cudaStream_t st)
+{
+    switch (kind) {
+    case SCORUS_LP_GAUSSIAN: return launch_twalk_LpGaussian(tp, g, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_twalk_LpBoundedGaussian(tp, g, st);
+    case SCORUS_LP_ROSENBROCK: return launch_twalk_LpRosenbrock(tp, g, st);
+    case SCORUS_LP_RASTRIGIN: return launch_twalk_LpRastrigin(tp, g, st);
+    case SCORUS_LP_BIMODAL2D: return launch_twalk_LpBimodal2d(tp, g, st);
+    case SCORUS_LP_STEP2D: return launch_twalk_LpStep2d(tp, g, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_twalk_LpCorrGaussian(tp, g, st);
+    case SCORUS_LP_MIXTURE: return launch_twalk_LpMixture(tp, g, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace scorus

@@ -20,6 +20,7 @@
 #include "stats_kernel.cuh"
 #include "swap_kernel.cuh"
 #include "tile_common.cuh"
+#include "twalk_kernel.cuh"
 
 using namespace scorus;
 
@@ -81,6 +82,8 @@ struct scorus_ctx {
     uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
     double *d_r = nullptr;      size_t r_cap = 0;
     uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
+    uint8_t *d_tw_kernel = nullptr; size_t tw_kernel_cap = 0;   // t-walk, caller-supplied draws
+    double *d_tw_walk = nullptr;    size_t tw_walk_cap = 0;
 
     int lp_kind = -1;
     uint32_t nparams = 0;
@@ -242,7 +245,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
             if (ctx->peer_lp[q]) cudaIpcCloseMemHandle(ctx->peer_lp[q]);
         }
     void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_stage, ctx->d_stage_lp, ctx->d_part, ctx->d_stat,
-                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace, ctx->d_rung_stats, ctx->d_mom, ctx->d_iat};
+                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace, ctx->d_rung_stats, ctx->d_mom, ctx->d_iat, ctx->d_tw_kernel, ctx->d_tw_walk};
     for (void *b : p2p)
         if (b) cudaFree(b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1499,12 +1502,181 @@ extern "C" int scorus_trace_iat(scorus_ctx *ctx, double c_window, size_t max_lag
 }
 
 // ------------------------------------------------------------------------------------------
+// t-walk: src/mcmc/twalk.rs
+// ------------------------------------------------------------------------------------------
+extern "C" int scorus_twalk_params_default(size_t dim, scorus_twalk_params *out)
+{
+    if (!out || dim == 0) return SCORUS_ERR_INVALID_ARG;
+    const double n = (double)dim, n1phi = 4.0;  // TWalkParams::new, twalk.rs:89-110
+    out->aw = 1.5;
+    out->at = 6.0;
+    out->pphi = (n < n1phi ? n : n1phi) / n;
+    out->fw[0] = 0.0 + 0.5;
+    out->fw[1] = out->fw[0] + 0.5;
+    return SCORUS_OK;
+}
+
+static int twalk_common(scorus_ctx *ctx, const scorus_twalk_params *tw, const double *beta, size_t nbeta, TwalkParams *tp,
+                        Geometry *g)
+{
+    int rc = scorus_check_sample_args(ctx->n, ctx->n, nbeta);  // n = B * n/B (:675), pairs need an even rung (:610)
+    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
+    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    if (!(tw->pphi > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "pphi must be > 0 (gen_update_flags would loop forever)");
+    if (!(tw->fw[1] > 0.0) || !(tw->fw[0] >= 0.0) || tw->fw[0] > tw->fw[1])
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "fw must be cumulative weights, 0 <= fw[0] <= fw[1], fw[1] > 0");
+    cudaSetDevice(ctx->device);
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    if ((rc = fill_common(ctx, &tp->s, g, nbeta))) return rc;
+    if (g->kernel != KERNEL_REG)
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "the t-walk needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
+    tp->aw = tw->aw;
+    tp->aw_ratio = tw->aw / (1.0 + tw->aw);  // twalk.rs:292
+    tp->at = tw->at;
+    tp->fw0 = tw->fw[0];
+    tp->fw1 = tw->fw[1];
+    tp->kernel_in = nullptr; tp->b_in = nullptr; tp->walk_u_in = nullptr;
+    StepParams &p = tp->s;
+    p.flag_kind = SCORUS_UFS_PROB;
+    p.flag_bits = flag_bits_for(tw->pphi);
+    p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(tw->pphi, 1.0) * 4294967296.0)
+                                   : (uint64_t)(fmin(tw->pphi, 1.0) * (double)(1u << p.flag_bits));
+    return SCORUS_OK;
+}
+
+// twalk::sample (:586-648): one matching, two half-passes (sample1 :650-762) with the roles exchanged
+extern "C" int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *tw, const double *beta, size_t nbeta,
+                                   uint64_t nsteps)
+{
+    if (!ctx || !tw || !beta) return SCORUS_ERR_INVALID_ARG;
+    TwalkParams tp;
+    Geometry g;
+    memset(&tp, 0, sizeof(tp));
+    int rc = twalk_common(ctx, tw, beta, nbeta, &tp, &g);
+    if (rc) return rc;
+    StepParams &p = tp.s;
+    const bool exact = p.npb <= kExactShuffleMax;
+    if (exact && !ctx->d_order) CU(cudaMalloc(&ctx->d_order, ctx->n * sizeof(uint32_t)));
+    for (uint64_t s = 0; s < nsteps; ++s) {
+        tp.order_step = ctx->step;
+        if (exact) {
+            exact_order_kernel<<<(unsigned)nbeta, (p.npb + 31u) & ~31u, 0, ctx->stream>>>(ctx->seed, ctx->step, p.npb, ctx->d_order, (uint32_t)ctx->w_off);
+            ++ctx->launches;
+            p.order = ctx->d_order;
+        }
+        for (uint32_t half = 0; half < 2; ++half) {
+            tp.half = half;
+            p.step = ctx->step;
+            stamp_tiles(ctx, &p, g);
+            cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
+            ++ctx->launches;
+            ++ctx->step;
+        }
+        if ((rc = after_step(ctx))) return rc;
+    }
+    count_proposed(ctx, nbeta, p.npb, 0, ctx->n, nsteps);  // every walker is proposed once per t-walk step
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_twalk_half_fixed(scorus_ctx *ctx, const scorus_twalk_params *tw, const double *beta, size_t nbeta,
+                                       const uint32_t *order, int half, const uint8_t *kernel, const double *b,
+                                       const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted_out)
+{
+    if (!ctx || !tw || !beta || !order || !kernel || !b || !flags || !walk_u || !u) return SCORUS_ERR_INVALID_ARG;
+    if (half != 0 && half != 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "half must be 0 or 1");
+    TwalkParams tp;
+    Geometry g;
+    memset(&tp, 0, sizeof(tp));
+    int rc = twalk_common(ctx, tw, beta, nbeta, &tp, &g);
+    if (rc) return rc;
+    StepParams &p = tp.s;
+    const size_t n = ctx->n, dim = ctx->dim, npb = p.npb, npair = n / 2;
+    // the matching: a permutation whose pairs (2k, 2k+1) stay inside one rung (:605-612)
+    std::vector<uint8_t> seen(n, 0);
+    for (size_t k = 0; k < n; ++k) {
+        if (order[k] >= n || seen[order[k]] || order[k] / npb != order[k ^ 1] / npb || order[k] / npb != k / npb)
+            return fail(ctx, SCORUS_ERR_INVALID_ARG, "order[] is not a rung-by-rung permutation at position %zu", k);
+        seen[order[k]] = 1;
+    }
+    // per-pair draws -> per-walker arrays (the kernel indexes its streams by walker)
+    std::vector<uint8_t> kw(n, 0), fw(n * dim, 0);
+    std::vector<double> bw(n, 1.0), uw(n, 1.0), ww(n * dim, 0.0);
+    for (size_t k = 0; k < npair; ++k) {
+        if (kernel[k] > 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "kernel[%zu] must be 0 (Walk) or 1 (Traverse)", k);
+        const size_t w = order[2 * k + half];
+        kw[w] = kernel[k]; bw[w] = b[k]; uw[w] = u[k];
+        memcpy(&fw[w * dim], flags + k * dim, dim);
+        memcpy(&ww[w * dim], walk_u + k * dim, dim * sizeof(double));
+    }
+    if (!ctx->d_order) CU(cudaMalloc(&ctx->d_order, n * sizeof(uint32_t)));
+    if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, n * sizeof(double)));
+    if (!ctx->d_u) CU(cudaMalloc(&ctx->d_u, n * sizeof(double)));
+    if (!ctx->d_acc) CU(cudaMalloc(&ctx->d_acc, n));
+    if ((rc = ensure(ctx, (void **)&ctx->d_flags, &ctx->flags_cap, n * dim))) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_tw_kernel, &ctx->tw_kernel_cap, n))) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_tw_walk, &ctx->tw_walk_cap, n * dim * sizeof(double)))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_order, order, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_z, bw.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_u, uw.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_flags, fw.data(), n * dim, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_tw_kernel, kw.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_tw_walk, ww.data(), n * dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_acc, 0, n, ctx->stream));
+    p.order = ctx->d_order; p.u_in = ctx->d_u; p.flags_in = ctx->d_flags; p.flag_len = (uint32_t)dim;
+    p.flag_kind = SCORUS_UFS_MASK; p.accepted_out = ctx->d_acc;
+    tp.kernel_in = ctx->d_tw_kernel; tp.b_in = ctx->d_z; tp.walk_u_in = ctx->d_tw_walk;
+    tp.half = (uint32_t)half;
+    tp.order_step = ctx->step;
+    p.step = ctx->step;
+    stamp_tiles(ctx, &p, g);
+    cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
+    ++ctx->launches;
+    // half a step: the movers of this half-pass were proposed
+    ctx->proposed += npair;
+    if (ctx->rung_proposed.size() < nbeta) ctx->rung_proposed.resize(nbeta, 0);
+    for (size_t r = 0; r < nbeta; ++r) ctx->rung_proposed[r] += npb / 2;
+    std::vector<uint8_t> acc_w(accepted_out ? n : 0);
+    if (accepted_out) CU(cudaMemcpyAsync(acc_w.data(), ctx->d_acc, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // the staging vectors are released here
+    if (accepted_out)
+        for (size_t k = 0; k < npair; ++k) accepted_out[k] = acc_w[order[2 * k + half]];
+    return SCORUS_OK;
+}
+
+// the device's sim_b value (:306-322) of walkers [0, count) at step counter `step`: the one draw of the t-walk
+// that goes through pow(), exposed so that a device-stream run can be replayed exactly
+__global__ void twalk_b_kernel(uint64_t seed, uint64_t step, uint32_t w_off, double at, uint32_t count, double *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const U4 q = draw(seed, step, ST_TW_B, i + w_off, 0);
+    out[i] = twalk_b(u53(q.x, q.y), u53(q.z, q.w), at);
+}
+
+extern "C" int scorus_twalk_draw_b(scorus_ctx *ctx, double at, uint64_t step, size_t count, double *out)
+{
+    if (!ctx || !out || count > ctx->n) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    if (count == 0) return SCORUS_OK;
+    if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, ctx->n * sizeof(double)));
+    twalk_b_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(ctx->seed, step, (uint32_t)ctx->w_off, at,
+                                                                           (uint32_t)count, ctx->d_z);
+    ++ctx->launches;
+    CU(cudaMemcpyAsync(out, ctx->d_z, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // literal drop-ins on host buffers
 // ------------------------------------------------------------------------------------------
-extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
-                                       const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
+// upload -> run(ctx) -> download, shared by the host-buffer entry points
+template <class Run>
+static int host_call(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, size_t nbeta, Run run)
 {
-    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
     int rc = scorus_check_sample_args(ctx->n, lp_len, nbeta);
     if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
     if ((rc = scorus_upload(ctx, ens, lp))) return rc;
@@ -1517,13 +1689,13 @@ extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp,
                         cudaPointerGetAttributes(&al, lp) == cudaSuccess && al.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (!pinned) {
-        if ((rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps))) return rc;
+        if ((rc = run())) return rc;
         return scorus_download(ctx, ens, lp);
     }
     if (!ctx->d_dirty) CU(cudaMalloc(&ctx->d_dirty, ctx->n));
     CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, ctx->stream));
     ctx->track_dirty = true;
-    rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps);
+    rc = run();
     ctx->track_dirty = false;
     if (rc) return rc;
     scatter_download_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, ctx->stream>>>(
@@ -1534,6 +1706,21 @@ extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp,
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "scatter download launch: %s", cudaGetErrorString(e));
     CU(cudaStreamSynchronize(ctx->stream));
     return SCORUS_OK;
+}
+
+extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                       const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
+{
+    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps); });
+}
+
+// twalk::sample on host buffers (the `ensemble_logprob: &mut (W, X)` argument, twalk.rs:588)
+extern "C" int scorus_twalk_sample_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len,
+                                        const scorus_twalk_params *tw, const double *beta, size_t nbeta, uint64_t nsteps)
+{
+    if (!ctx || !ens || !lp || !tw) return SCORUS_ERR_INVALID_ARG;
+    return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_twalk_sample(ctx, tw, beta, nbeta, nsteps); });
 }
 
 extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,

@@ -1,0 +1,292 @@
+// twalk_kernel.cuh -- one half-pass of the ensemble / parallel-tempering t-walk,
+// src/mcmc/twalk.rs: sample1 :650-762 = propose_move :505-532 (TWalkKernal::random :40-63, sim_walk
+// :274-304, sim_b :306-322, sim_traverse :324-353, gen_update_flags :259-272) for one member of every
+// pair, the log-density of the proposals, calc_a :463-503 and the accept loop :736-760, in one launch.
+// twalk::sample (:586-648) is two such launches over the same matching, the second with the roles
+// of each pair's members exchanged.
+//
+// Same shape as the stretch-move kernel (step_reg_kernel.cuh): a tile is 32 consecutive matching
+// positions = 16 pairs (positions 2k, 2k+1), a group of G lanes streams both rows of a pair into
+// registers, the proposal of the MOVING member (position parity == half) and its log-density terms
+// are computed from registers, the proposed row goes to shared memory and leaves it by a TMA bulk
+// store only if accepted.  The partner's row is read, never written: per full t-walk step every row
+// is read twice and written at most once (24 D + 16 bytes per walker-step).
+//
+// Rounding follows the reference operation by operation (-fmad=false): sim_walk computes
+// x + (x - xp) * z with z = (aw / (1 + aw)) * (aw * u*u + 2 u - 1) on flagged coordinates and z = 0 on
+// the others (:287-301); sim_traverse xp + b * (xp - x) on flagged coordinates (:344-347).
+#pragma once
+#include "step_reg_kernel.cuh"
+
+namespace scorus {
+
+enum : uint32_t {
+    ST_TW_B = 9,     // idx = walker, sub = 0: (r0,r1) -> x, (r2,r3) -> v of sim_b
+    ST_TW_WALK = 10  // idx = walker, sub = d/2: sim_walk uniforms of coordinates d, d+1
+};
+
+struct TwalkParams {
+    StepParams s;               // ensemble, streams, geometry; s.step = this half-pass's counter
+    double aw, aw_ratio, at;    // TWalkParams :75-83; aw_ratio = aw / (1 + aw)
+    double fw0, fw1;            // cumulative kernel weights (:93-101)
+    const uint8_t *kernel_in;   // caller-supplied draws, indexed by walker (or nullptr -> device streams)
+    const double *b_in;         // [n]
+    const double *walk_u_in;    // [n][dim]
+    uint64_t order_step;        // counter whose matching both half-passes share
+    uint32_t half;              // the member of each pair that moves: position parity
+};
+
+// sim_b (:306-322) from its two uniforms
+__device__ __forceinline__ double twalk_b(double x, double v, double at)
+{
+    if (x == 0.0) return x;
+    return v < (at - 1.0) / (2.0 * at) ? pow(x, 1.0 / (at + 1.0)) : pow(x, 1.0 / (1.0 - at));
+}
+
+template <class Plugin, int G, int ITERS>
+__global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twalk_half_kernel(const TwalkParams tp)
+{
+    using Geo = RegGeom<G, ITERS>;
+    constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;
+    const StepParams &p = tp.s;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t tile_bytes = 32u * p.row_stride;
+    const uint32_t warp_bytes = tile_bytes + ((p.flag_words * 128u + 127u) & ~127u);
+    unsigned char *ytile = smem + (size_t)warp * warp_bytes;
+    uint32_t *flagw = reinterpret_cast<uint32_t *>(ytile + tile_bytes);
+
+    const uint32_t gwarp = blockIdx.x * p.warps + warp;
+    const uint32_t nwarps = gridDim.x * p.warps;
+    const uint32_t grp = lane / G, j = lane % G;
+    const uint32_t nvec = p.pitch >> 1;
+    const uint32_t half = tp.half;
+    unsigned long long n_acc = 0;
+
+    grid_dep_launch();
+
+    Plugin plug;
+    plug.init(p.pparams, p.nparams, p.dim);
+
+    uint32_t key_rung = 0xFFFFFFFFu;
+    BijKeys K;
+    auto walker_of = [&](uint32_t pos) -> uint32_t {
+        if (p.order) return __ldg(p.order + pos);
+        const uint32_t r = pos / p.npb;
+        if (r != key_rung) { K = bij_keys(p.seed, tp.order_step, ST_PERM, r + p.rung_off); key_rung = r; }
+        return r * p.npb + bij(pos - r * p.npb, p.npb, p.bij_bits, K);
+    };
+    auto load_block = [&](double2 (&x)[GB][ITERS], uint32_t wt, int blk) {
+#pragma unroll
+        for (int i = 0; i < GB; ++i) {
+            const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
+            const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
+            const double2 *src = reinterpret_cast<const double2 *>(p.ens + (size_t)row * p.pitch);
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t c = (uint32_t)it * G + j;
+                x[i][it] = ld_stream(src + (c < nvec ? c : nvec - 1u));
+            }
+        }
+    };
+
+    grid_dep_wait();  // from here on: what earlier launches wrote (order, ensemble, log-probs)
+
+    const uint32_t ntiles = (p.n + 31u) >> 5;
+    uint32_t tile = gwarp;
+    if (tile >= ntiles) return;
+    uint32_t w;
+    bool act;
+    {
+        const uint32_t pos = tile * 32u + lane;
+        act = pos < p.n;
+        w = act ? walker_of(pos) : 0u;
+    }
+    const bool mover_lane = (lane & 1u) == half;  // tiles start at even positions
+    double lp_old = act && mover_lane ? __ldg(p.lp + w) : 0.0;
+    double2 xn[GB][ITERS];
+    load_block(xn, w, 0);
+
+    for (;;) {
+        const bool mv = act && mover_lane;
+        // ---- P1: lane = walker: kernel choice, b, accept uniform, flags ----
+        uint32_t kern = 0;
+        double b = 1.0, u = 1.0;
+        if (tp.kernel_in) {
+            if (mv) { kern = __ldg(tp.kernel_in + w); b = __ldg(tp.b_in + w); u = __ldg(p.u_in + w); }
+        } else if (mv) {
+            const U4 r = draw(p.seed, p.step, ST_ZU, w + p.w_off, 0);
+            kern = u53(r.x, r.y) * tp.fw1 < tp.fw0 ? 0u : 1u;  // TWalkKernal::random :57-62
+            u = u53(r.z, r.w);
+            if (kern == 1u) {
+                const U4 q = draw(p.seed, p.step, ST_TW_B, w + p.w_off, 0);
+                b = twalk_b(u53(q.x, q.y), u53(q.z, q.w), tp.at);
+            }
+        }
+        bulk_wait_read_all();  // the previous tile's accepted rows have left the y tile / flag words
+        __syncwarp();
+        const uint32_t nphi = gen_flags(p, w, flagw, lane, mv);
+        // calc_a :487-489, second summand: (nphi - 2) ln b for Traverse, nothing for Walk
+        const double lb = kern == 1u ? (double)((int)nphi - 2) * log(b) : 0.0;
+        const double beta = __ldg(p.beta + (act ? w / p.npb : 0u));
+        __syncwarp();
+
+        uint32_t tile_n = tile + nwarps;
+        if (p.tile_counter) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(p.tile_counter, 1ull) - p.tile_base;
+            t = __shfl_sync(0xffffffffu, t, 0);
+            tile_n = t + nwarps > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)(t + nwarps);
+        }
+        uint32_t w_n = 0;
+        bool act_n = false;
+        if (tile_n < ntiles) {
+            const uint32_t pos = tile_n * 32u + lane;
+            act_n = pos < p.n;
+            w_n = act_n ? walker_of(pos) : 0u;
+        }
+        const double lp_n = act_n && mover_lane ? __ldg(p.lp + w_n) : 0.0;
+
+        double tot[Plugin::kAcc], tot_eq = 0.0;
+#pragma unroll
+        for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
+
+#pragma unroll 1
+        for (int blk = 0; blk < NB; ++blk) {
+            double2 xc[GB][ITERS];
+#pragma unroll
+            for (int i = 0; i < GB; ++i)
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
+            if (blk + 1 < NB) load_block(xn, w, blk + 1);
+            else if (tile_n < ntiles) load_block(xn, w_n, 0);
+
+            double acc[Plugin::kAcc][GB], acc_eq[GB];
+#pragma unroll
+            for (int pr = 0; pr < PB; ++pr) {
+                const uint32_t wm = grp * G + (uint32_t)(blk * GB + 2 * pr) + half, wp = wm ^ 1u;  // tile rows: mover, partner
+                const uint32_t kern_m = __shfl_sync(0xffffffffu, kern, wm);
+                const double b_m = __shfl_sync(0xffffffffu, b, wm);
+                const uint32_t id_m = __shfl_sync(0xffffffffu, w, wm);
+                double2 *rowm = reinterpret_cast<double2 *>(ytile + wm * p.row_stride);
+                double2 *rowp = reinterpret_cast<double2 *>(ytile + wp * p.row_stride);
+                double2 y[ITERS];
+                double eq = 0.0;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const uint32_t c = (uint32_t)it * G + j;
+                    const uint32_t d = 2u * c;
+                    const double2 xm = half ? xc[2 * pr + 1][it] : xc[2 * pr][it];
+                    const double2 xp = half ? xc[2 * pr][it] : xc[2 * pr + 1][it];
+                    const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
+                    const uint32_t f = c < nvec ? flagw[wd * 32u + wm] >> (d & 31u) : 0u;
+                    double z0 = 0.0, z1 = 0.0;
+                    if (kern_m == 0u && (f & 3u)) {  // sim_walk :289-296
+                        double u0, u1;
+                        if (tp.walk_u_in) {
+                            const double *wu = tp.walk_u_in + (size_t)id_m * p.dim + d;
+                            u0 = __ldg(wu);
+                            u1 = d + 1u < p.dim ? __ldg(wu + 1) : 0.0;
+                        } else {
+                            const U4 r = draw(p.seed, p.step, ST_TW_WALK, id_m + p.w_off, c);
+                            u0 = u53(r.x, r.y);
+                            u1 = u53(r.z, r.w);
+                        }
+                        if (f & 1u) z0 = tp.aw_ratio * (tp.aw * (u0 * u0) + 2.0 * u0 - 1.0);
+                        if (f & 2u) z1 = tp.aw_ratio * (tp.aw * (u1 * u1) + 2.0 * u1 - 1.0);
+                    }
+                    // Walk: x + (x - xp) z on every coordinate (:298); Traverse: xp + b (xp - x) on flagged ones (:346)
+                    const double wx = xm.x + (xm.x - xp.x) * z0, wy = xm.y + (xm.y - xp.y) * z1;
+                    const double tx = (f & 1u) ? xp.x + b_m * (xp.x - xm.x) : xm.x;
+                    const double ty = (f & 2u) ? xp.y + b_m * (xp.y - xm.y) : xm.y;
+                    y[it].x = kern_m == 0u ? wx : tx;
+                    y[it].y = kern_m == 0u ? wy : ty;
+                    if (c < nvec) {
+                        rowm[c] = y[it];
+                        if constexpr (Plugin::kNeedsRow) rowp[c] = xp;  // the tile evaluation reads all 32 rows
+                        // all_different(yp, x) :226-240, x = the partner
+                        if (y[it].x == xp.x) eq += 1.0;
+                        if (d + 1u < p.dim && y[it].y == xp.y) eq += 1.0;
+                    }
+                }
+                double pa[Plugin::kAcc];
+#pragma unroll
+                for (int a = 0; a < Plugin::kAcc; ++a) pa[a] = 0.0;
+                if constexpr (!Plugin::kNeedsRow) {
+#pragma unroll
+                    for (int it = 0; it < ITERS; ++it) {
+                        const uint32_t c = (uint32_t)it * G + j;
+                        const uint32_t d = 2u * c;
+                        double nb = 0.0;
+                        if constexpr (Plugin::kNeedsNext) {
+                            nb = __shfl_down_sync(0xffffffffu, y[it].x, 1, G);
+                            if (ITERS > 1 && it + 1 < ITERS) {
+                                const double w0 = __shfl_sync(0xffffffffu, y[it + 1 < ITERS ? it + 1 : it].x, 0, G);
+                                if (j == G - 1) nb = w0;
+                            }
+                        }
+                        if (c < nvec) plug.terms(d, y[it].x, y[it].y, nb, d + 1u < p.dim, d + 2u < p.dim, pa);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < Plugin::kAcc; ++a) {
+                    acc[a][2 * pr] = half ? 0.0 : pa[a];
+                    acc[a][2 * pr + 1] = half ? pa[a] : 0.0;
+                }
+                acc_eq[2 * pr] = half ? 0.0 : eq;
+                acc_eq[2 * pr + 1] = half ? eq : 0.0;
+            }
+            if constexpr (!Plugin::kNeedsRow) {
+#pragma unroll
+                for (int a = 0; a < Plugin::kAcc; ++a) {
+                    double r = transpose_reduce<GB>(acc[a], lane);
+#pragma unroll
+                    for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
+                    if ((int)(j / GB) == blk) tot[a] = r;
+                }
+            }
+            {
+                double r = transpose_reduce<GB>(acc_eq, lane);
+#pragma unroll
+                for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
+                if ((int)(j / GB) == blk) tot_eq = r;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+
+        // ---- P5: lane = walker: calc_a :480-501 and the accept test :756-759 ----
+        unsigned char *own_b = ytile + lane * p.row_stride;
+        double lp_new;
+        if constexpr (Plugin::kNeedsRow) {
+            lp_new = plug.tile_logprob(ytile, p.row_stride, lane);
+        } else {
+            lp_new = plug.finish_acc(tot);
+        }
+        const double a_acc = (nphi == 0u || tot_eq > 0.0) ? 0.0 : exp((lp_new - lp_old) * beta + lb);
+        const bool accept = mv && (u < a_acc);
+        if (accept) {
+            bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
+            p.lp[w] = lp_new;
+            if (p.dirty) p.dirty[w] = 1;
+            ++n_acc;
+        }
+        bulk_commit();
+        if (p.accepted_out && mv) p.accepted_out[w] = accept ? 1 : 0;
+        if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
+
+        if (tile_n >= ntiles) break;
+        tile = tile_n;
+        w = w_n;
+        act = act_n;
+        lp_old = lp_n;
+    }
+
+    bulk_wait_all();
+    for (int off = 16; off; off >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, off);
+    if (lane == 0 && n_acc) atomicAdd(p.stats, n_acc);
+}
+
+}  // namespace scorus

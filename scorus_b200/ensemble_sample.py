@@ -389,6 +389,45 @@ class Sampler:
                                             window.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(mean), _dp(var)))
         return dict(tau=tau, window=window, mean=mean, var=var)
 
+    # -- t-walk, src/mcmc/twalk.rs (scorus_b200/twalk.py mirrors the module)
+    def twalk_sample(self, param, beta_list, nsteps: int = 1):
+        """twalk::sample (twalk.rs:586-648) on the resident ensemble, nsteps times."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        self._ok(self._lib.scorus_twalk_sample(self._ctx, C.byref(param._c()), _dp(beta), beta.size, nsteps))
+
+    def twalk_half_fixed(self, param, beta_list, order, half, kernel, b, flags, walk_u, u):
+        """One half-pass (sample1, twalk.rs:650-762) with supplied draws, per pair; returns accepted[n/2]."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        kernel = np.ascontiguousarray(kernel, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        walk_u = np.ascontiguousarray(walk_u, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        npair = self.n // 2
+        if (order.shape != (self.n,) or kernel.shape != (npair,) or b.shape != (npair,) or u.shape != (npair,)
+                or flags.shape != (npair, self.dim) or walk_u.shape != (npair, self.dim)):
+            raise ValueError("t-walk stream arrays must have one entry per pair (order: one per walker)")
+        acc = np.zeros(max(npair, 1), dtype=np.uint8)
+        u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+        self._ok(self._lib.scorus_twalk_half_fixed(
+            self._ctx, C.byref(param._c()), _dp(beta), beta.size, order.ctypes.data_as(u32p), int(half),
+            kernel.ctypes.data_as(u8p), _dp(b), flags.ctypes.data_as(u8p), _dp(walk_u), _dp(u), acc.ctypes.data_as(u8p)))
+        return acc[:npair]
+
+    def twalk_sample_host(self, ensemble, logprob, param, beta_list, nsteps: int = 1):
+        _check_arrays(ensemble, logprob)
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        self._ok(self._lib.scorus_twalk_sample_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0],
+                                                    C.byref(param._c()), _dp(beta), beta.size, nsteps))
+
+    def twalk_draw_b(self, at: float, step: int, count: Optional[int] = None) -> np.ndarray:
+        """sim_b (twalk.rs:306-322) of walkers [0, count) from the device stream at step counter `step`."""
+        count = self.n if count is None else count
+        out = np.empty(count)
+        self._ok(self._lib.scorus_twalk_draw_b(self._ctx, at, step, count, _dp(out)))
+        return out
+
     # -- sharding (one process per GPU; scorus_b200/distributed.py drives these)
     def set_shard(self, walker_offset: int, rung_offset: int, n_walkers_global: int):
         self._ok(self._lib.scorus_set_shard(self._ctx, walker_offset, rung_offset, n_walkers_global))
