@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--move", default="stretch", choices=["stretch", "twalk"],
+                    help="stretch = the headline metric (ensemble_sample::sample_pt); twalk = the t-walk move family "
+                         "(twalk::sample, SURVEY 8(f) rank 2) on the same workload, an extra measurement")
     ap.add_argument("--n-walkers", type=int, default=0, help="experiments only: override the workload's ensemble size")
     ap.add_argument("--global-every", type=int, default=1,
                     help="with --matching global/p2p: whole-ensemble matching every k-th step, shard-local in between")
@@ -197,7 +200,11 @@ def main():
         desc += f" [n_walkers overridden to {n}]"
     W = max(args.warmup, 3)
 
+    if args.move == "twalk":
+        desc += " [move: t-walk, twalk::sample with TWalkParams::new(dim)]"
     if args.impl == "reference":
+        if args.move != "stretch":
+            raise SystemExit("--impl reference times the headline path (--move stretch)")
         if rank != 0:
             return 0
         r = cpu_reference_leg(args.workload, args.steps, W, target_seconds=60.0)
@@ -266,6 +273,14 @@ def main():
         swap = s.swap_walkers
         can_swap = True
 
+    tw = sb.TWalkParams.new(dim)
+
+    def do_steps(count):
+        if args.move == "twalk":
+            s.twalk_sample(tw, beta, count)
+        else:
+            s.sample_pt(2.0, spec, beta, count)
+
     def run_steps(k0, count):
         # consecutive steps between two swaps go down in ONE library call (nsteps): the launches are
         # queued back to back from C, without a Python round trip per step
@@ -276,7 +291,7 @@ def main():
             nxt = min(end, (k // swap_every + 1) * swap_every) if (swap_every and nbeta > 1 and can_swap) else end
             if os.environ.get("BENCH_STEP_PER_CALL"):
                 nxt = k + 1
-            s.sample_pt(2.0, spec, beta, nxt - k)
+            do_steps(nxt - k)
             k = nxt
 
     run_steps(0, W)
@@ -313,15 +328,19 @@ def main():
         if world > 1:
             def host_step():  # upload shard, one (possibly exchanging) step, download shard
                 s.upload(h_ens, h_lp)
-                s.sample_pt(2.0, spec, beta, 1)
+                do_steps(1)
                 s.sampler.download(h_ens, h_lp)
             s.sampler.download(h_ens, h_lp)
             api = "ShardedSampler.upload + sample_pt + download (pinned host buffers, one step per call)"
         else:
             def host_step():
-                s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
+                if args.move == "twalk":
+                    s.twalk_sample_host(h_ens, h_lp, tw, beta)
+                else:
+                    s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
             s.download(h_ens, h_lp)
-            api = "Sampler.sample_pt_host -> scorus_sample_pt_host (pinned host buffers in/out, one step per call)"
+            api = ("Sampler.twalk_sample_host -> scorus_twalk_sample_host" if args.move == "twalk" else
+                   "Sampler.sample_pt_host -> scorus_sample_pt_host") + " (pinned host buffers in/out, one step per call)"
         host_step()  # warm-up
         torch.cuda.synchronize()
         if dist:
@@ -343,7 +362,7 @@ def main():
         e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": api}
-        if world == 1:
+        if world == 1 and args.move == "stretch":
             # extra, not the headline: a driver that records every 10th iteration (examples/test_emcee.rs:82-84)
             # makes one host round trip per 10 steps (scorus_sample_pt_host_n)
             torch.cuda.synchronize()
@@ -367,9 +386,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     kernel_name = {6: "step_reg_kernel<LpCorrGaussian> (K1 + K3 DMMA tile)"}.get(kind, "step_reg_kernel (K1)")
+    if args.move == "twalk":
+        kernel_name = "twalk_half_kernel (both half-passes of a t-walk step fused in one launch)"
     traffic = None
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.move == "stretch":
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
     if kind == 6:
         # dense quadratic form: 2 D^2 + 2 D flops per walker-step against an fp64 DGEMM
@@ -399,7 +420,7 @@ def main():
                             + (", swap kernels amortised in)" if swap_every else ")")}
 
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and args.move == "stretch":
         cpu = cpu_reference_leg(args.workload, 20, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")}
 
@@ -408,7 +429,7 @@ def main():
         "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "n_walkers": n, "dim": dim, "nbeta": nbeta, "ufs": ufs, "prob": prob, "a": 2.0,
-                   "parallelism": parallelism, "swap_every": swap_every,
+                   "move": args.move, "parallelism": parallelism, "swap_every": swap_every,
                    "l2": f"resident ensemble {n_local * dim * 8 / 2**20:.0f} MiB per GPU vs 126 MB L2 (no flush needed)"
                          if n_local * dim * 8 > 2 * 126e6 else "ensemble fits in L2: numbers are L2-resident, not HBM"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -174,6 +174,16 @@ public:
         check(scorus_draw_z(ctx_, a, 1, &z), ctx_);
         return z;
     }
+    // t-walk, src/mcmc/twalk.rs:586-648 (namespace twalk below mirrors the module)
+    void twalk_sample(const scorus_twalk_params &param, const std::vector<double> &beta, uint64_t nsteps = 1)
+    {
+        check(scorus_twalk_sample(ctx_, &param, beta.data(), beta.size(), nsteps), ctx_);
+    }
+    void twalk_sample_host(double *ens, double *lp, size_t lp_len, const scorus_twalk_params &param,
+                           const std::vector<double> &beta, uint64_t nsteps = 1)
+    {
+        check(scorus_twalk_sample_host(ctx_, ens, lp, lp_len, &param, beta.data(), beta.size(), nsteps), ctx_);
+    }
     // chain statistics on the device (what the example drivers compute from per-step downloads)
     struct RungStats { std::vector<uint64_t> accepted, proposed, swapped, swap_proposed; };
     RungStats rung_stats(size_t nrungs)
@@ -313,5 +323,47 @@ inline void swap_walkers(detail::Ensemble &ensemble, std::vector<double> &logpro
 inline double draw_z(DeviceRng &rng, double a) { return rng.sampler(LogProb::gaussian(), 2, 2).draw_z(a); }
 
 }  // namespace utils
+
+namespace twalk {
+
+// TWalkParams, src/mcmc/twalk.rs:75-130 (fw holds cumulative weights, as the reference stores them)
+struct TWalkParams : scorus_twalk_params {
+    static TWalkParams make(size_t n)  // TWalkParams::new(n), :89-110
+    {
+        TWalkParams p;
+        check(scorus_twalk_params_default(n, &p));
+        return p;
+    }
+    TWalkParams with_fw(double w0, double w1) const  // :112-124: plain weights in
+    {
+        TWalkParams p = *this;
+        p.fw[0] = 0.0 + w0;
+        p.fw[1] = p.fw[0] + w1;
+        return p;
+    }
+    TWalkParams with_pphi(double v) const  // :126-128
+    {
+        TWalkParams p = *this;
+        p.pphi = v;
+        return p;
+    }
+};
+
+// twalk::sample, :586-648, in place on the host containers; nthreads is accepted and ignored
+inline void sample(const LogProb &flogprob, std::pair<detail::Ensemble, std::vector<double>> &ensemble_logprob,
+                   const TWalkParams &param, DeviceRng &rng, const std::vector<double> &beta_list, size_t nthreads = 1)
+{
+    (void)nthreads;
+    detail::Ensemble &ensemble = ensemble_logprob.first;
+    std::vector<double> &logprob = ensemble_logprob.second;
+    check(scorus_check_sample_args(ensemble.size(), logprob.size(), beta_list.size()));  // :675 and the pairs of :610
+    const size_t dim = ensemble[0].size();
+    Sampler &s = rng.sampler(flogprob, ensemble.size(), dim);
+    std::vector<double> flat = detail::flatten(ensemble, dim);
+    s.twalk_sample_host(flat.data(), logprob.data(), logprob.size(), param, beta_list);
+    detail::unflatten(flat, ensemble, dim);
+}
+
+}  // namespace twalk
 }  // namespace mcmc
 }  // namespace scorus

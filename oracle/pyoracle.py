@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         L.orc_twalk_b_from_uniforms.argtypes = [dbl, dbl, dbl]
         L.orc_twalk_half_fixed.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, sz, C.POINTER(TwalkParams), u32p, ci, u8p, dp,
                                            u8p, dp, dp, u8p, dp, dp]
+        L.orc_twalk_draw_streams.argtypes = [C.c_void_p, sz, sz, sz, C.POINTER(TwalkParams), u32p, u8p, dp, u8p, dp, dp]
         L.orc_twalk_sample.argtypes = [ci, dp, sz, dp, dp, sz, sz, C.c_void_p, C.POINTER(TwalkParams), dp, sz]
         L.orc_philox_twalk_streams.argtypes = [u64, u64, u64, sz, sz, sz, C.POINTER(TwalkParams), ci, u32p, u8p, dp,
                                                u8p, dp, dp]
@@ -312,6 +313,21 @@ def twalk_half_fixed(kind, params, ens, lp, beta, tw, order, half, kernel, b, fl
     if rc:
         raise ValueError(f"orc_twalk_half_fixed rc={rc}")
     return (acc, prop, nlp) if want_proposals else acc
+
+
+def twalk_draw_streams(rng: Rng, n, dim, nbeta, tw):
+    """Draws of one twalk::sample call in the reference's order: order[n], then kernel / b / flags / walk_u / u with a
+    leading axis of 2 (the half-passes)."""
+    order = np.zeros(n, dtype=np.uint32)
+    kernel = np.zeros((2, n // 2), dtype=np.uint8)
+    b, u = np.zeros((2, n // 2)), np.zeros((2, n // 2))
+    flags = np.zeros((2, n // 2, dim), dtype=np.uint8)
+    walk_u = np.zeros((2, n // 2, dim))
+    rc = lib().orc_twalk_draw_streams(rng.ptr, n, dim, nbeta, C.byref(tw), _u32p(order), _u8p(kernel), _dp(b), _u8p(flags),
+                                      _dp(walk_u), _dp(u))
+    if rc:
+        raise ValueError(f"orc_twalk_draw_streams rc={rc}")
+    return order, kernel, b, flags, walk_u, u
 
 
 def twalk_sample(kind, params, ens, lp, rng: Rng, tw, beta):

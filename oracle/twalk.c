@@ -133,35 +133,49 @@ static void draw_proposal(orc_rng *g, size_t dim, const orc_twalk_params *tw, ui
             if (f[i]) wu[i] = orc_rng_uniform(g); /* :291, flagged coordinates only */
 }
 
-/* twalk::sample (:586-648) driven by the oracle's own generator in the reference's order: the rung shuffles,
- * then per half-pass every pair's proposal draws followed by every pair's accept uniform. */
-int orc_twalk_sample(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n, size_t dim,
-                     orc_rng *g, const orc_twalk_params *tw, const double *beta, size_t nbeta)
+/* The draws of one twalk::sample call (:586-648) in the reference's consumption order: the rung shuffles
+ * (:605-612), then per half-pass every pair's proposal draws (:676-688) followed by every pair's accept uniform
+ * (:756).  None depends on the state, so they can be drawn ahead.  order[n]; the rest [2][n/2](...[dim]). */
+int orc_twalk_draw_streams(orc_rng *g, size_t n, size_t dim, size_t nbeta, const orc_twalk_params *tw, uint32_t *order,
+                           uint8_t *kernel, double *b, uint8_t *flags, double *walk_u, double *u)
 {
     if (nbeta == 0 || n == 0) return ORC_ERR_INVALID_ARG;
     const size_t npb = n / nbeta, npair = n / 2;
     if (npb * nbeta != n) return ORC_ERR_NWALKERS_MISMATCHES_NBETA;
     if (npb % 2) return ORC_ERR_NWALKERS_IS_NOT_EVEN;
-    uint32_t *order = (uint32_t *)malloc(n * sizeof(uint32_t));
-    for (size_t r = 0; r < nbeta; ++r) { /* :605-612 */
+    for (size_t r = 0; r < nbeta; ++r) {
         for (size_t k = 0; k < npb; ++k) order[r * npb + k] = (uint32_t)(r * npb + k);
-        for (size_t i = npb; i-- > 1;) {
+        for (size_t i = npb; i-- > 1;) { /* SliceRandom::shuffle: Fisher-Yates from the top */
             const uint32_t j = orc_rng_below(g, (uint32_t)(i + 1));
             const uint32_t t = order[r * npb + i];
             order[r * npb + i] = order[r * npb + j];
             order[r * npb + j] = t;
         }
     }
-    uint8_t *kernel = (uint8_t *)malloc(npair), *flags = (uint8_t *)malloc(npair * dim);
-    double *b = (double *)malloc(npair * sizeof(double)), *wu = (double *)malloc(npair * dim * sizeof(double));
-    double *u = (double *)malloc(npair * sizeof(double));
-    int rc = ORC_OK;
-    for (int half = 0; half < 2 && rc == ORC_OK; ++half) { /* sample1 twice, :618-647 */
-        for (size_t k = 0; k < npair; ++k) draw_proposal(g, dim, tw, kernel + k, b + k, flags + k * dim, wu + k * dim);
-        for (size_t k = 0; k < npair; ++k) u[k] = orc_rng_uniform(g);
-        rc = orc_twalk_half_fixed(kind, params, nparams, ens, lp, n, dim, beta, nbeta, tw, order, half, kernel, b, flags,
-                                  wu, u, NULL, NULL, NULL);
+    for (size_t half = 0; half < 2; ++half) {
+        for (size_t k = 0; k < npair; ++k) {
+            const size_t e = half * npair + k;
+            draw_proposal(g, dim, tw, kernel + e, b + e, flags + e * dim, walk_u + e * dim);
+        }
+        for (size_t k = 0; k < npair; ++k) u[half * npair + k] = orc_rng_uniform(g);
     }
+    return ORC_OK;
+}
+
+/* twalk::sample = the draws above + the two half-passes */
+int orc_twalk_sample(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n, size_t dim,
+                     orc_rng *g, const orc_twalk_params *tw, const double *beta, size_t nbeta)
+{
+    const size_t npair = n / 2;
+    uint32_t *order = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    uint8_t *kernel = (uint8_t *)malloc(2 * npair + 1), *flags = (uint8_t *)malloc(2 * npair * dim + 1);
+    double *b = (double *)malloc((2 * npair + 1) * sizeof(double)), *wu = (double *)malloc((2 * npair * dim + 1) * sizeof(double));
+    double *u = (double *)malloc((2 * npair + 1) * sizeof(double));
+    int rc = orc_twalk_draw_streams(g, n, dim, nbeta, tw, order, kernel, b, flags, wu, u);
+    for (int half = 0; half < 2 && rc == ORC_OK; ++half)
+        rc = orc_twalk_half_fixed(kind, params, nparams, ens, lp, n, dim, beta, nbeta, tw, order, half,
+                                  kernel + half * npair, b + half * npair, flags + half * npair * dim,
+                                  wu + half * npair * dim, u + half * npair, NULL, NULL, NULL);
     free(order); free(kernel); free(flags); free(b); free(wu); free(u);
     return rc;
 }

@@ -36,6 +36,11 @@ pub const SCORUS_UFS_ONE_HOT_CYCLE: i32 = 2;
 pub const SCORUS_UFS_MASK: i32 = 3;
 pub const SCORUS_CFG_SEQUENTIAL_SUM: u32 = 1;
 
+/// TWalkParams, src/mcmc/twalk.rs:75-83 (fw cumulative)
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct scorus_twalk_params { pub aw: f64, pub at: f64, pub pphi: f64, pub fw: [f64; 2] }
+
 extern "C" {
     pub fn scorus_abi_version() -> c_int;
     pub fn scorus_status_string(status: c_int) -> *const c_char;
@@ -91,6 +96,16 @@ extern "C" {
                                    nsamples: *mut u64) -> c_int;
     pub fn scorus_trace_iat(ctx: *mut scorus_ctx, c_window: f64, max_lag: usize, tau_out: *mut f64,
                             window_out: *mut u32, mean_out: *mut f64, var_out: *mut f64) -> c_int;
+    /// the ensemble / parallel-tempering t-walk, src/mcmc/twalk.rs:586-762
+    pub fn scorus_twalk_params_default(dim: usize, out: *mut scorus_twalk_params) -> c_int;
+    pub fn scorus_twalk_sample(ctx: *mut scorus_ctx, tw: *const scorus_twalk_params, beta_list: *const f64, nbeta: usize,
+                               nsteps: u64) -> c_int;
+    pub fn scorus_twalk_half_fixed(ctx: *mut scorus_ctx, tw: *const scorus_twalk_params, beta_list: *const f64,
+                                   nbeta: usize, order: *const u32, half: c_int, kernel: *const u8, b: *const f64,
+                                   flags: *const u8, walk_u: *const f64, u: *const f64, accepted_out: *mut u8) -> c_int;
+    pub fn scorus_twalk_sample_host(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64, logprob_len: usize,
+                                    tw: *const scorus_twalk_params, beta_list: *const f64, nbeta: usize, nsteps: u64) -> c_int;
+    pub fn scorus_twalk_draw_b(ctx: *mut scorus_ctx, at: f64, step: u64, count: usize, out: *mut f64) -> c_int;
     /// one process per GPU: shards of one ensemble
     pub fn scorus_set_shard(ctx: *mut scorus_ctx, walker_offset: u64, rung_offset: u32, n_walkers_global: u64) -> c_int;
     pub fn scorus_sample_pt_global(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, beta_list: *const f64,

@@ -95,6 +95,10 @@ impl Sampler {
         self.with_ufs(ufs, |c| check(unsafe {
             sys::scorus_sample_pt_host(ctx, pe, pl, n_lp, a, c, beta.as_ptr(), beta.len()) }, ctx));
     }
+    pub fn twalk_sample_host(&self, ens: &mut [f64], lp: &mut [f64], param: &sys::scorus_twalk_params, beta: &[f64]) {
+        check(unsafe { sys::scorus_twalk_sample_host(self.ctx, ens.as_mut_ptr(), lp.as_mut_ptr(), lp.len(), param,
+                                                     beta.as_ptr(), beta.len(), 1) }, self.ctx);
+    }
     pub fn swap_walkers_host(&self, ens: &mut [f64], lp: &mut [f64], beta: &[f64]) {
         check(unsafe { sys::scorus_swap_walkers_host(self.ctx, ens.as_mut_ptr(), lp.as_mut_ptr(), lp.len(),
                                                      beta.as_ptr(), beta.len()) }, self.ctx);
@@ -150,4 +154,34 @@ where V: Clone + IndexableLinearSpace<f64> {
     let (mut flat, dim) = flatten(ensemble);
     rng.sampler(&LogProb::gaussian(0.5), ensemble.len(), dim).swap_walkers_host(&mut flat, logprob, beta_list);
     unflatten(&flat, ensemble, dim);
+}
+
+/// `mcmc::twalk`, ensemble entry point (src/mcmc/twalk.rs:586-648)
+pub mod twalk {
+    use super::*;
+
+    /// src/mcmc/twalk.rs:75-130; `fw` holds cumulative weights, as the reference stores them
+    #[derive(Clone, Copy, Debug)]
+    pub struct TWalkParams { pub aw: f64, pub at: f64, pub pphi: f64, pub fw: [f64; 2] }
+    impl TWalkParams {
+        pub fn new(n: usize) -> Self {
+            let mut c = sys::scorus_twalk_params { aw: 0.0, at: 0.0, pphi: 0.0, fw: [0.0; 2] };
+            check(unsafe { sys::scorus_twalk_params_default(n, &mut c) }, std::ptr::null());
+            Self { aw: c.aw, at: c.at, pphi: c.pphi, fw: c.fw }
+        }
+        pub fn with_fw(mut self, fw: [f64; 2]) -> Self { self.fw = [fw[0], fw[0] + fw[1]]; self }
+        pub fn with_pphi(self, pphi: f64) -> Self { Self { pphi, ..self } }
+    }
+
+    /// twalk::sample: `nthreads` is accepted and ignored (the log-densities are evaluated on the device)
+    pub fn sample<V>(flogprob: &LogProb, ensemble_logprob: &mut (Vec<V>, Vec<f64>), param: &TWalkParams,
+                     rng: &mut DeviceRng, beta_list: &[f64], _nthreads: usize)
+    where V: Clone + IndexableLinearSpace<f64> + Sync + Send {
+        let (ensemble, logprob) = (&mut ensemble_logprob.0, &mut ensemble_logprob.1);
+        check(unsafe { sys::scorus_check_sample_args(ensemble.len(), logprob.len(), beta_list.len()) }, std::ptr::null());
+        let (mut flat, dim) = flatten(ensemble);
+        let c = sys::scorus_twalk_params { aw: param.aw, at: param.at, pphi: param.pphi, fw: param.fw };
+        rng.sampler(flogprob, ensemble.len(), dim).twalk_sample_host(&mut flat, logprob, &c, beta_list);
+        unflatten(&flat, ensemble, dim);
+    }
 }

@@ -1557,6 +1557,7 @@ extern "C" int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *t
     if (rc) return rc;
     StepParams &p = tp.s;
     const bool exact = p.npb <= kExactShuffleMax;
+    const bool fused = env_int("SCORUS_TWALK_FUSED", 1) != 0;
     if (exact && !ctx->d_order) CU(cudaMalloc(&ctx->d_order, ctx->n * sizeof(uint32_t)));
     for (uint64_t s = 0; s < nsteps; ++s) {
         tp.order_step = ctx->step;
@@ -1565,14 +1566,24 @@ extern "C" int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *t
             ++ctx->launches;
             p.order = ctx->d_order;
         }
-        for (uint32_t half = 0; half < 2; ++half) {
-            tp.half = half;
+        if (fused) {  // both half-passes of every pair in one launch (twalk_kernel.cuh); counters step, step + 1
+            tp.half = 2;
             p.step = ctx->step;
             stamp_tiles(ctx, &p, g);
             cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
             ++ctx->launches;
-            ++ctx->step;
+            ctx->step += 2;
+        } else {
+            for (uint32_t half = 0; half < 2; ++half) {
+                tp.half = half;
+                p.step = ctx->step;
+                stamp_tiles(ctx, &p, g);
+                cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
+                if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
+                ++ctx->launches;
+                ++ctx->step;
+            }
         }
         if ((rc = after_step(ctx))) return rc;
     }

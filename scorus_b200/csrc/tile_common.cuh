@@ -142,7 +142,7 @@ __device__ __forceinline__ uint32_t walker_at(const StepParams &p, uint32_t j)
 
 // Prob(p): BPF random bits per coordinate, flag = value < thr; redrawn (attempt + 1) until one is set.
 template <int BPF>
-__device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint32_t w, uint32_t *flagw,
+__device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw,
                                                    uint32_t lane, bool act)
 {
     constexpr uint32_t FPC = 128u / BPF;   // flags per Philox call
@@ -156,7 +156,7 @@ __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint32_t
         nphi = 0;
         uint32_t cur = 0;
         for (uint32_t blk = 0; blk < nblk; ++blk) {
-            const U4 r = draw(p.seed, p.step, ST_FLAGS, w + p.w_off, attempt * nblk + blk);
+            const U4 r = draw(p.seed, step, ST_FLAGS, w + p.w_off, attempt * nblk + blk);
             const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (uint32_t wi = 0; wi < 4; ++wi) {
@@ -187,7 +187,9 @@ __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint32_t
     return nphi;
 }
 
-__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, uint32_t *flagw, uint32_t lane,
+// `step`: the counter the Prob stream is keyed by (p.step, except in the fused t-walk kernel whose two half-passes
+// use consecutive counters)
+__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw, uint32_t lane,
                                               bool act)
 {
     if (p.flag_kind == 2u) {  // ONE_HOT_CYCLE: the cycling closure, called once per walker in order
@@ -214,13 +216,17 @@ __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, u
         return nphi;
     }
     switch (p.flag_bits) {  // PROB
-    case 1: return gen_flags_prob<1>(p, w, flagw, lane, act);
-    case 2: return gen_flags_prob<2>(p, w, flagw, lane, act);
-    case 4: return gen_flags_prob<4>(p, w, flagw, lane, act);
-    case 8: return gen_flags_prob<8>(p, w, flagw, lane, act);
-    case 16: return gen_flags_prob<16>(p, w, flagw, lane, act);
-    default: return gen_flags_prob<32>(p, w, flagw, lane, act);
+    case 1: return gen_flags_prob<1>(p, step, w, flagw, lane, act);
+    case 2: return gen_flags_prob<2>(p, step, w, flagw, lane, act);
+    case 4: return gen_flags_prob<4>(p, step, w, flagw, lane, act);
+    case 8: return gen_flags_prob<8>(p, step, w, flagw, lane, act);
+    case 16: return gen_flags_prob<16>(p, step, w, flagw, lane, act);
+    default: return gen_flags_prob<32>(p, step, w, flagw, lane, act);
     }
+}
+__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, uint32_t *flagw, uint32_t lane, bool act)
+{
+    return gen_flags(p, p.step, w, flagw, lane, act);
 }
 
 // per-rung acceptance counts: one atomic per tile when the tile lies inside one rung (the usual case),

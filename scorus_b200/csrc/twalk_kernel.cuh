@@ -2,15 +2,20 @@
 // src/mcmc/twalk.rs: sample1 :650-762 = propose_move :505-532 (TWalkKernal::random :40-63, sim_walk
 // :274-304, sim_b :306-322, sim_traverse :324-353, gen_update_flags :259-272) for one member of every
 // pair, the log-density of the proposals, calc_a :463-503 and the accept loop :736-760, in one launch.
-// twalk::sample (:586-648) is two such launches over the same matching, the second with the roles
-// of each pair's members exchanged.
+// twalk::sample (:586-648) is two such half-passes over the same matching, the second with the roles
+// of each pair's members exchanged.  Because the pairs are disjoint and both half-passes share the
+// matching, the second half-pass of a pair depends on nothing but the first half-pass of the SAME
+// pair: with half = 2 the kernel runs both on a tile before moving on (one launch per t-walk step;
+// the rows are re-read for the second half-pass, from L2: they were streamed a few microseconds
+// earlier), so HBM sees each row once in and at most once out per step, as in the stretch move.
 //
 // Same shape as the stretch-move kernel (step_reg_kernel.cuh): a tile is 32 consecutive matching
 // positions = 16 pairs (positions 2k, 2k+1), a group of G lanes streams both rows of a pair into
 // registers, the proposal of the MOVING member (position parity == half) and its log-density terms
 // are computed from registers, the proposed row goes to shared memory and leaves it by a TMA bulk
-// store only if accepted.  The partner's row is read, never written: per full t-walk step every row
-// is read twice and written at most once (24 D + 16 bytes per walker-step).
+// store only if accepted.  The partner's row is read, never written.  Launched per half-pass (half = 0
+// or 1: the fixed-stream entry point, or SCORUS_TWALK_FUSED=0) every row is read from HBM twice per
+// t-walk step; fused (half = 2, the default) once.
 //
 // Rounding follows the reference operation by operation (-fmad=false): sim_walk computes
 // x + (x - xp) * z with z = (aw / (1 + aw)) * (aw * u*u + 2 u - 1) on flagged coordinates and z = 0 on
@@ -33,7 +38,8 @@ struct TwalkParams {
     const double *b_in;         // [n]
     const double *walk_u_in;    // [n][dim]
     uint64_t order_step;        // counter whose matching both half-passes share
-    uint32_t half;              // the member of each pair that moves: position parity
+    uint32_t half;              // the member of each pair that moves (position parity): 0, 1, or 2 = 0 then 1
+                                // fused, the second keyed by step counter s.step + 1
 };
 
 // sim_b (:306-322) from its two uniforms
@@ -62,7 +68,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
     const uint32_t nwarps = gridDim.x * p.warps;
     const uint32_t grp = lane / G, j = lane % G;
     const uint32_t nvec = p.pitch >> 1;
-    const uint32_t half = tp.half;
+    const bool both = tp.half == 2u;
+    const uint32_t h_begin = both ? 0u : tp.half, h_end = both ? 2u : tp.half + 1u;
     unsigned long long n_acc = 0;
 
     grid_dep_launch();
@@ -104,30 +111,34 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
         act = pos < p.n;
         w = act ? walker_of(pos) : 0u;
     }
-    const bool mover_lane = (lane & 1u) == half;  // tiles start at even positions
-    double lp_old = act && mover_lane ? __ldg(p.lp + w) : 0.0;
+    // tiles start at even positions: lane parity = position parity.  A lane takes part in the half-pass
+    // that moves its parity; in fused mode that is every lane, odd lanes one step counter later.
+    const uint32_t my_half = lane & 1u;
+    const bool lane_in = both || my_half == tp.half;
+    const uint64_t my_step = p.step + (both ? my_half : 0u);
+    double lp_old = act && lane_in ? __ldg(p.lp + w) : 0.0;
     double2 xn[GB][ITERS];
     load_block(xn, w, 0);
 
     for (;;) {
-        const bool mv = act && mover_lane;
+        const bool mv = act && lane_in;
         // ---- P1: lane = walker: kernel choice, b, accept uniform, flags ----
         uint32_t kern = 0;
         double b = 1.0, u = 1.0;
         if (tp.kernel_in) {
             if (mv) { kern = __ldg(tp.kernel_in + w); b = __ldg(tp.b_in + w); u = __ldg(p.u_in + w); }
         } else if (mv) {
-            const U4 r = draw(p.seed, p.step, ST_ZU, w + p.w_off, 0);
+            const U4 r = draw(p.seed, my_step, ST_ZU, w + p.w_off, 0);
             kern = u53(r.x, r.y) * tp.fw1 < tp.fw0 ? 0u : 1u;  // TWalkKernal::random :57-62
             u = u53(r.z, r.w);
             if (kern == 1u) {
-                const U4 q = draw(p.seed, p.step, ST_TW_B, w + p.w_off, 0);
+                const U4 q = draw(p.seed, my_step, ST_TW_B, w + p.w_off, 0);
                 b = twalk_b(u53(q.x, q.y), u53(q.z, q.w), tp.at);
             }
         }
         bulk_wait_read_all();  // the previous tile's accepted rows have left the y tile / flag words
         __syncwarp();
-        const uint32_t nphi = gen_flags(p, w, flagw, lane, mv);
+        const uint32_t nphi = gen_flags(p, my_step, w, flagw, lane, mv);
         // calc_a :487-489, second summand: (nphi - 2) ln b for Traverse, nothing for Walk
         const double lb = kern == 1u ? (double)((int)nphi - 2) * log(b) : 0.0;
         const double beta = __ldg(p.beta + (act ? w / p.npb : 0u));
@@ -147,135 +158,149 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
             act_n = pos < p.n;
             w_n = act_n ? walker_of(pos) : 0u;
         }
-        const double lp_n = act_n && mover_lane ? __ldg(p.lp + w_n) : 0.0;
+        const double lp_n = act_n && lane_in ? __ldg(p.lp + w_n) : 0.0;
 
-        double tot[Plugin::kAcc], tot_eq = 0.0;
+        bool accept = false;  // this lane's decision (set in the half-pass that moves it)
+#pragma unroll 1
+        for (uint32_t half = h_begin; half < h_end; ++half) {
+            // fused second half-pass: the partner is the first half-pass's mover, at its NEW position
+            const bool second = both && half == 1u;
+            double tot[Plugin::kAcc], tot_eq = 0.0;
 #pragma unroll
-        for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
+            for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
 
 #pragma unroll 1
-        for (int blk = 0; blk < NB; ++blk) {
-            double2 xc[GB][ITERS];
+            for (int blk = 0; blk < NB; ++blk) {
+                double2 xc[GB][ITERS];
 #pragma unroll
-            for (int i = 0; i < GB; ++i)
+                for (int i = 0; i < GB; ++i)
 #pragma unroll
-                for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
-            if (blk + 1 < NB) load_block(xn, w, blk + 1);
-            else if (tile_n < ntiles) load_block(xn, w_n, 0);
+                    for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
+                if (blk + 1 < NB) load_block(xn, w, blk + 1);
+                else if (half + 1u < h_end) load_block(xn, w, 0);  // the same tile again (old rows, from L2)
+                else if (tile_n < ntiles) load_block(xn, w_n, 0);
 
-            double acc[Plugin::kAcc][GB], acc_eq[GB];
+                double acc[Plugin::kAcc][GB], acc_eq[GB];
 #pragma unroll
-            for (int pr = 0; pr < PB; ++pr) {
-                const uint32_t wm = grp * G + (uint32_t)(blk * GB + 2 * pr) + half, wp = wm ^ 1u;  // tile rows: mover, partner
-                const uint32_t kern_m = __shfl_sync(0xffffffffu, kern, wm);
-                const double b_m = __shfl_sync(0xffffffffu, b, wm);
-                const uint32_t id_m = __shfl_sync(0xffffffffu, w, wm);
-                double2 *rowm = reinterpret_cast<double2 *>(ytile + wm * p.row_stride);
-                double2 *rowp = reinterpret_cast<double2 *>(ytile + wp * p.row_stride);
-                double2 y[ITERS];
-                double eq = 0.0;
-#pragma unroll
-                for (int it = 0; it < ITERS; ++it) {
-                    const uint32_t c = (uint32_t)it * G + j;
-                    const uint32_t d = 2u * c;
-                    const double2 xm = half ? xc[2 * pr + 1][it] : xc[2 * pr][it];
-                    const double2 xp = half ? xc[2 * pr][it] : xc[2 * pr + 1][it];
-                    const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
-                    const uint32_t f = c < nvec ? flagw[wd * 32u + wm] >> (d & 31u) : 0u;
-                    double z0 = 0.0, z1 = 0.0;
-                    if (kern_m == 0u && (f & 3u)) {  // sim_walk :289-296
-                        double u0, u1;
-                        if (tp.walk_u_in) {
-                            const double *wu = tp.walk_u_in + (size_t)id_m * p.dim + d;
-                            u0 = __ldg(wu);
-                            u1 = d + 1u < p.dim ? __ldg(wu + 1) : 0.0;
-                        } else {
-                            const U4 r = draw(p.seed, p.step, ST_TW_WALK, id_m + p.w_off, c);
-                            u0 = u53(r.x, r.y);
-                            u1 = u53(r.z, r.w);
-                        }
-                        if (f & 1u) z0 = tp.aw_ratio * (tp.aw * (u0 * u0) + 2.0 * u0 - 1.0);
-                        if (f & 2u) z1 = tp.aw_ratio * (tp.aw * (u1 * u1) + 2.0 * u1 - 1.0);
-                    }
-                    // Walk: x + (x - xp) z on every coordinate (:298); Traverse: xp + b (xp - x) on flagged ones (:346)
-                    const double wx = xm.x + (xm.x - xp.x) * z0, wy = xm.y + (xm.y - xp.y) * z1;
-                    const double tx = (f & 1u) ? xp.x + b_m * (xp.x - xm.x) : xm.x;
-                    const double ty = (f & 2u) ? xp.y + b_m * (xp.y - xm.y) : xm.y;
-                    y[it].x = kern_m == 0u ? wx : tx;
-                    y[it].y = kern_m == 0u ? wy : ty;
-                    if (c < nvec) {
-                        rowm[c] = y[it];
-                        if constexpr (Plugin::kNeedsRow) rowp[c] = xp;  // the tile evaluation reads all 32 rows
-                        // all_different(yp, x) :226-240, x = the partner
-                        if (y[it].x == xp.x) eq += 1.0;
-                        if (d + 1u < p.dim && y[it].y == xp.y) eq += 1.0;
-                    }
-                }
-                double pa[Plugin::kAcc];
-#pragma unroll
-                for (int a = 0; a < Plugin::kAcc; ++a) pa[a] = 0.0;
-                if constexpr (!Plugin::kNeedsRow) {
+                for (int pr = 0; pr < PB; ++pr) {
+                    const uint32_t wm = grp * G + (uint32_t)(blk * GB + 2 * pr) + half, wp = wm ^ 1u;  // tile rows: mover, partner
+                    const uint32_t kern_m = __shfl_sync(0xffffffffu, kern, wm);
+                    const double b_m = __shfl_sync(0xffffffffu, b, wm);
+                    const uint32_t id_m = __shfl_sync(0xffffffffu, w, wm);
+                    const bool moved_p = __shfl_sync(0xffffffffu, (uint32_t)accept, wp) != 0u && second;
+                    double2 *rowm = reinterpret_cast<double2 *>(ytile + wm * p.row_stride);
+                    double2 *rowp = reinterpret_cast<double2 *>(ytile + wp * p.row_stride);
+                    double2 y[ITERS];
+                    double eq = 0.0;
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) {
                         const uint32_t c = (uint32_t)it * G + j;
                         const uint32_t d = 2u * c;
-                        double nb = 0.0;
-                        if constexpr (Plugin::kNeedsNext) {
-                            nb = __shfl_down_sync(0xffffffffu, y[it].x, 1, G);
-                            if (ITERS > 1 && it + 1 < ITERS) {
-                                const double w0 = __shfl_sync(0xffffffffu, y[it + 1 < ITERS ? it + 1 : it].x, 0, G);
-                                if (j == G - 1) nb = w0;
+                        const double2 xm = half ? xc[2 * pr + 1][it] : xc[2 * pr][it];
+                        double2 xp = half ? xc[2 * pr][it] : xc[2 * pr + 1][it];
+                        // its accepted proposal is still in the tile (and on its way to global memory)
+                        if (moved_p && c < nvec) xp = rowp[c];
+                        const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
+                        const uint32_t f = c < nvec ? flagw[wd * 32u + wm] >> (d & 31u) : 0u;
+                        double z0 = 0.0, z1 = 0.0;
+                        if (kern_m == 0u && (f & 3u)) {  // sim_walk :289-296
+                            double u0, u1;
+                            if (tp.walk_u_in) {
+                                const double *wu = tp.walk_u_in + (size_t)id_m * p.dim + d;
+                                u0 = __ldg(wu);
+                                u1 = d + 1u < p.dim ? __ldg(wu + 1) : 0.0;
+                            } else {
+                                const U4 r = draw(p.seed, p.step + (both ? half : 0u), ST_TW_WALK, id_m + p.w_off, c);
+                                u0 = u53(r.x, r.y);
+                                u1 = u53(r.z, r.w);
                             }
+                            if (f & 1u) z0 = tp.aw_ratio * (tp.aw * (u0 * u0) + 2.0 * u0 - 1.0);
+                            if (f & 2u) z1 = tp.aw_ratio * (tp.aw * (u1 * u1) + 2.0 * u1 - 1.0);
                         }
-                        if (c < nvec) plug.terms(d, y[it].x, y[it].y, nb, d + 1u < p.dim, d + 2u < p.dim, pa);
+                        // Walk: x + (x - xp) z on every coordinate (:298); Traverse: xp + b (xp - x) on flagged ones (:346)
+                        const double wx = xm.x + (xm.x - xp.x) * z0, wy = xm.y + (xm.y - xp.y) * z1;
+                        const double tx = (f & 1u) ? xp.x + b_m * (xp.x - xm.x) : xm.x;
+                        const double ty = (f & 2u) ? xp.y + b_m * (xp.y - xm.y) : xm.y;
+                        y[it].x = kern_m == 0u ? wx : tx;
+                        y[it].y = kern_m == 0u ? wy : ty;
+                        if (c < nvec) {
+                            rowm[c] = y[it];
+                            if constexpr (Plugin::kNeedsRow) {
+                                if (!second) rowp[c] = xp;  // the tile evaluation reads all 32 rows
+                            }
+                            // all_different(yp, x) :226-240, x = the partner
+                            if (y[it].x == xp.x) eq += 1.0;
+                            if (d + 1u < p.dim && y[it].y == xp.y) eq += 1.0;
+                        }
+                    }
+                    double pa[Plugin::kAcc];
+#pragma unroll
+                    for (int a = 0; a < Plugin::kAcc; ++a) pa[a] = 0.0;
+                    if constexpr (!Plugin::kNeedsRow) {
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it) {
+                            const uint32_t c = (uint32_t)it * G + j;
+                            const uint32_t d = 2u * c;
+                            double nb = 0.0;
+                            if constexpr (Plugin::kNeedsNext) {
+                                nb = __shfl_down_sync(0xffffffffu, y[it].x, 1, G);
+                                if (ITERS > 1 && it + 1 < ITERS) {
+                                    const double w0 = __shfl_sync(0xffffffffu, y[it + 1 < ITERS ? it + 1 : it].x, 0, G);
+                                    if (j == G - 1) nb = w0;
+                                }
+                            }
+                            if (c < nvec) plug.terms(d, y[it].x, y[it].y, nb, d + 1u < p.dim, d + 2u < p.dim, pa);
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < Plugin::kAcc; ++a) {
+                        acc[a][2 * pr] = half ? 0.0 : pa[a];
+                        acc[a][2 * pr + 1] = half ? pa[a] : 0.0;
+                    }
+                    acc_eq[2 * pr] = half ? 0.0 : eq;
+                    acc_eq[2 * pr + 1] = half ? eq : 0.0;
+                }
+                if constexpr (!Plugin::kNeedsRow) {
+#pragma unroll
+                    for (int a = 0; a < Plugin::kAcc; ++a) {
+                        double r = transpose_reduce<GB>(acc[a], lane);
+#pragma unroll
+                        for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
+                        if ((int)(j / GB) == blk) tot[a] = r;
                     }
                 }
-#pragma unroll
-                for (int a = 0; a < Plugin::kAcc; ++a) {
-                    acc[a][2 * pr] = half ? 0.0 : pa[a];
-                    acc[a][2 * pr + 1] = half ? pa[a] : 0.0;
-                }
-                acc_eq[2 * pr] = half ? 0.0 : eq;
-                acc_eq[2 * pr + 1] = half ? eq : 0.0;
-            }
-            if constexpr (!Plugin::kNeedsRow) {
-#pragma unroll
-                for (int a = 0; a < Plugin::kAcc; ++a) {
-                    double r = transpose_reduce<GB>(acc[a], lane);
+                {
+                    double r = transpose_reduce<GB>(acc_eq, lane);
 #pragma unroll
                     for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
-                    if ((int)(j / GB) == blk) tot[a] = r;
+                    if ((int)(j / GB) == blk) tot_eq = r;
                 }
             }
-            {
-                double r = transpose_reduce<GB>(acc_eq, lane);
-#pragma unroll
-                for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
-                if ((int)(j / GB) == blk) tot_eq = r;
-            }
-        }
-        fence_proxy_async();
-        __syncwarp();
+            fence_proxy_async();
+            __syncwarp();
 
-        // ---- P5: lane = walker: calc_a :480-501 and the accept test :756-759 ----
-        unsigned char *own_b = ytile + lane * p.row_stride;
-        double lp_new;
-        if constexpr (Plugin::kNeedsRow) {
-            lp_new = plug.tile_logprob(ytile, p.row_stride, lane);
-        } else {
-            lp_new = plug.finish_acc(tot);
+            // ---- P5: lane = walker: calc_a :480-501 and the accept test :756-759, for this half-pass's movers ----
+            unsigned char *own_b = ytile + lane * p.row_stride;
+            double lp_new;
+            if constexpr (Plugin::kNeedsRow) {
+                lp_new = plug.tile_logprob(ytile, p.row_stride, lane);
+            } else {
+                lp_new = plug.finish_acc(tot);
+            }
+            const bool mine = act && my_half == half;
+            const double a_acc = (nphi == 0u || tot_eq > 0.0) ? 0.0 : exp((lp_new - lp_old) * beta + lb);
+            const bool acc_now = mine && (u < a_acc);
+            if (acc_now) {
+                bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
+                p.lp[w] = lp_new;
+                if (p.dirty) p.dirty[w] = 1;
+                ++n_acc;
+                accept = true;
+            }
+            bulk_commit();
+            if (p.accepted_out && mine) p.accepted_out[w] = acc_now ? 1 : 0;
+            if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, acc_now, lane);
         }
-        const double a_acc = (nphi == 0u || tot_eq > 0.0) ? 0.0 : exp((lp_new - lp_old) * beta + lb);
-        const bool accept = mv && (u < a_acc);
-        if (accept) {
-            bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
-            p.lp[w] = lp_new;
-            if (p.dirty) p.dirty[w] = 1;
-            ++n_acc;
-        }
-        bulk_commit();
-        if (p.accepted_out && mv) p.accepted_out[w] = accept ? 1 : 0;
-        if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
 
         if (tile_n >= ntiles) break;
         tile = tile_n;

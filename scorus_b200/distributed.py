@@ -215,6 +215,18 @@ class ShardedSampler:
             self._step_index += 1
             done += 1
 
+    def twalk_sample(self, param, beta_list: Sequence[float], nsteps: int = 1):
+        """twalk::sample (src/mcmc/twalk.rs:586-648) on this rank's shard.  Rung shards (whole rungs per rank):
+        the matching never leaves a rung, so no communication and the same chain as one GPU.  Walker shards:
+        the matching is drawn inside the shard (`matching="local"` only)."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if self.mode == "rungs":
+            self.sampler.twalk_sample(param, beta[self.rung_off:self.rung_off + self.nb_local], nsteps)
+            return
+        if self.matching != "local" and self.world > 1:
+            raise NotImplementedError("the t-walk across walker shards supports matching='local' only")
+        self.sampler.twalk_sample(param, beta, nsteps)
+
     def _barrier(self):
         """Stream-ordered barrier across ranks (a one-element all-reduce: no host synchronisation)."""
         self.dist.all_reduce(self._token, group=self.group)

@@ -52,6 +52,21 @@ int main(int argc, char **argv)
         }
         for (size_t i = 0; i < ensemble.size(); ++i) printf("B %zu %.17g %.17g %.17g\n", i, ensemble[i][0], ensemble[i][ndims - 1], logprob[i]);
     }
+    {   // the t-walk through the same host containers: twalk::sample(flogprob, &mut (ensemble, logprob), param, rng, beta, nthreads)
+        const size_t nbetas = 2, per = 8, ndims = 6;
+        std::vector<double> blist = {1.0, 0.5};
+        std::pair<std::vector<std::vector<double>>, std::vector<double>> el;
+        el.first.assign(nbetas * per, std::vector<double>(ndims));
+        for (auto &w : el.first)
+            for (auto &x : w) x = -1.0 + 2.0 * lcg(st);
+        el.second.resize(el.first.size());
+        DeviceRng rng(13);
+        LogProb lpf = LogProb::rosenbrock();
+        ensemble_sample::init_logprob(lpf, el.first, el.second, rng);
+        twalk::TWalkParams param = twalk::TWalkParams::make(ndims).with_pphi(0.5);
+        for (int k = 0; k < niter; ++k) twalk::sample(lpf, el, param, rng, blist, 4);
+        for (size_t i = 0; i < el.first.size(); ++i) printf("T %zu %.17g %.17g %.17g\n", i, el.first[i][0], el.first[i][ndims - 1], el.second[i]);
+    }
     {   // the reference's panics become exceptions
         std::vector<std::vector<double>> e(6, std::vector<double>(2, 0.1));
         std::vector<double> lp(6, 0.0);

@@ -77,7 +77,54 @@ def make(case):
     print(f"{name}: n={n} dim={dim} nbeta={nb} steps={steps} accept={np.mean(accs):.3f}")
 
 
+# t-walk (src/mcmc/twalk.rs:586-762): name, plugin kind, params, n, dim, nbeta, pphi (None = TWalkParams::new), steps, box, seed
+TWALK_CASES = [
+    ("twalk_gaussian_d2", po.LP_GAUSSIAN, [0.5], 16, 2, 1, None, 20, (0.9, 1.1), 11),
+    ("twalk_rosenbrock_d8_pt2", po.LP_ROSENBROCK, [], 24, 8, 2, None, 10, (0.9, 1.1), 12),
+    ("twalk_rastrigin_d10_pt4", po.LP_RASTRIGIN, [10.0], 32, 10, 4, 0.3, 10, (-0.5, 0.5), 13),
+    ("twalk_bimodal2d_pt2", po.LP_BIMODAL2D, [], 16, 2, 2, None, 12, None, 14),
+]
+
+
+def make_twalk(case):
+    name, kind, params, n, dim, nb, pphi, steps, box, seed = case
+    g = po.Rng(seed)
+    params = np.asarray(params, dtype=np.float64)
+    if box is None:
+        ens = np.ascontiguousarray(np.tile(np.array(BIMODAL_TABLE), (n // 8, 1)))
+    else:
+        ens = np.array([[box[0] + g.uniform() * (box[1] - box[0]) for _ in range(dim)] for _ in range(n)])
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    lp = po.init_logprob(kind, params, ens)
+    tw = po.twalk_params(dim, pphi=pphi)
+    out = dict(kind=kind, params=params, beta=beta, tw=np.array([tw.aw, tw.at, tw.pphi, tw.fw[0], tw.fw[1]]),
+               ens0=ens.copy(), lp0=lp.copy())
+    keys = ["order", "kernel", "b", "flags", "walk_u", "u", "accepted", "ens", "lp"]
+    acc = {k: [] for k in keys}
+    for k in range(steps):
+        order, kernel, b, flags, wu, u = po.twalk_draw_streams(g, n, dim, nb, tw)
+        accepted, enss, lps = [], [], []
+        for half in (0, 1):
+            e2, l2, a2 = no.twalk_half_fixed(kind, params, ens, lp, beta, tw.aw, order, half, kernel[half], b[half],
+                                             flags[half], wu[half], u[half])
+            a1 = po.twalk_half_fixed(kind, params, ens, lp, beta, tw, order, half, kernel[half], b[half], flags[half],
+                                     wu[half], u[half])
+            assert np.array_equal(a1, a2) and np.array_equal(ens, e2) and np.array_equal(lp, l2, equal_nan=True), (name, k, half)
+            accepted.append(a1); enss.append(ens.copy()); lps.append(lp.copy())
+        for key, v in zip(keys, [order, kernel, b, flags, wu, u, np.stack(accepted), np.stack(enss), np.stack(lps)]):
+            acc[key].append(v)
+    out.update({k: np.stack(v) for k, v in acc.items()})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: n={n} dim={dim} nbeta={nb} steps={steps} accept={np.mean(out['accepted']):.3f} "
+          f"traverse={np.mean(out['kernel']):.2f}")
+
+
 if __name__ == "__main__":
     po.build()
-    for c in CASES:
-        make(c)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "stretch"):
+        for c in CASES:
+            make(c)
+    if which in ("all", "twalk"):
+        for c in TWALK_CASES:
+            make_twalk(c)

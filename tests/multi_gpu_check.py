@@ -18,7 +18,7 @@ import scorus_b200 as sb  # noqa: E402
 from scorus_b200.distributed import ShardedSampler  # noqa: E402
 
 
-def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matching="global", p2p_swap=True):
+def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matching="global", p2p_swap=True, twalk=False):
     rank, world = dist.get_rank(), dist.get_world_size()
     rng = np.random.default_rng(1234)
     ens = np.ascontiguousarray(rng.uniform(box[0], box[1], (n, dim)))
@@ -34,8 +34,12 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
         if swap_every and k % swap_every == 0:
             ref.swap_walkers(beta)
             sh.swap_walkers(beta)
-        ref.sample_pt(2.0, ufs, beta, 1)
-        sh.sample_pt(2.0, ufs, beta, 1)
+        if twalk:   # the t-walk move family over the same shards (ufs unused)
+            ref.twalk_sample(sb.TWalkParams.new(dim), beta, 1)
+            sh.twalk_sample(sb.TWalkParams.new(dim), beta, 1)
+        else:
+            ref.sample_pt(2.0, ufs, beta, 1)
+            sh.sample_pt(2.0, ufs, beta, 1)
     want_e, want_lp = ref.download()
     got_e, got_lp = sh.download()
     ok_pos = np.array_equal(got_e, want_e[lo:hi])
@@ -95,6 +99,10 @@ def main():
                    sb.UpdateFlagSpec.Prob(0.5), 10, 0, (0.9, 1.1), matching="p2p")
     ok &= run_case("rastrigin_p2p_matching_small_odd", sb.Rastrigin(), 70 * world, 7, 1,
                    sb.UpdateFlagSpec.Prob(0.2), 10, 0, (-0.5, 0.5), matching="p2p")
+    # t-walk over rung shards: no per-step communication, cross-rank ladder swaps
+    ok &= run_case("twalk_rastrigin_pt", sb.Rastrigin(), 2048 * 4 * world, 10, 4 * world, None, 12, 4, (-0.5, 0.5), twalk=True)
+    ok &= run_case("twalk_rosenbrock_pt_small_rungs", sb.Rosenbrock(), 64 * 2 * world, 20, 2 * world, None, 12, 3, (0.9, 1.1),
+                   twalk=True)
     ok &= run_mixed(world)
     dist.barrier()
     dist.destroy_process_group()

@@ -271,6 +271,19 @@ def test_cpp_host_layer_matches_python_mirror(sb, tmp_path):
     assert len(got) == 32
     for i, t in enumerate(got):
         assert (float(t[2]), float(t[3]), float(t[4])) == (ens[i, 0], ens[i, 19], lp[i])
+    # T: the t-walk through mcmc::twalk::sample
+    ens = np.array([[-1.0 + 2.0 * lcg() for _ in range(6)] for _ in range(16)])
+    lp = np.empty(16)
+    dev = sb.DeviceRng(seed=13)
+    f = sb.Rosenbrock()
+    sb.init_logprob(f, ens, lp, dev)
+    param = sb.TWalkParams.new(6).with_pphi(0.5)
+    for _ in range(niter):
+        sb.twalk.sample(f, (ens, lp), param, dev, [1.0, 0.5], 4)
+    got = [ln.split() for ln in out if ln.startswith("T ")]
+    assert len(got) == 16
+    for i, t in enumerate(got):
+        assert (float(t[2]), float(t[3]), float(t[4])) == (ens[i, 0], ens[i, 5], lp[i])
     assert "C 2" in out and "D 4" in out  # NWalkersIsNotEven, BetaNotInDecrOrd
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from tests.test_parity_gpu import _params_for
-from tests.util import assert_lp_close
+from tests.util import assert_lp_close, twalk_golden_files
 
 pytestmark = pytest.mark.gpu
 
@@ -25,6 +25,24 @@ CASES = [
     (0, [0.5], 1024, 128, 1, (-1, 1)),
     (2, [], 34, 3, 17, (0.9, 1.1)),         # two walkers per rung
 ]
+
+
+@pytest.mark.parametrize("path", twalk_golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_fixed_stream(sb, path):
+    g = np.load(path)
+    kind, params, beta = int(g["kind"]), g["params"], g["beta"]
+    n, dim = g["ens0"].shape
+    tw = sb.TWalkParams(g["tw"][0], g["tw"][1], g["tw"][2], (g["tw"][3], g["tw"][4]))
+    with sb.Sampler(sb.LogProb(kind, tuple(params.tolist())), n, dim, seed=0) as s:
+        s.upload(np.ascontiguousarray(g["ens0"]), np.ascontiguousarray(g["lp0"]))
+        for k in range(g["order"].shape[0]):
+            for half in (0, 1):
+                acc = s.twalk_half_fixed(tw, beta, g["order"][k], half, g["kernel"][k, half], g["b"][k, half],
+                                         g["flags"][k, half], g["walk_u"][k, half], g["u"][k, half])
+                ens, lp = s.download()
+                assert np.array_equal(acc, g["accepted"][k, half]), f"accept mask differs at step {k} half {half}"
+                assert np.array_equal(ens, g["ens"][k, half]), f"positions differ at step {k} half {half}"
+                assert_lp_close(kind, params, ens, lp, g["lp"][k, half], exact=False)
 
 
 def _start(oracle, kind, params, n, dim, box, g):

@@ -11,7 +11,12 @@ EXACT_KINDS = {0, 1, 2, 6}
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """stretch-move vectors (the t-walk's are twalk_*.npz)"""
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith("twalk_"))
+
+
+def twalk_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "twalk_*.npz")))
 
 
 def lp_scale(kind, params, ens):
