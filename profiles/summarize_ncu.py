@@ -4,6 +4,7 @@ under profiles/.  Usage, from the repo root (needs `ncu` on PATH, no GPU):
 
   python profiles/summarize_ncu.py full  gpurun_out/prof_r1_c5_reg_final.ncu-rep c5 "<command line profiled>"
   python profiles/summarize_ncu.py list  gpurun_out/launches_r1_c5.csv c5 "<command line profiled>"
+  python profiles/summarize_ncu.py full  gpurun_out/prof_twalk_c5b.ncu-rep c5 "<command>" twalk   (other kernels: a tag)
 
 `full` writes profiles/r1_<wl>_step_reg_ncu_summary.txt and profiles/traffic_<wl>.json (the DRAM bytes
 bench.py reports as roofline.traffic); `list` writes profiles/r1_<wl>_launch_list_summary.csv (per-kernel
@@ -33,7 +34,7 @@ def to_bytes(unit, value):
     return float(value) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
 
 
-def full(rep, wl, cmd):
+def full(rep, wl, cmd, tag="step_reg"):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -54,7 +55,7 @@ def full(rep, wl, cmd):
         lines.append("")
         lines.append(f"SASS: {len(data)} instructions; executed warp-instructions {tot}; top opcodes (share):")
         lines.append("  " + ", ".join(f"{op} {c / tot:.3f}" for op, c in mix.most_common(14)))
-    out = os.path.join(ROOT, "profiles", f"r1_{wl}_step_reg_ncu_summary.txt")
+    out = os.path.join(ROOT, "profiles", f"r1_{wl}_{tag}_ncu_summary.txt")
     open(out, "w").write(f"{cmd}\n(B200, round 1, one launch = one step; times under ncu are not bench values)\n\n"
                          + "\n".join(lines) + "\n")
     rd, wr = to_bytes(*m["dram__bytes_read.sum"]), to_bytes(*m["dram__bytes_write.sum"])
@@ -62,7 +63,8 @@ def full(rep, wl, cmd):
                "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                "algorithmic_bytes_per_launch": ALG_BYTES.get(wl),
                "note": "rejected rows are not written back, so traffic can be below the algorithmic figure"},
-              open(os.path.join(ROOT, "profiles", f"traffic_{wl}.json"), "w"), indent=1)
+              open(os.path.join(ROOT, "profiles", f"traffic_{wl}.json" if tag == "step_reg" else f"traffic_{wl}_{tag}.json"), "w"),
+              indent=1)
     print(out, f"read {rd / 1e9:.3f} GB write {wr / 1e9:.3f} GB")
 
 
@@ -86,4 +88,7 @@ def launch_list(path, wl, cmd):
 if __name__ == "__main__":
     mode, path, wl = sys.argv[1:4]
     cmd = sys.argv[4] if len(sys.argv) > 4 else ""
-    (full if mode == "full" else launch_list)(path, wl, cmd)
+    if mode == "full":
+        full(path, wl, cmd, sys.argv[5] if len(sys.argv) > 5 else "step_reg")
+    else:
+        launch_list(path, wl, cmd)

@@ -1537,6 +1537,7 @@ static int twalk_common(scorus_ctx *ctx, const scorus_twalk_params *tw, const do
     tp->fw0 = tw->fw[0];
     tp->fw1 = tw->fw[1];
     tp->kernel_in = nullptr; tp->b_in = nullptr; tp->walk_u_in = nullptr;
+    tp->l2_keep = (uint32_t)env_int("SCORUS_TWALK_L2", 1);
     StepParams &p = tp->s;
     p.flag_kind = SCORUS_UFS_PROB;
     p.flag_bits = flag_bits_for(tw->pphi);

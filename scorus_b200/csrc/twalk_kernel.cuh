@@ -40,7 +40,25 @@ struct TwalkParams {
     uint64_t order_step;        // counter whose matching both half-passes share
     uint32_t half;              // the member of each pair that moves (position parity): 0, 1, or 2 = 0 then 1
                                 // fused, the second keyed by step counter s.step + 1
+    uint32_t l2_keep;           // fused mode, L2 policy of the first read of a row (it is read again ~20 us later):
+                                // 1 evict_last, 2 evict_normal, 0 no hint (SCORUS_TWALK_L2)
 };
+
+// 128-bit streaming load with an explicit L2 eviction policy.  The plain L1::no_allocate load is treated as
+// evict_first by L2 (ncu: lts__t_sectors_srcunit_tex_op_read_evict_first_*), right for rows read once and
+// wrong for the fused kernel's first read, whose second read then misses.
+__device__ __forceinline__ double2 ld_stream_hint(const double2 *p, uint64_t policy)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p), "l"(policy));
+    return v;
+}
+
+#ifndef SCORUS_TW_ROWS
+#define SCORUS_TW_ROWS 4
+#endif
 
 // sim_b (:306-322) from its two uniforms
 __device__ __forceinline__ double twalk_b(double x, double v, double at)
@@ -52,8 +70,10 @@ __device__ __forceinline__ double twalk_b(double x, double v, double at)
 template <class Plugin, int G, int ITERS>
 __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twalk_half_kernel(const TwalkParams tp)
 {
-    using Geo = RegGeom<G, ITERS>;
-    constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;
+    // rows per software-pipeline block: SCORUS_TW_ROWS (default 4 = two pairs) keeps the unrolled pair loop, and
+    // with it the per-tile instruction footprint, small enough for the 32 KB L1.5 instruction cache
+    constexpr int kWant = SCORUS_TW_ROWS / ITERS < 2 ? 2 : SCORUS_TW_ROWS / ITERS;
+    constexpr int GB = G < kWant ? G : kWant, PB = GB / 2, NB = G / GB;
     const StepParams &p = tp.s;
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -85,16 +105,26 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
         if (r != key_rung) { K = bij_keys(p.seed, tp.order_step, ST_PERM, r + p.rung_off); key_rung = r; }
         return r * p.npb + bij(pos - r * p.npb, p.npb, p.bij_bits, K);
     };
-    auto load_block = [&](double2 (&x)[GB][ITERS], uint32_t wt, int blk) {
+    uint64_t pol_keep = 0, pol_drop = 0;
+    if (both && tp.l2_keep) {
+        if (tp.l2_keep == 1u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
+    }
+    const bool hinted = both && tp.l2_keep != 0u;
+    // loads block `blk` of a tile for half-pass h: x[2k] = the moving member of pair k, x[2k+1] = its partner
+    auto load_block = [&](double2 (&x)[GB][ITERS], uint32_t wt, int blk, uint32_t h) {
+        const uint64_t pol = h == 0u ? pol_keep : pol_drop;  // fused mode: the rows come back for half-pass 1
 #pragma unroll
         for (int i = 0; i < GB; ++i) {
-            const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
+            const uint32_t wl = grp * G + ((uint32_t)(blk * GB + i) ^ h);
             const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
             const double2 *src = reinterpret_cast<const double2 *>(p.ens + (size_t)row * p.pitch);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t c = (uint32_t)it * G + j;
-                x[i][it] = ld_stream(src + (c < nvec ? c : nvec - 1u));
+                const double2 *q = src + (c < nvec ? c : nvec - 1u);
+                x[i][it] = hinted ? ld_stream_hint(q, pol) : ld_stream(q);
             }
         }
     };
@@ -118,7 +148,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
     const uint64_t my_step = p.step + (both ? my_half : 0u);
     double lp_old = act && lane_in ? __ldg(p.lp + w) : 0.0;
     double2 xn[GB][ITERS];
-    load_block(xn, w, 0);
+    load_block(xn, w, 0, h_begin);
 
     for (;;) {
         const bool mv = act && lane_in;
@@ -165,7 +195,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
         for (uint32_t half = h_begin; half < h_end; ++half) {
             // fused second half-pass: the partner is the first half-pass's mover, at its NEW position
             const bool second = both && half == 1u;
-            double tot[Plugin::kAcc], tot_eq = 0.0;
+            double tot[Plugin::kAcc];
+            bool my_eq = false;  // all_different (:226-240) failed for the pair this lane moves in
 #pragma unroll
             for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
 
@@ -176,11 +207,11 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                 for (int i = 0; i < GB; ++i)
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
-                if (blk + 1 < NB) load_block(xn, w, blk + 1);
-                else if (half + 1u < h_end) load_block(xn, w, 0);  // the same tile again (old rows, from L2)
-                else if (tile_n < ntiles) load_block(xn, w_n, 0);
+                if (blk + 1 < NB) load_block(xn, w, blk + 1, half);
+                else if (half + 1u < h_end) load_block(xn, w, 0, half + 1u);  // the same tile again (old rows, from L2)
+                else if (tile_n < ntiles) load_block(xn, w_n, 0, h_begin);
 
-                double acc[Plugin::kAcc][GB], acc_eq[GB];
+                double acc[Plugin::kAcc][GB];
 #pragma unroll
                 for (int pr = 0; pr < PB; ++pr) {
                     const uint32_t wm = grp * G + (uint32_t)(blk * GB + 2 * pr) + half, wp = wm ^ 1u;  // tile rows: mover, partner
@@ -191,13 +222,13 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                     double2 *rowm = reinterpret_cast<double2 *>(ytile + wm * p.row_stride);
                     double2 *rowp = reinterpret_cast<double2 *>(ytile + wp * p.row_stride);
                     double2 y[ITERS];
-                    double eq = 0.0;
+                    bool eq = false;
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) {
                         const uint32_t c = (uint32_t)it * G + j;
                         const uint32_t d = 2u * c;
-                        const double2 xm = half ? xc[2 * pr + 1][it] : xc[2 * pr][it];
-                        double2 xp = half ? xc[2 * pr][it] : xc[2 * pr + 1][it];
+                        const double2 xm = xc[2 * pr][it];
+                        double2 xp = xc[2 * pr + 1][it];
                         // its accepted proposal is still in the tile (and on its way to global memory)
                         if (moved_p && c < nvec) xp = rowp[c];
                         const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
@@ -229,8 +260,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                                 if (!second) rowp[c] = xp;  // the tile evaluation reads all 32 rows
                             }
                             // all_different(yp, x) :226-240, x = the partner
-                            if (y[it].x == xp.x) eq += 1.0;
-                            if (d + 1u < p.dim && y[it].y == xp.y) eq += 1.0;
+                            eq = eq || y[it].x == xp.x || (d + 1u < p.dim && y[it].y == xp.y);
                         }
                     }
                     double pa[Plugin::kAcc];
@@ -253,12 +283,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                         }
                     }
 #pragma unroll
-                    for (int a = 0; a < Plugin::kAcc; ++a) {
-                        acc[a][2 * pr] = half ? 0.0 : pa[a];
-                        acc[a][2 * pr + 1] = half ? pa[a] : 0.0;
-                    }
-                    acc_eq[2 * pr] = half ? 0.0 : eq;
-                    acc_eq[2 * pr + 1] = half ? eq : 0.0;
+                    for (int a = 0; a < Plugin::kAcc; ++a) { acc[a][2 * pr] = pa[a]; acc[a][2 * pr + 1] = 0.0; }
+                    // the G lanes of a group cover the mover's row, and the mover's own lane is one of them
+                    const uint32_t any_eq = __ballot_sync(0xffffffffu, eq) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u) << (grp * G));
+                    if (lane == wm && any_eq) my_eq = true;
                 }
                 if constexpr (!Plugin::kNeedsRow) {
 #pragma unroll
@@ -269,12 +297,11 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                         if ((int)(j / GB) == blk) tot[a] = r;
                     }
                 }
-                {
-                    double r = transpose_reduce<GB>(acc_eq, lane);
+            }
+            // the totals of pair k sit on the lane of its first member; in half-pass 1 the second member moves
+            if (half) {
 #pragma unroll
-                    for (int h = GB; h < G; h <<= 1) r += __shfl_xor_sync(0xffffffffu, r, h);
-                    if ((int)(j / GB) == blk) tot_eq = r;
-                }
+                for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = __shfl_xor_sync(0xffffffffu, tot[a], 1);
             }
             fence_proxy_async();
             __syncwarp();
@@ -288,7 +315,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                 lp_new = plug.finish_acc(tot);
             }
             const bool mine = act && my_half == half;
-            const double a_acc = (nphi == 0u || tot_eq > 0.0) ? 0.0 : exp((lp_new - lp_old) * beta + lb);
+            const double a_acc = (nphi == 0u || my_eq) ? 0.0 : exp((lp_new - lp_old) * beta + lb);
             const bool acc_now = mine && (u < a_acc);
             if (acc_now) {
                 bulk_store(p.ens + (size_t)w * p.pitch, smem_u32(own_b), p.row_bytes);
