@@ -192,6 +192,37 @@ int scorus_twalk_sample_host(scorus_ctx *ctx, double *ensemble, double *logprob,
  * pow(); exposed so that a device-stream run can be replayed exactly through scorus_twalk_half_fixed) */
 int scorus_twalk_draw_b(scorus_ctx *ctx, double at, uint64_t step, size_t count, double *out);
 
+/* ---- ensemble / parallel-tempering Hamiltonian Monte Carlo, src/mcmc/hmc/naive.rs ----
+ * HmcParam (:17-56): after an accepted step epsilon of the rung grows by (1 + adj_factor) with probability
+ * 1 - target_accept_ratio, after a rejected one it shrinks by the same factor with probability
+ * target_accept_ratio (:269-283).  quick_adj = {t, 0.01}, slow_adj = {t, 1e-6}, fixed = {t, 0}, default {0.99, 1e-6}. */
+typedef struct scorus_hmc_param {
+    double target_accept_ratio, adj_factor;
+} scorus_hmc_param;
+/* sample_ensemble_pt (:122-292) on the resident ensemble, nsteps times: fresh N(0, 1) momenta, l leapfrog steps
+ * (src/mcmc/hmc/utils.rs:6-30) of size epsilon[rung] under the tempered force beta * grad(logprob), accept with
+ * exp(beta (lp' - lp) + K - K') when that is finite.  The gradient -- the reference's second closure, grad_logprob --
+ * belongs to the log-density plugin (Gaussian, bounded Gaussian, Rosenbrock, Rastrigin have one; the others answer
+ * SCORUS_ERR_INVALID_ARG) and is recomputed from q0 at entry, as sample_ensemble_pt does (:139).  epsilon[nbeta] is
+ * in/out (host): for rungs of up to 4096 walkers it is updated exactly as the reference's sequential accept loop
+ * would (bit-identical); for larger rungs the same factors are applied at once, epsilon (1 + adj_factor)^(grown -
+ * shrunk), within n/nbeta * 2^-53 relative of the sequential result.  accepted_cnt[nbeta] (the reference's return
+ * value) may be NULL.  Walkers need not pair up (any n divisible by nbeta).  Synchronous. */
+int scorus_hmc_sample_ensemble_pt(scorus_ctx *ctx, double *epsilon, const double *beta_list, size_t nbeta, size_t l,
+                                  const scorus_hmc_param *param, uint64_t *accepted_cnt, uint64_t nsteps);
+/* one step with the draws supplied: p0[n][dim] momenta (:182-192), u1[n] accept uniforms (:269), u2[n] adaptation
+ * uniforms (:275 / :280); accepted_out[n] may be NULL */
+int scorus_hmc_sample_ensemble_pt_fixed(scorus_ctx *ctx, double *epsilon, const double *beta_list, size_t nbeta, size_t l,
+                                        const scorus_hmc_param *param, const double *p0, const double *u1,
+                                        const double *u2, uint8_t *accepted_out, uint64_t *accepted_cnt);
+/* sample_ensemble_pt on caller-owned host buffers (q0: &mut [V], lp: &mut [T]): upload, one step, download */
+int scorus_hmc_sample_ensemble_pt_host(scorus_ctx *ctx, double *q0, double *logprob, size_t logprob_len, double *epsilon,
+                                       const double *beta_list, size_t nbeta, size_t l, const scorus_hmc_param *param,
+                                       uint64_t *accepted_cnt);
+/* the device stream's momenta of walkers [0, count) at step counter `step`, out[count][dim] (they go through
+ * log / sqrt / sincos; exposed so that a device-stream run can be replayed exactly through the _fixed entry point) */
+int scorus_hmc_draw_momenta(scorus_ctx *ctx, uint64_t step, size_t count, double *out);
+
 /* ---- periphery of the path ----
  * get_one_init_realization, src/mcmc/init_ensemble.rs:19-32, for every walker on the device:
  * x[d] ~ U[lo[d], hi[d]) from the device stream; runs init_logprob if a log-density is registered. */

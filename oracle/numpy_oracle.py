@@ -235,3 +235,88 @@ def twalk_half_fixed(kind, params, ens, lp, beta, aw, order, half, kernel, b, fl
             lp[mover[k]] = ylp[k]
             acc[k] = 1
     return ens, lp, acc
+
+
+# ------------------------------------------------------------------------------------------------
+# ensemble / parallel-tempering HMC, src/mcmc/hmc/naive.rs + utils.rs (second restatement of oracle/hmc.c)
+# ------------------------------------------------------------------------------------------------
+def grad_logprob(kind: int, params, x: np.ndarray) -> np.ndarray:
+    """Gradient of the plugin's log-density at the rows of x[n, d] (formulas of oracle/hmc.c, the Rosenbrock one
+    from the reference's example closure, examples/test_hmc.rs:27-37)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, d = x.shape
+    p = np.asarray(params if params is not None else [], dtype=np.float64).ravel()
+    if kind == 0:
+        c = p[0] if p.size else 0.5
+        return (-2.0 * c) * x
+    if kind == 1:
+        return -2.0 * x
+    if kind == 2:
+        g = np.zeros_like(x)
+        for j in range(d):
+            r = np.zeros(n)
+            if j >= 1:
+                r = r - (200.0 * (x[:, j] - x[:, j - 1] * x[:, j - 1])) * 1.0
+            if j + 1 < d:
+                r = r - ((200.0 * (x[:, j + 1] - x[:, j] * x[:, j])) * (0.0 - 2.0 * x[:, j]) + 2.0 * (x[:, j] - 1.0))
+            g[:, j] = r
+        return g
+    if kind == 3:
+        a = p[0] if p.size else 10.0
+        two_pi = 2.0 * 3.14159265358979323846
+        k = two_pi * a
+        s = k * _vmath(math.sin, two_pi * x)
+        return (0.0 - s) - 2.0 * x
+    raise ValueError("plugin without a gradient")
+
+
+def _kinetic(p):
+    s = np.zeros(p.shape[0])
+    for j in range(p.shape[1]):     # p.dot(p): left to right
+        s = s + p[:, j] * p[:, j]
+    return s / 2.0 * 1.0
+
+
+def hmc_ensemble_pt_fixed(kind, params, q0, lp, epsilon, beta, l, target, adj, p0, u1, u2):
+    """sample_ensemble_pt (naive.rs:122-292) with supplied draws.  Returns (q, lp, epsilon, accepted[n], cnt[nbeta])."""
+    q0 = np.array(q0, dtype=np.float64)
+    lp = np.array(lp, dtype=np.float64)
+    epsilon = np.array(epsilon, dtype=np.float64)
+    beta = np.asarray(beta, dtype=np.float64)
+    n, d = q0.shape
+    npb = n // len(beta)
+    b = beta[np.arange(n) // npb][:, None]
+    e = epsilon[np.arange(n) // npb][:, None]
+    q, p = q0.copy(), np.array(p0, dtype=np.float64)
+    k0 = _kinetic(p)
+    lhq = grad_logprob(kind, params, q) * (-1.0 * b)               # :201-205 (gradient recomputed at entry, :139)
+    he = e * 0.5
+    for _ in range(l):                                              # leapfrog, utils.rs:17-29
+        p = p - lhq * he
+        q = q + (p * 1.0) * e
+        lhq = grad_logprob(kind, params, q) * (0.0 - b)
+        p = p - lhq * he
+    pu = -logprob(kind, params, q)
+    k1 = _kinetic(p)
+    with np.errstate(invalid="ignore", over="ignore"):
+        dh = b[:, 0] * (-lp - pu) + k0 - k1                         # :250
+    acc = np.zeros(n, dtype=np.uint8)
+    cnt = np.zeros(len(beta), dtype=np.uint64)
+    for i in range(n):                                              # accept loop :255-290
+        r = i // npb
+        ok = False
+        if math.isfinite(dh[i]):
+            try:
+                ok = u1[i] < math.exp(dh[i])
+            except OverflowError:
+                ok = True
+        if ok:
+            q0[i] = q[i]
+            lp[i] = -pu[i]
+            acc[i] = 1
+            cnt[r] += 1
+            if u2[i] < 1.0 - target:
+                epsilon[r] = epsilon[r] * (1.0 + adj)
+        elif u2[i] < target:
+            epsilon[r] = epsilon[r] / (1.0 + adj)
+    return q0, lp, epsilon, acc, cnt

@@ -27,7 +27,7 @@ ERR_LENGTH_MISMATCH, ERR_INVALID_ARG, ERR_NPHI_ZERO = 5, 6, 7
 
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so with the committed Makefile (gcc, no FMA contraction)."""
-    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "chain_stats.c", "twalk.c", "scorus_oracle.h", "Makefile"]
+    srcs = ["scorus_oracle.c", "philox_streams.c", "ref_structure_bench.c", "chain_stats.c", "twalk.c", "hmc.c", "scorus_oracle.h", "Makefile"]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
@@ -117,6 +117,9 @@ def lib() -> C.CDLL:
         L.orc_twalk_sample.argtypes = [ci, dp, sz, dp, dp, sz, sz, C.c_void_p, C.POINTER(TwalkParams), dp, sz]
         L.orc_philox_twalk_streams.argtypes = [u64, u64, u64, sz, sz, sz, C.POINTER(TwalkParams), ci, u32p, u8p, dp,
                                                u8p, dp, dp]
+        L.orc_grad_logprob.argtypes = [ci, dp, sz, dp, sz, dp]
+        L.orc_hmc_ensemble_pt_fixed.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, dp, sz, sz, dbl, dbl, dp, dp, dp, u8p, u64p]
+        L.orc_hmc_ensemble_pt.argtypes = [ci, dp, sz, dp, dp, sz, sz, C.c_void_p, dp, dp, sz, sz, dbl, dbl, u64p]
         L.orc_trace_iat.restype = None
         L.orc_trace_iat.argtypes = [dp, sz, sz, dbl, sz, dp, u32p, dp, dp, dp]
         L.orc_running_moments.restype = None
@@ -350,6 +353,52 @@ def philox_twalk_streams(seed, step, order_step, n, dim, nbeta, tw, half):
     if rc:
         raise ValueError(f"orc_philox_twalk_streams rc={rc}")
     return order, kernel, b, flags, walk_u, u
+
+
+def grad_logprob(kind, params, x):
+    """Gradient of the plugin's log-density at every row of x[n][dim]."""
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+    p, pp, npar = _params(params)
+    out = np.empty_like(x)
+    for i in range(x.shape[0]):
+        row = np.ascontiguousarray(x[i])
+        g = np.empty(x.shape[1])
+        rc = lib().orc_grad_logprob(kind, pp, npar, _dp(row), x.shape[1], _dp(g))
+        if rc:
+            raise ValueError(f"orc_grad_logprob rc={rc}")
+        out[i] = g
+    return out
+
+
+def hmc_ensemble_pt_fixed(kind, params, q0, lp, epsilon, beta, l, target, adj, p0, u1, u2):
+    """sample_ensemble_pt (naive.rs:122-292) with supplied momenta / uniforms, in place (q0, lp, epsilon);
+    returns (accepted[n], accepted_cnt[nbeta])."""
+    n, dim = q0.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    p0 = np.ascontiguousarray(p0, dtype=np.float64)
+    u1 = np.ascontiguousarray(u1, dtype=np.float64)
+    u2 = np.ascontiguousarray(u2, dtype=np.float64)
+    acc = np.zeros(n, dtype=np.uint8)
+    cnt = np.zeros(beta.shape[0], dtype=np.uint64)
+    rc = lib().orc_hmc_ensemble_pt_fixed(kind, pp, npar, _dp(q0), _dp(lp), n, dim, _dp(epsilon), _dp(beta), beta.shape[0], l,
+                                         target, adj, _dp(p0), _dp(u1), _dp(u2), _u8p(acc),
+                                         cnt.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc:
+        raise ValueError(f"orc_hmc_ensemble_pt_fixed rc={rc}")
+    return acc, cnt
+
+
+def hmc_ensemble_pt(kind, params, q0, lp, rng: Rng, epsilon, beta, l, target, adj):
+    n, dim = q0.shape
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    p, pp, npar = _params(params)
+    cnt = np.zeros(beta.shape[0], dtype=np.uint64)
+    rc = lib().orc_hmc_ensemble_pt(kind, pp, npar, _dp(q0), _dp(lp), n, dim, rng.ptr, _dp(epsilon), _dp(beta), beta.shape[0],
+                                   l, target, adj, cnt.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc:
+        raise ValueError(f"orc_hmc_ensemble_pt rc={rc}")
+    return cnt
 
 
 def trace_iat(trace, c_window=5.0, max_lag=0):

@@ -39,6 +39,11 @@ class TwalkParams(C.Structure):
     _fields_ = [("aw", C.c_double), ("at", C.c_double), ("pphi", C.c_double), ("fw", C.c_double * 2)]
 
 
+class HmcParam(C.Structure):
+    """scorus_hmc_param (include/scorus_b200.h): HmcParam of src/mcmc/hmc/naive.rs:17-23."""
+    _fields_ = [("target_accept_ratio", C.c_double), ("adj_factor", C.c_double)]
+
+
 _lib = None
 
 
@@ -87,6 +92,10 @@ def load() -> C.CDLL:
         "scorus_twalk_half_fixed": (ci, [vp, C.POINTER(TwalkParams), dp, sz, u32p, ci, u8p, dp, u8p, dp, dp, u8p]),
         "scorus_twalk_sample_host": (ci, [vp, dp, dp, sz, C.POINTER(TwalkParams), dp, sz, u64]),
         "scorus_twalk_draw_b": (ci, [vp, dbl, u64, sz, dp]),
+        "scorus_hmc_sample_ensemble_pt": (ci, [vp, dp, dp, sz, sz, C.POINTER(HmcParam), u64p, u64]),
+        "scorus_hmc_sample_ensemble_pt_fixed": (ci, [vp, dp, dp, sz, sz, C.POINTER(HmcParam), dp, dp, dp, u8p, u64p]),
+        "scorus_hmc_sample_ensemble_pt_host": (ci, [vp, dp, dp, sz, dp, dp, sz, sz, C.POINTER(HmcParam), u64p]),
+        "scorus_hmc_draw_momenta": (ci, [vp, u64, sz, dp]),
         "scorus_get_rung_stats": (ci, [vp, sz, u64p, u64p, u64p, u64p]),
         "scorus_moments_enable": (ci, [vp, sz, u64, ci]),
         "scorus_moments_download": (ci, [vp, sz, dp, dp, u64p]),
@@ -127,7 +136,8 @@ EXPORTS = [
     "scorus_sample_pt_host", "scorus_sample_pt_host_n", "scorus_swap_walkers_host", "scorus_init_ensemble", "scorus_mean", "scorus_cov",
     "scorus_trace_enable", "scorus_trace_download", "scorus_trace_stride", "scorus_get_rung_stats",
     "scorus_moments_enable", "scorus_moments_download", "scorus_trace_iat", "scorus_twalk_params_default",
-    "scorus_twalk_sample", "scorus_twalk_half_fixed", "scorus_twalk_sample_host", "scorus_twalk_draw_b", "scorus_set_shard", "scorus_sample_pt_global",
+    "scorus_twalk_sample", "scorus_twalk_half_fixed", "scorus_twalk_sample_host", "scorus_twalk_draw_b", "scorus_hmc_sample_ensemble_pt",
+    "scorus_hmc_sample_ensemble_pt_fixed", "scorus_hmc_sample_ensemble_pt_host", "scorus_hmc_draw_momenta", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
     "scorus_sample_pt_p2p_begin", "scorus_sample_pt_p2p_end", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",

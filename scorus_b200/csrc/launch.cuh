@@ -9,6 +9,7 @@ namespace scorus {
 
 struct StepParams;
 struct TwalkParams;
+struct HmcParams;
 
 enum : int { KERNEL_SEQ = 0, KERNEL_COOP = 1, KERNEL_REG = 2 };
 
@@ -23,7 +24,8 @@ struct Geometry {
     cudaError_t launch_step_##NAME(const StepParams &p, const Geometry &g, bool all_flags, \
                                    cudaStream_t st);                                                     \
     cudaError_t launch_init_##NAME(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);         \
-    cudaError_t launch_twalk_##NAME(const TwalkParams &tp, const Geometry &g, cudaStream_t st);
+    cudaError_t launch_twalk_##NAME(const TwalkParams &tp, const Geometry &g, cudaStream_t st);             \
+    cudaError_t launch_hmc_##NAME(const HmcParams &hp, uint32_t num_sms, cudaStream_t st);
 
 SCORUS_DECLARE_LAUNCHERS(LpGaussian)
 SCORUS_DECLARE_LAUNCHERS(LpBoundedGaussian)
@@ -38,5 +40,6 @@ SCORUS_DECLARE_LAUNCHERS(LpMixture)
 cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st);
 cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
 cudaError_t launch_twalk(int kind, const TwalkParams &tp, const Geometry &g, cudaStream_t st);
+cudaError_t launch_hmc(int kind, const HmcParams &hp, uint32_t num_sms, cudaStream_t st);  // cudaErrorNotSupported: no gradient
 
 }  // namespace scorus

@@ -49,4 +49,19 @@ cudaError_t launch_twalk(int kind, const TwalkParams &tp, const Geometry &g, cud
     }
 }
 
+cudaError_t launch_hmc(int kind, const HmcParams &hp, uint32_t num_sms, cudaStream_t st)
+{
+    switch (kind) {
+    case SCORUS_LP_GAUSSIAN: return launch_hmc_LpGaussian(hp, num_sms, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_hmc_LpBoundedGaussian(hp, num_sms, st);
+    case SCORUS_LP_ROSENBROCK: return launch_hmc_LpRosenbrock(hp, num_sms, st);
+    case SCORUS_LP_RASTRIGIN: return launch_hmc_LpRastrigin(hp, num_sms, st);
+    case SCORUS_LP_BIMODAL2D: return launch_hmc_LpBimodal2d(hp, num_sms, st);
+    case SCORUS_LP_STEP2D: return launch_hmc_LpStep2d(hp, num_sms, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_hmc_LpCorrGaussian(hp, num_sms, st);
+    case SCORUS_LP_MIXTURE: return launch_hmc_LpMixture(hp, num_sms, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace scorus

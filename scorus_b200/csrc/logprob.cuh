@@ -21,6 +21,12 @@
 //   double finish_acc(const double* acc)      // acc = lane-reduced accumulators
 //
 //   static constexpr bool kNeedsRow           // true: finish_row(row) evaluates from the whole row
+//
+// Gradient (hmc_kernel.cuh; replaces the reference's second closure `grad_logprob: &G`,
+// src/mcmc/hmc/naive.rs:124): plugins with kHasGrad provide
+//   void grad2(d, xm1, x0, x1, xp2, hasprev, has1, hasnb, g0, g1)   // d lp / d x[d], d lp / d x[d+1];
+//                                                                   // xm1 = x[d-1], xp2 = x[d+2]
+// with the operation order oracle/hmc.c: orc_grad_logprob states.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -51,6 +57,14 @@ struct LpGaussian {
         if (has1) a[0] -= (y1 * y1) * c;
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return a[0]; }
+    static constexpr bool kHasGrad = true;
+    __device__ __forceinline__ void grad2(uint32_t, double, double x0, double x1, double, bool, bool, bool, double &g0,
+                                          double &g1) const
+    {
+        const double k = -2.0 * c;
+        g0 = k * x0;
+        g1 = k * x1;
+    }
 };
 
 // examples/sample_bimodal.rs:35-44: subtract, then -inf as soon as one |x| exceeds the limit
@@ -83,6 +97,13 @@ struct LpBoundedGaussian {
         }
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return a[1] > 0.0 ? -INFINITY : a[0]; }
+    static constexpr bool kHasGrad = true;  // inside the box; a trajectory that ends outside has lp = -inf and is rejected
+    __device__ __forceinline__ void grad2(uint32_t, double, double x0, double x1, double, bool, bool, bool, double &g0,
+                                          double &g1) const
+    {
+        g0 = -2.0 * x0;
+        g1 = -2.0 * x1;
+    }
 };
 
 // examples/test_emcee.rs:26-32: -sum_i [100 (x[i+1] - x[i]^2)^2 + (1 - x[i])^2]
@@ -119,6 +140,22 @@ struct LpRosenbrock {
         if (hasnb) a[0] += term(y1, nb);
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return -a[0]; }
+    static constexpr bool kHasGrad = true;
+    // the reference's own example closure, examples/test_hmc.rs:27-37, keeping the i that contribute:
+    // g[j] = 0;  i = j-1: g[j] -= 200 (x[j] - x[j-1]^2) * 1;  i = j: g[j] -= 200 (x[j+1] - x[j]^2) (0 - 2 x[j]) + 2 (x[j] - 1)
+    static __device__ __forceinline__ double grad1(double xm, double x, double xn, bool hasprev, bool hasnext)
+    {
+        double r = 0.0;
+        if (hasprev) r -= (200.0 * (x - xm * xm)) * 1.0;
+        if (hasnext) r -= (200.0 * (xn - x * x)) * (0.0 - 2.0 * x) + 2.0 * (x - 1.0);
+        return r;
+    }
+    __device__ __forceinline__ void grad2(uint32_t, double xm1, double x0, double x1, double xp2, bool hasprev, bool has1,
+                                          bool hasnb, double &g0, double &g1) const
+    {
+        g0 = grad1(xm1, x0, x1, hasprev, has1);
+        g1 = grad1(x0, x1, xp2, true, hasnb);
+    }
 };
 
 // examples/sample_rastrigin.rs:17-25: -(n a) + sum [a cos(2 pi x) - x^2]
@@ -150,6 +187,16 @@ struct LpRastrigin {
         if (has1) s[0] += term(a, y1);
     }
     __device__ __forceinline__ double finish_acc(const double *s) const { return base + s[0]; }
+    static constexpr bool kHasGrad = true;  // g = -(2 pi a) sin(2 pi x) - 2 x
+    __device__ __forceinline__ void grad2(uint32_t, double, double x0, double x1, double, bool, bool, bool, double &g0,
+                                          double &g1) const
+    {
+        const double two_pi = 2.0 * 3.14159265358979323846;
+        const double k = two_pi * a;
+        const double s0 = k * sin(two_pi * x0), s1 = k * sin(two_pi * x1);
+        g0 = (0.0 - s0) - 2.0 * x0;
+        g1 = (0.0 - s1) - 2.0 * x1;
+    }
 };
 
 // examples/sample_bimodal.rs:46-54
@@ -158,6 +205,7 @@ struct LpBimodal2d {
     static constexpr int kMaxWarps = 14;
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;  // [0] carries x0, [1] carries x1
+    static constexpr bool kHasGrad = false;
     double lo0, hi0, lo1, hi1, split, mu_a, sg_a, mu_b, sg_b, x0, x1;
     uint32_t dim;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t d)
@@ -204,6 +252,7 @@ struct LpStep2d {
     static constexpr int kMaxWarps = 14;
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;
+    static constexpr bool kHasGrad = false;
     double x0, x1;
     uint32_t dim;
     __device__ __forceinline__ void init(const double *, uint32_t, uint32_t d)
@@ -238,6 +287,7 @@ struct LpMixture {
     static constexpr int kMaxWarps = 14;
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;
+    static constexpr bool kHasGrad = false;
     const double *m;
     double s1, s2, q1, q2;
     double den1, den2, c1, c2;  // (2 s) s and D ln s, hoisted out of the per-walker tail (same roundings)
@@ -314,6 +364,7 @@ struct LpCorrGaussian {
     static constexpr int kMaxWarps = 8;  // register kernel: 256 threads -> up to 255 registers for the DMMA accumulators
     static constexpr bool kNeedsNext = false;
     static constexpr int kAcc = 1;
+    static constexpr bool kHasGrad = false;
     const double *mu, *L;
     uint32_t dim;
     bool ok;

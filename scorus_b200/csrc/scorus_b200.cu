@@ -21,6 +21,7 @@
 #include "swap_kernel.cuh"
 #include "tile_common.cuh"
 #include "twalk_kernel.cuh"
+#include "hmc_kernel.cuh"
 
 using namespace scorus;
 
@@ -82,6 +83,9 @@ struct scorus_ctx {
     uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
     double *d_r = nullptr;      size_t r_cap = 0;
     uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
+    int8_t *d_hmc_adapt = nullptr;                              // HMC: step-size adaptation codes, one per walker
+    double *d_hmc_eps = nullptr; size_t hmc_eps_cap = 0;        // ... step size per rung
+    double *d_hmc_p = nullptr; size_t hmc_p_cap = 0;            // ... caller-supplied momenta
     uint8_t *d_tw_kernel = nullptr; size_t tw_kernel_cap = 0;   // t-walk, caller-supplied draws
     double *d_tw_walk = nullptr;    size_t tw_walk_cap = 0;
 
@@ -185,7 +189,7 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     if (!out || !cfg) return SCORUS_ERR_INVALID_ARG;
     *out = nullptr;
     if (cfg->n_walkers == 0) return SCORUS_ERR_NWALKERS_IS_ZERO;
-    if (cfg->n_walkers % 2) return SCORUS_ERR_NWALKERS_IS_NOT_EVEN;
+    // pairing moves (stretch, t-walk) check the parity of a rung per call (scorus_check_sample_args); HMC has no pairs
     if (cfg->dim == 0 || cfg->n_walkers > 0xFFFFFFFFull) return SCORUS_ERR_INVALID_ARG;
     int ndev = scorus_device_count();
     if (ndev <= 0) return SCORUS_ERR_NO_DEVICE;  // no CPU fallback, by design
@@ -245,7 +249,8 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
             if (ctx->peer_lp[q]) cudaIpcCloseMemHandle(ctx->peer_lp[q]);
         }
     void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_stage, ctx->d_stage_lp, ctx->d_part, ctx->d_stat,
-                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace, ctx->d_rung_stats, ctx->d_mom, ctx->d_iat, ctx->d_tw_kernel, ctx->d_tw_walk};
+                   ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace, ctx->d_rung_stats, ctx->d_mom, ctx->d_iat, ctx->d_tw_kernel, ctx->d_tw_walk,
+                   ctx->d_hmc_adapt, ctx->d_hmc_eps, ctx->d_hmc_p};
     for (void *b : p2p)
         if (b) cudaFree(b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1678,6 +1683,139 @@ extern "C" int scorus_twalk_draw_b(scorus_ctx *ctx, double at, uint64_t step, si
                                                                            (uint32_t)count, ctx->d_z);
     ++ctx->launches;
     CU(cudaMemcpyAsync(out, ctx->d_z, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ensemble / parallel-tempering HMC: src/mcmc/hmc/naive.rs:122-292
+// ------------------------------------------------------------------------------------------
+static int hmc_impl(scorus_ctx *ctx, double *epsilon, const double *beta, size_t nbeta, size_t l, const scorus_hmc_param *param,
+                    const double *p0, const double *u1, const double *u2, uint8_t *accepted_out, uint64_t *accepted_cnt,
+                    uint64_t nsteps)
+{
+    if (nbeta == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "nbeta == 0");
+    const size_t n = ctx->n, npb = n / nbeta, dim = ctx->dim;
+    // beta_list[i / n_per_beta] (:222) indexes past the list when the rungs do not divide the ensemble
+    if (npb * nbeta != n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
+    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    if (ctx->pitch > 256) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "HMC keeps a walker's q, p and force in registers: dim <= 256");
+    cudaSetDevice(ctx->device);
+    int rc = upload_beta(ctx, beta, nbeta);
+    if (rc) return rc;
+    HmcParams hp;
+    memset(&hp, 0, sizeof(hp));
+    Geometry g;
+    if ((rc = fill_common(ctx, &hp.s, &g, nbeta))) return rc;
+    if (!ctx->d_hmc_adapt) CU(cudaMalloc(&ctx->d_hmc_adapt, n));
+    if ((rc = ensure(ctx, (void **)&ctx->d_hmc_eps, &ctx->hmc_eps_cap, nbeta * sizeof(double)))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_hmc_eps, epsilon, nbeta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    hp.eps = ctx->d_hmc_eps;
+    hp.adapt_out = ctx->d_hmc_adapt;
+    hp.target_accept_ratio = param->target_accept_ratio;
+    hp.l = (uint32_t)l;
+    StepParams &p = hp.s;
+    if (p0) {  // caller-supplied draws (one step)
+        if (!ctx->d_u) CU(cudaMalloc(&ctx->d_u, n * sizeof(double)));
+        if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, n * sizeof(double)));
+        if (!ctx->d_acc) CU(cudaMalloc(&ctx->d_acc, n));
+        if ((rc = ensure(ctx, (void **)&ctx->d_hmc_p, &ctx->hmc_p_cap, n * dim * sizeof(double)))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_hmc_p, p0, n * dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_u, u1, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_z, u2, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        hp.p_in = ctx->d_hmc_p; p.u_in = ctx->d_u; hp.u2_in = ctx->d_z; p.accepted_out = ctx->d_acc;
+    }
+    // accepted_cnt: the per-rung acceptance counters before and after (single rung: the total)
+    std::vector<unsigned long long> before(nbeta, 0), after(nbeta, 0);
+    unsigned long long *cnt_src = nbeta > 1 ? ctx->d_rung_stats : ctx->d_stats;
+    if (accepted_cnt) {
+        CU(cudaMemcpyAsync(before.data(), cnt_src, nbeta * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    for (uint64_t s = 0; s < nsteps; ++s) {
+        p.step = ctx->step;
+        cudaError_t e = launch_hmc(ctx->lp_kind, hp, (uint32_t)ctx->num_sms, ctx->stream);
+        if (e == cudaErrorNotSupported) return fail(ctx, SCORUS_ERR_INVALID_ARG, "this log-density plugin has no gradient");
+        if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "hmc launch: %s", cudaGetErrorString(e));
+        ++ctx->launches;
+        if (param->adj_factor != 0.0) {  // HmcParam::fixed: epsilon * 1 and epsilon / 1 change nothing
+            if (npb <= kHmcExactAdapt)
+                hmc_adapt_kernel<<<(unsigned)((nbeta + 63) / 64), 64, 0, ctx->stream>>>(ctx->d_hmc_adapt, (uint32_t)npb, (uint32_t)nbeta,
+                                                                                      param->adj_factor, ctx->d_hmc_eps);
+            else
+                hmc_adapt_count_kernel<<<(unsigned)nbeta, 256, 0, ctx->stream>>>(ctx->d_hmc_adapt, (uint32_t)npb, param->adj_factor,
+                                                                               ctx->d_hmc_eps);
+            ++ctx->launches;
+        }
+        ++ctx->step;
+        if ((rc = after_step(ctx))) return rc;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "hmc launch: %s", cudaGetErrorString(e));
+    count_proposed(ctx, nbeta, npb, 0, n, nsteps);
+    CU(cudaMemcpyAsync(epsilon, ctx->d_hmc_eps, nbeta * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (accepted_out) CU(cudaMemcpyAsync(accepted_out, ctx->d_acc, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (accepted_cnt) CU(cudaMemcpyAsync(after.data(), cnt_src, nbeta * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // epsilon is an in/out host array: the call is synchronous
+    if (accepted_cnt)
+        for (size_t r = 0; r < nbeta; ++r) accepted_cnt[r] = after[r] - before[r];
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_hmc_sample_ensemble_pt(scorus_ctx *ctx, double *epsilon, const double *beta, size_t nbeta, size_t l,
+                                             const scorus_hmc_param *param, uint64_t *accepted_cnt, uint64_t nsteps)
+{
+    if (!ctx || !epsilon || !beta || !param) return SCORUS_ERR_INVALID_ARG;
+    return hmc_impl(ctx, epsilon, beta, nbeta, l, param, nullptr, nullptr, nullptr, nullptr, accepted_cnt, nsteps);
+}
+
+extern "C" int scorus_hmc_sample_ensemble_pt_fixed(scorus_ctx *ctx, double *epsilon, const double *beta, size_t nbeta, size_t l,
+                                                   const scorus_hmc_param *param, const double *p0, const double *u1,
+                                                   const double *u2, uint8_t *accepted_out, uint64_t *accepted_cnt)
+{
+    if (!ctx || !epsilon || !beta || !param || !p0 || !u1 || !u2) return SCORUS_ERR_INVALID_ARG;
+    return hmc_impl(ctx, epsilon, beta, nbeta, l, param, p0, u1, u2, accepted_out, accepted_cnt, 1);
+}
+
+// sample_ensemble_pt on caller-owned host buffers (q0: &mut [V], lp: &mut [T], :125-126)
+extern "C" int scorus_hmc_sample_ensemble_pt_host(scorus_ctx *ctx, double *q0, double *lp, size_t lp_len, double *epsilon,
+                                                  const double *beta, size_t nbeta, size_t l, const scorus_hmc_param *param,
+                                                  uint64_t *accepted_cnt)
+{
+    if (!ctx || !q0 || !lp || !epsilon || !beta || !param) return SCORUS_ERR_INVALID_ARG;
+    if (lp_len != ctx->n) return fail(ctx, SCORUS_ERR_LENGTH_MISMATCH, "assert_eq!(q0.len(), lp.len())");  // :177
+    int rc = scorus_upload(ctx, q0, lp);
+    if (rc) return rc;
+    if ((rc = hmc_impl(ctx, epsilon, beta, nbeta, l, param, nullptr, nullptr, nullptr, nullptr, accepted_cnt, 1))) return rc;
+    return scorus_download(ctx, q0, lp);
+}
+
+// the device stream's momenta of walkers [0, count) at step counter `step` (they go through log / sqrt / sincos;
+// exposed so that a device-stream run can be replayed exactly through scorus_hmc_sample_ensemble_pt_fixed)
+__global__ void hmc_momenta_kernel(uint64_t seed, uint64_t step, uint32_t w_off, uint32_t count, uint32_t dim, double *out)
+{
+    const uint32_t half = (dim + 1u) / 2u;
+    const size_t total = (size_t)count * half;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(g / half), c = (uint32_t)(g - (size_t)w * half);
+        const double2 m = hmc_momentum(seed, step, w + w_off, c);
+        out[(size_t)w * dim + 2u * c] = m.x;
+        if (2u * c + 1u < dim) out[(size_t)w * dim + 2u * c + 1u] = m.y;
+    }
+}
+
+extern "C" int scorus_hmc_draw_momenta(scorus_ctx *ctx, uint64_t step, size_t count, double *out)
+{
+    if (!ctx || !out || count > ctx->n) return SCORUS_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    if (count == 0) return SCORUS_OK;
+    int rc = ensure(ctx, (void **)&ctx->d_hmc_p, &ctx->hmc_p_cap, ctx->n * (size_t)ctx->dim * sizeof(double));
+    if (rc) return rc;
+    hmc_momenta_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(ctx->seed, step, (uint32_t)ctx->w_off, (uint32_t)count,
+                                                                           ctx->dim, ctx->d_hmc_p);
+    ++ctx->launches;
+    CU(cudaMemcpyAsync(out, ctx->d_hmc_p, count * ctx->dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SCORUS_OK;
 }

@@ -428,6 +428,51 @@ class Sampler:
         self._ok(self._lib.scorus_twalk_draw_b(self._ctx, at, step, count, _dp(out)))
         return out
 
+    # -- ensemble / parallel-tempering HMC, src/mcmc/hmc/naive.rs (scorus_b200/hmc.py mirrors the module)
+    def hmc_sample_ensemble_pt(self, epsilon, beta_list, l: int, param, nsteps: int = 1) -> np.ndarray:
+        """sample_ensemble_pt (naive.rs:122-292) on the resident ensemble; `epsilon` (float64 array, one per rung)
+        is updated in place; returns accepted_cnt per rung."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        _check_epsilon(epsilon, beta.size)
+        cnt = np.zeros(beta.size, dtype=np.uint64)
+        self._ok(self._lib.scorus_hmc_sample_ensemble_pt(self._ctx, _dp(epsilon), _dp(beta), beta.size, l, C.byref(param._c()),
+                                                         cnt.ctypes.data_as(C.POINTER(C.c_uint64)), nsteps))
+        return cnt
+
+    def hmc_sample_ensemble_pt_fixed(self, epsilon, beta_list, l: int, param, p0, u1, u2):
+        """One step with supplied momenta p0[n][dim], accept uniforms u1[n] and adaptation uniforms u2[n];
+        returns (accepted[n], accepted_cnt[nbeta])."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        _check_epsilon(epsilon, beta.size)
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        u1 = np.ascontiguousarray(u1, dtype=np.float64)
+        u2 = np.ascontiguousarray(u2, dtype=np.float64)
+        if p0.shape != (self.n, self.dim) or u1.shape != (self.n,) or u2.shape != (self.n,):
+            raise ValueError("p0 must be [n][dim], u1 and u2 [n]")
+        acc = np.zeros(self.n, dtype=np.uint8)
+        cnt = np.zeros(beta.size, dtype=np.uint64)
+        self._ok(self._lib.scorus_hmc_sample_ensemble_pt_fixed(
+            self._ctx, _dp(epsilon), _dp(beta), beta.size, l, C.byref(param._c()), _dp(p0), _dp(u1), _dp(u2),
+            acc.ctypes.data_as(C.POINTER(C.c_uint8)), cnt.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return acc, cnt
+
+    def hmc_sample_ensemble_pt_host(self, q0, lp, epsilon, beta_list, l: int, param) -> np.ndarray:
+        _check_arrays(q0, lp)
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        _check_epsilon(epsilon, beta.size)
+        cnt = np.zeros(beta.size, dtype=np.uint64)
+        self._ok(self._lib.scorus_hmc_sample_ensemble_pt_host(self._ctx, _dp(q0), _dp(lp), lp.shape[0], _dp(epsilon), _dp(beta),
+                                                              beta.size, l, C.byref(param._c()),
+                                                              cnt.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return cnt
+
+    def hmc_draw_momenta(self, step: int, count: Optional[int] = None) -> np.ndarray:
+        """Momenta of walkers [0, count) from the device stream at step counter `step`, [count][dim]."""
+        count = self.n if count is None else count
+        out = np.empty((count, self.dim))
+        self._ok(self._lib.scorus_hmc_draw_momenta(self._ctx, step, count, _dp(out)))
+        return out
+
     # -- sharding (one process per GPU; scorus_b200/distributed.py drives these)
     def set_shard(self, walker_offset: int, rung_offset: int, n_walkers_global: int):
         self._ok(self._lib.scorus_set_shard(self._ctx, walker_offset, rung_offset, n_walkers_global))
@@ -510,6 +555,12 @@ class DeviceRng:
         else:
             s.set_logprob(flogprob)
         return s
+
+
+def _check_epsilon(epsilon, nbeta: int):
+    if not (isinstance(epsilon, np.ndarray) and epsilon.dtype == np.float64 and epsilon.flags.c_contiguous
+            and epsilon.shape == (nbeta,)):
+        raise AssertionError("assert_eq!(epsilon.len(), nbeta): epsilon must be a float64 array with one entry per rung")
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

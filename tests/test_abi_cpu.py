@@ -68,8 +68,8 @@ def test_no_cpu_fallback_without_a_device(sb):
     ctx = C.c_void_p()
     cfg = _lib.Cfg(n_walkers=16, dim=2, device=-1, seed=0, flags=0, reserved=0)
     assert lib.scorus_ctx_create(C.byref(ctx), C.byref(cfg)) == _lib.ERR_NO_DEVICE and not ctx.value
-    cfg = _lib.Cfg(n_walkers=15, dim=2, device=-1, seed=0, flags=0, reserved=0)
-    assert lib.scorus_ctx_create(C.byref(ctx), C.byref(cfg)) == _lib.ERR_NWALKERS_IS_NOT_EVEN
+    cfg = _lib.Cfg(n_walkers=0, dim=2, device=-1, seed=0, flags=0, reserved=0)
+    assert lib.scorus_ctx_create(C.byref(ctx), C.byref(cfg)) == _lib.ERR_NWALKERS_IS_ZERO
 
 
 def test_host_mirror_keeps_reference_signatures(sb):
