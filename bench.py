@@ -178,9 +178,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--move", default="stretch", choices=["stretch", "twalk"],
+    ap.add_argument("--move", default="stretch", choices=["stretch", "twalk", "hmc"],
                     help="stretch = the headline metric (ensemble_sample::sample_pt); twalk = the t-walk move family "
-                         "(twalk::sample, SURVEY 8(f) rank 2) on the same workload, an extra measurement")
+                         "(twalk::sample, SURVEY 8(f) rank 2), hmc = ensemble-PT HMC (hmc::naive::sample_ensemble_pt, rank 3; "
+                         "10 leapfrog steps, fixed step size) on the same workload: extra measurements")
     ap.add_argument("--n-walkers", type=int, default=0, help="experiments only: override the workload's ensemble size")
     ap.add_argument("--global-every", type=int, default=1,
                     help="with --matching global/p2p: whole-ensemble matching every k-th step, shard-local in between")
@@ -202,6 +203,8 @@ def main():
 
     if args.move == "twalk":
         desc += " [move: t-walk, twalk::sample with TWalkParams::new(dim)]"
+    if args.move == "hmc":
+        desc += " [move: HMC, sample_ensemble_pt with l = 10 leapfrog steps, HmcParam::fixed]"
     if args.impl == "reference":
         if args.move != "stretch":
             raise SystemExit("--impl reference times the headline path (--move stretch)")
@@ -275,8 +278,15 @@ def main():
 
     tw = sb.TWalkParams.new(dim)
 
+    hmc_eps = np.full(nbeta if world == 1 else nb_local, {2: 0.002, 3: 0.02}.get(kind, 0.1))
+    hmc_param = sb.HmcParam.fixed(0.8)
+
     def do_steps(count):
-        if args.move == "twalk":
+        if args.move == "hmc":
+            if world > 1:
+                raise SystemExit("--move hmc is a single-GPU measurement")
+            s.hmc_sample_ensemble_pt(hmc_eps, beta, 10, hmc_param, count)
+        elif args.move == "twalk":
             s.twalk_sample(tw, beta, count)
         else:
             s.sample_pt(2.0, spec, beta, count)
@@ -334,13 +344,16 @@ def main():
             api = "ShardedSampler.upload + sample_pt + download (pinned host buffers, one step per call)"
         else:
             def host_step():
-                if args.move == "twalk":
+                if args.move == "hmc":
+                    s.hmc_sample_ensemble_pt_host(h_ens, h_lp, hmc_eps, beta, 10, hmc_param)
+                elif args.move == "twalk":
                     s.twalk_sample_host(h_ens, h_lp, tw, beta)
                 else:
                     s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
             s.download(h_ens, h_lp)
-            api = ("Sampler.twalk_sample_host -> scorus_twalk_sample_host" if args.move == "twalk" else
-                   "Sampler.sample_pt_host -> scorus_sample_pt_host") + " (pinned host buffers in/out, one step per call)"
+            api = {"twalk": "Sampler.twalk_sample_host -> scorus_twalk_sample_host",
+                   "hmc": "Sampler.hmc_sample_ensemble_pt_host -> scorus_hmc_sample_ensemble_pt_host",
+                   "stretch": "Sampler.sample_pt_host -> scorus_sample_pt_host"}[args.move] + " (pinned host buffers in/out, one step per call)"
         host_step()  # warm-up
         torch.cuda.synchronize()
         if dist:
@@ -388,6 +401,8 @@ def main():
     kernel_name = {6: "step_reg_kernel<LpCorrGaussian> (K1 + K3 DMMA tile)"}.get(kind, "step_reg_kernel (K1)")
     if args.move == "twalk":
         kernel_name = "twalk_half_kernel (both half-passes of a t-walk step fused in one launch)"
+    if args.move == "hmc":
+        kernel_name = "hmc_kernel (10 leapfrog steps per walker in registers: bound by fp64 arithmetic, not HBM)"
     traffic = None
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(prof) and args.move == "stretch":

@@ -184,6 +184,16 @@ public:
     {
         check(scorus_twalk_sample_host(ctx_, ens, lp, lp_len, &param, beta.data(), beta.size(), nsteps), ctx_);
     }
+    // ensemble / parallel-tempering HMC, src/mcmc/hmc/naive.rs:122-292 (namespace hmc below mirrors the module)
+    std::vector<size_t> hmc_sample_ensemble_pt_host(double *q0, double *lp, size_t lp_len, std::vector<double> &epsilon,
+                                                    const std::vector<double> &beta, size_t l, const scorus_hmc_param &param)
+    {
+        if (epsilon.size() != beta.size()) throw std::invalid_argument("assert_eq!(epsilon.len(), nbeta)");  // :179
+        std::vector<uint64_t> cnt(beta.size());
+        check(scorus_hmc_sample_ensemble_pt_host(ctx_, q0, lp, lp_len, epsilon.data(), beta.data(), beta.size(), l, &param,
+                                                 cnt.data()), ctx_);
+        return std::vector<size_t>(cnt.begin(), cnt.end());
+    }
     // chain statistics on the device (what the example drivers compute from per-step downloads)
     struct RungStats { std::vector<uint64_t> accepted, proposed, swapped, swap_proposed; };
     RungStats rung_stats(size_t nrungs)
@@ -365,5 +375,36 @@ inline void sample(const LogProb &flogprob, std::pair<detail::Ensemble, std::vec
 }
 
 }  // namespace twalk
+
+namespace hmc {
+namespace naive {
+
+// HmcParam, src/mcmc/hmc/naive.rs:17-56
+struct HmcParam : scorus_hmc_param {
+    HmcParam(double target_accept_ratio_, double adj_factor_) : scorus_hmc_param{target_accept_ratio_, adj_factor_} {}
+    HmcParam() : scorus_hmc_param{0.99, 0.000001} {}                                   // Default, :49-56
+    static HmcParam quick_adj(double t) { return HmcParam(t, 0.01); }                  // :36-38
+    static HmcParam slow_adj(double t) { return HmcParam(t, 0.000001); }               // :40-42
+    static HmcParam fixed(double t) { return HmcParam(t, 0.0); }                       // :44-46
+};
+
+// sample_ensemble_pt, :122-158, in place on the host containers; returns the accepted count per rung.  The
+// gradient (the reference's second closure) is the log-density plugin's own.
+inline std::vector<size_t> sample_ensemble_pt(const LogProb &flogprob, detail::Ensemble &q0, std::vector<double> &lp,
+                                              DeviceRng &rng, std::vector<double> &epsilon,
+                                              const std::vector<double> &beta_list, size_t l, const HmcParam &param)
+{
+    if (q0.empty()) throw McmcError(SCORUS_ERR_NWALKERS_IS_ZERO, "NWalkersIsZero");
+    if (q0.size() != lp.size()) throw std::invalid_argument("assert_eq!(q0.len(), lp.len())");  // :177
+    const size_t dim = q0[0].size();
+    Sampler &s = rng.sampler(flogprob, q0.size(), dim);
+    std::vector<double> flat = detail::flatten(q0, dim);
+    std::vector<size_t> cnt = s.hmc_sample_ensemble_pt_host(flat.data(), lp.data(), lp.size(), epsilon, beta_list, l, param);
+    detail::unflatten(flat, q0, dim);
+    return cnt;
+}
+
+}  // namespace naive
+}  // namespace hmc
 }  // namespace mcmc
 }  // namespace scorus

@@ -36,6 +36,11 @@ pub const SCORUS_UFS_ONE_HOT_CYCLE: i32 = 2;
 pub const SCORUS_UFS_MASK: i32 = 3;
 pub const SCORUS_CFG_SEQUENTIAL_SUM: u32 = 1;
 
+/// HmcParam, src/mcmc/hmc/naive.rs:17-23
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct scorus_hmc_param { pub target_accept_ratio: f64, pub adj_factor: f64 }
+
 /// TWalkParams, src/mcmc/twalk.rs:75-83 (fw cumulative)
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
@@ -106,6 +111,16 @@ extern "C" {
     pub fn scorus_twalk_sample_host(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64, logprob_len: usize,
                                     tw: *const scorus_twalk_params, beta_list: *const f64, nbeta: usize, nsteps: u64) -> c_int;
     pub fn scorus_twalk_draw_b(ctx: *mut scorus_ctx, at: f64, step: u64, count: usize, out: *mut f64) -> c_int;
+    /// ensemble / parallel-tempering HMC, src/mcmc/hmc/naive.rs:122-292
+    pub fn scorus_hmc_sample_ensemble_pt(ctx: *mut scorus_ctx, epsilon: *mut f64, beta_list: *const f64, nbeta: usize,
+                                         l: usize, param: *const scorus_hmc_param, accepted_cnt: *mut u64, nsteps: u64) -> c_int;
+    pub fn scorus_hmc_sample_ensemble_pt_fixed(ctx: *mut scorus_ctx, epsilon: *mut f64, beta_list: *const f64, nbeta: usize,
+                                               l: usize, param: *const scorus_hmc_param, p0: *const f64, u1: *const f64,
+                                               u2: *const f64, accepted_out: *mut u8, accepted_cnt: *mut u64) -> c_int;
+    pub fn scorus_hmc_sample_ensemble_pt_host(ctx: *mut scorus_ctx, q0: *mut f64, logprob: *mut f64, logprob_len: usize,
+                                              epsilon: *mut f64, beta_list: *const f64, nbeta: usize, l: usize,
+                                              param: *const scorus_hmc_param, accepted_cnt: *mut u64) -> c_int;
+    pub fn scorus_hmc_draw_momenta(ctx: *mut scorus_ctx, step: u64, count: usize, out: *mut f64) -> c_int;
     /// one process per GPU: shards of one ensemble
     pub fn scorus_set_shard(ctx: *mut scorus_ctx, walker_offset: u64, rung_offset: u32, n_walkers_global: u64) -> c_int;
     pub fn scorus_sample_pt_global(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, beta_list: *const f64,

@@ -99,6 +99,15 @@ impl Sampler {
         check(unsafe { sys::scorus_twalk_sample_host(self.ctx, ens.as_mut_ptr(), lp.as_mut_ptr(), lp.len(), param,
                                                      beta.as_ptr(), beta.len(), 1) }, self.ctx);
     }
+    pub fn hmc_sample_ensemble_pt_host(&self, q0: &mut [f64], lp: &mut [f64], epsilon: &mut [f64], beta: &[f64], l: usize,
+                                       param: &sys::scorus_hmc_param) -> Vec<usize> {
+        assert_eq!(epsilon.len(), beta.len());   // naive.rs:179
+        let mut cnt = vec![0u64; beta.len()];
+        check(unsafe { sys::scorus_hmc_sample_ensemble_pt_host(self.ctx, q0.as_mut_ptr(), lp.as_mut_ptr(), lp.len(),
+                                                               epsilon.as_mut_ptr(), beta.as_ptr(), beta.len(), l, param,
+                                                               cnt.as_mut_ptr()) }, self.ctx);
+        cnt.into_iter().map(|c| c as usize).collect()
+    }
     pub fn swap_walkers_host(&self, ens: &mut [f64], lp: &mut [f64], beta: &[f64]) {
         check(unsafe { sys::scorus_swap_walkers_host(self.ctx, ens.as_mut_ptr(), lp.as_mut_ptr(), lp.len(),
                                                      beta.as_ptr(), beta.len()) }, self.ctx);
@@ -183,5 +192,35 @@ pub mod twalk {
         let c = sys::scorus_twalk_params { aw: param.aw, at: param.at, pphi: param.pphi, fw: param.fw };
         rng.sampler(flogprob, ensemble.len(), dim).twalk_sample_host(&mut flat, logprob, &c, beta_list);
         unflatten(&flat, ensemble, dim);
+    }
+}
+
+/// `mcmc::hmc::naive`, ensemble entry point (src/mcmc/hmc/naive.rs:122-158)
+pub mod hmc {
+    pub mod naive {
+        use super::super::*;
+
+        /// naive.rs:17-56
+        #[derive(Clone, Copy, Debug)]
+        pub struct HmcParam { pub target_accept_ratio: f64, pub adj_factor: f64 }
+        impl HmcParam {
+            pub fn new(target_accept_ratio: f64, adj_factor: f64) -> Self { Self { target_accept_ratio, adj_factor } }
+            pub fn quick_adj(t: f64) -> Self { Self::new(t, 0.01) }
+            pub fn slow_adj(t: f64) -> Self { Self::new(t, 0.000_001) }
+            pub fn fixed(t: f64) -> Self { Self::new(t, 0.0) }
+        }
+        impl Default for HmcParam { fn default() -> Self { Self::new(0.99, 0.000_001) } }
+
+        /// sample_ensemble_pt: the gradient (the reference's `grad_logprob: &G`) is the plugin's own
+        pub fn sample_ensemble_pt<V>(flogprob: &LogProb, q0: &mut [V], lp: &mut [f64], rng: &mut DeviceRng,
+                                     epsilon: &mut [f64], beta_list: &[f64], l: usize, param: &HmcParam) -> Vec<usize>
+        where V: Clone + IndexableLinearSpace<f64> + Sync + Send {
+            assert_eq!(q0.len(), lp.len());
+            let (mut flat, dim) = flatten(q0);
+            let c = sys::scorus_hmc_param { target_accept_ratio: param.target_accept_ratio, adj_factor: param.adj_factor };
+            let cnt = rng.sampler(flogprob, q0.len(), dim).hmc_sample_ensemble_pt_host(&mut flat, lp, epsilon, beta_list, l, &c);
+            unflatten(&flat, q0, dim);
+            cnt
+        }
     }
 }

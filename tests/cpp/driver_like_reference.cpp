@@ -67,6 +67,23 @@ int main(int argc, char **argv)
         for (int k = 0; k < niter; ++k) twalk::sample(lpf, el, param, rng, blist, 4);
         for (size_t i = 0; i < el.first.size(); ++i) printf("T %zu %.17g %.17g %.17g\n", i, el.first[i][0], el.first[i][ndims - 1], el.second[i]);
     }
+    {   // ensemble-PT HMC: hmc::naive::sample_ensemble_pt(flogprob, grad, q0, lp, rng, epsilon, beta_list, l, param)
+        const size_t nbetas = 2, per = 5, ndims = 4;   // odd rungs: nothing pairs up in HMC
+        std::vector<double> blist = {1.0, 0.5}, epsilon = {0.01, 0.01};
+        std::vector<std::vector<double>> q0(nbetas * per, std::vector<double>(ndims));
+        for (auto &w : q0)
+            for (auto &x : w) x = 0.9 + 0.2 * lcg(st);
+        std::vector<double> lp(q0.size());
+        DeviceRng rng(17);
+        LogProb lpf = LogProb::rosenbrock();
+        ensemble_sample::init_logprob(lpf, q0, lp, rng);
+        hmc::naive::HmcParam param = hmc::naive::HmcParam::quick_adj(0.7);
+        size_t accepted = 0;
+        for (int k = 0; k < niter; ++k)
+            for (size_t c : hmc::naive::sample_ensemble_pt(lpf, q0, lp, rng, epsilon, blist, 3, param)) accepted += c;
+        for (size_t i = 0; i < q0.size(); ++i) printf("H %zu %.17g %.17g %.17g\n", i, q0[i][0], q0[i][ndims - 1], lp[i]);
+        printf("HE %.17g %.17g %zu\n", epsilon[0], epsilon[1], accepted);
+    }
     {   // the reference's panics become exceptions
         std::vector<std::vector<double>> e(6, std::vector<double>(2, 0.1));
         std::vector<double> lp(6, 0.0);

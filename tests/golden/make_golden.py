@@ -119,6 +119,43 @@ def make_twalk(case):
           f"traverse={np.mean(out['kernel']):.2f}")
 
 
+# ensemble-PT HMC (src/mcmc/hmc/naive.rs:122-292): name, kind, params, n, dim, nbeta, l, epsilon, steps, box, seed
+HMC_CASES = [
+    ("hmc_gaussian_d3_pt2", po.LP_GAUSSIAN, [0.5], 14, 3, 2, 5, 1.6, 12, (-1.0, 1.0), 21),
+    ("hmc_rosenbrock_d2", po.LP_ROSENBROCK, [], 9, 2, 1, 2, 0.06, 12, (0.8, 1.2), 22),   # examples/test_hmc.rs shape
+    ("hmc_rosenbrock_d8_pt3", po.LP_ROSENBROCK, [], 24, 8, 3, 3, 0.03, 10, (0.9, 1.1), 23),
+    ("hmc_bounded_gaussian_d3", po.LP_BOUNDED_GAUSSIAN, [1.5], 16, 3, 1, 6, 0.4, 10, (-1.4, 1.4), 24),
+]
+
+
+def make_hmc(case):
+    name, kind, params, n, dim, nb, l, eps0, steps, box, seed = case
+    g = po.Rng(seed)
+    params = np.asarray(params, dtype=np.float64)
+    q = np.array([[box[0] + g.uniform() * (box[1] - box[0]) for _ in range(dim)] for _ in range(n)])
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    lp = po.init_logprob(kind, params, q)
+    eps = np.full(nb, eps0)
+    target, adj = 0.7, 0.01
+    out = dict(kind=kind, params=params, beta=beta, l=l, target=target, adj=adj, q0=q.copy(), lp0=lp.copy(), eps0=eps.copy())
+    keys = ["p0", "u1", "u2", "accepted", "cnt", "q", "lp", "eps"]
+    acc = {k: [] for k in keys}
+    nrm = np.random.default_rng(seed)      # the momenta are inputs: any N(0, 1) draws do
+    for k in range(steps):
+        p0 = nrm.standard_normal((n, dim))
+        u1 = np.array([g.uniform() for _ in range(n)])
+        u2 = np.array([g.uniform() for _ in range(n)])
+        q2, l2, e2, a2, c2 = no.hmc_ensemble_pt_fixed(kind, params, q, lp, eps, beta, l, target, adj, p0, u1, u2)
+        a1, c1 = po.hmc_ensemble_pt_fixed(kind, params, q, lp, eps, beta, l, target, adj, p0, u1, u2)
+        assert np.array_equal(a1, a2) and np.array_equal(c1, c2) and np.array_equal(q, q2), (name, k)
+        assert np.array_equal(lp, l2, equal_nan=True) and np.array_equal(eps, e2), (name, k)
+        for key, v in zip(keys, [p0, u1, u2, a1, c1, q.copy(), lp.copy(), eps.copy()]):
+            acc[key].append(v)
+    out.update({k: np.stack(v) for k, v in acc.items()})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: n={n} dim={dim} nbeta={nb} l={l} steps={steps} accept={np.mean(out['accepted']):.3f} eps={eps}")
+
+
 if __name__ == "__main__":
     po.build()
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -128,3 +165,6 @@ if __name__ == "__main__":
     if which in ("all", "twalk"):
         for c in TWALK_CASES:
             make_twalk(c)
+    if which in ("all", "hmc"):
+        for c in HMC_CASES:
+            make_hmc(c)

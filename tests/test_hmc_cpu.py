@@ -4,6 +4,22 @@ import numpy as np
 import pytest
 
 from oracle import numpy_oracle as no
+from tests.util import hmc_golden_files
+
+
+@pytest.mark.parametrize("path", hmc_golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_vectors_both_restatements(oracle, path):
+    g = np.load(path)
+    kind, params, beta, l = int(g["kind"]), g["params"], g["beta"], int(g["l"])
+    target, adj = float(g["target"]), float(g["adj"])
+    q, lp, eps = g["q0"].copy(), g["lp0"].copy(), g["eps0"].copy()
+    for k in range(g["p0"].shape[0]):
+        q2, l2, e2, a2, c2 = no.hmc_ensemble_pt_fixed(kind, params, q, lp, eps, beta, l, target, adj, g["p0"][k], g["u1"][k], g["u2"][k])
+        acc, cnt = oracle.hmc_ensemble_pt_fixed(kind, params, q, lp, eps, beta, l, target, adj, g["p0"][k], g["u1"][k], g["u2"][k])
+        assert np.array_equal(acc, g["accepted"][k]) and np.array_equal(a2, acc) and np.array_equal(cnt, g["cnt"][k])
+        assert np.array_equal(q, g["q"][k]) and np.array_equal(q2, q)
+        assert np.array_equal(lp, g["lp"][k], equal_nan=True) and np.array_equal(l2, lp, equal_nan=True)
+        assert np.array_equal(eps, g["eps"][k]) and np.array_equal(e2, eps)
 
 
 @pytest.mark.parametrize("kind,params", [(0, [0.5]), (0, [1.0]), (1, [1.5]), (2, []), (3, [10.0])])

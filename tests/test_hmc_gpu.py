@@ -5,7 +5,7 @@ force: Rastrigin), log-probs agree within 1e-12 of their sum of |terms|."""
 import numpy as np
 import pytest
 
-from tests.util import assert_lp_close
+from tests.util import assert_lp_close, hmc_golden_files
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +22,24 @@ CASES = [
     (3, [10.0], 4096, 10, 16, 5, 0.02, (-0.5, 0.5)),
     (1, [1.5], 512, 5, 2, 6, 0.3, (-1.4, 1.4)),    # trajectories that leave the box: lp = -inf, dh not finite
 ]
+
+
+@pytest.mark.parametrize("path", hmc_golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_fixed_stream(sb, path):
+    g = np.load(path)
+    kind, params, beta, l = int(g["kind"]), g["params"], g["beta"], int(g["l"])
+    param = sb.HmcParam.new(float(g["target"]), float(g["adj"]))
+    n, dim = g["q0"].shape
+    eps = g["eps0"].copy()
+    with sb.Sampler(sb.LogProb(kind, tuple(params.tolist())), n, dim, seed=0) as s:
+        s.upload(np.ascontiguousarray(g["q0"]), np.ascontiguousarray(g["lp0"]))
+        for k in range(g["p0"].shape[0]):
+            acc, cnt = s.hmc_sample_ensemble_pt_fixed(eps, beta, l, param, g["p0"][k], g["u1"][k], g["u2"][k])
+            q, lp = s.download()
+            assert np.array_equal(acc, g["accepted"][k]) and np.array_equal(cnt, g["cnt"][k]), f"decisions differ at step {k}"
+            assert np.array_equal(q, g["q"][k]), f"positions differ at step {k}"
+            assert np.array_equal(eps, g["eps"][k]), f"epsilon differs at step {k}"
+            assert_lp_close(kind, params, q, lp, g["lp"][k], exact=False)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}_l{c[5]}")

@@ -284,6 +284,22 @@ def test_cpp_host_layer_matches_python_mirror(sb, tmp_path):
     assert len(got) == 16
     for i, t in enumerate(got):
         assert (float(t[2]), float(t[3]), float(t[4])) == (ens[i, 0], ens[i, 5], lp[i])
+    # H: ensemble-PT HMC through mcmc::hmc::naive::sample_ensemble_pt
+    q0 = np.array([[0.9 + 0.2 * lcg() for _ in range(4)] for _ in range(10)])
+    lp = np.empty(10)
+    dev = sb.DeviceRng(seed=17)
+    f = sb.Rosenbrock()
+    sb.init_logprob(f, q0, lp, dev)
+    eps = np.array([0.01, 0.01])
+    accepted = 0
+    for _ in range(niter):
+        accepted += sum(sb.hmc.sample_ensemble_pt(f, None, q0, lp, dev, eps, [1.0, 0.5], 3, sb.HmcParam.quick_adj(0.7)))
+    got = [ln.split() for ln in out if ln.startswith("H ")]
+    assert len(got) == 10
+    for i, t in enumerate(got):
+        assert (float(t[2]), float(t[3]), float(t[4])) == (q0[i, 0], q0[i, 3], lp[i])
+    he = [ln.split() for ln in out if ln.startswith("HE ")][0]
+    assert (float(he[1]), float(he[2]), int(he[3])) == (eps[0], eps[1], accepted)
     assert "C 2" in out and "D 4" in out  # NWalkersIsNotEven, BetaNotInDecrOrd
 
 

@@ -12,7 +12,12 @@ EXACT_KINDS = {0, 1, 2, 6}
 
 def golden_files():
     """stretch-move vectors (the t-walk's are twalk_*.npz)"""
-    return sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith("twalk_"))
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(f).startswith(("twalk_", "hmc_")))
+
+
+def hmc_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "hmc_*.npz")))
 
 
 def twalk_golden_files():
