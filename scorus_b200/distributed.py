@@ -227,6 +227,19 @@ class ShardedSampler:
             raise NotImplementedError("the t-walk across walker shards supports matching='local' only")
         self.sampler.twalk_sample(param, beta, nsteps)
 
+    def hmc_sample_ensemble_pt(self, epsilon, beta_list: Sequence[float], l: int, param, nsteps: int = 1):
+        """hmc::naive::sample_ensemble_pt (src/mcmc/hmc/naive.rs:122-292) on this rank's shard: walkers are
+        independent, so there is no communication.  Rung shards: `epsilon` is the whole ladder's array, this rank
+        updates (in place) and returns the counts of its own rungs only.  Walker shards of one rung would each adapt
+        their own copy of the rung's step size, so they take a fixed one (`HmcParam.fixed`)."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if self.mode == "rungs":
+            lo, hi = self.rung_off, self.rung_off + self.nb_local
+            return self.sampler.hmc_sample_ensemble_pt(epsilon[lo:hi], beta[lo:hi], l, param, nsteps)
+        if self.world > 1 and param.adj_factor != 0.0:
+            raise NotImplementedError("HMC across walker shards needs a fixed step size (HmcParam.fixed)")
+        return self.sampler.hmc_sample_ensemble_pt(epsilon, beta, l, param, nsteps)
+
     def _barrier(self):
         """Stream-ordered barrier across ranks (a one-element all-reduce: no host synchronisation)."""
         self.dist.all_reduce(self._token, group=self.group)

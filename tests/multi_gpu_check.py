@@ -54,6 +54,40 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
     return bool(flag.item())
 
 
+def run_hmc(world):
+    """Ensemble-PT HMC over rung shards: identical to the single-GPU chain, adapted step sizes included."""
+    rank = dist.get_rank()
+    nbeta, npb, dim, l = 2 * world, 512, 8, 4
+    n = nbeta * npb
+    rng = np.random.default_rng(55)
+    q = np.ascontiguousarray(rng.uniform(0.9, 1.1, (n, dim)))
+    beta = 2.0 ** -(np.arange(nbeta) / 2.0)
+    param = sb.HmcParam.quick_adj(0.7)
+    ref = sb.Sampler(sb.Rosenbrock(), n, dim, seed=31, device=torch.cuda.current_device())
+    ref.upload(q, None)
+    sh = ShardedSampler(sb.Rosenbrock(), n, dim, nbeta=nbeta, seed=31)
+    lo, hi = sh.w_off, sh.w_off + sh.n_local
+    sh.upload(np.ascontiguousarray(q[lo:hi]), None)
+    eps_ref, eps_sh = np.full(nbeta, 0.003), np.full(nbeta, 0.003)
+    for k in range(8):
+        if k % 4 == 0:
+            ref.swap_walkers(beta)
+            sh.swap_walkers(beta)
+        ref.hmc_sample_ensemble_pt(eps_ref, beta, l, param, 1)
+        sh.hmc_sample_ensemble_pt(eps_sh, beta, l, param, 1)
+    want_q, want_lp = ref.download()
+    got_q, got_lp = sh.download()
+    r0, r1 = sh.rung_off, sh.rung_off + sh.nb_local
+    ok = (np.array_equal(got_q, want_q[lo:hi]) and np.allclose(got_lp, want_lp[lo:hi], rtol=1e-12, atol=1e-9)
+          and np.array_equal(eps_sh[r0:r1], eps_ref[r0:r1]) and not np.array_equal(want_q, q))
+    flag = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"hmc_rosenbrock_pt: mode={sh.mode} world={world} n={n} dim={dim} nbeta={nbeta} {'OK' if flag.item() else 'MISMATCH'}", flush=True)
+    ref.close()
+    return bool(flag.item())
+
+
 def run_mixed(world):
     """Whole-ensemble matching every 5th step, shard-local in between: a different (still valid) kernel,
     so it is checked statistically: unit Gaussian in, unit Gaussian out, across all shards."""
@@ -103,6 +137,7 @@ def main():
     ok &= run_case("twalk_rastrigin_pt", sb.Rastrigin(), 2048 * 4 * world, 10, 4 * world, None, 12, 4, (-0.5, 0.5), twalk=True)
     ok &= run_case("twalk_rosenbrock_pt_small_rungs", sb.Rosenbrock(), 64 * 2 * world, 20, 2 * world, None, 12, 3, (0.9, 1.1),
                    twalk=True)
+    ok &= run_hmc(world)
     ok &= run_mixed(world)
     dist.barrier()
     dist.destroy_process_group()
