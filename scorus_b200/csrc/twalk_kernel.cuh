@@ -174,6 +174,41 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
         const double beta = __ldg(p.beta + (act ? w / p.npb : 0u));
         __syncwarp();
 
+        // sim_walk's z (:289-296) of a walker's flagged coordinates, computed by the walker's own lane (one Philox call
+        // per flagged chunk: a handful per walker) and parked in the walker's row of the y tile, where the proposal loop
+        // picks them up before it overwrites the row with y.  Doing this in the loop instead costs a Philox call per
+        // pair and trip for the whole warp (19 % of the kernel's instructions).
+        auto scatter_walk_z = [&](bool mine_now) {
+            if (mine_now && kern == 0u) {
+                double *row = reinterpret_cast<double *>(ytile + lane * p.row_stride);
+                for (uint32_t wd = 0; wd < p.flag_words; ++wd) {
+                    uint32_t bits = flagw[wd * 32u + lane];
+                    while (bits) {
+                        const uint32_t sh = (uint32_t)(__ffs((int)bits) - 1) & ~1u;  // the chunk's even coordinate, within the word
+                        const uint32_t d0 = wd * 32u + sh, two = (bits >> sh) & 3u;
+                        double u0, u1;
+                        if (tp.walk_u_in) {
+                            const double *wu = tp.walk_u_in + (size_t)w * p.dim + d0;
+                            u0 = __ldg(wu);
+                            u1 = d0 + 1u < p.dim ? __ldg(wu + 1) : 0.0;
+                        } else {
+                            const U4 r = draw(p.seed, my_step, ST_TW_WALK, w + p.w_off, d0 >> 1);
+                            u0 = u53(r.x, r.y);
+                            u1 = u53(r.z, r.w);
+                        }
+                        if (two & 1u) row[d0] = tp.aw_ratio * (tp.aw * (u0 * u0) + 2.0 * u0 - 1.0);
+                        if (two & 2u) row[d0 + 1u] = tp.aw_ratio * (tp.aw * (u1 * u1) + 2.0 * u1 - 1.0);
+                        bits &= ~(3u << sh);
+                    }
+                }
+            }
+        };
+        // dense targets rewrite the partner's row during a half-pass (tile evaluation), so their z go in per half-pass
+        if constexpr (!Plugin::kNeedsRow) {
+            scatter_walk_z(mv);
+            __syncwarp();
+        }
+
         uint32_t tile_n = tile + nwarps;
         if (p.tile_counter) {
             unsigned long long t = 0;
@@ -195,6 +230,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
         for (uint32_t half = h_begin; half < h_end; ++half) {
             // fused second half-pass: the partner is the first half-pass's mover, at its NEW position
             const bool second = both && half == 1u;
+            if constexpr (Plugin::kNeedsRow) {
+                scatter_walk_z(act && my_half == half);
+                __syncwarp();
+            }
             double tot[Plugin::kAcc];
             bool my_eq = false;  // all_different (:226-240) failed for the pair this lane moves in
 #pragma unroll
@@ -217,7 +256,6 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                     const uint32_t wm = grp * G + (uint32_t)(blk * GB + 2 * pr) + half, wp = wm ^ 1u;  // tile rows: mover, partner
                     const uint32_t kern_m = __shfl_sync(0xffffffffu, kern, wm);
                     const double b_m = __shfl_sync(0xffffffffu, b, wm);
-                    const uint32_t id_m = __shfl_sync(0xffffffffu, w, wm);
                     const bool moved_p = __shfl_sync(0xffffffffu, (uint32_t)accept, wp) != 0u && second;
                     double2 *rowm = reinterpret_cast<double2 *>(ytile + wm * p.row_stride);
                     double2 *rowp = reinterpret_cast<double2 *>(ytile + wp * p.row_stride);
@@ -234,19 +272,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twa
                         const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
                         const uint32_t f = c < nvec ? flagw[wd * 32u + wm] >> (d & 31u) : 0u;
                         double z0 = 0.0, z1 = 0.0;
-                        if (kern_m == 0u && (f & 3u)) {  // sim_walk :289-296
-                            double u0, u1;
-                            if (tp.walk_u_in) {
-                                const double *wu = tp.walk_u_in + (size_t)id_m * p.dim + d;
-                                u0 = __ldg(wu);
-                                u1 = d + 1u < p.dim ? __ldg(wu + 1) : 0.0;
-                            } else {
-                                const U4 r = draw(p.seed, p.step + (both ? half : 0u), ST_TW_WALK, id_m + p.w_off, c);
-                                u0 = u53(r.x, r.y);
-                                u1 = u53(r.z, r.w);
-                            }
-                            if (f & 1u) z0 = tp.aw_ratio * (tp.aw * (u0 * u0) + 2.0 * u0 - 1.0);
-                            if (f & 2u) z1 = tp.aw_ratio * (tp.aw * (u1 * u1) + 2.0 * u1 - 1.0);
+                        if (kern_m == 0u && (f & 3u)) {  // sim_walk :289-296: z of the flagged coordinates, parked in the row
+                            const double2 zz = rowm[c];
+                            if (f & 1u) z0 = zz.x;
+                            if (f & 2u) z1 = zz.y;
                         }
                         // Walk: x + (x - xp) z on every coordinate (:298); Traverse: xp + b (xp - x) on flagged ones (:346)
                         const double wx = xm.x + (xm.x - xp.x) * z0, wy = xm.y + (xm.y - xp.y) * z1;

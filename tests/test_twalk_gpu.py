@@ -82,7 +82,9 @@ def test_half_pass_fixed_stream_vs_oracle(sb, oracle, case, pphi):
 
 
 @pytest.mark.parametrize("kind,params,n,dim,nb", [(0, [0.5], 256, 6, 2), (2, [], 4096, 64, 1), (3, [10.0], 2048, 10, 8),
-                                                  (2, [], 4096, 20, 2)])
+                                                  (2, [], 4096, 20, 2),
+                                                  (3, [10.0], 8192, 10, 2),     # rungs above 1024 walkers: keyed-bijection matching
+                                                  (0, [0.5], 4096, 32, 1), (0, [0.5], 2048, 130, 1)])
 def test_device_streams_replay_through_oracle(sb, oracle, kind, params, n, dim, nb):
     """twalk::sample on the device streams == the oracle fed the CPU restatement of those streams (b taken from
     the device: the one draw that goes through pow())."""
