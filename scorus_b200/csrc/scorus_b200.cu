@@ -614,6 +614,10 @@ static int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta
     p->w_off = (uint32_t)ctx->w_off; p->rung_off = ctx->rung_off; p->n_global = ctx->n_global;
     p->src_ens = ctx->d_ens; p->src_lp = ctx->d_lp; p->n_dev = nullptr; p->w_lo = 0; p->w_hi = (uint32_t)ctx->n;
     p->dirty = ctx->track_dirty ? ctx->d_dirty : nullptr;
+    // measured (profiles/r1_notes.md): +4 % at 32-D (rows of 256 B: too few bytes in flight per warp to cover DRAM
+    // latency), -9 % at 64-D (already at 92 % of the roofline), nothing at 10-D (arithmetic-bound)
+    const int pf = env_int("SCORUS_L2_PREFETCH", -1);
+    p->l2_prefetch = pf < 0 ? (g->row_bytes >= 128u && g->row_bytes <= 256u ? 1u : 0u) : (pf ? 1u : 0u);
     if (nbeta > 1) {
         if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
         p->rung_acc = ctx->d_rung_stats;

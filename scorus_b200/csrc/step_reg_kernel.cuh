@@ -213,6 +213,13 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
             w_n = p.w_lo;
         }
         lp_n = load_lp(w_n, act_n);
+        if constexpr (!kStaged) {
+            if (p.l2_prefetch && act_n) {  // my next-tile row -> L2, a whole tile ahead of its loads
+                const char *r = reinterpret_cast<const char *>(p.src_ens + (size_t)w_n * p.pitch);
+                for (uint32_t off = 0; off < p.row_bytes; off += 128u) prefetch_l2(r + off);
+                prefetch_l2(r + p.row_bytes - 1u);
+            }
+        }
 
         double tot[Plugin::kAcc];
 #pragma unroll

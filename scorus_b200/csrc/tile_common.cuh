@@ -58,6 +58,10 @@ struct StepParams {
     // Chain statistics: per-rung acceptance counts, indexed like beta; nullptr for
     // single-rung calls, whose count is stats[0].
     unsigned long long *rung_acc;
+    // Register kernel: when a warp learns the walkers of its NEXT tile (one tile ahead), every lane asks L2 for that
+    // walker's row, so that the block loads of the next tile find their lines in L2 instead of waiting on DRAM
+    // (SCORUS_L2_PREFETCH; by default only for rows of 128..256 bytes, where it pays).
+    uint32_t l2_prefetch;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
@@ -120,6 +124,7 @@ __device__ __forceinline__ void fence_proxy_async()
 // its writes are visible, grid_dep_launch lets the successor's blocks be scheduled early.
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_mbar_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
