@@ -428,3 +428,20 @@ def test_host_call_pinned_and_pageable_buffers_agree(sb, dim):
             out.append((ens.copy(), lp.copy()))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert not np.array_equal(out[0][0], ens0)
+
+
+def test_pso_hand_off_from_ensemble(sb, oracle):
+    """ParticleSwarmMaximizer::init_swarm_from_ensemble (src/opt/pso.rs:177-192): zero velocity, fitness = func(position)."""
+    g = np.random.default_rng(4)
+    ens = np.ascontiguousarray(g.uniform(0.5, 1.5, (20, 6)))
+    swarm = sb.pso.init_swarm_from_ensemble(sb.Rosenbrock(), ens, sb.DeviceRng(seed=1))
+    want = oracle.init_logprob(2, [], ens)
+    assert len(swarm) == 20 and all(p.pbest is None and not p.velocity.any() for p in swarm)
+    assert np.array_equal(np.array([p.position for p in swarm]), ens)
+    assert np.allclose([p.fitness for p in swarm], want, rtol=1e-12)
+    with sb.Sampler(sb.Rosenbrock(), 20, 6, seed=1) as s:
+        s.upload(ens, None)
+        s.sample(2.0, sb.UpdateFlagSpec.All(), 5)
+        e, lp = s.download()
+        swarm = sb.pso.swarm_from_sampler(s)
+    assert np.array_equal(np.array([p.position for p in swarm]), e) and np.array_equal([p.fitness for p in swarm], lp)
