@@ -424,6 +424,10 @@ def main():
                     "traffic": traffic, "kernel": kernel_name,
                     "peak_source": "cuBLAS fp64 DGEMM 4096^3 via torch.matmul, best of 6, measured in this run",
                     "algorithmic_flops_per_walker_step": 2 * dim * dim + 2 * dim, "walkers_per_launch": n_local,
+                    # the workload's L is an upper-triangular (Cholesky-type) factor: the kernel starts the k loop of
+                    # column block n0 at n0, so it EXECUTES this fraction of the accounted dense 2 D^2 flops
+                    # ("a triangular-factor formulation does half -- still account at 2 D^2")
+                    "executed_fraction_of_accounted_flops": sum(dim - n0 for n0 in range(0, dim, 32)) / (dim * len(range(0, dim, 32))),
                     "hbm_frac": b_alg(dim) * n_local * args.steps / (ms * 1e-3) / 1e9 / peak}
     else:
         bytes_per_launch = b_alg(dim) * n_local

@@ -367,13 +367,14 @@ struct LpCorrGaussian {
     static constexpr bool kHasGrad = false;
     const double *mu, *L;
     uint32_t dim;
-    bool ok;
+    bool ok, upper;  // upper: L[n][k] == 0 for k < n (flagged by scorus_set_logprob after {mu, L})
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t d)
     {
         ok = np >= d + d * d;
         mu = p;
         L = p + d;
         dim = d;
+        upper = np > d + d * d && __ldg(p + d + d * d) != 0.0;
     }
     __device__ __forceinline__ void accum(uint32_t, double) {}
     __device__ __forceinline__ double finish() const { return NAN; }
@@ -393,7 +394,8 @@ struct LpCorrGaussian {
         for (int ng = 0; ng < NA; ++ng)
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) c[ng][mt][0] = c[ng][mt][1] = 0.0;
-        for (uint32_t k0 = 0; k0 < dim; k0 += 4) {
+        // columns n0.. of W only see L[n][k] with k >= n0 when L is upper triangular (n0 is a multiple of 8)
+        for (uint32_t k0 = upper ? n0 : 0u; k0 < dim; k0 += 4) {
             const uint32_t k = k0 + t;
             const bool kin = k < dim;
             const double mu_k = kin ? __ldg(mu + k) : 0.0;

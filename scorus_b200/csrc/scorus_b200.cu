@@ -352,12 +352,22 @@ extern "C" int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *param
     if (kind == SCORUS_LP_MIXTURE && nparams != 2 + d)
         return fail(ctx, SCORUS_ERR_INVALID_ARG, "MIXTURE takes 2 + dim params");
     cudaSetDevice(ctx->device);
-    int rc = ensure(ctx, (void **)&ctx->d_params, &ctx->params_cap, (nparams ? nparams : 1) * sizeof(double));
+    // dense Gaussian: one extra device-side value after {mu, L} tells the tile kernel that L is upper triangular
+    // (a Cholesky-type factor), so that the k loop of column block n0 can start at n0 instead of 0
+    const bool corr = kind == SCORUS_LP_CORR_GAUSSIAN;
+    double upper = 1.0;
+    if (corr)
+        for (size_t i = 1; i < d && upper != 0.0; ++i)
+            for (size_t j = 0; j < i; ++j)
+                if (params[d + i * d + j] != 0.0) { upper = 0.0; break; }
+    const size_t ndev = nparams + (corr ? 1 : 0);
+    int rc = ensure(ctx, (void **)&ctx->d_params, &ctx->params_cap, (ndev ? ndev : 1) * sizeof(double));
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     if (nparams) CU(cudaMemcpy(ctx->d_params, params, nparams * sizeof(double), cudaMemcpyHostToDevice));
+    if (corr) CU(cudaMemcpy(ctx->d_params + nparams, &upper, sizeof(double), cudaMemcpyHostToDevice));
     ctx->lp_kind = kind;
-    ctx->nparams = (uint32_t)nparams;
+    ctx->nparams = (uint32_t)ndev;
     return SCORUS_OK;
 }
 

@@ -445,3 +445,27 @@ def test_pso_hand_off_from_ensemble(sb, oracle):
         e, lp = s.download()
         swarm = sb.pso.swarm_from_sampler(s)
     assert np.array_equal(np.array([p.position for p in swarm]), e) and np.array_equal([p.fitness for p in swarm], lp)
+
+
+@pytest.mark.parametrize("dim", [12, 100, 130])
+@pytest.mark.parametrize("shape", ["dense", "upper", "lower"])
+def test_corr_gaussian_factor_shapes(sb, oracle, dim, shape):
+    """The dense-target tile kernel skips the zero half of an upper-triangular factor (the k loop of column block
+    n0 starts at n0); a general or lower-triangular L must take the full loop.  Same answers either way."""
+    n = 128
+    g = np.random.default_rng(dim)
+    M = g.normal(size=(dim, dim)) * 0.2 + np.eye(dim)
+    L = {"dense": M, "upper": np.triu(M), "lower": np.tril(M)}[shape]
+    params = np.concatenate([g.normal(size=dim) * 0.1, L.ravel()])
+    ens = np.ascontiguousarray(g.uniform(-1, 1, (n, dim)))
+    lp = oracle.init_logprob(6, params, ens)
+    rng = oracle.Rng(3)
+    with sb.Sampler(sb.LogProb(6, tuple(params.tolist())), n, dim, seed=0) as s:
+        s.upload(ens, lp)
+        for step in range(3):
+            partner, z, flags, u, _ = oracle.draw_sample_streams(rng, n, dim, 1, 2.0, oracle.UFS_PROB, 0.5)
+            rc, want_acc = oracle.sample_pt_fixed(6, params, ens, lp, [1.0], partner, z, flags, u)
+            acc = s.sample_pt_fixed([1.0], partner, z, flags, u)
+            got_e, got_lp = s.download()
+            assert rc == 0 and np.array_equal(acc, want_acc) and np.array_equal(got_e, ens)
+            assert_lp_close(6, params, ens, got_lp, lp, exact=False)
