@@ -167,6 +167,42 @@ def cpu_reference_leg(wl, steps, warmup, sample_walkers=None, target_seconds=12.
     }
 
 
+def cpu_move_leg(wl, move, target_seconds=8.0):
+    """CPU port of the other two move families (oracle/twalk.c, oracle/hmc.c: serial restatements, one core) on a
+    bounded sample of the workload, for the GPU-to-CPU ratio of those paths."""
+    from oracle import pyoracle as po
+    po.build()
+    desc, kind, n, dim, nbeta, ufs, prob, box, swap_every = WORKLOADS[wl]
+    params = workload_params(kind, dim)
+    npb = n // nbeta
+    nb_s = max(1, min(nbeta, (1 << 14) // npb)) if nbeta > 1 else 1
+    n_s = nb_s * npb if nbeta > 1 else min(n, 1 << 14)
+    beta = betas(nbeta)[:nb_s]
+    ens = make_ensemble(n_s, dim, box, 5, kind)
+    lp = po.init_logprob(kind, params, ens)
+    rng = po.Rng(3)
+    tw = po.twalk_params(dim)
+    eps = np.full(nb_s, {2: 0.002, 3: 0.02}.get(kind, 0.1))
+
+    def one():
+        if move == "twalk":
+            po.twalk_sample(kind, params, ens, lp, rng, tw, beta)
+        else:
+            po.hmc_ensemble_pt(kind, params, ens, lp, rng, eps, beta, 10, 0.8, 0.0)
+
+    t0 = time.perf_counter()
+    one()
+    t1 = time.perf_counter() - t0
+    k = int(max(1, min(50, target_seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+    t = time.perf_counter() - t0
+    return {"value": n_s * k / t, "unit": "walker-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{k} steps of the first {n_s} walkers ({nb_s} rung(s)) of {desc}; serial C restatement "
+                      f"(oracle/{'twalk' if move == 'twalk' else 'hmc'}.c), one core"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,7 +371,17 @@ def main():
     if not args.no_e2e:
         h_ens = sb.pinned_empty((n_local, dim))
         h_lp = sb.pinned_empty((n_local,))
-        if world > 1:
+        shard_local = world > 1 and args.move == "stretch" and (s.mode == "rungs" or args.matching == "local")
+        if shard_local:
+            # no per-step exchange: every rank makes the reference-shaped call on its own shard (accepted rows only
+            # travel back, as on one GPU)
+            local_beta = beta[s.rung_off:s.rung_off + s.nb_local] if s.mode == "rungs" else beta
+
+            def host_step():
+                s.sampler.sample_pt_host(h_ens, h_lp, 2.0, spec, local_beta)
+            s.sampler.download(h_ens, h_lp)
+            api = "per rank: Sampler.sample_pt_host -> scorus_sample_pt_host on its shard (pinned host buffers, one step per call)"
+        elif world > 1:
             def host_step():  # upload shard, one (possibly exchanging) step, download shard
                 s.upload(h_ens, h_lp)
                 do_steps(1)
@@ -369,9 +415,11 @@ def main():
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        bytes_dir = n_local * dim * 8 + n_local * 8
-        # single-GPU host call on pinned buffers: only accepted walkers are written back (scatter download)
-        d2h = int(acc_per_step * (dim * 8 + 8)) if world == 1 and os.environ.get("SCORUS_SCATTER_DOWNLOAD", "1") != "0" else bytes_dir
+        # whole job: every rank copies its own shard (rank 0's accept count stands for the others')
+        bytes_dir = (n_local * dim * 8 + n_local * 8) * world
+        # host call on pinned buffers: only accepted walkers are written back (scatter download)
+        scatter = (world == 1 or shard_local) and os.environ.get("SCORUS_SCATTER_DOWNLOAD", "1") != "0"
+        d2h = int(acc_per_step * world * (dim * 8 + 8)) if scatter else bytes_dir
         e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": api}
@@ -442,6 +490,8 @@ def main():
     if not args.no_cpu and world == 1 and args.move == "stretch":
         cpu = cpu_reference_leg(args.workload, 20, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")}
+    elif not args.no_cpu and world == 1:
+        cpu = cpu_move_leg(args.workload, args.move)
 
     line = {
         "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s", "n_gpus": world,
