@@ -202,7 +202,7 @@ typedef struct scorus_hmc_param {
 /* sample_ensemble_pt (:122-292) on the resident ensemble, nsteps times: fresh N(0, 1) momenta, l leapfrog steps
  * (src/mcmc/hmc/utils.rs:6-30) of size epsilon[rung] under the tempered force beta * grad(logprob), accept with
  * exp(beta (lp' - lp) + K - K') when that is finite.  The gradient -- the reference's second closure, grad_logprob --
- * belongs to the log-density plugin (Gaussian, bounded Gaussian, Rosenbrock, Rastrigin have one; the others answer
+ * belongs to the log-density plugin (Gaussian, bounded Gaussian, Rosenbrock, Rastrigin, mixture have one; the others answer
  * SCORUS_ERR_INVALID_ARG) and is recomputed from q0 at entry, as sample_ensemble_pt does (:139).  epsilon[nbeta] is
  * in/out (host): for rungs of up to 4096 walkers it is updated exactly as the reference's sequential accept loop
  * would (bit-identical); for larger rungs the same factors are applied at once, epsilon (1 + adj_factor)^(grown -

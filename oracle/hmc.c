@@ -46,6 +46,23 @@ int orc_grad_logprob(int kind, const double *params, size_t nparams, const doubl
         }
         return ORC_OK;
     }
+    case ORC_LP_MIXTURE: { /* logsumexp of two isotropic Gaussians at +m, -m: w1 (-(x-m)/s1^2) + w2 (-(x+m)/s2^2) */
+        if (nparams < 2 + dim) return ORC_ERR_INVALID_ARG;
+        const double s1 = params[0], s2 = params[1];
+        const double *m = params + 2;
+        double q1 = 0.0, q2 = 0.0;
+        for (size_t i = 0; i < dim; ++i) {
+            const double a = x[i] - m[i], b = x[i] + m[i];
+            q1 += a * a;
+            q2 += b * b;
+        }
+        const double t1 = (-q1) / ((2.0 * s1) * s1) - (double)dim * log(s1);
+        const double t2 = (-q2) / ((2.0 * s2) * s2) - (double)dim * log(s2);
+        const double lse = orc_logprob(kind, params, nparams, x, dim);
+        const double r1 = exp(t1 - lse) / (s1 * s1), r2 = exp(t2 - lse) / (s2 * s2);
+        for (size_t j = 0; j < dim; ++j) g[j] = (0.0 - r1 * (x[j] - m[j])) - r2 * (x[j] + m[j]);
+        return ORC_OK;
+    }
     default:
         return ORC_ERR_INVALID_ARG;
     }

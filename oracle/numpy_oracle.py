@@ -267,6 +267,19 @@ def grad_logprob(kind: int, params, x: np.ndarray) -> np.ndarray:
         k = two_pi * a
         s = k * _vmath(math.sin, two_pi * x)
         return (0.0 - s) - 2.0 * x
+    if kind == 7:
+        s1, s2, m = p[0], p[1], p[2:2 + d]
+        q1, q2 = np.zeros(n), np.zeros(n)
+        for i in range(d):
+            a, b = x[:, i] - m[i], x[:, i] + m[i]
+            q1 = q1 + a * a
+            q2 = q2 + b * b
+        t1 = (-q1) / ((2.0 * s1) * s1) - float(d) * math.log(s1)
+        t2 = (-q2) / ((2.0 * s2) * s2) - float(d) * math.log(s2)
+        lse = logprob(kind, params, x)
+        r1 = _vmath(math.exp, t1 - lse) / (s1 * s1)
+        r2 = _vmath(math.exp, t2 - lse) / (s2 * s2)
+        return (0.0 - r1[:, None] * (x - m)) - r2[:, None] * (x + m)
     raise ValueError("plugin without a gradient")
 
 

@@ -103,6 +103,17 @@ __global__ void __launch_bounds__(256) hmc_kernel(const HmcParams hp)
 
         // force at a point: lhq = grad(q) * scale; neighbours x[d-1], x[d+2] from the adjacent lanes / trips
         auto force = [&](double scale) {
+            if constexpr (Plugin::kGradNeedsSums) {  // row-wide sums first (mixture: the component weights)
+                double a[Plugin::kAcc];
+#pragma unroll
+                for (int k = 0; k < Plugin::kAcc; ++k) a[k] = 0.0;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it)
+                    if (in[it]) plug.terms(2u * ((uint32_t)it * G + j), q[it].x, q[it].y, 0.0, has1[it], false, a);
+#pragma unroll
+                for (int k = 0; k < Plugin::kAcc; ++k) a[k] = group_sum<G>(a[k]);
+                plug.grad_prepare(a);
+            }
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t c = (uint32_t)it * G + j, d = 2u * c;

@@ -58,6 +58,7 @@ struct LpGaussian {
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return a[0]; }
     static constexpr bool kHasGrad = true;
+    static constexpr bool kGradNeedsSums = false;
     __device__ __forceinline__ void grad2(uint32_t, double, double x0, double x1, double, bool, bool, bool, double &g0,
                                           double &g1) const
     {
@@ -98,6 +99,7 @@ struct LpBoundedGaussian {
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return a[1] > 0.0 ? -INFINITY : a[0]; }
     static constexpr bool kHasGrad = true;  // inside the box; a trajectory that ends outside has lp = -inf and is rejected
+    static constexpr bool kGradNeedsSums = false;
     __device__ __forceinline__ void grad2(uint32_t, double, double x0, double x1, double, bool, bool, bool, double &g0,
                                           double &g1) const
     {
@@ -141,6 +143,7 @@ struct LpRosenbrock {
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return -a[0]; }
     static constexpr bool kHasGrad = true;
+    static constexpr bool kGradNeedsSums = false;
     // the reference's own example closure, examples/test_hmc.rs:27-37, keeping the i that contribute:
     // g[j] = 0;  i = j-1: g[j] -= 200 (x[j] - x[j-1]^2) * 1;  i = j: g[j] -= 200 (x[j+1] - x[j]^2) (0 - 2 x[j]) + 2 (x[j] - 1)
     static __device__ __forceinline__ double grad1(double xm, double x, double xn, bool hasprev, bool hasnext)
@@ -188,6 +191,7 @@ struct LpRastrigin {
     }
     __device__ __forceinline__ double finish_acc(const double *s) const { return base + s[0]; }
     static constexpr bool kHasGrad = true;  // g = -(2 pi a) sin(2 pi x) - 2 x
+    static constexpr bool kGradNeedsSums = false;
     __device__ __forceinline__ void grad2(uint32_t, double, double x0, double x1, double, bool, bool, bool, double &g0,
                                           double &g1) const
     {
@@ -206,6 +210,7 @@ struct LpBimodal2d {
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;  // [0] carries x0, [1] carries x1
     static constexpr bool kHasGrad = false;
+    static constexpr bool kGradNeedsSums = false;
     double lo0, hi0, lo1, hi1, split, mu_a, sg_a, mu_b, sg_b, x0, x1;
     uint32_t dim;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t d)
@@ -253,6 +258,7 @@ struct LpStep2d {
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;
     static constexpr bool kHasGrad = false;
+    static constexpr bool kGradNeedsSums = false;
     double x0, x1;
     uint32_t dim;
     __device__ __forceinline__ void init(const double *, uint32_t, uint32_t d)
@@ -287,10 +293,12 @@ struct LpMixture {
     static constexpr int kMaxWarps = 14;
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 2;
-    static constexpr bool kHasGrad = false;
+    static constexpr bool kHasGrad = true;
+    static constexpr bool kGradNeedsSums = true;  // the component weights need |x - m|^2 and |x + m|^2 of the whole row
     const double *m;
     double s1, s2, q1, q2;
     double den1, den2, c1, c2;  // (2 s) s and D ln s, hoisted out of the per-walker tail (same roundings)
+    double r1, r2;              // gradient: component weight / sigma^2 of the current point (grad_prepare)
     uint32_t dim;
     bool ok;
     __device__ __forceinline__ void init(const double *p, uint32_t np, uint32_t d)
@@ -338,6 +346,22 @@ struct LpMixture {
         }
     }
     __device__ __forceinline__ double finish_acc(const double *a) const { return eval(a[0], a[1]); }
+    // gradient of the logsumexp: w1 (-(x - m) / s1^2) + w2 (-(x + m) / s2^2), w_i = exp(t_i - lse); a = the row's
+    // (|x - m|^2, |x + m|^2) as terms() accumulates them
+    __device__ __forceinline__ void grad_prepare(const double *a)
+    {
+        const double t1 = (-a[0]) / den1 - c1, t2 = (-a[1]) / den2 - c2;
+        const double lse = eval(a[0], a[1]);
+        r1 = exp(t1 - lse) / (s1 * s1);
+        r2 = exp(t2 - lse) / (s2 * s2);
+    }
+    __device__ __forceinline__ void grad2(uint32_t d, double, double x0, double x1, double, bool, bool has1, bool, double &g0,
+                                          double &g1) const
+    {
+        const double m0 = ok ? __ldg(m + d) : 0.0, m1 = ok && has1 ? __ldg(m + d + 1) : 0.0;
+        g0 = (0.0 - r1 * (x0 - m0)) - r2 * (x0 + m0);
+        g1 = (0.0 - r1 * (x1 - m1)) - r2 * (x1 + m1);
+    }
 };
 
 #ifndef SCORUS_K3_NG
@@ -365,6 +389,7 @@ struct LpCorrGaussian {
     static constexpr bool kNeedsNext = false;
     static constexpr int kAcc = 1;
     static constexpr bool kHasGrad = false;
+    static constexpr bool kGradNeedsSums = false;
     const double *mu, *L;
     uint32_t dim;
     bool ok, upper;  // upper: L[n][k] == 0 for k < n (flagged by scorus_set_logprob after {mu, L})

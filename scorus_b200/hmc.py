@@ -3,7 +3,7 @@ parallel-tempering entry point: `HmcParam` (:17-56) and `sample_ensemble_pt` (:1
 on the device (scorus_b200/csrc/hmc_kernel.cuh); nothing here computes.
 
 The reference takes the gradient as a second closure, `grad_logprob: &G`.  Here the gradient belongs to the
-log-density plugin (Gaussian, BoundedGaussian, Rosenbrock, Rastrigin have one); the `grad_logprob` argument is kept
+log-density plugin (Gaussian, BoundedGaussian, Rosenbrock, Rastrigin, Mixture have one); the `grad_logprob` argument is kept
 for the call shape and must be None or the same plugin.  The single-chain `sample` (:58-120) is the same arithmetic
 for one walker at beta = 1 on the calling thread -- not a data-parallel path, not mirrored.
 """

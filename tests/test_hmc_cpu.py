@@ -22,7 +22,8 @@ def test_golden_vectors_both_restatements(oracle, path):
         assert np.array_equal(eps, g["eps"][k]) and np.array_equal(e2, eps)
 
 
-@pytest.mark.parametrize("kind,params", [(0, [0.5]), (0, [1.0]), (1, [1.5]), (2, []), (3, [10.0])])
+@pytest.mark.parametrize("kind,params", [(0, [0.5]), (0, [1.0]), (1, [1.5]), (2, []), (3, [10.0]),
+                                         (7, [1.0, 2.0, 1.5] + [0.0] * 8)])
 def test_gradients_match_finite_differences_and_numpy(oracle, kind, params):
     g = np.random.default_rng(kind)
     x = g.uniform(-1.0, 1.0, (5, 9))
@@ -39,7 +40,7 @@ def test_gradients_match_finite_differences_and_numpy(oracle, kind, params):
 
 def test_plugins_without_gradient_say_so(oracle):
     with pytest.raises(ValueError):
-        oracle.grad_logprob(7, [1.0, 2.0, 5.0, 0.0], np.zeros((1, 2)))
+        oracle.grad_logprob(4, [], np.zeros((1, 2)) + 0.3)
 
 
 @pytest.mark.parametrize("kind,params,n,dim,nb,l", [(0, [0.5], 32, 5, 2, 4), (2, [], 24, 8, 3, 3), (3, [10.0], 40, 10, 4, 5),
