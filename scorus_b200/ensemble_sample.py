@@ -249,6 +249,12 @@ class Sampler:
         self._ok(self._lib.scorus_download(self._ctx, _dp(ensemble), _dp(logprob)))
         return ensemble, logprob
 
+    def download_logprob(self) -> np.ndarray:
+        """Only the cached log-probs (8 bytes per walker): scorus_download with a NULL ensemble."""
+        lp = np.empty(self.n)
+        self._ok(self._lib.scorus_download(self._ctx, None, _dp(lp)))
+        return lp
+
     # -- the hot path
     def init_logprob(self):
         self._ok(self._lib.scorus_init_logprob(self._ctx))
