@@ -24,11 +24,17 @@ fn main() {
     };
     let mut main = cc::Build::new();
     base(&mut main);
-    main.file(csrc.join("scorus_b200.cu")).file(csrc.join("launch_dispatch.cu")).compile("scorus_b200_core");
-    for p in plugins {
-        let mut b = cc::Build::new();
-        base(&mut b);
-        b.define("SCORUS_PLUGIN", p).file(csrc.join("launch_plugin.cu")).compile(&format!("scorus_b200_{p}"));
+    for api in ["api_core.cu", "api_shard.cu", "api_stats.cu", "api_moves.cu", "api_host.cu", "launch_dispatch.cu"] {
+        main.file(csrc.join(api));
+    }
+    main.compile("scorus_b200_core");
+    // one translation unit per (kernel family, log-density plugin), as scorus_b200/csrc/Makefile does
+    for unit in ["launch", "twalk", "hmc"] {
+        for p in plugins {
+            let mut b = cc::Build::new();
+            base(&mut b);
+            b.define("SCORUS_PLUGIN", p).file(csrc.join(format!("{unit}_plugin.cu"))).compile(&format!("scorus_b200_{unit}_{p}"));
+        }
     }
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rerun-if-changed={}", csrc.display());

@@ -1,0 +1,70 @@
+// api_host.cu -- C ABI, part 5: the literal drop-ins on caller-owned host buffers -- what a reference call site
+// (`&mut [V]`, `&mut [T]` in, updated in place) maps to: upload, the move on the device, download.
+#include "host_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// literal drop-ins on host buffers
+// ------------------------------------------------------------------------------------------
+// upload -> run(ctx) -> download, shared by the host-buffer entry points
+template <class Run>
+static int host_call(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, size_t nbeta, Run run)
+{
+    int rc = scorus_check_sample_args(ctx->n, lp_len, nbeta);
+    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
+    if ((rc = scorus_upload(ctx, ens, lp))) return rc;
+    // Pinned (device-mapped) host buffers: after the steps only the accepted walkers differ from what
+    // was just uploaded, so only those rows travel back, written in place by scatter_download_kernel.
+    // Pageable buffers take the full copy.
+    cudaPointerAttributes ae{}, al{};
+    const bool pinned = env_int("SCORUS_SCATTER_DOWNLOAD", 1) &&
+                        cudaPointerGetAttributes(&ae, ens) == cudaSuccess && ae.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&al, lp) == cudaSuccess && al.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {
+        if ((rc = run())) return rc;
+        return scorus_download(ctx, ens, lp);
+    }
+    if (!ctx->d_dirty) CU(cudaMalloc(&ctx->d_dirty, ctx->n));
+    CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, ctx->stream));
+    ctx->track_dirty = true;
+    rc = run();
+    ctx->track_dirty = false;
+    if (rc) return rc;
+    if ((rc = launch_scatter_download(ctx, (double *)ae.devicePointer, (double *)al.devicePointer))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                       const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
+{
+    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps); });
+}
+
+// twalk::sample on host buffers (the `ensemble_logprob: &mut (W, X)` argument, twalk.rs:588)
+extern "C" int scorus_twalk_sample_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len,
+                                        const scorus_twalk_params *tw, const double *beta, size_t nbeta, uint64_t nsteps)
+{
+    if (!ctx || !ens || !lp || !tw) return SCORUS_ERR_INVALID_ARG;
+    return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_twalk_sample(ctx, tw, beta, nbeta, nsteps); });
+}
+
+extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                     const scorus_ufs *ufs, const double *beta, size_t nbeta)
+{
+    return scorus_sample_pt_host_n(ctx, ens, lp, lp_len, a, ufs, beta, nbeta, 1);
+}
+
+extern "C" int scorus_swap_walkers_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len,
+                                        const double *beta, size_t nbeta)
+{
+    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    if (nbeta == 0) return SCORUS_ERR_INVALID_ARG;
+    if ((ctx->n / nbeta) * nbeta != ctx->n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
+    if (lp_len != ctx->n) return SCORUS_OK;  // src/mcmc/utils.rs:88: silently does nothing
+    int rc = scorus_check_beta_order(beta, nbeta);
+    if (rc) return fail(ctx, rc, "beta list must be in decreasing order");
+    if ((rc = scorus_upload(ctx, ens, lp))) return rc;
+    if ((rc = scorus_swap_walkers(ctx, beta, nbeta))) return rc;
+    return scorus_download(ctx, ens, lp);
+}

@@ -1,0 +1,142 @@
+// host_common.cuh -- what the translation units of the C ABI share: the context, error plumbing and the
+// helpers that several entry points use.  Private to scorus_b200/csrc (the public surface is
+// include/scorus_b200.h).  There is deliberately no CPU path anywhere behind it.
+#pragma once
+#include "../../include/scorus_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "launch.cuh"
+#include "swap_params.cuh"
+#include "tile_common.cuh"
+#include "twalk_kernel.cuh"
+
+using namespace scorus;
+
+struct scorus_ctx {
+    int device = 0;
+    uint64_t n = 0;
+    uint32_t dim = 0, pitch = 0;
+    uint64_t seed = 0;
+    uint64_t step = 0, swap_call = 0, onehot = 0;
+    uint64_t w_off = 0, n_global = 0;  // shard position in the whole ensemble (scorus_set_shard)
+    uint32_t rung_off = 0;
+    uint64_t launches = 0, proposed = 0, swap_proposed = 0;
+    int num_sms = 0, smem_optin = 0;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double *d_ens = nullptr, *d_lp = nullptr, *d_scratch = nullptr;
+    double *d_beta = nullptr;   // the beta list of the current call (one of beta_cache)
+    struct BetaEntry { std::vector<double> host; double *dev = nullptr; uint64_t used = 0; };
+    std::vector<BetaEntry> beta_cache;  // callers alternate between a few lists (local / global ladder)
+    uint64_t beta_clock = 0;
+    double *d_params = nullptr; size_t params_cap = 0;
+    uint32_t *d_order = nullptr, *d_src = nullptr;
+    uint32_t *d_gorder = nullptr; size_t gorder_cap = 0;   // global-matching mode: exact order of the whole ensemble
+    uint32_t *d_pairs = nullptr;  size_t pairs_cap = 0;    // ... local pair list
+    uint32_t *d_count = nullptr;
+    // one-sided partner reads over NVLink (scorus_ipc_attach): peers' ensembles / log-probs mapped here
+    int world = 1, rank = 0;
+    double *peer_ens[16] = {nullptr}, *peer_lp[16] = {nullptr};
+    double **d_peer_ens = nullptr, **d_peer_lp = nullptr;   // device copies of the tables
+    double *d_stage = nullptr, *d_stage_lp = nullptr;       // pulled partner rows, one per local walker
+    // K6: statistics scratch and the chain trace
+    double *d_part = nullptr; size_t part_cap = 0;
+    double *d_stat = nullptr; size_t stat_cap = 0;
+    uint32_t *d_tr_walker = nullptr, *d_tr_coord = nullptr;
+    double *d_trace = nullptr;
+    size_t tr_ncap = 0, tr_capacity = 0, tr_count = 0;
+    uint64_t tr_every = 1, tr_tick = 0;                     // capture after every tr_every-th step
+    // chain statistics: per-rung accepted moves [0, rung_cap) and per-stage accepted exchanges [rung_cap, 2 rung_cap)
+    unsigned long long *d_rung_stats = nullptr; size_t rung_cap = 0;
+    std::vector<uint64_t> rung_proposed, stage_proposed;
+    // running per-rung moments: sums of (x - shift) and of its outer products, taken every mom_every-th step
+    double *d_mom = nullptr;   // [shift: rungs*dim][s1: rungs*dim][s2: rungs*dim*dim]
+    double *d_iat = nullptr; size_t iat_cap = 0;
+    uint32_t mom_rungs = 0; bool mom_cov = false;
+    uint64_t mom_every = 1, mom_tick = 0, mom_count = 0;
+    bool p2p_pending = false;                                // scorus_sample_pt_p2p_begin without _end
+    StepParams p2p_params;
+    Geometry p2p_geom;
+    bool p2p_all_flags = false;
+    unsigned long long *d_stats = nullptr;
+    // scratch for caller-supplied streams
+    double *d_z = nullptr, *d_u = nullptr;
+    uint8_t *d_flags = nullptr; size_t flags_cap = 0;
+    uint8_t *d_acc = nullptr;
+    uint8_t *d_dirty = nullptr;     // host-buffer call: walkers accepted since the upload
+    unsigned long long *d_tile_counter = nullptr;  // dynamic tile scheduling of the register kernel
+    unsigned long long tile_ticket = 0;
+    bool track_dirty = false;
+    uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
+    double *d_r = nullptr;      size_t r_cap = 0;
+    uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
+    int8_t *d_hmc_adapt = nullptr;                              // HMC: step-size adaptation codes, one per walker
+    double *d_hmc_eps = nullptr; size_t hmc_eps_cap = 0;        // ... step size per rung
+    double *d_hmc_p = nullptr; size_t hmc_p_cap = 0;            // ... caller-supplied momenta
+    uint8_t *d_tw_kernel = nullptr; size_t tw_kernel_cap = 0;   // t-walk, caller-supplied draws
+    double *d_tw_walk = nullptr;    size_t tw_walk_cap = 0;
+
+    int lp_kind = -1;
+    uint32_t nparams = 0;
+    bool uploaded = false;
+    bool sequential = false;  // SCORUS_CFG_SEQUENTIAL_SUM
+    std::string err;
+};
+
+inline int fail(scorus_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, SCORUS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+namespace scorus {
+namespace host {
+
+// api_core.cu
+int env_int(const char *name, int dflt);
+int ensure(scorus_ctx *ctx, void **buf, size_t *cap, size_t bytes);
+int step_geometry(scorus_ctx *ctx, Geometry *g);
+int upload_beta(scorus_ctx *ctx, const double *beta, size_t nbeta);
+void stamp_tiles(scorus_ctx *ctx, StepParams *p, const Geometry &g);
+uint32_t flag_bits_for(double prob);
+int ensure_rung_stats(scorus_ctx *ctx, size_t nbeta);
+void count_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb, uint64_t w_lo, uint64_t w_hi, uint64_t steps);
+void count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb);
+int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta);
+// kernels of swap_kernel.cuh, launched from more than one translation unit
+void launch_exact_order(scorus_ctx *ctx, uint64_t step, size_t nbeta, uint32_t npb, uint32_t *order, uint32_t w_off);
+void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv);
+void launch_swap_chain(scorus_ctx *ctx, const SwapParams &sp);
+// api_stats.cu
+int after_step(scorus_ctx *ctx);  // chain capture and running moments, after every step
+int launch_scatter_download(scorus_ctx *ctx, double *host_ens, double *host_lp);
+
+}  // namespace host
+}  // namespace scorus
+
+using namespace scorus::host;

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "rng.cuh"
+#include "swap_params.cuh"
 
 namespace scorus {
 
@@ -66,18 +67,6 @@ __global__ void __launch_bounds__(1024) exact_jvec_kernel(uint64_t seed, uint64_
     }
 }
 
-struct SwapParams {
-    double *lp;            // [n] in/out
-    const double *beta;    // [nbeta]
-    const uint32_t *jinv;  // [(nbeta-1)][npb] cold slot of each hot slot, or nullptr -> bijection
-    const double *r_in;    // [(nbeta-1)][npb] indexed by cold slot, or nullptr -> Philox
-    uint32_t *src;         // [n] out: original slot of the walker that ends in each slot
-    uint8_t *swapped_out;  // [(nbeta-1)][npb] indexed by cold slot, or nullptr
-    unsigned long long *stats;  // [2] swapped, [3] swap_proposed
-    unsigned long long *stage_swapped;  // [nbeta-1] accepted exchanges between rung k and k+1, or nullptr
-    uint64_t seed, swap_call;
-    uint32_t npb, nbeta, bij_bits;
-};
 
 __global__ void __launch_bounds__(128) swap_chain_kernel(const SwapParams p)
 {
