@@ -298,7 +298,7 @@ int scorus::host::step_geometry(scorus_ctx *ctx, Geometry *g)
         const size_t per_warp = tile + flag_bytes;
         const size_t l1_keep = (size_t)env_int("SCORUS_L1_KB", 32) * 1024u;
         // mirrors reg_kernel_max_warps (step_reg_kernel.cuh): dense plugin 8, rows of <= 8 double2 16, else 14
-        uint32_t w = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN ? 8 : (ctx->pitch / 2 <= 8 ? 16 : 14);
+        uint32_t w = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN ? 8 : (ctx->pitch / 2 <= 16 ? 16 : 14);
         while (w >= 1 && w * per_warp > budget) --w;
         while (w > 8 && w * per_warp + l1_keep > budget) --w;
         if (w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);

@@ -46,13 +46,13 @@ struct RegGeom {
 
 // kStaged: one-sided multi-GPU mode (remote partners' rows pulled into p.stage_ens / p.stage_lp).  A
 // template parameter because even uniform branches on it cost 12 % in the single-GPU kernel.
-// Warps per block (= per SM).  Rows of up to 8 double2 (G <= 8) are cheap in registers and bound by
-// arithmetic: 16 warps under a 128-register cap measured faster (10-D Rastrigin 0.156 -> 0.144 ms);
+// Warps per block (= per SM).  Rows of up to 16 double2 (G <= 16) fit 128 registers anyway: 16 warps measured
+// faster (10-D Rastrigin 0.156 -> 0.144 ms; 32-D: neutral for the stretch move, +11 % for the t-walk);
 // wider rows keep 14 warps and up to 146 registers (the 64-D kernel lost 3 % under the tighter cap).
 template <class Plugin, int G>
 constexpr int reg_kernel_max_warps()
 {
-    return Plugin::kMaxWarps == 14 && G <= 8 ? 16 : Plugin::kMaxWarps;
+    return Plugin::kMaxWarps == 14 && G <= 16 ? 16 : Plugin::kMaxWarps;
 }
 
 template <class Plugin, int G, int ITERS, bool kStaged = false>
