@@ -469,3 +469,44 @@ def test_corr_gaussian_factor_shapes(sb, oracle, dim, shape):
             got_e, got_lp = s.download()
             assert rc == 0 and np.array_equal(acc, want_acc) and np.array_equal(got_e, ens)
             assert_lp_close(6, params, ens, got_lp, lp, exact=False)
+
+
+@pytest.mark.parametrize("move", ["stretch", "twalk", "hmc"])
+def test_checkpoint_resume_is_bit_identical(sb, move):
+    """(download, counters, epsilon) taken mid-run and restored into a fresh context with the same seed continues the
+    chain exactly: the device streams are pure functions of (seed, counters, walker)."""
+    nb, npb, dim = 4, 64, 7
+    n = nb * npb
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    f = sb.Rosenbrock()
+    tw, hp = sb.TWalkParams.new(dim), sb.HmcParam.quick_adj(0.7)
+
+    def advance(s, eps, k):
+        for i in range(k):
+            if i % 3 == 0:
+                s.swap_walkers(beta)
+            if move == "stretch":
+                s.sample_pt(2.0, sb.UpdateFlagSpec.OneHotCycle(), beta, 1)   # the cycling closure's state is a counter too
+            elif move == "twalk":
+                s.twalk_sample(tw, beta, 1)
+            else:
+                s.hmc_sample_ensemble_pt(eps, beta, 3, hp, 1)
+
+    ens0 = np.ascontiguousarray(np.random.default_rng(1).uniform(0.8, 1.2, (n, dim)))
+    with sb.Sampler(f, n, dim, seed=99) as a:
+        a.upload(ens0, None)
+        eps_a = np.full(nb, 0.004)
+        advance(a, eps_a, 12)
+        want = a.download()
+    with sb.Sampler(f, n, dim, seed=99) as b:
+        b.upload(ens0, None)
+        eps_b = np.full(nb, 0.004)
+        advance(b, eps_b, 6)
+        ckpt = (b.download(), b.counters, eps_b.copy())
+    with sb.Sampler(f, n, dim, seed=99) as c:
+        c.upload(*ckpt[0])
+        c.counters = ckpt[1]
+        eps_c = ckpt[2].copy()
+        advance(c, eps_c, 6)
+        got = c.download()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(eps_c, eps_a)
