@@ -3,6 +3,7 @@
 // (src/mcmc/ensemble_sample.rs:87-190) and swap_walkers (src/mcmc/utils.rs:72-112).  Validates the
 // reference's preconditions and launches the kernels of step_*_kernel.cuh and swap_kernel.cuh.
 #include "host_common.cuh"
+#include "step_small_kernel.cuh"
 #include "swap_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -545,6 +546,25 @@ void launch_swap_chain(scorus_ctx *ctx, const SwapParams &sp)
 }  // namespace host
 }  // namespace scorus
 
+// One-block ensembles (step_small_kernel.cuh): the whole ensemble in shared memory, any number of steps per launch.
+// Chosen by size alone -- never by the number of steps of a call -- so that k calls of one step and one call of k
+// steps are the same arithmetic.  SCORUS_KERNEL=reg|seq|coop keeps the streaming kernels (tests, measurements).
+static bool small_geometry(const scorus_ctx *ctx, Geometry *g)
+{
+    const char *force = getenv("SCORUS_KERNEL");
+    if (ctx->sequential || ctx->n > 1024 || !env_int("SCORUS_SMALL", 1)) return false;
+    if (force && *force && strcmp(force, "small")) return false;
+    const uint32_t warps = (uint32_t)((ctx->n + 31u) / 32u);
+    const SmallLayout L = small_layout((uint32_t)ctx->n, ctx->pitch, g->flag_words, warps);
+    if (L.total > (size_t)ctx->smem_optin) return false;
+    g->kernel = KERNEL_SMALL;
+    g->warps = warps;
+    g->grid = 1;
+    g->smem = L.total;
+    g->pdl = 0;
+    return true;
+}
+
 extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
                                 size_t nbeta, uint64_t nsteps)
 {
@@ -591,6 +611,27 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
         break;
     }
     default: return fail(ctx, SCORUS_ERR_INVALID_ARG, "unknown UpdateFlagSpec kind %d", ufs->kind);
+    }
+
+    if (small_geometry(ctx, &g)) {
+        // without per-step hooks (chain capture, running moments) all nsteps go down in one launch
+        const bool hooks = ctx->tr_ncap != 0 || ctx->mom_rungs != 0;
+        uint64_t done = 0;
+        while (done < nsteps) {
+            const uint32_t inner = hooks ? 1u : (uint32_t)std::min<uint64_t>(nsteps - done, 1u << 20);
+            p.step = ctx->step;
+            p.onehot = ctx->onehot;
+            cudaError_t e = launch_small(ctx->lp_kind, p, g, inner, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
+            ++ctx->launches;
+            ctx->step += inner;
+            if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE)
+                ctx->onehot = (ctx->onehot + (uint64_t)inner * (ctx->n_global % ctx->dim)) % ctx->dim;
+            done += inner;
+            if (hooks && (rc = after_step(ctx))) return rc;
+        }
+        count_proposed(ctx, nbeta, p.npb, 0, ctx->n, nsteps);
+        return SCORUS_OK;
     }
 
     bool exact = p.npb <= kExactShuffleMax;
@@ -672,8 +713,13 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
     p.order = ctx->d_order; p.z_in = ctx->d_z; p.u_in = ctx->d_u; p.flags_in = ctx->d_flags;
     p.flag_len = (uint32_t)flag_len; p.flag_kind = SCORUS_UFS_MASK; p.accepted_out = ctx->d_acc;
     p.step = ctx->step;
-    stamp_tiles(ctx, &p, g);
-    cudaError_t e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
+    cudaError_t e;
+    if (small_geometry(ctx, &g)) {
+        e = launch_small(ctx->lp_kind, p, g, 1, ctx->stream);
+    } else {
+        stamp_tiles(ctx, &p, g);
+        e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
+    }
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     count_proposed(ctx, nbeta, p.npb, 0, n, 1);

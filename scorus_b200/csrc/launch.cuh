@@ -11,7 +11,7 @@ struct StepParams;
 struct TwalkParams;
 struct HmcParams;
 
-enum : int { KERNEL_SEQ = 0, KERNEL_COOP = 1, KERNEL_REG = 2 };
+enum : int { KERNEL_SEQ = 0, KERNEL_COOP = 1, KERNEL_REG = 2, KERNEL_SMALL = 3 };
 
 struct Geometry {
     uint32_t row_bytes, row_stride, flag_words, stages, warps, grid;
@@ -24,6 +24,7 @@ struct Geometry {
     cudaError_t launch_step_##NAME(const StepParams &p, const Geometry &g, bool all_flags, \
                                    cudaStream_t st);                                                     \
     cudaError_t launch_init_##NAME(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);         \
+    cudaError_t launch_small_##NAME(const StepParams &p, const Geometry &g, uint32_t inner_steps, cudaStream_t st); \
     cudaError_t launch_twalk_##NAME(const TwalkParams &tp, const Geometry &g, cudaStream_t st);             \
     cudaError_t launch_hmc_##NAME(const HmcParams &hp, uint32_t num_sms, cudaStream_t st);
 
@@ -39,6 +40,8 @@ SCORUS_DECLARE_LAUNCHERS(LpMixture)
 // dispatch on the plugin id of include/scorus_b200.h (SCORUS_LP_*)
 cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st);
 cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);
+// one-block ensembles: inner_steps consecutive steps in one launch (step_small_kernel.cuh)
+cudaError_t launch_small(int kind, const StepParams &p, const Geometry &g, uint32_t inner_steps, cudaStream_t st);
 cudaError_t launch_twalk(int kind, const TwalkParams &tp, const Geometry &g, cudaStream_t st);
 cudaError_t launch_hmc(int kind, const HmcParams &hp, uint32_t num_sms, cudaStream_t st);  // cudaErrorNotSupported: no gradient
 

@@ -64,4 +64,19 @@ cudaError_t launch_hmc(int kind, const HmcParams &hp, uint32_t num_sms, cudaStre
     }
 }
 
+cudaError_t launch_small(int kind, const StepParams &p, const Geometry &g, uint32_t inner_steps, cudaStream_t st)
+{
+    switch (kind) {
+    case SCORUS_LP_GAUSSIAN: return launch_small_LpGaussian(p, g, inner_steps, st);
+    case SCORUS_LP_BOUNDED_GAUSSIAN: return launch_small_LpBoundedGaussian(p, g, inner_steps, st);
+    case SCORUS_LP_ROSENBROCK: return launch_small_LpRosenbrock(p, g, inner_steps, st);
+    case SCORUS_LP_RASTRIGIN: return launch_small_LpRastrigin(p, g, inner_steps, st);
+    case SCORUS_LP_BIMODAL2D: return launch_small_LpBimodal2d(p, g, inner_steps, st);
+    case SCORUS_LP_STEP2D: return launch_small_LpStep2d(p, g, inner_steps, st);
+    case SCORUS_LP_CORR_GAUSSIAN: return launch_small_LpCorrGaussian(p, g, inner_steps, st);
+    case SCORUS_LP_MIXTURE: return launch_small_LpMixture(p, g, inner_steps, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace scorus

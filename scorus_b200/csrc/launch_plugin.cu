@@ -4,6 +4,7 @@
 #include "step_coop_kernel.cuh"
 #include "step_kernel.cuh"
 #include "step_reg_kernel.cuh"
+#include "step_small_kernel.cuh"
 
 #ifndef SCORUS_PLUGIN
 #error "compile with -DSCORUS_PLUGIN=LpGaussian (or another plugin of logprob.cuh)"
@@ -92,6 +93,16 @@ cudaError_t SCORUS_CAT(launch_init_, SCORUS_PLUGIN)(const StepParams &p, uint32_
     cudaError_t e = cudaFuncSetAttribute(init_logprob_kernel<Plugin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     init_logprob_kernel<Plugin><<<grid, p.warps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t SCORUS_CAT(launch_small_, SCORUS_PLUGIN)(const StepParams &p, const Geometry &g, uint32_t inner_steps,
+                                                     cudaStream_t st)
+{
+    using Plugin = SCORUS_PLUGIN;
+    cudaError_t e = cudaFuncSetAttribute(step_small_kernel<Plugin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    step_small_kernel<Plugin><<<1, g.warps * 32, g.smem, st>>>(p, inner_steps);
     return cudaGetLastError();
 }
 

@@ -192,13 +192,13 @@ __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint64_t
     return nphi;
 }
 
-// `step`: the counter the Prob stream is keyed by (p.step, except in the fused t-walk kernel whose two half-passes
-// use consecutive counters)
-__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw, uint32_t lane,
-                                              bool act)
+// `step`, `onehot`: the counters the Prob stream / the cycling closure are keyed by (p.step, p.onehot, except in the
+// kernels that run several steps or half-passes per launch)
+__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step, uint64_t onehot, uint32_t w, uint32_t *flagw,
+                                              uint32_t lane, bool act)
 {
     if (p.flag_kind == 2u) {  // ONE_HOT_CYCLE: the cycling closure, called once per walker in order
-        const uint32_t hot = (uint32_t)((p.onehot + 1ull + (uint64_t)w + (uint64_t)p.w_off) % (uint64_t)p.dim);
+        const uint32_t hot = (uint32_t)((onehot + 1ull + (uint64_t)w + (uint64_t)p.w_off) % (uint64_t)p.dim);
         for (uint32_t wd = 0; wd < p.flag_words; ++wd)
             flagw[wd * 32u + lane] = (hot >> 5) == wd ? (1u << (hot & 31u)) : 0u;
         return 1u;
@@ -229,9 +229,14 @@ __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step
     default: return gen_flags_prob<32>(p, step, w, flagw, lane, act);
     }
 }
+__device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw, uint32_t lane,
+                                              bool act)
+{
+    return gen_flags(p, step, p.onehot, w, flagw, lane, act);
+}
 __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint32_t w, uint32_t *flagw, uint32_t lane, bool act)
 {
-    return gen_flags(p, p.step, w, flagw, lane, act);
+    return gen_flags(p, p.step, p.onehot, w, flagw, lane, act);
 }
 
 // per-rung acceptance counts: one atomic per tile when the tile lies inside one rung (the usual case),

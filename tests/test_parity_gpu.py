@@ -17,9 +17,14 @@ def _box(rng, n, d, lo, hi):
     return np.ascontiguousarray(rng.uniform(lo, hi, (n, d)))
 
 
-@pytest.mark.parametrize("seq", [False, True], ids=["reg", "seq"])
+@pytest.mark.parametrize("variant", ["default", "reg", "seq"])
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
-def test_golden_fixed_stream(sb, path, seq):
+def test_golden_fixed_stream(sb, path, variant, monkeypatch):
+    """default: what a caller gets (these ensembles fit one block: step_small_kernel.cuh); reg: the streaming
+    register kernel forced; seq: SCORUS_CFG_SEQUENTIAL_SUM."""
+    seq = variant == "seq"
+    if variant == "reg":
+        monkeypatch.setenv("SCORUS_KERNEL", "reg")
     g = np.load(path)
     kind, params, beta = int(g["kind"]), g["params"], g["beta"]
     n, dim = g["ens0"].shape
@@ -74,14 +79,15 @@ def _params_for(kind, params, dim, rng):
 
 
 @pytest.mark.parametrize("case", SHAPES, ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}")
-@pytest.mark.parametrize("variant", ["reg", "seq", "coop"])
+@pytest.mark.parametrize("variant", ["default", "reg", "seq", "coop"])
 @pytest.mark.parametrize("ufs", ["prob", "all", "short"])
 def test_fixed_stream_vs_oracle(sb, oracle, case, ufs, variant, monkeypatch):
-    """variant: the default register-streaming kernel, the sequential-sum kernel
-    (SCORUS_CFG_SEQUENTIAL_SUM), or the TMA-staged cooperative kernel (forced here; used for dim > 256)."""
+    """variant: the default dispatch (one-block ensembles: the shared-memory kernel; else register streaming, or
+    the cooperative kernel above 256-D), the register-streaming kernel forced, the sequential-sum kernel
+    (SCORUS_CFG_SEQUENTIAL_SUM), or the TMA-staged cooperative kernel forced."""
     seq = variant == "seq"
-    if variant == "coop":
-        monkeypatch.setenv("SCORUS_KERNEL", "coop")
+    if variant in ("coop", "reg"):
+        monkeypatch.setenv("SCORUS_KERNEL", variant)
     kind, params, n, dim, nb, box = case
     rng = np.random.default_rng(1000 * kind + dim)
     params = _params_for(kind, params, dim, rng)
@@ -510,3 +516,46 @@ def test_checkpoint_resume_is_bit_identical(sb, move):
         advance(c, eps_c, 6)
         got = c.download()
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(eps_c, eps_a)
+
+
+@pytest.mark.parametrize("kind,params,n,dim,nb,ufs", [(0, [0.5], 16, 2, 1, "prob"), (2, [], 96, 20, 4, "onehot"),
+                                                      (3, [10.0], 1024, 10, 8, "prob"), (6, None, 64, 12, 1, "all"),
+                                                      (1, [1.5], 34, 3, 17, "prob")])
+def test_one_block_ensembles_run_many_steps_per_launch(sb, kind, params, n, dim, nb, ufs, monkeypatch):
+    """Ensembles that fit a thread block take the shared-memory kernel: k steps in one launch == k launches of one
+    step == the same call with the chain capture hook on (one launch per step again) == the streaming register
+    kernel's chain (positions bit for bit; log-probs to 1e-12: sequential against tree sums)."""
+    g = np.random.default_rng(n)
+    params = _params_for(kind, params, dim, g)
+    f = sb.LogProb(kind, tuple(params.tolist()))
+    ens0 = _box(g, n, dim, 0.5, 1.5) if kind == 2 else _box(g, n, dim, -1, 1)
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    spec = {"prob": sb.UpdateFlagSpec.Prob(0.5), "onehot": sb.UpdateFlagSpec.OneHotCycle(), "all": sb.UpdateFlagSpec.All()}[ufs]
+    steps = 23
+
+    def run(mode):
+        with sb.Sampler(f, n, dim, seed=3) as s:
+            s.upload(ens0, None)
+            l0 = s.launch_count
+            if mode == "one_call":
+                s.sample_pt(2.0, spec, beta, steps)
+            elif mode == "per_step":
+                for _ in range(steps):
+                    s.sample_pt(2.0, spec, beta, 1)
+            else:  # chain capture on: the hook runs between steps
+                s.trace_enable([0], [0], steps)
+                s.sample_pt(2.0, spec, beta, steps)
+                assert s.trace_download(steps).shape == (steps, 1)
+            return s.download(), s.launch_count - l0, s.counters, s.stats()
+
+    (e1, l1), n1, c1, st1 = run("one_call")
+    (e2, l2), n2, c2, st2 = run("per_step")
+    (e3, l3), n3, c3, st3 = run("hooks")
+    assert n1 == 1 and n2 == steps and n3 >= 2 * steps
+    for e, l, c, st in ((e2, l2, c2, st2), (e3, l3, c3, st3)):
+        assert np.array_equal(e, e1) and np.array_equal(l, l1) and c == c1 and st == st1
+    assert st1["proposed"] == steps * n and 0 < st1["accepted"] < steps * n
+    monkeypatch.setenv("SCORUS_KERNEL", "reg")
+    (e4, l4), n4, c4, st4 = run("one_call")
+    assert n4 >= steps and np.array_equal(e4, e1) and c4 == c1 and st4["accepted"] == st1["accepted"]
+    assert_lp_close(kind, params, e1, l1, l4, exact=False)
