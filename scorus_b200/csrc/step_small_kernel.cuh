@@ -3,9 +3,9 @@
 //
 // The big kernels pay a launch per step; for a 16-walker ensemble (BASELINE config 1, the shape of the
 // reference's own examples/test_emcee.rs) that launch IS the step: 4.2 us, what the reference-structured
-// CPU port needs too.  Here thread t owns matching position t: per step the rungs are shuffled (rank of
-// 64-bit Philox keys, the same keys and tie-break as exact_order_kernel), every thread draws its walker's
-// z / u / flags from the same streams as the other kernels, builds the proposal from the OLD rows of its
+// CPU port needs too.  Here thread t owns walker t: per step the rungs are shuffled (rank of 64-bit Philox
+// keys, the same keys and tie-break as exact_order_kernel), every thread draws its walker's z / u / flags
+// from the same streams as the other kernels, builds the proposal from the OLD rows of its
 // walker and partner (src/mcmc/ensemble_sample.rs:155-159), evaluates the log-density with the plugin's
 // sequential interface -- the reference's left-to-right sums, so log-probs are bit-identical to the
 // oracle for the transcendental-free targets -- and, after a block barrier, commits accepted rows
@@ -69,31 +69,15 @@ __global__ void __launch_bounds__(1024, 1) step_small_kernel(const StepParams p,
         const uint64_t step = p.step + s;
         const uint64_t onehot = (p.onehot + (uint64_t)s * dim_mod) % p.dim;  // the cycling closure advances by n per step
 
-        // ---- matching order: the caller's (fixed streams) or the exact shuffle of every rung ----
-        uint32_t w = 0, partner = 0;
-        if (p.order) {
-            if (act) { w = __ldg(p.order + t); partner = __ldg(p.order + (t ^ 1u)); }
-        } else {
-            if (act) {
-                const U4 o = draw(p.seed, step, ST_PERM_KEY, p.w_off + t, 0);
-                keys[t] = ((uint64_t)o.y << 32) | o.x;
-            }
-            __syncthreads();
-            if (act) {
-                const uint32_t base = (t / p.npb) * p.npb;
-                const uint64_t kt = keys[t];
-                uint32_t rank = 0;
-                for (uint32_t jj = 0; jj < p.npb; ++jj) {
-                    const uint64_t kj = keys[base + jj];
-                    rank += (kj < kt) || (kj == kt && base + jj < t);
-                }
-                ord[base + rank] = t;
-            }
-            __syncthreads();
-            if (act) { w = ord[t]; partner = ord[t ^ 1u]; }
+        // thread t = walker t.  Its draws (shuffle key, z, u, flags) are independent of the matching, so the three
+        // Philox calls overlap instead of queueing behind the two barriers of the shuffle.
+        const uint32_t w = t;
+        uint64_t key = 0;
+        if (!p.order && act) {
+            const U4 o = draw(p.seed, step, ST_PERM_KEY, p.w_off + t, 0);
+            key = ((uint64_t)o.y << 32) | o.x;
+            keys[t] = key;
         }
-
-        // ---- z, u, flags of my walker (same streams as the streaming kernels) ----
         double z = 1.0, u = 1.0;
         if (p.z_in) {
             if (act) { z = __ldg(p.z_in + w); u = __ldg(p.u_in + w); }
@@ -105,6 +89,30 @@ __global__ void __launch_bounds__(1024, 1) step_small_kernel(const StepParams p,
         uint32_t nphi = p.dim;
         const bool all_flags = p.flag_kind == 1u;
         if (!all_flags) nphi = gen_flags(p, step, onehot, w, flagw, lane, act);
+        const double lz = (double)(nphi - 1u) * log(z);  // ensemble_sample.rs:184, first summand
+
+        // ---- partner: from the caller's matching (fixed streams) or the exact shuffle of every rung ----
+        uint32_t partner = 0;
+        if (p.order) {
+            if (act) ord[__ldg(p.order + t)] = __ldg(p.order + (t ^ 1u));  // walker at position t -> its partner
+            __syncthreads();
+            if (act) partner = ord[w];
+        } else {
+            __syncthreads();
+            uint32_t pos = 0;
+            if (act) {
+                const uint32_t base = (t / p.npb) * p.npb;
+                uint32_t rank = 0;
+                for (uint32_t jj = 0; jj < p.npb; ++jj) {
+                    const uint64_t kj = keys[base + jj];
+                    rank += (kj < key) || (kj == key && base + jj < t);
+                }
+                pos = base + rank;
+                ord[pos] = t;
+            }
+            __syncthreads();
+            if (act) partner = ord[pos ^ 1u];
+        }
 
         // ---- proposal from the old rows + log-density, one pass over the row ----
         bool accept = false;
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(1024, 1) step_small_kernel(const StepParams p,
             else lp_new = plug.finish();
             // Metropolis accept, ensemble_sample.rs:181-188
             const double beta = __ldg(p.beta + w / p.npb);
-            const double q = exp((double)(nphi - 1u) * log(z) + (lp_new - LP[w]) * beta);
+            const double q = exp(lz + (lp_new - LP[w]) * beta);
             accept = u < q;
         }
         __syncthreads();  // every thread has read the old rows it needs
