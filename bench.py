@@ -366,6 +366,33 @@ def main():
     stats = s.stats()
     value = n * args.steps / (ms * 1e-3)
 
+    # ---- the ladder swap on its own (reported separately; amortised into `value` above) ----
+    swap_stage = None
+    if swap_every and nbeta > 1 and can_swap and world == 1:
+        k_sw = 20
+        sw0 = stats["swapped"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k_sw):
+            swap(beta)
+            do_steps(1)              # a step in between, as in the drivers: the next swap sees fresh log-probs
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_both = e0.elapsed_time(e1) / k_sw
+        e0.record(stream)
+        do_steps(k_sw)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_step = e0.elapsed_time(e1) / k_sw
+        moved = (s.stats()["swapped"] - sw0) / k_sw          # accepted exchanges per call = rows moved / 2
+        sw_bytes = 16.0 * n + 2.0 * moved * 16.0 * dim       # lp read + write; every accepted exchange moves two rows
+        t_swap = max(t_both - t_step, 1e-6)
+        swap_stage = {"ms_per_call": t_swap, "accepted_exchanges_per_call": moved,
+                      "algorithmic_bytes_per_call": sw_bytes, "gbps": sw_bytes / (t_swap * 1e-3) / 1e9,
+                      "note": "swap + one step minus one step, 20 calls; bound by the chain kernel's B-1 dependent steps "
+                              "(latency), not by HBM"}
+        stats = s.stats()
+
     # ---- e2e: the reference-shaped call on pinned host buffers, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -504,6 +531,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "accept_rate": stats["accepted"] / max(1, stats["proposed"]),
     }
+    if swap_stage:
+        line["swap_stage"] = swap_stage
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
