@@ -270,7 +270,7 @@ int scorus::host::env_int(const char *name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
-int scorus::host::step_geometry(scorus_ctx *ctx, Geometry *g)
+int scorus::host::step_geometry(scorus_ctx *ctx, Geometry *g, bool tile_in_smem)
 {
     g->row_bytes = ctx->pitch * 8u;
     g->row_stride = g->row_bytes;
@@ -293,13 +293,19 @@ int scorus::host::step_geometry(scorus_ctx *ctx, Geometry *g)
     }
 
     if (g->kernel == KERNEL_REG) {
-        // one tile of proposed rows + the flag words per warp; at most 14 warps (448 threads)
-        // leave SCORUS_L1_KB (default 32) of the SM's unified array to L1: the row loads stream through
-        // it, and with the carve-out at its maximum the kernel ran 12 % slower (profiles/r1_notes.md)
-        const size_t per_warp = tile + flag_bytes;
-        const size_t l1_keep = (size_t)env_int("SCORUS_L1_KB", 32) * 1024u;
-        // mirrors reg_kernel_max_warps (step_reg_kernel.cuh): dense plugin 8, rows of <= 8 double2 16, else 14
-        uint32_t w = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN ? 8 : (ctx->pitch / 2 <= 16 ? 16 : 14);
+        // per warp: the flag words, plus -- for the kernels that stage proposals in shared memory (the dense target's
+        // tensor-core evaluation, the t-walk) -- one tile of 32 rows.  Those leave SCORUS_L1_KB (default 32) of the
+        // SM's unified array to L1: the row loads stream through it, and with the carve-out at its maximum the
+        // kernel ran 12 % slower (profiles/r1_notes.md).  The stretch move on the other targets keeps its proposals
+        // in registers (step_reg_kernel.cuh, kDirect) and is bound by registers only: 16 warps.
+        const bool dense = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN;
+        const uint32_t nvec = ctx->pitch / 2;
+        // mirrors reg_kernel_direct (step_reg_kernel.cuh): rows of 9..16 double2 (16-lane groups) keep the tile
+        const bool tiled = tile_in_smem || dense || (nvec > 8 && nvec <= 16);
+        const size_t per_warp = (tiled ? tile : 0) + flag_bytes;
+        const size_t l1_keep = tiled ? (size_t)env_int("SCORUS_L1_KB", 32) * 1024u : 0;
+        // mirrors reg_kernel_max_warps (step_reg_kernel.cuh): dense plugin 8, everything else 16
+        uint32_t w = dense ? 8 : 16;
         while (w >= 1 && w * per_warp > budget) --w;
         while (w > 8 && w * per_warp + l1_keep > budget) --w;
         if (w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);
@@ -343,7 +349,7 @@ extern "C" int scorus_init_logprob(scorus_ctx *ctx)
     if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
     cudaSetDevice(ctx->device);
     Geometry g;
-    int rc = step_geometry(ctx, &g);
+    int rc = step_geometry(ctx, &g, false);
     if (rc) return rc;
     StepParams p;
     memset(&p, 0, sizeof(p));
@@ -496,9 +502,9 @@ void scorus::host::count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t n
     for (size_t k = 0; k + 1 < nbeta; ++k) ctx->stage_proposed[k] += npb;
 }
 
-int scorus::host::fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta)
+int scorus::host::fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool tile_in_smem)
 {
-    int rc = step_geometry(ctx, g);
+    int rc = step_geometry(ctx, g, tile_in_smem);
     if (rc) return rc;
     memset(p, 0, sizeof(*p));
     p->ens = ctx->d_ens; p->lp = ctx->d_lp; p->beta = ctx->d_beta; p->pparams = ctx->d_params;

@@ -31,7 +31,7 @@ static int twalk_common(scorus_ctx *ctx, const scorus_twalk_params *tw, const do
         return fail(ctx, SCORUS_ERR_INVALID_ARG, "fw must be cumulative weights, 0 <= fw[0] <= fw[1], fw[1] > 0");
     cudaSetDevice(ctx->device);
     if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
-    if ((rc = fill_common(ctx, &tp->s, g, nbeta))) return rc;
+    if ((rc = fill_common(ctx, &tp->s, g, nbeta, true))) return rc;
     if (g->kernel != KERNEL_REG)
         return fail(ctx, SCORUS_ERR_INVALID_ARG, "the t-walk needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
     tp->aw = tw->aw;

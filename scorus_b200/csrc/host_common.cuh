@@ -120,14 +120,15 @@ namespace host {
 // api_core.cu
 int env_int(const char *name, int dflt);
 int ensure(scorus_ctx *ctx, void **buf, size_t *cap, size_t bytes);
-int step_geometry(scorus_ctx *ctx, Geometry *g);
+int step_geometry(scorus_ctx *ctx, Geometry *g, bool tile_in_smem);
 int upload_beta(scorus_ctx *ctx, const double *beta, size_t nbeta);
 void stamp_tiles(scorus_ctx *ctx, StepParams *p, const Geometry &g);
 uint32_t flag_bits_for(double prob);
 int ensure_rung_stats(scorus_ctx *ctx, size_t nbeta);
 void count_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb, uint64_t w_lo, uint64_t w_hi, uint64_t steps);
 void count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb);
-int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta);
+// tile_in_smem: the kernel about to be launched stages a 32-row tile of proposals per warp (t-walk; the dense target)
+int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool tile_in_smem = false);
 // kernels of swap_kernel.cuh, launched from more than one translation unit
 void launch_exact_order(scorus_ctx *ctx, uint64_t step, size_t nbeta, uint32_t npb, uint32_t *order, uint32_t w_off);
 void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv);

@@ -46,13 +46,18 @@ struct RegGeom {
 
 // kStaged: one-sided multi-GPU mode (remote partners' rows pulled into p.stage_ens / p.stage_lp).  A
 // template parameter because even uniform branches on it cost 12 % in the single-GPU kernel.
-// Warps per block (= per SM).  Rows of up to 16 double2 (G <= 16) fit 128 registers anyway: 16 warps measured
-// faster (10-D Rastrigin 0.156 -> 0.144 ms; 32-D: neutral for the stretch move, +11 % for the t-walk);
-// wider rows keep 14 warps and up to 146 registers (the 64-D kernel lost 3 % under the tighter cap).
+// Warps per block (= per SM): 16 under a 128-register cap; the dense plugin keeps 8 warps and up to 255 registers
+// for its DMMA accumulators.
 template <class Plugin, int G>
 constexpr int reg_kernel_max_warps()
 {
-    return Plugin::kMaxWarps == 14 && G <= 16 ? 16 : Plugin::kMaxWarps;
+    return Plugin::kMaxWarps == 14 ? 16 : Plugin::kMaxWarps;
+}
+
+template <class Plugin, int G>
+__host__ __device__ constexpr bool reg_kernel_direct()
+{
+    return !Plugin::kNeedsRow && G != 16;
 }
 
 template <class Plugin, int G, int ITERS, bool kStaged = false>
@@ -60,11 +65,16 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
 {
     using Geo = RegGeom<G, ITERS>;
     constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;
+    // direct: proposals never touch shared memory (only the flag words do).  The dense plugin keeps the y tile, which
+    // its tensor-core evaluation reads; so do rows of 9..16 double2 (G = 16): their tile is small enough for 16
+    // warps anyway, and deciding per block of 8 rows would run the scalar tail twice per tile at half occupancy
+    // (measured at 32-D: 0.129 ms with the tile, 0.148 ms direct)
+    constexpr bool kDirect = reg_kernel_direct<Plugin, G>();
 
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t tile_bytes = 32u * p.row_stride;
+    const uint32_t tile_bytes = kDirect ? 0u : 32u * p.row_stride;
     const uint32_t warp_bytes = tile_bytes + ((p.flag_words * 128u + 127u) & ~127u);
     unsigned char *ytile = smem + (size_t)warp * warp_bytes;
     uint32_t *flagw = reinterpret_cast<uint32_t *>(ytile + tile_bytes);
@@ -184,8 +194,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
             z = z_from_uniform(u53(r.x, r.y), p.inv_sqrt_a, p.z_range);
             u = u53(r.z, r.w);
         }
-        // the previous tile's accepted rows must have left the y tile / flag words before reuse
-        bulk_wait_read_all();
+        // the previous tile's accepted rows must have left the y tile before reuse
+        if constexpr (!kDirect) bulk_wait_read_all();
         __syncwarp();
         uint32_t nphi = p.dim;
         if (!all_flags) nphi = gen_flags(p, w, flagw, lane, act);
@@ -224,6 +234,9 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
         double tot[Plugin::kAcc];
 #pragma unroll
         for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
+        // global-matching mode: walkers outside [w_lo, w_hi) belong to another rank, which updates them
+        const bool mine = act && w >= p.w_lo && w < p.w_hi;
+        bool accept = false;
 
 #pragma unroll 1
         for (int blk = 0; blk < NB; ++blk) {
@@ -236,6 +249,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
             else if (tile_n < ntiles) load_block(xn, w_n, 0);
 
             double acc[Plugin::kAcc][GB];
+            [[maybe_unused]] double2 yk[kDirect ? GB : 1][ITERS];  // direct path: the block's proposals stay in registers
 #pragma unroll
             for (int pr = 0; pr < PB; ++pr) {
                 const uint32_t wa = grp * G + (uint32_t)(blk * GB + 2 * pr), wb = wa + 1u;
@@ -261,7 +275,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
                     { double t1 = xa.y * za, t2 = xb.y * omza; ya[it].y = (fa & 2u) ? t1 + t2 : xa.y; }
                     { double t1 = xb.x * zb, t2 = xa.x * omzb; yb[it].x = (fb & 1u) ? t1 + t2 : xb.x; }
                     { double t1 = xb.y * zb, t2 = xa.y * omzb; yb[it].y = (fb & 2u) ? t1 + t2 : xb.y; }
-                    if (c < nvec) {
+                    if constexpr (kDirect) {
+                        yk[2 * pr][it] = ya[it];
+                        yk[2 * pr + 1][it] = yb[it];
+                    } else if (c < nvec) {
                         rowa[c] = ya[it];
                         rowb[c] = yb[it];
                     }
@@ -304,31 +321,62 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
                     if ((int)(j / GB) == blk) tot[a] = r;
                 }
             }
+            if constexpr (kDirect) {
+                // ---- P5, per block: the lanes whose walkers are this block's rows decide (Metropolis accept,
+                // ensemble_sample.rs:181-188); accepted rows go from the registers of the group's lanes straight to
+                // global memory, one coalesced 16 G-byte burst per row and trip -- no shared-memory tile, so the
+                // block size is bound by registers only (16 warps per SM instead of 11 at 64-D)
+                bool acc_now = false;
+                if ((int)(j / GB) == blk) {
+                    const double lp_new = plug.finish_acc(tot);
+                    const double q = exp(lz + (lp_new - lp_old) * beta);
+                    acc_now = mine && (u < q);
+                    if (acc_now) {
+                        p.lp[w - p.w_lo] = lp_new;
+                        if (p.dirty) p.dirty[w - p.w_lo] = 1;
+                        ++n_acc;
+                        accept = true;
+                    }
+                }
+                const uint32_t accmask = __ballot_sync(0xffffffffu, acc_now);
+#pragma unroll
+                for (int i = 0; i < GB; ++i) {
+                    const uint32_t rl = grp * G + (uint32_t)(blk * GB + i);
+                    const uint32_t row = __shfl_sync(0xffffffffu, w, rl);
+                    if ((accmask >> rl) & 1u) {
+                        double2 *dst = reinterpret_cast<double2 *>(p.ens + (size_t)(row - p.w_lo) * p.pitch);
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it) {
+                            const uint32_t c = (uint32_t)it * G + j;
+                            if (c < nvec) dst[c] = yk[i][it];
+                        }
+                    }
+                }
+            }
         }
-        fence_proxy_async();  // my writes of the proposed rows -> visible to the TMA stores below
-        __syncwarp();
+        if constexpr (!kDirect) {
+            fence_proxy_async();  // my writes of the proposed rows -> visible to the TMA stores below
+            __syncwarp();
 
-        // ---- P5: lane = walker: Metropolis accept, ensemble_sample.rs:181-188 ----
-        unsigned char *own_b = ytile + lane * p.row_stride;
-        double lp_new;
-        if constexpr (Plugin::kNeedsRow) {
-            // K3: dense targets evaluate the whole tile of proposed rows on the fp64 tensor cores
-            lp_new = plug.tile_logprob(ytile, p.row_stride, lane);
-        } else {
-            lp_new = plug.finish_acc(tot);
+            // ---- P5: lane = walker: Metropolis accept, ensemble_sample.rs:181-188 ----
+            unsigned char *own_b = ytile + lane * p.row_stride;
+            double lp_new;
+            if constexpr (Plugin::kNeedsRow) {
+                // K3: dense targets evaluate the whole tile of proposed rows on the fp64 tensor cores
+                lp_new = plug.tile_logprob(ytile, p.row_stride, lane);
+            } else {
+                lp_new = plug.finish_acc(tot);
+            }
+            const double q = exp(lz + (lp_new - lp_old) * beta);
+            accept = mine && (u < q);
+            if (accept) {
+                bulk_store(p.ens + (size_t)(w - p.w_lo) * p.pitch, smem_u32(own_b), p.row_bytes);
+                p.lp[w - p.w_lo] = lp_new;
+                if (p.dirty) p.dirty[w - p.w_lo] = 1;
+                ++n_acc;
+            }
+            bulk_commit();
         }
-        const double delta_lp = lp_new - lp_old;
-        const double q = exp(lz + delta_lp * beta);
-        // global-matching mode: walkers outside [w_lo, w_hi) belong to another rank, which updates them
-        const bool mine = act && w >= p.w_lo && w < p.w_hi;
-        const bool accept = mine && (u < q);
-        if (accept) {
-            bulk_store(p.ens + (size_t)(w - p.w_lo) * p.pitch, smem_u32(own_b), p.row_bytes);
-            p.lp[w - p.w_lo] = lp_new;
-            if (p.dirty) p.dirty[w - p.w_lo] = 1;
-            ++n_acc;
-        }
-        bulk_commit();
         if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0;
         if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
 
@@ -339,7 +387,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
         lp_old = lp_n;
     }
 
-    bulk_wait_all();
+    if constexpr (!kDirect) bulk_wait_all();
     for (int off = 16; off; off >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, off);
     if (lane == 0 && n_acc) atomicAdd(p.stats, n_acc);
 }
