@@ -5,24 +5,26 @@
 // (:135-148), z draw (:149 -> utils.rs:33-45), update flags (:150-153 -> :38-54), proposal
 // (:155-159 -> :57-75 -> utils.rs:47-56), log-density (:161) and Metropolis accept (:164-189).
 //
-// Why a third shape (profiles/r1_notes.md has the measurements): staging the OLD rows in shared
-// memory (step_kernel.cuh, step_coop_kernel.cuh) costs two tiles of shared memory per warp, which
-// caps an SM at 6 warps for D = 64 -- 1.5 warps per scheduler cannot hide fp64 / LDS latency and
-// the kernel ran at 43 % of the HBM roofline, issue-bound.  Here the old rows never touch shared
-// memory:
-//   * a group of G lanes owns a pair; lane j loads double2 chunk j (+ k*G) of BOTH rows straight
-//     into registers with 128-bit coalesced loads (a row is one contiguous 16*G-byte burst), one
-//     block of 8 rows ahead of the arithmetic (software pipeline, 4 KB in flight per warp);
-//   * the proposals y = x1*z + x2*(1-z) (both walkers of the pair, from the old values) and their
-//     log-density terms are computed from registers; Rosenbrock's neighbour coordinate comes from
-//     the next lane by shuffle;
-//   * only the PROPOSED rows go to shared memory (one tile per warp -> 13 warps per SM at D = 64),
-//     and only accepted ones leave it, through TMA bulk stores (cp.async.bulk shared->global);
-//   * per-lane partial sums are combined by a transposed shuffle tree so that lane = walker for the
-//     scalar tail (exp, accept), as in the cooperative kernel.
-// HBM traffic stays at the algorithmic 16*D+16 bytes per walker-step (less: rejected rows are not
-// written).  Positions are bit-identical to the reference's rounding sequence; log-probs differ
-// from a left-to-right sum by a few ulp of the sum of |terms| (fixed tree, deterministic).
+// Why this shape (profiles/r1_notes.md has the measurements): staging the OLD rows in shared memory
+// (step_kernel.cuh, step_coop_kernel.cuh) costs two tiles of shared memory per warp, which caps an SM at 6
+// warps for D = 64 -- the kernel ran at 43 % of the HBM roofline, issue-bound.  Here:
+//   * a group of G lanes owns a pair; lane j loads double2 chunk j (+ k*G) of BOTH rows straight into
+//     registers with 128-bit coalesced loads (a row is one contiguous 16*G-byte burst), one block of 8 rows
+//     ahead of the arithmetic (software pipeline, 4 KB in flight per warp);
+//   * the proposals y = x1*z + x2*(1-z) (both walkers of the pair, from the old values) and their log-density
+//     terms are computed from registers; Rosenbrock's neighbour coordinate comes from the next lane by shuffle;
+//   * per-lane partial sums are combined by a transposed shuffle tree, which hands each row's total to the lane
+//     whose walker it is, so the scalar tail (exp, accept) runs with lane = walker;
+//   * direct mode (kDirect, the default): the tail runs per block of 8 rows and accepted rows go from the
+//     group's registers straight to global memory -- shared memory holds the flag words only and the block size
+//     is bound by registers (16 warps per SM: 0.64-0.66 ms per 2^22 x 64-D step);
+//   * tile mode (the dense target, whose tensor-core evaluation reads the tile; rows of 9..16 double2): the
+//     PROPOSED rows wait in a shared-memory tile, the tail runs once per tile and accepted rows leave through
+//     TMA bulk stores (cp.async.bulk shared->global).  This was the only mode at first (11 warps per SM at
+//     D = 64, 0.726 ms).
+// HBM traffic stays below the algorithmic 16*D+16 bytes per walker-step (rejected rows are not written).
+// Positions are bit-identical to the reference's rounding sequence; log-probs differ from a left-to-right
+// sum by a few ulp of the sum of |terms| (fixed tree, deterministic).
 #pragma once
 #include "step_coop_kernel.cuh"  // transpose_reduce
 #include "tile_common.cuh"
