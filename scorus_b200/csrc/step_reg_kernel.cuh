@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) ste
 #pragma unroll
                         for (int it = 0; it < ITERS; ++it) {
                             const uint32_t c = (uint32_t)it * G + j;
-                            if (c < nvec) dst[c] = yk[i][it];
+                            if (c < nvec) __stcs(dst + c, yk[i][it]);  // written once, next read a whole step away
                         }
                     }
                 }
