@@ -104,15 +104,19 @@ int scorus_device_count(void);
 int scorus_check_sample_args(size_t n_walkers, size_t logprob_len, size_t nbeta);
 int scorus_check_beta_order(const double *beta_list, size_t nbeta);
 
-/* ---- context: owns the device copy of (ensemble, logprob) ---- */
+/* ---- context: owns the device copy of (ensemble, logprob), i.e. of the `ensemble: &mut [V]` and
+ * `cached_logprob: &mut [T]` arguments every reference call takes (src/mcmc/ensemble_sample.rs:89-90, :109-110;
+ * src/mcmc/utils.rs:73-74) ---- */
 int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg);
 void scorus_ctx_destroy(scorus_ctx *ctx);
 const char *scorus_last_error(const scorus_ctx *ctx);
 
-/* registers the log-density; replaces the `flogprob` argument of every reference call */
+/* registers the log-density; replaces the `flogprob: &F` argument of every reference call
+ * (src/mcmc/ensemble_sample.rs:78, :88, :108; bounds :102) */
 int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *params, size_t nparams);
 
-/* host <-> device. logprob == NULL on upload runs init_logprob on the device. */
+/* host <-> device: the caller's `&mut [V]` / `&mut [T]` slices (src/mcmc/ensemble_sample.rs:109-110) as flat
+ * walker-major arrays.  logprob == NULL on upload runs init_logprob (:77-85) on the device. */
 int scorus_upload(scorus_ctx *ctx, const double *ensemble, const double *logprob);
 int scorus_download(scorus_ctx *ctx, double *ensemble, double *logprob);
 
@@ -188,7 +192,7 @@ int scorus_twalk_half_fixed(scorus_ctx *ctx, const scorus_twalk_params *tw, cons
 /* twalk::sample on caller-owned host buffers (`ensemble_logprob: &mut (W, X)`, :588): upload, nsteps, download */
 int scorus_twalk_sample_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
                              const scorus_twalk_params *tw, const double *beta_list, size_t nbeta, uint64_t nsteps);
-/* the device stream's sim_b value of walkers [0, count) at step counter `step` (the one draw that goes through
+/* the device stream's sim_b value (src/mcmc/twalk.rs:306-322) of walkers [0, count) at step counter `step` (the one draw that goes through
  * pow(); exposed so that a device-stream run can be replayed exactly through scorus_twalk_half_fixed) */
 int scorus_twalk_draw_b(scorus_ctx *ctx, double at, uint64_t step, size_t count, double *out);
 
@@ -215,11 +219,11 @@ int scorus_hmc_sample_ensemble_pt(scorus_ctx *ctx, double *epsilon, const double
 int scorus_hmc_sample_ensemble_pt_fixed(scorus_ctx *ctx, double *epsilon, const double *beta_list, size_t nbeta, size_t l,
                                         const scorus_hmc_param *param, const double *p0, const double *u1,
                                         const double *u2, uint8_t *accepted_out, uint64_t *accepted_cnt);
-/* sample_ensemble_pt on caller-owned host buffers (q0: &mut [V], lp: &mut [T]): upload, one step, download */
+/* sample_ensemble_pt on caller-owned host buffers (q0: &mut [V], lp: &mut [T], src/mcmc/hmc/naive.rs:125-126): upload, one step, download */
 int scorus_hmc_sample_ensemble_pt_host(scorus_ctx *ctx, double *q0, double *logprob, size_t logprob_len, double *epsilon,
                                        const double *beta_list, size_t nbeta, size_t l, const scorus_hmc_param *param,
                                        uint64_t *accepted_cnt);
-/* the device stream's momenta of walkers [0, count) at step counter `step`, out[count][dim] (they go through
+/* the device stream's momenta (the draws of src/mcmc/hmc/naive.rs:182-192) of walkers [0, count) at step counter `step`, out[count][dim] (they go through
  * log / sqrt / sincos; exposed so that a device-stream run can be replayed exactly through the _fixed entry point) */
 int scorus_hmc_draw_momenta(scorus_ctx *ctx, uint64_t step, size_t count, double *out);
 
@@ -255,7 +259,8 @@ int scorus_get_rung_stats(scorus_ctx *ctx, size_t nrungs, uint64_t *accepted, ui
  * scorus_moments_download reports nsamples = accumulations x walkers per rung; cov_out may be NULL. */
 int scorus_moments_enable(scorus_ctx *ctx, size_t nrungs, uint64_t every, int with_cov);
 int scorus_moments_download(scorus_ctx *ctx, size_t rung, double *mean_out, double *cov_out, uint64_t *nsamples);
-/* Integrated autocorrelation time of every captured series (scorus_trace_enable), from the rows recorded so
+/* No reference counterpart (the drivers only record the chains, examples/sample_bimodal.rs:137-139).
+ * Integrated autocorrelation time of every captured series (scorus_trace_enable), from the rows recorded so
  * far (the buffer is not rewound): C(k) = sum_{t<T-k} (x_t - m)(x_{t+k} - m) / T for k <= max_lag (0 = T-1),
  * tau(M) = 1 + 2 sum_{k=1..M} C(k)/C(0) with Sokal's window, M = the first lag with M >= c_window * tau(M)
  * (max_lag if none: check window_out).  tau_out / window_out / mean_out / var_out (= C(0)) have ncapture
@@ -263,7 +268,9 @@ int scorus_moments_download(scorus_ctx *ctx, size_t rung, double *mean_out, doub
 int scorus_trace_iat(scorus_ctx *ctx, double c_window, size_t max_lag, double *tau_out, uint32_t *window_out,
                      double *mean_out, double *var_out);
 
-/* ---- sharding: one process per GPU ----
+/* ---- sharding: one process per GPU.  No reference counterpart (the reference is one
+ * process); what makes it exact is that the pairing never leaves a rung (src/mcmc/ensemble_sample.rs:136-146) and
+ * that swap_walkers only couples adjacent rungs (src/mcmc/utils.rs:89-108) ----
  * scorus_set_shard tells a context which slice of the whole ensemble it holds: its walker i is
  * global walker walker_offset + i, its rung r is global rung rung_offset + r.  The device streams are
  * keyed by global ids, so a sharded run draws exactly what a single-GPU run of the whole ensemble
@@ -282,13 +289,14 @@ int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_ufs *ufs, co
 int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta_list, size_t nbeta, double *lp_all,
                             uint32_t *src_all);
 
-/* One-sided partner exchange: scorus_ipc_export fills two 64-byte CUDA IPC handles (ensemble,
+/* One-sided partner exchange (the rows `ensemble[i.1]` of src/mcmc/ensemble_sample.rs:157 that live on another GPU):
+ * scorus_ipc_export fills two 64-byte CUDA IPC handles (ensemble,
  * log-probs); after the ranks have exchanged them (any transport), scorus_ipc_attach maps every
  * peer's buffers so that kernels of this context can read partner rows straight over NVLink. */
 int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens_64b, void *handle_lp_64b);
 int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_ens, const void *handles_lp);
 
-/* sample_pt of a walker shard with the reference's whole-ensemble matching, WITHOUT an all-gather:
+/* sample_pt of a walker shard with the reference's whole-ensemble matching (src/mcmc/ensemble_sample.rs:135-148), WITHOUT an all-gather:
  * _begin builds the local pair list and pulls only the remote partners' rows over NVLink (one-sided
  * reads of the peers mapped by scorus_ipc_attach); _end runs the fused step.  The caller inserts a
  * stream-ordered barrier across ranks before _begin and between _begin and _end (peers must not
@@ -296,25 +304,30 @@ int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_
 int scorus_sample_pt_p2p_begin(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
 int scorus_sample_pt_p2p_end(scorus_ctx *ctx);
 
-/* Applies a swap plan to this rank's slots with one-sided reads of the peers (scorus_ipc_attach):
+/* Applies a swap plan (the row and log-prob exchanges of src/mcmc/utils.rs:106-107) to this rank's slots with one-sided
+ * reads of the peers (scorus_ipc_attach):
  * phase 0 pulls every incoming row into scratch, the caller barriers across ranks, phase 1 commits
  * rows and log-probs.  Equal shards (n_global = world * n_local). */
 int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, const double *lp_all, int phase);
 
-/* ---- plumbing ---- */
+/* ---- plumbing (no reference counterpart: the reference call returns when the step is done; these calls are
+ * asynchronous on the context's stream unless they return host data) ---- */
 int scorus_sync(scorus_ctx *ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream; NULL is CUDA's legacy default
  * stream, as everywhere in CUDA); scorus_reset_stream returns to the context's own stream */
 int scorus_set_stream(scorus_ctx *ctx, void *cuda_stream);
 int scorus_reset_stream(scorus_ctx *ctx);
 void *scorus_get_stream(scorus_ctx *ctx);
-/* device pointers of the resident state: ensemble rows are pitch_elems doubles apart */
+/* device pointers of the resident state (the device-side `ensemble` / `cached_logprob`, src/mcmc/ensemble_sample.rs:
+ * 109-110): ensemble rows are pitch_elems doubles apart */
 int scorus_device_buffers(scorus_ctx *ctx, double **ensemble, size_t *pitch_elems, double **logprob);
-/* RNG position = (step counter, swap-call counter, one-hot cycle counter); with the seed and a
+/* what is left of `rng: &mut U` (src/mcmc/ensemble_sample.rs:111, src/mcmc/utils.rs:75) on the device:
+ * RNG position = (step counter, swap-call counter, one-hot cycle counter); with the seed and a
  * download this is a complete checkpoint */
 int scorus_get_counters(const scorus_ctx *ctx, uint64_t *step, uint64_t *swap_call, uint64_t *onehot);
 int scorus_set_counters(scorus_ctx *ctx, uint64_t step, uint64_t swap_call, uint64_t onehot);
-/* running totals since creation (synchronises): accepted / proposed moves, accepted / proposed swaps */
+/* the accept branch of src/mcmc/ensemble_sample.rs:185-188 and the swap branch of src/mcmc/utils.rs:105-107, counted:
+ * running totals since creation (synchronises): accepted / proposed moves, accepted / proposed swaps */
 int scorus_get_stats(scorus_ctx *ctx, uint64_t *accepted, uint64_t *proposed, uint64_t *swapped,
                      uint64_t *swap_proposed);
 /* number of kernels this library has launched on this context since creation */
