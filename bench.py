@@ -511,7 +511,12 @@ def main():
                     "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
                     "algorithmic_bytes_per_walker_step": b_alg(dim), "walkers_per_launch": n_local,
                     "note": "launch time = device time of the timed region / steps (one step kernel launch per step"
-                            + (", swap kernels amortised in)" if swap_every else ")")}
+                            + (", swap kernels amortised in)" if swap_every else ")")
+                            + "; the algorithmic figure counts every row as written, the kernel writes accepted rows "
+                              "only, so frac can exceed 1: traffic_frac is the ncu-measured DRAM traffic over the same "
+                              "time against the same peak"}
+        if traffic:
+            roofline["traffic_frac"] = traffic * args.steps / (ms * 1e-3) / 1e9 / peak
 
     cpu = None
     if not args.no_cpu and world == 1 and args.move == "stretch":
