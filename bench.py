@@ -480,7 +480,7 @@ def main():
         kernel_name = "hmc_kernel (10 leapfrog steps per walker in registers: bound by fp64 arithmetic, not HBM)"
     traffic = None
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(prof) and args.move == "stretch":
+    if os.path.exists(prof) and args.move == "stretch" and world == 1 and not args.n_walkers:  # measured for this exact launch shape
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
     if kind == 6:
         # dense quadratic form: 2 D^2 + 2 D flops per walker-step against an fp64 DGEMM
