@@ -41,6 +41,21 @@ static int twalk_common(scorus_ctx *ctx, const scorus_twalk_params *tw, const do
     tp->fw1 = tw->fw[1];
     tp->kernel_in = nullptr; tp->b_in = nullptr; tp->walk_u_in = nullptr;
     tp->l2_keep = (uint32_t)env_int("SCORUS_TWALK_L2", 1);
+    // twalk_direct_kernel.cuh: no shared-memory tile (flag words + a short z list per walker), 16 warps per SM.
+    // Measured: 2.28 -> 2.00 ms per step at 64-D (the tile held the SM at 11 warps); at 10-D, where the tile is small
+    // and a one-block tile cannot prefetch its own re-read, 0.201 -> 0.209 ms: rows of up to 16 double2 keep the tile.
+    // SCORUS_TWALK_DIRECT=0 / 2 forces the tile / the direct kernel wherever it exists.
+    const uint32_t nvec = ctx->pitch / 2;
+    const int want_direct = env_int("SCORUS_TWALK_DIRECT", 1);
+    if (want_direct && ctx->lp_kind != SCORUS_LP_CORR_GAUSSIAN && (nvec > 16 || (want_direct == 2 && !(nvec > 8 && nvec <= 16)))) {
+        tp->direct = 1;
+        const size_t per_warp = (((size_t)g->flag_words * 128u + 127u) & ~(size_t)127u) + 32u * 8u * sizeof(double);
+        const uint32_t ntiles = (uint32_t)((ctx->n + 31u) / 32u);
+        g->warps = 16;
+        g->smem = g->warps * per_warp;
+        g->grid = std::min<uint32_t>((uint32_t)ctx->num_sms, (ntiles + g->warps - 1) / g->warps);
+        tp->s.warps = g->warps;
+    }
     StepParams &p = tp->s;
     p.flag_kind = SCORUS_UFS_PROB;
     p.flag_bits = flag_bits_for(tw->pphi);

@@ -42,6 +42,7 @@ struct TwalkParams {
                                 // fused, the second keyed by step counter s.step + 1
     uint32_t l2_keep;           // fused mode, L2 policy of the first read of a row (it is read again ~20 us later):
                                 // 1 evict_last, 2 evict_normal, 0 no hint (SCORUS_TWALK_L2)
+    uint32_t direct;            // launch twalk_direct_kernel (no shared-memory tile) where the plugin / row width allow
 };
 
 // 128-bit streaming load with an explicit L2 eviction policy.  The plain L1::no_allocate load is treated as

@@ -1,6 +1,7 @@
 // twalk_plugin.cu -- instantiates the t-walk half-pass kernel for ONE log-density plugin and exports its
 // launcher.  Compiled once per plugin with -DSCORUS_PLUGIN=<struct name> (see Makefile).
 #include "launch.cuh"
+#include "twalk_direct_kernel.cuh"
 #include "twalk_kernel.cuh"
 
 #ifndef SCORUS_PLUGIN
@@ -37,6 +38,17 @@ cudaError_t SCORUS_CAT(launch_twalk_, SCORUS_PLUGIN)(const TwalkParams &tp, cons
 {
     using Plugin = SCORUS_PLUGIN;
     const uint32_t nvec = tp.s.pitch / 2;
+    if constexpr (!Plugin::kNeedsRow) {
+        if (tp.direct && !(nvec > 8 && nvec <= 16)) {  // mirrors reg_kernel_direct (step_reg_kernel.cuh)
+            if (nvec == 5 || nvec == 6) return launch_twalk_kernel(twalk_direct_kernel<Plugin, 2, 3>, tp, g, st);
+            if (nvec > 64) return launch_twalk_kernel(twalk_direct_kernel<Plugin, 32, 4>, tp, g, st);
+            if (nvec > 32) return launch_twalk_kernel(twalk_direct_kernel<Plugin, 32, 2>, tp, g, st);
+            if (nvec > 16) return launch_twalk_kernel(twalk_direct_kernel<Plugin, 32, 1>, tp, g, st);
+            if (nvec > 4) return launch_twalk_kernel(twalk_direct_kernel<Plugin, 8, 1>, tp, g, st);
+            if (nvec > 2) return launch_twalk_kernel(twalk_direct_kernel<Plugin, 4, 1>, tp, g, st);
+            return launch_twalk_kernel(twalk_direct_kernel<Plugin, 2, 1>, tp, g, st);
+        }
+    }
     if (nvec == 5 || nvec == 6) return launch_twalk_kernel(twalk_half_kernel<Plugin, 2, 3>, tp, g, st);
     if (nvec > 64) return launch_twalk_kernel(twalk_half_kernel<Plugin, 32, 4>, tp, g, st);
     if (nvec > 32) return launch_twalk_kernel(twalk_half_kernel<Plugin, 32, 2>, tp, g, st);

@@ -55,7 +55,13 @@ def _start(oracle, kind, params, n, dim, box, g):
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}")
 @pytest.mark.parametrize("pphi", [None, 1.0], ids=["pphi_default", "pphi_1"])
-def test_half_pass_fixed_stream_vs_oracle(sb, oracle, case, pphi):
+@pytest.mark.parametrize("kernel", ["default", "tile", "direct"])
+def test_half_pass_fixed_stream_vs_oracle(sb, oracle, case, pphi, kernel, monkeypatch):
+    """kernel: the default choice, the shared-memory-tile kernel forced (twalk_kernel.cuh), or the register kernel
+    forced wherever it exists (twalk_direct_kernel.cuh; pphi = 1 exercises its in-loop draws: more flagged coordinates
+    than the per-walker z list holds)."""
+    if kernel != "default":
+        monkeypatch.setenv("SCORUS_TWALK_DIRECT", "0" if kernel == "tile" else "2")
     kind, params, n, dim, nb, box = case
     g = np.random.default_rng(n * 31 + dim)
     params = _params_for(kind, params, dim, g)
@@ -85,9 +91,12 @@ def test_half_pass_fixed_stream_vs_oracle(sb, oracle, case, pphi):
                                                   (2, [], 4096, 20, 2),
                                                   (3, [10.0], 8192, 10, 2),     # rungs above 1024 walkers: keyed-bijection matching
                                                   (0, [0.5], 4096, 32, 1), (0, [0.5], 2048, 130, 1)])
-def test_device_streams_replay_through_oracle(sb, oracle, kind, params, n, dim, nb):
+@pytest.mark.parametrize("kernel", ["default", "tile", "direct"])
+def test_device_streams_replay_through_oracle(sb, oracle, kind, params, n, dim, nb, kernel, monkeypatch):
     """twalk::sample on the device streams == the oracle fed the CPU restatement of those streams (b taken from
-    the device: the one draw that goes through pow())."""
+    the device: the one draw that goes through pow()); with the default kernel choice and with either kernel forced."""
+    if kernel != "default":
+        monkeypatch.setenv("SCORUS_TWALK_DIRECT", "0" if kernel == "tile" else "2")
     g = np.random.default_rng(5)
     beta = 2.0 ** (-np.arange(nb, dtype=np.float64))
     ens, lp = _start(oracle, kind, params, n, dim, (0.5, 1.5), g)
