@@ -34,9 +34,10 @@ static cudaError_t launch_twalk_kernel(K kernel, const TwalkParams &tp, const Ge
     return cudaGetLastError();
 }
 
-cudaError_t SCORUS_CAT(launch_twalk_, SCORUS_PLUGIN)(const TwalkParams &tp, const Geometry &g, cudaStream_t st)
+// a template so that `if constexpr` really discards the register kernel for the dense plugin
+template <class Plugin>
+static cudaError_t launch_twalk_impl(const TwalkParams &tp, const Geometry &g, cudaStream_t st)
 {
-    using Plugin = SCORUS_PLUGIN;
     const uint32_t nvec = tp.s.pitch / 2;
     if constexpr (!Plugin::kNeedsRow) {
         if (tp.direct && !(nvec > 8 && nvec <= 16)) {  // mirrors reg_kernel_direct (step_reg_kernel.cuh)
@@ -61,6 +62,11 @@ cudaError_t SCORUS_CAT(launch_twalk_, SCORUS_PLUGIN)(const TwalkParams &tp, cons
     case 16: return launch_twalk_kernel(twalk_half_kernel<Plugin, 16, 1>, tp, g, st);
     default: return launch_twalk_kernel(twalk_half_kernel<Plugin, 32, 1>, tp, g, st);
     }
+}
+
+cudaError_t SCORUS_CAT(launch_twalk_, SCORUS_PLUGIN)(const TwalkParams &tp, const Geometry &g, cudaStream_t st)
+{
+    return launch_twalk_impl<SCORUS_PLUGIN>(tp, g, st);
 }
 
 }  // namespace scorus
