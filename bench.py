@@ -314,14 +314,12 @@ def main():
 
     tw = sb.TWalkParams.new(dim)
 
-    hmc_eps = np.full(nbeta if world == 1 else nb_local, {2: 0.002, 3: 0.02}.get(kind, 0.1))
+    hmc_eps = np.full(nbeta, {2: 0.002, 3: 0.02}.get(kind, 0.1))   # the whole ladder's step sizes (a rank uses its rungs')
     hmc_param = sb.HmcParam.fixed(0.8)
 
     def do_steps(count):
         if args.move == "hmc":
-            if world > 1:
-                raise SystemExit("--move hmc is a single-GPU measurement")
-            s.hmc_sample_ensemble_pt(hmc_eps, beta, 10, hmc_param, count)
+            s.hmc_sample_ensemble_pt(hmc_eps, beta, 10, hmc_param, count)   # walkers are independent: no exchange on any sharding
         elif args.move == "twalk":
             s.twalk_sample(tw, beta, count)
         else:
