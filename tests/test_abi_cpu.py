@@ -29,6 +29,22 @@ def test_library_exports_every_declared_symbol(sb):
     assert lib.scorus_abi_version() == 1
 
 
+def test_rust_sys_and_cpp_mirror_cover_the_header():
+    """The Rust -sys crate (source only: no toolchain here) declares every function of the header and nothing else;
+    the C++ mirror includes the header itself, so it only has to parse."""
+    rs = open(os.path.join(ROOT, "rust", "scorus-b200-sys", "src", "lib.rs")).read()
+    declared_rs = sorted(set(re.findall(r"pub fn (scorus_[a-z0-9_]+)", rs)))
+    assert declared_rs == _header_functions()
+    for struct in ("scorus_cfg", "scorus_ufs", "scorus_twalk_params", "scorus_hmc_param"):
+        assert f"pub struct {struct}" in rs
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "driver_like_reference.cpp")], check=True, env=env)
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "scorus_b200.h")],
+                   check=True, env=env)
+
+
 def test_status_strings_and_mcmc_err_codes(sb):
     from scorus_b200 import _lib
     lib = _lib.load()
