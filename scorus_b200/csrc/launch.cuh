@@ -5,6 +5,15 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Shape of the register-streaming stretch kernel (step_reg_kernel.cuh), shared with the host geometry.  Rows wider
+// than 16 double2 and up to 64 (G = 32, one or two chunks per lane) run 4 rows per software-pipeline block under a 96-register
+// cap, 20 warps per SM: the kernel is latency-bound and more resident warps pay (2^22 x 64-D: 0.64 -> 0.61 ms);
+// narrower rows keep 8 rows per block and 16 warps (10-D lost 5 % with the tighter cap).
+#define SCORUS_REG_ROWS_WIDE 4
+#define SCORUS_REG_WARPS_WIDE 20
+#define SCORUS_REG_ROWS 8
+#define SCORUS_REG_WARPS 16
+
 namespace scorus {
 
 struct StepParams;

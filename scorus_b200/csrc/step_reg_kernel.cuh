@@ -26,6 +26,7 @@
 // Positions are bit-identical to the reference's rounding sequence; log-probs differ from a left-to-right
 // sum by a few ulp of the sum of |terms| (fixed tree, deterministic).
 #pragma once
+#include "launch.cuh"            // SCORUS_REG_ROWS, SCORUS_REG_WARPS
 #include "step_coop_kernel.cuh"  // transpose_reduce
 #include "tile_common.cuh"
 
@@ -41,17 +42,25 @@ __device__ __forceinline__ double2 ld_stream(const double2 *p)
 
 template <int G, int ITERS>
 struct RegGeom {
-    static constexpr int kRowsPerBlock = (G < 8 / ITERS) ? G : (8 / ITERS < 2 ? 2 : 8 / ITERS);  // GB
+    static constexpr int kRows = (G == 32 && ITERS <= 2) ? SCORUS_REG_ROWS_WIDE : SCORUS_REG_ROWS;
+    static constexpr int kRowsPerBlock = (G < kRows / ITERS) ? G : (kRows / ITERS < 2 ? 2 : kRows / ITERS);  // GB
     static constexpr int kPairs = kRowsPerBlock / 2;
     static constexpr int kBlocks = G / kRowsPerBlock;
 };
 
 // kStaged: one-sided multi-GPU mode (remote partners' rows pulled into p.stage_ens / p.stage_lp).  A
 // template parameter because even uniform branches on it cost 12 % in the single-GPU kernel.
-// Warps per block (= per SM): 16 under a 128-register cap; the dense plugin keeps 8 warps and up to 255 registers
-// for its DMMA accumulators.
-template <class Plugin, int G>
+// Warps per block (= per SM): 20 under a 96-register cap for rows wider than 16 double2 (launch.cuh), 16 under 128
+// registers otherwise; the dense plugin keeps 8 warps and up to 255 registers for its DMMA accumulators.
+template <class Plugin, int G, int ITERS>
 constexpr int reg_kernel_max_warps()
+{
+    return Plugin::kMaxWarps == 14 ? ((G == 32 && ITERS <= 2) ? SCORUS_REG_WARPS_WIDE : SCORUS_REG_WARPS) : Plugin::kMaxWarps;
+}
+
+// the t-walk kernels (twalk_kernel.cuh, twalk_direct_kernel.cuh) keep 16 warps: they need up to 128 registers
+template <class Plugin, int G>
+constexpr int twalk_max_warps()
 {
     return Plugin::kMaxWarps == 14 ? 16 : Plugin::kMaxWarps;
 }
@@ -63,7 +72,7 @@ __host__ __device__ constexpr bool reg_kernel_direct()
 }
 
 template <class Plugin, int G, int ITERS, bool kStaged = false>
-__global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) step_reg_kernel(const StepParams p)
+__global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32, 1) step_reg_kernel(const StepParams p)
 {
     using Geo = RegGeom<G, ITERS>;
     constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;

@@ -19,7 +19,7 @@ namespace scorus {
 constexpr uint32_t kTwalkZList = 8;  // Walk z values parked per walker; a walker with more flagged coordinates draws in the loop
 
 template <class Plugin, int G, int ITERS>
-__global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G>() * 32, 1) twalk_direct_kernel(const TwalkParams tp)
+__global__ void __launch_bounds__(twalk_max_warps<Plugin, G>() * 32, 1) twalk_direct_kernel(const TwalkParams tp)
 {
     constexpr int kWant = SCORUS_TW_ROWS / ITERS < 2 ? 2 : SCORUS_TW_ROWS / ITERS;
     constexpr int GB = G < kWant ? G : kWant, PB = GB / 2, NB = G / GB;
