@@ -158,12 +158,25 @@ def cpu_reference_leg(wl, steps, warmup, sample_walkers=None, target_seconds=12.
     t, stage = po.ref_structure_run(kind, params, ens, lp, beta, 2.0, ukind, prob, 12, k, cores)
     value = n_s * k / t
     names = ["pairing", "z", "flags", "proposal", "logprob", "accept"]
+    # the best-effort flat CPU variant: contiguous buffers, every stage threaded, the device's counter-based
+    # streams -- so that the GPU is not only compared with an allocation-bound structure
+    flat = None
+    if ufs != "onehot":
+        e2, l2 = ens.copy(), lp.copy()
+        tf1 = po.flat_threaded_run(kind, params, e2, l2, beta, 2.0, ukind, prob, 13, 0, 1, cores)
+        kf = int(max(1, min(steps, 0.5 * target_seconds / max(tf1, 1e-6))))
+        tf = po.flat_threaded_run(kind, params, e2, l2, beta, 2.0, ukind, prob, 13, 1, kf, cores)
+        if tf > 0:
+            flat = {"value": n_s * kf / tf, "unit": "walker-steps/s", "cores": cores, "steps": kf,
+                    "note": "flat buffers, all stages threaded (oracle/ref_structure_bench.c: orc_flat_threaded_run): what a "
+                            "CPU rewrite could do, not what the reference does"}
     return {
         "value": value, "unit": "walker-steps/s", "cores": cores, "kind": "port",
         "sample": f"{k} steps of the first {n_s} walkers ({nb_s} rung(s)) of {desc}; reference-structured C port "
                   f"(per-walker heap vectors, serial stages, log-density on {cores} threads)",
         "seconds": t, "steps": k, "n_walkers": n_s,
         "stage_share": {nm: float(s / stage.sum()) for nm, s in zip(names, stage)},
+        "flat_threaded": flat,
     }
 
 
@@ -253,7 +266,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n_walkers": n, "dim": dim, "nbeta": nbeta, "ufs": ufs, "prob": prob, "a": 2.0,
                        "sample_walkers": r["n_walkers"]},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share", "flat_threaded")},
             "e2e": {"value": r["value"], "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -519,7 +532,7 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1 and args.move == "stretch":
         cpu = cpu_reference_leg(args.workload, 20, 1)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share")}
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_share", "flat_threaded")}
     elif not args.no_cpu and world == 1:
         cpu = cpu_move_leg(args.workload, args.move)
 
