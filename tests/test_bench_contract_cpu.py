@@ -22,6 +22,9 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the best-effort flat CPU variant is reported beside the reference-structured port
+    assert cb["flat_threaded"]["value"] > 0 and cb["flat_threaded"]["unit"] == d["unit"]
+    assert abs(sum(cb["stage_share"].values()) - 1.0) < 1e-9
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -38,3 +41,13 @@ def test_workloads_cover_baseline_configs():
     assert (w["c4"][2], w["c4"][3], w["c4"][4]) == (64 * 16384, 10, 64)  # 64 rungs x 16,384, 10-D Rastrigin
     assert (w["c5"][2], w["c5"][3]) == (1 << 22, 64)                 # 64-D Rosenbrock, 2^22 walkers
     assert bench.b_alg(64) == 1040 and bench.b_alg(10) == 176        # 16 D + 16 bytes per walker-step
+
+
+def test_cpu_legs_of_the_other_move_families():
+    """bench.py --move twalk|hmc time the serial C restatements on a bounded sample as their cpu_baseline."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    for move in ("twalk", "hmc"):
+        r = bench.cpu_move_leg("c4", move, target_seconds=0.5)
+        assert r["value"] > 0 and r["cores"] == 1 and r["kind"] == "port" and move in r["sample"].replace("t-walk", "twalk")
