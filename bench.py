@@ -232,11 +232,15 @@ def main():
                          "(twalk::sample, SURVEY 8(f) rank 2), hmc = ensemble-PT HMC (hmc::naive::sample_ensemble_pt, rank 3; "
                          "10 leapfrog steps, fixed step size) on the same workload: extra measurements")
     ap.add_argument("--n-walkers", type=int, default=0, help="experiments only: override the workload's ensemble size")
-    ap.add_argument("--global-every", type=int, default=1,
-                    help="with --matching global/p2p: whole-ensemble matching every k-th step, shard-local in between")
-    ap.add_argument("--matching", default="local", choices=["local", "global", "p2p"],
-                    help="N>1, single temperature: shard-local matchings (no per-step exchange) or the "
-                         "reference's whole-ensemble matching over an NCCL all-gather per step")
+    ap.add_argument("--global-every", type=int, default=4,
+                    help="N>1, --matching p2p/global: the whole-ensemble matching on every k-th step, shard-local (blocked) "
+                         "matching in between; 1 = the reference's matching on every step")
+    ap.add_argument("--matching", default="p2p", choices=["local", "global", "p2p"],
+                    help="N>1, single temperature: p2p = the reference's whole-ensemble matching, one-sided over NVLink "
+                         "(pair owner reads / writes the partner's row in the peer's HBM); global = the same over an NCCL "
+                         "all-gather of the ensemble per step; local = shard-local matchings only (no exchange: the "
+                         "replica upper bound)")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the sharded-vs-single-GPU parity cases before timing")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -291,6 +295,17 @@ def main():
     stream = torch.cuda.Stream()  # the launch stream; the CUDA events below are recorded on it
     torch.cuda.set_stream(stream)
     beta = betas(nbeta)
+    parity_check = None
+    if world > 1 and not args.no_verify and args.move == "stretch":
+        # sharded chain == single-GPU chain, in the modes the lines below are measured in (scorus_b200/selfcheck.py)
+        from scorus_b200.selfcheck import sharded_parity_cases
+        log = []
+        cases, same = sharded_parity_cases(quick=True, log=log.append)
+        parity_check = {"cases": cases, "identical": bool(same), "world": world, "log": log}
+        if not same:
+            if rank == 0:
+                print("\n".join(log), file=sys.stderr)
+            raise SystemExit("sharded run differs from the single-GPU chain: not timing it")
     if world > 1:
         from scorus_b200.distributed import ShardedSampler
         s = ShardedSampler(sb.LogProb(kind, tuple(params)), n, dim, nbeta=nbeta, seed=2024, matching=args.matching,
@@ -302,11 +317,12 @@ def main():
         elif args.matching == "global":
             parallelism = f"walker shards x{world}, whole-ensemble matching, NCCL all-gather of the ensemble per step"
         elif args.matching == "p2p":
-            parallelism = f"walker shards x{world}, whole-ensemble matching, one-sided NVLink reads of remote partners"
+            parallelism = (f"walker shards x{world}, cross-shard exchange: whole-ensemble matching, pair owner reads / writes "
+                           "the remote partner's row one-sidedly over NVLink, one flag barrier per step")
         else:
-            parallelism = f"walker shards x{world}, shard-local matching (no per-step exchange)"
+            parallelism = f"walker shards x{world}, shard-local matching only (no exchange: replica upper bound)"
         if s.mode == "walkers" and args.matching != "local" and args.global_every > 1:
-            parallelism += f" every {args.global_every}th step, shard-local matching in between"
+            parallelism += f"; on every {args.global_every}th step, shard-local (blocked) matching in between"
         ens = make_ensemble(n_local, dim, box, 5 + rank, kind)
         s.upload(ens, None)
         s.sync()
@@ -376,6 +392,51 @@ def main():
         ms = float(t.item())
     stats = s.stats()
     value = n * args.steps / (ms * 1e-3)
+
+    # ---- walker shards: the pieces of the schedule on their own, and the NVLink denominators ----
+    extra = None
+    if world > 1 and s.mode == "walkers" and args.move == "stretch":
+        def timed(fn, k):
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(k); e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / k], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        k_x = max(8, min(args.steps, 40))
+        t_local = timed(lambda k: s.sampler.sample_pt(2.0, spec, beta, k), k_x)
+        extra = {"replicas_upper_bound": {"ms_per_step": t_local, "value": n / (t_local * 1e-3),
+                                          "note": "shard-local matching on every step: no exchange at all"}}
+        if s.p2p:
+            t_glob = timed(lambda k: s.sampler.sample_pt_peer(2.0, spec, beta, k), k_x)
+            acc = stats["accepted"] / max(1, stats["proposed"])
+            cross = (n_local / 2) * (world - 1) / world                 # owned pairs whose partner lives on a peer
+            rd, wr = cross * (dim * 8 + 8), cross * acc * (dim * 8 + 8)
+            ce, sm = s.sampler.peer_read_bandwidth((rank + 1) % world, 0, 5)
+            bw = torch.tensor([ce, sm], device="cuda", dtype=torch.float64)
+            dist.all_reduce(bw, op=dist.ReduceOp.MIN)
+            ce, sm = float(bw[0].item()), float(bw[1].item())
+            extra["exchange_every_step"] = {
+                "ms_per_step": t_glob, "value": n / (t_glob * 1e-3),
+                "nvlink_read_bytes_per_gpu_step": rd, "nvlink_write_bytes_per_gpu_step": wr,
+                "roofline": {"bound": "nvlink", "achieved": rd / (t_glob * 1e-3) / 1e9, "peak": sm, "unit": "GB/s",
+                             "frac": rd / (t_glob * 1e-3) / 1e9 / sm,
+                             "peak_source": "scorus_peer_read_bandwidth: all ranks reading the next rank's ensemble at once, "
+                                            "SM 16-byte loads (min over ranks), measured in this run"},
+                "note": "the reference's whole-ensemble matching on every step (k = 1)"}
+            # NCCL's all-gather of the ensemble (what BASELINE.json's wording would do every step), for the record
+            buf = torch.empty((n, s.pitch), dtype=torch.float64, device="cuda")
+            def ag(k):
+                for _ in range(k):
+                    dist.all_gather_into_tensor(buf, s.ens)
+            ag(1)
+            t_ag = timed(ag, 3)
+            extra["nvlink"] = {"peer_read_copy_engine_gbps": ce, "peer_read_sm_loads_gbps": sm,
+                               "nccl_allgather_ms": t_ag,
+                               "nccl_allgather_busbw_gbps": n_local * s.pitch * 8 * (world - 1) / (t_ag * 1e-3) / 1e9}
+            del buf
+        stats = s.stats()
 
     # ---- the ladder swap on its own (reported separately; amortised into `value` above) ----
     swap_stage = None
@@ -549,6 +610,10 @@ def main():
     }
     if swap_stage:
         line["swap_stage"] = swap_stage
+    if extra:
+        line["extra"] = extra
+    if parity_check:
+        line["parity_check"] = parity_check
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

@@ -43,7 +43,9 @@ enum {
     SCORUS_ERR_NPHI_ZERO = 7,                 /* `nphi - 1` on usize, ensemble_sample.rs:184 */
     SCORUS_ERR_NO_LOGPROB = 8,                /* no log-density plugin registered */
     SCORUS_ERR_NOT_UPLOADED = 9,
-    SCORUS_ERR_DIM_TOO_LARGE = 10,            /* one 32-walker tile must fit in shared memory */
+    SCORUS_ERR_DIM_TOO_LARGE = 10,            /* the reference is dimension-generic; here the stretch move needs two 32-row
+                                               * tiles in 227 KB of shared memory above dim 256 (dim <= ~440), the
+                                               * t-walk and HMC keep a row in registers (dim <= 256) */
     SCORUS_ERR_CUDA = 100,                    /* see scorus_last_error */
     SCORUS_ERR_NO_DEVICE = 101
 };
@@ -117,6 +119,9 @@ int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *params, size_t n
 
 /* host <-> device: the caller's `&mut [V]` / `&mut [T]` slices (src/mcmc/ensemble_sample.rs:109-110) as flat
  * walker-major arrays.  logprob == NULL on upload runs init_logprob (:77-85) on the device. */
+/* scorus_upload is asynchronous on the context's stream when the source is page-locked (scorus_host_alloc): the
+ * caller must not reuse or free the buffers before scorus_sync (or any call that returns host data).  Pageable
+ * sources are staged by the driver and may be reused on return. */
 int scorus_upload(scorus_ctx *ctx, const double *ensemble, const double *logprob);
 int scorus_download(scorus_ctx *ctx, double *ensemble, double *logprob);
 
@@ -296,13 +301,34 @@ int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta_list, size_t nbe
 int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens_64b, void *handle_lp_64b);
 int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_ens, const void *handles_lp);
 
-/* sample_pt of a walker shard with the reference's whole-ensemble matching (src/mcmc/ensemble_sample.rs:135-148), WITHOUT an all-gather:
- * _begin builds the local pair list and pulls only the remote partners' rows over NVLink (one-sided
- * reads of the peers mapped by scorus_ipc_attach); _end runs the fused step.  The caller inserts a
- * stream-ordered barrier across ranks before _begin and between _begin and _end (peers must not
- * overwrite rows that are still being read).  Identical to the single-GPU step. */
-int scorus_sample_pt_p2p_begin(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
-int scorus_sample_pt_p2p_end(scorus_ctx *ctx);
+/* sample_pt of a walker shard with the reference's whole-ensemble matching (src/mcmc/ensemble_sample.rs:135-148), WITHOUT an
+ * all-gather and without staging copies: every pair of the matching is owned by the rank holding its even-position
+ * member; the owner reads the partner's row where it lives (one-sided loads over NVLink from the peers mapped by
+ * scorus_ipc_attach), runs the fused step for BOTH walkers and writes accepted rows / log-probs back to their home
+ * ranks.  Each row crosses NVLink at most once per direction per step and nothing is computed twice.  Synchronisation:
+ * one flag barrier in peer memory before each step (inside the pair-list kernel) and one after the last step -- no
+ * NCCL call, no host synchronisation.  Every rank calls it with the same arguments.  nsteps consecutive steps;
+ * identical to the single-GPU steps (streams are keyed by global walker ids). */
+int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta,
+                          uint64_t nsteps);
+/* The barrier on its own (stream-ordered; every attached rank must call it the same number of times). */
+int scorus_peer_barrier(scorus_ctx *ctx);
+
+/* Measurement only (the roofline denominator of the one-sided step): read bandwidth of this GPU from rank `peer`'s
+ * mapped ensemble over NVLink, by a copy-engine memcpy and by an SM kernel of 16-byte streaming loads; GB/s.
+ * bytes == 0: the whole buffer. */
+int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t bytes, int iters, double *gbps_copy_engine,
+                               double *gbps_sm_loads);
+
+/* Blocked matchings.  The reference pairs walkers over the whole rung (src/mcmc/ensemble_sample.rs:135-148).  With
+ * nblocks > 1 a "local" step cuts every rung into nblocks contiguous blocks that pair among themselves -- what the
+ * shards of a multi-GPU run do on the steps where they exchange nothing; global_every = k >= 1 makes every step whose
+ * index is a multiple of k a whole-rung step again (0: never).  The schedule depends on the step index only, so each
+ * step's matching is independent of the state and the move stays a valid stretch move.  block_offset shifts the
+ * stream keys of the blocks (a shard that is block c of the whole ensemble passes c), so that one GPU with
+ * (nblocks = world, global_every = k) and `world` shards running scorus_sample_pt / scorus_sample_pt_peer on the same
+ * schedule produce the same chain bit for bit.  Default (1, 0, 0): the reference's matching on every step. */
+int scorus_set_matching_blocks(scorus_ctx *ctx, uint32_t nblocks, uint32_t block_offset, uint64_t global_every);
 
 /* Applies a swap plan (the row and log-prob exchanges of src/mcmc/utils.rs:106-107) to this rank's slots with one-sided
  * reads of the peers (scorus_ipc_attach):

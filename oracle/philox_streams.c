@@ -29,6 +29,8 @@ enum {
 };
 
 #define EXACT_SHUFFLE_MAX 1024u
+/* Prob(p) flags: after this many all-false draws one coordinate is set, uniformly placed (tile_common.cuh) */
+#define MAX_FLAG_ATTEMPTS 64u
 
 static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
@@ -98,33 +100,78 @@ static int cmp_keyed(const void *a, const void *b)
     return x->id < y->id ? -1 : (x->id > y->id);
 }
 
-/* order[j] = walker at matching position j; positions 2k and 2k+1 are partners */
-static void pairing_order(uint64_t seed, uint64_t step, size_t n, size_t nbeta, uint32_t *order)
+/* order[j] = walker at matching position j; positions 2k and 2k+1 are partners.  Every rung is cut into
+ * `nblocks` contiguous blocks that are matched separately (nblocks = 1: the reference's whole-rung matching,
+ * ensemble_sample.rs:135-148; nblocks > 1: the shard-local steps of the k-schedule).
+ * Block c of rung r draws its bijection keys at (idx = r, sub = 2c, 2c + 1); blocks of up to 1024 walkers are
+ * shuffled exactly by ranking their walkers' 64-bit keys. */
+static void pairing_order_blocked(uint64_t seed, uint64_t step, size_t n, size_t nbeta, size_t nblocks, uint32_t *order)
 {
-    size_t npb = n / nbeta;
-    if (npb <= EXACT_SHUFFLE_MAX) {
-        keyed *kv = (keyed *)malloc(npb * sizeof(keyed));
-        for (size_t r = 0; r < nbeta; ++r) {
-            for (size_t k = 0; k < npb; ++k) {
+    size_t npb = n / nbeta, bs = npb / nblocks;
+    if (bs <= EXACT_SHUFFLE_MAX) {
+        keyed *kv = (keyed *)malloc(bs * sizeof(keyed));
+        for (size_t blk = 0; blk < nbeta * nblocks; ++blk) {
+            for (size_t k = 0; k < bs; ++k) {
                 uint32_t o[4];
-                uint32_t w = (uint32_t)(r * npb + k);
+                uint32_t w = (uint32_t)(blk * bs + k);
                 draw(seed, step, ST_PERM_KEY, w, 0, o);
                 kv[k].key = ((uint64_t)o[1] << 32) | o[0];
                 kv[k].id = w;
             }
-            qsort(kv, npb, sizeof(keyed), cmp_keyed);
-            for (size_t k = 0; k < npb; ++k) order[r * npb + k] = kv[k].id;
+            qsort(kv, bs, sizeof(keyed), cmp_keyed);
+            for (size_t k = 0; k < bs; ++k) order[blk * bs + k] = kv[k].id;
         }
         free(kv);
     } else {
-        for (size_t r = 0; r < nbeta; ++r) {
-            uint32_t k[8];
-            draw(seed, step, ST_PERM, (uint32_t)r, 0, k);
-            draw(seed, step, ST_PERM, (uint32_t)r, 1, k + 4);
-            for (size_t j = 0; j < npb; ++j)
-                order[r * npb + j] = (uint32_t)(r * npb) + bij((uint32_t)j, (uint32_t)npb, k);
-        }
+        for (size_t r = 0; r < nbeta; ++r)
+            for (size_t c = 0; c < nblocks; ++c) {
+                uint32_t k[8];
+                draw(seed, step, ST_PERM, (uint32_t)r, (uint32_t)(2 * c), k);
+                draw(seed, step, ST_PERM, (uint32_t)r, (uint32_t)(2 * c + 1), k + 4);
+                const size_t base = r * npb + c * bs;
+                for (size_t j = 0; j < bs; ++j) order[base + j] = (uint32_t)base + bij((uint32_t)j, (uint32_t)bs, k);
+            }
     }
+}
+
+static void pairing_order(uint64_t seed, uint64_t step, size_t n, size_t nbeta, uint32_t *order)
+{
+    pairing_order_blocked(seed, step, n, nbeta, 1, order);
+}
+
+/* Prob(p) flags of walker w at `step` into f[dim] (the device's gen_flags_prob, tile_common.cuh): bpf bits per
+ * coordinate, flag = value < thr, redrawn until one is set; bounded by MAX_FLAG_ATTEMPTS */
+static void prob_flags(uint64_t seed, uint64_t step, uint32_t w, size_t dim, uint32_t bpf, uint64_t thr, uint8_t *f)
+{
+    const uint32_t fpc = 128 / bpf;
+    const uint32_t nblk = (uint32_t)((dim + fpc - 1) / fpc);
+    const uint64_t vmask = bpf == 32 ? 0xFFFFFFFFull : ((1ull << bpf) - 1);
+    uint32_t o[4];
+    for (uint32_t attempt = 0; attempt < MAX_FLAG_ATTEMPTS; ++attempt) {
+        int any = 0;
+        for (uint32_t blk = 0; blk < nblk; ++blk) {
+            draw(seed, step, ST_FLAGS, w, attempt * nblk + blk, o);
+            for (uint32_t q = 0; q < fpc; ++q) {
+                const size_t d = (size_t)blk * fpc + q;
+                if (d >= dim) break;
+                const uint32_t bit = q * bpf;
+                const uint64_t v = (o[bit / 32] >> (bit % 32)) & vmask;
+                f[d] = v < thr;
+                any |= f[d];
+            }
+        }
+        if (any) return;
+    }
+    draw(seed, step, ST_FLAGS, w, MAX_FLAG_ATTEMPTS * nblk, o);
+    f[(size_t)(((uint64_t)o[0] * (uint64_t)dim) >> 32)] = 1;
+}
+
+/* threshold on bpf random bits: prob * 2^bpf (rounded to nearest for 32 bits), at least 1 */
+static uint64_t flag_threshold(double prob, uint32_t bpf)
+{
+    const double q = fmin(prob, 1.0);
+    uint64_t thr = bpf == 32 ? (uint64_t)llrint(q * 4294967296.0) : (uint64_t)(q * (double)(1u << bpf));
+    return thr ? thr : 1;
 }
 
 /* bits per Bernoulli flag: the smallest of 1,2,4,8,16 for which prob*2^bits is an integer, else 32 */
@@ -138,25 +185,46 @@ static uint32_t flag_bits(double prob)
     return 32;
 }
 
-int orc_philox_sample_streams(uint64_t seed, uint64_t step, size_t n, size_t dim, size_t nbeta,
-                              double a, int ufs_kind, double prob, uint64_t onehot_counter,
-                              uint32_t *partner, double *z, uint8_t *flags, double *u)
+/* The device streams of one sample_pt step.  walkers == NULL: all n walkers (m ignored), outputs indexed by walker.
+ * walkers != NULL: only the m listed walkers (outputs indexed 0..m-1; partner[] still holds global ids) -- streams
+ * are keyed by walker, so a sample of a 2^22-walker step is replayed at the cost of the sample (plus one pass
+ * over the pairing bijection). */
+int orc_philox_sample_streams_ex(uint64_t seed, uint64_t step, size_t n, size_t dim, size_t nbeta, double a,
+                                 int ufs_kind, double prob, uint64_t onehot_counter, size_t nblocks,
+                                 const uint32_t *walkers, size_t m, uint32_t *partner, double *z, uint8_t *flags,
+                                 double *u)
 {
-    if (nbeta == 0 || n == 0 || n % nbeta || (n / nbeta) % 2) return ORC_ERR_INVALID_ARG;
+    if (nbeta == 0 || n == 0 || n % nbeta || nblocks == 0) return ORC_ERR_INVALID_ARG;
+    const size_t npb = n / nbeta;
+    if (npb % nblocks || (npb / nblocks) % 2) return ORC_ERR_INVALID_ARG;
+    if (!walkers) m = n;
     uint32_t *order = (uint32_t *)malloc(n * sizeof(uint32_t));
-    pairing_order(seed, step, n, nbeta, order);
-    for (size_t j = 0; j < n; j += 2) {
-        partner[order[j]] = order[j + 1];
-        partner[order[j + 1]] = order[j];
+    pairing_order_blocked(seed, step, n, nbeta, nblocks, order);
+    if (!walkers) {
+        for (size_t j = 0; j < n; j += 2) {
+            partner[order[j]] = order[j + 1];
+            partner[order[j + 1]] = order[j];
+        }
+    } else {
+        uint32_t *mate = (uint32_t *)malloc(n * sizeof(uint32_t));
+        for (size_t j = 0; j < n; j += 2) {
+            mate[order[j]] = order[j + 1];
+            mate[order[j + 1]] = order[j];
+        }
+        for (size_t i = 0; i < m; ++i) {
+            if (walkers[i] >= n) { free(mate); free(order); return ORC_ERR_INVALID_ARG; }
+            partner[i] = mate[walkers[i]];
+        }
+        free(mate);
     }
     free(order);
 
     double sqrt_a = sqrt(a);
     double inv_sqrt_a = 1.0 / sqrt_a;
     double range = 2.0 * (sqrt_a - inv_sqrt_a);
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < m; ++i) {
         uint32_t o[4];
-        draw(seed, step, ST_ZU, (uint32_t)i, 0, o);
+        draw(seed, step, ST_ZU, walkers ? walkers[i] : (uint32_t)i, 0, o);
         double p = u53(o[0], o[1]) * range;
         double y = inv_sqrt_a + p / 2.0;
         z[i] = y * y;
@@ -164,44 +232,31 @@ int orc_philox_sample_streams(uint64_t seed, uint64_t step, size_t n, size_t dim
     }
 
     if (ufs_kind == ORC_UFS_ALL) {
-        memset(flags, 1, n * dim);
+        memset(flags, 1, m * dim);
     } else if (ufs_kind == ORC_UFS_ONE_HOT_CYCLE) {
-        for (size_t i = 0; i < n; ++i) {
-            size_t hot = (size_t)((onehot_counter + 1 + i) % dim);
+        for (size_t i = 0; i < m; ++i) {
+            size_t hot = (size_t)((onehot_counter + 1 + (walkers ? walkers[i] : i)) % dim);
             for (size_t k = 0; k < dim; ++k) flags[i * dim + k] = (k == hot);
         }
     } else if (ufs_kind == ORC_UFS_PROB) {
         if (!(prob > 0.0)) return ORC_ERR_INVALID_ARG;
-        uint32_t bpf = flag_bits(prob);
-        uint32_t fpc = 128 / bpf;
-        uint32_t nblk = (uint32_t)((dim + fpc - 1) / fpc);
-        /* threshold: flag = value < thr; thr = prob * 2^bpf (rounded to nearest for 32 bits) */
-        uint64_t thr = bpf == 32 ? (uint64_t)llrint(fmin(prob, 1.0) * 4294967296.0)
-                                 : (uint64_t)(fmin(prob, 1.0) * (double)(1u << bpf));
-        uint64_t vmask = bpf == 32 ? 0xFFFFFFFFull : ((1ull << bpf) - 1);
-        for (size_t i = 0; i < n; ++i) {
-            for (uint32_t attempt = 0;; ++attempt) {
-                int any = 0;
-                for (uint32_t blk = 0; blk < nblk; ++blk) {
-                    uint32_t o[4];
-                    draw(seed, step, ST_FLAGS, (uint32_t)i, attempt * nblk + blk, o);
-                    for (uint32_t w = 0; w < fpc; ++w) {
-                        size_t d = (size_t)blk * fpc + w;
-                        if (d >= dim) break;
-                        uint32_t bit = w * bpf;
-                        uint64_t v = (o[bit / 32] >> (bit % 32)) & vmask;
-                        uint8_t f = v < thr;
-                        flags[i * dim + d] = f;
-                        any |= f;
-                    }
-                }
-                if (any) break;
-            }
-        }
+        const uint32_t bpf = flag_bits(fmin(prob, 1.0));
+        const uint64_t thr = flag_threshold(prob, bpf);
+        for (size_t i = 0; i < m; ++i)
+            prob_flags(seed, step, walkers ? walkers[i] : (uint32_t)i, dim, bpf, thr, flags + i * dim);
     } else {
         return ORC_ERR_INVALID_ARG;
     }
     return ORC_OK;
+}
+
+int orc_philox_sample_streams(uint64_t seed, uint64_t step, size_t n, size_t dim, size_t nbeta,
+                              double a, int ufs_kind, double prob, uint64_t onehot_counter,
+                              uint32_t *partner, double *z, uint8_t *flags, double *u)
+{
+    if (nbeta == 0 || n == 0 || n % nbeta || (n / nbeta) % 2) return ORC_ERR_INVALID_ARG;
+    return orc_philox_sample_streams_ex(seed, step, n, dim, nbeta, a, ufs_kind, prob, onehot_counter, 1, NULL, 0,
+                                        partner, z, flags, u);
 }
 
 int orc_philox_swap_streams(uint64_t seed, uint64_t swap_call, size_t n, size_t nbeta,
@@ -268,12 +323,8 @@ int orc_philox_twalk_streams(uint64_t seed, uint64_t step, uint64_t order_step, 
     if (nbeta == 0 || n == 0 || n % nbeta || (n / nbeta) % 2) return ORC_ERR_INVALID_ARG;
     if (!(tw->pphi > 0.0)) return ORC_ERR_INVALID_ARG;
     pairing_order(seed, order_step, n, nbeta, order);
-    const uint32_t bpf = flag_bits(tw->pphi);
-    const uint32_t fpc = 128 / bpf;
-    const uint32_t nblk = (uint32_t)((dim + fpc - 1) / fpc);
-    const uint64_t thr = bpf == 32 ? (uint64_t)llrint(fmin(tw->pphi, 1.0) * 4294967296.0)
-                                   : (uint64_t)(fmin(tw->pphi, 1.0) * (double)(1u << bpf));
-    const uint64_t vmask = bpf == 32 ? 0xFFFFFFFFull : ((1ull << bpf) - 1);
+    const uint32_t bpf = flag_bits(fmin(tw->pphi, 1.0));
+    const uint64_t thr = flag_threshold(tw->pphi, bpf);
     for (size_t k = 0; k < n / 2; ++k) {
         const uint32_t w = order[2 * k + half];
         uint32_t o[4];
@@ -285,22 +336,7 @@ int orc_philox_twalk_streams(uint64_t seed, uint64_t step, uint64_t order_step, 
             draw(seed, step, ST_TW_B, w, 0, o);
             b[k] = orc_twalk_b_from_uniforms(u53(o[0], o[1]), u53(o[2], o[3]), tw->at);
         }
-        uint8_t *f = flags + k * dim;
-        for (uint32_t attempt = 0;; ++attempt) {
-            int any = 0;
-            for (uint32_t blk = 0; blk < nblk; ++blk) {
-                draw(seed, step, ST_FLAGS, w, attempt * nblk + blk, o);
-                for (uint32_t q = 0; q < fpc; ++q) {
-                    const size_t d = (size_t)blk * fpc + q;
-                    if (d >= dim) break;
-                    const uint32_t bit = q * bpf;
-                    const uint64_t v = (o[bit / 32] >> (bit % 32)) & vmask;
-                    f[d] = v < thr;
-                    any |= f[d];
-                }
-            }
-            if (any) break;
-        }
+        prob_flags(seed, step, w, dim, bpf, thr, flags + k * dim);
         for (size_t d = 0; d < dim; d += 2) {
             draw(seed, step, ST_TW_WALK, w, (uint32_t)(d / 2), o);
             walk_u[k * dim + d] = u53(o[0], o[1]);

@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
         L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
         L.orc_philox_sample_streams.restype = ci
         L.orc_philox_sample_streams.argtypes = [u64, u64, sz, sz, sz, dbl, ci, dbl, u64, u32p, dp, u8p, dp]
+        L.orc_philox_sample_streams_ex.restype = ci
+        L.orc_philox_sample_streams_ex.argtypes = [u64, u64, sz, sz, sz, dbl, ci, dbl, u64, sz, u32p, sz, u32p, dp, u8p, dp]
         L.orc_philox_swap_streams.restype = ci
         L.orc_philox_swap_streams.argtypes = [u64, u64, sz, sz, u32p, dp]
         L.orc_philox_init_ensemble.restype = None
@@ -113,6 +115,7 @@ def lib() -> C.CDLL:
         L.orc_twalk_b_from_uniforms.argtypes = [dbl, dbl, dbl]
         L.orc_twalk_half_fixed.argtypes = [ci, dp, sz, dp, dp, sz, sz, dp, sz, C.POINTER(TwalkParams), u32p, ci, u8p, dp,
                                            u8p, dp, dp, u8p, dp, dp]
+        L.orc_twalk_half_fixed_literal.argtypes = L.orc_twalk_half_fixed.argtypes
         L.orc_twalk_draw_streams.argtypes = [C.c_void_p, sz, sz, sz, C.POINTER(TwalkParams), u32p, u8p, dp, u8p, dp, dp]
         L.orc_twalk_sample.argtypes = [ci, dp, sz, dp, dp, sz, sz, C.c_void_p, C.POINTER(TwalkParams), dp, sz]
         L.orc_philox_twalk_streams.argtypes = [u64, u64, u64, sz, sz, sz, C.POINTER(TwalkParams), ci, u32p, u8p, dp,
@@ -296,8 +299,10 @@ def twalk_params(dim, pphi=None, fw=None, aw=None, at=None) -> TwalkParams:
     return t
 
 
-def twalk_half_fixed(kind, params, ens, lp, beta, tw, order, half, kernel, b, flags, walk_u, u, want_proposals=False):
-    """One half-pass of twalk::sample1 with supplied draws, in place; returns accepted[n/2] (+ proposals, new_lp)."""
+def twalk_half_fixed(kind, params, ens, lp, beta, tw, order, half, kernel, b, flags, walk_u, u, want_proposals=False,
+                     literal_index=False):
+    """One half-pass of twalk::sample1 with supplied draws, in place; returns accepted[n/2] (+ proposals, new_lp).
+    literal_index: the reference's index arithmetic as written (reads rung 0's walkers for every rung)."""
     n, dim = ens.shape
     beta = np.ascontiguousarray(beta, dtype=np.float64)
     p, pp, npar = _params(params)
@@ -310,7 +315,8 @@ def twalk_half_fixed(kind, params, ens, lp, beta, tw, order, half, kernel, b, fl
     acc = np.zeros(n // 2, dtype=np.uint8)
     prop = np.zeros((n // 2, dim)) if want_proposals else None
     nlp = np.zeros(n // 2) if want_proposals else None
-    rc = lib().orc_twalk_half_fixed(kind, pp, npar, _dp(ens), _dp(lp), n, dim, _dp(beta), beta.shape[0], C.byref(tw),
+    fn = lib().orc_twalk_half_fixed_literal if literal_index else lib().orc_twalk_half_fixed
+    rc = fn(kind, pp, npar, _dp(ens), _dp(lp), n, dim, _dp(beta), beta.shape[0], C.byref(tw),
                                     _u32p(order), half, _u8p(kernel), _dp(b), _u8p(flags), _dp(walk_u), _dp(u),
                                     _u8p(acc), _dp(prop), _dp(nlp))
     if rc:
@@ -440,6 +446,22 @@ def philox_sample_streams(seed, step, n, dim, nbeta, a, ufs_kind, prob=0.5, oneh
                                          _u32p(partner), _dp(z), _u8p(flags), _dp(u))
     if rc:
         raise ValueError(f"orc_philox_sample_streams rc={rc}")
+    return partner, z, flags, u
+
+
+def philox_sample_streams_ex(seed, step, n, dim, nbeta, a, ufs_kind, prob=0.5, onehot_counter=0, nblocks=1, walkers=None):
+    """philox_sample_streams with `nblocks` separately matched blocks per rung and, if `walkers` is given, for that
+    sample of walkers only (outputs in the order of `walkers`; partner holds global ids)."""
+    w = None if walkers is None else np.ascontiguousarray(walkers, dtype=np.uint32)
+    m = n if w is None else w.size
+    partner = np.zeros(m, dtype=np.uint32)
+    z = np.zeros(m)
+    u = np.zeros(m)
+    flags = np.zeros((m, dim), dtype=np.uint8)
+    rc = lib().orc_philox_sample_streams_ex(seed, step, n, dim, nbeta, a, ufs_kind, prob, onehot_counter, nblocks,
+                                            _u32p(w), m, _u32p(partner), _dp(z), _u8p(flags), _dp(u))
+    if rc:
+        raise ValueError(f"orc_philox_sample_streams_ex rc={rc}")
     return partner, z, flags, u
 
 

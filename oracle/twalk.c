@@ -9,7 +9,9 @@
  * ibeta * nwalkers_per_beta when it WRITES (:757-758): with B > 1 every rung would propose from rung 0's
  * walkers.  With B = 1 there is no shift and nothing to decide.  This restatement (and the device path)
  * applies the shift on both sides -- the pairs of rung r are walkers of rung r -- which is the only reading
- * under which rung r samples its own tempered density.  DESIGN.md section 4.7 records it. */
+ * under which rung r samples its own tempered density.  DESIGN.md section 4.7 records it.  The literal reading
+ * is kept beside it (orc_twalk_half_fixed_literal) so that the difference is pinned by a test, not by prose:
+ * parity with the reference AS WRITTEN holds for B = 1 only. */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -40,12 +42,13 @@ double orc_twalk_b_from_uniforms(double x, double v, double at)
  *   kernel[k] 0 = Walk, 1 = Traverse;  b[k] (Traverse);  flags[k][dim];  walk_u[k][dim] (Walk, flagged
  *   coordinates only);  u[k] accept uniform.  accepted[k] (out, may be NULL), proposed [k][dim] / new_lp[k]
  *   (out, may be NULL). */
-int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n,
-                         size_t dim, const double *beta, size_t nbeta, const orc_twalk_params *tw,
-                         const uint32_t *order, int half, const uint8_t *kernel, const double *b,
-                         const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted,
-                         double *proposed, double *new_lp)
+static int twalk_half_impl(int literal_index, int kind, const double *params, size_t nparams, double *ens, double *lp,
+                           size_t n, size_t dim, const double *beta, size_t nbeta, const orc_twalk_params *tw,
+                           const uint32_t *order, int half, const uint8_t *kernel, const double *b,
+                           const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted,
+                           double *proposed, double *new_lp)
 {
+    (void)tw;
     if (nbeta == 0 || n == 0) return ORC_ERR_INVALID_ARG;
     const size_t npb = n / nbeta;
     if (npb * nbeta != n) return ORC_ERR_NWALKERS_MISMATCHES_NBETA; /* assert :675 */
@@ -54,9 +57,11 @@ int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double 
     double *y = (double *)malloc(npair * dim * sizeof(double));
     double *ylp = (double *)malloc(npair * sizeof(double));
     /* proposals of every pair from the ensemble as it stands (:676-688), then their log-densities (:693-732) */
+    /* literal_index: the indices sample1 READS with are the rung-local ones of :605-612, i.e. walkers of rung 0 */
+#define RD(idx) (literal_index ? (size_t)(idx) % npb : (size_t)(idx))
     for (size_t k = 0; k < npair; ++k) {
-        const double *x = ens + (size_t)order[2 * k + half] * dim;        /* the walker that moves */
-        const double *xp = ens + (size_t)order[2 * k + 1 - half] * dim;   /* its partner */
+        const double *x = ens + RD(order[2 * k + half]) * dim;        /* the walker that moves */
+        const double *xp = ens + RD(order[2 * k + 1 - half]) * dim;   /* its partner */
         const uint8_t *f = flags + k * dim;
         double *yk = y + k * dim;
         if (kernel[k] == 0) {
@@ -77,7 +82,8 @@ int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double 
     }
     /* accept loop :736-760, pairs in order */
     for (size_t k = 0; k < npair; ++k) {
-        const size_t i1 = order[2 * k + half], i2 = order[2 * k + 1 - half];
+        const size_t i1 = order[2 * k + half];                 /* where the move is WRITTEN (:757-758: shifted) */
+        const size_t r1 = RD(i1), i2 = RD(order[2 * k + 1 - half]); /* what calc_a READS (:741-749) */
         const double *yk = y + k * dim, *xpart = ens + i2 * dim;
         const uint8_t *f = flags + k * dim;
         size_t nphi = 0;
@@ -90,9 +96,9 @@ int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double 
         if (nphi == 0 || !all_diff) {
             a = 0.0; /* :482-483 */
         } else if (kernel[k] == 0) {
-            a = exp((ylp[k] - lp[i1]) * bt); /* :486 */
+            a = exp((ylp[k] - lp[r1]) * bt); /* :486 */
         } else {
-            a = exp((ylp[k] - lp[i1]) * bt + (double)((long)nphi - 2) * log(b[k])); /* :487-489 */
+            a = exp((ylp[k] - lp[r1]) * bt + (double)((long)nphi - 2) * log(b[k])); /* :487-489 */
         }
         const int acc = u[k] < a; /* :756 */
         if (acc) {
@@ -106,6 +112,33 @@ int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double 
     free(y);
     free(ylp);
     return ORC_OK;
+#undef RD
+}
+
+int orc_twalk_half_fixed(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n,
+                         size_t dim, const double *beta, size_t nbeta, const orc_twalk_params *tw,
+                         const uint32_t *order, int half, const uint8_t *kernel, const double *b,
+                         const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted,
+                         double *proposed, double *new_lp)
+{
+    return twalk_half_impl(0, kind, params, nparams, ens, lp, n, dim, beta, nbeta, tw, order, half, kernel, b, flags,
+                           walk_u, u, accepted, proposed, new_lp);
+}
+
+/* The same half-pass following the reference's index arithmetic LITERALLY: pairs are rung-local indices
+ * (twalk.rs:605-612), sample1 reads walkers and log-probs with them unshifted (:686-690 propose_move,
+ * :741-749 calc_a) -- rung 0's walkers, whatever the rung -- and writes shifted by ibeta * nwalkers_per_beta
+ * (:757-758).  Identical to orc_twalk_half_fixed for one rung; for B > 1 every rung proposes from, and is
+ * accepted against, rung 0 (tests/test_twalk_cpu.py pins where the two readings part).  `order` holds global
+ * ids as above; the rung-local index is id % (n / nbeta). */
+int orc_twalk_half_fixed_literal(int kind, const double *params, size_t nparams, double *ens, double *lp, size_t n,
+                                 size_t dim, const double *beta, size_t nbeta, const orc_twalk_params *tw,
+                                 const uint32_t *order, int half, const uint8_t *kernel, const double *b,
+                                 const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted,
+                                 double *proposed, double *new_lp)
+{
+    return twalk_half_impl(1, kind, params, nparams, ens, lp, n, dim, beta, nbeta, tw, order, half, kernel, b, flags,
+                           walk_u, u, accepted, proposed, new_lp);
 }
 
 /* the draws of propose_move (:519-531) for one pair, in the reference's consumption order */

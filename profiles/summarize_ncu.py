@@ -6,8 +6,8 @@ under profiles/.  Usage, from the repo root (needs `ncu` on PATH, no GPU):
   python profiles/summarize_ncu.py list  gpurun_out/launches_r1_c5.csv c5 "<command line profiled>"
   python profiles/summarize_ncu.py full  gpurun_out/prof_twalk_c5b.ncu-rep c5 "<command>" twalk   (other kernels: a tag)
 
-`full` writes profiles/r1_<wl>_step_reg_ncu_summary.txt and profiles/traffic_<wl>.json (the DRAM bytes
-bench.py reports as roofline.traffic); `list` writes profiles/r1_<wl>_launch_list_summary.csv (per-kernel
+`full` writes profiles/<round>_<wl>_step_reg_ncu_summary.txt and profiles/traffic_<wl>.json (the DRAM bytes
+bench.py reports as roofline.traffic); `list` writes profiles/<round>_<wl>_launch_list_summary.csv (per-kernel
 launch counts, mean time and SHARE of the step; per-launch times under ncu are cold-cache and serialised).
 """
 import collections
@@ -18,6 +18,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROUND = os.environ.get("ROUND", "r2")  # prefix of the files written (profiles are named per round)
 ALG_BYTES = {"c1": 48 * 16, "c2": 1616 * 65536, "c3": 528 * (1 << 20), "c4": 176 * (1 << 20), "c5": 1040 * (1 << 22)}
 KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__block_size",
@@ -37,7 +38,7 @@ def to_bytes(unit, value):
 def full(rep, wl, cmd, tag="step_reg"):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + int(os.environ.get("NCU_ROW", "0"))]
     m = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
     lines = [f"{k:75s} {m[k][1]} {m[k][0]}" for k in KEYS if k in m]
     lines += [f"{h:75s} {m[h][1]}" for h in hdr
@@ -49,14 +50,16 @@ def full(rep, wl, cmd, tag="step_reg"):
         isrc, iex = h2.index("Source"), h2.index("Instructions Executed")
         mix = collections.Counter()
         for r in data:
+            if len(r) <= max(isrc, iex) or not r[isrc].split():
+                continue
             t = r[isrc].split()
             mix[(t[1] if t[0].startswith("@") else t[0]).split(".")[0]] += int(r[iex])
         tot = sum(mix.values())
         lines.append("")
         lines.append(f"SASS: {len(data)} instructions; executed warp-instructions {tot}; top opcodes (share):")
         lines.append("  " + ", ".join(f"{op} {c / tot:.3f}" for op, c in mix.most_common(14)))
-    out = os.path.join(ROOT, "profiles", f"r1_{wl}_{tag}_ncu_summary.txt")
-    open(out, "w").write(f"{cmd}\n(B200, round 1, one launch = one step; times under ncu are not bench values)\n\n"
+    out = os.path.join(ROOT, "profiles", f"{ROUND}_{wl}_{tag}_ncu_summary.txt")
+    open(out, "w").write(f"{cmd}\n(B200, {ROUND}, one launch = one step; times under ncu are not bench values)\n\n"
                          + "\n".join(lines) + "\n")
     rd, wr = to_bytes(*m["dram__bytes_read.sum"]), to_bytes(*m["dram__bytes_write.sum"])
     json.dump({"kernel": m["Kernel Name"][1], "workload": wl, "source": os.path.relpath(out, ROOT),
@@ -80,7 +83,7 @@ def launch_list(path, wl, cmd):
     out = ["kernel,launches,total_us,mean_us,share"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"{k},{len(v)},{sum(v):.1f},{sum(v) / len(v):.1f},{sum(v) / tot:.4f}")
-    dst = os.path.join(ROOT, "profiles", f"r1_{wl}_launch_list_summary.csv")
+    dst = os.path.join(ROOT, "profiles", f"{ROUND}_{wl}_launch_list_summary.csv")
     open(dst, "w").write(f"# {cmd}\n# per-launch times are cold-cache and serialised under ncu: read SHARES\n" + "\n".join(out) + "\n")
     print("\n".join(out))
 

@@ -110,7 +110,10 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     ctx->stream = ctx->own_stream;
     size_t ens_bytes = (size_t)ctx->n * ctx->pitch * sizeof(double);
     if ((e = cudaMalloc(&ctx->d_ens, ens_bytes)) != cudaSuccess) return bail(e, "cudaMalloc ensemble");
-    if ((e = cudaMalloc(&ctx->d_lp, ctx->n * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logprob");
+    // 32 extra slots behind the log-probs: the flag row of the inter-rank barrier (api_shard.cu), reachable by the peers
+    // through the same IPC mapping as the log-probs
+    if ((e = cudaMalloc(&ctx->d_lp, (ctx->n + 32) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logprob");
+    cudaMemsetAsync(ctx->d_lp + ctx->n, 0, 32 * sizeof(double), ctx->stream);
     if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc stats");
     if ((e = cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tile counter");
     cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned long long), ctx->stream);
@@ -137,7 +140,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
             if (ctx->peer_ens[q]) cudaIpcCloseMemHandle(ctx->peer_ens[q]);
             if (ctx->peer_lp[q]) cudaIpcCloseMemHandle(ctx->peer_lp[q]);
         }
-    void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_stage, ctx->d_stage_lp, ctx->d_part, ctx->d_stat,
+    void *p2p[] = {ctx->d_peer_ens, ctx->d_peer_lp, ctx->d_part, ctx->d_stat,
                    ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace, ctx->d_rung_stats, ctx->d_mom, ctx->d_iat, ctx->d_tw_kernel, ctx->d_tw_walk,
                    ctx->d_hmc_adapt, ctx->d_hmc_eps, ctx->d_hmc_p};
     for (void *b : p2p)
@@ -449,8 +452,36 @@ void scorus::host::stamp_tiles(scorus_ctx *ctx, StepParams *p, const Geometry &g
     if (g.kernel == KERNEL_REG && !p->n_dev && env_int("SCORUS_DYNAMIC_TILES", 1)) {
         p->tile_counter = ctx->d_tile_counter;
         p->tile_base = ctx->tile_ticket;
-        ctx->tile_ticket += p->ntiles;
     }
+}
+
+// the device counter moves by ntiles per launch that RAN: advance the host's copy only after a successful launch
+void scorus::host::commit_tiles(scorus_ctx *ctx, const StepParams &p)
+{
+    if (p.tile_counter == ctx->d_tile_counter) ctx->tile_ticket += p.ntiles;
+}
+
+void scorus::host::set_matching(const scorus_ctx *ctx, StepParams *p, uint64_t step)
+{
+    const bool whole = ctx->mblocks <= 1 || (ctx->global_every && step % ctx->global_every == 0);
+    p->mblk = whole ? p->npb : p->npb / ctx->mblocks;
+    p->mblk_bits = bij_bits(p->mblk);
+    p->mblk_off = ctx->mblk_off;
+}
+
+// Blocked matchings: on "local" steps every rung is cut into `nblocks` contiguous blocks that pair among themselves;
+// with global_every = k >= 1 the steps whose index is a multiple of k use the reference's whole-rung matching
+// (ensemble_sample.rs:135-148).  The schedule depends on the step index only, so every step's matching is independent
+// of the state: each step is a valid stretch move.  This is what a sharded run does when it exchanges partners only
+// every k-th step, stated for one GPU so that the two can be compared bit for bit.
+// block_offset shifts the stream keys of the blocks: a shard that IS block c of a larger ensemble passes c.
+extern "C" int scorus_set_matching_blocks(scorus_ctx *ctx, uint32_t nblocks, uint32_t block_offset, uint64_t global_every)
+{
+    if (!ctx || nblocks == 0) return SCORUS_ERR_INVALID_ARG;
+    ctx->mblocks = nblocks;
+    ctx->mblk_off = block_offset;
+    ctx->global_every = global_every;
+    return SCORUS_OK;
 }
 
 uint32_t scorus::host::flag_bits_for(double prob)
@@ -461,6 +492,20 @@ uint32_t scorus::host::flag_bits_for(double prob)
         if (t == floor(t)) return b;
     }
     return 32;
+}
+
+// Prob(p): flag d of a walker is (value < thr) on flag_bits random bits.  The threshold is clamped to >= 1 so that
+// a tiny p (below 2^-33, which would round to 0) still sets flags -- with thr == 0 no flag could ever be set and
+// the redraw loop of ensemble_sample.rs:43-50 would never end.  The device loop is bounded as well
+// (kMaxFlagAttempts, tile_common.cuh).
+int scorus::host::set_prob_flags(scorus_ctx *ctx, StepParams *p, double prob)
+{
+    if (!(prob > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "Prob(p) needs p > 0 (the reference would loop forever)");
+    const double q = fmin(prob, 1.0);
+    p->flag_bits = flag_bits_for(q);
+    p->flag_thr = p->flag_bits == 32 ? (uint64_t)llrint(q * 4294967296.0) : (uint64_t)(q * (double)(1u << p->flag_bits));
+    if (p->flag_thr == 0) p->flag_thr = 1;
+    return SCORUS_OK;
 }
 
 // chain statistics: device counters per rung (accepted moves) and per exchange stage (accepted swaps),
@@ -516,6 +561,7 @@ int scorus::host::fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_
     p->flag_words = g->flag_words;
     p->ntiles = (uint32_t)((ctx->n + 31u) / 32u);
     p->bij_bits = bij_bits(p->npb);
+    p->mblk = p->npb; p->mblk_bits = p->bij_bits; p->mblk_off = ctx->mblk_off;
     p->debug_identity = env_int("SCORUS_DEBUG_IDENTITY", 0) ? 1u : 0u;
     p->w_off = (uint32_t)ctx->w_off; p->rung_off = ctx->rung_off; p->n_global = ctx->n_global;
     p->src_ens = ctx->d_ens; p->src_lp = ctx->d_lp; p->n_dev = nullptr; p->w_lo = 0; p->w_hi = (uint32_t)ctx->n;
@@ -559,7 +605,7 @@ void launch_swap_chain(scorus_ctx *ctx, const SwapParams &sp)
 static bool small_geometry(const scorus_ctx *ctx, Geometry *g)
 {
     const char *force = getenv("SCORUS_KERNEL");
-    if (ctx->sequential || ctx->n > 1024 || !env_int("SCORUS_SMALL", 1)) return false;
+    if (ctx->sequential || ctx->n > 1024 || ctx->mblocks > 1 || !env_int("SCORUS_SMALL", 1)) return false;
     if (force && *force && strcmp(force, "small")) return false;
     const uint32_t warps = (uint32_t)((ctx->n + 31u) / 32u);
     const SmallLayout L = small_layout((uint32_t)ctx->n, ctx->pitch, g->flag_words, warps);
@@ -595,10 +641,7 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
     switch (ufs->kind) {
     case SCORUS_UFS_ALL: all_flags = true; break;
     case SCORUS_UFS_PROB:
-        if (!(ufs->prob > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "Prob(p) needs p > 0 (the reference would loop forever)");
-        p.flag_bits = flag_bits_for(ufs->prob);
-        p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(ufs->prob, 1.0) * 4294967296.0)
-                                       : (uint64_t)(fmin(ufs->prob, 1.0) * (double)(1u << p.flag_bits));
+        if ((rc = set_prob_flags(ctx, &p, ufs->prob))) return rc;
         break;
     case SCORUS_UFS_ONE_HOT_CYCLE: break;
     case SCORUS_UFS_MASK: {
@@ -641,26 +684,29 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
         return SCORUS_OK;
     }
 
-    bool exact = p.npb <= kExactShuffleMax;
+    if (ctx->mblocks > 1 && (p.npb % ctx->mblocks || (p.npb / ctx->mblocks) % 2))
+        return fail(ctx, SCORUS_ERR_NWALKERS_IS_NOT_EVEN, "a rung of %u walkers does not split into %u even matching blocks", p.npb, ctx->mblocks);
     // one-block ensembles: the register kernel shuffles the rungs itself (step_reg_kernel.cuh)
     const size_t fused_bytes = ctx->n * (sizeof(uint64_t) + sizeof(uint32_t));
-    if (exact && g.kernel == KERNEL_REG && g.grid == 1 && g.smem + fused_bytes <= (size_t)ctx->smem_optin &&
-        env_int("SCORUS_FUSED_ORDER", 1)) {
+    if (p.npb <= kExactShuffleMax && ctx->mblocks == 1 && g.kernel == KERNEL_REG && g.grid == 1 &&
+        g.smem + fused_bytes <= (size_t)ctx->smem_optin && env_int("SCORUS_FUSED_ORDER", 1)) {
         p.fused_order = 1;
         g.smem += fused_bytes;
-        exact = false;
     }
-    if (exact && !ctx->d_order) CU(cudaMalloc(&ctx->d_order, ctx->n * sizeof(uint32_t)));
     for (uint64_t s = 0; s < nsteps; ++s) {
         p.step = ctx->step;
         p.onehot = ctx->onehot;
-        if (exact) {
-            launch_exact_order(ctx, ctx->step, nbeta, p.npb, ctx->d_order, (uint32_t)ctx->w_off);
+        set_matching(ctx, &p, ctx->step);
+        p.order = nullptr;
+        if (p.mblk <= kExactShuffleMax && !p.fused_order) {  // exact uniform shuffle of every matching block
+            if (!ctx->d_order) CU(cudaMalloc(&ctx->d_order, ctx->n * sizeof(uint32_t)));
+            launch_exact_order(ctx, ctx->step, ctx->n / p.mblk, p.mblk, ctx->d_order, (uint32_t)ctx->w_off);
             p.order = ctx->d_order;
         }
         stamp_tiles(ctx, &p, g);
         cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
+        commit_tiles(ctx, p);
         ++ctx->launches;
         ++ctx->step;
         if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
@@ -726,6 +772,7 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
     } else {
         stamp_tiles(ctx, &p, g);
         e = launch_step(ctx->lp_kind, p, g, false, ctx->stream);
+        if (e == cudaSuccess) commit_tiles(ctx, p);
     }
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;

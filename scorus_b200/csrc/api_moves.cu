@@ -58,10 +58,7 @@ static int twalk_common(scorus_ctx *ctx, const scorus_twalk_params *tw, const do
     }
     StepParams &p = tp->s;
     p.flag_kind = SCORUS_UFS_PROB;
-    p.flag_bits = flag_bits_for(tw->pphi);
-    p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(tw->pphi, 1.0) * 4294967296.0)
-                                   : (uint64_t)(fmin(tw->pphi, 1.0) * (double)(1u << p.flag_bits));
-    return SCORUS_OK;
+    return set_prob_flags(ctx, &p, tw->pphi);
 }
 
 // twalk::sample (:586-648): one matching, two half-passes (sample1 :650-762) with the roles exchanged
@@ -90,6 +87,7 @@ extern "C" int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *t
             stamp_tiles(ctx, &p, g);
             cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
+            commit_tiles(ctx, p);
             ++ctx->launches;
             ctx->step += 2;
         } else {
@@ -99,6 +97,7 @@ extern "C" int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *t
                 stamp_tiles(ctx, &p, g);
                 cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
                 if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
+            commit_tiles(ctx, p);
                 ++ctx->launches;
                 ++ctx->step;
             }
@@ -162,6 +161,7 @@ extern "C" int scorus_twalk_half_fixed(scorus_ctx *ctx, const scorus_twalk_param
     stamp_tiles(ctx, &p, g);
     cudaError_t e = launch_twalk(ctx->lp_kind, tp, g, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "t-walk launch: %s", cudaGetErrorString(e));
+            commit_tiles(ctx, p);
     ++ctx->launches;
     // half a step: the movers of this half-pass were proposed
     ctx->proposed += npair;

@@ -2,6 +2,7 @@
 // whole-ensemble matching over gathered copies, the redundant swap plan, and the one-sided NVLink paths
 // (CUDA IPC mappings of the peers' buffers, partner pulls, swap row pulls).
 #include "host_common.cuh"
+#include "step_reg_kernel.cuh"  // ld_stream
 
 // ------------------------------------------------------------------------------------------
 // sharding: one process per GPU
@@ -19,80 +20,185 @@ extern "C" int scorus_set_shard(scorus_ctx *ctx, uint64_t walker_offset, uint32_
     return SCORUS_OK;
 }
 
-// walker at every matching position of the WHOLE ensemble -> pairs with a member in [w_lo, w_hi)
-__global__ void local_pairs_kernel(const StepParams p, uint32_t n_global, uint32_t *pairs, uint32_t *count)
+// ------------------------------------------------------------------------------------------
+// pair lists of a shard under the whole-ensemble matching
+// ------------------------------------------------------------------------------------------
+// PAIRS_EITHER: every pair with a member in [w_lo, w_hi) (all-gather mode: both ranks of a cross pair compute it,
+// each keeps its own walker).  PAIRS_OWNER: every pair whose EVEN-position member is in [w_lo, w_hi) -- each pair on
+// exactly one rank, which updates both walkers (one-sided mode).  The positions are a keyed bijection of the walkers,
+// so ownership is balanced to O(sqrt(n)) without any exchange.
+enum : int { PAIRS_EITHER = 0, PAIRS_OWNER = 1 };
+
+// stream-ordered barrier across the ranks of scorus_ipc_attach, by flags in peer memory: rank r stores `epoch` into
+// slot r of every peer's flag row (the 32 doubles behind its log-probs) and waits until all slots of its own row
+// have reached it.  Threads 0..world-1 of ONE block.  Everything this GPU wrote before (kernel boundary +
+// fence.sys) is visible to a peer that has seen the flag.  A peer that never arrives traps after 20 s instead of
+// hanging the GPU.
+struct PeerTable { double *lp[16]; };
+__device__ __forceinline__ void peer_barrier_device(const PeerTable &t, uint32_t n_local, int world, int rank,
+                                                    unsigned long long epoch)
+{
+    const int q = (int)threadIdx.x;
+    if (q >= world) return;
+    unsigned long long *theirs = reinterpret_cast<unsigned long long *>(t.lp[q] + n_local) + rank;
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(t.lp[rank] + n_local) + q;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    unsigned long long v, t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) __trap();
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerTable t, uint32_t n_local, int world, int rank,
+                                                          unsigned long long epoch)
+{
+    peer_barrier_device(t, n_local, world, rank, epoch);
+}
+
+// large rungs: each local walker finds its matching position with the inverse bijection (rng.cuh) -- O(n_local) per
+// rank, no pass over the whole matching.  Block 0 first runs the inter-rank barrier when epoch != 0 (the pair list
+// depends on the step index only, so building it overlaps the wait); thread 0 also resets the tile counter of the
+// step kernel that follows.
+__global__ void __launch_bounds__(256) shard_pairs_kernel(const StepParams p, int mode, uint32_t *pairs, uint32_t *count,
+                                                          unsigned long long *tile_counter, const PeerTable t, int world,
+                                                          int rank, unsigned long long epoch)
+{
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0 && tile_counter) *tile_counter = 0ull;
+        if (epoch) peer_barrier_device(t, p.w_hi - p.w_lo, world, rank, epoch);
+    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    bool emit = false;
+    uint32_t a = 0, b = 0;
+    if (i < p.w_hi - p.w_lo) {
+        const uint32_t w = p.w_lo + i, r = w / p.npb, k = w - r * p.npb;
+        const BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off);
+        const uint32_t pos = bij_inv(k, p.npb, p.bij_bits, K);
+        const uint32_t mate = r * p.npb + bij(pos ^ 1u, p.npb, p.bij_bits, K);
+        const bool even = (pos & 1u) == 0u;
+        const bool mate_local = mate >= p.w_lo && mate < p.w_hi;
+        emit = mode == PAIRS_OWNER ? even : (even || !mate_local);
+        a = even ? w : mate;  // list order = matching order: even position first
+        b = even ? mate : w;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(count, 2u * (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (emit) {
+            const uint32_t slot = base + 2u * (uint32_t)__popc(m & ((1u << lane) - 1u));
+            pairs[slot] = a;
+            pairs[slot + 1] = b;
+        }
+    }
+}
+
+// small rungs (exact shuffle: the order of the whole ensemble is in p.order): scan the matching
+__global__ void local_pairs_kernel(const StepParams p, uint32_t n_global, int mode, uint32_t *pairs, uint32_t *count)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (2u * k + 1u >= n_global) return;
     const uint32_t a = walker_at(p, 2u * k), b = walker_at(p, 2u * k + 1u);
     const bool ina = a >= p.w_lo && a < p.w_hi, inb = b >= p.w_lo && b < p.w_hi;
-    if (ina || inb) {
+    if (mode == PAIRS_OWNER ? ina : (ina || inb)) {
         const uint32_t slot = atomicAdd(count, 2u);
         pairs[slot] = a;
         pairs[slot + 1] = b;
     }
 }
 
-extern "C" int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
-                                       size_t nbeta, const double *ens_all, const double *lp_all)
+// common front end of the two whole-ensemble-matching entry points: validates, fills the launch parameters with
+// GLOBAL ids and builds this rank's pair list for step ctx->step.  epoch != 0: the list kernel starts with the
+// inter-rank barrier.
+static int global_matching_setup(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta, size_t nbeta,
+                                 int mode, unsigned long long epoch, StepParams *pp, Geometry *gp, bool *all_flags)
 {
-    if (!ctx || !ufs || !beta || !ens_all || !lp_all) return SCORUS_ERR_INVALID_ARG;
     const size_t ng = ctx->n_global;
     int rc = scorus_check_sample_args(ng, ng, nbeta);
     if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
     if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
     if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
     if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1");
-    if (ufs->kind == SCORUS_UFS_MASK) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-evaluated masks are not supported across shards");
-    if (ctx->sequential || ctx->pitch > 256) return fail(ctx, SCORUS_ERR_INVALID_ARG, "global matching needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
+    if (ufs->kind == SCORUS_UFS_MASK) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-evaluated masks are per shard: use scorus_sample_pt_fixed on a gathered ensemble");
+    if (ctx->sequential || ctx->pitch > 256) return fail(ctx, SCORUS_ERR_INVALID_ARG, "whole-ensemble matching over shards needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
     cudaSetDevice(ctx->device);
-
-    StepParams p;
-    Geometry g;
+    StepParams &p = *pp;
+    Geometry &g = *gp;
     if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
     if ((rc = fill_common(ctx, &p, &g, nbeta))) return rc;
-    if (g.kernel != KERNEL_REG) return fail(ctx, SCORUS_ERR_INVALID_ARG, "global matching needs the register kernel");
+    if (g.kernel != KERNEL_REG) return fail(ctx, SCORUS_ERR_INVALID_ARG, "whole-ensemble matching over shards needs the register kernel");
     const double sqrt_a = sqrt(a);
     p.inv_sqrt_a = 1.0 / sqrt_a;
     p.z_range = 2.0 * (sqrt_a - p.inv_sqrt_a);
     p.flag_kind = (uint32_t)ufs->kind;
-    bool all_flags = ufs->kind == SCORUS_UFS_ALL;
-    if (ufs->kind == SCORUS_UFS_PROB) {
-        if (!(ufs->prob > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "Prob(p) needs p > 0");
-        p.flag_bits = flag_bits_for(ufs->prob);
-        p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(ufs->prob, 1.0) * 4294967296.0)
-                                       : (uint64_t)(fmin(ufs->prob, 1.0) * (double)(1u << p.flag_bits));
-    }
-    // ids are global in this mode: no offsets on the stream keys
+    *all_flags = ufs->kind == SCORUS_UFS_ALL;
+    if (ufs->kind == SCORUS_UFS_PROB && (rc = set_prob_flags(ctx, &p, ufs->prob))) return rc;
+    // ids are global in this mode: no offsets on the stream keys, whole-rung matching
     p.npb = (uint32_t)(ng / nbeta);
     p.bij_bits = bij_bits(p.npb);
+    p.mblk = p.npb; p.mblk_bits = p.bij_bits; p.mblk_off = 0;
     p.w_off = 0; p.rung_off = 0;
     p.w_lo = (uint32_t)ctx->w_off; p.w_hi = (uint32_t)(ctx->w_off + ctx->n);
     p.step = ctx->step; p.onehot = ctx->onehot;
     p.order = nullptr;
-    if (p.npb <= kExactShuffleMax) {  // exact shuffle of every rung of the whole ensemble
+    p.dirty = nullptr;
+    if ((rc = ensure(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * ctx->n * sizeof(uint32_t)))) return rc;
+    if (!ctx->d_count) CU(cudaMalloc(&ctx->d_count, sizeof(uint32_t) + 2 * sizeof(unsigned long long)));
+    unsigned long long *tile_counter = reinterpret_cast<unsigned long long *>(ctx->d_count) + 1;
+    CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(uint32_t), ctx->stream));
+    PeerTable t;
+    for (int q = 0; q < 16; ++q) t.lp[q] = ctx->peer_lp[q];
+    if (p.npb <= kExactShuffleMax) {
+        // exact shuffle of every rung of the whole ensemble (small rungs), then a scan of the matching
         if ((rc = ensure(ctx, (void **)&ctx->d_gorder, &ctx->gorder_cap, ng * sizeof(uint32_t)))) return rc;
         launch_exact_order(ctx, ctx->step, nbeta, p.npb, ctx->d_gorder, 0u);
         p.order = ctx->d_gorder;
+        if (epoch) peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(t, (uint32_t)ctx->n, ctx->world, ctx->rank, epoch);
+        CU(cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+        local_pairs_kernel<<<(unsigned)((ng / 2 + 255) / 256), 256, 0, ctx->stream>>>(p, (uint32_t)ng, mode, ctx->d_pairs, ctx->d_count);
+        ctx->launches += epoch ? 2 : 1;
+    } else {
+        shard_pairs_kernel<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(p, mode, ctx->d_pairs, ctx->d_count, tile_counter,
+                                                                                   t, ctx->world, ctx->rank, epoch);
+        ++ctx->launches;
     }
-    if ((rc = ensure(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * ctx->n * sizeof(uint32_t)))) return rc;
-    if (!ctx->d_count) CU(cudaMalloc(&ctx->d_count, sizeof(uint32_t)));
-    CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(uint32_t), ctx->stream));
-    local_pairs_kernel<<<(unsigned)((ng / 2 + 255) / 256), 256, 0, ctx->stream>>>(p, (uint32_t)ng, ctx->d_pairs, ctx->d_count);
-    ++ctx->launches;
-    // the step itself: pair list as the matching order, rows from the gathered copies
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "pair list launch: %s", cudaGetErrorString(e));
+    // the step itself: pair list as the matching order, tiles claimed dynamically from the counter the list kernel reset
     p.order = ctx->d_pairs;
     p.n_dev = ctx->d_count;
     p.n = (uint32_t)(2 * ctx->n);
     p.ntiles = (p.n + 31u) / 32u;
-    p.src_ens = ens_all;
+    p.tile_counter = env_int("SCORUS_DYNAMIC_TILES", 1) ? tile_counter : nullptr;
+    p.tile_base = 0;
+    return SCORUS_OK;
+}
+
+extern "C" int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
+                                       size_t nbeta, const double *ens_all, const double *lp_all)
+{
+    if (!ctx || !ufs || !beta || !ens_all || !lp_all) return SCORUS_ERR_INVALID_ARG;
+    StepParams p;
+    Geometry g;
+    bool all_flags = false;
+    int rc = global_matching_setup(ctx, a, ufs, beta, nbeta, PAIRS_EITHER, 0ull, &p, &g, &all_flags);
+    if (rc) return rc;
+    p.src_ens = ens_all;  // rows from the gathered copies
     p.src_lp = lp_all;
     cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
     ++ctx->launches;
     ++ctx->step;
     count_proposed(ctx, nbeta, p.npb, p.w_lo, p.w_hi, 1);
-    if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ng) % ctx->dim;
+    if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
     return after_step(ctx);
 }
 
@@ -137,6 +243,7 @@ extern "C" int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens, void *handle
     if (!ctx || !handle_ens || !handle_lp) return SCORUS_ERR_INVALID_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));  // the barrier flags behind the log-probs are zeroed before a peer can write them
     CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_ens, ctx->d_ens));
     CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_lp, ctx->d_lp));
     return SCORUS_OK;
@@ -162,123 +269,117 @@ extern "C" int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const voi
     if (!ctx->d_peer_lp) CU(cudaMalloc(&ctx->d_peer_lp, 16 * sizeof(double *)));
     CU(cudaMemcpy(ctx->d_peer_ens, ctx->peer_ens, 16 * sizeof(double *), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_peer_lp, ctx->peer_lp, 16 * sizeof(double *), cudaMemcpyHostToDevice));
-    if (!ctx->d_stage) CU(cudaMalloc(&ctx->d_stage, ctx->n * (size_t)ctx->pitch * sizeof(double)));
-    if (!ctx->d_stage_lp) CU(cudaMalloc(&ctx->d_stage_lp, ctx->n * sizeof(double)));
+    ctx->bar_epoch = 0;
     return SCORUS_OK;
 }
 
-// pulls, for every pair with exactly one local member, the remote member's row and log-prob into the
-// stage slot of the local member.  One warp per pair, four pairs in flight per warp.
-__global__ void __launch_bounds__(256) pull_partners_kernel(const uint32_t *pairs, const uint32_t *count, uint32_t w_lo,
-                                                            uint32_t w_hi, uint32_t n_local, uint32_t pitch,
-                                                            double *const *peer_ens, double *const *peer_lp,
-                                                            double *stage, double *stage_lp)
+// Measured NVLink read bandwidth of this GPU from one peer, the denominator of the one-sided step's roofline: (a) a
+// copy-engine cudaMemcpyAsync from the peer's mapped ensemble, (b) an SM kernel streaming 16-byte loads from it, the
+// access pattern of the step kernel.  `bytes` of the peer's ensemble buffer are read `iters` times; results in GB/s.
+__global__ void __launch_bounds__(512) peer_read_kernel(const double2 *src, size_t nvec, double *sink)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t npairs = __ldg(count) >> 1, nvec = pitch >> 1;
-    for (uint32_t pr = warp; pr < npairs; pr += nwarps) {
-        const uint32_t a = __ldg(pairs + 2 * pr), b = __ldg(pairs + 2 * pr + 1);
-        const bool ina = a >= w_lo && a < w_hi, inb = b >= w_lo && b < w_hi;
-        if (ina == inb) continue;  // both local: nothing to pull
-        const uint32_t local = ina ? a : b, remote = ina ? b : a;
-        const uint32_t q = remote / n_local, r = remote - q * n_local;
-        const double2 *src = reinterpret_cast<const double2 *>(peer_ens[q] + (size_t)r * pitch);
-        double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)(local - w_lo) * pitch);
-        for (uint32_t c = lane; c < nvec; c += 128) {  // up to four 16-byte peer loads in flight per lane
-            double2 v0 = src[c], v1, v2, v3;
-            const bool h1 = c + 32 < nvec, h2 = c + 64 < nvec, h3 = c + 96 < nvec;
-            if (h1) v1 = src[c + 32];
-            if (h2) v2 = src[c + 64];
-            if (h3) v3 = src[c + 96];
-            dst[c] = v0;
-            if (h1) dst[c + 32] = v1;
-            if (h2) dst[c + 64] = v2;
-            if (h3) dst[c + 96] = v3;
-        }
-        if (lane == 0) stage_lp[local - w_lo] = peer_lp[q][r];
+    double acc = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+        const double2 a = ld_stream(src + i), b = ld_stream(src + i + stride), c = ld_stream(src + i + 2 * stride),
+                      d = ld_stream(src + i + 3 * stride);
+        acc += a.x + a.y + b.x + b.y + c.x + c.y + d.x + d.y;
     }
+    for (; i < nvec; i += stride) { const double2 a = ld_stream(src + i); acc += a.x + a.y; }
+    if (acc == 1.2345e300) *sink = acc;  // keeps the loads alive
 }
 
-// sample_pt of a walker shard with the whole-ensemble matching, phase 1: build the local pair list
-// and pull the remote partners' rows over NVLink.  Every rank must pass a barrier on the stream
-// before (peers finished their previous step) and after (nobody writes before everybody has read).
-extern "C" int scorus_sample_pt_p2p_begin(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta,
-                                          size_t nbeta)
+extern "C" int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t bytes, int iters, double *gbps_copy_engine,
+                                          double *gbps_sm_loads)
+{
+    if (!ctx || iters < 1) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx->d_peer_ens || peer < 0 || peer >= ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
+    cudaSetDevice(ctx->device);
+    const size_t cap = ctx->n * (size_t)ctx->pitch * sizeof(double);
+    if (bytes == 0 || bytes > cap) bytes = cap;
+    bytes &= ~(size_t)15;
+    if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, cap));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float ms = 0.f;
+    CU(cudaMemcpyAsync(ctx->d_scratch, ctx->peer_ens[peer], bytes, cudaMemcpyDeviceToDevice, ctx->stream));  // warm-up
+    CU(cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < iters; ++k)
+        CU(cudaMemcpyAsync(ctx->d_scratch, ctx->peer_ens[peer], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (gbps_copy_engine) *gbps_copy_engine = (double)bytes * iters / (ms * 1e-3) / 1e9;
+    const unsigned grid = (unsigned)ctx->num_sms * 4u;
+    peer_read_kernel<<<grid, 512, 0, ctx->stream>>>((const double2 *)ctx->peer_ens[peer], bytes / 16, ctx->d_scratch);
+    CU(cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < iters; ++k)
+        peer_read_kernel<<<grid, 512, 0, ctx->stream>>>((const double2 *)ctx->peer_ens[peer], bytes / 16, ctx->d_scratch);
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (gbps_sm_loads) *gbps_sm_loads = (double)bytes * iters / (ms * 1e-3) / 1e9;
+    ctx->launches += (uint64_t)iters + 1;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return SCORUS_OK;
+}
+
+// Stream-ordered barrier across the attached ranks (flags in peer memory, no host synchronisation, no NCCL).
+// Every rank must call it the same number of times.
+extern "C" int scorus_peer_barrier(scorus_ctx *ctx)
+{
+    if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
+    cudaSetDevice(ctx->device);
+    PeerTable t;
+    for (int q = 0; q < 16; ++q) t.lp[q] = ctx->peer_lp[q];
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(t, (uint32_t)ctx->n, ctx->world, ctx->rank, ++ctx->bar_epoch);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "barrier launch: %s", cudaGetErrorString(e));
+    return SCORUS_OK;
+}
+
+// sample_pt of a walker shard under the reference's whole-ensemble matching (ensemble_sample.rs:135-148), one-sided:
+// every pair of the matching is OWNED by the rank that holds its even-position member; the owner reads both rows
+// where they live (a remote partner's row straight from the peer's HBM over NVLink, no staging copy), proposes and
+// decides for both walkers, and writes accepted rows and log-probs back to their home ranks.  A walker is in exactly
+// one pair and a pair on exactly one rank, so nothing is computed twice, half of the cross-rank rows travel, and
+// inside a step no rank touches a row another rank uses: the only synchronisation is ONE barrier before each step
+// (fused into the pair-list kernel) and one after the last, so that whatever follows sees every peer's writes.
+// Results are bit-identical to the single-GPU step (same streams, keyed by global walker ids).
+extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta, size_t nbeta,
+                                     uint64_t nsteps)
 {
     if (!ctx || !ufs || !beta) return SCORUS_ERR_INVALID_ARG;
     if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
-    if (ctx->p2p_pending) return fail(ctx, SCORUS_ERR_INVALID_ARG, "scorus_sample_pt_p2p_end has not been called");
-    const size_t ng = ctx->n_global;
-    int rc = scorus_check_sample_args(ng, ng, nbeta);
-    if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
-    if (ng != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");
-    if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
-    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
-    if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1");
-    if (ufs->kind == SCORUS_UFS_MASK) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-evaluated masks are not supported across shards");
-    cudaSetDevice(ctx->device);
-    StepParams &p = ctx->p2p_params;
-    Geometry &g = ctx->p2p_geom;
-    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
-    if ((rc = fill_common(ctx, &p, &g, nbeta))) return rc;
-    if (g.kernel != KERNEL_REG) return fail(ctx, SCORUS_ERR_INVALID_ARG, "one-sided matching needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
-    const double sqrt_a = sqrt(a);
-    p.inv_sqrt_a = 1.0 / sqrt_a;
-    p.z_range = 2.0 * (sqrt_a - p.inv_sqrt_a);
-    p.flag_kind = (uint32_t)ufs->kind;
-    ctx->p2p_all_flags = ufs->kind == SCORUS_UFS_ALL;
-    if (ufs->kind == SCORUS_UFS_PROB) {
-        if (!(ufs->prob > 0.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "Prob(p) needs p > 0");
-        p.flag_bits = flag_bits_for(ufs->prob);
-        p.flag_thr = p.flag_bits == 32 ? (uint64_t)llrint(fmin(ufs->prob, 1.0) * 4294967296.0)
-                                       : (uint64_t)(fmin(ufs->prob, 1.0) * (double)(1u << p.flag_bits));
+    if (ctx->n_global != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");
+    if (ctx->n > (1u << 28)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "at most 2^28 walkers per shard");
+    if (ctx->track_dirty) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-buffer calls are per shard");
+    for (uint64_t s = 0; s < nsteps; ++s) {
+        StepParams p;
+        Geometry g;
+        bool all_flags = false;
+        int rc = global_matching_setup(ctx, a, ufs, beta, nbeta, PAIRS_OWNER, ++ctx->bar_epoch, &p, &g, &all_flags);
+        if (rc) return rc;
+        for (int q = 0; q < 16; ++q) { p.peer_ens[q] = ctx->peer_ens[q]; p.peer_lp[q] = ctx->peer_lp[q]; }
+        p.peer_n = (uint32_t)ctx->n;
+        p.accepted_out = nullptr;
+        cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
+        ++ctx->launches;
+        ++ctx->step;
+        count_proposed(ctx, nbeta, p.npb, p.w_lo, p.w_hi, 1);
+        if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
+        if (ctx->tr_ncap != 0 || ctx->mom_rungs != 0) {  // per-step hooks read the local rows: peers must be done
+            if ((rc = scorus_peer_barrier(ctx))) return rc;
+            if ((rc = after_step(ctx))) return rc;
+        }
     }
-    p.npb = (uint32_t)(ng / nbeta);
-    p.bij_bits = bij_bits(p.npb);
-    p.w_off = 0; p.rung_off = 0;
-    p.w_lo = (uint32_t)ctx->w_off; p.w_hi = (uint32_t)(ctx->w_off + ctx->n);
-    p.step = ctx->step; p.onehot = ctx->onehot;
-    p.order = nullptr;
-    if (p.npb <= kExactShuffleMax) {
-        if ((rc = ensure(ctx, (void **)&ctx->d_gorder, &ctx->gorder_cap, ng * sizeof(uint32_t)))) return rc;
-        launch_exact_order(ctx, ctx->step, nbeta, p.npb, ctx->d_gorder, 0u);
-        p.order = ctx->d_gorder;
-    }
-    if ((rc = ensure(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * ctx->n * sizeof(uint32_t)))) return rc;
-    if (!ctx->d_count) CU(cudaMalloc(&ctx->d_count, sizeof(uint32_t)));
-    CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(uint32_t), ctx->stream));
-    local_pairs_kernel<<<(unsigned)((ng / 2 + 255) / 256), 256, 0, ctx->stream>>>(p, (uint32_t)ng, ctx->d_pairs, ctx->d_count);
-    pull_partners_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, ctx->stream>>>(
-        ctx->d_pairs, ctx->d_count, p.w_lo, p.w_hi, (uint32_t)ctx->n, ctx->pitch, ctx->d_peer_ens, ctx->d_peer_lp,
-        ctx->d_stage, ctx->d_stage_lp);
-    ctx->launches += 2;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "pull launch: %s", cudaGetErrorString(e));
-    p.order = ctx->d_pairs;
-    p.n_dev = ctx->d_count;
-    p.n = (uint32_t)(2 * ctx->n);
-    p.ntiles = (p.n + 31u) / 32u;
-    p.stage_ens = ctx->d_stage;
-    p.stage_lp = ctx->d_stage_lp;
-    ctx->p2p_pending = true;
-    return SCORUS_OK;
-}
-
-// phase 2: the fused step on local rows + staged partner rows
-extern "C" int scorus_sample_pt_p2p_end(scorus_ctx *ctx)
-{
-    if (!ctx) return SCORUS_ERR_INVALID_ARG;
-    if (!ctx->p2p_pending) return fail(ctx, SCORUS_ERR_INVALID_ARG, "no step pending");
-    cudaSetDevice(ctx->device);
-    ctx->p2p_pending = false;
-    cudaError_t e = launch_step(ctx->lp_kind, ctx->p2p_params, ctx->p2p_geom, ctx->p2p_all_flags, ctx->stream);
-    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
-    ++ctx->launches;
-    ++ctx->step;
-    count_proposed(ctx, ctx->p2p_params.nbeta, ctx->p2p_params.npb, ctx->p2p_params.w_lo, ctx->p2p_params.w_hi, 1);
-    if (ctx->p2p_params.flag_kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
-    return after_step(ctx);
+    return nsteps ? scorus_peer_barrier(ctx) : SCORUS_OK;
 }
 
 // rows of a cross-rank ladder swap, pulled one-sidedly: scratch[slot] <- (peer holding src)[src] for

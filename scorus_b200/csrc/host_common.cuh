@@ -48,7 +48,11 @@ struct scorus_ctx {
     int world = 1, rank = 0;
     double *peer_ens[16] = {nullptr}, *peer_lp[16] = {nullptr};
     double **d_peer_ens = nullptr, **d_peer_lp = nullptr;   // device copies of the tables
-    double *d_stage = nullptr, *d_stage_lp = nullptr;       // pulled partner rows, one per local walker
+    unsigned long long bar_epoch = 0;                       // inter-rank flag barrier (api_shard.cu): calls so far
+    // blocked matchings (scorus_set_matching_blocks): blocks per rung on "local" steps, key offset of block 0,
+    // and the schedule: global_every = k >= 1 -> steps with step % k == 0 match whole rungs; 0 -> never
+    uint32_t mblocks = 1, mblk_off = 0;
+    uint64_t global_every = 0;
     // K6: statistics scratch and the chain trace
     double *d_part = nullptr; size_t part_cap = 0;
     double *d_stat = nullptr; size_t stat_cap = 0;
@@ -64,10 +68,6 @@ struct scorus_ctx {
     double *d_iat = nullptr; size_t iat_cap = 0;
     uint32_t mom_rungs = 0; bool mom_cov = false;
     uint64_t mom_every = 1, mom_tick = 0, mom_count = 0;
-    bool p2p_pending = false;                                // scorus_sample_pt_p2p_begin without _end
-    StepParams p2p_params;
-    Geometry p2p_geom;
-    bool p2p_all_flags = false;
     unsigned long long *d_stats = nullptr;
     // scratch for caller-supplied streams
     double *d_z = nullptr, *d_u = nullptr;
@@ -123,7 +123,12 @@ int ensure(scorus_ctx *ctx, void **buf, size_t *cap, size_t bytes);
 int step_geometry(scorus_ctx *ctx, Geometry *g, bool tile_in_smem);
 int upload_beta(scorus_ctx *ctx, const double *beta, size_t nbeta);
 void stamp_tiles(scorus_ctx *ctx, StepParams *p, const Geometry &g);
+void commit_tiles(scorus_ctx *ctx, const StepParams &p);  // after the launch succeeded: advance the host's ticket
+// matching blocks of step `step` under the context's schedule -> p.mblk / mblk_bits / mblk_off
+void set_matching(const scorus_ctx *ctx, StepParams *p, uint64_t step);
 uint32_t flag_bits_for(double prob);
+// UpdateFlagSpec::Prob(p) -> p.flag_bits / p.flag_thr (the one place that quantises p; INVALID_ARG unless p > 0)
+int set_prob_flags(scorus_ctx *ctx, StepParams *p, double prob);
 int ensure_rung_stats(scorus_ctx *ctx, size_t nbeta);
 void count_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb, uint64_t w_lo, uint64_t w_hi, uint64_t steps);
 void count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb);

@@ -59,9 +59,9 @@ cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const G
         // rows of 5 or 6 double2 (D = 9..12): two lanes x three chunks wastes 1/6 of the lanes, eight lanes
         // x one chunk would waste 3/8 -- and these targets (10-D Rastrigin) are bound by fp64 arithmetic
         if (nvec == 5 || nvec == 6)
-            return p.stage_ens ? launch_kernel(step_reg_kernel<Plugin, 2, 3, true>, p, g, st)
+            return p.peer_n ? launch_kernel(step_reg_kernel<Plugin, 2, 3, true>, p, g, st)
                                : launch_kernel(step_reg_kernel<Plugin, 2, 3>, p, g, st);
-        if (p.stage_ens) {  // one-sided multi-GPU mode
+        if (p.peer_n) {  // one-sided multi-GPU mode: rows read from / written to their home ranks
             if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4, true>, p, g, st);
             if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2, true>, p, g, st);
             switch (coop_group(p.pitch)) {

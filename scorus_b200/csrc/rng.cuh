@@ -73,10 +73,12 @@ __host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi)
 
 struct BijKeys { uint32_t k[8]; };
 
+// sub0: first of the two draws the keys come from -- 0 for a whole-rung matching, 2c for matching block c of the
+// rung (blocked matchings)
 __host__ __device__ __forceinline__ BijKeys bij_keys(uint64_t seed, uint64_t step, uint32_t stream,
-                                                     uint32_t idx)
+                                                     uint32_t idx, uint32_t sub0 = 0)
 {
-    U4 a = draw(seed, step, stream, idx, 0), b = draw(seed, step, stream, idx, 1);
+    U4 a = draw(seed, step, stream, idx, sub0), b = draw(seed, step, stream, idx, sub0 + 1u);
     BijKeys r;
     r.k[0] = a.x; r.k[1] = a.y; r.k[2] = a.z; r.k[3] = a.w;
     r.k[4] = b.x; r.k[5] = b.y; r.k[6] = b.z; r.k[7] = b.w;
@@ -106,6 +108,41 @@ __host__ __device__ __forceinline__ uint32_t bij(uint32_t x, uint32_t n, uint32_
         x = (x + K.k[6]) & mask; x = (x * (K.k[7] | 1u)) & mask; x ^= x >> s1; x = (x * C3) & mask; x ^= x >> s2;
     } while (x >= n);
     return x;
+}
+
+// ---- the inverse bijection: position of a walker in the matching order ----
+// Every round of bij is invertible on b-bit integers (add, multiply by an odd number, xorshift), and the inverse of a
+// cycle-walked permutation is the cycle-walked inverse, so a rank of a sharded run finds the matching position -- and
+// with it the partner -- of each of ITS walkers in O(1) instead of scanning the whole matching (api_shard.cu).
+__host__ __device__ constexpr uint32_t inv_odd32(uint32_t a)
+{
+    uint32_t x = a;  // a*a = 1 mod 8: three correct bits, doubled by every Newton step
+    for (int i = 0; i < 4; ++i) x *= 2u - a * x;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t unxorshift(uint32_t y, uint32_t s, uint32_t b)
+{
+    uint32_t x = y;
+    for (uint32_t t = s; t < b; t += s) x ^= y >> t;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t bij_inv(uint32_t y, uint32_t n, uint32_t b, const BijKeys &K)
+{
+    constexpr uint32_t I0 = inv_odd32(0x9E3779B1u), I1 = inv_odd32(0x85EBCA6Bu), I2 = inv_odd32(0xC2B2AE35u),
+                       I3 = inv_odd32(0x27D4EB2Fu);
+    const uint32_t mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    uint32_t s1 = (b + 1) / 2, s2 = b / 3;
+    if (s1 < 1) s1 = 1;
+    if (s2 < 1) s2 = 1;
+    const uint32_t m0 = inv_odd32(K.k[1] | 1u), m1 = inv_odd32(K.k[3] | 1u), m2 = inv_odd32(K.k[5] | 1u),
+                   m3 = inv_odd32(K.k[7] | 1u);
+    do {
+        y = unxorshift(y, s2, b); y = (y * I3) & mask; y = unxorshift(y, s1, b); y = (y * m3) & mask; y = (y - K.k[6]) & mask;
+        y = unxorshift(y, s2, b); y = (y * I2) & mask; y = unxorshift(y, s1, b); y = (y * m2) & mask; y = (y - K.k[4]) & mask;
+        y = unxorshift(y, s2, b); y = (y * I1) & mask; y = unxorshift(y, s1, b); y = (y * m1) & mask; y = (y - K.k[2]) & mask;
+        y = unxorshift(y, s2, b); y = (y * I0) & mask; y = unxorshift(y, s1, b); y = (y * m0) & mask; y = (y - K.k[0]) & mask;
+    } while (y >= n);
+    return y;
 }
 
 // Goodman-Weare stretch factor from a unit uniform: src/mcmc/utils.rs:39-44 with

@@ -48,8 +48,11 @@ struct RegGeom {
     static constexpr int kBlocks = G / kRowsPerBlock;
 };
 
-// kStaged: one-sided multi-GPU mode (remote partners' rows pulled into p.stage_ens / p.stage_lp).  A
-// template parameter because even uniform branches on it cost 12 % in the single-GPU kernel.
+// kPeer: one-sided multi-GPU mode -- this rank owns the pairs of its list and reads / writes BOTH rows wherever they
+// live (p.peer_ens / p.peer_lp: CUDA-IPC mappings of the peers' buffers, loads and stores travel over NVLink).  A pair
+// is owned by exactly one rank and a walker is in exactly one pair, so within a step nobody else touches either row:
+// one barrier between steps is all the synchronisation there is (api_shard.cu).  A template parameter because even
+// uniform branches on it cost 12 % in the single-GPU kernel.
 // Warps per block (= per SM): 20 under a 96-register cap for rows wider than 16 double2 (launch.cuh), 16 under 128
 // registers otherwise; the dense plugin keeps 8 warps and up to 255 registers for its DMMA accumulators.
 template <class Plugin, int G, int ITERS>
@@ -71,7 +74,15 @@ __host__ __device__ constexpr bool reg_kernel_direct()
     return !Plugin::kNeedsRow && G != 16;
 }
 
-template <class Plugin, int G, int ITERS, bool kStaged = false>
+// 8-byte read of a peer's memory: not through the non-coherent path (the value was written by another GPU)
+__device__ __forceinline__ double ld_peer_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <class Plugin, int G, int ITERS, bool kPeer = false>
 __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32, 1) step_reg_kernel(const StepParams p)
 {
     using Geo = RegGeom<G, ITERS>;
@@ -135,23 +146,30 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         if (sm_order) return sm_order[pos];
         if (p.order) return __ldg(p.order + pos);
         if (p.debug_identity) return pos;
-        const uint32_t r = pos / p.npb;
-        if (r != key_rung) { K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off); key_rung = r; }
-        return r * p.npb + bij(pos - r * p.npb, p.npb, p.bij_bits, K);
+        const uint32_t blk = pos / p.mblk;  // matching block (the whole rung unless the matching is blocked)
+        if (blk != key_rung) {
+            const uint32_t r = pos / p.npb;
+            K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off, 2u * (blk - r * (p.npb / p.mblk) + p.mblk_off));
+            key_rung = blk;
+        }
+        return blk * p.mblk + bij(pos - blk * p.mblk, p.mblk, p.mblk_bits, K);
+    };
+    // peer mode: home of a walker as (rank << 28 | row), computed once per tile by the walker's lane
+    auto home_of = [&](uint32_t wid) -> uint32_t {
+        const uint32_t q = wid / p.peer_n;
+        return (q << 28) | (wid - q * p.peer_n);
     };
 
-    // loads block `blk` of a tile whose lane = walker ids are `wt`: rows wl = grp*G + blk*GB + i
+    // loads block `blk` of a tile whose lane = walker ids are `wt` (peer mode: lane = walker homes): rows
+    // wl = grp*G + blk*GB + i
     auto load_block = [&](double2 (&x)[GB][ITERS], uint32_t wt, int blk) {
 #pragma unroll
         for (int i = 0; i < GB; ++i) {
             const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
             const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
-            const double *base = p.src_ens + (size_t)row * p.pitch;
-            if constexpr (kStaged) {  // one-sided mode: my rows are local, a remote partner's row sits in the stage
-                const uint32_t mate = __shfl_sync(0xffffffffu, wt, wl ^ 1u);
-                const bool mine_r = row >= p.w_lo && row < p.w_hi;
-                base = mine_r ? p.ens + (size_t)(row - p.w_lo) * p.pitch : p.stage_ens + (size_t)(mate - p.w_lo) * p.pitch;
-            }
+            const double *base;
+            if constexpr (kPeer) base = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;  // maybe over NVLink
+            else base = p.src_ens + (size_t)row * p.pitch;
             const double2 *src = reinterpret_cast<const double2 *>(base);
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
@@ -179,20 +197,16 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         act = pos < npos;
         w = act ? walker_of(pos) : p.w_lo;
     }
-    // old log-prob: from the (gathered) array, or in one-sided mode local / staged like the rows
-    auto load_lp = [&](uint32_t wid, bool a) -> double {
-        if constexpr (kStaged) {
-            const uint32_t mate = __shfl_xor_sync(0xffffffffu, wid, 1);
-            if (!a) return 0.0;
-            const bool mine_w = wid >= p.w_lo && wid < p.w_hi;
-            return mine_w ? __ldg(p.lp + (wid - p.w_lo)) : __ldg(p.stage_lp + (mate - p.w_lo));
-        } else {
-            return a ? __ldg(p.src_lp + wid) : 0.0;
-        }
+    [[maybe_unused]] uint32_t home = 0, home_n = 0;  // peer mode: where my walker (of this / the next tile) lives
+    if constexpr (kPeer) home = home_of(w);
+    // old log-prob: from the (gathered) array, or in one-sided mode from the walker's home rank
+    auto load_lp = [&](uint32_t wid, uint32_t hm, bool a) -> double {
+        if constexpr (kPeer) return a ? ld_peer_f64(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
+        else return a ? __ldg(p.src_lp + wid) : 0.0;
     };
-    double lp_old = load_lp(w, act);
+    double lp_old = load_lp(w, home, act);
     double2 xn[GB][ITERS];
-    load_block(xn, w, 0);
+    load_block(xn, kPeer ? home : w, 0);
 
     for (;;) {
         // ---- P1: lane = walker: z, u, flags, (nphi-1) ln z ----
@@ -233,8 +247,9 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         } else {
             w_n = p.w_lo;
         }
-        lp_n = load_lp(w_n, act_n);
-        if constexpr (!kStaged) {
+        if constexpr (kPeer) home_n = home_of(w_n);
+        lp_n = load_lp(w_n, home_n, act_n);
+        if constexpr (!kPeer) {
             if (p.l2_prefetch && act_n) {  // my next-tile row -> L2, a whole tile ahead of its loads
                 const char *r = reinterpret_cast<const char *>(p.src_ens + (size_t)w_n * p.pitch);
                 for (uint32_t off = 0; off < p.row_bytes; off += 128u) prefetch_l2(r + off);
@@ -245,8 +260,11 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         double tot[Plugin::kAcc];
 #pragma unroll
         for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
-        // global-matching mode: walkers outside [w_lo, w_hi) belong to another rank, which updates them
-        const bool mine = act && w >= p.w_lo && w < p.w_hi;
+        // global-matching mode: walkers outside [w_lo, w_hi) belong to another rank, which updates them; peer mode: this
+        // rank owns the pair and updates both walkers at their homes
+        const bool mine = kPeer ? act : (act && w >= p.w_lo && w < p.w_hi);
+        // where my walker's results go: local row, or (peer mode) its home rank's buffers
+        double *const my_lp = kPeer ? p.peer_lp[home >> 28] + (home & 0x0FFFFFFFu) : p.lp + (w - p.w_lo);
         bool accept = false;
 
 #pragma unroll 1
@@ -256,8 +274,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             for (int i = 0; i < GB; ++i)
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
-            if (blk + 1 < NB) load_block(xn, w, blk + 1);
-            else if (tile_n < ntiles) load_block(xn, w_n, 0);
+            if (blk + 1 < NB) load_block(xn, kPeer ? home : w, blk + 1);
+            else if (tile_n < ntiles) load_block(xn, kPeer ? home_n : w_n, 0);
 
             double acc[Plugin::kAcc][GB];
             [[maybe_unused]] double2 yk[kDirect ? GB : 1][ITERS];  // direct path: the block's proposals stay in registers
@@ -343,8 +361,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     const double q = exp(lz + (lp_new - lp_old) * beta);
                     acc_now = mine && (u < q);
                     if (acc_now) {
-                        p.lp[w - p.w_lo] = lp_new;
-                        if (p.dirty) p.dirty[w - p.w_lo] = 1;
+                        *my_lp = lp_new;
+                        if constexpr (!kPeer) { if (p.dirty) p.dirty[w - p.w_lo] = 1; }
                         ++n_acc;
                         accept = true;
                     }
@@ -353,9 +371,12 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
 #pragma unroll
                 for (int i = 0; i < GB; ++i) {
                     const uint32_t rl = grp * G + (uint32_t)(blk * GB + i);
-                    const uint32_t row = __shfl_sync(0xffffffffu, w, rl);
+                    const uint32_t row = __shfl_sync(0xffffffffu, kPeer ? home : w, rl);
                     if ((accmask >> rl) & 1u) {
-                        double2 *dst = reinterpret_cast<double2 *>(p.ens + (size_t)(row - p.w_lo) * p.pitch);
+                        double *rowp;
+                        if constexpr (kPeer) rowp = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;
+                        else rowp = p.ens + (size_t)(row - p.w_lo) * p.pitch;
+                        double2 *dst = reinterpret_cast<double2 *>(rowp);
 #pragma unroll
                         for (int it = 0; it < ITERS; ++it) {
                             const uint32_t c = (uint32_t)it * G + j;
@@ -381,14 +402,17 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             const double q = exp(lz + (lp_new - lp_old) * beta);
             accept = mine && (u < q);
             if (accept) {
-                bulk_store(p.ens + (size_t)(w - p.w_lo) * p.pitch, smem_u32(own_b), p.row_bytes);
-                p.lp[w - p.w_lo] = lp_new;
-                if (p.dirty) p.dirty[w - p.w_lo] = 1;
+                double *rowp;
+                if constexpr (kPeer) rowp = p.peer_ens[home >> 28] + (size_t)(home & 0x0FFFFFFFu) * p.pitch;
+                else rowp = p.ens + (size_t)(w - p.w_lo) * p.pitch;
+                bulk_store(rowp, smem_u32(own_b), p.row_bytes);
+                *my_lp = lp_new;
+                if constexpr (!kPeer) { if (p.dirty) p.dirty[w - p.w_lo] = 1; }
                 ++n_acc;
             }
             bulk_commit();
         }
-        if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0;
+        if constexpr (!kPeer) { if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0; }
         if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
 
         if (tile_n >= ntiles) break;
@@ -396,6 +420,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         w = w_n;
         act = act_n;
         lp_old = lp_n;
+        if constexpr (kPeer) home = home_n;
     }
 
     if constexpr (!kDirect) bulk_wait_all();

@@ -42,11 +42,18 @@ struct StepParams {
     const double *src_ens;
     const double *src_lp;
     const uint32_t *n_dev;    // if set, the number of matching positions is read from device memory
-    // One-sided mode: instead of gathered copies, remote partners' rows were pulled over NVLink into
-    // stage_ens / stage_lp, indexed by the LOCAL member of the pair (local row = id - w_lo).
-    const double *stage_ens;
-    const double *stage_lp;
+    // One-sided ("peer") mode: the pair list in `order` holds the pairs this rank OWNS (global ids); the kernel reads
+    // both rows wherever they live -- peer_ens[q] / peer_lp[q] are the CUDA-IPC mappings of rank q's buffers (own
+    // rank: the local buffers) -- and writes both walkers' accepted rows and log-probs back to their home ranks over
+    // NVLink.  Walker w lives on rank w / peer_n at row w % peer_n.  peer_n == 0: not in this mode.
+    double *peer_ens[16];
+    double *peer_lp[16];
+    uint32_t peer_n;
     uint32_t w_lo, w_hi;
+    // Blocked matchings: every rung is cut into blocks of `mblk` walkers that are matched
+    // separately (mblk == npb: the reference's whole-rung matching); block c of a rung takes its bijection keys at
+    // sub = 2 (c + mblk_off), so that a shard holding block c of the whole ensemble draws what the single-GPU run draws.
+    uint32_t mblk, mblk_bits, mblk_off;
     // Dynamic tile scheduling (register kernel, single-GPU mode): after its first tile a warp takes
     // the next unclaimed one, tile = nwarps + (atomicAdd(tile_counter, 1) - tile_base).  Every launch
     // advances the counter by exactly ntiles, so the host knows the next base without a reset.
@@ -135,17 +142,22 @@ __device__ __forceinline__ uint32_t walker_at(const StepParams &p, uint32_t j)
 {
     if (p.order) return __ldg(p.order + j);
     if (p.debug_identity) return j;
-    uint32_t r = j / p.npb;
-    uint32_t k = j - r * p.npb;
-    BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off);
-    return r * p.npb + bij(k, p.npb, p.bij_bits, K);
+    const uint32_t blk = j / p.mblk, r = j / p.npb;
+    const uint32_t c = blk - r * (p.npb / p.mblk);
+    BijKeys K = bij_keys(p.seed, p.step, ST_PERM, r + p.rung_off, 2u * (c + p.mblk_off));
+    return blk * p.mblk + bij(j - blk * p.mblk, p.mblk, p.mblk_bits, K);
 }
 
 // ---- update flags (src/mcmc/ensemble_sample.rs:38-54), one lane per walker ----
 // Flag words live in shared memory as flagw[word * 32 + lane]: bit (d & 31) of word (d >> 5) set
 // means coordinate d moves.  Returns nphi = number of set flags that count (:164-167).
 
-// Prob(p): BPF random bits per coordinate, flag = value < thr; redrawn (attempt + 1) until one is set.
+// Prob(p): BPF random bits per coordinate, flag = value < thr; redrawn (attempt + 1) until one is set
+// (ensemble_sample.rs:43-50).  The loop is bounded: after kMaxFlagAttempts all-false draws (probability
+// (1-p)^(64 D): never at the p*D of any example) ONE coordinate is set, uniformly chosen from a further draw
+// (sub = kMaxFlagAttempts * nblk) -- which is also the exact p -> 0 limit of the reference's conditional law,
+// "exactly one flag, uniformly placed".  No input can make a kernel spin; oracle/philox_streams.c restates it.
+constexpr uint32_t kMaxFlagAttempts = 64;
 template <int BPF>
 __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw,
                                                    uint32_t lane, bool act)
@@ -188,6 +200,13 @@ __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint64_t
             }
         }
         if (nphi > 0 || !act) break;
+        if (attempt + 1u == kMaxFlagAttempts) {  // every word above was just written as zero
+            const U4 r = draw(p.seed, step, ST_FLAGS, w + p.w_off, kMaxFlagAttempts * nblk);
+            const uint32_t d = __umulhi(r.x, p.dim);
+            flagw[(d >> 5) * 32u + lane] = 1u << (d & 31u);
+            nphi = 1;
+            break;
+        }
     }
     return nphi;
 }

@@ -9,17 +9,20 @@ Two layouts, chosen from (nbeta, world size):
   (8*N bytes), every rank computes the same swap plan on its GPU (scorus_swap_plan_device), and only the
   rows that cross a rank boundary are exchanged (all_to_all_single).
 * ``walkers`` -- single-temperature runs: contiguous walker shards.
-    - matching="global": the reference's whole-rung matching.  Each step all-gathers the ensemble over
-      NVLink and runs scorus_sample_pt_global; results are bit-identical to the single-GPU run.  It is
-      NVLink-bound -- the faithful, not the fast, configuration.
-    - matching="p2p": the same matching without the all-gather: each rank maps its peers' buffers
-      (CUDA IPC) and pulls only the rows of its walkers' remote partners with one-sided NVLink reads
-      (1/world of the all-gather's traffic), then runs the fused step; also bit-identical.
-    - matching="local": every shard pairs within itself, no per-step exchange (each shard is itself a
-      valid ensemble; the matching stays state-independent, so the move is still a valid MCMC kernel).
+    - matching="p2p": the reference's whole-rung matching, one-sided.  Every pair is owned by the rank holding its
+      even-position member; the owner reads the partner's row straight from its home GPU over NVLink (CUDA IPC
+      mappings), runs the fused step for both walkers and writes accepted rows back.  One flag barrier in peer
+      memory per step, no NCCL call, nothing computed twice (scorus_sample_pt_peer).  Bit-identical to one GPU.
+    - matching="global": the same matching, literally as BASELINE.json words it: an NCCL all-gather of the
+      ensemble per step, then scorus_sample_pt_global.  NVLink-bound -- the baseline to beat.
+    - matching="local": every shard pairs within itself, no exchange: a BLOCKED matching (one block per shard).
+  ``global_every = k`` interleaves: steps whose index is a multiple of k use the whole-ensemble matching ("p2p" or
+  "global"), the others the blocked one.  The schedule depends on the step index only, so every step's matching is
+  independent of the state and each step is a valid stretch move; cross-shard mixing costs 1/k of the NVLink traffic.
 
-Random streams are keyed by global walker / rung ids (Sampler.set_shard), so ``rungs`` and
-``walkers/global`` reproduce the single-GPU chain exactly.
+Random streams are keyed by global walker / rung / block ids (Sampler.set_shard, set_matching_blocks), so EVERY mode
+reproduces a single-GPU chain bit for bit: ``rungs`` and ``walkers`` with k = 1 the reference-matching chain,
+``walkers`` with k > 1 or "local" the single-GPU chain with ``set_matching_blocks(world, 0, k)``.
 """
 from __future__ import annotations
 
@@ -141,20 +144,19 @@ class ShardedSampler:
         if matching not in ("global", "p2p", "local"):
             raise ValueError("matching must be 'global', 'p2p' or 'local'")
         self.matching = matching
-        # global_every = k > 1 (matching "global" / "p2p"): only every k-th step uses the whole-ensemble
-        # matching, the steps in between pair inside each shard.  The schedule depends on the
-        # step index only, so every step's matching is still state-independent -- a valid kernel whose
-        # cross-shard mixing costs 1/k of the NVLink traffic.
+        # global_every = k > 1 (matching "global" / "p2p"): only the steps whose index is a multiple of k use the
+        # whole-ensemble matching, the others pair inside each shard
         self.global_every = max(1, int(global_every))
-        self._step_index = 0
         dev = torch.cuda.current_device() if device is None else device
         self.device = torch.device("cuda", dev)
-        # shard-local matchings are independent ensembles: give each shard its own stream key
-        local = self.mode == "walkers" and matching == "local"
-        self.sampler = Sampler(flogprob, self.n_local, dim, seed=seed + (self.rank if local else 0), device=dev)
-        if not local:
-            self.sampler.set_shard(self.w_off, self.rung_off, n_walkers)
-        self.sampler.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.sampler = Sampler(flogprob, self.n_local, dim, seed=seed, device=dev)
+        self.sampler.set_shard(self.w_off, self.rung_off, n_walkers)
+        if self.mode == "walkers":
+            # a shard is matching block `rank` of the whole ensemble: its local steps take that block's stream keys
+            self.sampler.set_matching_blocks(1, self.rank, 0)
+        # every launch and every collective of this object goes to ONE stream, captured here
+        self._stream = torch.cuda.current_stream(self.device)
+        self.sampler.set_stream(self._stream.cuda_stream)
         self.ens, self.lp, self.pitch = device_views(self.sampler, self.device)
         self._ens_all = self._lp_all = self._src_all = None
         self._token = None
@@ -166,7 +168,6 @@ class ShardedSampler:
             handles = [None] * self.world
             dist.all_gather_object(handles, mine, group=group)
             self.sampler.ipc_attach(self.world, self.rank, [h[0] for h in handles], [h[1] for h in handles])
-            self._token = torch.zeros(1, device=self.device)
 
     # -- data
     def upload(self, ens_local: np.ndarray, lp_local: Optional[np.ndarray] = None):
@@ -193,26 +194,24 @@ class ShardedSampler:
         if self.matching == "local" or self.world == 1:
             self.sampler.sample_pt(a, ufs, beta, nsteps)
             return
-        done = 0
+        done, k = 0, self.global_every
         while done < nsteps:
-            k = self.global_every
-            if k > 1 and self._step_index % k != 0:                  # shard-local steps up to the next global one
-                run = min(nsteps - done, k - self._step_index % k)
+            index = self.sampler.counters[0]                         # the step counter drives the schedule
+            if index % k != 0:                                       # shard-local steps up to the next global one
+                run = min(nsteps - done, k - index % k)
                 self.sampler.sample_pt(a, ufs, beta, run)
-                self._step_index += run
                 done += run
                 continue
             if self.matching == "p2p":
-                self._barrier()                                      # peers have finished their previous step
-                self.sampler.sample_pt_p2p_begin(a, ufs, beta)       # pull remote partners' rows over NVLink
-                self._barrier()                                      # nobody writes before everybody has read
-                self.sampler.sample_pt_p2p_end()                     # fused step, in place
-            else:                                                    # all-gather + global-matching step
+                run = nsteps - done if k == 1 else 1                 # consecutive global steps: one library call
+                self.sampler.sample_pt_peer(a, ufs, beta, run)
+                done += run
+                continue
+            with self.torch.cuda.stream(self._stream):               # all-gather + global-matching step
                 ens_all, lp_all, _ = self._gather_buffers()
                 self.dist.all_gather_into_tensor(ens_all, self.ens, group=self.group)
                 self.dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
-                self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
-            self._step_index += 1
+            self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
             done += 1
 
     def twalk_sample(self, param, beta_list: Sequence[float], nsteps: int = 1):
@@ -241,8 +240,9 @@ class ShardedSampler:
         return self.sampler.hmc_sample_ensemble_pt(epsilon, beta, l, param, nsteps)
 
     def _barrier(self):
-        """Stream-ordered barrier across ranks (a one-element all-reduce: no host synchronisation)."""
-        self.dist.all_reduce(self._token, group=self.group)
+        """Stream-ordered barrier across ranks: flags in peer memory (scorus_peer_barrier), no NCCL call, no host
+        synchronisation."""
+        self.sampler.peer_barrier()
 
     def swap_walkers(self, beta_list: Sequence[float]):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
@@ -253,8 +253,9 @@ class ShardedSampler:
             # walker shards of a tempered ensemble whose rungs do not divide over the ranks
             raise NotImplementedError("swap_walkers across walker shards needs nbeta % world == 0")
         t, dist = self.torch, self.dist
-        _, lp_all, src_all = self._gather_buffers()
-        dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
+        with t.cuda.stream(self._stream):
+            _, lp_all, src_all = self._gather_buffers()
+            dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
         self.sampler.swap_plan_device(beta, lp_all.data_ptr(), src_all.data_ptr())
         if self.p2p:
             # one-sided: pull incoming rows from the peers' (still old) buffers, barrier, commit
@@ -262,20 +263,32 @@ class ShardedSampler:
             self._barrier()
             self.sampler.swap_apply_p2p(src_all.data_ptr(), lp_all.data_ptr(), 1)
             return   # a step only writes the rank's own rows: no barrier needed after the commit
-        local_dst, local_src, send_idx, recv_dst, send_counts, recv_counts = exchange_plan_torch(
-            src_all, self.n_local, self.world, self.rank)
-        send = self.ens.index_select(0, send_idx)                    # old rows, gathered before any write
-        local_rows = self.ens.index_select(0, local_src)
-        recv = t.empty((sum(recv_counts), self.pitch), dtype=t.float64, device=self.device)
-        dist.all_to_all_single(recv, send, recv_counts, send_counts, group=self.group)
-        if local_dst.numel():
-            self.ens.index_copy_(0, local_dst, local_rows)
-        if recv_dst.numel():
-            self.ens.index_copy_(0, recv_dst, recv)
-        self.lp.copy_(lp_all[self.w_off:self.w_off + self.n_local])
+        with t.cuda.stream(self._stream):
+            local_dst, local_src, send_idx, recv_dst, send_counts, recv_counts = exchange_plan_torch(
+                src_all, self.n_local, self.world, self.rank)
+            send = self.ens.index_select(0, send_idx)                # old rows, gathered before any write
+            local_rows = self.ens.index_select(0, local_src)
+            recv = t.empty((sum(recv_counts), self.pitch), dtype=t.float64, device=self.device)
+            dist.all_to_all_single(recv, send, recv_counts, send_counts, group=self.group)
+            if local_dst.numel():
+                self.ens.index_copy_(0, local_dst, local_rows)
+            if recv_dst.numel():
+                self.ens.index_copy_(0, recv_dst, recv)
+            self.lp.copy_(lp_all[self.w_off:self.w_off + self.n_local])
 
     def sync(self):
         self.sampler.sync()
+
+    def close(self):
+        """Releases the context; every rank waits until all are done with the buffers it exported."""
+        if self.sampler is None:
+            return
+        self.sampler.sync()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        self.ens = self.lp = self._ens_all = self._lp_all = self._src_all = None
+        self.sampler.close()
+        self.sampler = None
 
     def stats(self):
         return self.sampler.stats()

@@ -503,13 +503,26 @@ class Sampler:
         be, bl = b"".join(handles_ens), b"".join(handles_lp)
         self._ok(self._lib.scorus_ipc_attach(self._ctx, world, rank, be, bl))
 
-    def sample_pt_p2p_begin(self, a: float, ufs: UpdateFlagSpec, beta_list):
+    def sample_pt_peer(self, a: float, ufs: UpdateFlagSpec, beta_list, nsteps: int = 1):
+        """Whole-ensemble matching over walker shards, one-sided (scorus_sample_pt_peer): the owner of a pair reads the
+        partner's row from its home GPU over NVLink and writes both walkers' results back."""
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         u, keep = ufs._c(self.n, self.dim)
-        self._ok(self._lib.scorus_sample_pt_p2p_begin(self._ctx, a, C.byref(u), _dp(beta), beta.size))
+        self._ok(self._lib.scorus_sample_pt_peer(self._ctx, a, C.byref(u), _dp(beta), beta.size, nsteps))
 
-    def sample_pt_p2p_end(self):
-        self._ok(self._lib.scorus_sample_pt_p2p_end(self._ctx))
+    def peer_read_bandwidth(self, peer: int, nbytes: int = 0, iters: int = 5):
+        """(copy-engine GB/s, SM-load GB/s) of this GPU reading rank `peer`'s ensemble over NVLink (measurement only)."""
+        ce, sm = C.c_double(0.0), C.c_double(0.0)
+        self._ok(self._lib.scorus_peer_read_bandwidth(self._ctx, peer, nbytes, iters, C.byref(ce), C.byref(sm)))
+        return ce.value, sm.value
+
+    def peer_barrier(self):
+        self._ok(self._lib.scorus_peer_barrier(self._ctx))
+
+    def set_matching_blocks(self, nblocks: int = 1, block_offset: int = 0, global_every: int = 0):
+        """Blocked matchings (scorus_set_matching_blocks): `nblocks` separately matched blocks per rung, whole-rung
+        matching on the steps whose index is a multiple of `global_every` (0: never)."""
+        self._ok(self._lib.scorus_set_matching_blocks(self._ctx, nblocks, block_offset, global_every))
 
     def swap_apply_p2p(self, src_all_ptr: int, lp_all_ptr: int, phase: int):
         self._ok(self._lib.scorus_swap_apply_p2p(self._ctx, C.c_void_p(src_all_ptr), C.c_void_p(lp_all_ptr), phase))

@@ -94,3 +94,50 @@ def test_argument_checks(oracle):
     ens, lp = np.zeros((6, 2)), np.zeros(6)
     assert oracle.twalk_sample(0, [0.5], ens, lp, oracle.Rng(1), tw, [1.0, 0.5, 0.25, 0.125]) == oracle.ERR_NWALKERS_MISMATCHES_NBETA
     assert oracle.twalk_sample(0, [0.5], ens, lp, oracle.Rng(1), tw, [1.0, 0.5]) == oracle.ERR_NWALKERS_IS_NOT_EVEN
+
+
+def test_literal_index_reading_of_the_reference_parts_from_the_shipped_one_at_two_rungs(oracle):
+    """twalk.rs:605-612 builds every rung's pairs from rung-LOCAL indices; sample1 reads walkers and log-probs with
+    them unshifted (:686-690, :741-749) and writes shifted by ibeta * nwalkers_per_beta (:757-758).  The shipped
+    reading (oracle/twalk.c: orc_twalk_half_fixed, the device kernels) shifts both sides; the literal one
+    (orc_twalk_half_fixed_literal) follows the Rust as written.  This pins where they part:
+      * one rung: bit-identical -- parity with the reference as written holds there;
+      * two rungs, same draws: rung 0 evolves identically in both readings, rung 1 does not; under the literal
+        reading every row accepted into rung 1 is a proposal built from rung 0's walkers, and rung 1 never moves off
+        them: its own starting positions play no part."""
+    rng = np.random.default_rng(4)
+    dim = 6
+    tw = oracle.twalk_params(dim)
+    for nb in (1, 2):
+        npb = 64
+        n = nb * npb
+        beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+        ens0 = np.ascontiguousarray(rng.normal(size=(n, dim)))
+        if nb == 2:
+            ens0[npb:] += 50.0      # rung 1 starts far away from rung 0: the two readings cannot agree by accident
+        lp0 = oracle.init_logprob(0, [0.5], ens0)
+        g = oracle.Rng(11)
+        e_s, l_s, e_l, l_l = ens0.copy(), lp0.copy(), ens0.copy(), lp0.copy()
+        for step in range(6):
+            order, kernel, b, flags, wu, u = oracle.twalk_draw_streams(g, n, dim, nb, tw)
+            for half in (0, 1):
+                a = (order, half, kernel[half], b[half], flags[half], wu[half], u[half])
+                acc_s, prop_s, _ = oracle.twalk_half_fixed(0, [0.5], e_s, l_s, beta, tw, *a, want_proposals=True)
+                pre_l = e_l.copy()
+                acc_l, prop_l, _ = oracle.twalk_half_fixed(0, [0.5], e_l, l_l, beta, tw, *a, want_proposals=True,
+                                                           literal_index=True)
+                if nb == 2:
+                    # literal proposals of rung 1's pairs are functions of rung 0's rows only
+                    movers = order[half::2]
+                    r1 = movers >= npb
+                    src = pre_l[movers[r1] - npb]
+                    assert np.all(np.abs(prop_l[r1] - src).max(axis=1) < 40.0), "literal proposals come from rung 0"
+                    assert np.all(np.abs(prop_s[r1]).max(axis=1) > 40.0), "shipped proposals stay with rung 1's walkers"
+        if nb == 1:
+            assert np.array_equal(e_s, e_l) and np.array_equal(l_s, l_l)
+        else:
+            assert np.array_equal(e_s[:npb], e_l[:npb]) and np.array_equal(l_s[:npb], l_l[:npb])   # rung 0: the same chain
+            assert not np.array_equal(e_s[npb:], e_l[npb:])
+            moved = np.any(e_l[npb:] != ens0[npb:], axis=1)
+            assert moved.any() and np.all(np.abs(e_l[npb:][moved]).max(axis=1) < 40.0)    # accepted rows sit in rung 0's cloud
+            assert np.all(np.abs(e_s[npb:]).max(axis=1) > 40.0)                            # shipped: rung 1 stays its own chain
