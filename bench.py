@@ -232,7 +232,7 @@ def main():
                          "(twalk::sample, SURVEY 8(f) rank 2), hmc = ensemble-PT HMC (hmc::naive::sample_ensemble_pt, rank 3; "
                          "10 leapfrog steps, fixed step size) on the same workload: extra measurements")
     ap.add_argument("--n-walkers", type=int, default=0, help="experiments only: override the workload's ensemble size")
-    ap.add_argument("--global-every", type=int, default=4,
+    ap.add_argument("--global-every", type=int, default=8,
                     help="N>1, --matching p2p/global: the whole-ensemble matching on every k-th step, shard-local (blocked) "
                          "matching in between; 1 = the reference's matching on every step")
     ap.add_argument("--matching", default="p2p", choices=["local", "global", "p2p"],
@@ -367,6 +367,76 @@ def main():
             do_steps(nxt - k)
             k = nxt
 
+    # ---- walker shards: the pieces of the schedule on their own, and the NVLink denominators ----
+    extra = None
+    if world > 1 and s.mode == "walkers" and args.move == "stretch":
+        def timed(fn, k):
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(k); e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / k], device="cuda", dtype=torch.float64)
+            if os.environ.get("BENCH_DIAG"):
+                allt = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                diag.append([round(float(x.item()), 5) for x in allt])
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        diag = []
+        k_x = max(8, min(args.steps, 40))
+        t_local = timed(lambda k: s.sampler.sample_pt(2.0, spec, beta, k), k_x)
+        extra = {"replicas_upper_bound": {"ms_per_step": t_local, "value": n / (t_local * 1e-3),
+                                          "note": "shard-local matching on every step: no exchange at all"}}
+        if s.p2p:
+            t_glob = timed(lambda k: s.sampler.sample_pt_peer(2.0, spec, beta, k), k_x)
+            st_x = s.stats()
+            acc = st_x["accepted"] / max(1, st_x["proposed"])
+            cross = (n_local / 2) * (world - 1) / world                 # owned pairs whose partner lives on a peer
+            rd, wr = cross * (dim * 8 + 8), cross * acc * (dim * 8 + 8)
+            ce, sm, rr = s.sampler.peer_read_bandwidth((rank + 1) % world, 0, 5)
+            bw = torch.tensor([ce, sm, rr], device="cuda", dtype=torch.float64)
+            dist.all_reduce(bw, op=dist.ReduceOp.MIN)
+            ce, sm, rr = (float(v) for v in bw.tolist())
+            # what crosses NVLink INTO a GPU per step: the partner rows it reads, the accepted rows its peers write into
+            # it, and (not counted in the algorithmic figure) the request / acknowledge packets of the opposite streams
+            extra["exchange_every_step"] = {
+                "ms_per_step": t_glob, "value": n / (t_glob * 1e-3),
+                "nvlink_read_bytes_per_gpu_step": rd, "nvlink_write_bytes_per_gpu_step": wr,
+                "roofline": {"bound": "nvlink", "achieved": (rd + wr) / (t_glob * 1e-3) / 1e9, "peak": sm, "unit": "GB/s",
+                             "frac": (rd + wr) / (t_glob * 1e-3) / 1e9 / sm,
+                             "traffic": "inbound per GPU: remote partner rows read + accepted rows written by the peers",
+                             "peak_source": "scorus_peer_read_bandwidth: all ranks reading the next rank's ensemble at once, "
+                                            "SM 16-byte loads (min over ranks), measured in this run"},
+                "note": "the reference's whole-ensemble matching on every step (k = 1)"}
+            # NCCL's all-gather of the ensemble (what BASELINE.json's wording would do every step), for the record
+            buf = torch.empty((n, s.pitch), dtype=torch.float64, device="cuda")
+            def ag(k):
+                for _ in range(k):
+                    dist.all_gather_into_tensor(buf, s.ens)
+            ag(1)
+            t_ag = timed(ag, 3)
+            extra["nvlink"] = {"peer_read_copy_engine_gbps": ce, "peer_read_sm_loads_gbps": sm,
+                               "peer_read_scrambled_rows_gbps": rr,
+                               "nccl_allgather_ms": t_ag,
+                               "nccl_allgather_busbw_gbps": n_local * s.pitch * 8 * (world - 1) / (t_ag * 1e-3) / 1e9}
+            del buf
+            if os.environ.get("BENCH_DIAG"):
+                kk = max(2, args.global_every)
+                def cycle(c):
+                    for _ in range(c):
+                        s.sampler.sample_pt_peer(2.0, spec, beta, 1)
+                        s.sampler.sample_pt(2.0, spec, beta, kk - 1)
+                t_cyc = timed(cycle, 10)
+                extra["diag"] = {"per_rank_ms": diag, "order": ["local", "exchange", "allgather", "cycle"],
+                                 "cycle_ms_per_cycle": t_cyc, "cycle_steps": kk}
+
+    # burn-in, untimed and on top of the W warm-up steps: the timed region of a multi-GPU run is a few milliseconds, shorter
+    # than the clock ramp of a GPU that idled while the host built the ensemble (measured at 8 GPUs: the same 100 steps
+    # took 0.16-0.21 ms/step cold and 0.14 ms/step after a second of work)
+    t_burn = time.perf_counter()
+    while time.perf_counter() - t_burn < float(os.environ.get("BENCH_BURN_IN_S", "0.4")):
+        do_steps(8)
+        torch.cuda.synchronize()
     run_steps(0, W)
     torch.cuda.synchronize()
     if dist:
@@ -392,51 +462,6 @@ def main():
         ms = float(t.item())
     stats = s.stats()
     value = n * args.steps / (ms * 1e-3)
-
-    # ---- walker shards: the pieces of the schedule on their own, and the NVLink denominators ----
-    extra = None
-    if world > 1 and s.mode == "walkers" and args.move == "stretch":
-        def timed(fn, k):
-            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream); fn(k); e1.record(stream)
-            torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / k], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        k_x = max(8, min(args.steps, 40))
-        t_local = timed(lambda k: s.sampler.sample_pt(2.0, spec, beta, k), k_x)
-        extra = {"replicas_upper_bound": {"ms_per_step": t_local, "value": n / (t_local * 1e-3),
-                                          "note": "shard-local matching on every step: no exchange at all"}}
-        if s.p2p:
-            t_glob = timed(lambda k: s.sampler.sample_pt_peer(2.0, spec, beta, k), k_x)
-            acc = stats["accepted"] / max(1, stats["proposed"])
-            cross = (n_local / 2) * (world - 1) / world                 # owned pairs whose partner lives on a peer
-            rd, wr = cross * (dim * 8 + 8), cross * acc * (dim * 8 + 8)
-            ce, sm = s.sampler.peer_read_bandwidth((rank + 1) % world, 0, 5)
-            bw = torch.tensor([ce, sm], device="cuda", dtype=torch.float64)
-            dist.all_reduce(bw, op=dist.ReduceOp.MIN)
-            ce, sm = float(bw[0].item()), float(bw[1].item())
-            extra["exchange_every_step"] = {
-                "ms_per_step": t_glob, "value": n / (t_glob * 1e-3),
-                "nvlink_read_bytes_per_gpu_step": rd, "nvlink_write_bytes_per_gpu_step": wr,
-                "roofline": {"bound": "nvlink", "achieved": rd / (t_glob * 1e-3) / 1e9, "peak": sm, "unit": "GB/s",
-                             "frac": rd / (t_glob * 1e-3) / 1e9 / sm,
-                             "peak_source": "scorus_peer_read_bandwidth: all ranks reading the next rank's ensemble at once, "
-                                            "SM 16-byte loads (min over ranks), measured in this run"},
-                "note": "the reference's whole-ensemble matching on every step (k = 1)"}
-            # NCCL's all-gather of the ensemble (what BASELINE.json's wording would do every step), for the record
-            buf = torch.empty((n, s.pitch), dtype=torch.float64, device="cuda")
-            def ag(k):
-                for _ in range(k):
-                    dist.all_gather_into_tensor(buf, s.ens)
-            ag(1)
-            t_ag = timed(ag, 3)
-            extra["nvlink"] = {"peer_read_copy_engine_gbps": ce, "peer_read_sm_loads_gbps": sm,
-                               "nccl_allgather_ms": t_ag,
-                               "nccl_allgather_busbw_gbps": n_local * s.pitch * 8 * (world - 1) / (t_ag * 1e-3) / 1e9}
-            del buf
-        stats = s.stats()
 
     # ---- the ladder swap on its own (reported separately; amortised into `value` above) ----
     swap_stage = None
@@ -471,22 +496,21 @@ def main():
         h_ens = sb.pinned_empty((n_local, dim))
         h_lp = sb.pinned_empty((n_local,))
         shard_local = world > 1 and args.move == "stretch" and (s.mode == "rungs" or args.matching == "local")
-        if shard_local:
-            # no per-step exchange: every rank makes the reference-shaped call on its own shard (accepted rows only
-            # travel back, as on one GPU)
-            local_beta = beta[s.rung_off:s.rung_off + s.nb_local] if s.mode == "rungs" else beta
-
+        if world > 1 and args.move == "stretch":
+            # every rank makes the reference-shaped call on its own shard: upload, the step the schedule prescribes
+            # (shard-local, or one-sided whole-ensemble matching), write-back of the shard's accepted walkers
             def host_step():
-                s.sampler.sample_pt_host(h_ens, h_lp, 2.0, spec, local_beta)
+                s.sample_pt_host(h_ens, h_lp, 2.0, spec, beta)
             s.sampler.download(h_ens, h_lp)
-            api = "per rank: Sampler.sample_pt_host -> scorus_sample_pt_host on its shard (pinned host buffers, one step per call)"
+            api = ("per rank: ShardedSampler.sample_pt_host -> scorus_sample_pt_host / scorus_sample_pt_peer_host on its shard "
+                   "(pinned host buffers, one step per call)")
         elif world > 1:
-            def host_step():  # upload shard, one (possibly exchanging) step, download shard
+            def host_step():  # upload shard, one step, download shard
                 s.upload(h_ens, h_lp)
                 do_steps(1)
                 s.sampler.download(h_ens, h_lp)
             s.sampler.download(h_ens, h_lp)
-            api = "ShardedSampler.upload + sample_pt + download (pinned host buffers, one step per call)"
+            api = "ShardedSampler.upload + step + download (pinned host buffers, one step per call)"
         else:
             def host_step():
                 if args.move == "hmc":
@@ -517,7 +541,8 @@ def main():
         # whole job: every rank copies its own shard (rank 0's accept count stands for the others')
         bytes_dir = (n_local * dim * 8 + n_local * 8) * world
         # host call on pinned buffers: only accepted walkers are written back (scatter download)
-        scatter = (world == 1 or shard_local) and os.environ.get("SCORUS_SCATTER_DOWNLOAD", "1") != "0"
+        scatter = (world == 1 or shard_local or (args.move == "stretch" and args.matching != "global")) \
+            and os.environ.get("SCORUS_SCATTER_DOWNLOAD", "1") != "0"
         d2h = int(acc_per_step * world * (dim * 8 + 8)) if scatter else bytes_dir
         e2e = {"value": n * args.e2e_steps / dt, "unit": "walker-steps/s", "h2d_bytes_per_step": bytes_dir,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,

@@ -311,14 +311,19 @@ int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_
  * identical to the single-GPU steps (streams are keyed by global walker ids). */
 int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta,
                           uint64_t nsteps);
+/* scorus_sample_pt_peer on caller-owned host buffers of this rank's shard (the reference-shaped call, collective over
+ * the ranks): upload, nsteps one-sided steps, write-back of the shard's accepted walkers (pinned buffers: only those). */
+int scorus_sample_pt_peer_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len, double a,
+                               const scorus_ufs *ufs, const double *beta_list, size_t nbeta, uint64_t nsteps);
 /* The barrier on its own (stream-ordered; every attached rank must call it the same number of times). */
 int scorus_peer_barrier(scorus_ctx *ctx);
 
 /* Measurement only (the roofline denominator of the one-sided step): read bandwidth of this GPU from rank `peer`'s
- * mapped ensemble over NVLink, by a copy-engine memcpy and by an SM kernel of 16-byte streaming loads; GB/s.
+ * mapped ensemble over NVLink, by a copy-engine memcpy, by an SM kernel of 16-byte streaming loads, and by the same
+ * loads on whole rows in a scrambled order (the step kernel's access pattern; may be NULL); GB/s.
  * bytes == 0: the whole buffer. */
 int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t bytes, int iters, double *gbps_copy_engine,
-                               double *gbps_sm_loads);
+                               double *gbps_sm_loads, double *gbps_random_rows);
 
 /* Blocked matchings.  The reference pairs walkers over the whole rung (src/mcmc/ensemble_sample.rs:135-148).  With
  * nblocks > 1 a "local" step cuts every rung into nblocks contiguous blocks that pair among themselves -- what the
@@ -335,6 +340,11 @@ int scorus_set_matching_blocks(scorus_ctx *ctx, uint32_t nblocks, uint32_t block
  * phase 0 pulls every incoming row into scratch, the caller barriers across ranks, phase 1 commits
  * rows and log-probs.  Equal shards (n_global = world * n_local). */
 int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, const double *lp_all, int phase);
+
+/* swap_walkers (src/mcmc/utils.rs:72-112) over rung shards in one call: barrier, the whole ladder decided on every rank
+ * from log-probs read one-sidedly out of the peers' memory, incoming rows pulled over NVLink, barrier, commit.  No
+ * NCCL, no host synchronisation; every rank calls it with the GLOBAL beta list.  Identical to the single-GPU swap. */
+int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta_list, size_t nbeta);
 
 /* ---- plumbing (no reference counterpart: the reference call returns when the step is done; these calls are
  * asynchronous on the context's stream unless they return host data) ---- */

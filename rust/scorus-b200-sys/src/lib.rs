@@ -132,9 +132,13 @@ extern "C" {
                              handles_lp: *const c_void) -> c_int;
     pub fn scorus_sample_pt_peer(ctx: *mut scorus_ctx, a: f64, ufs: *const scorus_ufs, beta_list: *const f64,
                                  nbeta: usize, nsteps: u64) -> c_int;
+    pub fn scorus_sample_pt_peer_host(ctx: *mut scorus_ctx, ensemble: *mut f64, logprob: *mut f64, logprob_len: usize,
+                                      a: f64, ufs: *const scorus_ufs, beta_list: *const f64, nbeta: usize,
+                                      nsteps: u64) -> c_int;
     pub fn scorus_peer_barrier(ctx: *mut scorus_ctx) -> c_int;
+    pub fn scorus_swap_walkers_peer(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize) -> c_int;
     pub fn scorus_peer_read_bandwidth(ctx: *mut scorus_ctx, peer: c_int, bytes: usize, iters: c_int,
-                                      gbps_copy_engine: *mut f64, gbps_sm_loads: *mut f64) -> c_int;
+                                      gbps_copy_engine: *mut f64, gbps_sm_loads: *mut f64, gbps_random_rows: *mut f64) -> c_int;
     pub fn scorus_set_matching_blocks(ctx: *mut scorus_ctx, nblocks: u32, block_offset: u32, global_every: u64) -> c_int;
     pub fn scorus_swap_apply_p2p(ctx: *mut scorus_ctx, src_all: *const u32, lp_all: *const f64, phase: c_int) -> c_int;
     pub fn scorus_sync(ctx: *mut scorus_ctx) -> c_int;

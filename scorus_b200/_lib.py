@@ -106,8 +106,10 @@ def load() -> C.CDLL:
         "scorus_ipc_export": (ci, [vp, vp, vp]),
         "scorus_ipc_attach": (ci, [vp, ci, ci, vp, vp]),
         "scorus_sample_pt_peer": (ci, [vp, dbl, C.POINTER(Ufs), dp, sz, u64]),
+        "scorus_sample_pt_peer_host": (ci, [vp, dp, dp, sz, dbl, C.POINTER(Ufs), dp, sz, u64]),
         "scorus_peer_barrier": (ci, [vp]),
-        "scorus_peer_read_bandwidth": (ci, [vp, ci, sz, ci, dp, dp]),
+        "scorus_swap_walkers_peer": (ci, [vp, dp, sz]),
+        "scorus_peer_read_bandwidth": (ci, [vp, ci, sz, ci, dp, dp, dp]),
         "scorus_set_matching_blocks": (ci, [vp, C.c_uint32, C.c_uint32, u64]),
         "scorus_swap_apply_p2p": (ci, [vp, vp, vp, ci]),
         "scorus_sync": (ci, [vp]),
@@ -141,7 +143,7 @@ EXPORTS = [
     "scorus_twalk_sample", "scorus_twalk_half_fixed", "scorus_twalk_sample_host", "scorus_twalk_draw_b", "scorus_hmc_sample_ensemble_pt",
     "scorus_hmc_sample_ensemble_pt_fixed", "scorus_hmc_sample_ensemble_pt_host", "scorus_hmc_draw_momenta", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
-    "scorus_sample_pt_peer", "scorus_peer_barrier", "scorus_peer_read_bandwidth", "scorus_set_matching_blocks", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
+    "scorus_sample_pt_peer", "scorus_sample_pt_peer_host", "scorus_peer_barrier", "scorus_swap_walkers_peer", "scorus_peer_read_bandwidth", "scorus_set_matching_blocks", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",
     "scorus_get_stats", "scorus_launch_count", "scorus_host_alloc", "scorus_host_free",
 ]

@@ -112,8 +112,12 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     if ((e = cudaMalloc(&ctx->d_ens, ens_bytes)) != cudaSuccess) return bail(e, "cudaMalloc ensemble");
     // 32 extra slots behind the log-probs: the flag row of the inter-rank barrier (api_shard.cu), reachable by the peers
     // through the same IPC mapping as the log-probs
-    if ((e = cudaMalloc(&ctx->d_lp, (ctx->n + 32) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logprob");
+    // ... and one byte per walker behind those: "accepted since the upload" marks of the host-buffer calls, in the same
+    // allocation so that the owner of a pair on another GPU can mark its partner there (one-sided mode)
+    if ((e = cudaMalloc(&ctx->d_lp, (ctx->n + 32) * sizeof(double) + ((ctx->n + 15) & ~(uint64_t)15))) != cudaSuccess)
+        return bail(e, "cudaMalloc logprob");
     cudaMemsetAsync(ctx->d_lp + ctx->n, 0, 32 * sizeof(double), ctx->stream);
+    ctx->d_dirty = reinterpret_cast<uint8_t *>(ctx->d_lp + ctx->n + 32);
     if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc stats");
     if ((e = cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tile counter");
     cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned long long), ctx->stream);
@@ -130,7 +134,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_dirty, ctx->d_tile_counter};
+                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (auto &e : ctx->beta_cache)
@@ -591,10 +595,24 @@ void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv
         ctx->seed, ctx->swap_call, (uint32_t)npb, (uint32_t)nbeta, jinv);
     ++ctx->launches;
 }
-void launch_swap_chain(scorus_ctx *ctx, const SwapParams &sp)
+int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp)
 {
-    swap_chain_kernel<<<(unsigned)((sp.npb + 127) / 128), 128, 0, ctx->stream>>>(sp);
-    ++ctx->launches;
+    // the uniforms and their logarithms for every (stage, cold slot), then the chain sweep (swap_kernel.cuh)
+    const size_t m = (size_t)(sp.nbeta - 1) * sp.npb;
+    int rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * 2 * sizeof(double));
+    if (rc) return rc;
+    sp.chain_r = reinterpret_cast<double *>(ctx->d_chain);
+    sp.chain_lr = sp.chain_r + m;
+    const unsigned ublocks = (unsigned)std::min<size_t>((m + 255) / 256, (size_t)ctx->num_sms * 16u);
+    swap_uniforms_kernel<<<ublocks, 256, 0, ctx->stream>>>(sp);
+    const unsigned T = 128;
+    const size_t smem = (size_t)kSwapChunk * T * (2 * sizeof(double) + sizeof(uint32_t)) +
+                        (sp.jinv ? 0 : (size_t)(sp.nbeta - 1) * 8 * sizeof(uint32_t));
+    cudaError_t e = cudaFuncSetAttribute(swap_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernel's key table: %s", cudaGetErrorString(e));
+    swap_chain_kernel<<<(unsigned)((sp.npb + T - 1) / T), T, smem, ctx->stream>>>(sp);
+    ctx->launches += 2;
+    return SCORUS_OK;
 }
 }  // namespace host
 }  // namespace scorus
@@ -833,7 +851,7 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
     memset(&sp, 0, sizeof(sp));
     if (!ctx->d_src) CU(cudaMalloc(&ctx->d_src, n * sizeof(uint32_t)));
     if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, n * (size_t)ctx->pitch * sizeof(double)));
-    sp.lp = ctx->d_lp; sp.beta = ctx->d_beta; sp.src = ctx->d_src; sp.stats = ctx->d_stats;
+    sp.lp = ctx->d_lp; sp.lp_src = ctx->d_lp; sp.beta = ctx->d_beta; sp.src = ctx->d_src; sp.stats = ctx->d_stats;
     if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
     sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
     sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
@@ -865,17 +883,27 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
         if ((rc = ensure(ctx, (void **)&ctx->d_swapped, &ctx->swapped_cap, m))) return rc;
         sp.swapped_out = ctx->d_swapped;
     }
-    launch_swap_chain(ctx, sp);
+    if ((rc = launch_swap_chain(ctx, sp))) return rc;
     const uint32_t vpr = ctx->pitch / 2;
     const size_t total = n * (size_t)vpr;
     unsigned blocks = (unsigned)((total + 255) / 256);
     unsigned cap = (unsigned)ctx->num_sms * 16u;
     if (blocks > cap) blocks = cap;
-    permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
-                                                         (uint32_t)n, vpr, 0);
-    permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
-                                                         (uint32_t)n, vpr, 1);
-    ctx->launches += 2;
+    if (!ctx->d_peer_ens && env_int("SCORUS_SWAP_FLIP", 1)) {
+        // one pass: every row goes to its new slot in the second buffer, which then becomes the ensemble (the first
+        // version gathered the moved rows into scratch and copied them back: two passes -- at c4, where 87 % of the
+        // exchanges are accepted, nearly every row twice).  Buffers mapped by peers (scorus_ipc_attach) stay put.
+        gather_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
+                                                            (uint32_t)n, vpr);
+        std::swap(ctx->d_ens, ctx->d_scratch);
+        ++ctx->launches;
+    } else {
+        permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
+                                                             (uint32_t)n, vpr, 0);
+        permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
+                                                             (uint32_t)n, vpr, 1);
+        ctx->launches += 2;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap launch: %s", cudaGetErrorString(e));
     ++ctx->swap_call;

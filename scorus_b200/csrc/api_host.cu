@@ -9,7 +9,7 @@
 template <class Run>
 static int host_call(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, size_t nbeta, Run run)
 {
-    int rc = scorus_check_sample_args(ctx->n, lp_len, nbeta);
+    int rc = nbeta ? scorus_check_sample_args(ctx->n, lp_len, nbeta) : SCORUS_OK;  // nbeta == 0: checked by the callee
     if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
     if ((rc = scorus_upload(ctx, ens, lp))) return rc;
     // Pinned (device-mapped) host buffers: after the steps only the accepted walkers differ from what
@@ -24,7 +24,6 @@ static int host_call(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, si
         if ((rc = run())) return rc;
         return scorus_download(ctx, ens, lp);
     }
-    if (!ctx->d_dirty) CU(cudaMalloc(&ctx->d_dirty, ctx->n));
     CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, ctx->stream));
     ctx->track_dirty = true;
     rc = run();
@@ -39,6 +38,19 @@ extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp,
 {
     if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
     return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps); });
+}
+
+// the same call for a walker shard of an ensemble spread over several GPUs, whole-ensemble matching, one-sided
+// (scorus_sample_pt_peer): every rank calls it at the same time with its own shard's host buffers.  The owner of a
+// pair marks an accepted partner on the partner's home GPU, so each rank still writes back only the walkers of ITS
+// shard that were accepted, whoever computed them.
+extern "C" int scorus_sample_pt_peer_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
+                                          const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
+{
+    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    if (lp_len != ctx->n) return fail(ctx, SCORUS_ERR_LENGTH_MISMATCH, "ensemble and logprob lengths differ");
+    // the rung arithmetic belongs to the whole ensemble (checked by scorus_sample_pt_peer): only the lengths here
+    return host_call(ctx, ens, lp, lp_len, 0, [&] { return scorus_sample_pt_peer(ctx, a, ufs, beta, nbeta, nsteps); });
 }
 
 // twalk::sample on host buffers (the `ensemble_logprob: &mut (W, X)` argument, twalk.rs:588)

@@ -149,7 +149,7 @@ static int global_matching_setup(scorus_ctx *ctx, double a, const scorus_ufs *uf
     p.w_lo = (uint32_t)ctx->w_off; p.w_hi = (uint32_t)(ctx->w_off + ctx->n);
     p.step = ctx->step; p.onehot = ctx->onehot;
     p.order = nullptr;
-    p.dirty = nullptr;
+    if (mode != PAIRS_OWNER) p.dirty = nullptr;  // one-sided mode: the marks live behind every rank's log-probs
     if ((rc = ensure(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * ctx->n * sizeof(uint32_t)))) return rc;
     if (!ctx->d_count) CU(cudaMalloc(&ctx->d_count, sizeof(uint32_t) + 2 * sizeof(unsigned long long)));
     unsigned long long *tile_counter = reinterpret_cast<unsigned long long *>(ctx->d_count) + 1;
@@ -216,7 +216,7 @@ extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size
     if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
     SwapParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.lp = lp_all; sp.beta = ctx->d_beta; sp.src = src_all; sp.stats = ctx->d_stats;
+    sp.lp = lp_all; sp.lp_src = lp_all; sp.beta = ctx->d_beta; sp.src = src_all; sp.stats = ctx->d_stats;
     if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
     sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
     sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
@@ -227,7 +227,7 @@ extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size
         launch_exact_jvec(ctx, nbeta, npb, ctx->d_jinv);
         sp.jinv = ctx->d_jinv;
     }
-    launch_swap_chain(ctx, sp);
+    if ((rc = launch_swap_chain(ctx, sp))) return rc;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap plan launch: %s", cudaGetErrorString(e));
     ++ctx->swap_call;
@@ -290,8 +290,28 @@ __global__ void __launch_bounds__(512) peer_read_kernel(const double2 *src, size
     if (acc == 1.2345e300) *sink = acc;  // keeps the loads alive
 }
 
+// the step kernel's pattern: whole rows (one warp-wide 16-byte-per-lane load per 512 bytes) at pseudo-random row indices
+__global__ void __launch_bounds__(512) peer_read_rows_kernel(const double2 *src, uint32_t nrows, uint32_t vec_per_row, double *sink)
+{
+    double acc = 0.0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t b = bij_bits(nrows);
+    BijKeys K;
+    for (int q = 0; q < 8; ++q) K.k[q] = 0x9E3779B9u * (uint32_t)(q + 1) + 12345u;
+    for (uint32_t i = warp; i + 3 * nwarps < nrows; i += 4 * nwarps) {  // four rows in flight per warp
+        const double2 *r0 = src + (size_t)bij(i, nrows, b, K) * vec_per_row, *r1 = src + (size_t)bij(i + nwarps, nrows, b, K) * vec_per_row,
+                      *r2 = src + (size_t)bij(i + 2 * nwarps, nrows, b, K) * vec_per_row, *r3 = src + (size_t)bij(i + 3 * nwarps, nrows, b, K) * vec_per_row;
+        for (uint32_t c = lane; c < vec_per_row; c += 32) {
+            const double2 a = ld_stream(r0 + c), e = ld_stream(r1 + c), f = ld_stream(r2 + c), g = ld_stream(r3 + c);
+            acc += a.x + a.y + e.x + e.y + f.x + f.y + g.x + g.y;
+        }
+    }
+    if (acc == 1.2345e300) *sink = acc;
+}
+
 extern "C" int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t bytes, int iters, double *gbps_copy_engine,
-                                          double *gbps_sm_loads)
+                                          double *gbps_sm_loads, double *gbps_random_rows)
 {
     if (!ctx || iters < 1) return SCORUS_ERR_INVALID_ARG;
     if (!ctx->d_peer_ens || peer < 0 || peer >= ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
@@ -322,6 +342,18 @@ extern "C" int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t byte
     CU(cudaEventElapsedTime(&ms, e0, e1));
     if (gbps_sm_loads) *gbps_sm_loads = (double)bytes * iters / (ms * 1e-3) / 1e9;
     ctx->launches += (uint64_t)iters + 1;
+    if (gbps_random_rows) {  // the rows of the peer's ensemble in a scrambled order, each read once per pass
+        const uint32_t vpr = ctx->pitch / 2, nrows = (uint32_t)((bytes / 16) / vpr) & ~3u;
+        peer_read_rows_kernel<<<grid, 512, 0, ctx->stream>>>((const double2 *)ctx->peer_ens[peer], nrows, vpr, ctx->d_scratch);
+        CU(cudaEventRecord(e0, ctx->stream));
+        for (int k = 0; k < iters; ++k)
+            peer_read_rows_kernel<<<grid, 512, 0, ctx->stream>>>((const double2 *)ctx->peer_ens[peer], nrows, vpr, ctx->d_scratch);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        *gbps_random_rows = (double)nrows * vpr * 16.0 * iters / (ms * 1e-3) / 1e9;
+        ctx->launches += (uint64_t)iters + 1;
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return SCORUS_OK;
@@ -358,7 +390,6 @@ extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs
     if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     if (ctx->n_global != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");
     if (ctx->n > (1u << 28)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "at most 2^28 walkers per shard");
-    if (ctx->track_dirty) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-buffer calls are per shard");
     for (uint64_t s = 0; s < nsteps; ++s) {
         StepParams p;
         Geometry g;
@@ -368,6 +399,25 @@ extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs
         for (int q = 0; q < 16; ++q) { p.peer_ens[q] = ctx->peer_ens[q]; p.peer_lp[q] = ctx->peer_lp[q]; }
         p.peer_n = (uint32_t)ctx->n;
         p.accepted_out = nullptr;
+        // partner rows a tile ahead through a shared-memory stage (step_reg_kernel.cuh, kPeer == 2) where the kernel
+        // keeps its proposals in registers: 16 rows + 8 mbarriers per warp on top of the flag words
+        {
+            const uint32_t nvec = ctx->pitch / 2;
+            const bool direct = ctx->lp_kind != SCORUS_LP_CORR_GAUSSIAN && !(nvec > 8 && nvec <= 16);
+            if (direct && env_int("SCORUS_PEER_STAGE", 1)) {
+                const size_t base = g.smem / g.warps, extra = 16u * (size_t)g.row_stride + 128u;
+                uint32_t w = g.warps;
+                while (w > 1 && w * (base + extra) > (size_t)ctx->smem_optin) --w;
+                if (w * (base + extra) <= (size_t)ctx->smem_optin) {
+                    g.warps = w;
+                    g.smem = w * (base + extra);
+                    p.warps = w;
+                    p.peer_stage = 1;
+                    const uint32_t ntl = (uint32_t)((ctx->n + 31u) / 32u);
+                    g.grid = std::min<uint32_t>((uint32_t)ctx->num_sms, (ntl + w - 1) / w);
+                }
+            }
+        }
         cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
         ++ctx->launches;
@@ -382,21 +432,20 @@ extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs
     return nsteps ? scorus_peer_barrier(ctx) : SCORUS_OK;
 }
 
-// rows of a cross-rank ladder swap, pulled one-sidedly: scratch[slot] <- (peer holding src)[src] for
-// every local slot whose walker changes.  One warp per slot.
+// rows of a cross-rank ladder swap, pulled one-sidedly: scratch[slot] <- (peer holding src)[src] for every local slot
+// whose walker changes.  One thread per 16-byte chunk of a row (a warp per row left 27 of 32 lanes idle at 10-D and
+// queued the rows of a warp behind one another's NVLink latency).
 __global__ void __launch_bounds__(256) swap_pull_rows_kernel(const uint32_t *src_all, uint32_t w_lo, uint32_t n_local,
                                                              uint32_t pitch, double *const *peer_ens, double *scratch)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nvec = pitch >> 1;
-    for (uint32_t i = warp; i < n_local; i += nwarps) {
+    const size_t total = (size_t)n_local * nvec;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(g / nvec), c = (uint32_t)(g - (size_t)i * nvec);
         const uint32_t s = __ldg(src_all + w_lo + i);
         if (s == w_lo + i) continue;
         const uint32_t q = s / n_local, r = s - q * n_local;
-        const double2 *src = reinterpret_cast<const double2 *>(peer_ens[q] + (size_t)r * pitch);
-        double2 *dst = reinterpret_cast<double2 *>(scratch + (size_t)i * pitch);
-        for (uint32_t c = lane; c < nvec; c += 32) dst[c] = src[c];
+        reinterpret_cast<double2 *>(scratch)[g] = ld_stream(reinterpret_cast<const double2 *>(peer_ens[q] + (size_t)r * pitch) + c);
     }
 }
 
@@ -404,15 +453,13 @@ __global__ void __launch_bounds__(256) swap_commit_rows_kernel(const uint32_t *s
                                                                uint32_t n_local, uint32_t pitch, const double *scratch,
                                                                double *ens, double *lp)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nvec = pitch >> 1;
-    for (uint32_t i = warp; i < n_local; i += nwarps) {
-        if (lane == 0) lp[i] = __ldg(lp_all + w_lo + i);
+    const size_t total = (size_t)n_local * nvec;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(g / nvec), c = (uint32_t)(g - (size_t)i * nvec);
+        if (c == 0) lp[i] = __ldg(lp_all + w_lo + i);
         if (__ldg(src_all + w_lo + i) == w_lo + i) continue;
-        const double2 *src = reinterpret_cast<const double2 *>(scratch + (size_t)i * pitch);
-        double2 *dst = reinterpret_cast<double2 *>(ens + (size_t)i * pitch);
-        for (uint32_t c = lane; c < nvec; c += 32) dst[c] = src[c];
+        reinterpret_cast<double2 *>(ens)[g] = reinterpret_cast<const double2 *>(scratch)[g];
     }
 }
 
@@ -425,7 +472,8 @@ extern "C" int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, c
     if (!ctx->d_peer_ens) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     cudaSetDevice(ctx->device);
     if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, ctx->n * (size_t)ctx->pitch * sizeof(double)));
-    const unsigned blocks = (unsigned)ctx->num_sms * 8u;
+    const size_t chunks = ctx->n * (size_t)(ctx->pitch / 2);
+    const unsigned blocks = (unsigned)std::min<size_t>((chunks + 255) / 256, (size_t)ctx->num_sms * 16u);
     if (phase == 0)
         swap_pull_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(src_all, (uint32_t)ctx->w_off, (uint32_t)ctx->n, ctx->pitch,
                                                               ctx->d_peer_ens, ctx->d_scratch);
@@ -436,4 +484,64 @@ extern "C" int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap apply launch: %s", cudaGetErrorString(e));
     return SCORUS_OK;
+}
+
+// every rank's log-probs into one local array: coalesced one-sided reads of the peers' mappings (8 bytes per walker)
+__global__ void __launch_bounds__(256) gather_lp_kernel(const PeerTable t, uint32_t n_local, uint32_t n_global, double *lp_all)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_global; i += gridDim.x * blockDim.x) {
+        const uint32_t q = i / n_local;
+        double v;  // another GPU wrote it: not through the non-coherent path
+        asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(t.lp[q] + (i - q * n_local)));
+        lp_all[i] = v;
+    }
+}
+
+// swap_walkers (src/mcmc/utils.rs:72-112) of a ladder whose rungs are spread over the attached ranks, in ONE call and
+// without NCCL: barrier (every rank's log-probs are final); every rank gathers all log-probs with coalesced one-sided
+// reads (a scattered 8-byte NVLink read per chain stage inside the latency-bound chain kernel cost 0.8 ms at 8 GPUs)
+// and decides the whole ladder; pulls the rows that move into its slots from wherever they live; barrier (nobody
+// overwrites a row a peer still has to read); commit.  Identical to the single-GPU swap.
+extern "C" int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta, size_t nbeta)
+{
+    if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
+    const size_t n = ctx->n_global;
+    if (n != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");
+    if (nbeta == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "nbeta == 0");
+    const size_t npb = n / nbeta;
+    if (npb * nbeta != n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
+    int rc = scorus_check_beta_order(beta, nbeta);
+    if (rc) return fail(ctx, rc, "beta list must be in decreasing order");
+    if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
+    cudaSetDevice(ctx->device);
+    if (nbeta == 1) { ++ctx->swap_call; return SCORUS_OK; }
+    if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_lp_all, &ctx->lp_all_cap, n * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_src_all, &ctx->src_all_cap, n * sizeof(uint32_t)))) return rc;
+    if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, ctx->n * (size_t)ctx->pitch * sizeof(double)));
+    if ((rc = scorus_peer_barrier(ctx))) return rc;
+    SwapParams sp;
+    memset(&sp, 0, sizeof(sp));
+    PeerTable t;
+    for (int q = 0; q < 16; ++q) t.lp[q] = ctx->peer_lp[q];
+    gather_lp_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(t, (uint32_t)ctx->n, (uint32_t)n, ctx->d_lp_all);
+    ++ctx->launches;
+    sp.lp = ctx->d_lp_all; sp.lp_src = ctx->d_lp_all; sp.beta = ctx->d_beta; sp.src = ctx->d_src_all; sp.stats = ctx->d_stats;
+    if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
+    sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
+    sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
+    sp.npb = (uint32_t)npb; sp.nbeta = (uint32_t)nbeta; sp.bij_bits = bij_bits((uint32_t)npb);
+    if (npb <= kExactShuffleMax) {
+        const size_t m = (nbeta - 1) * npb;
+        if ((rc = ensure(ctx, (void **)&ctx->d_jinv, &ctx->jinv_cap, m * sizeof(uint32_t)))) return rc;
+        launch_exact_jvec(ctx, nbeta, npb, ctx->d_jinv);
+        sp.jinv = ctx->d_jinv;
+    }
+    if ((rc = launch_swap_chain(ctx, sp))) return rc;
+    ++ctx->swap_call;
+    count_swap_proposed(ctx, nbeta, npb);
+    if ((rc = scorus_swap_apply_p2p(ctx, ctx->d_src_all, ctx->d_lp_all, 0))) return rc;
+    if ((rc = scorus_peer_barrier(ctx))) return rc;
+    return scorus_swap_apply_p2p(ctx, ctx->d_src_all, ctx->d_lp_all, 1);
 }

@@ -80,6 +80,9 @@ struct scorus_ctx {
     uint32_t *d_jinv = nullptr; size_t jinv_cap = 0;
     double *d_r = nullptr;      size_t r_cap = 0;
     uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
+    double *d_lp_all = nullptr; size_t lp_all_cap = 0;          // sharded ladder swap: the plan for all slots
+    uint32_t *d_src_all = nullptr; size_t src_all_cap = 0;
+    void *d_chain = nullptr; size_t chain_cap = 0;              // scratch rows of the two-pass swap chain kernel
     int8_t *d_hmc_adapt = nullptr;                              // HMC: step-size adaptation codes, one per walker
     double *d_hmc_eps = nullptr; size_t hmc_eps_cap = 0;        // ... step size per rung
     double *d_hmc_p = nullptr; size_t hmc_p_cap = 0;            // ... caller-supplied momenta
@@ -137,7 +140,7 @@ int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool 
 // kernels of swap_kernel.cuh, launched from more than one translation unit
 void launch_exact_order(scorus_ctx *ctx, uint64_t step, size_t nbeta, uint32_t npb, uint32_t *order, uint32_t w_off);
 void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv);
-void launch_swap_chain(scorus_ctx *ctx, const SwapParams &sp);
+int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp);
 // api_stats.cu
 int after_step(scorus_ctx *ctx);  // chain capture and running moments, after every step
 int launch_scatter_download(scorus_ctx *ctx, double *host_ens, double *host_lp);

@@ -46,6 +46,20 @@ static int coop_group(uint32_t pitch)
     return (int)g;
 }
 
+// the register kernel in its three flavours: single GPU / gathered copies (0), one-sided with both rows through
+// registers (1), one-sided with the partner rows staged by TMA (2: direct mode, when the host laid out the stage)
+template <class Plugin, int G, int ITERS>
+static cudaError_t launch_reg(const StepParams &p, const Geometry &g, cudaStream_t st)
+{
+    if (p.peer_n) {
+        if constexpr (reg_kernel_direct<Plugin, G>()) {
+            if (p.peer_stage) return launch_kernel(step_reg_kernel<Plugin, G, ITERS, 2>, p, g, st);
+        }
+        return launch_kernel(step_reg_kernel<Plugin, G, ITERS, 1>, p, g, st);
+    }
+    return launch_kernel(step_reg_kernel<Plugin, G, ITERS, 0>, p, g, st);
+}
+
 cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const Geometry &g, bool all_flags,
                                                     cudaStream_t st)
 {
@@ -58,28 +72,15 @@ cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const G
     if (g.kernel == KERNEL_REG) {
         // rows of 5 or 6 double2 (D = 9..12): two lanes x three chunks wastes 1/6 of the lanes, eight lanes
         // x one chunk would waste 3/8 -- and these targets (10-D Rastrigin) are bound by fp64 arithmetic
-        if (nvec == 5 || nvec == 6)
-            return p.peer_n ? launch_kernel(step_reg_kernel<Plugin, 2, 3, true>, p, g, st)
-                               : launch_kernel(step_reg_kernel<Plugin, 2, 3>, p, g, st);
-        if (p.peer_n) {  // one-sided multi-GPU mode: rows read from / written to their home ranks
-            if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4, true>, p, g, st);
-            if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2, true>, p, g, st);
-            switch (coop_group(p.pitch)) {
-            case 2: return launch_kernel(step_reg_kernel<Plugin, 2, 1, true>, p, g, st);
-            case 4: return launch_kernel(step_reg_kernel<Plugin, 4, 1, true>, p, g, st);
-            case 8: return launch_kernel(step_reg_kernel<Plugin, 8, 1, true>, p, g, st);
-            case 16: return launch_kernel(step_reg_kernel<Plugin, 16, 1, true>, p, g, st);
-            default: return launch_kernel(step_reg_kernel<Plugin, 32, 1, true>, p, g, st);
-            }
-        }
-        if (nvec > 64) return launch_kernel(step_reg_kernel<Plugin, 32, 4>, p, g, st);
-        if (nvec > 32) return launch_kernel(step_reg_kernel<Plugin, 32, 2>, p, g, st);
+        if (nvec == 5 || nvec == 6) return launch_reg<Plugin, 2, 3>(p, g, st);
+        if (nvec > 64) return launch_reg<Plugin, 32, 4>(p, g, st);
+        if (nvec > 32) return launch_reg<Plugin, 32, 2>(p, g, st);
         switch (coop_group(p.pitch)) {
-        case 2: return launch_kernel(step_reg_kernel<Plugin, 2, 1>, p, g, st);
-        case 4: return launch_kernel(step_reg_kernel<Plugin, 4, 1>, p, g, st);
-        case 8: return launch_kernel(step_reg_kernel<Plugin, 8, 1>, p, g, st);
-        case 16: return launch_kernel(step_reg_kernel<Plugin, 16, 1>, p, g, st);
-        default: return launch_kernel(step_reg_kernel<Plugin, 32, 1>, p, g, st);
+        case 2: return launch_reg<Plugin, 2, 1>(p, g, st);
+        case 4: return launch_reg<Plugin, 4, 1>(p, g, st);
+        case 8: return launch_reg<Plugin, 8, 1>(p, g, st);
+        case 16: return launch_reg<Plugin, 16, 1>(p, g, st);
+        default: return launch_reg<Plugin, 32, 1>(p, g, st);
         }
     }
     // cooperative kernel with the old rows staged by TMA: any dimension that fits a tile

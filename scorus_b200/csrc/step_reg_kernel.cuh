@@ -53,6 +53,15 @@ struct RegGeom {
 // is owned by exactly one rank and a walker is in exactly one pair, so within a step nobody else touches either row:
 // one barrier between steps is all the synchronisation there is (api_shard.cu).  A template parameter because even
 // uniform branches on it cost 12 % in the single-GPU kernel.
+//   kPeer == 1: both rows of a pair stream through registers as in the single-GPU kernel (tile mode: the dense target,
+//               rows of 9..16 double2).
+//   kPeer == 2 (direct mode): the PARTNER rows -- the ones that may live on another GPU -- of a whole tile are fetched
+//               a tile ahead by TMA bulk copies (cp.async.bulk, one instruction per row, completion on an mbarrier per
+//               block slot) into a per-warp shared-memory stage, refilled slot by slot as the blocks consume it.  An
+//               NVLink read takes several times an HBM read; with the register pipeline (one block of 4 rows ahead) a
+//               warp sat out that latency once per block and the step ran at 65 % of the measured NVLink read
+//               bandwidth, local and remote traffic in turn rather than together (2 GPUs: 0.65 ms against 0.31 ms
+//               shard-local, profiles/r2_notes.md).  The owner's own rows keep the register pipeline.
 // Warps per block (= per SM): 20 under a 96-register cap for rows wider than 16 double2 (launch.cuh), 16 under 128
 // registers otherwise; the dense plugin keeps 8 warps and up to 255 registers for its DMMA accumulators.
 template <class Plugin, int G, int ITERS>
@@ -82,11 +91,15 @@ __device__ __forceinline__ double ld_peer_f64(const double *p)
     return v;
 }
 
-template <class Plugin, int G, int ITERS, bool kPeer = false>
+template <class Plugin, int G, int ITERS, int kPeer = 0>
 __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32, 1) step_reg_kernel(const StepParams p)
 {
     using Geo = RegGeom<G, ITERS>;
     constexpr int GB = Geo::kRowsPerBlock, PB = Geo::kPairs, NB = Geo::kBlocks;
+    constexpr bool kStageB = kPeer == 2;                 // partner rows through the shared-memory stage
+    constexpr int RL = kStageB ? 2 : 1;                  // register pipeline: every row, or the even (own) rows only
+    constexpr int NR = GB / RL;                          // rows per block held in registers
+    constexpr uint32_t kSlotRows = (32 / G) * (GB / 2);  // partner rows per block slot of the stage
     // direct: proposals never touch shared memory (only the flag words do).  The dense plugin keeps the y tile, which
     // its tensor-core evaluation reads; so do rows of 9..16 double2 (G = 16): their tile is small enough for 16
     // warps anyway, and deciding per block of 8 rows would run the scalar tail twice per tile at half occupancy
@@ -96,10 +109,14 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
+    static_assert(!kStageB || kDirect, "the partner stage is built for the direct mode");
     const uint32_t tile_bytes = kDirect ? 0u : 32u * p.row_stride;
-    const uint32_t warp_bytes = tile_bytes + ((p.flag_words * 128u + 127u) & ~127u);
+    const uint32_t stage_bytes = kStageB ? 16u * p.row_stride + 128u : 0u;  // 16 partner rows + NB mbarriers
+    const uint32_t warp_bytes = tile_bytes + stage_bytes + ((p.flag_words * 128u + 127u) & ~127u);
     unsigned char *ytile = smem + (size_t)warp * warp_bytes;
-    uint32_t *flagw = reinterpret_cast<uint32_t *>(ytile + tile_bytes);
+    [[maybe_unused]] unsigned char *bstage = ytile + tile_bytes;
+    [[maybe_unused]] const uint32_t bars = smem_u32(bstage + 16u * p.row_stride);  // NB x 8 bytes
+    uint32_t *flagw = reinterpret_cast<uint32_t *>(ytile + tile_bytes + stage_bytes);
 
     const uint32_t gwarp = blockIdx.x * p.warps + warp;
     const uint32_t nwarps = gridDim.x * p.warps;
@@ -162,13 +179,13 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
 
     // loads block `blk` of a tile whose lane = walker ids are `wt` (peer mode: lane = walker homes): rows
     // wl = grp*G + blk*GB + i
-    auto load_block = [&](double2 (&x)[GB][ITERS], uint32_t wt, int blk) {
+    auto load_block = [&](double2 (&x)[NR][ITERS], uint32_t wt, int blk) {
 #pragma unroll
-        for (int i = 0; i < GB; ++i) {
-            const uint32_t wl = grp * G + (uint32_t)(blk * GB + i);
+        for (int i = 0; i < NR; ++i) {
+            const uint32_t wl = grp * G + (uint32_t)(blk * GB + i * RL);
             const uint32_t row = __shfl_sync(0xffffffffu, wt, wl);
             const double *base;
-            if constexpr (kPeer) base = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;  // maybe over NVLink
+            if constexpr (kPeer != 0) base = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;  // maybe over NVLink
             else base = p.src_ens + (size_t)row * p.pitch;
             const double2 *src = reinterpret_cast<const double2 *>(base);
 #pragma unroll
@@ -180,6 +197,27 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             }
         }
     };
+
+    // partner stage: slot `blk` holds the partner (odd-lane) rows of block blk of a tile; every odd lane fetches its own
+    // walker's row with one bulk copy, lane 0 arms the slot's mbarrier with the byte count
+    [[maybe_unused]] auto stage_issue = [&](uint32_t hm, int blk) {
+        if constexpr (kStageB) {
+            const uint32_t bar = bars + 8u * (uint32_t)blk;
+            if (lane == 0) mbar_expect_tx(bar, kSlotRows * p.row_bytes);
+            if ((lane & 1u) && (int)((lane % G) / GB) == blk)
+                bulk_load(smem_u32(bstage + (lane >> 1) * p.row_stride),
+                          p.peer_ens[hm >> 28] + (size_t)(hm & 0x0FFFFFFFu) * p.pitch, p.row_bytes, bar);
+        }
+    };
+    if constexpr (kStageB) {
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) mbar_init(bars + 8u * b, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    [[maybe_unused]] uint32_t stage_phase = 0;
 
     // Everything above touches launch parameters and constants only.  From here on the kernel reads what
     // earlier launches wrote (order / pair lists, the ensemble, the log-probs): wait for them.
@@ -198,15 +236,19 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         w = act ? walker_of(pos) : p.w_lo;
     }
     [[maybe_unused]] uint32_t home = 0, home_n = 0;  // peer mode: where my walker (of this / the next tile) lives
-    if constexpr (kPeer) home = home_of(w);
+    if constexpr (kPeer != 0) home = home_of(w);
     // old log-prob: from the (gathered) array, or in one-sided mode from the walker's home rank
     auto load_lp = [&](uint32_t wid, uint32_t hm, bool a) -> double {
-        if constexpr (kPeer) return a ? ld_peer_f64(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
+        if constexpr (kPeer != 0) return a ? ld_peer_f64(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
         else return a ? __ldg(p.src_lp + wid) : 0.0;
     };
     double lp_old = load_lp(w, home, act);
-    double2 xn[GB][ITERS];
-    load_block(xn, kPeer ? home : w, 0);
+    if constexpr (kStageB) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) stage_issue(home, b);  // the first tile's partner rows, all slots
+    }
+    double2 xn[NR][ITERS];
+    load_block(xn, kPeer != 0 ? home : w, 0);
 
     for (;;) {
         // ---- P1: lane = walker: z, u, flags, (nphi-1) ln z ----
@@ -247,9 +289,9 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         } else {
             w_n = p.w_lo;
         }
-        if constexpr (kPeer) home_n = home_of(w_n);
+        if constexpr (kPeer != 0) home_n = home_of(w_n);
         lp_n = load_lp(w_n, home_n, act_n);
-        if constexpr (!kPeer) {
+        if constexpr (kPeer == 0) {
             if (p.l2_prefetch && act_n) {  // my next-tile row -> L2, a whole tile ahead of its loads
                 const char *r = reinterpret_cast<const char *>(p.src_ens + (size_t)w_n * p.pitch);
                 for (uint32_t off = 0; off < p.row_bytes; off += 128u) prefetch_l2(r + off);
@@ -262,20 +304,21 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         for (int a = 0; a < Plugin::kAcc; ++a) tot[a] = 0.0;
         // global-matching mode: walkers outside [w_lo, w_hi) belong to another rank, which updates them; peer mode: this
         // rank owns the pair and updates both walkers at their homes
-        const bool mine = kPeer ? act : (act && w >= p.w_lo && w < p.w_hi);
+        const bool mine = kPeer != 0 ? act : (act && w >= p.w_lo && w < p.w_hi);
         // where my walker's results go: local row, or (peer mode) its home rank's buffers
-        double *const my_lp = kPeer ? p.peer_lp[home >> 28] + (home & 0x0FFFFFFFu) : p.lp + (w - p.w_lo);
+        double *const my_lp = kPeer != 0 ? p.peer_lp[home >> 28] + (home & 0x0FFFFFFFu) : p.lp + (w - p.w_lo);
         bool accept = false;
 
 #pragma unroll 1
         for (int blk = 0; blk < NB; ++blk) {
-            double2 xc[GB][ITERS];
+            double2 xc[NR][ITERS];
 #pragma unroll
-            for (int i = 0; i < GB; ++i)
+            for (int i = 0; i < NR; ++i)
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
-            if (blk + 1 < NB) load_block(xn, kPeer ? home : w, blk + 1);
-            else if (tile_n < ntiles) load_block(xn, kPeer ? home_n : w_n, 0);
+            if (blk + 1 < NB) load_block(xn, kPeer != 0 ? home : w, blk + 1);
+            else if (tile_n < ntiles) load_block(xn, kPeer != 0 ? home_n : w_n, 0);
+            if constexpr (kStageB) mbar_wait(bars + 8u * (uint32_t)blk, stage_phase);  // this block's partner rows have landed
 
             double acc[Plugin::kAcc][GB];
             [[maybe_unused]] double2 yk[kDirect ? GB : 1][ITERS];  // direct path: the block's proposals stay in registers
@@ -291,7 +334,14 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                 for (int it = 0; it < ITERS; ++it) {
                     const uint32_t c = (uint32_t)it * G + j;
                     const uint32_t d = 2u * c;
-                    const double2 xa = xc[2 * pr][it], xb = xc[2 * pr + 1][it];
+                    double2 xa, xb;
+                    if constexpr (kStageB) {
+                        xa = xc[pr][it];
+                        xb = *reinterpret_cast<const double2 *>(bstage + (wb >> 1) * p.row_stride + (c < nvec ? c : nvec - 1u) * 16u);
+                    } else {
+                        xa = xc[2 * pr][it];
+                        xb = xc[2 * pr + 1][it];
+                    }
                     uint32_t fa = 3u, fb = 3u;
                     if (!all_flags) {
                         const uint32_t wd = (d >> 5) < p.flag_words ? (d >> 5) : 0u;
@@ -341,6 +391,11 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
 #pragma unroll
                 for (int a = 0; a < Plugin::kAcc; ++a) { acc[a][2 * pr] = pa[a]; acc[a][2 * pr + 1] = pb[a]; }
             }
+            if constexpr (kStageB) {
+                // every lane has the slot's rows in registers: refill it with the next tile's partner rows
+                __syncwarp();
+                if (tile_n < ntiles) stage_issue(home_n, blk);
+            }
             if constexpr (!Plugin::kNeedsRow) {
 #pragma unroll
                 for (int a = 0; a < Plugin::kAcc; ++a) {
@@ -362,7 +417,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     acc_now = mine && (u < q);
                     if (acc_now) {
                         *my_lp = lp_new;
-                        if constexpr (!kPeer) { if (p.dirty) p.dirty[w - p.w_lo] = 1; }
+                        if (p.dirty) {  // host-buffer call: this walker's row has to travel back (one-sided mode: mark it on its home GPU)
+                            if constexpr (kPeer != 0) reinterpret_cast<uint8_t *>(p.peer_lp[home >> 28] + p.peer_n + 32)[home & 0x0FFFFFFFu] = 1;
+                            else p.dirty[w - p.w_lo] = 1;
+                        }
                         ++n_acc;
                         accept = true;
                     }
@@ -371,10 +429,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
 #pragma unroll
                 for (int i = 0; i < GB; ++i) {
                     const uint32_t rl = grp * G + (uint32_t)(blk * GB + i);
-                    const uint32_t row = __shfl_sync(0xffffffffu, kPeer ? home : w, rl);
+                    const uint32_t row = __shfl_sync(0xffffffffu, kPeer != 0 ? home : w, rl);
                     if ((accmask >> rl) & 1u) {
                         double *rowp;
-                        if constexpr (kPeer) rowp = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;
+                        if constexpr (kPeer != 0) rowp = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;
                         else rowp = p.ens + (size_t)(row - p.w_lo) * p.pitch;
                         double2 *dst = reinterpret_cast<double2 *>(rowp);
 #pragma unroll
@@ -403,16 +461,19 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             accept = mine && (u < q);
             if (accept) {
                 double *rowp;
-                if constexpr (kPeer) rowp = p.peer_ens[home >> 28] + (size_t)(home & 0x0FFFFFFFu) * p.pitch;
+                if constexpr (kPeer != 0) rowp = p.peer_ens[home >> 28] + (size_t)(home & 0x0FFFFFFFu) * p.pitch;
                 else rowp = p.ens + (size_t)(w - p.w_lo) * p.pitch;
                 bulk_store(rowp, smem_u32(own_b), p.row_bytes);
                 *my_lp = lp_new;
-                if constexpr (!kPeer) { if (p.dirty) p.dirty[w - p.w_lo] = 1; }
+                if (p.dirty) {  // host-buffer call: this walker's row has to travel back (one-sided mode: mark it on its home GPU)
+                            if constexpr (kPeer != 0) reinterpret_cast<uint8_t *>(p.peer_lp[home >> 28] + p.peer_n + 32)[home & 0x0FFFFFFFu] = 1;
+                            else p.dirty[w - p.w_lo] = 1;
+                        }
                 ++n_acc;
             }
             bulk_commit();
         }
-        if constexpr (!kPeer) { if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0; }
+        if constexpr (kPeer == 0) { if (p.accepted_out && mine) p.accepted_out[w - p.w_lo] = accept ? 1 : 0; }
         if (p.rung_acc) count_rung_accepts(p.rung_acc, act ? w / p.npb : 0u, act, accept, lane);
 
         if (tile_n >= ntiles) break;
@@ -420,7 +481,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         w = w_n;
         act = act_n;
         lp_old = lp_n;
-        if constexpr (kPeer) home = home_n;
+        if constexpr (kPeer != 0) home = home_n;
+        if constexpr (kStageB) stage_phase ^= 1u;
     }
 
     if constexpr (!kDirect) bulk_wait_all();

@@ -49,6 +49,7 @@ struct StepParams {
     double *peer_ens[16];
     double *peer_lp[16];
     uint32_t peer_n;
+    uint32_t peer_stage;  // the launch has room for the partner-row stage (16 rows + mbarriers per warp): kPeer == 2
     uint32_t w_lo, w_hi;
     // Blocked matchings: every rung is cut into blocks of `mblk` walkers that are matched
     // separately (mblk == npb: the reference's whole-rung matching); block c of a rung takes its bijection keys at

@@ -147,6 +147,12 @@ class ShardedSampler:
         # global_every = k > 1 (matching "global" / "p2p"): only the steps whose index is a multiple of k use the
         # whole-ensemble matching, the others pair inside each shard
         self.global_every = max(1, int(global_every))
+        if self.mode == "walkers" and nbeta > 1:
+            # a tempered ensemble whose rungs do not divide over the ranks: shard boundaries cut through rungs, so there
+            # is no shard-local step -- every step uses the whole-rung matching, one-sided, and so does the ladder swap
+            if matching != "p2p":
+                raise ValueError("tempered walker shards (nbeta % world != 0) need matching='p2p'")
+            self.global_every = 1
         dev = torch.cuda.current_device() if device is None else device
         self.device = torch.device("cuda", dev)
         self.sampler = Sampler(flogprob, self.n_local, dim, seed=seed, device=dev)
@@ -214,6 +220,25 @@ class ShardedSampler:
             self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
             done += 1
 
+    def sample_pt_host(self, ens_local: np.ndarray, lp_local: np.ndarray, a: float, ufs: UpdateFlagSpec,
+                       beta_list: Sequence[float]):
+        """The reference-shaped call (host buffers in, ONE step, host buffers out) on this rank's shard; collective.
+        The step is the one the schedule prescribes for the current step index: shard-local, or the whole-ensemble
+        matching one-sided.  With pinned buffers only the shard's accepted walkers are written back."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if self.mode == "rungs":
+            self.sampler.sample_pt_host(ens_local, lp_local, a, ufs, beta[self.rung_off:self.rung_off + self.nb_local])
+            return
+        index = self.sampler.counters[0]
+        if self.matching == "local" or self.world == 1 or index % self.global_every != 0:
+            self.sampler.sample_pt_host(ens_local, lp_local, a, ufs, beta)
+        elif self.matching == "p2p":
+            self.sampler.sample_pt_peer_host(ens_local, lp_local, a, ufs, beta)
+        else:
+            self.upload(ens_local, lp_local)
+            self.sample_pt(a, ufs, beta, 1)
+            self.sampler.download(ens_local, lp_local)
+
     def twalk_sample(self, param, beta_list: Sequence[float], nsteps: int = 1):
         """twalk::sample (src/mcmc/twalk.rs:586-648) on this rank's shard.  Rung shards (whole rungs per rank):
         the matching never leaves a rung, so no communication and the same chain as one GPU.  Walker shards:
@@ -246,23 +271,24 @@ class ShardedSampler:
 
     def swap_walkers(self, beta_list: Sequence[float]):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
-        if self.world == 1 or self.mode != "rungs":
-            if self.mode == "rungs" or self.world == 1:
-                self.sampler.swap_walkers(beta)
-                return
-            # walker shards of a tempered ensemble whose rungs do not divide over the ranks
-            raise NotImplementedError("swap_walkers across walker shards needs nbeta % world == 0")
+        if self.world == 1:
+            self.sampler.swap_walkers(beta)
+            return
+        if self.mode != "rungs":
+            # walker shards: the one-sided swap works on global slots, wherever the rung boundaries fall
+            if len(beta) > 1:
+                self.sampler.swap_walkers_peer(beta)
+            return
         t, dist = self.torch, self.dist
+        if self.p2p:
+            # one-sided, one library call: barrier, the plan from log-probs read out of the peers' memory, incoming rows
+            # pulled over NVLink, barrier, commit.  A step only writes the rank's own rows: no barrier after the commit.
+            self.sampler.swap_walkers_peer(beta)
+            return
         with t.cuda.stream(self._stream):
             _, lp_all, src_all = self._gather_buffers()
             dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
         self.sampler.swap_plan_device(beta, lp_all.data_ptr(), src_all.data_ptr())
-        if self.p2p:
-            # one-sided: pull incoming rows from the peers' (still old) buffers, barrier, commit
-            self.sampler.swap_apply_p2p(src_all.data_ptr(), lp_all.data_ptr(), 0)
-            self._barrier()
-            self.sampler.swap_apply_p2p(src_all.data_ptr(), lp_all.data_ptr(), 1)
-            return   # a step only writes the rank's own rows: no barrier needed after the commit
         with t.cuda.stream(self._stream):
             local_dst, local_src, send_idx, recv_dst, send_counts, recv_counts = exchange_plan_torch(
                 src_all, self.n_local, self.world, self.rank)

@@ -316,6 +316,15 @@ class Sampler:
         self._ok(self._lib.scorus_sample_pt_host_n(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0], a,
                                                    C.byref(u), _dp(beta), beta.size, nsteps))
 
+    def sample_pt_peer_host(self, ensemble, logprob, a, ufs: UpdateFlagSpec, beta_list, nsteps: int = 1):
+        """The reference-shaped call for one shard of a multi-GPU ensemble (collective: every rank calls it with its
+        own shard's host buffers): upload, one-sided whole-ensemble steps, write-back of the accepted walkers."""
+        _check_arrays(ensemble, logprob)
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        u, keep = ufs._c(self.n, self.dim)
+        self._ok(self._lib.scorus_sample_pt_peer_host(self._ctx, _dp(ensemble), _dp(logprob), logprob.shape[0], a,
+                                                      C.byref(u), _dp(beta), beta.size, nsteps))
+
     def swap_walkers_host(self, ensemble, logprob, beta_list):
         _check_arrays(ensemble, logprob)
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
@@ -511,10 +520,16 @@ class Sampler:
         self._ok(self._lib.scorus_sample_pt_peer(self._ctx, a, C.byref(u), _dp(beta), beta.size, nsteps))
 
     def peer_read_bandwidth(self, peer: int, nbytes: int = 0, iters: int = 5):
-        """(copy-engine GB/s, SM-load GB/s) of this GPU reading rank `peer`'s ensemble over NVLink (measurement only)."""
-        ce, sm = C.c_double(0.0), C.c_double(0.0)
-        self._ok(self._lib.scorus_peer_read_bandwidth(self._ctx, peer, nbytes, iters, C.byref(ce), C.byref(sm)))
-        return ce.value, sm.value
+        """(copy-engine, SM sequential loads, SM loads of whole rows in a scrambled order) GB/s of this GPU reading rank
+        `peer`'s ensemble over NVLink (measurement only)."""
+        ce, sm, rr = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+        self._ok(self._lib.scorus_peer_read_bandwidth(self._ctx, peer, nbytes, iters, C.byref(ce), C.byref(sm), C.byref(rr)))
+        return ce.value, sm.value, rr.value
+
+    def swap_walkers_peer(self, beta_list):
+        """swap_walkers over rung shards, one-sided (scorus_swap_walkers_peer); beta_list is the whole ladder."""
+        beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        self._ok(self._lib.scorus_swap_walkers_peer(self._ctx, _dp(beta), beta.size))
 
     def peer_barrier(self):
         self._ok(self._lib.scorus_peer_barrier(self._ctx))

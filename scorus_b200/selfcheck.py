@@ -13,7 +13,9 @@ from __future__ import annotations
 
 import numpy as np
 
-from .ensemble_sample import (Gaussian, HmcParam, Mixture, Rastrigin, Rosenbrock, Sampler, TWalkParams, UpdateFlagSpec)
+from .ensemble_sample import Gaussian, Mixture, Rastrigin, Rosenbrock, Sampler, UpdateFlagSpec
+from .hmc import HmcParam
+from .twalk import TWalkParams
 
 
 def _all_ok(torch, dist, ok: bool) -> bool:
@@ -70,6 +72,41 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
         every = f" every {global_every}" if global_every > 1 else ""
         log(f"{name}: mode={sh.mode}/{matching}{every}{'/one-sided' if sh.p2p else ''} world={world} n={n} dim={dim} "
             f"nbeta={nbeta} steps={steps} {'OK' if ok else 'MISMATCH'} (pos={ok_pos} lp={ok_lp} moved={moved} counts={ok_cnt})")
+    ref.close()
+    sh.close()
+    return ok
+
+
+def run_host_call(world, log=print):
+    """The reference-shaped call on pinned host buffers, per shard (ShardedSampler.sample_pt_host), on the schedule
+    'whole-ensemble matching on every 2nd step': the host buffers must hold the single-GPU chain after every call --
+    i.e. every accepted walker of the shard travelled back, whichever rank computed it."""
+    import torch
+    import torch.distributed as dist
+    from .distributed import ShardedSampler
+    from .ensemble_sample import pinned_empty
+    rank = dist.get_rank()
+    n, dim, seed = 4096 * world, 64, 77
+    rng = np.random.default_rng(9)
+    ens = np.ascontiguousarray(rng.uniform(0.9, 1.1, (n, dim)))
+    ref = Sampler(Rosenbrock(), n, dim, seed=seed, device=torch.cuda.current_device())
+    ref.set_matching_blocks(world, 0, 2)
+    ref.upload(ens, None)
+    _, lp0 = ref.download()
+    sh = ShardedSampler(Rosenbrock(), n, dim, nbeta=1, seed=seed, matching="p2p", global_every=2)
+    lo, hi = sh.w_off, sh.w_off + sh.n_local
+    h_ens, h_lp = pinned_empty((sh.n_local, dim)), pinned_empty((sh.n_local,))
+    h_ens[:] = ens[lo:hi]
+    h_lp[:] = lp0[lo:hi]
+    ok = True
+    for k in range(6):
+        ref.sample_pt(2.0, UpdateFlagSpec.Prob(0.5), [1.0], 1)
+        sh.sample_pt_host(h_ens, h_lp, 2.0, UpdateFlagSpec.Prob(0.5), [1.0])
+        want_e, want_lp = ref.download()
+        ok = ok and np.array_equal(h_ens, want_e[lo:hi]) and np.allclose(h_lp, want_lp[lo:hi], rtol=1e-12, atol=1e-9)
+    ok = _all_ok(torch, dist, ok and not np.array_equal(want_e, ens))
+    if rank == 0:
+        log(f"host_call_one_sided_every2: world={world} n={n} dim={dim} {'OK' if ok else 'MISMATCH'}")
     ref.close()
     sh.close()
     return ok
@@ -164,6 +201,10 @@ def sharded_parity_cases(quick: bool = False, log=print):
                         matching="p2p", global_every=3, log=log))
     res.append(run_case("rosenbrock_shard_local", Rosenbrock(), 8192 * world, 64, 1, P(0.5), 6, 0, (0.9, 1.1),
                         matching="local", steps_per_call=3, log=log))
+    # a tempered ensemble whose three rungs do not divide over the ranks: walker shards cut through rungs; every step and
+    # every ladder swap is one-sided
+    res.append(run_case("rastrigin_pt_walker_shards", Rastrigin(), 3 * 2048 * world, 10, 3, P(0.2), 12, 4, (-0.5, 0.5),
+                        matching="p2p", log=log))
     # the same matching over an NCCL all-gather of the ensemble (BASELINE.json's wording), also on the k-schedule
     res.append(run_case("rosenbrock_allgather", Rosenbrock(), 8192 * world, 64, 1, P(0.5), 10, 0, (0.9, 1.1), log=log))
     res.append(run_case("mixture_allgather_small", Mixture(1.0, 2.0, [5.0] + [0.0] * 5), 64 * world, 6, 1, A(), 10, 0,
@@ -183,5 +224,6 @@ def sharded_parity_cases(quick: bool = False, log=print):
     res.append(run_case("twalk_rosenbrock_pt_small_rungs", Rosenbrock(), 64 * 2 * world, 20, 2 * world, None, 12, 3,
                         (0.9, 1.1), twalk=True, log=log))
     res.append(run_hmc(world, log=log))
+    res.append(run_host_call(world, log=log))
     res.append(run_mixed_statistics(world, log=log))
     return len(res), all(res)

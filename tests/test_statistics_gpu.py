@@ -181,3 +181,39 @@ def test_bimodal_reference_target_with_ladder(sb):
     assert 0.35 < frac_wide < 0.65, frac_wide            # exact: 0.5
     assert abs(out[:, 1].mean() - 25.505) < 1.5          # exact: 25.505
     assert abs(out[:, 0].mean()) < 1.6                   # exact: 0; dominated by the mode-weight error
+
+
+def test_k_schedule_keeps_moments_and_autocorrelation_time(sb):
+    """Evidence for the multi-GPU schedule: pairing inside `blocks` sub-ensembles on most steps
+    and over the whole ensemble on every k-th is still the stretch move -- every step's matching is independent of
+    the state -- so it must sample the same law with the same mixing.  c3-like target (two-component mixture, 8-D),
+    512 walkers cut into 8 blocks of 64 (a bench shard holds 2^19): the moments agree within 5 sigma of the Monte
+    Carlo error and the integrated autocorrelation time of the per-walker chains within 20 % for k = 1 (the
+    reference's matching), 4, 8 and k = infinity (blocks only: the replica upper bound of the bench)."""
+    n, dim, steps, burn = 512, 8, 6000, 1000
+    m = [2.0] + [0.0] * (dim - 1)
+    f = sb.Mixture(1.0, 1.0, m)                     # two unit Gaussians at +-2 e0: E[x0] = 0, E[x0^2] = 5, E[x1^2] = 1
+    rng = np.random.default_rng(12)
+    ens0 = rng.normal(size=(n, dim))
+    ens0[:, 0] += np.where(rng.random(n) < 0.5, 2.0, -2.0)
+    out = {}
+    for name, blocks, k in (("k1", 1, 0), ("k4", 8, 4), ("k8", 8, 8), ("blocks_only", 8, 0)):
+        rec = []
+        with sb.Sampler(f, n, dim, seed=2025) as s:
+            s.set_matching_blocks(blocks, 0, k)
+            s.upload(np.ascontiguousarray(ens0), None)
+            s.sample_pt(2.0, sb.UpdateFlagSpec.Prob(0.5), [1.0], burn)
+            for t in range(steps):
+                s.sample_pt(2.0, sb.UpdateFlagSpec.Prob(0.5), [1.0], 1)
+                e, _ = s.download()
+                rec.append(e[:, :2].copy())
+        x = np.asarray(rec)                          # [steps, walkers, 2]
+        tau0, tau1 = iat_walkers(x[:, :, 0]), iat_walkers(x[:, :, 1])
+        out[name] = (x[:, :, 0].mean(), (x[:, :, 0] ** 2).mean(), (x[:, :, 1] ** 2).mean(), tau0, tau1)
+    ref = out["k1"]
+    neff = steps * n / max(ref[3], ref[4])
+    for name, (m0, s0, s1, tau0, tau1) in out.items():
+        assert abs(m0) < 5.0 * math.sqrt(5.0 / neff) + 0.02, (name, m0)
+        assert abs(s0 - 5.0) < 5.0 * math.sqrt(2.0 * 25.0 / neff) + 0.05, (name, s0)
+        assert abs(s1 - 1.0) < 5.0 * math.sqrt(2.0 / neff) + 0.02, (name, s1)
+        assert abs(tau0 / ref[3] - 1.0) < 0.20 and abs(tau1 / ref[4] - 1.0) < 0.20, (name, tau0, tau1, ref[3], ref[4])
