@@ -109,7 +109,8 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         if not self.samples:  # fallback: one nvidia-smi query
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
@@ -371,6 +372,7 @@ def main():
     extra = None
     if world > 1 and s.mode == "walkers" and args.move == "stretch":
         def timed(fn, k):
+            fn(3)    # NVLink and clocks awake before the timed calls (the first exchange steps after an idle spell ran 30 % slow)
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream); fn(k); e1.record(stream)
@@ -443,7 +445,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if os.environ.get("BENCH_CLOCKS", "1") != "0":
+        clocks.start()
     l0 = launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -465,7 +468,7 @@ def main():
 
     # ---- the ladder swap on its own (reported separately; amortised into `value` above) ----
     swap_stage = None
-    if swap_every and nbeta > 1 and can_swap and world == 1:
+    if swap_every and nbeta > 1 and can_swap:
         k_sw = 20
         sw0 = stats["swapped"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -481,6 +484,10 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         t_step = e0.elapsed_time(e1) / k_sw
+        if dist:
+            tt = torch.tensor([t_both, t_step], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_both, t_step = float(tt[0].item()), float(tt[1].item())
         moved = (s.stats()["swapped"] - sw0) / k_sw          # accepted exchanges per call = rows moved / 2
         sw_bytes = 16.0 * n + 2.0 * moved * 16.0 * dim       # lp read + write; every accepted exchange moves two rows
         t_swap = max(t_both - t_step, 1e-6)

@@ -88,16 +88,22 @@ __global__ void __launch_bounds__(256) shard_pairs_kernel(const StepParams p, in
         a = even ? w : mate;  // list order = matching order: even position first
         b = even ? mate : w;
     }
+    // one atomic per BLOCK on the list length (one per warp was 131072 same-address atomics at 2^22 walkers: most of
+    // the kernel's 111 us, profiles/r2_c5_peer_single_launch_list_summary.csv)
+    __shared__ uint32_t warp_cnt[8], block_base;
     const unsigned m = __ballot_sync(0xffffffffu, emit);
-    if (m) {
-        uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(count, 2u * (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (emit) {
-            const uint32_t slot = base + 2u * (uint32_t)__popc(m & ((1u << lane) - 1u));
-            pairs[slot] = a;
-            pairs[slot + 1] = b;
-        }
+    if (lane == 0) warp_cnt[threadIdx.x >> 5] = (uint32_t)__popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int wq = 0; wq < 8; ++wq) { const uint32_t c = warp_cnt[wq]; warp_cnt[wq] = tot; tot += c; }
+        block_base = tot ? atomicAdd(count, 2u * tot) : 0u;
+    }
+    __syncthreads();
+    if (emit) {
+        const uint32_t slot = block_base + 2u * (warp_cnt[threadIdx.x >> 5] + (uint32_t)__popc(m & ((1u << lane) - 1u)));
+        pairs[slot] = a;
+        pairs[slot + 1] = b;
     }
 }
 
@@ -520,13 +526,21 @@ extern "C" int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta, siz
     if ((rc = ensure(ctx, (void **)&ctx->d_lp_all, &ctx->lp_all_cap, n * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, (void **)&ctx->d_src_all, &ctx->src_all_cap, n * sizeof(uint32_t)))) return rc;
     if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, ctx->n * (size_t)ctx->pitch * sizeof(double)));
+    // SCORUS_SWAP_DIAG=1 (measurement only): CUDA events between the phases, printed by rank 0 after a synchronise
+    const bool diag = env_int("SCORUS_SWAP_DIAG", 0) != 0;
+    cudaEvent_t ev[7];
+    int nev = 0;
+    auto mark = [&]() { if (diag) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], ctx->stream); ++nev; } };
+    mark();
     if ((rc = scorus_peer_barrier(ctx))) return rc;
+    mark();
     SwapParams sp;
     memset(&sp, 0, sizeof(sp));
     PeerTable t;
     for (int q = 0; q < 16; ++q) t.lp[q] = ctx->peer_lp[q];
     gather_lp_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(t, (uint32_t)ctx->n, (uint32_t)n, ctx->d_lp_all);
     ++ctx->launches;
+    mark();
     sp.lp = ctx->d_lp_all; sp.lp_src = ctx->d_lp_all; sp.beta = ctx->d_beta; sp.src = ctx->d_src_all; sp.stats = ctx->d_stats;
     if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
     sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
@@ -539,9 +553,23 @@ extern "C" int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta, siz
         sp.jinv = ctx->d_jinv;
     }
     if ((rc = launch_swap_chain(ctx, sp))) return rc;
+    mark();
     ++ctx->swap_call;
     count_swap_proposed(ctx, nbeta, npb);
     if ((rc = scorus_swap_apply_p2p(ctx, ctx->d_src_all, ctx->d_lp_all, 0))) return rc;
+    mark();
     if ((rc = scorus_peer_barrier(ctx))) return rc;
-    return scorus_swap_apply_p2p(ctx, ctx->d_src_all, ctx->d_lp_all, 1);
+    mark();
+    rc = scorus_swap_apply_p2p(ctx, ctx->d_src_all, ctx->d_lp_all, 1);
+    mark();
+    if (diag) {
+        cudaStreamSynchronize(ctx->stream);
+        float ms[6];
+        for (int k = 0; k + 1 < nev; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+        if (ctx->rank == 0)
+            fprintf(stderr, "swap_walkers_peer us: barrier %.1f gather_lp %.1f plan %.1f pull %.1f barrier %.1f commit %.1f\n",
+                    1e3 * ms[0], 1e3 * ms[1], 1e3 * ms[2], 1e3 * ms[3], 1e3 * ms[4], 1e3 * ms[5]);
+        for (int k = 0; k < nev; ++k) cudaEventDestroy(ev[k]);
+    }
+    return rc;
 }
