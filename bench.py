@@ -70,14 +70,21 @@ def b_alg(dim):
     return 16 * dim + 16
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region (pynvml, else nvidia-smi), sampled by the main thread
+    while the GPU works through the queued steps -- after the last launch has been enqueued, before the synchronise.
+    Round 1 polled NVML from a second thread every 5 ms; with one process per GPU on eight GPUs those queries took
+    tens of milliseconds each and stalled the launches of the timed region (the same 100 steps: 0.136 ms/step with the
+    thread off, 0.546 with it on, profiles/r2_notes.md), and initialising NVML right before the first timed launch cost
+    another 2 ms.  NVML is therefore initialised at start-up and never queried while launches are being enqueued."""
+    NAMES = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+             "hw_power_brake": 0x80, "sync_boost": 0x10, "display_clocks": 0x100}
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop_evt = threading.Event()
         self._nvml = None
+        if os.environ.get("BENCH_CLOCKS", "1") == "0":
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -87,30 +94,30 @@ class ClockSampler(threading.Thread):
         except Exception:
             self._nvml = None
 
-    def run(self):
-        if self._nvml is None:
-            return
+    def sample(self):
         nv = self._nvml
-        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
-                 "hw_power_brake": 0x80, "sync_boost": 0x10, "display_clocks": 0x100}
-        while not self._stop_evt.is_set():
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
             except Exception:
-                pass
-            time.sleep(0.005)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for k, bit in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def sample_until(self, event, period=0.002, limit=200):
+        """Call after the timed steps have been enqueued: samples until `event` (recorded after them) has completed."""
+        self.sample()
+        while not event.query() and len(self.samples) < limit:
+            time.sleep(period)
+            self.sample()
 
     def stop(self):
-        self._stop_evt.set()
-        if self.is_alive():
-            self.join(timeout=2)
         if not self.samples:  # fallback: one nvidia-smi query
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
@@ -284,6 +291,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    clocks = ClockSampler(local_rank)   # NVML initialised here, long before the timed region
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -444,14 +452,12 @@ def main():
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    if os.environ.get("BENCH_CLOCKS", "1") != "0":
-        clocks.start()
     l0 = launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     run_steps(W, args.steps)
     ev1.record(stream)
+    clocks.sample_until(ev1)     # the GPU is still working through the queue: clocks under load, no launch in its way
     torch.cuda.synchronize()
     if dist:
         dist.barrier()

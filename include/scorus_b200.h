@@ -86,6 +86,12 @@ typedef struct scorus_ufs {
  * cooperative kernel sums per-lane partials in a fixed tree instead: same positions and accept
  * decisions, log-probs equal to a few ulp, about 2x faster. */
 #define SCORUS_CFG_SEQUENTIAL_SUM 1u
+/* T = f32: the reference is generic over the walkers' scalar type (`T: Float`, src/mcmc/ensemble_sample.rs:95).  An f32
+ * context holds the ensemble and the log-probs as float and runs the f32 instantiation of the fused step kernel, of
+ * init_logprob and of the ladder swap (all targets but the tensor-core dense Gaussian); host arrays go through the
+ * *_f32 entry points below, scalars (a, beta, plugin parameters) stay double in the ABI.  Everything else -- t-walk,
+ * HMC, statistics, sharding, host-buffer calls, SEQUENTIAL_SUM -- answers SCORUS_ERR_INVALID_ARG on such a context. */
+#define SCORUS_CFG_F32 2u
 typedef struct scorus_cfg {
     uint64_t n_walkers; /* ensemble.len() */
     uint32_t dim;       /* ensemble[i].dimension() */
@@ -345,6 +351,19 @@ int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, const double
  * from log-probs read one-sidedly out of the peers' memory, incoming rows pulled over NVLink, barrier, commit.  No
  * NCCL, no host synchronisation; every rank calls it with the GLOBAL beta list.  Identical to the single-GPU swap. */
 int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta_list, size_t nbeta);
+
+/* ---- T = f32 (SCORUS_CFG_F32): the calls that carry walker data, with float arrays.  scorus_set_logprob,
+ * scorus_init_logprob, scorus_sample, scorus_sample_pt, scorus_swap_walkers, scorus_get_stats, the counters and the
+ * stream calls are shared with f64 contexts. ---- */
+int scorus_upload_f32(scorus_ctx *ctx, const float *ensemble, const float *logprob);
+int scorus_download_f32(scorus_ctx *ctx, float *ensemble, float *logprob);
+/* sample_pt with every draw supplied (src/mcmc/ensemble_sample.rs:107-190 at T = f32): as scorus_sample_pt_fixed */
+int scorus_sample_pt_fixed_f32(scorus_ctx *ctx, const double *beta_list, size_t nbeta, const uint32_t *partner,
+                               const float *z, const uint8_t *flags, size_t flag_len, const float *u,
+                               uint8_t *accepted_out);
+/* swap_walkers with every draw supplied (src/mcmc/utils.rs:72-112 at T = f32): as scorus_swap_walkers_fixed */
+int scorus_swap_walkers_fixed_f32(scorus_ctx *ctx, const double *beta_list, size_t nbeta, const uint32_t *jvec,
+                                  const float *r, uint8_t *swapped_out);
 
 /* ---- plumbing (no reference counterpart: the reference call returns when the step is done; these calls are
  * asynchronous on the context's stream unless they return host data) ---- */

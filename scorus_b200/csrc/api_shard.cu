@@ -538,7 +538,9 @@ extern "C" int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta, siz
     memset(&sp, 0, sizeof(sp));
     PeerTable t;
     for (int q = 0; q < 16; ++q) t.lp[q] = ctx->peer_lp[q];
-    gather_lp_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(t, (uint32_t)ctx->n, (uint32_t)n, ctx->d_lp_all);
+    // one element per thread: every NVLink read in flight at once (a grid-stride loop of seven dependent-latency reads
+    // per thread took 32 us for 8 MB at 8 GPUs)
+    gather_lp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t, (uint32_t)ctx->n, (uint32_t)n, ctx->d_lp_all);
     ++ctx->launches;
     mark();
     sp.lp = ctx->d_lp_all; sp.lp_src = ctx->d_lp_all; sp.beta = ctx->d_beta; sp.src = ctx->d_src_all; sp.stats = ctx->d_stats;

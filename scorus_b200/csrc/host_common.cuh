@@ -93,6 +93,7 @@ struct scorus_ctx {
     uint32_t nparams = 0;
     bool uploaded = false;
     bool sequential = false;  // SCORUS_CFG_SEQUENTIAL_SUM
+    bool f32 = false;         // SCORUS_CFG_F32: d_ens / d_lp hold float, kernels of namespace scorus::f32 (api_f32.cu)
     std::string err;
 };
 
@@ -108,6 +109,13 @@ inline int fail(scorus_ctx *c, int code, const char *fmt, ...)
     }
     return code;
 }
+
+// entry points without an f32 instantiation
+#define F64_ONLY(ctx)                                                                                          \
+    do {                                                                                                       \
+        if ((ctx) && (ctx)->f32)                                                                               \
+            return fail((ctx), SCORUS_ERR_INVALID_ARG, "%s is not available on an f32 context", __func__);     \
+    } while (0)
 
 #define CU(call)                                                                                   \
     do {                                                                                           \
@@ -141,6 +149,11 @@ int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool 
 void launch_exact_order(scorus_ctx *ctx, uint64_t step, size_t nbeta, uint32_t npb, uint32_t *order, uint32_t w_off);
 void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv);
 int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp);
+// api_f32.cu: the T = f32 paths behind the shared entry points
+int f32_set_params(scorus_ctx *ctx, const double *params, size_t nparams);
+int f32_init_logprob(scorus_ctx *ctx);
+int f32_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps);
+int f32_swap_walkers(scorus_ctx *ctx, const double *beta, size_t nbeta);
 // api_stats.cu
 int after_step(scorus_ctx *ctx);  // chain capture and running moments, after every step
 int launch_scatter_download(scorus_ctx *ctx, double *host_ens, double *host_lp);

@@ -4,7 +4,9 @@
 #include "step_coop_kernel.cuh"
 #include "step_kernel.cuh"
 #include "step_reg_kernel.cuh"
+#ifndef SCORUS_F32  // the f32 instantiation (gen_f32.py) covers the register kernel, init_logprob and the swap
 #include "step_small_kernel.cuh"
+#endif
 
 #ifndef SCORUS_PLUGIN
 #error "compile with -DSCORUS_PLUGIN=LpGaussian (or another plugin of logprob.cuh)"
@@ -64,10 +66,14 @@ cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const G
                                                     cudaStream_t st)
 {
     using Plugin = SCORUS_PLUGIN;
+#ifdef SCORUS_F32
+    if (g.kernel != KERNEL_REG) return cudaErrorNotSupported;
+#else
     if (g.kernel == KERNEL_SEQ) {
         if (all_flags) return launch_kernel(step_seq_kernel<Plugin, true>, p, g, st);
         return launch_kernel(step_seq_kernel<Plugin, false>, p, g, st);
     }
+#endif
     const uint32_t nvec = p.pitch / 2;
     if (g.kernel == KERNEL_REG) {
         // rows of 5 or 6 double2 (D = 9..12): two lanes x three chunks wastes 1/6 of the lanes, eight lanes
@@ -83,9 +89,13 @@ cudaError_t SCORUS_CAT(launch_step_, SCORUS_PLUGIN)(const StepParams &p, const G
         default: return launch_reg<Plugin, 32, 1>(p, g, st);
         }
     }
+#ifdef SCORUS_F32
+    return cudaErrorNotSupported;
+#else
     // cooperative kernel with the old rows staged by TMA: any dimension that fits a tile
     if (nvec >= 32) return launch_kernel(step_coop_kernel<Plugin, 32>, p, g, st);
     return launch_kernel(step_coop_kernel<Plugin, 8>, p, g, st);
+#endif
 }
 
 cudaError_t SCORUS_CAT(launch_init_, SCORUS_PLUGIN)(const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st)
@@ -97,6 +107,7 @@ cudaError_t SCORUS_CAT(launch_init_, SCORUS_PLUGIN)(const StepParams &p, uint32_
     return cudaGetLastError();
 }
 
+#ifndef SCORUS_F32
 cudaError_t SCORUS_CAT(launch_small_, SCORUS_PLUGIN)(const StepParams &p, const Geometry &g, uint32_t inner_steps,
                                                      cudaStream_t st)
 {
@@ -106,5 +117,6 @@ cudaError_t SCORUS_CAT(launch_small_, SCORUS_PLUGIN)(const StepParams &p, const 
     step_small_kernel<Plugin><<<1, g.warps * 32, g.smem, st>>>(p, inner_steps);
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace scorus

@@ -364,6 +364,7 @@ struct LpMixture {
     }
 };
 
+#ifndef SCORUS_F32  // the dense target runs on the fp64 tensor cores: no f32 instantiation (gen_f32.py)
 #ifndef SCORUS_K3_NG
 #define SCORUS_K3_NG 4
 #endif
@@ -485,5 +486,6 @@ struct LpCorrGaussian {
         return -0.5 * s;
     }
 };
+#endif  // SCORUS_F32
 
 }  // namespace scorus

@@ -145,13 +145,73 @@ __host__ __device__ __forceinline__ uint32_t bij_inv(uint32_t y, uint32_t n, uin
     return y;
 }
 
+// ---- the pieces that depend on the scalar type T of the walkers (the reference is generic over T: Float,
+// src/mcmc/ensemble_sample.rs:95; the f32 instantiation of the kernels is produced from the same sources, gen_f32.py) ----
+// unit uniform in [0,1) at the type's full mantissa: 53 bits of (hi, lo) for f64, the top 24 bits of hi for f32
+template <typename T> __host__ __device__ __forceinline__ T to_unit(uint32_t lo, uint32_t hi);
+template <> __host__ __device__ __forceinline__ double to_unit<double>(uint32_t lo, uint32_t hi) { return u53(lo, hi); }
+template <> __host__ __device__ __forceinline__ float to_unit<float>(uint32_t, uint32_t hi) { return (float)(hi >> 8) * 0x1.0p-24f; }
+template <typename T> __host__ __device__ __forceinline__ T real_nan();
+template <> __host__ __device__ __forceinline__ double real_nan<double>()
+{
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(0x7ff8000000000000ll);
+#else
+    return __builtin_nan("");
+#endif
+}
+template <> __host__ __device__ __forceinline__ float real_nan<float>()
+{
+#ifdef __CUDA_ARCH__
+    return __int_as_float(0x7fc00000);
+#else
+    return __builtin_nanf("");
+#endif
+}
+// guard band of the exp-free swap decision (swap_kernel.cuh): far above the rounding of exp / log in T, far below
+// anything that matters
+template <typename T> __host__ __device__ __forceinline__ T swap_guard();
+template <> __host__ __device__ __forceinline__ double swap_guard<double>() { return 1e-9; }
+template <> __host__ __device__ __forceinline__ float swap_guard<float>() { return 1e-4f; }
+
 // Goodman-Weare stretch factor from a unit uniform: src/mcmc/utils.rs:39-44 with
 // p = u * 2(sqrt a - 1/sqrt a);  inv_sqrt_a and range are computed once on the host.
-__host__ __device__ __forceinline__ double z_from_uniform(double u01, double inv_sqrt_a, double range)
+template <typename T>
+__host__ __device__ __forceinline__ T z_from_uniform(T u01, T inv_sqrt_a, T range)
 {
-    double p = u01 * range;
-    double y = inv_sqrt_a + p / 2.0;
+    T p = u01 * range;
+    T y = inv_sqrt_a + p / T(2);
     return y * y;
 }
+
+#ifdef __CUDACC__
+// streaming loads: read once, do not keep in L1 (the shared-memory carve-out leaves little).  One 16-byte (f64) or
+// 8-byte (f32) chunk = two coordinates.
+__device__ __forceinline__ double2 ld_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ld_stream(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+// scalar read of a peer's memory: not through the non-coherent path (the value was written by another GPU)
+__device__ __forceinline__ double ld_peer(const double *p)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_peer(const float *p)
+{
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+#endif
 
 }  // namespace scorus

@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(512, 1) step_seq_kernel(const StepParams p)
             u = act ? __ldg(p.u_in + w) : 1.0;
         } else {
             U4 r = draw(p.seed, p.step, ST_ZU, w + p.w_off, 0);
-            z = z_from_uniform(u53(r.x, r.y), p.inv_sqrt_a, p.z_range);
-            u = u53(r.z, r.w);
+            z = z_from_uniform(to_unit<double>(r.x, r.y), p.inv_sqrt_a, p.z_range);
+            u = to_unit<double>(r.z, r.w);
         }
 
         // ---- update flags (:38-54) ----

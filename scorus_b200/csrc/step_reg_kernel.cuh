@@ -32,14 +32,6 @@
 
 namespace scorus {
 
-// 128-bit streaming load: read once, do not keep in L1 (the shared-memory carve-out leaves little)
-__device__ __forceinline__ double2 ld_stream(const double2 *p)
-{
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
 template <int G, int ITERS>
 struct RegGeom {
     static constexpr int kRows = (G == 32 && ITERS <= 2) ? SCORUS_REG_ROWS_WIDE : SCORUS_REG_ROWS;
@@ -81,14 +73,6 @@ template <class Plugin, int G>
 __host__ __device__ constexpr bool reg_kernel_direct()
 {
     return !Plugin::kNeedsRow && G != 16;
-}
-
-// 8-byte read of a peer's memory: not through the non-coherent path (the value was written by another GPU)
-__device__ __forceinline__ double ld_peer_f64(const double *p)
-{
-    double v;
-    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
 }
 
 template <class Plugin, int G, int ITERS, int kPeer = 0>
@@ -239,7 +223,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
     if constexpr (kPeer != 0) home = home_of(w);
     // old log-prob: from the (gathered) array, or in one-sided mode from the walker's home rank
     auto load_lp = [&](uint32_t wid, uint32_t hm, bool a) -> double {
-        if constexpr (kPeer != 0) return a ? ld_peer_f64(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
+        if constexpr (kPeer != 0) return a ? ld_peer(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
         else return a ? __ldg(p.src_lp + wid) : 0.0;
     };
     double lp_old = load_lp(w, home, act);
@@ -258,8 +242,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             u = act ? __ldg(p.u_in + w) : 1.0;
         } else {
             const U4 r = draw(p.seed, p.step, ST_ZU, w + p.w_off, 0);
-            z = z_from_uniform(u53(r.x, r.y), p.inv_sqrt_a, p.z_range);
-            u = u53(r.z, r.w);
+            z = z_from_uniform(to_unit<double>(r.x, r.y), p.inv_sqrt_a, p.z_range);
+            u = to_unit<double>(r.z, r.w);
         }
         // the previous tile's accepted rows must have left the y tile before reuse
         if constexpr (!kDirect) bulk_wait_read_all();

@@ -95,18 +95,21 @@ __global__ void __launch_bounds__(256) swap_uniforms_kernel(const SwapParams p)
             r = __ldg(p.r_in + e);
         } else {
             const U4 o = draw(p.seed, p.swap_call, ST_SWAP_U, j2, i);
-            r = u53(o.x, o.y);
+            r = to_unit<double>(o.x, o.y);
         }
         p.chain_r[e] = r;
         // ln r for the exp-free decision; anything but 0 < r < 1 (only a caller-supplied r can be) is marked NaN and
         // decided by the literal expression
-        p.chain_lr[e] = (r > 0.0 && r < 1.0) ? log(r) : __longlong_as_double(0x7ff8000000000000ll);
+        p.chain_lr[e] = (r > 0.0 && r < 1.0) ? log(r) : real_nan<double>();
     }
 }
 
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+// asynchronous copy of one scalar (BYTES = its size), global -> shared
+template <int BYTES>
+__device__ __forceinline__ void cp_async_scalar(void *smem_dst, const void *gsrc)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "n"(BYTES)
                  : "memory");
 }
 
@@ -148,8 +151,8 @@ __global__ void __launch_bounds__(128) swap_chain_kernel(const SwapParams p)
                     j2 = bij(a1, npb, p.bij_bits, K);
                 }
                 t_j2[k * T + tid] = j2;
-                cp_async8(t_lp + k * T + tid, p.lp_src + (size_t)(i - 1) * npb + j2);
-                cp_async8(t_lr + k * T + tid, p.chain_lr + (size_t)s * npb + j2);
+                cp_async_scalar<sizeof(double)>(t_lp + k * T + tid, p.lp_src + (size_t)(i - 1) * npb + j2);
+                cp_async_scalar<sizeof(double)>(t_lr + k * T + tid, p.chain_lr + (size_t)s * npb + j2);
                 a1 = j2;
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(128) swap_chain_kernel(const SwapParams p)
                 const uint32_t hot = i * npb + a2, cold = (i - 1) * npb + j2;
                 const double beta1 = __ldg(p.beta + i), beta2 = __ldg(p.beta + i - 1);
                 const double x = (beta2 - beta1) * (-lp_cold + carry_lp);  // exchange_prob's exponent, utils.rs:63-66
-                const double d = 1e-9 * (1.0 + fabs(x));
+                const double d = swap_guard<double>() * (1.0 + fabs(x));
                 bool sw;
                 if (lr == lr && x >= d) {
                     sw = true;                       // exp(x) > 1: probability 1, and 0 < r < 1
