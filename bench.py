@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+ELEM = 8   # bytes per coordinate of the run (--dtype)
 
 WORKLOADS = {
     # name: (description, kind, n, dim, nbeta, ufs, prob, init box, swap_every)
@@ -66,8 +67,8 @@ def betas(nbeta):
     return (2.0 ** -(np.arange(nbeta) / k)).astype(np.float64)
 
 
-def b_alg(dim):
-    return 16 * dim + 16
+def b_alg(dim, elem=8):
+    return 2 * elem * dim + 2 * elem
 
 
 class ClockSampler:
@@ -248,6 +249,9 @@ def main():
                          "(pair owner reads / writes the partner's row in the peer's HBM); global = the same over an NCCL "
                          "all-gather of the ensemble per step; local = shard-local matchings only (no exchange: the "
                          "replica upper bound)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f32: the T = f32 instantiation of the step / init / swap kernels (one GPU, device-timed line only; "
+                         "roofline bytes 8 D + 8 per walker-step)")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the sharded-vs-single-GPU parity cases before timing")
     args = ap.parse_args()
 
@@ -261,6 +265,10 @@ def main():
         n = args.n_walkers
         desc += f" [n_walkers overridden to {n}]"
     W = max(args.warmup, 3)
+    global ELEM
+    ELEM = 4 if args.dtype == "f32" else 8
+    if args.dtype == "f32" and world > 1:
+        raise SystemExit("--dtype f32 is a single-GPU line")
 
     if args.move == "twalk":
         desc += " [move: t-walk, twalk::sample with TWalkParams::new(dim)]"
@@ -342,7 +350,14 @@ def main():
         n_local, nb_local = n, nbeta
         parallelism = "single gpu"
         ens = make_ensemble(n_local, dim, box, 5, kind)
-        s = sb.Sampler(sb.LogProb(kind, tuple(params)), n_local, dim, seed=2024, device=local_rank)
+        if args.dtype == "f32":
+            if args.move != "stretch":
+                raise SystemExit("--dtype f32 covers the stretch move (K1 / K2 / K5)")
+            args.no_e2e, args.no_cpu = True, True      # host-buffer calls and the CPU port are f64
+            ens = np.ascontiguousarray(ens.astype(np.float32))
+            s = sb.Sampler(sb.LogProb(kind, tuple(params)), n_local, dim, seed=2024, device=local_rank, dtype=np.float32)
+        else:
+            s = sb.Sampler(sb.LogProb(kind, tuple(params)), n_local, dim, seed=2024, device=local_rank)
         s.set_stream(stream.cuda_stream)
         s.upload(ens, None)
         s.sync()
@@ -590,7 +605,7 @@ def main():
         kernel_name = "hmc_kernel (10 leapfrog steps per walker in registers: bound by fp64 arithmetic, not HBM)"
     traffic = None
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(prof) and args.move == "stretch" and world == 1 and not args.n_walkers:  # measured for this exact launch shape
+    if os.path.exists(prof) and args.move == "stretch" and world == 1 and not args.n_walkers and args.dtype == "f64":  # measured for this exact launch shape
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
     if kind == 6:
         # dense quadratic form: 2 D^2 + 2 D flops per walker-step against an fp64 DGEMM
@@ -613,13 +628,13 @@ def main():
                     # column block n0 at n0, so it EXECUTES this fraction of the accounted dense 2 D^2 flops
                     # ("a triangular-factor formulation does half -- still account at 2 D^2")
                     "executed_fraction_of_accounted_flops": sum(dim - n0 for n0 in range(0, dim, 32)) / (dim * len(range(0, dim, 32))),
-                    "hbm_frac": b_alg(dim) * n_local * args.steps / (ms * 1e-3) / 1e9 / peak}
+                    "hbm_frac": b_alg(dim, ELEM) * n_local * args.steps / (ms * 1e-3) / 1e9 / peak}
     else:
-        bytes_per_launch = b_alg(dim) * n_local
+        bytes_per_launch = b_alg(dim, ELEM) * n_local
         achieved = bytes_per_launch * args.steps / (ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
-                    "algorithmic_bytes_per_walker_step": b_alg(dim), "walkers_per_launch": n_local,
+                    "algorithmic_bytes_per_walker_step": b_alg(dim, ELEM), "walkers_per_launch": n_local,
                     "note": "launch time = device time of the timed region / steps (one step kernel launch per step"
                             + (", swap kernels amortised in)" if swap_every else ")")
                             + "; the algorithmic figure counts every row as written, the kernel writes accepted rows "
@@ -638,11 +653,11 @@ def main():
     line = {
         "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": desc, "n_walkers": n, "dim": dim, "nbeta": nbeta, "ufs": ufs, "prob": prob, "a": 2.0,
                    "move": args.move, "parallelism": parallelism, "swap_every": swap_every,
-                   "l2": f"resident ensemble {n_local * dim * 8 / 2**20:.0f} MiB per GPU vs 126 MB L2 (no flush needed)"
-                         if n_local * dim * 8 > 2 * 126e6 else "ensemble fits in L2: numbers are L2-resident, not HBM"},
+                   "l2": f"resident ensemble {n_local * dim * ELEM / 2**20:.0f} MiB per GPU vs 126 MB L2 (no flush needed)"
+                         if n_local * dim * ELEM > 2 * 126e6 else "ensemble fits in L2: numbers are L2-resident, not HBM"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "accept_rate": stats["accepted"] / max(1, stats["proposed"]),
     }

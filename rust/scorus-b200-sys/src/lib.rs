@@ -35,6 +35,7 @@ pub const SCORUS_UFS_ALL: i32 = 1;
 pub const SCORUS_UFS_ONE_HOT_CYCLE: i32 = 2;
 pub const SCORUS_UFS_MASK: i32 = 3;
 pub const SCORUS_CFG_SEQUENTIAL_SUM: u32 = 1;
+pub const SCORUS_CFG_F32: u32 = 2;
 
 /// HmcParam, src/mcmc/hmc/naive.rs:17-23
 #[repr(C)]
@@ -136,6 +137,13 @@ extern "C" {
                                       a: f64, ufs: *const scorus_ufs, beta_list: *const f64, nbeta: usize,
                                       nsteps: u64) -> c_int;
     pub fn scorus_peer_barrier(ctx: *mut scorus_ctx) -> c_int;
+    pub fn scorus_upload_f32(ctx: *mut scorus_ctx, ensemble: *const f32, logprob: *const f32) -> c_int;
+    pub fn scorus_download_f32(ctx: *mut scorus_ctx, ensemble: *mut f32, logprob: *mut f32) -> c_int;
+    pub fn scorus_sample_pt_fixed_f32(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize, partner: *const u32,
+                                      z: *const f32, flags: *const u8, flag_len: usize, u: *const f32,
+                                      accepted_out: *mut u8) -> c_int;
+    pub fn scorus_swap_walkers_fixed_f32(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize, jvec: *const u32,
+                                         r: *const f32, swapped_out: *mut u8) -> c_int;
     pub fn scorus_swap_walkers_peer(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize) -> c_int;
     pub fn scorus_peer_read_bandwidth(ctx: *mut scorus_ctx, peer: c_int, bytes: usize, iters: c_int,
                                       gbps_copy_engine: *mut f64, gbps_sm_loads: *mut f64, gbps_random_rows: *mut f64) -> c_int;

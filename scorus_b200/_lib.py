@@ -33,6 +33,7 @@ LP_GAUSSIAN, LP_BOUNDED_GAUSSIAN, LP_ROSENBROCK, LP_RASTRIGIN = 0, 1, 2, 3
 LP_BIMODAL2D, LP_STEP2D, LP_CORR_GAUSSIAN, LP_MIXTURE = 4, 5, 6, 7
 UFS_PROB, UFS_ALL, UFS_ONE_HOT_CYCLE, UFS_MASK = 0, 1, 2, 3
 CFG_SEQUENTIAL_SUM = 1
+CFG_F32 = 2
 
 class TwalkParams(C.Structure):
     """scorus_twalk_params (include/scorus_b200.h): TWalkParams of src/mcmc/twalk.rs:75-83, fw cumulative."""
@@ -59,6 +60,7 @@ def load() -> C.CDLL:
     vp, sz, u64, dbl, ci = C.c_void_p, C.c_size_t, C.c_uint64, C.c_double, C.c_int
     dp, u32p, u8p, u64p = (C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
                            C.POINTER(C.c_uint64))
+    fp = C.POINTER(C.c_float)
     sig = {
         "scorus_abi_version": (ci, []),
         "scorus_status_string": (C.c_char_p, [ci]),
@@ -106,6 +108,10 @@ def load() -> C.CDLL:
         "scorus_ipc_export": (ci, [vp, vp, vp]),
         "scorus_ipc_attach": (ci, [vp, ci, ci, vp, vp]),
         "scorus_sample_pt_peer": (ci, [vp, dbl, C.POINTER(Ufs), dp, sz, u64]),
+        "scorus_upload_f32": (ci, [vp, fp, fp]),
+        "scorus_download_f32": (ci, [vp, fp, fp]),
+        "scorus_sample_pt_fixed_f32": (ci, [vp, dp, sz, u32p, fp, u8p, sz, fp, u8p]),
+        "scorus_swap_walkers_fixed_f32": (ci, [vp, dp, sz, u32p, fp, u8p]),
         "scorus_sample_pt_peer_host": (ci, [vp, dp, dp, sz, dbl, C.POINTER(Ufs), dp, sz, u64]),
         "scorus_peer_barrier": (ci, [vp]),
         "scorus_swap_walkers_peer": (ci, [vp, dp, sz]),
@@ -143,7 +149,8 @@ EXPORTS = [
     "scorus_twalk_sample", "scorus_twalk_half_fixed", "scorus_twalk_sample_host", "scorus_twalk_draw_b", "scorus_hmc_sample_ensemble_pt",
     "scorus_hmc_sample_ensemble_pt_fixed", "scorus_hmc_sample_ensemble_pt_host", "scorus_hmc_draw_momenta", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
-    "scorus_sample_pt_peer", "scorus_sample_pt_peer_host", "scorus_peer_barrier", "scorus_swap_walkers_peer", "scorus_peer_read_bandwidth", "scorus_set_matching_blocks", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
+    "scorus_sample_pt_peer", "scorus_upload_f32", "scorus_download_f32", "scorus_sample_pt_fixed_f32", "scorus_swap_walkers_fixed_f32",
+    "scorus_sample_pt_peer_host", "scorus_peer_barrier", "scorus_swap_walkers_peer", "scorus_peer_read_bandwidth", "scorus_set_matching_blocks", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",
     "scorus_get_stats", "scorus_launch_count", "scorus_host_alloc", "scorus_host_free",
 ]

@@ -93,7 +93,11 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     ctx->device = dev;
     ctx->n = cfg->n_walkers;
     ctx->dim = cfg->dim;
-    ctx->pitch = cfg->dim + (cfg->dim & 1u);  // rows are 16-byte multiples for cp.async.bulk
+    ctx->f32 = (cfg->flags & SCORUS_CFG_F32) != 0;
+    if (ctx->f32 && (cfg->flags & SCORUS_CFG_SEQUENTIAL_SUM)) { delete ctx; return SCORUS_ERR_INVALID_ARG; }
+    ctx->elem = ctx->f32 ? 4u : 8u;
+    // rows are 16-byte multiples for cp.async.bulk: 2 doubles or 4 floats
+    ctx->pitch = ctx->f32 ? ((cfg->dim + 3u) & ~3u) : cfg->dim + (cfg->dim & 1u);
     ctx->seed = cfg->seed;
     ctx->n_global = cfg->n_walkers;
     ctx->sequential = (cfg->flags & SCORUS_CFG_SEQUENTIAL_SUM) != 0;
@@ -108,7 +112,7 @@ extern "C" int scorus_ctx_create(scorus_ctx **out, const scorus_cfg *cfg)
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(e, "cudaStreamCreate");
     ctx->stream = ctx->own_stream;
-    size_t ens_bytes = (size_t)ctx->n * ctx->pitch * sizeof(double);
+    size_t ens_bytes = (size_t)ctx->n * ctx->pitch * ctx->elem;
     if ((e = cudaMalloc(&ctx->d_ens, ens_bytes)) != cudaSuccess) return bail(e, "cudaMalloc ensemble");
     // 32 extra slots behind the log-probs: the flag row of the inter-rank barrier (api_shard.cu), reachable by the peers
     // through the same IPC mapping as the log-probs
@@ -134,7 +138,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
+                    ctx->d_beta_f32, ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (auto &e : ctx->beta_cache)
@@ -184,6 +188,7 @@ extern "C" int scorus_sync(scorus_ctx *ctx)
 extern "C" int scorus_device_buffers(scorus_ctx *ctx, double **ens, size_t *pitch, double **lp)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (ens) *ens = ctx->d_ens;
     if (pitch) *pitch = ctx->pitch;
     if (lp) *lp = ctx->d_lp;
@@ -248,6 +253,14 @@ extern "C" int scorus_set_logprob(scorus_ctx *ctx, int kind, const double *param
     if (kind == SCORUS_LP_MIXTURE && nparams != 2 + d)
         return fail(ctx, SCORUS_ERR_INVALID_ARG, "MIXTURE takes 2 + dim params");
     cudaSetDevice(ctx->device);
+    if (ctx->f32) {  // parameters as float on the device (api_f32.cu)
+        const int old = ctx->lp_kind;
+        ctx->lp_kind = kind;
+        int rc32 = f32_set_params(ctx, params, nparams);
+        if (rc32) { ctx->lp_kind = old; return rc32; }
+        ctx->nparams = (uint32_t)nparams;
+        return SCORUS_OK;
+    }
     // dense Gaussian: one extra device-side value after {mu, L} tells the tile kernel that L is upper triangular
     // (a Cholesky-type factor), so that the k loop of column block n0 can start at n0 instead of 0
     const bool corr = kind == SCORUS_LP_CORR_GAUSSIAN;
@@ -279,7 +292,7 @@ int scorus::host::env_int(const char *name, int dflt)
 
 int scorus::host::step_geometry(scorus_ctx *ctx, Geometry *g, bool tile_in_smem)
 {
-    g->row_bytes = ctx->pitch * 8u;
+    g->row_bytes = ctx->pitch * ctx->elem;
     g->row_stride = g->row_bytes;
     if (((g->row_stride / 16u) & 1u) == 0) g->row_stride += 16u;  // odd number of 16-byte units
     g->flag_words = (ctx->dim + 31u) / 32u;
@@ -356,6 +369,7 @@ extern "C" int scorus_init_logprob(scorus_ctx *ctx)
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
     if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
     cudaSetDevice(ctx->device);
+    if (ctx->f32) return f32_init_logprob(ctx);
     Geometry g;
     int rc = step_geometry(ctx, &g, false);
     if (rc) return rc;
@@ -386,6 +400,7 @@ extern "C" int scorus_init_logprob(scorus_ctx *ctx)
 extern "C" int scorus_upload(scorus_ctx *ctx, const double *ens, const double *lp)
 {
     if (!ctx || !ens) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     const size_t rb = (size_t)ctx->dim * sizeof(double);
     CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(double), ens, rb, rb, ctx->n,
@@ -403,6 +418,7 @@ extern "C" int scorus_upload(scorus_ctx *ctx, const double *ens, const double *l
 extern "C" int scorus_download(scorus_ctx *ctx, double *ens, double *lp)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "nothing uploaded");
     cudaSetDevice(ctx->device);
     const size_t rb = (size_t)ctx->dim * sizeof(double);
@@ -646,6 +662,11 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
     if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
     if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1 (empty Uniform range panics in the reference)");
     cudaSetDevice(ctx->device);
+    if (ctx->f32) {
+        if (ctx->mblocks > 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "blocked matchings are not available on an f32 context");
+        if (ctx->tr_ncap != 0 || ctx->mom_rungs != 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "chain capture is not available on an f32 context");
+        return f32_sample_pt(ctx, a, ufs, beta, nbeta, nsteps);
+    }
 
     StepParams p;
     Geometry g;
@@ -745,6 +766,7 @@ extern "C" int scorus_sample_pt_fixed(scorus_ctx *ctx, const double *beta, size_
                                       uint8_t *accepted_out)
 {
     if (!ctx || !beta || !partner || !z || !flags || !u) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     int rc = scorus_check_sample_args(ctx->n, ctx->n, nbeta);
     if (rc) return fail(ctx, rc, "%s", scorus_status_string(rc));
     if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
@@ -816,6 +838,7 @@ __global__ void draw_z_kernel(uint64_t seed, uint64_t step, double inv_sqrt_a, d
 extern "C" int scorus_draw_z(scorus_ctx *ctx, double a, size_t count, double *out)
 {
     if (!ctx || !out || count > ctx->n) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1");
     cudaSetDevice(ctx->device);
     if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, ctx->n * sizeof(double)));
@@ -916,6 +939,7 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
 extern "C" int scorus_swap_walkers(scorus_ctx *ctx, const double *beta, size_t nbeta)
 {
     if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
+    if (ctx->f32) return f32_swap_walkers(ctx, beta, nbeta);
     return swap_impl(ctx, beta, nbeta, nullptr, nullptr, nullptr);
 }
 
@@ -923,6 +947,7 @@ extern "C" int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta, si
                                          const double *r, uint8_t *swapped_out)
 {
     if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (nbeta > 1 && (!jvec || !r)) return SCORUS_ERR_INVALID_ARG;
     return swap_impl(ctx, beta, nbeta, nbeta > 1 ? jvec : nullptr, r, swapped_out);
 }

@@ -37,6 +37,7 @@ extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp,
                                        const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
 {
     if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps); });
 }
 
@@ -48,6 +49,7 @@ extern "C" int scorus_sample_pt_peer_host(scorus_ctx *ctx, double *ens, double *
                                           const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
 {
     if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (lp_len != ctx->n) return fail(ctx, SCORUS_ERR_LENGTH_MISMATCH, "ensemble and logprob lengths differ");
     // the rung arithmetic belongs to the whole ensemble (checked by scorus_sample_pt_peer): only the lengths here
     return host_call(ctx, ens, lp, lp_len, 0, [&] { return scorus_sample_pt_peer(ctx, a, ufs, beta, nbeta, nsteps); });
@@ -58,12 +60,14 @@ extern "C" int scorus_twalk_sample_host(scorus_ctx *ctx, double *ens, double *lp
                                         const scorus_twalk_params *tw, const double *beta, size_t nbeta, uint64_t nsteps)
 {
     if (!ctx || !ens || !lp || !tw) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_twalk_sample(ctx, tw, beta, nbeta, nsteps); });
 }
 
 extern "C" int scorus_sample_pt_host(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
                                      const scorus_ufs *ufs, const double *beta, size_t nbeta)
 {
+    F64_ONLY(ctx);
     return scorus_sample_pt_host_n(ctx, ens, lp, lp_len, a, ufs, beta, nbeta, 1);
 }
 
@@ -71,6 +75,7 @@ extern "C" int scorus_swap_walkers_host(scorus_ctx *ctx, double *ens, double *lp
                                         const double *beta, size_t nbeta)
 {
     if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (nbeta == 0) return SCORUS_ERR_INVALID_ARG;
     if ((ctx->n / nbeta) * nbeta != ctx->n) return fail(ctx, SCORUS_ERR_NWALKERS_MISMATCHES_NBETA, "NWalkersMismatchesNBeta");
     if (lp_len != ctx->n) return SCORUS_OK;  // src/mcmc/utils.rs:88: silently does nothing

@@ -66,6 +66,7 @@ extern "C" int scorus_twalk_sample(scorus_ctx *ctx, const scorus_twalk_params *t
                                    uint64_t nsteps)
 {
     if (!ctx || !tw || !beta) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     TwalkParams tp;
     Geometry g;
     memset(&tp, 0, sizeof(tp));
@@ -113,6 +114,7 @@ extern "C" int scorus_twalk_half_fixed(scorus_ctx *ctx, const scorus_twalk_param
                                        const uint8_t *flags, const double *walk_u, const double *u, uint8_t *accepted_out)
 {
     if (!ctx || !tw || !beta || !order || !kernel || !b || !flags || !walk_u || !u) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (half != 0 && half != 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "half must be 0 or 1");
     TwalkParams tp;
     Geometry g;
@@ -188,6 +190,7 @@ __global__ void twalk_b_kernel(uint64_t seed, uint64_t step, uint32_t w_off, dou
 extern "C" int scorus_twalk_draw_b(scorus_ctx *ctx, double at, uint64_t step, size_t count, double *out)
 {
     if (!ctx || !out || count > ctx->n) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     if (count == 0) return SCORUS_OK;
     if (!ctx->d_z) CU(cudaMalloc(&ctx->d_z, ctx->n * sizeof(double)));
@@ -279,6 +282,7 @@ extern "C" int scorus_hmc_sample_ensemble_pt(scorus_ctx *ctx, double *epsilon, c
                                              const scorus_hmc_param *param, uint64_t *accepted_cnt, uint64_t nsteps)
 {
     if (!ctx || !epsilon || !beta || !param) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     return hmc_impl(ctx, epsilon, beta, nbeta, l, param, nullptr, nullptr, nullptr, nullptr, accepted_cnt, nsteps);
 }
 
@@ -287,6 +291,7 @@ extern "C" int scorus_hmc_sample_ensemble_pt_fixed(scorus_ctx *ctx, double *epsi
                                                    const double *u2, uint8_t *accepted_out, uint64_t *accepted_cnt)
 {
     if (!ctx || !epsilon || !beta || !param || !p0 || !u1 || !u2) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     return hmc_impl(ctx, epsilon, beta, nbeta, l, param, p0, u1, u2, accepted_out, accepted_cnt, 1);
 }
 
@@ -296,6 +301,7 @@ extern "C" int scorus_hmc_sample_ensemble_pt_host(scorus_ctx *ctx, double *q0, d
                                                   uint64_t *accepted_cnt)
 {
     if (!ctx || !q0 || !lp || !epsilon || !beta || !param) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (lp_len != ctx->n) return fail(ctx, SCORUS_ERR_LENGTH_MISMATCH, "assert_eq!(q0.len(), lp.len())");  // :177
     int rc = scorus_upload(ctx, q0, lp);
     if (rc) return rc;
@@ -320,6 +326,7 @@ __global__ void hmc_momenta_kernel(uint64_t seed, uint64_t step, uint32_t w_off,
 extern "C" int scorus_hmc_draw_momenta(scorus_ctx *ctx, uint64_t step, size_t count, double *out)
 {
     if (!ctx || !out || count > ctx->n) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     if (count == 0) return SCORUS_OK;
     int rc = ensure(ctx, (void **)&ctx->d_hmc_p, &ctx->hmc_p_cap, ctx->n * (size_t)ctx->dim * sizeof(double));

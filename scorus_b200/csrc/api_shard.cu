@@ -10,6 +10,7 @@
 extern "C" int scorus_set_shard(scorus_ctx *ctx, uint64_t walker_offset, uint32_t rung_offset, uint64_t n_walkers_global)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (walker_offset + ctx->n > n_walkers_global || n_walkers_global > 0xFFFFFFFFull)
         return fail(ctx, SCORUS_ERR_INVALID_ARG, "shard [%llu, %llu) does not fit in %llu walkers",
                     (unsigned long long)walker_offset, (unsigned long long)(walker_offset + ctx->n),
@@ -192,6 +193,7 @@ extern "C" int scorus_sample_pt_global(scorus_ctx *ctx, double a, const scorus_u
                                        size_t nbeta, const double *ens_all, const double *lp_all)
 {
     if (!ctx || !ufs || !beta || !ens_all || !lp_all) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     StepParams p;
     Geometry g;
     bool all_flags = false;
@@ -212,6 +214,7 @@ extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size
                                        uint32_t *src_all)
 {
     if (!ctx || !beta || !lp_all || !src_all) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     const size_t n = ctx->n_global;
     if (nbeta == 0) return fail(ctx, SCORUS_ERR_INVALID_ARG, "nbeta == 0");
     const size_t npb = n / nbeta;
@@ -247,6 +250,7 @@ extern "C" int scorus_swap_plan_device(scorus_ctx *ctx, const double *beta, size
 extern "C" int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens, void *handle_lp)
 {
     if (!ctx || !handle_ens || !handle_lp) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));  // the barrier flags behind the log-probs are zeroed before a peer can write them
@@ -258,6 +262,7 @@ extern "C" int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens, void *handle
 extern "C" int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_ens, const void *handles_lp)
 {
     if (!ctx || world < 1 || world > 16 || rank < 0 || rank >= world || !handles_ens || !handles_lp)
+    F64_ONLY(ctx);
         return SCORUS_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     const cudaIpcMemHandle_t *he = (const cudaIpcMemHandle_t *)handles_ens, *hl = (const cudaIpcMemHandle_t *)handles_lp;
@@ -320,6 +325,7 @@ extern "C" int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t byte
                                           double *gbps_sm_loads, double *gbps_random_rows)
 {
     if (!ctx || iters < 1) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->d_peer_ens || peer < 0 || peer >= ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     cudaSetDevice(ctx->device);
     const size_t cap = ctx->n * (size_t)ctx->pitch * sizeof(double);
@@ -370,6 +376,7 @@ extern "C" int scorus_peer_read_bandwidth(scorus_ctx *ctx, int peer, size_t byte
 extern "C" int scorus_peer_barrier(scorus_ctx *ctx)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     cudaSetDevice(ctx->device);
     PeerTable t;
@@ -393,6 +400,7 @@ extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs
                                      uint64_t nsteps)
 {
     if (!ctx || !ufs || !beta) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     if (ctx->n_global != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");
     if (ctx->n > (1u << 28)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "at most 2^28 walkers per shard");
@@ -475,6 +483,7 @@ __global__ void __launch_bounds__(256) swap_commit_rows_kernel(const uint32_t *s
 extern "C" int scorus_swap_apply_p2p(scorus_ctx *ctx, const uint32_t *src_all, const double *lp_all, int phase)
 {
     if (!ctx || !src_all || !lp_all) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->d_peer_ens) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     cudaSetDevice(ctx->device);
     if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, ctx->n * (size_t)ctx->pitch * sizeof(double)));
@@ -511,6 +520,7 @@ __global__ void __launch_bounds__(256) gather_lp_kernel(const PeerTable t, uint3
 extern "C" int scorus_swap_walkers_peer(scorus_ctx *ctx, const double *beta, size_t nbeta)
 {
     if (!ctx || !beta) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     const size_t n = ctx->n_global;
     if (n != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");

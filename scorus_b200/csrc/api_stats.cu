@@ -42,6 +42,7 @@ int scorus::host::launch_scatter_download(scorus_ctx *ctx, double *host_ens, dou
 extern "C" int scorus_init_ensemble(scorus_ctx *ctx, const double *lo, const double *hi)
 {
     if (!ctx || !lo || !hi) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     for (uint32_t d = 0; d < ctx->dim; ++d)
         if (!(lo[d] < hi[d])) return fail(ctx, SCORUS_ERR_INVALID_ARG, "empty range in coordinate %u (Uniform::new panics)", d);
     cudaSetDevice(ctx->device);
@@ -96,12 +97,14 @@ static int stats_impl(scorus_ctx *ctx, size_t first, size_t count, double *mean_
 extern "C" int scorus_mean(scorus_ctx *ctx, size_t first, size_t count, double *mean_out)
 {
     if (!ctx || !mean_out) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     return stats_impl(ctx, first, count, mean_out, nullptr);
 }
 
 extern "C" int scorus_cov(scorus_ctx *ctx, size_t first, size_t count, double *cov_out)
 {
     if (!ctx || !cov_out) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     return stats_impl(ctx, first, count, nullptr, cov_out);
 }
 
@@ -109,6 +112,7 @@ extern "C" int scorus_trace_enable(scorus_ctx *ctx, const uint32_t *walkers, con
                                    size_t capacity_steps)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
     void *old[] = {ctx->d_tr_walker, ctx->d_tr_coord, ctx->d_trace};
@@ -135,6 +139,7 @@ extern "C" int scorus_trace_enable(scorus_ctx *ctx, const uint32_t *walkers, con
 extern "C" int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_steps, size_t *nrecorded)
 {
     if (!ctx || !nrecorded) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     size_t k = ctx->tr_count < max_steps ? ctx->tr_count : max_steps;
     if (k && out) CU(cudaMemcpyAsync(out, ctx->d_trace, k * ctx->tr_ncap * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -147,6 +152,7 @@ extern "C" int scorus_trace_download(scorus_ctx *ctx, double *out, size_t max_st
 extern "C" int scorus_trace_stride(scorus_ctx *ctx, uint64_t every)
 {
     if (!ctx || every == 0) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     ctx->tr_every = every;
     ctx->tr_tick = 0;
     return SCORUS_OK;
@@ -194,6 +200,7 @@ static uint32_t moment_blocks(const scorus_ctx *ctx, uint64_t npb, uint32_t rung
 extern "C" int scorus_moments_enable(scorus_ctx *ctx, size_t nrungs, uint64_t every, int with_cov)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_mom) { cudaFree(ctx->d_mom); ctx->d_mom = nullptr; }
@@ -248,6 +255,7 @@ static int accumulate_moments(scorus_ctx *ctx)
 extern "C" int scorus_moments_download(scorus_ctx *ctx, size_t rung, double *mean_out, double *cov_out, uint64_t *nsamples)
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->mom_rungs) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_moments_enable first");
     if (rung >= ctx->mom_rungs) return fail(ctx, SCORUS_ERR_INVALID_ARG, "rung %zu of %u", rung, ctx->mom_rungs);
     if (cov_out && !ctx->mom_cov) return fail(ctx, SCORUS_ERR_INVALID_ARG, "moments were enabled without the covariance");
@@ -276,6 +284,7 @@ extern "C" int scorus_trace_iat(scorus_ctx *ctx, double c_window, size_t max_lag
                                 double *mean_out, double *var_out)
 {
     if (!ctx || !tau_out) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     if (!ctx->tr_ncap) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_trace_enable first");
     const size_t T = ctx->tr_count, C = ctx->tr_ncap;
     if (T < 2) return fail(ctx, SCORUS_ERR_INVALID_ARG, "need at least two recorded steps");

@@ -94,6 +94,10 @@ struct scorus_ctx {
     bool uploaded = false;
     bool sequential = false;  // SCORUS_CFG_SEQUENTIAL_SUM
     bool f32 = false;         // SCORUS_CFG_F32: d_ens / d_lp hold float, kernels of namespace scorus::f32 (api_f32.cu)
+    uint32_t elem = 8;        // bytes per coordinate
+    float *d_beta_f32 = nullptr; size_t beta_f32_cap = 0;   // f32 contexts: the beta list as float
+    std::vector<float> beta_f32_host;
+    std::vector<double> beta_f32_src;
     std::string err;
 };
 

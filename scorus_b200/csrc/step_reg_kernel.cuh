@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                                 if (j == G - 1) { nba = wa0; nbb = wb0; }
                             }
                         }
-                        if (c < nvec) {
+                        if (c < nvec && d < p.dim) {  // (f32 rows are padded to 4 coordinates: a chunk can be all padding)
                             const bool has1 = d + 1u < p.dim, hasnb = d + 2u < p.dim;
                             plug.terms(d, ya[it].x, ya[it].y, nba, has1, hasnb, pa);
                             plug.terms(d, yb[it].x, yb[it].y, nbb, has1, hasnb, pb);

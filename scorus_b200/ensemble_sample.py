@@ -169,26 +169,38 @@ def _dp(a: Optional[np.ndarray]):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 
 
-def _check_arrays(ensemble: np.ndarray, logprob: Optional[np.ndarray]):
-    if not (isinstance(ensemble, np.ndarray) and ensemble.dtype == np.float64 and ensemble.ndim == 2
+def _check_arrays(ensemble: np.ndarray, logprob: Optional[np.ndarray], dtype=np.float64):
+    name = np.dtype(dtype).name
+    if not (isinstance(ensemble, np.ndarray) and ensemble.dtype == dtype and ensemble.ndim == 2
             and ensemble.flags.c_contiguous):
-        raise TypeError("ensemble must be a C-contiguous float64 array [n_walkers, dim]")
-    if logprob is not None and not (isinstance(logprob, np.ndarray) and logprob.dtype == np.float64
+        raise TypeError(f"ensemble must be a C-contiguous {name} array [n_walkers, dim]")
+    if logprob is not None and not (isinstance(logprob, np.ndarray) and logprob.dtype == dtype
                                     and logprob.ndim == 1 and logprob.flags.c_contiguous):
-        raise TypeError("logprob must be a C-contiguous float64 array [n_walkers]")
+        raise TypeError(f"logprob must be a C-contiguous {name} array [n_walkers]")
+
+
+def _fp(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
 
 
 class Sampler:
     """RAII handle over scorus_ctx: the device-resident (ensemble, logprob) plus RNG counters."""
 
     def __init__(self, flogprob: LogProb, n_walkers: int, dim: int, seed: int = 0, device: int = -1,
-                 sequential_sum: bool = False):
+                 sequential_sum: bool = False, dtype=np.float64):
         """sequential_sum=True selects SCORUS_CFG_SEQUENTIAL_SUM: one lane per walker, log-density
-        summed left to right like the reference closures (bit-identical log-probs, ~2x slower)."""
+        summed left to right like the reference closures (bit-identical log-probs, ~2x slower).
+        dtype=np.float32 selects SCORUS_CFG_F32 (`T = f32`, ensemble_sample.rs:95): upload / download /
+        sample_pt_fixed / swap_walkers_fixed then take float32 arrays; sample, sample_pt, swap_walkers and
+        init_logprob are the same calls."""
         self._lib = L.load()
         self._ctx = C.c_void_p()
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("dtype must be float64 or float32")
+        self.f32 = self.dtype == np.dtype(np.float32)
         cfg = L.Cfg(n_walkers=n_walkers, dim=dim, device=device, seed=seed,
-                    flags=L.CFG_SEQUENTIAL_SUM if sequential_sum else 0, reserved=0)
+                    flags=(L.CFG_SEQUENTIAL_SUM if sequential_sum else 0) | (L.CFG_F32 if self.f32 else 0), reserved=0)
         _raise(self._lib.scorus_ctx_create(C.byref(self._ctx), C.byref(cfg)))
         self.n, self.dim, self.seed = n_walkers, dim, seed
         self.flogprob = None
@@ -232,27 +244,36 @@ class Sampler:
 
     # -- data movement
     def upload(self, ensemble: np.ndarray, logprob: Optional[np.ndarray] = None):
-        _check_arrays(ensemble, logprob)
+        _check_arrays(ensemble, logprob, self.dtype)
         if ensemble.shape != (self.n, self.dim):
             raise ValueError("ensemble shape does not match the sampler")
         if logprob is not None and logprob.shape[0] != self.n:
             raise AssertionError("ensemble and logprob lengths differ")
-        self._ok(self._lib.scorus_upload(self._ctx, _dp(ensemble), _dp(logprob)))
+        if self.f32:
+            self._ok(self._lib.scorus_upload_f32(self._ctx, _fp(ensemble), _fp(logprob)))
+        else:
+            self._ok(self._lib.scorus_upload(self._ctx, _dp(ensemble), _dp(logprob)))
         self._ok(self._lib.scorus_sync(self._ctx))
 
     def download(self, ensemble: Optional[np.ndarray] = None, logprob: Optional[np.ndarray] = None):
         if ensemble is None:
-            ensemble = np.empty((self.n, self.dim))
+            ensemble = np.empty((self.n, self.dim), dtype=self.dtype)
         if logprob is None:
-            logprob = np.empty(self.n)
-        _check_arrays(ensemble, logprob)
-        self._ok(self._lib.scorus_download(self._ctx, _dp(ensemble), _dp(logprob)))
+            logprob = np.empty(self.n, dtype=self.dtype)
+        _check_arrays(ensemble, logprob, self.dtype)
+        if self.f32:
+            self._ok(self._lib.scorus_download_f32(self._ctx, _fp(ensemble), _fp(logprob)))
+        else:
+            self._ok(self._lib.scorus_download(self._ctx, _dp(ensemble), _dp(logprob)))
         return ensemble, logprob
 
     def download_logprob(self) -> np.ndarray:
-        """Only the cached log-probs (8 bytes per walker): scorus_download with a NULL ensemble."""
-        lp = np.empty(self.n)
-        self._ok(self._lib.scorus_download(self._ctx, None, _dp(lp)))
+        """Only the cached log-probs (one scalar per walker): scorus_download with a NULL ensemble."""
+        lp = np.empty(self.n, dtype=self.dtype)
+        if self.f32:
+            self._ok(self._lib.scorus_download_f32(self._ctx, None, _fp(lp)))
+        else:
+            self._ok(self._lib.scorus_download(self._ctx, None, _dp(lp)))
         return lp
 
     # -- the hot path
@@ -275,13 +296,19 @@ class Sampler:
     def sample_pt_fixed(self, beta_list, partner, z, flags, u):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         partner = np.ascontiguousarray(partner, dtype=np.uint32)
-        z = np.ascontiguousarray(z, dtype=np.float64)
-        u = np.ascontiguousarray(u, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=self.dtype)
+        u = np.ascontiguousarray(u, dtype=self.dtype)
         flags = np.ascontiguousarray(flags, dtype=np.uint8)
         if partner.shape != (self.n,) or z.shape != (self.n,) or u.shape != (self.n,) or flags.shape[0] != self.n:
             raise ValueError("stream arrays must have one entry per walker")
         flag_len = flags.shape[1] if flags.ndim == 2 else self.dim
         acc = np.zeros(self.n, dtype=np.uint8)
+        if self.f32:
+            self._ok(self._lib.scorus_sample_pt_fixed_f32(
+                self._ctx, _dp(beta), beta.size, partner.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(z),
+                flags.ctypes.data_as(C.POINTER(C.c_uint8)), flag_len, _fp(u),
+                acc.ctypes.data_as(C.POINTER(C.c_uint8))))
+            return acc
         self._ok(self._lib.scorus_sample_pt_fixed(
             self._ctx, _dp(beta), beta.size, partner.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(z),
             flags.ctypes.data_as(C.POINTER(C.c_uint8)), flag_len, _dp(u),
@@ -300,8 +327,13 @@ class Sampler:
     def swap_walkers_fixed(self, beta_list, jvec, r):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         jvec = np.ascontiguousarray(jvec, dtype=np.uint32)
-        r = np.ascontiguousarray(r, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=self.dtype)
         sw = np.zeros(max(jvec.size, 1), dtype=np.uint8)
+        if self.f32:
+            self._ok(self._lib.scorus_swap_walkers_fixed_f32(
+                self._ctx, _dp(beta), beta.size, jvec.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(r),
+                sw.ctypes.data_as(C.POINTER(C.c_uint8))))
+            return sw[:jvec.size].reshape(jvec.shape)
         self._ok(self._lib.scorus_swap_walkers_fixed(
             self._ctx, _dp(beta), beta.size, jvec.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(r),
             sw.ctypes.data_as(C.POINTER(C.c_uint8))))
