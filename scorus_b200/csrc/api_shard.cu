@@ -262,8 +262,8 @@ extern "C" int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens, void *handle
 extern "C" int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_ens, const void *handles_lp)
 {
     if (!ctx || world < 1 || world > 16 || rank < 0 || rank >= world || !handles_ens || !handles_lp)
-    F64_ONLY(ctx);
         return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
     const cudaIpcMemHandle_t *he = (const cudaIpcMemHandle_t *)handles_ens, *hl = (const cudaIpcMemHandle_t *)handles_lp;
     for (int q = 0; q < world; ++q) {
