@@ -177,8 +177,9 @@ def cpu_reference_leg(wl, steps, warmup, sample_walkers=None, target_seconds=12.
         tf = po.flat_threaded_run(kind, params, e2, l2, beta, 2.0, ukind, prob, 13, 1, kf, cores)
         if tf > 0:
             flat = {"value": n_s * kf / tf, "unit": "walker-steps/s", "cores": cores, "steps": kf,
-                    "note": "flat buffers, all stages threaded (oracle/ref_structure_bench.c: orc_flat_threaded_run): what a "
-                            "CPU rewrite could do, not what the reference does"}
+                    "note": "flat buffers, all stages threaded including the counter-based stream generation "
+                            "(oracle/ref_structure_bench.c: orc_flat_threaded_run): what a CPU rewrite could do, not what the "
+                            "reference does"}
     return {
         "value": value, "unit": "walker-steps/s", "cores": cores, "kind": "port",
         "sample": f"{k} steps of the first {n_s} walkers ({nb_s} rung(s)) of {desc}; reference-structured C port "

@@ -163,7 +163,12 @@ int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta_list, size_t n
 
 /* The literal drop-in for the reference's `&mut [V]`, `&mut [T]` call shape: host buffers in,
  * one sample_pt step, host buffers out (upload + step + download on the context's stream).
- * logprob_len is cached_logprob.len() (checked like ensemble_sample.rs:133). */
+ * logprob_len is cached_logprob.len() (checked like ensemble_sample.rs:133).
+ * This per-step form exists for parity with the reference's call sites, not for speed: every call is a PCIe round
+ * trip plus a synchronise (~50 us even for the 16 walkers of examples/test_emcee.rs, where the reference's own CPU
+ * step takes 3 us; PCIe-bound at 2^22 walkers).  Drivers should use scorus_sample_pt_host_n with the number of steps
+ * between two recorded samples, or keep the ensemble on the device (scorus_upload once, scorus_sample_pt with nsteps,
+ * scorus_trace_* / scorus_moments_* for the recording): a one-block ensemble then runs all nsteps in ONE launch. */
 int scorus_sample_pt_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
                           double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
 /* The same with nsteps steps between the upload and the download: what a driver that records every

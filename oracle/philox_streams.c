@@ -250,6 +250,58 @@ int orc_philox_sample_streams_ex(uint64_t seed, uint64_t step, size_t n, size_t 
     return ORC_OK;
 }
 
+/* The same streams by RANGES, so that a threaded caller (the flat CPU baseline, ref_structure_bench.c) can generate
+ * them on all cores: partners of the matching positions [pos_lo, pos_hi) (even bounds; large rungs only -- the keyed
+ * bijection is a pure function of the position), and z / flags / u of the walkers [w_lo, w_hi). */
+int orc_philox_partner_range(uint64_t seed, uint64_t step, size_t n, size_t nbeta, size_t pos_lo, size_t pos_hi,
+                             uint32_t *partner)
+{
+    const size_t npb = n / nbeta;
+    if (npb <= EXACT_SHUFFLE_MAX || (pos_lo & 1) || (pos_hi & 1)) return ORC_ERR_INVALID_ARG;
+    size_t r_cur = (size_t)-1;
+    uint32_t k[8];
+    for (size_t j = pos_lo; j < pos_hi; j += 2) {
+        const size_t r = j / npb;
+        if (r != r_cur) {
+            draw(seed, step, ST_PERM, (uint32_t)r, 0, k);
+            draw(seed, step, ST_PERM, (uint32_t)r, 1, k + 4);
+            r_cur = r;
+        }
+        const uint32_t wa = (uint32_t)(r * npb) + bij((uint32_t)(j - r * npb), (uint32_t)npb, k);
+        const uint32_t wb = (uint32_t)(r * npb) + bij((uint32_t)(j + 1 - r * npb), (uint32_t)npb, k);
+        partner[wa] = wb;
+        partner[wb] = wa;
+    }
+    return ORC_OK;
+}
+
+int orc_philox_walker_range(uint64_t seed, uint64_t step, size_t dim, double a, int ufs_kind, double prob,
+                            uint64_t onehot_counter, size_t w_lo, size_t w_hi, double *z, uint8_t *flags, double *u)
+{
+    const double sqrt_a = sqrt(a), inv_sqrt_a = 1.0 / sqrt_a, range = 2.0 * (sqrt_a - inv_sqrt_a);
+    const uint32_t bpf = ufs_kind == ORC_UFS_PROB ? flag_bits(fmin(prob, 1.0)) : 1;
+    const uint64_t thr = ufs_kind == ORC_UFS_PROB ? flag_threshold(prob, bpf) : 0;
+    if (ufs_kind == ORC_UFS_PROB && !(prob > 0.0)) return ORC_ERR_INVALID_ARG;
+    for (size_t i = w_lo; i < w_hi; ++i) {
+        uint32_t o[4];
+        draw(seed, step, ST_ZU, (uint32_t)i, 0, o);
+        const double p = u53(o[0], o[1]) * range, y = inv_sqrt_a + p / 2.0;
+        z[i] = y * y;
+        u[i] = u53(o[2], o[3]);
+        if (ufs_kind == ORC_UFS_ALL) {
+            memset(flags + i * dim, 1, dim);
+        } else if (ufs_kind == ORC_UFS_ONE_HOT_CYCLE) {
+            const size_t hot = (size_t)((onehot_counter + 1 + i) % dim);
+            for (size_t d = 0; d < dim; ++d) flags[i * dim + d] = (d == hot);
+        } else if (ufs_kind == ORC_UFS_PROB) {
+            prob_flags(seed, step, (uint32_t)i, dim, bpf, thr, flags + i * dim);
+        } else {
+            return ORC_ERR_INVALID_ARG;
+        }
+    }
+    return ORC_OK;
+}
+
 int orc_philox_sample_streams(uint64_t seed, uint64_t step, size_t n, size_t dim, size_t nbeta,
                               double a, int ufs_kind, double prob, uint64_t onehot_counter,
                               uint32_t *partner, double *z, uint8_t *flags, double *u)

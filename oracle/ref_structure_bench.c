@@ -267,6 +267,22 @@ static void flat_accept_range(size_t lo, size_t hi, void *c)
     }
 }
 
+typedef struct {
+    uint64_t seed, step, onehot; size_t n, dim, nbeta; double a; int ufs_kind; double prob;
+    uint32_t *partner; double *z, *u; uint8_t *flags; int rc;
+} stream_ctx;
+static void stream_partner_range(size_t lo, size_t hi, void *c)
+{
+    stream_ctx *k = (stream_ctx *)c;  /* lo, hi count PAIRS */
+    if (orc_philox_partner_range(k->seed, k->step, k->n, k->nbeta, 2 * lo, 2 * hi, k->partner)) k->rc = 1;
+}
+static void stream_walker_range(size_t lo, size_t hi, void *c)
+{
+    stream_ctx *k = (stream_ctx *)c;
+    if (orc_philox_walker_range(k->seed, k->step, k->dim, k->a, k->ufs_kind, k->prob, k->onehot, lo, hi, k->z, k->flags, k->u))
+        k->rc = 1;
+}
+
 double orc_flat_threaded_run(int kind, const double *params, size_t nparams, double *ens,
                              double *lp, size_t n, size_t dim, const double *beta, size_t nbeta,
                              double a, int ufs_kind, double prob, uint64_t seed,
@@ -284,10 +300,15 @@ double orc_flat_threaded_run(int kind, const double *params, size_t nparams, dou
     uint64_t onehot = 0;
     double t0 = now_s();
     for (size_t s = 0; s < nsteps; ++s) {
-        /* stream generation is serial here only because orc_philox_sample_streams is; it is
-         * counter-based, so it is timed but could itself be threaded */
-        if (orc_philox_sample_streams(seed, first_step + s, n, dim, nbeta, a, ufs_kind, prob, onehot,
-                                      partner, z, flags, u)) { t0 = now_s() + 1.0; break; }
+        /* the streams are counter-based: generated on all threads too (large rungs; rungs of up to 1024 walkers are
+         * shuffled exactly by a sort per rung and stay serial) */
+        if (npb > 1024) {
+            stream_ctx sc = {seed, first_step + s, onehot, n, dim, nbeta, a, ufs_kind, prob, partner, z, u, flags, 0};
+            parallel_for(n / 2, 4096, nthreads, stream_partner_range, &sc);
+            parallel_for(n, 1024, nthreads, stream_walker_range, &sc);
+            if (sc.rc) { t0 = now_s() + 1.0; break; }
+        } else if (orc_philox_sample_streams(seed, first_step + s, n, dim, nbeta, a, ufs_kind, prob, onehot,
+                                             partner, z, flags, u)) { t0 = now_s() + 1.0; break; }
         onehot = (onehot + n) % dim;
         flat_ctx fc = {kind, params, nparams, dim, npb, ens, lp, beta, partner, z, u, flags, prop, nlp};
         parallel_for(n, 1024, nthreads, flat_propose_range, &fc);
