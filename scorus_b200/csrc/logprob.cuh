@@ -420,36 +420,21 @@ struct LpCorrGaussian {
         for (int ng = 0; ng < NA; ++ng)
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) c[ng][mt][0] = c[ng][mt][1] = 0.0;
-        // columns n0.. of W only see L[n][k] with k >= n0 when L is upper triangular (n0 is a multiple of 8).
-        // Software pipeline: the fragments of k-step k0 + 4 are loaded (4 LDS for A, NA LDG for B, mu) before the
-        // 4 NA DMMAs of k-step k0 are issued, so that the tensor pipe does not sit out the load latency at the top
-        // of every k-step (it did: DMMA pipe 30 % active, long_scoreboard 4.2 per issue, profiles/r1_c2_*).
-        auto load_frags = [&](uint32_t k0, double (&a)[4], double (&b)[NA]) {
+        // columns n0.. of W only see L[n][k] with k >= n0 when L is upper triangular (n0 is a multiple of 8)
+        for (uint32_t k0 = upper ? n0 : 0u; k0 < dim; k0 += 4) {
             const uint32_t k = k0 + t;
             const bool kin = k < dim;
             const double mu_k = kin ? __ldg(mu + k) : 0.0;
+            double a[4];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) a[mt] = kin ? rows[mt][k] - mu_k : 0.0;
 #pragma unroll
             for (int ng = 0; ng < NA; ++ng) {
                 const uint32_t n = n0 + 8u * ng + g;  // W column = row of L:  B[k][n] = L[n][k]
-                b[ng] = (kin && n < dim) ? __ldg(L + (size_t)n * dim + k) : 0.0;
+                const double b = (kin && n < dim) ? __ldg(L + (size_t)n * dim + k) : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma_m8n8k4(c[ng][mt], a[mt], b);
             }
-        };
-        const uint32_t kbeg = upper ? n0 : 0u;
-        double a_cur[4], b_cur[NA];
-        load_frags(kbeg, a_cur, b_cur);
-        for (uint32_t k0 = kbeg; k0 < dim; k0 += 4) {
-            double a_nxt[4], b_nxt[NA];
-            load_frags(k0 + 4u, a_nxt, b_nxt);  // beyond dim: zeros, no loads
-#pragma unroll
-            for (int ng = 0; ng < NA; ++ng)
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) dmma_m8n8k4(c[ng][mt], a_cur[mt], b_cur[ng]);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) a_cur[mt] = a_nxt[mt];
-#pragma unroll
-            for (int ng = 0; ng < NA; ++ng) b_cur[ng] = b_nxt[ng];
         }
 #pragma unroll
         for (int ng = 0; ng < NA; ++ng)
