@@ -321,12 +321,12 @@ int scorus::host::step_geometry(scorus_ctx *ctx, Geometry *g, bool tile_in_smem)
         const bool dense = ctx->lp_kind == SCORUS_LP_CORR_GAUSSIAN;
         const uint32_t nvec = ctx->pitch / 2;
         // mirrors reg_kernel_direct (step_reg_kernel.cuh): rows of 9..16 double2 (16-lane groups) keep the tile
-        const bool tiled = tile_in_smem || dense || (nvec > 8 && nvec <= 16);
+        const bool tiled = tile_in_smem || dense || (!SCORUS_G16_DIRECT && nvec > 8 && nvec <= 16);
         const size_t per_warp = (tiled ? tile : 0) + flag_bytes;
         const size_t l1_keep = tiled ? (size_t)env_int("SCORUS_L1_KB", 32) * 1024u : 0;
         // mirrors reg_kernel_max_warps / twalk_max_warps (step_reg_kernel.cuh): dense plugin 8, the t-walk's tile kernel
         // 16, the stretch kernels SCORUS_REG_WARPS
-        uint32_t w = dense ? 8 : (tile_in_smem ? 16 : (nvec > 16 && nvec <= 64 ? SCORUS_REG_WARPS_WIDE : SCORUS_REG_WARPS));
+        uint32_t w = dense ? 8 : (tile_in_smem ? 16 : (nvec > (SCORUS_G16_WIDE ? 8u : 16u) && nvec <= 64 ? SCORUS_REG_WARPS_WIDE : SCORUS_REG_WARPS));
         while (w >= 1 && w * per_warp > budget) --w;
         while (w > 8 && w * per_warp + l1_keep > budget) --w;
         if (w == 0) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "dim %u: a 32-walker tile does not fit in %d bytes of shared memory", ctx->dim, ctx->smem_optin);

@@ -417,7 +417,7 @@ extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs
         // keeps its proposals in registers: 16 rows + 8 mbarriers per warp on top of the flag words
         {
             const uint32_t nvec = ctx->pitch / 2;
-            const bool direct = ctx->lp_kind != SCORUS_LP_CORR_GAUSSIAN && !(nvec > 8 && nvec <= 16);
+            const bool direct = ctx->lp_kind != SCORUS_LP_CORR_GAUSSIAN && (SCORUS_G16_DIRECT || !(nvec > 8 && nvec <= 16));
             if (direct && env_int("SCORUS_PEER_STAGE", 1)) {
                 const size_t base = g.smem / g.warps, extra = 16u * (size_t)g.row_stride + 128u;
                 uint32_t w = g.warps;

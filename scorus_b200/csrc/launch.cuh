@@ -13,6 +13,13 @@
 #define SCORUS_REG_WARPS_WIDE 20
 #define SCORUS_REG_ROWS 8
 #define SCORUS_REG_WARPS 16
+// rows of 9..16 double2 (16 lanes per row, tile mode): 1 = the wide shape (4 rows per block, 20 warps) for them too
+#ifndef SCORUS_G16_DIRECT
+#define SCORUS_G16_DIRECT 0
+#endif
+#ifndef SCORUS_G16_WIDE
+#define SCORUS_G16_WIDE 1
+#endif
 
 namespace scorus {
 

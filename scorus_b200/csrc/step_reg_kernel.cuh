@@ -34,7 +34,7 @@ namespace scorus {
 
 template <int G, int ITERS>
 struct RegGeom {
-    static constexpr int kRows = (G == 32 && ITERS <= 2) ? SCORUS_REG_ROWS_WIDE : SCORUS_REG_ROWS;
+    static constexpr int kRows = ((G == 32 && ITERS <= 2) || (G == 16 && SCORUS_G16_WIDE)) ? SCORUS_REG_ROWS_WIDE : SCORUS_REG_ROWS;
     static constexpr int kRowsPerBlock = (G < kRows / ITERS) ? G : (kRows / ITERS < 2 ? 2 : kRows / ITERS);  // GB
     static constexpr int kPairs = kRowsPerBlock / 2;
     static constexpr int kBlocks = G / kRowsPerBlock;
@@ -59,7 +59,7 @@ struct RegGeom {
 template <class Plugin, int G, int ITERS>
 constexpr int reg_kernel_max_warps()
 {
-    return Plugin::kMaxWarps == 14 ? ((G == 32 && ITERS <= 2) ? SCORUS_REG_WARPS_WIDE : SCORUS_REG_WARPS) : Plugin::kMaxWarps;
+    return Plugin::kMaxWarps == 14 ? (((G == 32 && ITERS <= 2) || (G == 16 && SCORUS_G16_WIDE)) ? SCORUS_REG_WARPS_WIDE : SCORUS_REG_WARPS) : Plugin::kMaxWarps;
 }
 
 // the t-walk kernels (twalk_kernel.cuh, twalk_direct_kernel.cuh) keep 16 warps: they need up to 128 registers
@@ -72,7 +72,7 @@ constexpr int twalk_max_warps()
 template <class Plugin, int G>
 __host__ __device__ constexpr bool reg_kernel_direct()
 {
-    return !Plugin::kNeedsRow && G != 16;
+    return !Plugin::kNeedsRow && (G != 16 || SCORUS_G16_DIRECT);
 }
 
 template <class Plugin, int G, int ITERS, int kPeer = 0>
