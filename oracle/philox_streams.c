@@ -141,8 +141,34 @@ static void pairing_order(uint64_t seed, uint64_t step, size_t n, size_t nbeta, 
 
 /* Prob(p) flags of walker w at `step` into f[dim] (the device's gen_flags_prob, tile_common.cuh): bpf bits per
  * coordinate, flag = value < thr, redrawn until one is set; bounded by MAX_FLAG_ATTEMPTS */
-static void prob_flags(uint64_t seed, uint64_t step, uint32_t w, size_t dim, uint32_t bpf, uint64_t thr, uint8_t *f)
+/* 32 bits per coordinate (a p that is not a multiple of 2^-16): no redraw loop (gen_flags_first, tile_common.cuh).  The
+ * position J of the first set flag given that one is set is truncated-geometric; it is read off 32-bit thresholds
+ * cdf[j] = (1 - (1-p)^(j+1)) / (1 - (1-p)^D) * 2^32 with the random word of coordinate 0; coordinates before J are clear,
+ * J is set, the ones after J are iid Bernoulli from their own words. */
+static void prob_flags_first(uint64_t seed, uint64_t step, uint32_t w, size_t dim, double prob, uint64_t thr, uint8_t *f)
 {
+    const double q = fmin(prob, 1.0), lq = log1p(-q), den = expm1((double)dim * lq);
+    uint32_t o[4];
+    draw(seed, step, ST_FLAGS, w, 0, o);
+    size_t J = 0;
+    while (J + 1 < dim) {
+        const double t = expm1((double)(J + 1) * lq) / den * 4294967296.0;
+        const long long v = llrint(t);
+        const uint32_t c = v < 0 ? 0u : (v > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)v);
+        if (o[0] >= c) ++J;
+        else break;
+    }
+    const uint32_t thr32 = thr > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr;
+    for (size_t d = 0; d < dim; ++d) {
+        if (d % 4 == 0 && d) draw(seed, step, ST_FLAGS, w, (uint32_t)(d / 4), o);
+        f[d] = d < J ? 0 : (d == J ? 1 : (uint8_t)(o[d % 4] < thr32));
+    }
+}
+
+static void prob_flags(uint64_t seed, uint64_t step, uint32_t w, size_t dim, double prob, uint32_t bpf, uint64_t thr,
+                       uint8_t *f)
+{
+    if (bpf == 32) { prob_flags_first(seed, step, w, dim, prob, thr, f); return; }
     const uint32_t fpc = 128 / bpf;
     const uint32_t nblk = (uint32_t)((dim + fpc - 1) / fpc);
     const uint64_t vmask = bpf == 32 ? 0xFFFFFFFFull : ((1ull << bpf) - 1);
@@ -243,7 +269,7 @@ int orc_philox_sample_streams_ex(uint64_t seed, uint64_t step, size_t n, size_t 
         const uint32_t bpf = flag_bits(fmin(prob, 1.0));
         const uint64_t thr = flag_threshold(prob, bpf);
         for (size_t i = 0; i < m; ++i)
-            prob_flags(seed, step, walkers ? walkers[i] : (uint32_t)i, dim, bpf, thr, flags + i * dim);
+            prob_flags(seed, step, walkers ? walkers[i] : (uint32_t)i, dim, prob, bpf, thr, flags + i * dim);
     } else {
         return ORC_ERR_INVALID_ARG;
     }
@@ -294,7 +320,7 @@ int orc_philox_walker_range(uint64_t seed, uint64_t step, size_t dim, double a, 
             const size_t hot = (size_t)((onehot_counter + 1 + i) % dim);
             for (size_t d = 0; d < dim; ++d) flags[i * dim + d] = (d == hot);
         } else if (ufs_kind == ORC_UFS_PROB) {
-            prob_flags(seed, step, (uint32_t)i, dim, bpf, thr, flags + i * dim);
+            prob_flags(seed, step, (uint32_t)i, dim, prob, bpf, thr, flags + i * dim);
         } else {
             return ORC_ERR_INVALID_ARG;
         }
@@ -388,7 +414,7 @@ int orc_philox_twalk_streams(uint64_t seed, uint64_t step, uint64_t order_step, 
             draw(seed, step, ST_TW_B, w, 0, o);
             b[k] = orc_twalk_b_from_uniforms(u53(o[0], o[1]), u53(o[2], o[3]), tw->at);
         }
-        prob_flags(seed, step, w, dim, bpf, thr, flags + k * dim);
+        prob_flags(seed, step, w, dim, tw->pphi, bpf, thr, flags + k * dim);
         for (size_t d = 0; d < dim; d += 2) {
             draw(seed, step, ST_TW_WALK, w, (uint32_t)(d / 2), o);
             walk_u[k * dim + d] = u53(o[0], o[1]);

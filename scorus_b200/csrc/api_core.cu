@@ -138,7 +138,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_beta_f32, ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
+                    ctx->d_beta_f32, ctx->d_flag_cdf, ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (auto &e : ctx->beta_cache)
@@ -525,6 +525,26 @@ int scorus::host::set_prob_flags(scorus_ctx *ctx, StepParams *p, double prob)
     p->flag_bits = flag_bits_for(q);
     p->flag_thr = p->flag_bits == 32 ? (uint64_t)llrint(q * 4294967296.0) : (uint64_t)(q * (double)(1u << p->flag_bits));
     if (p->flag_thr == 0) p->flag_thr = 1;
+    p->flag_cdf = nullptr;
+    if (p->flag_bits == 32) {
+        // thresholds of the first set flag's position (tile_common.cuh: gen_flags_first), cached per (p, dim):
+        // cdf[j] = (1 - (1-p)^(j+1)) / (1 - (1-p)^D) in 32-bit fixed point, via expm1 / log1p so that a tiny p keeps its digits
+        if (ctx->flag_cdf_prob != q || !ctx->d_flag_cdf) {
+            const uint32_t D = ctx->dim;
+            std::vector<uint32_t> cdf(D);
+            const double lq = log1p(-q), den = expm1((double)D * lq);
+            for (uint32_t j = 0; j < D; ++j) {
+                const double t = expm1((double)(j + 1u) * lq) / den * 4294967296.0;
+                const long long v = llrint(t);
+                cdf[j] = v < 0 ? 0u : (v > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)v);
+            }
+            if (!ctx->d_flag_cdf) CU(cudaMalloc(&ctx->d_flag_cdf, D * sizeof(uint32_t)));
+            CU(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the old table
+            CU(cudaMemcpy(ctx->d_flag_cdf, cdf.data(), D * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            ctx->flag_cdf_prob = q;
+        }
+        p->flag_cdf = ctx->d_flag_cdf;
+    }
     return SCORUS_OK;
 }
 

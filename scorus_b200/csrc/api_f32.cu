@@ -168,7 +168,7 @@ int scorus::host::f32_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
     case SCORUS_UFS_PROB: {
         StepParams q;  // the threshold is the same quantisation of p for both scalar types
         if ((rc = set_prob_flags(ctx, &q, ufs->prob))) return rc;
-        p.flag_bits = q.flag_bits; p.flag_thr = q.flag_thr;
+        p.flag_bits = q.flag_bits; p.flag_thr = q.flag_thr; p.flag_cdf = q.flag_cdf;
         break;
     }
     case SCORUS_UFS_ONE_HOT_CYCLE: break;

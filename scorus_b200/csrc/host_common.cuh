@@ -72,6 +72,7 @@ struct scorus_ctx {
     // scratch for caller-supplied streams
     double *d_z = nullptr, *d_u = nullptr;
     uint8_t *d_flags = nullptr; size_t flags_cap = 0;
+    uint32_t *d_flag_cdf = nullptr; double flag_cdf_prob = -1.0;  // Prob(p) at 32 bits: thresholds of the first set flag
     uint8_t *d_acc = nullptr;
     uint8_t *d_dirty = nullptr;     // host-buffer call: walkers accepted since the upload
     unsigned long long *d_tile_counter = nullptr;  // dynamic tile scheduling of the register kernel

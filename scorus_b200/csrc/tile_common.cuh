@@ -24,6 +24,9 @@ struct StepParams {
     unsigned long long *stats;  // [0] accepted, [1] proposed
     uint64_t seed, step, onehot;
     uint64_t flag_thr;      // Bernoulli threshold on flag_bits random bits
+    // flag_bits == 32 (a p that is not a multiple of 2^-16): [dim] 32-bit thresholds of the position of the FIRST set
+    // flag given that one is set, cdf[j] = P(first <= j | any) * 2^32 (gen_flags_first below); device memory
+    const uint32_t *flag_cdf;
     double inv_sqrt_a, z_range;
     uint32_t n, npb, dim, pitch, nbeta, nparams;
     uint32_t flag_len, flag_bits, flag_kind;  // flag_kind: SCORUS_UFS_*
@@ -212,6 +215,49 @@ __device__ __forceinline__ uint32_t gen_flags_prob(const StepParams &p, uint64_t
     return nphi;
 }
 
+// Prob(p) at 32 bits per coordinate WITHOUT the redraw loop.  The reference draws D Bernoulli(p) flags and starts over
+// while none is set (ensemble_sample.rs:43-50): the result is D iid flags conditioned on "at least one".  The same law,
+// drawn in one pass: the position J of the first set flag is truncated-geometric, P(J <= j | any) =
+// (1 - (1-p)^(j+1)) / (1 - (1-p)^D) -- read off a table of 32-bit thresholds (computed once on the host) with the random
+// word of coordinate 0, which the construction never needs as a Bernoulli draw (coordinate 0 is either the first set
+// flag or clear); coordinates before J are clear, J is set, coordinates after J are iid Bernoulli(p) from their own words.
+// No loop, so nothing to bound, and no extra random numbers.  At c4 (10-D, p = 0.2: 11 % of the walkers redraw, i.e.
+// nearly every warp ran the three Philox calls of an attempt two or three times) this was 40 % of the step's
+// instructions (profiles/r2_c4_step_reg_ncu_summary.txt).  oracle/philox_streams.c restates it.
+__device__ __forceinline__ uint32_t gen_flags_first(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw,
+                                                    uint32_t lane)
+{
+    const uint32_t nblk = (p.dim + 3u) / 4u;
+    const uint32_t thr = (uint32_t)(p.flag_thr > 0xFFFFFFFFull ? 0xFFFFFFFFull : p.flag_thr);
+    U4 r = draw(p.seed, step, ST_FLAGS, w + p.w_off, 0);
+    uint32_t lo = 0, hi = p.dim - 1u;  // J = number of j < dim-1 with word0 >= cdf[j]
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (r.x >= __ldg(p.flag_cdf + mid)) lo = mid + 1u;
+        else hi = mid;
+    }
+    const uint32_t J = lo;
+    uint32_t nphi = 0, cur = 0;
+    for (uint32_t blk = 0; blk < nblk; ++blk) {
+        if (blk) r = draw(p.seed, step, ST_FLAGS, w + p.w_off, blk);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (uint32_t wi = 0; wi < 4; ++wi) {
+            const uint32_t d = blk * 4u + wi;
+            if (d < p.dim) {
+                const uint32_t f = d < J ? 0u : (d == J ? 1u : (uint32_t)(rr[wi] < thr));
+                nphi += f;
+                cur |= f << (d & 31u);
+                if (((d + 1u) & 31u) == 0u || d + 1u >= p.dim) {
+                    flagw[(d >> 5) * 32u + lane] = cur;
+                    cur = 0;
+                }
+            }
+        }
+    }
+    return nphi;
+}
+
 // `step`, `onehot`: the counters the Prob stream / the cycling closure are keyed by (p.step, p.onehot, except in the
 // kernels that run several steps or half-passes per launch)
 __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step, uint64_t onehot, uint32_t w, uint32_t *flagw,
@@ -246,7 +292,7 @@ __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step
     case 4: return gen_flags_prob<4>(p, step, w, flagw, lane, act);
     case 8: return gen_flags_prob<8>(p, step, w, flagw, lane, act);
     case 16: return gen_flags_prob<16>(p, step, w, flagw, lane, act);
-    default: return gen_flags_prob<32>(p, step, w, flagw, lane, act);
+    default: return p.flag_cdf ? gen_flags_first(p, step, w, flagw, lane) : gen_flags_prob<32>(p, step, w, flagw, lane, act);
     }
 }
 __device__ __forceinline__ uint32_t gen_flags(const StepParams &p, uint64_t step, uint32_t w, uint32_t *flagw, uint32_t lane,
