@@ -49,6 +49,24 @@ def shard_layout(n_walkers: int, nbeta: int, world: int, rank: int):
     return "walkers", rank * n_local, n_local, 0, nbeta
 
 
+def owned_pairs(order: np.ndarray, n_local: int, rank: int) -> np.ndarray:
+    """The pairs of a whole-ensemble matching that `rank` computes in the one-sided exchange step, as [k, 2] walker ids.
+    order[j] = walker at matching position j (positions 2k, 2k+1 are partners).  Rule (api_shard.cu:
+    shard_pairs_kernel): a pair belongs to the rank holding its EVEN-position member -- every pair on exactly one
+    rank, which updates both of its walkers; positions are a keyed bijection of the walkers, so the split is balanced
+    to O(sqrt(n))."""
+    order = np.asarray(order, dtype=np.int64)
+    a, b = order[0::2], order[1::2]
+    mine = a // n_local == rank
+    return np.stack([a[mine], b[mine]], axis=1)
+
+
+def is_exchange_step(step_index: int, global_every: int) -> bool:
+    """The k-schedule: steps whose index is a multiple of k use the whole-ensemble matching (the same rule as
+    scorus_set_matching_blocks on one GPU)."""
+    return global_every <= 1 or step_index % global_every == 0
+
+
 def exchange_plan(src_all: np.ndarray, n_local: int, world: int, rank: int):
     """Who sends which rows to whom after a ladder swap.
 
@@ -203,7 +221,7 @@ class ShardedSampler:
         done, k = 0, self.global_every
         while done < nsteps:
             index = self.sampler.counters[0]                         # the step counter drives the schedule
-            if index % k != 0:                                       # shard-local steps up to the next global one
+            if not is_exchange_step(index, k):                       # shard-local steps up to the next global one
                 run = min(nsteps - done, k - index % k)
                 self.sampler.sample_pt(a, ufs, beta, run)
                 done += run

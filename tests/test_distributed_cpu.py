@@ -7,7 +7,7 @@ import socket
 import numpy as np
 import pytest
 
-from scorus_b200.distributed import exchange_plan, exchange_plan_torch, shard_layout
+from scorus_b200.distributed import exchange_plan, exchange_plan_torch, is_exchange_step, owned_pairs, shard_layout
 
 
 def test_shard_layout():
@@ -117,6 +117,90 @@ def test_row_exchange_world2_gloo(oracle):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, src, ens, want, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == [1] * world
+
+
+def test_pair_ownership_partitions_the_matching(oracle):
+    """Every pair of the whole-ensemble matching is owned by exactly one rank, the owner holds its even-position member,
+    and the split is balanced; the schedule rule is the single-GPU one."""
+    n, world = 1 << 14, 8
+    n_local = n // world
+    partner, _, _, _ = oracle.philox_sample_streams(3, 5, n, 4, 1, 2.0, oracle.UFS_ALL, 0.5, 0)
+    # rebuild an order array from the partner map (any order of the pairs: ownership only needs "even member")
+    firsts = np.flatnonzero(partner > np.arange(n))
+    rng = np.random.default_rng(0)
+    flip = rng.random(firsts.size) < 0.5
+    a = np.where(flip, partner[firsts], firsts)
+    b = np.where(flip, firsts, partner[firsts])
+    order = np.stack([a, b], axis=1).reshape(-1)
+    owned = [owned_pairs(order, n_local, r) for r in range(world)]
+    allp = np.concatenate(owned)
+    assert allp.shape[0] == n // 2 and np.array_equal(np.sort(allp.reshape(-1)), np.arange(n))
+    for r, pr in enumerate(owned):
+        assert np.all(pr[:, 0] // n_local == r)
+        assert abs(pr.shape[0] - n // 2 // world) < 6 * np.sqrt(n / 2 / world)
+    assert [is_exchange_step(s, 4) for s in range(6)] == [True, False, False, False, True, False]
+    assert all(is_exchange_step(s, 1) for s in range(4))
+
+
+def _owner_worker(rank, world, port, kind, params, ens, lp, beta, streams, want_e, want_lp, q):
+    """The one-sided exchange step emulated on CPU ranks: each rank runs the oracle on the pairs it OWNS (reading both rows
+    from the gathered pre-step state, as the device reads a remote partner over NVLink) and the results go back to the
+    walkers' home ranks."""
+    import torch
+    import torch.distributed as dist
+    from oracle import pyoracle as po
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, dim = ens.shape
+    n_local = n // world
+    partner, z, flags, u = streams
+    firsts = np.flatnonzero(partner > np.arange(n))
+    order = np.stack([firsts, partner[firsts]], axis=1).reshape(-1)       # even position: the lower id (any rule works)
+    mine = owned_pairs(order, n_local, rank)
+    ids = mine.reshape(-1)
+    sub_e, sub_lp = np.ascontiguousarray(ens[ids]), np.ascontiguousarray(lp[ids])
+    local = np.arange(ids.size, dtype=np.uint32) ^ 1
+    rc, acc = po.sample_pt_fixed(kind, params, sub_e, sub_lp, beta, local, z[ids], flags[ids], u[ids])
+    assert rc == 0
+    # write-back to the home ranks: (walker id, row, lp) of everything this rank computed
+    out = [None] * world
+    dist.all_gather_object(out, (ids, sub_e, sub_lp))
+    new_e, new_lp = ens.copy(), lp.copy()
+    for i, e, l in out:
+        new_e[i], new_lp[i] = e, l
+    lo = rank * n_local
+    ok = bool(np.array_equal(new_e[lo:lo + n_local], want_e[lo:lo + n_local]) and
+              np.array_equal(new_lp[lo:lo + n_local], want_lp[lo:lo + n_local]))
+    gathered = [torch.zeros(1, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor([int(ok)], dtype=torch.int32))
+    if rank == 0:
+        q.put([int(t.item()) for t in gathered])
+    dist.destroy_process_group()
+
+
+def test_owner_computes_exchange_step_world2_gloo(oracle):
+    """world_size 2 on CPU: pair ownership + write-back reproduce the oracle's whole-ensemble step exactly."""
+    import torch.multiprocessing as mp
+    g = np.random.default_rng(4)
+    n, dim, world = 256, 6, 2
+    ens = np.ascontiguousarray(g.uniform(0.9, 1.1, (n, dim)))
+    lp = oracle.init_logprob(2, [], ens)
+    beta = np.ones(1)
+    streams = oracle.philox_sample_streams(21, 0, n, dim, 1, 2.0, oracle.UFS_PROB, 0.5, 0)
+    want_e, want_lp = ens.copy(), lp.copy()
+    rc, acc = oracle.sample_pt_fixed(2, [], want_e, want_lp, beta, *streams)
+    assert rc == 0 and acc.sum() > 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_owner_worker, args=(r, world, port, 2, [], ens, lp, beta, streams, want_e, want_lp, q))
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
