@@ -239,6 +239,10 @@ int scorus_hmc_sample_ensemble_pt_fixed(scorus_ctx *ctx, double *epsilon, const 
 int scorus_hmc_sample_ensemble_pt_host(scorus_ctx *ctx, double *q0, double *logprob, size_t logprob_len, double *epsilon,
                                        const double *beta_list, size_t nbeta, size_t l, const scorus_hmc_param *param,
                                        uint64_t *accepted_cnt);
+/* #grow - #shrink of the step-size adaptation codes the LAST HMC step wrote for this context's walkers
+ * (src/mcmc/hmc/naive.rs:274-283).  Walker shards of one rung run the step with HmcParam::fixed, sum this over the ranks and
+ * apply epsilon (1 + adj)^net once: the single-GPU result for rungs above 4096 walkers, bit for bit. */
+int scorus_hmc_adapt_net(scorus_ctx *ctx, int64_t *net_out);
 /* the device stream's momenta (the draws of src/mcmc/hmc/naive.rs:182-192) of walkers [0, count) at step counter `step`, out[count][dim] (they go through
  * log / sqrt / sincos; exposed so that a device-stream run can be replayed exactly through the _fixed entry point) */
 int scorus_hmc_draw_momenta(scorus_ctx *ctx, uint64_t step, size_t count, double *out);

@@ -137,6 +137,7 @@ extern "C" {
                                       a: f64, ufs: *const scorus_ufs, beta_list: *const f64, nbeta: usize,
                                       nsteps: u64) -> c_int;
     pub fn scorus_peer_barrier(ctx: *mut scorus_ctx) -> c_int;
+    pub fn scorus_hmc_adapt_net(ctx: *mut scorus_ctx, net_out: *mut i64) -> c_int;
     pub fn scorus_upload_f32(ctx: *mut scorus_ctx, ensemble: *const f32, logprob: *const f32) -> c_int;
     pub fn scorus_download_f32(ctx: *mut scorus_ctx, ensemble: *mut f32, logprob: *mut f32) -> c_int;
     pub fn scorus_sample_pt_fixed_f32(ctx: *mut scorus_ctx, beta_list: *const f64, nbeta: usize, partner: *const u32,

@@ -113,6 +113,7 @@ def load() -> C.CDLL:
         "scorus_sample_pt_fixed_f32": (ci, [vp, dp, sz, u32p, fp, u8p, sz, fp, u8p]),
         "scorus_swap_walkers_fixed_f32": (ci, [vp, dp, sz, u32p, fp, u8p]),
         "scorus_sample_pt_peer_host": (ci, [vp, dp, dp, sz, dbl, C.POINTER(Ufs), dp, sz, u64]),
+        "scorus_hmc_adapt_net": (ci, [vp, C.POINTER(C.c_int64)]),
         "scorus_peer_barrier": (ci, [vp]),
         "scorus_swap_walkers_peer": (ci, [vp, dp, sz]),
         "scorus_peer_read_bandwidth": (ci, [vp, ci, sz, ci, dp, dp, dp]),
@@ -150,7 +151,7 @@ EXPORTS = [
     "scorus_hmc_sample_ensemble_pt_fixed", "scorus_hmc_sample_ensemble_pt_host", "scorus_hmc_draw_momenta", "scorus_set_shard", "scorus_sample_pt_global",
     "scorus_swap_plan_device", "scorus_ipc_export", "scorus_ipc_attach",
     "scorus_sample_pt_peer", "scorus_upload_f32", "scorus_download_f32", "scorus_sample_pt_fixed_f32", "scorus_swap_walkers_fixed_f32",
-    "scorus_sample_pt_peer_host", "scorus_peer_barrier", "scorus_swap_walkers_peer", "scorus_peer_read_bandwidth", "scorus_set_matching_blocks", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
+    "scorus_sample_pt_peer_host", "scorus_hmc_adapt_net", "scorus_peer_barrier", "scorus_swap_walkers_peer", "scorus_peer_read_bandwidth", "scorus_set_matching_blocks", "scorus_swap_apply_p2p", "scorus_sync", "scorus_set_stream", "scorus_reset_stream",
     "scorus_get_stream", "scorus_device_buffers", "scorus_get_counters", "scorus_set_counters",
     "scorus_get_stats", "scorus_launch_count", "scorus_host_alloc", "scorus_host_free",
 ]

@@ -295,6 +295,38 @@ extern "C" int scorus_hmc_sample_ensemble_pt_fixed(scorus_ctx *ctx, double *epsi
     return hmc_impl(ctx, epsilon, beta, nbeta, l, param, p0, u1, u2, accepted_out, accepted_cnt, 1);
 }
 
+// Net step-size adaptation of the LAST HMC step over this context's walkers: #grow - #shrink of the codes the kernel
+// wrote (naive.rs:274-283).  For walker shards of one rung: every rank runs the step with HmcParam::fixed, the nets are
+// summed over the ranks and epsilon (1 + adj)^net is applied once -- what the single-GPU path does for rungs above 4096
+// walkers (hmc_adapt_count_kernel), so the sharded epsilon is the single-GPU epsilon bit for bit.
+static __global__ void __launch_bounds__(256) hmc_net_kernel(const int8_t *adapt, uint32_t n, long long *net)
+{
+    long long v = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += adapt[i];
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(net), (unsigned long long)v);
+}
+
+extern "C" int scorus_hmc_adapt_net(scorus_ctx *ctx, int64_t *net_out)
+{
+    if (!ctx || !net_out) return SCORUS_ERR_INVALID_ARG;
+    F64_ONLY(ctx);
+    if (!ctx->d_hmc_adapt) return fail(ctx, SCORUS_ERR_INVALID_ARG, "no HMC step has run on this context");
+    cudaSetDevice(ctx->device);
+    int rc = ensure(ctx, (void **)&ctx->d_hmc_eps, &ctx->hmc_eps_cap, sizeof(double));
+    if (rc) return rc;
+    long long *d_net = reinterpret_cast<long long *>(ctx->d_hmc_eps);  // scratch: epsilon went back to the host already
+    CU(cudaMemsetAsync(d_net, 0, sizeof(long long), ctx->stream));
+    hmc_net_kernel<<<(unsigned)std::min<size_t>((ctx->n + 255) / 256, (size_t)ctx->num_sms * 8u), 256, 0, ctx->stream>>>(
+        ctx->d_hmc_adapt, (uint32_t)ctx->n, d_net);
+    ++ctx->launches;
+    long long h = 0;
+    CU(cudaMemcpyAsync(&h, d_net, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *net_out = (int64_t)h;
+    return SCORUS_OK;
+}
+
 // sample_ensemble_pt on caller-owned host buffers (q0: &mut [V], lp: &mut [T], :125-126)
 extern "C" int scorus_hmc_sample_ensemble_pt_host(scorus_ctx *ctx, double *q0, double *lp, size_t lp_len, double *epsilon,
                                                   const double *beta, size_t nbeta, size_t l, const scorus_hmc_param *param,

@@ -272,14 +272,33 @@ class ShardedSampler:
     def hmc_sample_ensemble_pt(self, epsilon, beta_list: Sequence[float], l: int, param, nsteps: int = 1):
         """hmc::naive::sample_ensemble_pt (src/mcmc/hmc/naive.rs:122-292) on this rank's shard: walkers are
         independent, so there is no communication.  Rung shards: `epsilon` is the whole ladder's array, this rank
-        updates (in place) and returns the counts of its own rungs only.  Walker shards of one rung would each adapt
-        their own copy of the rung's step size, so they take a fixed one (`HmcParam.fixed`)."""
+        updates (in place) and returns the counts of its own rungs only.  Walker shards of one rung adapt ONE step size:
+        the ranks' net adaptation counts are summed every step (below)."""
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         if self.mode == "rungs":
             lo, hi = self.rung_off, self.rung_off + self.nb_local
             return self.sampler.hmc_sample_ensemble_pt(epsilon[lo:hi], beta[lo:hi], l, param, nsteps)
         if self.world > 1 and param.adj_factor != 0.0:
-            raise NotImplementedError("HMC across walker shards needs a fixed step size (HmcParam.fixed)")
+            # walker shards of ONE rung with an adapting step size: every rank runs the step with the step size frozen,
+            # the nets (#grow - #shrink, naive.rs:274-283) are summed over the ranks and epsilon (1 + adj)^net is applied
+            # once -- what one GPU does for a rung above 4096 walkers, so epsilon matches it bit for bit
+            if len(beta) != 1:
+                raise NotImplementedError("adaptive HMC over walker shards: one rung (rung shards cover tempered runs)")
+            from .hmc import HmcParam
+            frozen = HmcParam(param.target_accept_ratio, 0.0)
+            total = np.zeros(1, dtype=np.uint64)
+            for _ in range(nsteps):
+                total += self.sampler.hmc_sample_ensemble_pt(epsilon, beta, l, frozen, 1)
+                net = self.torch.tensor([self.sampler.hmc_adapt_net()], dtype=self.torch.int64, device=self.device)
+                self.dist.all_reduce(net, group=self.group)
+                m, base, pw = abs(int(net.item())), 1.0 + param.adj_factor, 1.0
+                while m:                                   # repeated squaring, as hmc_adapt_count_kernel does
+                    if m & 1:
+                        pw = pw * base
+                    base = base * base
+                    m >>= 1
+                epsilon[0] = epsilon[0] / pw if int(net.item()) < 0 else epsilon[0] * pw
+            return total
         return self.sampler.hmc_sample_ensemble_pt(epsilon, beta, l, param, nsteps)
 
     def _barrier(self):

@@ -513,6 +513,12 @@ class Sampler:
                                                               cnt.ctypes.data_as(C.POINTER(C.c_uint64))))
         return cnt
 
+    def hmc_adapt_net(self) -> int:
+        """#grow - #shrink of the adaptation codes of the last HMC step (scorus_hmc_adapt_net)."""
+        v = C.c_int64(0)
+        self._ok(self._lib.scorus_hmc_adapt_net(self._ctx, C.byref(v)))
+        return int(v.value)
+
     def hmc_draw_momenta(self, step: int, count: Optional[int] = None) -> np.ndarray:
         """Momenta of walkers [0, count) from the device stream at step counter `step`, [count][dim]."""
         count = self.n if count is None else count

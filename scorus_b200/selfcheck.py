@@ -149,6 +149,39 @@ def run_hmc(world, log=print):
     return ok
 
 
+def run_hmc_walker_shards(world, log=print):
+    """Adaptive-step-size HMC over walker shards of ONE rung: positions, log-probs and the adapted epsilon identical to the
+    single-GPU chain (whose rung, above 4096 walkers, adapts by the same net count)."""
+    import torch
+    import torch.distributed as dist
+    from .distributed import ShardedSampler
+    rank = dist.get_rank()
+    n, dim, l = 4096 * world, 8, 3
+    rng = np.random.default_rng(56)
+    q = np.ascontiguousarray(rng.uniform(0.9, 1.1, (n, dim)))
+    param = HmcParam.quick_adj(0.7)
+    ref = Sampler(Rosenbrock(), n, dim, seed=33, device=torch.cuda.current_device())
+    ref.upload(q, None)
+    sh = ShardedSampler(Rosenbrock(), n, dim, nbeta=1, seed=33, matching="local")
+    lo, hi = sh.w_off, sh.w_off + sh.n_local
+    sh.upload(np.ascontiguousarray(q[lo:hi]), None)
+    eps_ref, eps_sh = np.full(1, 0.003), np.full(1, 0.003)
+    cnt_ref = ref.hmc_sample_ensemble_pt(eps_ref, [1.0], l, param, 5)
+    cnt_sh = torch.tensor([int(sh.hmc_sample_ensemble_pt(eps_sh, [1.0], l, param, 5)[0])], device="cuda", dtype=torch.int64)
+    dist.all_reduce(cnt_sh)
+    want_q, want_lp = ref.download()
+    got_q, got_lp = sh.download()
+    ok = (np.array_equal(got_q, want_q[lo:hi]) and np.allclose(got_lp, want_lp[lo:hi], rtol=1e-12, atol=1e-9)
+          and eps_sh[0] == eps_ref[0] and eps_ref[0] != 0.003 and int(cnt_sh.item()) == int(cnt_ref[0]))
+    ok = _all_ok(torch, dist, ok)
+    if rank == 0:
+        log(f"hmc_rosenbrock_walker_shards_adaptive: world={world} n={n} dim={dim} eps {eps_ref[0]:.6g} / {eps_sh[0]:.6g} "
+            f"{'OK' if ok else 'MISMATCH'}")
+    ref.close()
+    sh.close()
+    return ok
+
+
 def run_mixed_statistics(world, log=print):
     """Whole-ensemble matching every 5th step, shard-local in between, also checked for what it samples: unit
     Gaussian in, unit Gaussian out, across all shards."""
@@ -224,6 +257,7 @@ def sharded_parity_cases(quick: bool = False, log=print):
     res.append(run_case("twalk_rosenbrock_pt_small_rungs", Rosenbrock(), 64 * 2 * world, 20, 2 * world, None, 12, 3,
                         (0.9, 1.1), twalk=True, log=log))
     res.append(run_hmc(world, log=log))
+    res.append(run_hmc_walker_shards(world, log=log))
     res.append(run_host_call(world, log=log))
     res.append(run_mixed_statistics(world, log=log))
     return len(res), all(res)
