@@ -33,7 +33,7 @@ enum : int { PAIRS_EITHER = 0, PAIRS_OWNER = 1 };
 // stream-ordered barrier across the ranks of scorus_ipc_attach, by flags in peer memory: rank r stores `epoch` into
 // slot r of every peer's flag row (the 32 doubles behind its log-probs) and waits until all slots of its own row
 // have reached it.  Threads 0..world-1 of ONE block.  Everything this GPU wrote before (kernel boundary +
-// fence.sys) is visible to a peer that has seen the flag.  A peer that never arrives traps after 20 s instead of
+// fence.sys) is visible to a peer that has seen the flag.  A peer that never arrives traps after 60 s instead of
 // hanging the GPU.
 struct PeerTable { double *lp[16]; };
 __device__ __forceinline__ void peer_barrier_device(const PeerTable &t, uint32_t n_local, int world, int rank,
@@ -51,7 +51,7 @@ __device__ __forceinline__ void peer_barrier_device(const PeerTable &t, uint32_t
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
         if (v >= epoch) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) __trap();
+        if (t1 - t0 > 60000000000ull) __trap();
     }
     __threadfence_system();
 }
