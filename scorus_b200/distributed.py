@@ -183,7 +183,6 @@ class ShardedSampler:
         self.sampler.set_stream(self._stream.cuda_stream)
         self.ens, self.lp, self.pitch = device_views(self.sampler, self.device)
         self._ens_all = self._lp_all = self._src_all = None
-        self._token = None
         self.p2p = False
         if self.world > 1 and ((self.mode == "walkers" and matching == "p2p") or (self.mode == "rungs" and p2p_swap)):
             self.p2p = True
