@@ -264,6 +264,8 @@ extern "C" int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const voi
     if (!ctx || world < 1 || world > 16 || rank < 0 || rank >= world || !handles_ens || !handles_lp)
         return SCORUS_ERR_INVALID_ARG;
     F64_ONLY(ctx);
+    // the barrier epochs live in the peers' memory: a second attach would restart them below what the flags already hold
+    if (ctx->d_peer_ens) return fail(ctx, SCORUS_ERR_INVALID_ARG, "this context is already attached to its peers");
     cudaSetDevice(ctx->device);
     const cudaIpcMemHandle_t *he = (const cudaIpcMemHandle_t *)handles_ens, *hl = (const cudaIpcMemHandle_t *)handles_lp;
     for (int q = 0; q < world; ++q) {
