@@ -309,6 +309,8 @@ class ShardedSampler:
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         if self.world == 1:
             self.sampler.swap_walkers(beta)
+            # the swap leaves the rows in the context's second buffer (the two change roles): refresh the views
+            self.ens, self.lp, self.pitch = device_views(self.sampler, self.device)
             return
         if self.mode != "rungs":
             # walker shards: the one-sided swap works on global slots, wherever the rung boundaries fall
