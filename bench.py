@@ -643,6 +643,23 @@ def main():
                               "time against the same peak"}
         if traffic:
             roofline["traffic_frac"] = traffic * args.steps / (ms * 1e-3) / 1e9 / peak
+        if world == 1 and args.move == "stretch" and args.dtype == "f64" and n_local * dim * 8 > 2 * 126e6:
+            # what HBM delivers for the kernel's ACCESS PATTERN -- every row read once in a scrambled order -- measured
+            # here on a second context of the same shape (a world of one rank reads its own ensemble)
+            try:
+                probe = sb.Sampler(sb.Gaussian(0.5), n_local, dim, seed=1, device=local_rank)
+                probe.init_ensemble(0.0, 1.0)
+                he, hl = probe.ipc_export()
+                probe.ipc_attach(1, 0, [he], [hl])
+                _, seq, rows = probe.peer_read_bandwidth(0, 0, 5)
+                probe.close()
+                roofline["access_pattern"] = {
+                    "sequential_read_gbps": seq, "scrambled_rows_read_gbps": rows,
+                    "traffic_over_scrambled_rows": (traffic * args.steps / (ms * 1e-3) / 1e9 / rows) if traffic else None,
+                    "note": "pure reads, 64 warps per SM: the ceiling for partner rows of a random matching; "
+                            "profiles/r2_notes.md section 4"}
+            except Exception as ex:   # a measurement aid: never fails the line
+                roofline["access_pattern"] = {"error": str(ex)}
 
     cpu = None
     if not args.no_cpu and world == 1 and args.move == "stretch":
