@@ -138,7 +138,7 @@ extern "C" void scorus_ctx_destroy(scorus_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_ens, ctx->d_lp, ctx->d_scratch, ctx->d_params, ctx->d_order,
                     ctx->d_src, ctx->d_stats, ctx->d_z, ctx->d_u, ctx->d_flags, ctx->d_acc,
-                    ctx->d_beta_f32, ctx->d_flag_cdf, ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
+                    ctx->d_beta_f32, ctx->d_flag_cdf, ctx->d_jinv, ctx->d_r, ctx->d_swapped, ctx->d_chain, ctx->d_swap_out, ctx->d_lp_all, ctx->d_src_all, ctx->d_gorder, ctx->d_pairs, ctx->d_count, ctx->d_tile_counter};
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (auto &e : ctx->beta_cache)
@@ -189,6 +189,8 @@ extern "C" int scorus_device_buffers(scorus_ctx *ctx, double **ens, size_t *pitc
 {
     if (!ctx) return SCORUS_ERR_INVALID_ARG;
     F64_ONLY(ctx);
+    int rc = settle_swap(ctx);  // the pointers handed out are of the buffers as the caller expects them: rows in their slots
+    if (rc) return rc;
     if (ens) *ens = ctx->d_ens;
     if (pitch) *pitch = ctx->pitch;
     if (lp) *lp = ctx->d_lp;
@@ -371,8 +373,9 @@ extern "C" int scorus_init_logprob(scorus_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->f32) return f32_init_logprob(ctx);
     Geometry g;
-    int rc = step_geometry(ctx, &g, false);
+    int rc = settle_swap(ctx);
     if (rc) return rc;
+    if ((rc = step_geometry(ctx, &g, false))) return rc;
     StepParams p;
     memset(&p, 0, sizeof(p));
     p.ens = ctx->d_ens; p.lp = ctx->d_lp; p.pparams = ctx->d_params; p.nparams = ctx->nparams;
@@ -402,6 +405,7 @@ extern "C" int scorus_upload(scorus_ctx *ctx, const double *ens, const double *l
     if (!ctx || !ens) return SCORUS_ERR_INVALID_ARG;
     F64_ONLY(ctx);
     cudaSetDevice(ctx->device);
+    ctx->swap_pending = false;  // everything a pending swap would have moved is overwritten here
     const size_t rb = (size_t)ctx->dim * sizeof(double);
     CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(double), ens, rb, rb, ctx->n,
                          cudaMemcpyHostToDevice, ctx->stream));
@@ -421,6 +425,8 @@ extern "C" int scorus_download(scorus_ctx *ctx, double *ens, double *lp)
     F64_ONLY(ctx);
     if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "nothing uploaded");
     cudaSetDevice(ctx->device);
+    int rc = settle_swap(ctx);
+    if (rc) return rc;
     const size_t rb = (size_t)ctx->dim * sizeof(double);
     if (ens)
         CU(cudaMemcpy2DAsync(ens, rb, ctx->d_ens, (size_t)ctx->pitch * sizeof(double), rb, ctx->n,
@@ -588,10 +594,12 @@ void scorus::host::count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t n
     for (size_t k = 0; k + 1 < nbeta; ++k) ctx->stage_proposed[k] += npb;
 }
 
-int scorus::host::fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool tile_in_smem)
+int scorus::host::fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool tile_in_smem,
+                              bool keep_pending_swap)
 {
-    int rc = step_geometry(ctx, g, tile_in_smem);
-    if (rc) return rc;
+    int rc;
+    if (!keep_pending_swap && (rc = settle_swap(ctx))) return rc;
+    if ((rc = step_geometry(ctx, g, tile_in_smem))) return rc;
     memset(p, 0, sizeof(*p));
     p->ens = ctx->d_ens; p->lp = ctx->d_lp; p->beta = ctx->d_beta; p->pparams = ctx->d_params;
     p->nparams = ctx->nparams; p->stats = ctx->d_stats; p->seed = ctx->seed;
@@ -633,21 +641,39 @@ void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv
 }
 int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp)
 {
-    // the uniforms and their logarithms for every (stage, cold slot), then the chain sweep (swap_kernel.cuh)
+    // the slot walk over (segment, slot) with the uniforms, their logarithms and the cold log-probs, then the carry
+    // sweep, one thread per chain (swap_kernel.cuh)
     const size_t m = (size_t)(sp.nbeta - 1) * sp.npb;
-    int rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * 2 * sizeof(double));
+    int rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * sizeof(SwapRec));
     if (rc) return rc;
-    sp.chain_r = reinterpret_cast<double *>(ctx->d_chain);
-    sp.chain_lr = sp.chain_r + m;
-    const unsigned ublocks = (unsigned)std::min<size_t>((m + 255) / 256, (size_t)ctx->num_sms * 16u);
-    swap_uniforms_kernel<<<ublocks, 256, 0, ctx->stream>>>(sp);
+    sp.tbl_rec = reinterpret_cast<SwapRec *>(ctx->d_chain);
+    const unsigned nseg = (unsigned)((sp.nbeta - 1 + kSwapSeg - 1) / kSwapSeg);
+    if (nseg > 65535u) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernels (%u)", sp.nbeta);
+    swap_paths_kernel<<<dim3((sp.npb + 255u) / 256u, nseg), 256, 0, ctx->stream>>>(sp);
     const unsigned T = 128;
-    const size_t smem = (size_t)kSwapChunk * T * (2 * sizeof(double) + sizeof(uint32_t)) +
-                        (sp.jinv ? 0 : (size_t)(sp.nbeta - 1) * 8 * sizeof(uint32_t));
-    cudaError_t e = cudaFuncSetAttribute(swap_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernel's key table: %s", cudaGetErrorString(e));
-    swap_chain_kernel<<<(unsigned)((sp.npb + T - 1) / T), T, smem, ctx->stream>>>(sp);
+    // per-stage beta differences and exchange counters of a block in shared memory when the ladder is short enough
+    const size_t walk_smem = (size_t)(sp.nbeta - 1) * (sizeof(double) + sizeof(unsigned int));
+    if (sp.nbeta - 1 <= kSwapSmemStages)
+        swap_walk_kernel<true><<<(unsigned)((sp.npb + T - 1) / T), T, walk_smem, ctx->stream>>>(sp);
+    else
+        swap_walk_kernel<false><<<(unsigned)((sp.npb + T - 1) / T), T, 0, ctx->stream>>>(sp);
     ctx->launches += 2;
+    return SCORUS_OK;
+}
+int settle_swap(scorus_ctx *ctx)
+{
+    if (!ctx->swap_pending) return SCORUS_OK;
+    cudaSetDevice(ctx->device);
+    const uint32_t vpr = ctx->pitch / 2;
+    const size_t total = ctx->n * (size_t)vpr;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 16u);
+    apply_swap_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2 *)ctx->d_ens, (double2 *)ctx->d_scratch,
+                                                      (const SwapOut *)ctx->d_swap_out, ctx->d_lp, (uint32_t)ctx->n, vpr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap row move: %s", cudaGetErrorString(e));
+    std::swap(ctx->d_ens, ctx->d_scratch);  // the second buffer becomes the ensemble
+    ctx->swap_pending = false;
+    ++ctx->launches;
     return SCORUS_OK;
 }
 }  // namespace host
@@ -691,7 +717,19 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
     StepParams p;
     Geometry g;
     if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
-    if ((rc = fill_common(ctx, &p, &g, nbeta))) return rc;
+    if ((rc = fill_common(ctx, &p, &g, nbeta, false, true))) return rc;
+    // a ladder swap left its rows to this call (swap_impl): the first step moves them itself when its kernel can
+    // (single launch over the whole ensemble, register kernel in direct mode), otherwise they move now
+    bool move_rows = false;
+    if (ctx->swap_pending) {
+        Geometry gs = g;
+        move_rows = !small_geometry(ctx, &gs) && step_can_remap(ctx->lp_kind, ctx->pitch, g) && g.grid > 1 &&
+                    !ctx->track_dirty && nsteps > 0 && env_int("SCORUS_SWAP_FUSE", 1);
+        if (!move_rows) {
+            if ((rc = settle_swap(ctx))) return rc;
+            p.ens = ctx->d_ens; p.src_ens = ctx->d_ens;
+        }
+    }
     const double sqrt_a = sqrt(a);
     p.inv_sqrt_a = 1.0 / sqrt_a;
     p.z_range = 2.0 * (sqrt_a - p.inv_sqrt_a);  // src/mcmc/utils.rs:42
@@ -762,10 +800,22 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
             launch_exact_order(ctx, ctx->step, ctx->n / p.mblk, p.mblk, ctx->d_order, (uint32_t)ctx->w_off);
             p.order = ctx->d_order;
         }
+        if (move_rows) {  // read through the swap's result, write every row to the second buffer
+            p.remap = ctx->d_swap_out;
+            p.src_ens = ctx->d_ens;
+            p.ens = ctx->d_scratch;
+        }
         stamp_tiles(ctx, &p, g);
         cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
         commit_tiles(ctx, p);
+        if (move_rows) {  // ... which is the ensemble from here on
+            std::swap(ctx->d_ens, ctx->d_scratch);
+            ctx->swap_pending = false;
+            move_rows = false;
+            p.remap = nullptr;
+            p.ens = ctx->d_ens; p.src_ens = ctx->d_ens;
+        }
         ++ctx->launches;
         ++ctx->step;
         if (ufs->kind == SCORUS_UFS_ONE_HOT_CYCLE) ctx->onehot = (ctx->onehot + ctx->n_global) % ctx->dim;
@@ -890,11 +940,21 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
     if ((rc = upload_beta(ctx, beta, nbeta))) return rc;
     const size_t m = (nbeta - 1) * npb;
 
+    if ((rc = settle_swap(ctx))) return rc;  // a swap right after a swap
     SwapParams sp;
     memset(&sp, 0, sizeof(sp));
-    if (!ctx->d_src) CU(cudaMalloc(&ctx->d_src, n * sizeof(uint32_t)));
     if (!ctx->d_scratch) CU(cudaMalloc(&ctx->d_scratch, n * (size_t)ctx->pitch * sizeof(double)));
-    sp.lp = ctx->d_lp; sp.lp_src = ctx->d_lp; sp.beta = ctx->d_beta; sp.src = ctx->d_src; sp.stats = ctx->d_stats;
+    // buffers mapped by peers (scorus_ipc_attach) stay put: the rows move in place, through scratch; otherwise the
+    // sweep's result stays interleaved and the rows move with the next step (or when anything else looks, settle_swap)
+    const bool in_place = ctx->d_peer_ens != nullptr;
+    if (in_place) {
+        if (!ctx->d_src) CU(cudaMalloc(&ctx->d_src, n * sizeof(uint32_t)));
+        sp.lp = ctx->d_lp; sp.src = ctx->d_src;
+    } else {
+        if ((rc = ensure(ctx, &ctx->d_swap_out, &ctx->swap_out_cap, n * sizeof(SwapOut)))) return rc;
+        sp.out = (SwapOut *)ctx->d_swap_out;
+    }
+    sp.lp_src = ctx->d_lp; sp.beta = ctx->d_beta; sp.stats = ctx->d_stats;
     if ((rc = ensure_rung_stats(ctx, nbeta))) return rc;
     sp.stage_swapped = ctx->d_rung_stats + ctx->rung_cap;
     sp.seed = ctx->seed; sp.swap_call = ctx->swap_call;
@@ -927,25 +987,21 @@ static int swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, const ui
         sp.swapped_out = ctx->d_swapped;
     }
     if ((rc = launch_swap_chain(ctx, sp))) return rc;
-    const uint32_t vpr = ctx->pitch / 2;
-    const size_t total = n * (size_t)vpr;
-    unsigned blocks = (unsigned)((total + 255) / 256);
-    unsigned cap = (unsigned)ctx->num_sms * 16u;
-    if (blocks > cap) blocks = cap;
-    if (!ctx->d_peer_ens && env_int("SCORUS_SWAP_FLIP", 1)) {
-        // one pass: every row goes to its new slot in the second buffer, which then becomes the ensemble (the first
-        // version gathered the moved rows into scratch and copied them back: two passes -- at c4, where 87 % of the
-        // exchanges are accepted, nearly every row twice).  Buffers mapped by peers (scorus_ipc_attach) stay put.
-        gather_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
-                                                            (uint32_t)n, vpr);
-        std::swap(ctx->d_ens, ctx->d_scratch);
-        ++ctx->launches;
-    } else {
+    if (in_place) {
+        const uint32_t vpr = ctx->pitch / 2;
+        const size_t total = n * (size_t)vpr;
+        const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 16u);
         permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
                                                              (uint32_t)n, vpr, 0);
         permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((double2 *)ctx->d_ens, (double2 *)ctx->d_scratch, ctx->d_src,
                                                              (uint32_t)n, vpr, 1);
         ctx->launches += 2;
+    } else {
+        // the rows go to their new slots in the second buffer, which then becomes the ensemble -- one pass, by the next
+        // step itself (SCORUS_SWAP_FUSE=0: right away; the first version gathered the moved rows into scratch and
+        // copied them back: two passes -- at c4, where 87 % of the exchanges are accepted, nearly every row twice)
+        ctx->swap_pending = true;
+        if (!env_int("SCORUS_SWAP_FUSE", 1) && (rc = settle_swap(ctx))) return rc;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap launch: %s", cudaGetErrorString(e));

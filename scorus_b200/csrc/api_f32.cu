@@ -5,7 +5,7 @@
 // float, everything else (validation, counters, streams, matching orders, statistics counters) shared with f64.
 #include "host_common.cuh"
 
-#include "gen_f32/swap_kernel.cuh"   // scorus::f32::{SwapParams, swap_uniforms_kernel, swap_chain_kernel, gather_rows_kernel}
+#include "gen_f32/swap_kernel.cuh"   // scorus::f32::{SwapParams, swap_paths_kernel, swap_walk_kernel, gather_rows_kernel}
 #include "gen_f32/tile_common.cuh"   // scorus::f32::StepParams
 
 namespace scorus {
@@ -348,17 +348,18 @@ static int f32_swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, cons
         if ((rc = ensure(ctx, (void **)&ctx->d_swapped, &ctx->swapped_cap, m))) return rc;
         sp.swapped_out = ctx->d_swapped;
     }
-    if ((rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * 2 * sizeof(double)))) return rc;
-    sp.chain_r = reinterpret_cast<float *>(ctx->d_chain);
-    sp.chain_lr = sp.chain_r + m;
-    const unsigned ublocks = (unsigned)std::min<size_t>((m + 255) / 256, (size_t)ctx->num_sms * 16u);
-    F::swap_uniforms_kernel<<<ublocks, 256, 0, ctx->stream>>>(sp);
+    if ((rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * sizeof(F::SwapRec)))) return rc;
+    sp.tbl_rec = reinterpret_cast<F::SwapRec *>(ctx->d_chain);
+    const unsigned nseg = (unsigned)((nbeta - 1 + F::kSwapSeg - 1) / F::kSwapSeg);
+    if (nseg > 65535u) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernels (%zu)", nbeta);
+    F::swap_paths_kernel<<<dim3((unsigned)((npb + 255) / 256), nseg), 256, 0, ctx->stream>>>(sp);
     const unsigned T = 128;
-    const size_t smem = (size_t)F::kSwapChunk * T * (2 * sizeof(float) + sizeof(uint32_t)) +
-                        (sp.jinv ? 0 : (size_t)(nbeta - 1) * 8 * sizeof(uint32_t));
-    cudaError_t e = cudaFuncSetAttribute(F::swap_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernel's key table: %s", cudaGetErrorString(e));
-    F::swap_chain_kernel<<<(unsigned)((npb + T - 1) / T), T, smem, ctx->stream>>>(sp);
+    // per-stage beta differences and exchange counters of a block in shared memory when the ladder is short enough
+    const size_t walk_smem = (size_t)(nbeta - 1) * (sizeof(float) + sizeof(unsigned int));
+    if (nbeta - 1 <= F::kSwapSmemStages)
+        F::swap_walk_kernel<true><<<(unsigned)((npb + T - 1) / T), T, walk_smem, ctx->stream>>>(sp);
+    else
+        F::swap_walk_kernel<false><<<(unsigned)((npb + T - 1) / T), T, 0, ctx->stream>>>(sp);
     const uint32_t vpr = ctx->pitch / 2;  // float2 chunks per row
     const size_t total = n * (size_t)vpr;
     const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 16u);
@@ -366,7 +367,7 @@ static int f32_swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, cons
                                                            (uint32_t)n, vpr);
     std::swap(ctx->d_ens, ctx->d_scratch);
     ctx->launches += 3;
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "swap launch (f32): %s", cudaGetErrorString(e));
     ++ctx->swap_call;
     count_swap_proposed(ctx, nbeta, npb);

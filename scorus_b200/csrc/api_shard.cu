@@ -253,6 +253,8 @@ extern "C" int scorus_ipc_export(scorus_ctx *ctx, void *handle_ens, void *handle
     F64_ONLY(ctx);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaSetDevice(ctx->device);
+    int rc = settle_swap(ctx);  // the handles are of the buffers that hold the ensemble from here on
+    if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));  // the barrier flags behind the log-probs are zeroed before a peer can write them
     CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_ens, ctx->d_ens));
     CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_lp, ctx->d_lp));
@@ -267,6 +269,10 @@ extern "C" int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const voi
     // the barrier epochs live in the peers' memory: a second attach would restart them below what the flags already hold
     if (ctx->d_peer_ens) return fail(ctx, SCORUS_ERR_INVALID_ARG, "this context is already attached to its peers");
     cudaSetDevice(ctx->device);
+    {
+        int rc = settle_swap(ctx);
+        if (rc) return rc;
+    }
     const cudaIpcMemHandle_t *he = (const cudaIpcMemHandle_t *)handles_ens, *hl = (const cudaIpcMemHandle_t *)handles_lp;
     for (int q = 0; q < world; ++q) {
         if (q == rank) { ctx->peer_ens[q] = ctx->d_ens; ctx->peer_lp[q] = ctx->d_lp; continue; }

@@ -10,6 +10,10 @@ static int accumulate_moments(scorus_ctx *ctx);
 // running moments (scorus_moments_enable)
 int scorus::host::after_step(scorus_ctx *ctx)
 {
+    if (ctx->swap_pending) {  // (a step leaves none; kept so that a new caller cannot read rows that have not moved)
+        int rc = settle_swap(ctx);
+        if (rc) return rc;
+    }
     if (ctx->tr_ncap && ctx->tr_count < ctx->tr_capacity && ++ctx->tr_tick >= ctx->tr_every) {
         ctx->tr_tick = 0;
         trace_kernel<<<(unsigned)((ctx->tr_ncap + 127) / 128), 128, 0, ctx->stream>>>(
@@ -28,6 +32,8 @@ int scorus::host::after_step(scorus_ctx *ctx)
 // the download half of the host-buffer calls (api_host.cu): accepted walkers only, written in place
 int scorus::host::launch_scatter_download(scorus_ctx *ctx, double *host_ens, double *host_lp)
 {
+    int rc = settle_swap(ctx);
+    if (rc) return rc;
     scatter_download_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, ctx->stream>>>(
         ctx->d_ens, ctx->d_lp, ctx->d_dirty, (uint32_t)ctx->n, ctx->dim, ctx->pitch, host_ens, host_lp);
     ++ctx->launches;
@@ -46,6 +52,7 @@ extern "C" int scorus_init_ensemble(scorus_ctx *ctx, const double *lo, const dou
     for (uint32_t d = 0; d < ctx->dim; ++d)
         if (!(lo[d] < hi[d])) return fail(ctx, SCORUS_ERR_INVALID_ARG, "empty range in coordinate %u (Uniform::new panics)", d);
     cudaSetDevice(ctx->device);
+    ctx->swap_pending = false;  // every row is overwritten below
     int rc = ensure(ctx, (void **)&ctx->d_stat, &ctx->stat_cap, 2 * (size_t)ctx->dim * sizeof(double));
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -66,9 +73,11 @@ static int stats_impl(scorus_ctx *ctx, size_t first, size_t count, double *mean_
     const uint32_t dim = ctx->dim, len = dim * dim;
     if (cov_out && dim > (uint32_t)kCovMaxDim) return fail(ctx, SCORUS_ERR_DIM_TOO_LARGE, "cov supports dim <= %d", kCovMaxDim);
     cudaSetDevice(ctx->device);
+    int rc = settle_swap(ctx);
+    if (rc) return rc;
     uint32_t blocks = (uint32_t)ctx->num_sms * 2u;
     if (blocks > count) blocks = (uint32_t)count;
-    int rc = ensure(ctx, (void **)&ctx->d_part, &ctx->part_cap, (size_t)blocks * (cov_out ? len : dim) * sizeof(double));
+    rc = ensure(ctx, (void **)&ctx->d_part, &ctx->part_cap, (size_t)blocks * (cov_out ? len : dim) * sizeof(double));
     if (rc) return rc;
     if ((rc = ensure(ctx, (void **)&ctx->d_stat, &ctx->stat_cap, ((size_t)dim + len) * sizeof(double)))) return rc;
     double *d_mean = ctx->d_stat, *d_cov = ctx->d_stat + dim;

@@ -83,7 +83,12 @@ struct scorus_ctx {
     uint8_t *d_swapped = nullptr; size_t swapped_cap = 0;
     double *d_lp_all = nullptr; size_t lp_all_cap = 0;          // sharded ladder swap: the plan for all slots
     uint32_t *d_src_all = nullptr; size_t src_all_cap = 0;
-    void *d_chain = nullptr; size_t chain_cap = 0;              // scratch rows of the two-pass swap chain kernel
+    void *d_chain = nullptr; size_t chain_cap = 0;              // records of the ladder swap's sub-chains (swap_kernel.cuh)
+    // A single-GPU f64 swap leaves its result interleaved in d_swap_out and the rows where they were: the stretch step
+    // that follows reads through it and writes every row to its new slot itself (step_reg_kernel.cuh, kRemap); anything
+    // else that looks at the ensemble or the log-probs first calls settle_swap (api_core.cu), which moves the rows.
+    void *d_swap_out = nullptr; size_t swap_out_cap = 0;
+    bool swap_pending = false;
     int8_t *d_hmc_adapt = nullptr;                              // HMC: step-size adaptation codes, one per walker
     double *d_hmc_eps = nullptr; size_t hmc_eps_cap = 0;        // ... step size per rung
     double *d_hmc_p = nullptr; size_t hmc_p_cap = 0;            // ... caller-supplied momenta
@@ -149,11 +154,15 @@ int ensure_rung_stats(scorus_ctx *ctx, size_t nbeta);
 void count_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb, uint64_t w_lo, uint64_t w_hi, uint64_t steps);
 void count_swap_proposed(scorus_ctx *ctx, size_t nbeta, uint64_t npb);
 // tile_in_smem: the kernel about to be launched stages a 32-row tile of proposals per warp (t-walk; the dense target)
-int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool tile_in_smem = false);
+// keep_pending_swap: the caller handles a pending swap itself (the stretch step: fused, or settled there)
+int fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_t nbeta, bool tile_in_smem = false,
+                bool keep_pending_swap = false);
 // kernels of swap_kernel.cuh, launched from more than one translation unit
 void launch_exact_order(scorus_ctx *ctx, uint64_t step, size_t nbeta, uint32_t npb, uint32_t *order, uint32_t w_off);
 void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv);
 int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp);
+// rows and log-probs of a pending swap to their slots (no-op when nothing is pending)
+int settle_swap(scorus_ctx *ctx);
 // api_f32.cu: the T = f32 paths behind the shared entry points
 int f32_set_params(scorus_ctx *ctx, const double *params, size_t nparams);
 int f32_init_logprob(scorus_ctx *ctx);

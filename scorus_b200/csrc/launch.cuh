@@ -53,6 +53,10 @@ SCORUS_DECLARE_LAUNCHERS(LpStep2d)
 SCORUS_DECLARE_LAUNCHERS(LpCorrGaussian)
 SCORUS_DECLARE_LAUNCHERS(LpMixture)
 
+// whether the stretch step of this geometry has the row-moving variant (step_reg_kernel.cuh kRemap: register kernel,
+// direct mode -- every target but the dense one, rows outside 9..16 chunks); mirrors launch_step's dispatch
+bool step_can_remap(int kind, uint32_t pitch, const Geometry &g);
+
 // dispatch on the plugin id of include/scorus_b200.h (SCORUS_LP_*)
 cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st);
 cudaError_t launch_init(int kind, const StepParams &p, uint32_t grid, size_t smem, cudaStream_t st);

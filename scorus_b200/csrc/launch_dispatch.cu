@@ -4,6 +4,13 @@
 
 namespace scorus {
 
+bool step_can_remap(int kind, uint32_t pitch, const Geometry &g)
+{
+    if (g.kernel != KERNEL_REG || kind == SCORUS_LP_CORR_GAUSSIAN) return false;  // kNeedsRow: tile mode
+    const uint32_t nvec = pitch / 2;
+    return SCORUS_G16_DIRECT || nvec < 9 || nvec > 16;  // 16 lanes per row: tile mode (launch_plugin.cu, reg_kernel_direct)
+}
+
 cudaError_t launch_step(int kind, const StepParams &p, const Geometry &g, bool all_flags, cudaStream_t st)
 {
     switch (kind) {

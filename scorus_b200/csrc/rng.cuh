@@ -171,7 +171,7 @@ template <> __host__ __device__ __forceinline__ float real_nan<float>()
 // guard band of the exp-free swap decision (swap_kernel.cuh): far above the rounding of exp / log in T, far below
 // anything that matters
 template <typename T> __host__ __device__ __forceinline__ T swap_guard();
-template <> __host__ __device__ __forceinline__ double swap_guard<double>() { return 1e-9; }
+template <> __host__ __device__ __forceinline__ double swap_guard<double>() { return 1e-5; }
 template <> __host__ __device__ __forceinline__ float swap_guard<float>() { return 1e-4f; }
 
 // Goodman-Weare stretch factor from a unit uniform: src/mcmc/utils.rs:39-44 with

@@ -75,7 +75,8 @@ __host__ __device__ constexpr bool reg_kernel_direct()
     return !Plugin::kNeedsRow && (G != 16 || SCORUS_G16_DIRECT);
 }
 
-template <class Plugin, int G, int ITERS, int kPeer = 0>
+// kRemap: the step after a ladder swap moves the rows (StepParams::remap); single GPU, direct mode only
+template <class Plugin, int G, int ITERS, int kPeer = 0, bool kRemap = false>
 __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32, 1) step_reg_kernel(const StepParams p)
 {
     using Geo = RegGeom<G, ITERS>;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     static_assert(!kStageB || kDirect, "the partner stage is built for the direct mode");
+    static_assert(!kRemap || (kDirect && kPeer == 0), "the row-moving step is built for the single-GPU direct mode");
     const uint32_t tile_bytes = kDirect ? 0u : 32u * p.row_stride;
     const uint32_t stage_bytes = kStageB ? 16u * p.row_stride + 128u : 0u;  // 16 partner rows + NB mbarriers
     const uint32_t warp_bytes = tile_bytes + stage_bytes + ((p.flag_words * 128u + 127u) & ~127u);
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
 
     // loads block `blk` of a tile whose lane = walker ids are `wt` (peer mode: lane = walker homes): rows
     // wl = grp*G + blk*GB + i
+    // (kRemap: lane = slot the walker's row is in now)
     auto load_block = [&](double2 (&x)[NR][ITERS], uint32_t wt, int blk) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
@@ -222,17 +225,31 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
     [[maybe_unused]] uint32_t home = 0, home_n = 0;  // peer mode: where my walker (of this / the next tile) lives
     if constexpr (kPeer != 0) home = home_of(w);
     // old log-prob: from the (gathered) array, or in one-sided mode from the walker's home rank
-    auto load_lp = [&](uint32_t wid, uint32_t hm, bool a) -> double {
-        if constexpr (kPeer != 0) return a ? ld_peer(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
-        else return a ? __ldg(p.src_lp + wid) : 0.0;
+    [[maybe_unused]] uint32_t rsrc = 0, rsrc_n = 0;  // kRemap: where my walker's row (of this / the next tile) is now
+    auto load_lp = [&](uint32_t wid, uint32_t hm, bool a, uint32_t &row_now) -> double {
+        if constexpr (kRemap) {
+            SwapOut o;
+            o.lp = 0.0; o.src = wid; o.pad = 0u;
+            if (a) {  // one 16-byte read-only load
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(p.remap) + wid);
+                static_assert(sizeof(SwapOut) == sizeof(int4), "SwapOut is one 16-byte record");
+                memcpy(&o, &v, sizeof(o));
+            }
+            row_now = o.src;
+            return o.lp;
+        } else if constexpr (kPeer != 0) {
+            return a ? ld_peer(p.peer_lp[hm >> 28] + (hm & 0x0FFFFFFFu)) : 0.0;
+        } else {
+            return a ? __ldg(p.src_lp + wid) : 0.0;
+        }
     };
-    double lp_old = load_lp(w, home, act);
+    double lp_old = load_lp(w, home, act, rsrc);
     if constexpr (kStageB) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) stage_issue(home, b);  // the first tile's partner rows, all slots
     }
     double2 xn[NR][ITERS];
-    load_block(xn, kPeer != 0 ? home : w, 0);
+    load_block(xn, kPeer != 0 ? home : (kRemap ? rsrc : w), 0);
 
     for (;;) {
         // ---- P1: lane = walker: z, u, flags, (nphi-1) ln z ----
@@ -274,10 +291,10 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             w_n = p.w_lo;
         }
         if constexpr (kPeer != 0) home_n = home_of(w_n);
-        lp_n = load_lp(w_n, home_n, act_n);
+        lp_n = load_lp(w_n, home_n, act_n, rsrc_n);
         if constexpr (kPeer == 0) {
             if (p.l2_prefetch && act_n) {  // my next-tile row -> L2, a whole tile ahead of its loads
-                const char *r = reinterpret_cast<const char *>(p.src_ens + (size_t)w_n * p.pitch);
+                const char *r = reinterpret_cast<const char *>(p.src_ens + (size_t)(kRemap ? rsrc_n : w_n) * p.pitch);
                 for (uint32_t off = 0; off < p.row_bytes; off += 128u) prefetch_l2(r + off);
                 prefetch_l2(r + p.row_bytes - 1u);
             }
@@ -300,8 +317,8 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             for (int i = 0; i < NR; ++i)
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) xc[i][it] = xn[i][it];
-            if (blk + 1 < NB) load_block(xn, kPeer != 0 ? home : w, blk + 1);
-            else if (tile_n < ntiles) load_block(xn, kPeer != 0 ? home_n : w_n, 0);
+            if (blk + 1 < NB) load_block(xn, kPeer != 0 ? home : (kRemap ? rsrc : w), blk + 1);
+            else if (tile_n < ntiles) load_block(xn, kPeer != 0 ? home_n : (kRemap ? rsrc_n : w_n), 0);
             if constexpr (kStageB) mbar_wait(bars + 8u * (uint32_t)blk, stage_phase);  // this block's partner rows have landed
 
             double acc[Plugin::kAcc][GB];
@@ -399,6 +416,9 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     const double lp_new = plug.finish_acc(tot);
                     const double q = exp(lz + (lp_new - lp_old) * beta);
                     acc_now = mine && (u < q);
+                    if constexpr (kRemap) {
+                        if (mine && !acc_now) *my_lp = lp_old;  // the swap's log-prob reaches the array here
+                    }
                     if (acc_now) {
                         *my_lp = lp_new;
                         if (p.dirty) {  // host-buffer call: this walker's row has to travel back (one-sided mode: mark it on its home GPU)
@@ -410,11 +430,19 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     }
                 }
                 const uint32_t accmask = __ballot_sync(0xffffffffu, acc_now);
+                // kRemap: every row of mine goes to its slot in the second buffer, accepted or not
+                [[maybe_unused]] const uint32_t minemask = kRemap ? __ballot_sync(0xffffffffu, mine && (int)(j / GB) == blk) : 0u;
 #pragma unroll
                 for (int i = 0; i < GB; ++i) {
                     const uint32_t rl = grp * G + (uint32_t)(blk * GB + i);
                     const uint32_t row = __shfl_sync(0xffffffffu, kPeer != 0 ? home : w, rl);
-                    if ((accmask >> rl) & 1u) {
+                    if constexpr (kRemap) {
+                        if (!((accmask >> rl) & 1u)) {
+#pragma unroll
+                            for (int it = 0; it < ITERS; ++it) yk[i][it] = xc[i][it];
+                        }
+                    }
+                    if (((kRemap ? minemask : accmask) >> rl) & 1u) {
                         double *rowp;
                         if constexpr (kPeer != 0) rowp = p.peer_ens[row >> 28] + (size_t)(row & 0x0FFFFFFFu) * p.pitch;
                         else rowp = p.ens + (size_t)(row - p.w_lo) * p.pitch;

@@ -2,6 +2,7 @@
 // mbarrier + bulk async copies (TMA, non-tensor form), the matching order and the update-flag
 // generator.
 #pragma once
+#include "swap_params.cuh"
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -73,6 +74,12 @@ struct StepParams {
     // walker's row, so that the block loads of the next tile find their lines in L2 instead of waiting on DRAM
     // (SCORUS_L2_PREFETCH; by default only for rows of 128..256 bytes, where it pays).
     uint32_t l2_prefetch;
+    // Register kernel, direct mode, single GPU (kRemap): the step right after a ladder swap.  The swap left its result
+    // interleaved, remap[w] = {log-prob of the walker that belongs in slot w, slot its row is still in} (swap_params.cuh
+    // SwapOut), and moved nothing: this step reads walker w's row from src_ens at remap[w].src and writes EVERY row --
+    // proposal if accepted, the old row if not -- and every log-prob to slot w of ens / lp, the context's second buffer,
+    // which the host then makes the ensemble.  The swap's row pass (read + write of the whole ensemble) disappears.
+    const void *remap;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
