@@ -643,18 +643,17 @@ int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp)
 {
     // the slot walk over (segment, slot) with the uniforms, their logarithms and the cold log-probs, then the carry
     // sweep, one thread per chain (swap_kernel.cuh)
-    const size_t m = (size_t)(sp.nbeta - 1) * sp.npb;
-    int rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * sizeof(SwapRec));
-    if (rc) return rc;
-    sp.tbl_rec = reinterpret_cast<SwapRec *>(ctx->d_chain);
     const unsigned nseg = (unsigned)((sp.nbeta - 1 + kSwapSeg - 1) / kSwapSeg);
-    if (nseg > 65535u) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernels (%u)", sp.nbeta);
-    swap_paths_kernel<<<dim3((sp.npb + 255u) / 256u, nseg), 256, 0, ctx->stream>>>(sp);
+    if (nseg > 65535u) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernels (%zu)", (size_t)sp.nbeta);
+    int rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, (size_t)nseg * sp.npb * sizeof(SwapSeg));
+    if (rc) return rc;
+    sp.tbl_seg = reinterpret_cast<SwapSeg *>(ctx->d_chain);
+    sp.debug_direct_store = env_int("SCORUS_SWAP_DIRECT_STORE", 0) ? 1u : 0u;
+    swap_paths_kernel<<<dim3((unsigned)((sp.npb + 127) / 128), nseg), 256, 0, ctx->stream>>>(sp);
     const unsigned T = 128;
-    // per-stage beta differences and exchange counters of a block in shared memory when the ladder is short enough
-    const size_t walk_smem = (size_t)(sp.nbeta - 1) * (sizeof(double) + sizeof(unsigned int));
+    // per-stage exchange counters of a block in shared memory when the ladder is short enough
     if (sp.nbeta - 1 <= kSwapSmemStages)
-        swap_walk_kernel<true><<<(unsigned)((sp.npb + T - 1) / T), T, walk_smem, ctx->stream>>>(sp);
+        swap_walk_kernel<true><<<(unsigned)((sp.npb + T - 1) / T), T, (size_t)(sp.nbeta - 1) * sizeof(unsigned int), ctx->stream>>>(sp);
     else
         swap_walk_kernel<false><<<(unsigned)((sp.npb + T - 1) / T), T, 0, ctx->stream>>>(sp);
     ctx->launches += 2;

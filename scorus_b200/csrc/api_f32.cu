@@ -348,16 +348,16 @@ static int f32_swap_impl(scorus_ctx *ctx, const double *beta, size_t nbeta, cons
         if ((rc = ensure(ctx, (void **)&ctx->d_swapped, &ctx->swapped_cap, m))) return rc;
         sp.swapped_out = ctx->d_swapped;
     }
-    if ((rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, m * sizeof(F::SwapRec)))) return rc;
-    sp.tbl_rec = reinterpret_cast<F::SwapRec *>(ctx->d_chain);
     const unsigned nseg = (unsigned)((nbeta - 1 + F::kSwapSeg - 1) / F::kSwapSeg);
-    if (nseg > 65535u) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernels (%zu)", nbeta);
-    F::swap_paths_kernel<<<dim3((unsigned)((npb + 255) / 256), nseg), 256, 0, ctx->stream>>>(sp);
+    if (nseg > 65535u) return fail(ctx, SCORUS_ERR_INVALID_ARG, "too many rungs for the swap kernels (%zu)", (size_t)nbeta);
+    rc = ensure(ctx, (void **)&ctx->d_chain, &ctx->chain_cap, (size_t)nseg * npb * sizeof(F::SwapSeg));
+    if (rc) return rc;
+    sp.tbl_seg = reinterpret_cast<F::SwapSeg *>(ctx->d_chain);
+    F::swap_paths_kernel<<<dim3((unsigned)((npb + 127) / 128), nseg), 256, 0, ctx->stream>>>(sp);
     const unsigned T = 128;
-    // per-stage beta differences and exchange counters of a block in shared memory when the ladder is short enough
-    const size_t walk_smem = (size_t)(nbeta - 1) * (sizeof(float) + sizeof(unsigned int));
+    // per-stage exchange counters of a block in shared memory when the ladder is short enough
     if (nbeta - 1 <= F::kSwapSmemStages)
-        F::swap_walk_kernel<true><<<(unsigned)((npb + T - 1) / T), T, walk_smem, ctx->stream>>>(sp);
+        F::swap_walk_kernel<true><<<(unsigned)((npb + T - 1) / T), T, (size_t)(nbeta - 1) * sizeof(unsigned int), ctx->stream>>>(sp);
     else
         F::swap_walk_kernel<false><<<(unsigned)((npb + T - 1) / T), T, 0, ctx->stream>>>(sp);
     const uint32_t vpr = ctx->pitch / 2;  // float2 chunks per row

@@ -173,6 +173,11 @@ template <> __host__ __device__ __forceinline__ float real_nan<float>()
 template <typename T> __host__ __device__ __forceinline__ T swap_guard();
 template <> __host__ __device__ __forceinline__ double swap_guard<double>() { return 1e-5; }
 template <> __host__ __device__ __forceinline__ float swap_guard<float>() { return 1e-4f; }
+// ... and what is added to the band per unit of the magnitudes that enter the threshold, against the rounding of the
+// threshold itself (thousands of ulps of T)
+template <typename T> __host__ __device__ __forceinline__ T swap_round_guard();
+template <> __host__ __device__ __forceinline__ double swap_round_guard<double>() { return 1e-12; }
+template <> __host__ __device__ __forceinline__ float swap_round_guard<float>() { return 1e-5f; }
 
 // Goodman-Weare stretch factor from a unit uniform: src/mcmc/utils.rs:39-44 with
 // p = u * 2(sqrt a - 1/sqrt a);  inv_sqrt_a and range are computed once on the host.

@@ -70,25 +70,22 @@ __global__ void __launch_bounds__(1024) exact_jvec_kernel(uint64_t seed, uint64_
 
 
 // The sweep is latency, not work: 16384 chains are 512 warps -- a few per SM -- so every instruction of a chain's
-// thread is paid at its full latency.  History (profiles/r2_notes.md section 2): one dependent loop per chain with keys,
+// thread is paid at its full latency, and a lone warp per scheduler issues IN ORDER: whatever is not on the critical path
+// still stands in front of it.  History (profiles/r2_notes.md section 2): one dependent loop per chain with keys,
 // bijection, a DRAM-latency log-prob load, a Philox draw and an exp per stage: 76 us at 64 rungs x 16384 chains, as long
 // as a step; uniforms hoisted into a parallel kernel and the chain split in two passes per thread (slots, then
-// decisions): 9.7 + 43.8 us, still 188 instructions per stage issued by a lone warp per scheduler.  What has to be
-// sequential PER CHAIN is only the carry of the travelling walker; which slots a chain visits is a function of the
-// permutations alone, and every slot of a rung lies on exactly one chain -- so the slot walk parallelises over
-// SEGMENTS of the ladder as well as over chains:
-//   * swap_paths_kernel, one thread per (segment g of kSwapSeg stages, hot slot x of the segment's first stage): walks
-//     the sub-chain that starts at x (bijection or jinv, integer work), then -- independent per stage -- draws the
-//     swap uniform of each visited cold slot, takes its logarithm, gathers the cold slot's log-prob, and writes the
-//     three into tables indexed [stage][x].  ceil((B-1)/kSwapSeg) x npb threads: 4096 warps at c4, throughput-bound.
-//   * swap_walk_kernel, one thread per chain: per segment ONE dependent fetch (the records of sub-chain x, all stages at
-//     once, and with the last of them the next segment's x; the next segment is requested before this one is decided),
-//     then per stage the decision r < min(1, exp(x)), x = (beta_cold - beta_hot)(lp_carry - lp_cold), utils.rs:63-69,105,
-//     taken WITHOUT the exp wherever ln r and x are not within 1e-9 of each other: ln r < x - d  =>  r < exp(x) (1 - 1e-9...),
-//     far outside the rounding of either side, so the shortcut returns exactly what the exp comparison returns; the
-//     one-in-10^9 close calls, r = 0 and non-finite x take the literal path.  The dependent chain per stage is two adds,
-//     two multiplies, the compares and a select.
-constexpr uint32_t kSwapSeg = 8;  // stages per segment
+// decisions): 9.7 + 43.8 us; slot walk parallel over segments with one 16-byte record per (stage, x), eight scattered
+// sectors per chain and segment: 14 + 21 us, bound by the scattered misses (a separate decide / emit pair: 17 + 11).
+// What has to be sequential PER CHAIN is only the carry of the travelling walker's log-prob; which slots a chain visits
+// is a function of the permutations alone, and every slot of a rung lies on exactly one chain:
+//   * swap_paths_kernel, threads over (segment g of kSwapSeg stages, hot slot x of the segment's first stage, half h):
+//     walks the sub-chain that starts at x (bijection or jinv, integer work), then -- independent per stage, one half of
+//     the segment per thread -- draws the swap uniform of each visited cold slot, gathers the cold slot's log-prob and
+//     turns the decision into a threshold on the carried log-prob (SwapSeg, swap_params.cuh).  8192 warps at c4.
+//   * swap_walk_kernel, one thread per chain: per segment ONE dependent fetch (the chain's SwapSeg block: contiguous; its
+//     last cold slot names the next segment's block, which is requested before this segment is decided), then per stage
+//     two compares of the carried log-prob and the selects; inside the band (one decision in 10^4..10^5), for r outside
+//     (0, 1) and for non-finite values the literal expression r < min(1, exp(x)), utils.rs:63-69,105.
 
 // swap uniform of (stage s, cold slot j2); hot rung i = nbeta-1-s
 __device__ __forceinline__ double swap_uniform(const SwapParams &p, uint32_t s, uint32_t j2)
@@ -100,26 +97,43 @@ __device__ __forceinline__ double swap_uniform(const SwapParams &p, uint32_t s, 
 
 __global__ void __launch_bounds__(256) swap_paths_kernel(const SwapParams p)
 {
+    constexpr uint32_t kHalf = kSwapSeg / 2;
+    constexpr uint32_t kXs = 128;                            // slots x per block, two threads (halves) each
+    constexpr uint32_t NQ = sizeof(SwapSeg) / 16;            // 16-byte pieces of a block of the table
+    constexpr uint32_t NT = kHalf * sizeof(double) / 16;     // ... of a half of mid[] / lp[]
+    constexpr uint32_t kLpCol = kSwapSeg * sizeof(double) / 16, kWCol = 2 * kLpCol, kColdCol = kWCol + kSwapSeg * 4 / 16;
+    static_assert(kHalf == 4 && kColdCol + 2 == NQ, "layout of SwapSeg");
+    // the block's part of the table, staged so that it leaves in whole cache lines (a thread's pieces are 16..32 bytes
+    // at a stride of sizeof(SwapSeg): written straight to global memory they cost the load/store unit one slot per lane
+    // and piece, 6 us more at c4); rows padded by one piece: conflict-free 16-byte accesses
+    __shared__ int4 stage[kXs * (NQ + 1)];
     __shared__ uint32_t seg_keys[kSwapSeg][8];
+    __shared__ double seg_inv_db[kSwapSeg];
     const uint32_t B = p.nbeta, npb = p.npb, S = B - 1u;
-    const uint32_t s0 = blockIdx.y * kSwapSeg;
+    const uint32_t g = blockIdx.y, s0 = g * kSwapSeg;
     const uint32_t ns = min(kSwapSeg, S - s0);
-    if (!p.jinv) {
-        if (threadIdx.x < ns) {
-            const BijKeys K = bij_keys(p.seed, p.swap_call, ST_SWAP_PERM, B - 1u - (s0 + threadIdx.x));
+    // which half of the segment's stages this thread draws for (its walk stops where its half ends)
+    const uint32_t xl = threadIdx.x % kXs, h = threadIdx.x / kXs;
+    const uint32_t k_lo = h * kHalf, k_hi = min(k_lo + kHalf, ns);
+    if (threadIdx.x < ns) {
+        const uint32_t i = B - 1u - (s0 + threadIdx.x);
+        if (!p.jinv) {
+            const BijKeys K = bij_keys(p.seed, p.swap_call, ST_SWAP_PERM, i);
 #pragma unroll
             for (int q = 0; q < 8; ++q) seg_keys[threadIdx.x][q] = K.k[q];
         }
-        __syncthreads();
+        const double db = __ldg(p.beta + i - 1u) - __ldg(p.beta + i);  // utils.rs:63-66: (beta2 - beta1), hot rung i
+        seg_inv_db[threadIdx.x] = db > 0.0 ? 1.0 / db : real_nan<double>();
     }
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= npb) return;
+    __syncthreads();
+    const uint32_t x0 = blockIdx.x * kXs;
+    const uint32_t x = min(x0 + xl, npb - 1u);  // (threads past the last slot shadow it; their rows are not written out)
     // the sub-chain's slots: hot slot a of stage s meets cold slot j2 = next_s(a), the hot slot of stage s + 1
     uint32_t j2v[kSwapSeg];
     uint32_t a = x;
 #pragma unroll
     for (uint32_t k = 0; k < kSwapSeg; ++k) {
-        if (k < ns) {
+        if (k < k_hi) {
             uint32_t j2;
             if (p.jinv) {
                 j2 = __ldg(p.jinv + (size_t)(s0 + k) * npb + a);
@@ -133,42 +147,88 @@ __global__ void __launch_bounds__(256) swap_paths_kernel(const SwapParams p)
             a = j2;
         }
     }
-    // per stage, independent of one another: cold log-prob, ln r
+    // per stage, independent of one another: cold log-prob, threshold, band
+    double mid[kHalf], lpv[kHalf];
+    float wv[kHalf];
+    uint32_t cv[kHalf];
 #pragma unroll
-    for (uint32_t k = 0; k < kSwapSeg; ++k) {
-        if (k < ns) {
-            const uint32_t s = s0 + k, i = B - 1u - s, j2 = j2v[k];
+    for (uint32_t kk = 0; kk < kHalf; ++kk) {
+        const uint32_t k = k_lo + kk;
+        mid[kk] = real_nan<double>(); lpv[kk] = 0.0; wv[kk] = 0.0f; cv[kk] = 0u;
+        if (k < k_hi) {
+            const uint32_t s = s0 + k, i = B - 1u - s, j2 = h ? j2v[kHalf + kk] : j2v[kk];  // (constant indices: registers)
             const double r = swap_uniform(p, s, j2);
-            SwapRec rec;
-            rec.lp = __ldg(p.lp_src + (size_t)(i - 1u) * npb + j2);
-            // ln r in f32: the decision's guard band is orders of magnitude wider than the rounding (swap_walk_kernel).
-            // Anything but 0 < r < 1 (only a caller-supplied r can be) is marked NaN and decided by the literal expression
-            rec.lr = (r > 0.0 && r < 1.0) ? logf((float)r) : real_nan<float>();
-            rec.cold = (i - 1u) * npb + j2;
-            p.tbl_rec[(size_t)s * npb + x] = rec;
+            const double lp_cold = __ldg(p.lp_src + (size_t)(i - 1u) * npb + j2);
+            // ln r in f32 and 1/db instead of a division: their errors (1e-7 relative) are far inside the band.
+            // Anything but 0 < r < 1 (only a caller-supplied r can be) leaves mid = NaN: decided by the literal expression
+            const double L = (r > 0.0 && r < 1.0) ? (double)logf((float)r) : real_nan<double>();
+            const double inv_db = seg_inv_db[k];
+            const double q = L * inv_db;
+            // band: the old guard of the exponent (ln r vs x within 1e-5 (1 + |ln r|)) carried over to log-prob units,
+            // plus the rounding of mid itself; rounded up into f32
+            const double w = (swap_guard<double>() * (1.0 + fabs(L))) * inv_db + swap_round_guard<double>() * (fabs(lp_cold) + fabs(q));
+            mid[kk] = lp_cold + q;
+            lpv[kk] = lp_cold;
+            wv[kk] = (float)w * 1.001f;
+            cv[kk] = (i - 1u) * npb + j2;
         }
     }
+    // this thread's half of row xl (for the stages past the ladder's end: mid = NaN, never read)
+    if (p.debug_direct_store) {  // measurement / debugging only: straight to global memory
+        if (x0 + xl < npb) {
+            SwapSeg *blk = p.tbl_seg + (size_t)g * npb + x;
+            int4 v[NT];
+            memcpy(v, mid, sizeof(mid));
+#pragma unroll
+            for (uint32_t q = 0; q < NT; ++q) reinterpret_cast<int4 *>(blk->mid + k_lo)[q] = v[q];
+            memcpy(v, lpv, sizeof(lpv));
+#pragma unroll
+            for (uint32_t q = 0; q < NT; ++q) reinterpret_cast<int4 *>(blk->lp + k_lo)[q] = v[q];
+            int4 u;
+            memcpy(&u, wv, 16);
+            *reinterpret_cast<int4 *>(blk->w + k_lo) = u;
+            memcpy(&u, cv, 16);
+            *reinterpret_cast<int4 *>(blk->cold + k_lo) = u;
+        }
+        return;
+    }
+    {
+        int4 *row = stage + xl * (NQ + 1u);
+        int4 v[NT];
+        memcpy(v, mid, sizeof(mid));
+#pragma unroll
+        for (uint32_t q = 0; q < NT; ++q) row[h * NT + q] = v[q];
+        memcpy(v, lpv, sizeof(lpv));
+#pragma unroll
+        for (uint32_t q = 0; q < NT; ++q) row[kLpCol + h * NT + q] = v[q];
+        int4 u;
+        memcpy(&u, wv, 16);
+        row[kWCol + h] = u;
+        memcpy(&u, cv, 16);
+        row[kColdCol + h] = u;
+    }
+    __syncthreads();
+    const uint32_t nrows = min(kXs, npb - x0);
+    int4 *dst = reinterpret_cast<int4 *>(p.tbl_seg + (size_t)g * npb + x0);
+    for (uint32_t e = threadIdx.x; e < nrows * NQ; e += blockDim.x) dst[e] = stage[(e / NQ) * (NQ + 1u) + e % NQ];
 }
 
-// kSmem: the per-stage beta differences and exchange counters of the block live in shared memory (any ladder of up to
-// kSwapSmemStages stages; longer ones read beta and count through global memory)
-constexpr uint32_t kSwapSmemStages = 3072;
+// kSmem: the exchange counters of the block live in shared memory (any ladder of up to kSwapSmemStages stages; longer
+// ones count through global memory)
+constexpr uint32_t kSwapSmemStages = 8192;
 
 template <bool kSmem>
 __global__ void __launch_bounds__(128) swap_walk_kernel(const SwapParams p)
 {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const uint32_t B = p.nbeta, npb = p.npb, S = B - 1u, T = blockDim.x, tid = threadIdx.x;
-    double *dbeta = reinterpret_cast<double *>(walk_smem);            // [S] beta_cold - beta_hot of stage s
-    unsigned int *stage_cnt = reinterpret_cast<unsigned int *>(dbeta + S);  // [S] accepted exchanges of this block
+    unsigned int *stage_cnt = reinterpret_cast<unsigned int *>(walk_smem);  // [S] accepted exchanges of this block
     const bool count = p.stage_swapped != nullptr;
     if constexpr (kSmem) {
-        for (uint32_t s = tid; s < S; s += T) {
-            const uint32_t i = B - 1u - s;
-            dbeta[s] = __ldg(p.beta + i - 1u) - __ldg(p.beta + i);  // utils.rs:63-66: (beta2 - beta1), hot rung i
-            stage_cnt[s] = 0u;
+        if (count) {
+            for (uint32_t s = tid; s < S; s += T) stage_cnt[s] = 0u;
+            __syncthreads();
         }
-        __syncthreads();
     }
     // every lane runs the sweep (ballots stay whole-warp); lanes past the last chain shadow it and write nothing
     const uint32_t c_raw = blockIdx.x * T + tid;
@@ -184,62 +244,47 @@ __global__ void __launch_bounds__(128) swap_walk_kernel(const SwapParams p)
         if (p.out) {
             SwapOut o;
             o.lp = lp; o.src = src; o.pad = 0u;
-            p.out[slot] = o;
+            st16(p.out + slot, o);
         } else {
             p.src[slot] = src;
             p.lp[slot] = lp;
         }
     };
-    SwapRec recn[kSwapSeg];
-    double dbn[kSwapSeg];
-    // the records of sub-chain x over the stages of the segment that starts at s0 (stages past the ladder's end re-read
-    // its last record, never used: no select behind the loads)
-    auto fetch = [&](uint32_t s0, uint32_t x) {
-#pragma unroll
-        for (uint32_t k = 0; k < kSwapSeg; ++k) {
-            const uint32_t s = s0 + k < S ? s0 + k : S - 1u;
-            recn[k] = p.tbl_rec[(size_t)s * npb + x];
-            if constexpr (kSmem) dbn[k] = dbeta[s];
-            else dbn[k] = __ldg(p.beta + (B - 2u - s)) - __ldg(p.beta + (B - 1u - s));
-        }
-    };
+    SwapSeg nxt = ld16(p.tbl_seg + c);
     auto segment = [&](uint32_t s0, auto full_tag) {
         constexpr bool kFull = decltype(full_tag)::value;
-        SwapRec rec[kSwapSeg];
-        uint32_t cold[kSwapSeg];
-        double db[kSwapSeg];
-#pragma unroll
-        for (uint32_t k = 0; k < kSwapSeg; ++k) { rec[k] = recn[k]; cold[k] = recn[k].cold; db[k] = dbn[k]; }
+        const SwapSeg sg = nxt;
         if constexpr (kFull) {
             // the next segment's sub-chain starts where this one ends: requested before this segment is decided
-            if (s0 + kSwapSeg < S) fetch(s0 + kSwapSeg, cold[kSwapSeg - 1u] - (B - 1u - s0 - kSwapSeg) * npb);
+            if (s0 + kSwapSeg < S)
+                nxt = ld16(p.tbl_seg + (size_t)(s0 / kSwapSeg + 1u) * npb + (sg.cold[kSwapSeg - 1u] - (B - 1u - s0 - kSwapSeg) * npb));
         }
         uint32_t swbits = 0;
 #pragma unroll
         for (uint32_t k = 0; k < kSwapSeg; ++k) {
             const uint32_t s = s0 + k;
             if (kFull || s < S) {  // hottest stage first (utils.rs:89-108)
-                const double lp_cold = rec[k].lp, lr = (double)rec[k].lr;
-                const double x = db[k] * (-lp_cold + carry_lp);  // exchange_prob's exponent, utils.rs:63-66
-                const double d = swap_guard<double>() * (1.0 + fabs(x));
-                const bool c1 = (lr == lr) & (x >= d);  // exp(x) > 1: probability 1, and 0 < r < 1
-                const bool c2 = lr < x - d;             // r < exp(x) < 1 by a margin far above any rounding
-                const bool c3 = lr > x + d;             // r > exp(x) by such a margin
-                bool sw = c1 | c2;
-                if (__builtin_expect(!(c1 | c2 | c3), 0)) {
-                    // too close to call, r outside (0, 1), or x not finite: the literal expression
+                const double lp_cold = sg.lp[k], wd = (double)sg.w[k];
+                const double hi = sg.mid[k] + wd, lo = sg.mid[k] - wd;
+                const bool up = carry_lp > hi;  // r < exp(x) by a margin far above any rounding (or x > 0)
+                const bool dn = carry_lp < lo;  // r > exp(x) by such a margin
+                bool sw = up;
+                if (__builtin_expect(!(up | dn), 0)) {
+                    // inside the band, r outside (0, 1), or something not finite: the literal expression
                     const uint32_t i = B - 1u - s;
-                    const double r = swap_uniform(p, s, cold[k] - (i - 1u) * npb);
+                    const double r = swap_uniform(p, s, sg.cold[k] - (i - 1u) * npb);
+                    const double beta1 = __ldg(p.beta + i), beta2 = __ldg(p.beta + i - 1u);
+                    const double x = (beta2 - beta1) * (-lp_cold + carry_lp);  // exchange_prob's exponent, utils.rs:63-66
                     const double ex = exp(x);
                     const double ep = ex > 1.0 ? 1.0 : ex;
                     sw = r < ep;  // utils.rs:105 (NaN -> no swap)
                 }
                 // swap: the cold walker comes up and is final here, the carried walker goes down; else the carried
                 // walker stays here and the cold one travels on
-                if (valid) store_slot(hot, sw ? cold[k] : carry_src, sw ? lp_cold : carry_lp);
-                carry_src = sw ? carry_src : cold[k];
+                if (valid) store_slot(hot, sw ? sg.cold[k] : carry_src, sw ? lp_cold : carry_lp);
+                carry_src = sw ? carry_src : sg.cold[k];
                 carry_lp = sw ? carry_lp : lp_cold;
-                hot = cold[k];
+                hot = sg.cold[k];
                 swbits |= (sw ? 1u : 0u) << k;
             }
         }
@@ -250,24 +295,26 @@ __global__ void __launch_bounds__(128) swap_walk_kernel(const SwapParams p)
             for (uint32_t k = 0; k < kSwapSeg; ++k)
                 if (kFull || s0 + k < S) {
                     const uint32_t s = s0 + k, i = B - 1u - s;
-                    p.swapped_out[(size_t)s * npb + (cold[k] - (i - 1u) * npb)] = (swbits >> k) & 1u;
+                    p.swapped_out[(size_t)s * npb + (sg.cold[k] - (i - 1u) * npb)] = (swbits >> k) & 1u;
                 }
         }
         if (count) {
-            // all lanes of the warp ran the same stages: one atomic per warp per stage, off the carry chain
+            // all lanes of the warp ran the same stages: lane k gathers the count of stage k, one atomic instruction per
+            // warp and segment, off the carry chain
+            unsigned mine = 0;
 #pragma unroll
-            for (uint32_t k = 0; k < kSwapSeg; ++k)
-                if (kFull || s0 + k < S) {
-                    const unsigned m = __ballot_sync(0xffffffffu, (swbits >> k) & 1u);
-                    if ((tid & 31u) == 0u && m) {
-                        if constexpr (kSmem) atomicAdd(stage_cnt + s0 + k, (unsigned)__popc(m));
-                        else atomicAdd(p.stage_swapped + (B - 2u - s0 - k), (unsigned long long)__popc(m));
-                    }
-                }
+            for (uint32_t k = 0; k < kSwapSeg; ++k) {
+                const unsigned m = __ballot_sync(0xffffffffu, (swbits >> k) & 1u);
+                if ((tid & 31u) == k) mine = (unsigned)__popc(m);
+            }
+            const uint32_t k = tid & 31u;
+            if (k < kSwapSeg && s0 + k < S && mine) {
+                if constexpr (kSmem) atomicAdd(stage_cnt + s0 + k, mine);
+                else atomicAdd(p.stage_swapped + (B - 2u - s0 - k), (unsigned long long)mine);
+            }
         }
     };
 
-    fetch(0u, c);
     uint32_t s0 = 0;
     for (; s0 + kSwapSeg <= S; s0 += kSwapSeg) segment(s0, std::true_type{});
     if (s0 < S) segment(s0, std::false_type{});
@@ -308,7 +355,7 @@ __global__ void __launch_bounds__(256) apply_swap_kernel(const double2 *__restri
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const uint32_t slot = (uint32_t)(g / vec_per_row);
         const uint32_t v = (uint32_t)(g - (size_t)slot * vec_per_row);
-        const SwapOut o = out[slot];
+        const SwapOut o = ld16(out + slot);
         dst[g] = src_ens[(size_t)o.src * vec_per_row + v];
         if (v == 0u) lp[slot] = o.lp;
     }

@@ -6,11 +6,19 @@
 
 namespace scorus {
 
-// what the sub-chain starting at hot slot x meets at one stage: one 16-byte scattered read per stage of the sweep
-struct __align__(16) SwapRec {
-    double lp;      // log-prob of the cold slot
-    float lr;       // ln r of its swap uniform, rounded to f32 (the guard band of the decision covers the rounding); NaN: decide literally
-    uint32_t cold;  // global index of the cold slot
+constexpr uint32_t kSwapSeg = 8;  // stages per segment of the ladder (swap_kernel.cuh)
+
+// What the sub-chain that starts at hot slot x of a segment's first stage meets over the segment's stages, one
+// contiguous block per (segment, x): the sweep fetches a whole segment of a chain with consecutive 16-byte loads of one
+// or two cache lines.  Per stage: the carried walker swaps with the cold slot's iff r < min(1, exp(db (lp_carry -
+// lp_cold))), db = beta_cold - beta_hot (utils.rs:63-69,105)  <=>  lp_carry > lp_cold + ln r / db = mid, so the sweep
+// compares the carried log-prob with mid -/+ w and evaluates the literal expression only inside that band; w covers
+// the rounding of everything on both sides by orders of magnitude (swap_paths_kernel).
+struct __align__(16) SwapSeg {
+    double mid[kSwapSeg];     // NaN: decide literally (r outside (0, 1), db <= 0, non-finite log-prob)
+    double lp[kSwapSeg];      // log-prob of the cold slot
+    float w[kSwapSeg];        // half-width of the literal band around mid
+    uint32_t cold[kSwapSeg];  // global index of the cold slot
 };
 
 // interleaved result of a swap, [n] indexed by slot: one 16-byte scattered write per slot instead of two, and the step
@@ -20,6 +28,33 @@ struct __align__(16) SwapOut {
     uint32_t src;  // slot its row is in before the rows move
     uint32_t pad;
 };
+
+// the records move as 16-byte accesses (the compiler splits a struct copy into 8-byte ones, and a scattered access costs
+// the load/store unit one slot per lane whatever its width)
+#ifdef __CUDACC__
+template <class R>
+__device__ __forceinline__ R ld16(const R *p)
+{
+    static_assert(sizeof(R) % 16 == 0, "16-byte records");
+    constexpr int NQ = sizeof(R) / 16;
+    int4 v[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = reinterpret_cast<const int4 *>(p)[q];
+    R o;
+    memcpy(&o, v, sizeof(R));
+    return o;
+}
+template <class R>
+__device__ __forceinline__ void st16(R *p, const R &o)
+{
+    static_assert(sizeof(R) % 16 == 0, "16-byte records");
+    constexpr int NQ = sizeof(R) / 16;
+    int4 v[NQ];
+    memcpy(v, &o, sizeof(R));
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) reinterpret_cast<int4 *>(p)[q] = v[q];
+}
+#endif
 
 struct SwapParams {
     SwapOut *out;          // [n] out, interleaved -- or nullptr: results go to the two arrays lp / src below
@@ -32,9 +67,10 @@ struct SwapParams {
     uint8_t *swapped_out;  // [(nbeta-1)][npb] indexed by cold slot, or nullptr
     unsigned long long *stats;  // [2] swapped, [3] swap_proposed
     unsigned long long *stage_swapped;  // [nbeta-1] accepted exchanges between rung k and k+1, or nullptr
-    // scratch of the swap, [(nbeta-1)][npb], indexed [stage][hot slot x of the stage's segment start], written by
+    // scratch of the swap, [segments][npb], indexed [segment][hot slot x of the segment's first stage], written by
     // swap_paths_kernel for swap_walk_kernel
-    SwapRec *tbl_rec;
+    SwapSeg *tbl_seg;
+    uint32_t debug_direct_store;  // SCORUS_SWAP_DIRECT_STORE=1: swap_paths_kernel skips its shared-memory stage
     uint64_t seed, swap_call;
     uint32_t npb, nbeta, bij_bits;
 };
