@@ -515,8 +515,8 @@ def main():
         t_swap = max(t_both - t_step, 1e-6)
         swap_stage = {"ms_per_call": t_swap, "accepted_exchanges_per_call": moved,
                       "algorithmic_bytes_per_call": sw_bytes, "gbps": sw_bytes / (t_swap * 1e-3) / 1e9,
-                      "note": "swap + one step minus one step, 20 calls; bound by the chain kernel's B-1 dependent steps "
-                              "(latency), not by HBM"}
+                      "note": "swap + one step minus one step, 20 calls (the rows move inside the step that follows the "
+                              "swap); bound by the sweep's dependent steps and scattered accesses, not by HBM"}
         stats = s.stats()
 
     # ---- e2e: the reference-shaped call on pinned host buffers, copies inside the timed region ----

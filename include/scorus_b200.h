@@ -383,9 +383,12 @@ int scorus_set_stream(scorus_ctx *ctx, void *cuda_stream);
 int scorus_reset_stream(scorus_ctx *ctx);
 void *scorus_get_stream(scorus_ctx *ctx);
 /* device pointers of the resident state (the device-side `ensemble` / `cached_logprob`, src/mcmc/ensemble_sample.rs:
- * 109-110): ensemble rows are pitch_elems doubles apart.  The ensemble pointer is valid until the next
- * scorus_swap_walkers on this context: a ladder swap writes every row to its new slot in the context's second buffer
- * and the two buffers change roles (contexts attached to peers by scorus_ipc_attach keep their buffer). */
+ * 109-110): ensemble rows are pitch_elems doubles apart.  Both pointers are valid until the next
+ * scorus_swap_walkers on this context and must be read again after it: a ladder swap leaves its rows to the stretch
+ * step that follows, which writes every row to its new slot in the context's second buffer (the two buffers change
+ * roles); this call -- like every other entry point that looks at the ensemble -- first moves rows and log-probs of a
+ * pending swap to their slots, so what it returns is the state after the swap (contexts attached to peers by
+ * scorus_ipc_attach keep their buffer). */
 int scorus_device_buffers(scorus_ctx *ctx, double **ensemble, size_t *pitch_elems, double **logprob);
 /* what is left of `rng: &mut U` (src/mcmc/ensemble_sample.rs:111, src/mcmc/utils.rs:75) on the device:
  * RNG position = (step counter, swap-call counter, one-hot cycle counter); with the seed and a

@@ -30,6 +30,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include "rng.cuh"  // fma_t
 
 namespace scorus {
 
@@ -168,11 +169,46 @@ struct LpRastrigin {
     static constexpr bool kNeedsNext = false;  // terms() uses the coordinate after the lane's chunk
     static constexpr int kAcc = 1;
     double a, acc, base;
+    // cos(2 pi y) without a general-purpose cos: y - rint(y) is exact and |r| <= 1/2, cos(2 pi r) = -cos(2 pi (1/2 - |r|))
+    // beyond a quarter period, and on [0, 1/4] an even polynomial in b (Taylor in b^2 to b^22: truncation 2e-17) by
+    // Horner -- twenty instructions and NO branch, so the twelve evaluations a lane makes per tile interleave; the
+    // library cos is 56 instructions behind a slow-path branch that serialises them (27 % of the c4 step's instructions
+    // and 29 % of its stall samples, profiles/r2b_c4_step_lines.txt).  Within 3.2e-16 of the true cos(2 pi y) (measured
+    // over 2e5 arguments in [-6, 6]); the reference's cos(fl(2 pi y)) is itself 5e-15 away from it -- the rounding of
+    // the argument -- so the two differ by that much per term, far inside the 1e-12 sum|terms| bar of the parity tests.
+    static __device__ __forceinline__ double cos2pi(double y)
+    {
+        const double r = y - rint(y);
+        const double ar = fabs(r);
+        const bool flip = ar > 0.25;
+        const double b = flip ? 0.5 - ar : ar;
+        const double s = b * b;
+        // (-1)^k (2 pi)^(2k) / (2k)!, k = 1..11 (typed constants: the f32 instantiation converts them)
+        const double c1 = -0x1.3bd3cc9be45dep+4, c2 = 0x1.03c1f081b5ac4p+6, c3 = -0x1.55d3c7e3cbffap+6, c4 = 0x1.e1f506891babbp+5,
+                     c5 = -0x1.a6d1f2a204a8cp+4, c6 = 0x1.f9d38a3763cc3p+2, c7 = -0x1.b6e24f44b128fp+0, c8 = 0x1.20c62c2f2d7f5p-2,
+                     c9 = -0x1.2a0c591af8314p-5, c10 = 0x1.ef6e308d6d1c4p-9, c11 = -0x1.52ae4120fde27p-12, one = 1.0;
+        double p;
+        if constexpr (sizeof(double) == 8) {  // (the f32 instantiation reads sizeof(float): seven terms are its 1e-8)
+            p = c11;
+            p = fma_t(p, s, c10);
+            p = fma_t(p, s, c9);
+            p = fma_t(p, s, c8);
+            p = fma_t(p, s, c7);
+        } else {
+            p = c7;
+        }
+        p = fma_t(p, s, c6);
+        p = fma_t(p, s, c5);
+        p = fma_t(p, s, c4);
+        p = fma_t(p, s, c3);
+        p = fma_t(p, s, c2);
+        p = fma_t(p, s, c1);
+        p = fma_t(p, s, one);
+        return flip ? -p : p;
+    }
     static __device__ __forceinline__ double term(double a, double y)
     {
-        const double two_pi = 2.0 * 3.14159265358979323846;
-        double arg = two_pi * y;
-        double c = a * cos(arg);
+        double c = a * cos2pi(y);  // examples/sample_rastrigin.rs:21: a * (2 pi x).cos()
         double sq = y * y;
         return c - sq;
     }

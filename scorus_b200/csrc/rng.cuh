@@ -190,6 +190,10 @@ __host__ __device__ __forceinline__ T z_from_uniform(T u01, T inv_sqrt_a, T rang
 }
 
 #ifdef __CUDACC__
+// fused multiply-add in T, whatever -fmad says (the kernels are built with -fmad=false: the reference rounds every
+// multiply and add; polynomial evaluations inside a transcendental are not the reference's arithmetic)
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 // streaming loads: read once, do not keep in L1 (the shared-memory carve-out leaves little).  One 16-byte (f64) or
 // 8-byte (f32) chunk = two coordinates.
 __device__ __forceinline__ double2 ld_stream(const double2 *p)
