@@ -134,7 +134,17 @@ static int global_matching_setup(scorus_ctx *ctx, double a, const scorus_ufs *uf
     if (ctx->lp_kind < 0) return fail(ctx, SCORUS_ERR_NO_LOGPROB, "call scorus_set_logprob first");
     if (!ctx->uploaded) return fail(ctx, SCORUS_ERR_NOT_UPLOADED, "call scorus_upload first");
     if (!(a > 1.0)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "stretch scale a must be > 1");
-    if (ufs->kind == SCORUS_UFS_MASK) return fail(ctx, SCORUS_ERR_INVALID_ARG, "host-evaluated masks are per shard: use scorus_sample_pt_fixed on a gathered ensemble");
+    // UpdateFlagSpec::Func (ensemble_sample.rs:31,52,150-153): the closure is called once per walker of the WHOLE
+    // ensemble in order, so over shards the mask covers all n_global walkers (every rank evaluates the same closure
+    // n_global times, as the single-GPU run does) and is indexed by global walker id
+    if (ufs->kind == SCORUS_UFS_MASK) {
+        if (!ufs->mask || ufs->mask_len > ctx->dim) return fail(ctx, SCORUS_ERR_INVALID_ARG, "bad mask");
+        for (size_t i = 0; i < ng; ++i) {
+            size_t c = 0;
+            for (size_t k = 0; k < ufs->mask_len; ++k) c += ufs->mask[i * ufs->mask_len + k] ? 1 : 0;
+            if (c == 0) return fail(ctx, SCORUS_ERR_NPHI_ZERO, "walker %zu has no update flag set", i);
+        }
+    }
     if (ctx->sequential || ctx->pitch > 256) return fail(ctx, SCORUS_ERR_INVALID_ARG, "whole-ensemble matching over shards needs the register kernel (dim <= 256, no SEQUENTIAL_SUM)");
     cudaSetDevice(ctx->device);
     StepParams &p = *pp;
@@ -148,6 +158,14 @@ static int global_matching_setup(scorus_ctx *ctx, double a, const scorus_ufs *uf
     p.flag_kind = (uint32_t)ufs->kind;
     *all_flags = ufs->kind == SCORUS_UFS_ALL;
     if (ufs->kind == SCORUS_UFS_PROB && (rc = set_prob_flags(ctx, &p, ufs->prob))) return rc;
+    if (ufs->kind == SCORUS_UFS_MASK) {
+        const size_t bytes = ng * ufs->mask_len;
+        if ((rc = ensure(ctx, (void **)&ctx->d_flags, &ctx->flags_cap, bytes ? bytes : 1))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_flags, ufs->mask, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // the caller's mask is released on return
+        p.flags_in = ctx->d_flags;
+        p.flag_len = (uint32_t)ufs->mask_len;
+    }
     // ids are global in this mode: no offsets on the stream keys, whole-rung matching
     p.npb = (uint32_t)(ng / nbeta);
     p.bij_bits = bij_bits(p.npb);
@@ -412,6 +430,7 @@ extern "C" int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs
     if (!ctx->d_peer_ens || ctx->world < 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "call scorus_ipc_attach first");
     if (ctx->n_global != ctx->n * (size_t)ctx->world) return fail(ctx, SCORUS_ERR_INVALID_ARG, "shards must be equal");
     if (ctx->n > (1u << 28)) return fail(ctx, SCORUS_ERR_INVALID_ARG, "at most 2^28 walkers per shard");
+    if (ufs->kind == SCORUS_UFS_MASK && nsteps != 1) return fail(ctx, SCORUS_ERR_INVALID_ARG, "a host-evaluated mask covers exactly one step");
     for (uint64_t s = 0; s < nsteps; ++s) {
         StepParams p;
         Geometry g;

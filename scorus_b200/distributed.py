@@ -30,6 +30,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
+from . import _lib as L
 from .ensemble_sample import LogProb, Sampler, UpdateFlagSpec
 
 
@@ -173,6 +174,7 @@ class ShardedSampler:
             self.global_every = 1
         dev = torch.cuda.current_device() if device is None else device
         self.device = torch.device("cuda", dev)
+        self._flogprob, self._seed, self._full = flogprob, seed, None
         self.sampler = Sampler(flogprob, self.n_local, dim, seed=seed, device=dev)
         self.sampler.set_shard(self.w_off, self.rung_off, n_walkers)
         if self.mode == "walkers":
@@ -210,6 +212,25 @@ class ShardedSampler:
     # -- the hot path
     def sample_pt(self, a: float, ufs: UpdateFlagSpec, beta_list: Sequence[float], nsteps: int = 1):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
+        if ufs.kind == L.UFS_MASK and self.world > 1:
+            # UpdateFlagSpec::Func (ensemble_sample.rs:31,52,150-153): the closure is called once per walker of the WHOLE
+            # ensemble, in order, every step.  Every rank holds the same closure in the same state, so every rank makes
+            # the same n_global calls -- the flags are then exactly the single-GPU run's -- and hands its shard (local
+            # step) or the whole matrix (whole-ensemble step: the owner of a pair needs both walkers' flags) on.
+            # UpdateFlagSpec.Mask: one step's flags of the whole ensemble, already evaluated.
+            if ufs.func is None and nsteps != 1:
+                raise ValueError("a mask covers exactly one step")
+            for _ in range(nsteps):
+                flags = ufs.evaluate(self.n_global) if ufs.func is not None else ufs.mask
+                if flags.shape[0] != self.n_global:
+                    raise ValueError(f"mask has {flags.shape[0]} rows for {self.n_global} walkers")
+                if self._step_is_local():
+                    flags = flags[self.w_off:self.w_off + self.n_local]
+                self._sample_pt(a, UpdateFlagSpec.Mask(flags), beta, 1)
+            return
+        self._sample_pt(a, ufs, beta, nsteps)
+
+    def _sample_pt(self, a: float, ufs: UpdateFlagSpec, beta: np.ndarray, nsteps: int):
         if self.mode == "rungs":
             local_beta = beta[self.rung_off:self.rung_off + self.nb_local]
             self.sampler.sample_pt(a, ufs, local_beta, nsteps)      # no communication
@@ -237,6 +258,13 @@ class ShardedSampler:
             self.sampler.sample_pt_global(a, ufs, beta, ens_all.data_ptr(), lp_all.data_ptr())
             done += 1
 
+    def _step_is_local(self) -> bool:
+        """Whether the step the schedule prescribes next pairs walkers inside this rank's shard (and so wants a shard's
+        worth of host-evaluated flags) rather than across the whole ensemble."""
+        if self.mode == "rungs" or self.matching == "local" or self.world == 1:
+            return True
+        return not is_exchange_step(self.sampler.counters[0], self.global_every)
+
     def sample_pt_host(self, ens_local: np.ndarray, lp_local: np.ndarray, a: float, ufs: UpdateFlagSpec,
                        beta_list: Sequence[float]):
         """The reference-shaped call (host buffers in, ONE step, host buffers out) on this rank's shard; collective.
@@ -259,14 +287,43 @@ class ShardedSampler:
     def twalk_sample(self, param, beta_list: Sequence[float], nsteps: int = 1):
         """twalk::sample (src/mcmc/twalk.rs:586-648) on this rank's shard.  Rung shards (whole rungs per rank):
         the matching never leaves a rung, so no communication and the same chain as one GPU.  Walker shards:
-        the matching is drawn inside the shard (`matching="local"` only)."""
+        the matching is drawn inside the shard (`matching="local"`), or over the whole ensemble with the compute
+        replicated on every rank (_twalk_replicated)."""
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
         if self.mode == "rungs":
             self.sampler.twalk_sample(param, beta[self.rung_off:self.rung_off + self.nb_local], nsteps)
             return
         if self.matching != "local" and self.world > 1:
-            raise NotImplementedError("the t-walk across walker shards supports matching='local' only")
+            self._twalk_replicated(param, beta, nsteps)
+            return
         self.sampler.twalk_sample(param, beta, nsteps)
+
+    def _twalk_replicated(self, param, beta: np.ndarray, nsteps: int):
+        """The t-walk under the reference's whole-rung matching (twalk.rs:600-612) across walker shards, REPLICATED:
+        the shards are all-gathered once per call, every rank steps the whole ensemble with the single-GPU kernel (same
+        seed and counters, so all ranks compute the same chain) and keeps its own rows.  Identical to the single-GPU
+        chain and no faster than it -- the t-walk kernels have no owner-computes form yet; rung shards (tempered runs)
+        and matching="local" are the paths that scale."""
+        t = self.torch
+        if self._full is None:
+            self._full = Sampler(self._flogprob, self.n_global, self.dim, seed=self._seed, device=self.device.index)
+            self._full.set_stream(self._stream.cuda_stream)
+            self._full.init_ensemble(0.0, 1.0)           # (marks the context as holding an ensemble; overwritten below)
+        self.ens, self.lp, self.pitch = device_views(self.sampler, self.device)
+        with t.cuda.stream(self._stream):
+            ens_all, lp_all, _ = self._gather_buffers()
+            self.dist.all_gather_into_tensor(ens_all, self.ens, group=self.group)
+            self.dist.all_gather_into_tensor(lp_all, self.lp, group=self.group)
+            fe, fl, _ = device_views(self._full, self.device)
+            fe.copy_(ens_all)
+            fl.copy_(lp_all)
+        self._full.counters = self.sampler.counters
+        self._full.twalk_sample(param, beta, nsteps)
+        with t.cuda.stream(self._stream):
+            fe, fl, _ = device_views(self._full, self.device)
+            self.ens.copy_(fe[self.w_off:self.w_off + self.n_local])
+            self.lp.copy_(fl[self.w_off:self.w_off + self.n_local])
+        self.sampler.counters = self._full.counters
 
     def hmc_sample_ensemble_pt(self, epsilon, beta_list: Sequence[float], l: int, param, nsteps: int = 1):
         """hmc::naive::sample_ensemble_pt (src/mcmc/hmc/naive.rs:122-292) on this rank's shard: walkers are
@@ -351,6 +408,9 @@ class ShardedSampler:
         if self.world > 1:
             self.dist.barrier(group=self.group)
         self.ens = self.lp = self._ens_all = self._lp_all = self._src_all = None
+        if self._full is not None:
+            self._full.close()
+            self._full = None
         self.sampler.close()
         self.sampler = None
 

@@ -120,8 +120,8 @@ def Mixture(sigma1: float, sigma2: float, m) -> LogProb:
 class UpdateFlagSpec:
     """enum UpdateFlagSpec { Prob(T), All, Func(&mut dyn FnMut() -> Vec<bool>) }"""
 
-    def __init__(self, kind: int, prob: float = 0.0, func: Optional[Callable[[], Sequence[bool]]] = None):
-        self.kind, self.prob, self.func = kind, prob, func
+    def __init__(self, kind: int, prob: float = 0.0, func: Optional[Callable[[], Sequence[bool]]] = None, mask=None):
+        self.kind, self.prob, self.func, self.mask = kind, prob, func, mask
 
     @classmethod
     def Prob(cls, p: float) -> "UpdateFlagSpec":
@@ -139,6 +139,23 @@ class UpdateFlagSpec:
         return cls(L.UFS_MASK, func=f)
 
     @classmethod
+    def Mask(cls, flags) -> "UpdateFlagSpec":
+        """The flags of ONE step as already evaluated, [n_walkers, flag_len] (what Func's closure returned, walker by
+        walker): how a sharded run hands each shard -- or the whole-ensemble step -- its rows of one evaluation."""
+        m = np.ascontiguousarray(np.asarray(flags).astype(np.uint8))
+        if m.ndim != 2:
+            raise ValueError("flags must be [n_walkers, flag_len]")
+        return cls(L.UFS_MASK, mask=m)
+
+    def evaluate(self, n: int) -> np.ndarray:
+        """Func: the closure called once per walker, in order (ensemble_sample.rs:150-153) -> [n, flag_len] uint8."""
+        rows = [np.asarray(self.func(), dtype=bool) for _ in range(n)]
+        lens = {r.size for r in rows}
+        if len(lens) != 1:
+            raise ValueError("Func must return flag vectors of one length per step")
+        return np.ascontiguousarray(np.stack(rows).astype(np.uint8))
+
+    @classmethod
     def OneHotCycle(cls) -> "UpdateFlagSpec":
         return cls(L.UFS_ONE_HOT_CYCLE)
 
@@ -149,14 +166,12 @@ class UpdateFlagSpec:
         u.prob = self.prob
         keep = None
         if self.kind == L.UFS_MASK:
-            rows = [np.asarray(self.func(), dtype=bool) for _ in range(n)]
-            lens = {r.size for r in rows}
-            if len(lens) != 1:
-                raise ValueError("Func must return flag vectors of one length per step")
-            flen = lens.pop()
+            keep = self.mask if self.mask is not None else self.evaluate(n)
+            if keep.shape[0] != n:
+                raise ValueError(f"mask has {keep.shape[0]} rows for {n} walkers")
+            flen = keep.shape[1]
             if flen > dim:
                 raise IndexError("update_flags longer than the walker (index panic, :70)")
-            keep = np.ascontiguousarray(np.stack(rows).astype(np.uint8))
             u.mask = keep.ctypes.data_as(C.POINTER(C.c_uint8))
             u.mask_len = flen
         return u, keep
@@ -203,6 +218,7 @@ class Sampler:
                     flags=(L.CFG_SEQUENTIAL_SUM if sequential_sum else 0) | (L.CFG_F32 if self.f32 else 0), reserved=0)
         _raise(self._lib.scorus_ctx_create(C.byref(self._ctx), C.byref(cfg)))
         self.n, self.dim, self.seed = n_walkers, dim, seed
+        self.n_global = n_walkers  # (set_shard: this context holds a shard of a larger ensemble)
         self.flogprob = None
         self.set_logprob(flogprob)
 
@@ -529,10 +545,11 @@ class Sampler:
     # -- sharding (one process per GPU; scorus_b200/distributed.py drives these)
     def set_shard(self, walker_offset: int, rung_offset: int, n_walkers_global: int):
         self._ok(self._lib.scorus_set_shard(self._ctx, walker_offset, rung_offset, n_walkers_global))
+        self.n_global = int(n_walkers_global)
 
     def sample_pt_global(self, a: float, ufs: UpdateFlagSpec, beta_list, ens_all_ptr: int, lp_all_ptr: int):
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
-        u, keep = ufs._c(self.n, self.dim)
+        u, keep = ufs._c(self.n_global if ufs.kind == L.UFS_MASK else self.n, self.dim)  # a mask covers the whole ensemble
         self._ok(self._lib.scorus_sample_pt_global(self._ctx, a, C.byref(u), _dp(beta), beta.size,
                                                    C.c_void_p(ens_all_ptr), C.c_void_p(lp_all_ptr)))
 
@@ -554,7 +571,7 @@ class Sampler:
         """Whole-ensemble matching over walker shards, one-sided (scorus_sample_pt_peer): the owner of a pair reads the
         partner's row from its home GPU over NVLink and writes both walkers' results back."""
         beta = np.ascontiguousarray(beta_list, dtype=np.float64)
-        u, keep = ufs._c(self.n, self.dim)
+        u, keep = ufs._c(self.n_global if ufs.kind == L.UFS_MASK else self.n, self.dim)  # a mask covers the whole ensemble
         self._ok(self._lib.scorus_sample_pt_peer(self._ctx, a, C.byref(u), _dp(beta), beta.size, nsteps))
 
     def peer_read_bandwidth(self, peer: int, nbytes: int = 0, iters: int = 5):

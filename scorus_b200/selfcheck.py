@@ -24,6 +24,19 @@ def _all_ok(torch, dist, ok: bool) -> bool:
     return bool(flag.item())
 
 
+def _cycling_flags(dim):
+    """A stateful Func closure (in the spirit of examples/sample_high_dim.rs:59-65): two flags, advancing per call."""
+    state = {"i": 0}
+
+    def f():
+        v = np.zeros(dim, dtype=bool)
+        v[state["i"] % dim] = True
+        v[(state["i"] * 3 + 1) % dim] = True
+        state["i"] += 1
+        return v
+    return f
+
+
 def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matching="global", p2p_swap=True, twalk=False,
              global_every=1, steps_per_call=1, log=print):
     """One sharded configuration against the single-GPU chain of the whole ensemble.  -> identical (bool)."""
@@ -44,6 +57,9 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
         ref.set_matching_blocks(world, 0, 0 if matching == "local" else global_every)
     lo, hi = sh.w_off, sh.w_off + sh.n_local
     sh.upload(np.ascontiguousarray(ens[lo:hi]), None)
+    ufs_ref = ufs_sh = ufs
+    if isinstance(ufs, str) and ufs == "func":   # two copies of one stateful closure: the reference's and the sharded run's
+        ufs_ref, ufs_sh = UpdateFlagSpec.Func(_cycling_flags(dim)), UpdateFlagSpec.Func(_cycling_flags(dim))
     k = 0
     while k < steps:
         if swap_every and k % swap_every == 0:
@@ -56,8 +72,8 @@ def run_case(name, flogprob, n, dim, nbeta, ufs, steps, swap_every, box, matchin
             ref.twalk_sample(TWalkParams.new(dim), beta, run)
             sh.twalk_sample(TWalkParams.new(dim), beta, run)
         else:
-            ref.sample_pt(2.0, ufs, beta, run)
-            sh.sample_pt(2.0, ufs, beta, run)
+            ref.sample_pt(2.0, ufs_ref, beta, run)
+            sh.sample_pt(2.0, ufs_sh, beta, run)
         k += run
     want_e, want_lp = ref.download()
     got_e, got_lp = sh.download()
@@ -256,6 +272,13 @@ def sharded_parity_cases(quick: bool = False, log=print):
                         twalk=True, log=log))
     res.append(run_case("twalk_rosenbrock_pt_small_rungs", Rosenbrock(), 64 * 2 * world, 20, 2 * world, None, 12, 3,
                         (0.9, 1.1), twalk=True, log=log))
+    # UpdateFlagSpec::Func over shards: every rank makes the closure's n_global calls; one-sided, k-schedule, all-gather
+    res.append(run_case("rosenbrock_func_flags_one_sided_every2", Rosenbrock(), 512 * world, 16, 1, "func", 6, 0, (0.9, 1.1),
+                        matching="p2p", global_every=2, log=log))
+    res.append(run_case("gauss_func_flags_allgather", Gaussian(0.5), 64 * world, 6, 1, "func", 4, 0, (-1.0, 1.0), log=log))
+    # t-walk with the whole-rung matching across walker shards (replicated compute)
+    res.append(run_case("twalk_rosenbrock_walker_shards_whole_matching", Rosenbrock(), 2048 * world, 20, 1, None, 6, 0,
+                        (0.9, 1.1), matching="p2p", twalk=True, steps_per_call=2, log=log))
     res.append(run_hmc(world, log=log))
     res.append(run_hmc_walker_shards(world, log=log))
     res.append(run_host_call(world, log=log))

@@ -207,3 +207,28 @@ def test_owner_computes_exchange_step_world2_gloo(oracle):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) == [1] * world
+
+
+def test_update_flag_spec_func_is_evaluated_once_per_walker_and_mask_carries_one_step():
+    """UpdateFlagSpec::Func (ensemble_sample.rs:31,52,150-153) over shards: every rank evaluates the closure for the whole
+    ensemble (`evaluate`) and hands rows of that one evaluation on (`Mask`)."""
+    import pytest
+    from scorus_b200 import UpdateFlagSpec
+    calls = []
+
+    def f():
+        calls.append(len(calls))
+        return [len(calls) % 2 == 0, True, False]
+    spec = UpdateFlagSpec.Func(f)
+    m = spec.evaluate(5)
+    assert m.shape == (5, 3) and m.dtype == np.uint8 and len(calls) == 5
+    assert m[:, 0].tolist() == [0, 1, 0, 1, 0] and m[:, 1].all() and not m[:, 2].any()
+    shard = UpdateFlagSpec.Mask(m[2:4])
+    st, keep = shard._c(2, 4)
+    assert st.mask_len == 3 and keep.shape == (2, 3) and len(calls) == 5      # nothing is evaluated again
+    with pytest.raises(ValueError):
+        shard._c(3, 4)                                                         # rows != walkers
+    with pytest.raises(IndexError):
+        shard._c(2, 2)                                                         # flags longer than a walker (:70)
+    with pytest.raises(ValueError):
+        UpdateFlagSpec.Mask(np.ones(4))

@@ -453,6 +453,30 @@ def test_pso_hand_off_from_ensemble(sb, oracle):
     assert np.array_equal(np.array([p.position for p in swarm]), e) and np.array_equal([p.fitness for p in swarm], lp)
 
 
+def test_pso_maximizer_from_a_resident_sampler(sb, oracle):
+    """ParticleSwarmMaximizer::from_ensemble (src/opt/pso.rs:108-132) on the ensemble a sampler holds: the cached
+    log-probs are the first fitness; `sample` (:214-272) re-evaluates the fitness on the device (update_fitness,
+    :194-212) and the swarm climbs."""
+    g = np.random.default_rng(9)
+    n, dim = 64, 6
+    ens = np.ascontiguousarray(g.uniform(0.5, 1.5, (n, dim)))
+    with sb.Sampler(sb.Rosenbrock(), n, dim, seed=2) as s:
+        s.upload(ens, None)
+        s.sample(2.0, sb.UpdateFlagSpec.All(), 3)
+        e, lp = s.download()
+        m = sb.pso.ParticleSwarmMaximizer.from_sampler(s, guess=np.ones(dim))
+    assert m.particle_count == n and m.ndim == dim and np.array_equal(m.position, e) and np.array_equal(m.fitness, lp)
+    assert m.gbest is not None and abs(m.gbest.fitness) < 1e-12          # Rosenbrock's maximum, the guess
+    m2 = sb.pso.ParticleSwarmMaximizer.from_ensemble(sb.Rosenbrock(), e)
+    assert np.allclose(m2.fitness, oracle.init_logprob(2, [], e), rtol=1e-12) and m2.gbest is None
+    first = float(m2.fitness.max())
+    rng = np.random.default_rng(5)
+    for _ in range(30):
+        m2.sample(rng, 0.6, 1.2, 1.2)
+    assert np.allclose(m2.fitness, oracle.init_logprob(2, [], m2.position), rtol=1e-12)   # the device's evaluation of the moved swarm
+    assert m2.gbest.fitness >= first and np.all(m2.pbest_fitness >= lp - 1e-300)
+
+
 @pytest.mark.parametrize("dim", [12, 100, 130])
 @pytest.mark.parametrize("shape", ["dense", "upper", "lower"])
 def test_corr_gaussian_factor_shapes(sb, oracle, dim, shape):

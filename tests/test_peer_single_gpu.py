@@ -50,6 +50,45 @@ def test_exchange_step_and_swap_in_a_world_of_one(sb, case):
         assert one.counters == ref.counters
 
 
+def _cycling_closure(dim, flen):
+    """A stateful Func closure in the spirit of examples/sample_high_dim.rs:59-65: two flags set, advancing by one
+    coordinate per call."""
+    state = {"i": 0}
+
+    def f():
+        v = np.zeros(flen, dtype=bool)
+        v[state["i"] % flen] = True
+        v[(state["i"] * 3 + 1) % flen] = True
+        state["i"] += 1
+        return v
+    return f
+
+
+@pytest.mark.parametrize("n,dim,flen", [(4096, 64, 64), (70, 7, 5)])
+def test_func_flags_over_the_one_sided_step(sb, n, dim, flen):
+    """UpdateFlagSpec::Func (ensemble_sample.rs:31,52,150-153) over the whole-ensemble one-sided step: the mask of the
+    whole ensemble, indexed by global walker id, gives the chain the ordinary step gives with the same closure."""
+    rng = np.random.default_rng(8)
+    ens = np.ascontiguousarray(rng.uniform(0.8, 1.2, (n, dim)))
+    with sb.Sampler(sb.Rosenbrock(), n, dim, seed=23) as ref, sb.Sampler(sb.Rosenbrock(), n, dim, seed=23) as one:
+        ref.upload(ens, None)
+        one.upload(ens, None)
+        _attach_world_of_one(one)
+        fa, fb = _cycling_closure(dim, flen), _cycling_closure(dim, flen)
+        for k in range(3):
+            ref.sample_pt(2.0, sb.UpdateFlagSpec.Func(fa), [1.0], 1)
+            one.sample_pt_peer(2.0, sb.UpdateFlagSpec.Mask(sb.UpdateFlagSpec.Func(fb).evaluate(n)), [1.0], 1)
+            e0, l0 = ref.download()
+            e1, l1 = one.download()
+            assert np.array_equal(e1, e0), f"positions differ after step {k}"
+            assert np.allclose(l1, l0, rtol=1e-12, atol=1e-9)
+        assert ref.stats()["accepted"] == one.stats()["accepted"] > 0
+        with pytest.raises(Exception):   # a mask covers exactly one step
+            one.sample_pt_peer(2.0, sb.UpdateFlagSpec.Mask(np.ones((n, flen), dtype=np.uint8)), [1.0], 2)
+        with pytest.raises(Exception):   # NPhiZero, ensemble_sample.rs:171-173
+            one.sample_pt_peer(2.0, sb.UpdateFlagSpec.Mask(np.zeros((n, flen), dtype=np.uint8)), [1.0], 1)
+
+
 def test_host_buffer_form_of_the_exchange_step(sb):
     """scorus_sample_pt_peer_host on pinned buffers: after every call the host arrays hold the chain (only the accepted
     walkers travel back -- marked on their home rank by the owner of the pair)."""
