@@ -625,6 +625,8 @@ int scorus::host::fill_common(scorus_ctx *ctx, StepParams *p, Geometry *g, size_
     return SCORUS_OK;
 }
 
+static bool small_geometry(const scorus_ctx *ctx, Geometry *g);
+
 // kernels of swap_kernel.cuh that other translation units launch too
 namespace scorus {
 namespace host {
@@ -658,6 +660,14 @@ int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp)
         swap_walk_kernel<false><<<(unsigned)((sp.npb + T - 1) / T), T, 0, ctx->stream>>>(sp);
     ctx->launches += 2;
     return SCORUS_OK;
+}
+bool stretch_step_moves_rows(scorus_ctx *ctx, size_t nbeta)
+{
+    if (ctx->f32 || ctx->sequential || ctx->d_peer_ens || ctx->lp_kind < 0 || nbeta == 0 || ctx->n % nbeta) return false;
+    Geometry g, gs;
+    if (step_geometry(ctx, &g, false) != SCORUS_OK) return false;
+    gs = g;
+    return !small_geometry(ctx, &gs) && step_can_remap(ctx->lp_kind, ctx->pitch, g) && g.grid > 1;
 }
 int settle_swap(scorus_ctx *ctx)
 {
@@ -720,6 +730,12 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
     // a ladder swap left its rows to this call (swap_impl): the first step moves them itself when its kernel can
     // (single launch over the whole ensemble, register kernel in direct mode), otherwise they move now
     bool move_rows = false;
+    // host-buffer call on pinned buffers: the first step streams the rows from the caller's ensemble (api_host.cu
+    // checked stretch_step_moves_rows and that nothing is pending)
+    double *const host_ens = ctx->host_ens, *const host_lp = ctx->host_lp;
+    ctx->host_ens = ctx->host_lp = nullptr;
+    if (host_ens && (ctx->swap_pending || nsteps == 0 || !stretch_step_moves_rows(ctx, nbeta)))
+        return fail(ctx, SCORUS_ERR_INVALID_ARG, "internal: this call cannot stream its rows from the host");
     if (ctx->swap_pending) {
         Geometry gs = g;
         move_rows = !small_geometry(ctx, &gs) && step_can_remap(ctx->lp_kind, ctx->pitch, g) && g.grid > 1 &&
@@ -804,6 +820,13 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
             p.src_ens = ctx->d_ens;
             p.ens = ctx->d_scratch;
         }
+        const uint32_t l2_prefetch = p.l2_prefetch;
+        if (host_ens && s == 0) {  // rows straight from the caller's pinned buffer, accepted rows straight back
+            p.src_ens = host_ens;
+            p.host_ens = host_ens;
+            p.host_lp = host_lp;
+            p.l2_prefetch = 0;
+        }
         stamp_tiles(ctx, &p, g);
         cudaError_t e = launch_step(ctx->lp_kind, p, g, all_flags, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, SCORUS_ERR_CUDA, "step launch: %s", cudaGetErrorString(e));
@@ -814,6 +837,11 @@ extern "C" int scorus_sample_pt(scorus_ctx *ctx, double a, const scorus_ufs *ufs
             move_rows = false;
             p.remap = nullptr;
             p.ens = ctx->d_ens; p.src_ens = ctx->d_ens;
+        }
+        if (host_ens && s == 0) {  // the device copy is complete from here on
+            p.src_ens = ctx->d_ens;
+            p.host_ens = p.host_lp = nullptr;
+            p.l2_prefetch = l2_prefetch;
         }
         ++ctx->launches;
         ++ctx->step;

@@ -33,11 +33,51 @@ static int host_call(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, si
     CU(cudaStreamSynchronize(ctx->stream));
     return SCORUS_OK;
 }
+// The stretch move on pinned buffers without an upload: the log-probs go up (8 bytes per walker), the FIRST step reads
+// the rows straight out of the caller's ensemble over PCIe -- every row is read exactly once by a step anyway -- writes
+// all of them to the device copy and every accepted row and log-prob straight back into the caller's arrays as it is
+// decided (step_reg_kernel.cuh, kRemap variant with host_ens set).  Upload, step and write-back of the serial form
+// (39 + 0.7 + 9 ms at 2^22 x 64-D) become one kernel in which both directions of the link run at once.  Further steps
+// of the same call run on the device copy and their accepted walkers leave through scatter_download_kernel as before.
+static int host_call_streamed(scorus_ctx *ctx, double *ens_dev, double *lp_host, double *lp_dev, double a,
+                              const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
+{
+    cudaSetDevice(ctx->device);
+    ctx->swap_pending = false;  // everything a pending swap would have moved is replaced by the caller's state
+    CU(cudaMemcpyAsync(ctx->d_lp, lp_host, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->uploaded = true;
+    CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, ctx->stream));
+    ctx->host_ens = ens_dev;
+    ctx->host_lp = lp_dev;
+    int rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, 1);
+    ctx->host_ens = ctx->host_lp = nullptr;
+    if (rc) { ctx->uploaded = false; return rc; }  // (the device copy may be incomplete: the caller's buffers are the state)
+    if (nsteps > 1) {
+        ctx->track_dirty = true;
+        rc = scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps - 1);
+        ctx->track_dirty = false;
+        if (rc) return rc;
+        if ((rc = launch_scatter_download(ctx, ens_dev, lp_dev))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SCORUS_OK;
+}
+
 extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp, size_t lp_len, double a,
                                        const scorus_ufs *ufs, const double *beta, size_t nbeta, uint64_t nsteps)
 {
-    if (!ctx || !ens || !lp) return SCORUS_ERR_INVALID_ARG;
+    if (!ctx || !ens || !lp || !ufs || !beta) return SCORUS_ERR_INVALID_ARG;
     F64_ONLY(ctx);
+    if (nsteps >= 1 && ctx->pitch == ctx->dim && env_int("SCORUS_HOST_STREAM", 1) && env_int("SCORUS_SCATTER_DOWNLOAD", 1) &&
+        scorus_check_sample_args(ctx->n, lp_len, nbeta) == SCORUS_OK && a > 1.0 && ufs->kind != SCORUS_UFS_MASK &&
+        !(ufs->kind == SCORUS_UFS_PROB && !(ufs->prob > 0.0)) && stretch_step_moves_rows(ctx, nbeta)) {
+        cudaPointerAttributes ae{}, al{};
+        const bool pinned = cudaPointerGetAttributes(&ae, ens) == cudaSuccess && ae.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&al, lp) == cudaSuccess && al.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned)
+            return host_call_streamed(ctx, (double *)ae.devicePointer, lp, (double *)al.devicePointer, a, ufs, beta, nbeta, nsteps);
+    }
     return host_call(ctx, ens, lp, lp_len, nbeta, [&] { return scorus_sample_pt(ctx, a, ufs, beta, nbeta, nsteps); });
 }
 

@@ -89,6 +89,10 @@ struct scorus_ctx {
     // else that looks at the ensemble or the log-probs first calls settle_swap (api_core.cu), which moves the rows.
     void *d_swap_out = nullptr; size_t swap_out_cap = 0;
     bool swap_pending = false;
+    // Host-buffer call (api_host.cu) on pinned buffers: device pointers of the caller's ensemble / log-probs for the
+    // FIRST step of the call, which streams the rows from there instead of an upload (step_reg_kernel.cuh, kRemap
+    // variant); consumed (reset) by that step
+    double *host_ens = nullptr, *host_lp = nullptr;
     int8_t *d_hmc_adapt = nullptr;                              // HMC: step-size adaptation codes, one per walker
     double *d_hmc_eps = nullptr; size_t hmc_eps_cap = 0;        // ... step size per rung
     double *d_hmc_p = nullptr; size_t hmc_p_cap = 0;            // ... caller-supplied momenta
@@ -163,6 +167,9 @@ void launch_exact_jvec(scorus_ctx *ctx, size_t nbeta, size_t npb, uint32_t *jinv
 int launch_swap_chain(scorus_ctx *ctx, SwapParams &sp);
 // rows and log-probs of a pending swap to their slots (no-op when nothing is pending)
 int settle_swap(scorus_ctx *ctx);
+// whether the stretch step of this context can take its rows from somewhere else and write all of them (the kRemap
+// variant of the register kernel: after a swap, or streaming from a pinned host buffer)
+bool stretch_step_moves_rows(scorus_ctx *ctx, size_t nbeta);
 // api_f32.cu: the T = f32 paths behind the shared entry points
 int f32_set_params(scorus_ctx *ctx, const double *params, size_t nparams);
 int f32_init_logprob(scorus_ctx *ctx);

@@ -60,7 +60,7 @@ static cudaError_t launch_reg(const StepParams &p, const Geometry &g, cudaStream
         return launch_kernel(step_reg_kernel<Plugin, G, ITERS, 1>, p, g, st);
     }
 #ifndef SCORUS_F32
-    if (p.remap) {  // the step after a ladder swap moves the rows (the host checked step_can_remap)
+    if (p.remap || p.host_ens) {  // the step after a ladder swap / the first step of a host-buffer call (the host checked step_can_remap)
         if constexpr (reg_kernel_direct<Plugin, G>()) return launch_kernel(step_reg_kernel<Plugin, G, ITERS, 0, true>, p, g, st);
         else return cudaErrorNotSupported;
     }

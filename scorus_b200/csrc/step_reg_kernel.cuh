@@ -230,10 +230,14 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         if constexpr (kRemap) {
             SwapOut o;
             o.lp = 0.0; o.src = wid; o.pad = 0u;
-            if (a) {  // one 16-byte read-only load
-                const int4 v = __ldg(reinterpret_cast<const int4 *>(p.remap) + wid);
-                static_assert(sizeof(SwapOut) == sizeof(int4), "SwapOut is one 16-byte record");
-                memcpy(&o, &v, sizeof(o));
+            if (a) {
+                if (p.remap) {  // after a ladder swap: one 16-byte read-only load
+                    const int4 v = __ldg(reinterpret_cast<const int4 *>(p.remap) + wid);
+                    static_assert(sizeof(SwapOut) == sizeof(int4), "SwapOut is one 16-byte record");
+                    memcpy(&o, &v, sizeof(o));
+                } else {        // host-buffer call: the row is where it belongs, in the caller's buffer
+                    o.lp = __ldg(p.src_lp + wid);
+                }
             }
             row_now = o.src;
             return o.lp;
@@ -421,6 +425,9 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     }
                     if (acc_now) {
                         *my_lp = lp_new;
+                        if constexpr (kRemap) {
+                            if (p.host_lp) p.host_lp[w] = lp_new;  // host-buffer call: straight back into the caller's array
+                        }
                         if (p.dirty) {  // host-buffer call: this walker's row has to travel back (one-sided mode: mark it on its home GPU)
                             if constexpr (kPeer != 0) reinterpret_cast<uint8_t *>(p.peer_lp[home >> 28] + p.peer_n + 32)[home & 0x0FFFFFFFu] = 1;
                             else p.dirty[w - p.w_lo] = 1;
@@ -437,7 +444,16 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     const uint32_t rl = grp * G + (uint32_t)(blk * GB + i);
                     const uint32_t row = __shfl_sync(0xffffffffu, kPeer != 0 ? home : w, rl);
                     if constexpr (kRemap) {
-                        if (!((accmask >> rl) & 1u)) {
+                        if ((accmask >> rl) & 1u) {
+                            if (p.host_ens) {  // host-buffer call: the accepted row goes back over PCIe now, while others still arrive
+                                double2 *hdst = reinterpret_cast<double2 *>(p.host_ens + (size_t)row * p.pitch);
+#pragma unroll
+                                for (int it = 0; it < ITERS; ++it) {
+                                    const uint32_t c = (uint32_t)it * G + j;
+                                    if (c < nvec) hdst[c] = yk[i][it];
+                                }
+                            }
+                        } else {
 #pragma unroll
                             for (int it = 0; it < ITERS; ++it) yk[i][it] = xc[i][it];
                         }

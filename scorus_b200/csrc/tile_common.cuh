@@ -80,6 +80,12 @@ struct StepParams {
     // proposal if accepted, the old row if not -- and every log-prob to slot w of ens / lp, the context's second buffer,
     // which the host then makes the ensemble.  The swap's row pass (read + write of the whole ensemble) disappears.
     const void *remap;
+    // The same variant as the first step of a host-buffer call (api_host.cu): remap == nullptr, src_ens is the caller's
+    // pinned, device-mapped ensemble (rows pitch == dim doubles apart) -- the rows are never uploaded: the step streams
+    // them over PCIe itself, writes every row to ens (the device copy the following steps use) and every ACCEPTED row
+    // and log-prob back to host_ens / host_lp as it is decided, so the two directions of the link run at once.
+    double *host_ens;
+    double *host_lp;
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form) ----
