@@ -407,8 +407,12 @@ extern "C" int scorus_upload(scorus_ctx *ctx, const double *ens, const double *l
     cudaSetDevice(ctx->device);
     ctx->swap_pending = false;  // everything a pending swap would have moved is overwritten here
     const size_t rb = (size_t)ctx->dim * sizeof(double);
-    CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(double), ens, rb, rb, ctx->n,
-                         cudaMemcpyHostToDevice, ctx->stream));
+    // (rows without padding: one flat copy -- a 2-D copy of 80-byte rows ran at 2 GB/s, 48 ms for the 84 MB of c4)
+    if (ctx->pitch == ctx->dim)
+        CU(cudaMemcpyAsync(ctx->d_ens, ens, rb * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(double), ens, rb, rb, ctx->n,
+                             cudaMemcpyHostToDevice, ctx->stream));
     ctx->uploaded = true;
     if (lp) {
         CU(cudaMemcpyAsync(ctx->d_lp, lp, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -428,7 +432,9 @@ extern "C" int scorus_download(scorus_ctx *ctx, double *ens, double *lp)
     int rc = settle_swap(ctx);
     if (rc) return rc;
     const size_t rb = (size_t)ctx->dim * sizeof(double);
-    if (ens)
+    if (ens && ctx->pitch == ctx->dim)
+        CU(cudaMemcpyAsync(ens, ctx->d_ens, rb * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    else if (ens)
         CU(cudaMemcpy2DAsync(ens, rb, ctx->d_ens, (size_t)ctx->pitch * sizeof(double), rb, ctx->n,
                              cudaMemcpyDeviceToHost, ctx->stream));
     if (lp) CU(cudaMemcpyAsync(lp, ctx->d_lp, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -217,7 +217,10 @@ extern "C" int scorus_upload_f32(scorus_ctx *ctx, const float *ens, const float 
     if (!ctx->f32) return fail(ctx, SCORUS_ERR_INVALID_ARG, "scorus_upload_f32 needs a SCORUS_CFG_F32 context");
     cudaSetDevice(ctx->device);
     const size_t rb = (size_t)ctx->dim * sizeof(float);
-    CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(float), ens, rb, rb, ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->pitch == ctx->dim)  // rows without padding: one flat copy
+        CU(cudaMemcpyAsync(ctx->d_ens, ens, rb * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CU(cudaMemcpy2DAsync(ctx->d_ens, (size_t)ctx->pitch * sizeof(float), ens, rb, rb, ctx->n, cudaMemcpyHostToDevice, ctx->stream));
     ctx->uploaded = true;
     if (lp) {
         CU(cudaMemcpyAsync(ctx->d_lp, lp, ctx->n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -234,7 +237,12 @@ extern "C" int scorus_download_f32(scorus_ctx *ctx, float *ens, float *lp)
     cudaSetDevice(ctx->device);
     const size_t rb = (size_t)ctx->dim * sizeof(float);
     if (ens)
-        CU(cudaMemcpy2DAsync(ens, rb, ctx->d_ens, (size_t)ctx->pitch * sizeof(float), rb, ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    {
+        if (ctx->pitch == ctx->dim)
+            CU(cudaMemcpyAsync(ens, ctx->d_ens, rb * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            CU(cudaMemcpy2DAsync(ens, rb, ctx->d_ens, (size_t)ctx->pitch * sizeof(float), rb, ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (lp) CU(cudaMemcpyAsync(lp, ctx->d_lp, ctx->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SCORUS_OK;

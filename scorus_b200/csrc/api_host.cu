@@ -68,7 +68,11 @@ extern "C" int scorus_sample_pt_host_n(scorus_ctx *ctx, double *ens, double *lp,
 {
     if (!ctx || !ens || !lp || !ufs || !beta) return SCORUS_ERR_INVALID_ARG;
     F64_ONLY(ctx);
-    if (nsteps >= 1 && ctx->pitch == ctx->dim && env_int("SCORUS_HOST_STREAM", 1) && env_int("SCORUS_SCATTER_DOWNLOAD", 1) &&
+    // rows of 512 bytes and more: the step's own reads reach 48 GB/s over PCIe (the copy engine: 55) and the write-back
+    // overlaps them -- 45 against 51 ms at 2^22 x 64-D; rows of 80 bytes travel at 11 GB/s that way and stay with the
+    // flat upload (3.9 against 7.9 ms at c4)
+    if (nsteps >= 1 && ctx->pitch == ctx->dim && (size_t)ctx->dim * sizeof(double) >= (size_t)env_int("SCORUS_HOST_STREAM_MIN_ROW", 512) &&
+        env_int("SCORUS_HOST_STREAM", 1) && env_int("SCORUS_SCATTER_DOWNLOAD", 1) &&
         scorus_check_sample_args(ctx->n, lp_len, nbeta) == SCORUS_OK && a > 1.0 && ufs->kind != SCORUS_UFS_MASK &&
         !(ufs->kind == SCORUS_UFS_PROB && !(ufs->prob > 0.0)) && stretch_step_moves_rows(ctx, nbeta)) {
         cudaPointerAttributes ae{}, al{};

@@ -11,8 +11,12 @@
 // narrower rows keep 8 rows per block and 16 warps (10-D lost 5 % with the tighter cap).
 #define SCORUS_REG_ROWS_WIDE 4
 #define SCORUS_REG_WARPS_WIDE 20
+#ifndef SCORUS_REG_ROWS
 #define SCORUS_REG_ROWS 8
+#endif
+#ifndef SCORUS_REG_WARPS
 #define SCORUS_REG_WARPS 16
+#endif
 // rows of 9..16 double2 (16 lanes per row, tile mode): 1 = the wide shape (4 rows per block, 20 warps) for them too
 #ifndef SCORUS_G16_DIRECT
 #define SCORUS_G16_DIRECT 0
