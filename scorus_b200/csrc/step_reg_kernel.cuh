@@ -266,6 +266,14 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
             z = z_from_uniform(to_unit<double>(r.x, r.y), p.inv_sqrt_a, p.z_range);
             u = to_unit<double>(r.z, r.w);
         }
+        // Direct mode decides per block of GB rows, with GB of the warp's 32 lanes active: an exp there runs NB times per
+        // tile at GB/32 efficiency (9 % of the instructions and 14 % of the stall samples of the 64-D step,
+        // profiles/r2b_c5_step_lines.txt).  ln u is taken HERE instead, once per tile with every lane busy, and the
+        // decision u < exp(t) becomes ln u < t wherever the two are not within the guard band of each other -- far
+        // outside the rounding of log and exp, so it is exactly the literal comparison's answer (the ladder swap's
+        // argument, swap_kernel.cuh); inside the band, for u = 0 and for a t that is not finite the lanes take the exp.
+        [[maybe_unused]] double lu = 0.0;
+        if constexpr (kDirect && NB > 1) lu = u > 0.0 ? log(u) : real_nan<double>();
         // the previous tile's accepted rows must have left the y tile before reuse
         if constexpr (!kDirect) bulk_wait_read_all();
         __syncwarp();
@@ -418,8 +426,17 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                 bool acc_now = false;
                 if ((int)(j / GB) == blk) {
                     const double lp_new = plug.finish_acc(tot);
-                    const double q = exp(lz + (lp_new - lp_old) * beta);
-                    acc_now = mine && (u < q);
+                    const double t = lz + (lp_new - lp_old) * beta;  // ensemble_sample.rs:184: ln q
+                    bool below;                                      // u < q = exp(t), :185
+                    if constexpr (NB > 1) {
+                        const double d = swap_guard<double>() * (1.0 + fabs(t));
+                        const bool yes = lu < t - d, no = lu > t + d;
+                        below = yes;
+                        if (__builtin_expect(!(yes | no), 0)) below = u < exp(t);
+                    } else {
+                        below = u < exp(t);
+                    }
+                    acc_now = mine && below;
                     if constexpr (kRemap) {
                         if (mine && !acc_now) *my_lp = lp_old;  // the swap's log-prob reaches the array here
                     }
