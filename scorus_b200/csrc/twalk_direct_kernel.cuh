@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(twalk_max_warps<Plugin, G>() * 32, 1) twalk_di
         __syncwarp();  // the previous tile's readers are done with the flag words and the z lists
         const uint32_t nphi = gen_flags(p, my_step, w, flagw, lane, mv);
         const double lb = kern == 1u ? (double)((int)nphi - 2) * log(b) : 0.0;
+        // ln u once per tile with every lane busy: the per-block decision below compares logarithms and takes the exp only
+        // inside the guard band (step_reg_kernel.cuh has the argument)
+        [[maybe_unused]] double lu = 0.0;
+        if constexpr (NB > 1) lu = u > 0.0 ? log(u) : real_nan<double>();
         const double beta = __ldg(p.beta + (act ? w / p.npb : 0u));
         // flagged coordinates before each flag word (8 bits per word: dim <= 256), and the z of the first
         // kTwalkZList flagged coordinates in increasing order (sim_walk :289-296; one Philox call per flagged chunk)
@@ -274,8 +278,18 @@ __global__ void __launch_bounds__(twalk_max_warps<Plugin, G>() * 32, 1) twalk_di
                 bool acc_now = false;
                 if ((int)(j / GB) == blk && act && my_half == half) {
                     const double lp_new = plug.finish_acc(tot);
-                    const double a_acc = (nphi == 0u || my_eq) ? 0.0 : exp((lp_new - lp_old) * beta + lb);
-                    acc_now = u < a_acc;
+                    // calc_a: A = 0 for an empty move, else exp(t); accepted iff u < A (:756-759)
+                    const double t = (lp_new - lp_old) * beta + lb;
+                    if (nphi == 0u || my_eq) {
+                        acc_now = false;  // u < 0.0
+                    } else if constexpr (NB > 1) {
+                        const double d = swap_guard<double>() * (1.0 + fabs(t));
+                        const bool yes = lu < t - d, no = lu > t + d;
+                        acc_now = yes;
+                        if (__builtin_expect(!(yes | no), 0)) acc_now = u < exp(t);
+                    } else {
+                        acc_now = u < exp(t);
+                    }
                     if (acc_now) {
                         p.lp[w] = lp_new;
                         if (p.dirty) p.dirty[w] = 1;
