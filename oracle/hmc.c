@@ -63,6 +63,24 @@ int orc_grad_logprob(int kind, const double *params, size_t nparams, const doubl
         for (size_t j = 0; j < dim; ++j) g[j] = (0.0 - r1 * (x[j] - m[j])) - r2 * (x[j] + m[j]);
         return ORC_OK;
     }
+    case ORC_LP_CORR_GAUSSIAN: { /* builder-defined lp = -1/2 |L (x - mu)|^2: g = 0 - L^T (L (x - mu)), both
+                                  * products summed left to right (the order scorus_b200/csrc/hmc_kernel.cuh keeps) */
+        if (nparams < dim + dim * dim) return ORC_ERR_INVALID_ARG;
+        const double *mu = params, *L = params + dim;
+        double *v = (double *)malloc(dim * sizeof(double));
+        for (size_t i = 0; i < dim; ++i) {
+            double w = 0.0;
+            for (size_t j = 0; j < dim; ++j) w += L[i * dim + j] * (x[j] - mu[j]);
+            v[i] = w;
+        }
+        for (size_t k = 0; k < dim; ++k) {
+            double s = 0.0;
+            for (size_t i = 0; i < dim; ++i) s += L[i * dim + k] * v[i];
+            g[k] = 0.0 - s;
+        }
+        free(v);
+        return ORC_OK;
+    }
     default:
         return ORC_ERR_INVALID_ARG;
     }

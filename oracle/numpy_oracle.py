@@ -267,6 +267,21 @@ def grad_logprob(kind: int, params, x: np.ndarray) -> np.ndarray:
         k = two_pi * a
         s = k * _vmath(math.sin, two_pi * x)
         return (0.0 - s) - 2.0 * x
+    if kind == 6:   # -1/2 |L (x - mu)|^2: g = 0 - L^T (L (x - mu)), both products summed left to right
+        mu, L = p[:d], p[d:d + d * d].reshape(d, d)
+        v = np.zeros((n, d))
+        for i in range(d):
+            w = np.zeros(n)
+            for j in range(d):
+                w = w + L[i, j] * (x[:, j] - mu[j])
+            v[:, i] = w
+        g = np.zeros_like(x)
+        for k in range(d):
+            s = np.zeros(n)
+            for i in range(d):
+                s = s + L[i, k] * v[:, i]
+            g[:, k] = 0.0 - s
+        return g
     if kind == 7:
         s1, s2, m = p[0], p[1], p[2:2 + d]
         q1, q2 = np.zeros(n), np.zeros(n)

@@ -101,8 +101,80 @@ __global__ void __launch_bounds__(256) hmc_kernel(const HmcParams hp)
             mom[it] = m;
         }
 
+        // Dense targets (kNeedsRow: lp = -1/2 |L (x - mu)|^2): v = L (x - mu) and g = 0 - L^T v as matrix-vector products
+        // over the group's lanes -- lane j owns the rows / columns of its coordinates, the other operand's chunks come
+        // round by shuffle, in coordinate order, so that every sum is the left-to-right sum oracle/hmc.c states.  L is
+        // read from L1 / L2 (D^2 doubles; 80 KB at D = 100): functional, not fast -- a tile GEMM over 32 walkers on the
+        // fp64 tensor cores (as K3 does for the stretch move) is what would make HMC on this target quick.
+        [[maybe_unused]] double2 vrow[ITERS];
+        [[maybe_unused]] auto dense_apply = [&]() {  // vrow <- L (q - mu), my rows
+            if constexpr (Plugin::kNeedsRow) {
+                const uint32_t D = p.dim;
+                double2 xm[ITERS];
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const uint32_t d = 2u * ((uint32_t)it * G + j);
+                    xm[it].x = in[it] ? q[it].x - __ldg(plug.mu + d) : 0.0;
+                    xm[it].y = has1[it] ? q[it].y - __ldg(plug.mu + d + 1u) : 0.0;
+                    vrow[it] = make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int itk = 0; itk < ITERS; ++itk)
+                    for (uint32_t jk = 0; jk < (uint32_t)G; ++jk) {
+                        const uint32_t k = 2u * ((uint32_t)itk * G + jk);
+                        if (k >= D) break;  // (uniform over the group)
+                        const double xk0 = __shfl_sync(0xffffffffu, xm[itk].x, jk, G), xk1 = __shfl_sync(0xffffffffu, xm[itk].y, jk, G);
+                        const bool k1 = k + 1u < D;
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it) {
+                            const uint32_t i = 2u * ((uint32_t)it * G + j);
+                            if (in[it]) {
+                                vrow[it].x += __ldg(plug.L + (size_t)i * D + k) * xk0;
+                                if (k1) vrow[it].x += __ldg(plug.L + (size_t)i * D + k + 1u) * xk1;
+                            }
+                            if (has1[it]) {
+                                vrow[it].y += __ldg(plug.L + (size_t)(i + 1u) * D + k) * xk0;
+                                if (k1) vrow[it].y += __ldg(plug.L + (size_t)(i + 1u) * D + k + 1u) * xk1;
+                            }
+                        }
+                    }
+            }
+        };
         // force at a point: lhq = grad(q) * scale; neighbours x[d-1], x[d+2] from the adjacent lanes / trips
         auto force = [&](double scale) {
+            if constexpr (Plugin::kNeedsRow) {
+                const uint32_t D = p.dim;
+                dense_apply();
+                double2 s[ITERS];
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) s[it] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int iti = 0; iti < ITERS; ++iti)
+                    for (uint32_t ji = 0; ji < (uint32_t)G; ++ji) {
+                        const uint32_t i = 2u * ((uint32_t)iti * G + ji);
+                        if (i >= D) break;
+                        const double v0 = __shfl_sync(0xffffffffu, vrow[iti].x, ji, G), v1 = __shfl_sync(0xffffffffu, vrow[iti].y, ji, G);
+                        const bool i1 = i + 1u < D;
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it) {
+                            const uint32_t k = 2u * ((uint32_t)it * G + j);
+                            if (in[it]) {
+                                s[it].x += __ldg(plug.L + (size_t)i * D + k) * v0;
+                                if (i1) s[it].x += __ldg(plug.L + (size_t)(i + 1u) * D + k) * v1;
+                            }
+                            if (has1[it]) {
+                                s[it].y += __ldg(plug.L + (size_t)i * D + k + 1u) * v0;
+                                if (i1) s[it].y += __ldg(plug.L + (size_t)(i + 1u) * D + k + 1u) * v1;
+                            }
+                        }
+                    }
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    f[it].x = in[it] ? (0.0 - s[it].x) * scale : 0.0;
+                    f[it].y = has1[it] ? (0.0 - s[it].y) * scale : 0.0;
+                }
+                return;
+            }
             if constexpr (Plugin::kGradNeedsSums) {  // row-wide sums first (mixture: the component weights)
                 double a[Plugin::kAcc];
 #pragma unroll
@@ -175,7 +247,17 @@ __global__ void __launch_bounds__(256) hmc_kernel(const HmcParams hp)
         }
 #pragma unroll
         for (int a = 0; a < Plugin::kAcc; ++a) acc[a] = group_sum<G>(acc[a]);
-        const double lp1 = plug.finish_acc(acc);
+        double lp1 = plug.finish_acc(acc);
+        if constexpr (Plugin::kNeedsRow) {  // -1/2 |L (q - mu)|^2 from the same product (fixed tree over the group's lanes)
+            dense_apply();
+            double ss = 0.0;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                if (in[it]) ss += vrow[it].x * vrow[it].x;
+                if (has1[it]) ss += vrow[it].y * vrow[it].y;
+            }
+            lp1 = plug.ok ? -0.5 * group_sum<G>(ss) : NAN;
+        }
         const double k1 = kinetic();
 
         // :231-253: current_u = -lp, proposed_u = -flogprob(q), dh = beta (u0 - u1) + k0 - k1

@@ -425,8 +425,14 @@ struct LpCorrGaussian {
     static constexpr int kMaxWarps = 8;  // register kernel: 256 threads -> up to 255 registers for the DMMA accumulators
     static constexpr bool kNeedsNext = false;
     static constexpr int kAcc = 1;
-    static constexpr bool kHasGrad = false;
+    // gradient -L^T L (x - mu): two matrix-vector products, evaluated by the HMC kernel's dense path (hmc_kernel.cuh:
+    // the walker's coordinates are spread over a group of lanes, so the products go through shuffles, not grad2)
+    static constexpr bool kHasGrad = true;
     static constexpr bool kGradNeedsSums = false;
+    __device__ __forceinline__ void grad2(uint32_t, double, double, double, double, bool, bool, bool, double &g0, double &g1) const
+    {
+        g0 = g1 = 0.0;  // (never called: kNeedsRow plugins take the dense path)
+    }
     const double *mu, *L;
     uint32_t dim;
     bool ok, upper;  // upper: L[n][k] == 0 for k < n (flagged by scorus_set_logprob after {mu, L})

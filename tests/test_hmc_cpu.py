@@ -22,8 +22,15 @@ def test_golden_vectors_both_restatements(oracle, path):
         assert np.array_equal(eps, g["eps"][k]) and np.array_equal(e2, eps)
 
 
+def _corr9():
+    g = np.random.default_rng(77)
+    L = np.eye(9) * 1.5 + 0.1 * g.normal(size=(9, 9))
+    return np.concatenate([g.uniform(-0.2, 0.2, 9), L.ravel()]).tolist()
+
+
 @pytest.mark.parametrize("kind,params", [(0, [0.5]), (0, [1.0]), (1, [1.5]), (2, []), (3, [10.0]),
-                                         (7, [1.0, 2.0, 1.5] + [0.0] * 8)])
+                                         (7, [1.0, 2.0, 1.5] + [0.0] * 8), (6, _corr9())],
+                         ids=lambda v: str(v) if isinstance(v, int) else f"p{len(v)}")
 def test_gradients_match_finite_differences_and_numpy(oracle, kind, params):
     g = np.random.default_rng(kind)
     x = g.uniform(-1.0, 1.0, (5, 9))
@@ -44,7 +51,8 @@ def test_plugins_without_gradient_say_so(oracle):
 
 
 @pytest.mark.parametrize("kind,params,n,dim,nb,l", [(0, [0.5], 32, 5, 2, 4), (2, [], 24, 8, 3, 3), (3, [10.0], 40, 10, 4, 5),
-                                                    (1, [1.5], 17, 3, 1, 6)])
+                                                    (1, [1.5], 17, 3, 1, 6), (6, _corr9(), 20, 9, 2, 3)],
+                         ids=lambda v: str(v) if isinstance(v, int) else f"p{len(v)}")
 def test_both_restatements_agree(oracle, kind, params, n, dim, nb, l):
     g = np.random.default_rng(dim)
     q = np.ascontiguousarray(g.uniform(0.8, 1.2, (n, dim)) if kind == 2 else g.uniform(-1, 1, (n, dim)))

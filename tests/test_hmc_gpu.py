@@ -23,7 +23,18 @@ CASES = [
     (1, [1.5], 512, 5, 2, 6, 0.3, (-1.4, 1.4)),    # trajectories that leave the box: lp = -inf, dh not finite
     (7, [1.0, 2.0, 3.0] + [0.0] * 31, 1024, 32, 2, 4, 0.4, (-4.0, 4.0)),   # mixture: row-wide sums before every force
     (7, [0.5, 1.5, 2.0, -1.0, 0.5], 256, 3, 1, 5, 0.3, (-3.0, 3.0)),
+    # the dense Gaussian -1/2 |L (x - mu)|^2 (BASELINE config 2's target): two matrix-vector products per force
+    (6, "corr", 256, 12, 2, 4, 0.1, (-1.0, 1.0)),      # 8 lanes per walker
+    (6, "corr", 96, 100, 1, 3, 0.05, (-1.0, 1.0)),     # 32 lanes, two chunks per lane
+    (6, "corr", 70, 7, 1, 5, 0.1, (-1.0, 1.0)),        # odd dim: the last chunk is half empty
 ]
+
+
+def _corr_params(dim):
+    """mu and a well-conditioned dense factor L (row-major) for SCORUS_LP_CORR_GAUSSIAN."""
+    g = np.random.default_rng(1000 + dim)
+    L = np.eye(dim) * 1.5 + 0.3 * g.normal(size=(dim, dim)) / np.sqrt(dim)
+    return np.concatenate([g.uniform(-0.2, 0.2, dim), L.ravel()]).tolist()
 
 
 @pytest.mark.parametrize("path", hmc_golden_files(), ids=lambda p: p.split("/")[-1][:-4])
@@ -47,6 +58,8 @@ def test_golden_fixed_stream(sb, path):
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"k{c[0]}_n{c[2]}_d{c[3]}_b{c[4]}_l{c[5]}")
 def test_fixed_stream_vs_oracle(sb, oracle, case):
     kind, params, n, dim, nb, l, eps0, box = case
+    if params == "corr":
+        params = _corr_params(dim)
     g = np.random.default_rng(n + dim)
     beta = 2.0 ** (-np.arange(nb, dtype=np.float64) / 2.0)
     q = np.ascontiguousarray(g.uniform(box[0], box[1], (n, dim)))
