@@ -168,7 +168,10 @@ int scorus_swap_walkers_fixed(scorus_ctx *ctx, const double *beta_list, size_t n
  * trip plus a synchronise (~50 us even for the 16 walkers of examples/test_emcee.rs, where the reference's own CPU
  * step takes 3 us; PCIe-bound at 2^22 walkers).  Drivers should use scorus_sample_pt_host_n with the number of steps
  * between two recorded samples, or keep the ensemble on the device (scorus_upload once, scorus_sample_pt with nsteps,
- * scorus_trace_* / scorus_moments_* for the recording): a one-block ensemble then runs all nsteps in ONE launch. */
+ * scorus_trace_* / scorus_moments_* for the recording): a one-block ensemble then runs all nsteps in ONE launch.
+ * On page-locked buffers (scorus_host_alloc / cudaHostAlloc) only the walkers accepted in the call are written back; with
+ * rows of 512 bytes and more the ensemble is not uploaded either: the first step reads the rows out of the caller's buffer
+ * over PCIe itself and writes accepted rows straight back, both directions of the link at once. */
 int scorus_sample_pt_host(scorus_ctx *ctx, double *ensemble, double *logprob, size_t logprob_len,
                           double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta);
 /* The same with nsteps steps between the upload and the download: what a driver that records every
@@ -222,8 +225,8 @@ typedef struct scorus_hmc_param {
 /* sample_ensemble_pt (:122-292) on the resident ensemble, nsteps times: fresh N(0, 1) momenta, l leapfrog steps
  * (src/mcmc/hmc/utils.rs:6-30) of size epsilon[rung] under the tempered force beta * grad(logprob), accept with
  * exp(beta (lp' - lp) + K - K') when that is finite.  The gradient -- the reference's second closure, grad_logprob --
- * belongs to the log-density plugin (Gaussian, bounded Gaussian, Rosenbrock, Rastrigin, mixture have one; the others answer
- * SCORUS_ERR_INVALID_ARG) and is recomputed from q0 at entry, as sample_ensemble_pt does (:139).  epsilon[nbeta] is
+ * belongs to the log-density plugin (Gaussian, bounded Gaussian, Rosenbrock, Rastrigin, mixture and the dense Gaussian
+ * have one; the bounded 2-D targets answer SCORUS_ERR_INVALID_ARG) and is recomputed from q0 at entry, as sample_ensemble_pt does (:139).  epsilon[nbeta] is
  * in/out (host): for rungs of up to 4096 walkers it is updated exactly as the reference's sequential accept loop
  * would (bit-identical); for larger rungs the same factors are applied at once, epsilon (1 + adj_factor)^(grown -
  * shrunk), within n/nbeta * 2^-53 relative of the sequential result.  accepted_cnt[nbeta] (the reference's return
@@ -323,7 +326,11 @@ int scorus_ipc_attach(scorus_ctx *ctx, int world, int rank, const void *handles_
  * ranks.  Each row crosses NVLink at most once per direction per step and nothing is computed twice.  Synchronisation:
  * one flag barrier in peer memory before each step (inside the pair-list kernel) and one after the last step -- no
  * NCCL call, no host synchronisation.  Every rank calls it with the same arguments.  nsteps consecutive steps;
- * identical to the single-GPU steps (streams are keyed by global walker ids). */
+ * identical to the single-GPU steps (streams are keyed by global walker ids).
+ * UpdateFlagSpec::Func (SCORUS_UFS_MASK; src/mcmc/ensemble_sample.rs:31,52,150-153): here and in
+ * scorus_sample_pt_global the mask covers the WHOLE ensemble, [n_walkers_global][mask_len] indexed by global walker id
+ * -- the closure is called once per walker of the whole ensemble in order, so every rank evaluates the same closure
+ * n_global times, as the single-GPU run does; the owner of a pair needs both walkers' flags.  One step per call. */
 int scorus_sample_pt_peer(scorus_ctx *ctx, double a, const scorus_ufs *ufs, const double *beta_list, size_t nbeta,
                           uint64_t nsteps);
 /* scorus_sample_pt_peer on caller-owned host buffers of this rank's shard (the reference-shaped call, collective over
