@@ -461,6 +461,12 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                     const uint32_t rl = grp * G + (uint32_t)(blk * GB + i);
                     const uint32_t row = __shfl_sync(0xffffffffu, kPeer != 0 ? home : w, rl);
                     if constexpr (kRemap) {
+                        // Rows narrower than a warp (several rows per lane group and block): a rejected row is fetched again
+                        // -- from L2, it was read a moment ago -- rather than kept in registers across the log-density
+                        // (10-D: 272 bytes of spills and +12 us per step otherwise).  Full-width rows (the shape that also
+                        // streams from host memory, where a second read would cross PCIe again) keep theirs.
+                        constexpr bool kReload = G < 32;
+                        [[maybe_unused]] const uint32_t row_src = kReload ? __shfl_sync(0xffffffffu, rsrc, rl) : 0u;
                         if ((accmask >> rl) & 1u) {
                             if (p.host_ens) {  // host-buffer call: the accepted row goes back over PCIe now, while others still arrive
                                 double2 *hdst = reinterpret_cast<double2 *>(p.host_ens + (size_t)row * p.pitch);
@@ -468,6 +474,15 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
                                 for (int it = 0; it < ITERS; ++it) {
                                     const uint32_t c = (uint32_t)it * G + j;
                                     if (c < nvec) hdst[c] = yk[i][it];
+                                }
+                            }
+                        } else if constexpr (kReload) {
+                            if ((minemask >> rl) & 1u) {
+                                const double2 *srcp = reinterpret_cast<const double2 *>(p.src_ens + (size_t)row_src * p.pitch);
+#pragma unroll
+                                for (int it = 0; it < ITERS; ++it) {
+                                    const uint32_t c = (uint32_t)it * G + j;
+                                    yk[i][it] = ld_stream(srcp + (c < nvec ? c : nvec - 1u));
                                 }
                             }
                         } else {
