@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(reg_kernel_max_warps<Plugin, G, ITERS>() * 32,
         act = act_n;
         lp_old = lp_n;
         if constexpr (kPeer != 0) home = home_n;
+        if constexpr (kRemap) rsrc = rsrc_n;  // (blocks 1.. of the tile and the re-fetch of rejected rows read through it)
         if constexpr (kStageB) stage_phase ^= 1u;
     }
 
