@@ -7,7 +7,10 @@ later tiles (blocks after the first, the re-fetch of rejected rows) are found th
   moved right away (SCORUS_SWAP_FUSE=0: apply_swap_kernel, then the ordinary step);
 * host-buffer call on pinned buffers: the step that streams its rows from the caller's ensemble against upload +
   ordinary step + download.
-A B200 keeps 148 x 16..20 warps resident: 2^18 walkers are 8192 tiles, three per warp."""
+* the one-sided exchange step in a world of one rank (tests/test_peer_single_gpu.py has the small cases): the partner
+  stage's mbarrier phases and its refill run from tile to tile too.
+A B200 keeps 148 x 16..20 warps resident: 2^18 walkers are 8192 tiles, three per warp.  (The file sorts last on purpose:
+these are the largest cases of the suite.)"""
 import os
 
 import numpy as np
@@ -94,3 +97,29 @@ def test_host_call_that_streams_its_rows(sb, n, dim, nb):
             assert ref.stats()["accepted"] == host.stats()["accepted"] > 0
     finally:
         _env("SCORUS_HOST_STREAM", saved)
+
+
+@pytest.mark.parametrize("make,n,dim,nb,prob", [(lambda sb: sb.Rosenbrock(), 1 << 18, 64, 1, 0.5),
+                                                (lambda sb: sb.Rastrigin(), 1 << 18, 10, 4, 0.2)],
+                         ids=["rosenbrock64", "rastrigin10_pt"])
+def test_one_sided_exchange_step_over_several_tiles_per_warp(sb, make, n, dim, nb, prob):
+    rng = np.random.default_rng(11)
+    ens = np.ascontiguousarray(rng.uniform(0.4, 1.1, (n, dim)))
+    beta = 2.0 ** -np.arange(nb, dtype=np.float64)
+    ufs = sb.UpdateFlagSpec.Prob(prob)
+    with sb.Sampler(make(sb), n, dim, seed=17) as ref, sb.Sampler(make(sb), n, dim, seed=17) as one:
+        ref.upload(ens, None)
+        one.upload(ens, None)
+        he, hl = one.ipc_export()
+        one.ipc_attach(1, 0, [he], [hl])
+        for k in range(2):
+            if nb > 1:
+                ref.swap_walkers(beta)
+                one.swap_walkers_peer(beta)
+            ref.sample_pt(2.0, ufs, beta, 2)
+            one.sample_pt_peer(2.0, ufs, beta, 2)
+            e0, l0 = ref.download()
+            e1, l1 = one.download()
+            assert np.array_equal(e1, e0), f"positions differ after round {k}: {int(np.any(e1 != e0, axis=1).sum())} walkers"
+            assert np.allclose(l1, l0, rtol=1e-12, atol=1e-9, equal_nan=True)
+        assert ref.stats()["accepted"] == one.stats()["accepted"] > 0
